@@ -1,0 +1,207 @@
+/* gridpp_b200.h -- C ABI of the B200-native gridpp hot path (libgridpp_b200.so).
+ *
+ * This is the drop-in boundary. Every entry point states which reference interface (file:line under the
+ * metno/gridpp tree) it replaces. Signatures are plain C: pointers, sizes, PODs, integer status. No torch,
+ * no C++ types. The C++ `gridpp::` host layer (include/gridpp.h in this repo) and the Python mirror
+ * (gridpp_b200/) are thin callers of these functions.
+ *
+ * Conventions
+ *   - Return value: GPP_OK or an error code; gpp_last_error() returns the message of the last failure on the
+ *     calling thread. GPP_ERR_INVALID_ARGUMENT corresponds to the reference's std::invalid_argument,
+ *     everything else to std::runtime_error (swig/gridpp.i:21-40 maps them to ValueError / RuntimeError).
+ *   - `*_host` entry points take HOST buffers, do the host<->device copies themselves and synchronise
+ *     before returning (this is what the reference-facing API calls). `*_device` entry points take DEVICE
+ *     buffers of the current device, enqueue on `stream` (a cudaStream_t passed as void*; NULL = default
+ *     stream) and do not synchronise.
+ *   - All fields are dense row-major float32; missing value = NaN (gridpp.h:49); a value is "valid" when it
+ *     is neither NaN nor +-inf (util.cpp:16-18).
+ *   - There is NO CPU fallback: every compute entry point fails with GPP_ERR_CUDA when no device is usable.
+ */
+#ifndef GRIDPP_B200_H
+#define GRIDPP_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPP_OK 0
+#define GPP_ERR_INVALID_ARGUMENT 1
+#define GPP_ERR_RUNTIME 2
+#define GPP_ERR_NOT_IMPLEMENTED 3
+#define GPP_ERR_CUDA 4
+
+/* gridpp::CoordinateType, gridpp.h:120-123 (numeric values kept) */
+#define GPP_GEODETIC 0
+#define GPP_CARTESIAN 1
+
+/* gridpp::Statistic, gridpp.h:88-100 (numeric values kept; only the hot-path statistics run on the device) */
+#define GPP_MEAN 0
+#define GPP_MIN 10
+#define GPP_MAX 30
+#define GPP_SUM 70
+#define GPP_COUNT 80
+
+/* Structure-function families, src/api/structure.cpp */
+#define GPP_STRUCT_BARNES 0   /* structure.cpp:143-282 */
+#define GPP_STRUCT_CRESSMAN 1 /* structure.cpp:287-312 */
+#define GPP_STRUCT_SOAR 2     /* structure.cpp:317-460 */
+#define GPP_STRUCT_TOAR 3     /* structure.cpp:467-610 */
+#define GPP_STRUCT_POWERLAW 4 /* structure.cpp:618-757 */
+#define GPP_STRUCT_LINEAR 5   /* structure.cpp:765-904 */
+
+/* One non-spatial structure function: rho = rho_h(dist/h) * rho_v(delev/v) * rho_w(dlaf/w), zero beyond
+ * loc_dist. POD replacement for the virtual class gridpp::StructureFunction (gridpp.h:2069-2343). */
+typedef struct gpp_structure_term {
+    int type;       /* GPP_STRUCT_* */
+    float h, v, w;  /* length scales (Linear: minimum correlations) */
+    float min_rho;  /* truncation correlation (structure.cpp:5 default 0.0013) */
+    float loc_dist; /* localization_distance(), computed on the host exactly as the reference does */
+} gpp_structure_term;
+
+/* n_terms == 1: a plain structure function. n_terms == 3: gridpp::MultipleStructure(h, v, w)
+ * (structure.cpp:90-138): term[0] sees only the horizontal separation, term[1] only the elevation
+ * difference, term[2] only the land-area-fraction difference; localization comes from term[0].
+ * has_cv != 0: wrapped in gridpp::CrossValidation(structure, cv_dist) (structure.cpp:909-944): background
+ * correlations are zeroed for observations closer than cv_dist. */
+typedef struct gpp_structure {
+    int n_terms;
+    gpp_structure_term term[3];
+    int has_cv;
+    float cv_dist;
+} gpp_structure;
+
+/* ---------------------------------------------------------------- library ---------------------------- */
+const char* gpp_version(void);                 /* gridpp::version(), gridpp.cpp:8-10 */
+const char* gpp_last_error(void);              /* message of the last failing call on this thread */
+int gpp_device_count(int* count);              /* number of usable CUDA devices (0 is not an error) */
+int gpp_set_device(int device);                /* device used by subsequent calls of this thread */
+int gpp_device_synchronize(void);
+
+/* ---------------------------------------------------------------- structure functions ---------------- */
+/* BarnesStructure(h,v,w,hmax) structure.cpp:143-167, CressmanStructure :287-297, SoarStructure :317-340,
+ * ToarStructure :467-490, PowerlawStructure :618-641, LinearStructure :765-788. hmax = NaN -> default
+ * min_rho. Validation errors match the constructors (GPP_ERR_INVALID_ARGUMENT). */
+int gpp_structure_init(gpp_structure* out, int type, float h, float v, float w, float hmax);
+/* MultipleStructure(structure_h, structure_v, structure_w), structure.cpp:90-94. Each input must be a
+ * single-term structure. */
+int gpp_structure_multiple(gpp_structure* out, const gpp_structure* sh, const gpp_structure* sv, const gpp_structure* sw);
+/* CrossValidation(structure, dist), structure.cpp:909-915 */
+int gpp_structure_cross_validation(gpp_structure* out, const gpp_structure* in, float dist);
+/* StructureFunction::corr / corr_background between two points given as (x,y,z,elev,laf) and
+ * localization_distance(): evaluated ON THE DEVICE with the same code the OI kernels inline.
+ * p1 and p2 hold n points each as 5 floats (x, y, z, elev, laf); background != 0 -> corr_background. */
+int gpp_structure_corr_host(const gpp_structure* s, const float* p1, const float* p2, int n, int background, float* out);
+
+/* ---------------------------------------------------------------- points / grid index ---------------- */
+/* Replaces gridpp::Points (points.cpp:9-31) + gridpp::KDTree (kdtree.cpp:6-16); a gridpp::Grid is the same
+ * object over its Y*X flattened nodes (grid.cpp:12-55). Host arrays are copied; elevs/lafs may be NULL
+ * (filled with NaN, points.cpp:23-30). Coordinates are converted on the host with the reference's formula
+ * (util.cpp:583-615) so x/y/z match the reference bit for bit; invalid coordinates -> INVALID_ARGUMENT. */
+typedef struct gpp_points gpp_points;
+int gpp_points_create(const float* lats, const float* lons, const float* elevs, const float* lafs, int n,
+                      int coordinate_type, gpp_points** out);
+void gpp_points_destroy(gpp_points* p);
+int gpp_points_size(const gpp_points* p);
+int gpp_points_coordinate_type(const gpp_points* p);
+/* KDTree::get_x/get_y/get_z (kdtree.cpp:213-221): copies n floats each; any pointer may be NULL */
+int gpp_points_get_xyz(const gpp_points* p, float* x, float* y, float* z);
+
+/* KDTree::get_closest_neighbours(lat,lon,1) for nq query points at once (kdtree.cpp:82-106; the per-point
+ * loop of nearest.cpp:7-222). out_index[q] = index of the nearest point, -1 if none. Ties resolve to the
+ * lowest index (Boost leaves them unspecified). */
+int gpp_points_nearest_host(const gpp_points* p, const float* qlats, const float* qlons, int nq,
+                            int include_match, int* out_index);
+/* KDTree::get_neighbours / get_neighbours_with_distance / get_num_neighbours (kdtree.cpp:18-80) for nq
+ * query points: a point is returned when it lies STRICTLY inside the box [q-r, q+r]^3 and its straight-line
+ * distance is <= r (and > 0 unless include_match). Results for query q are written at
+ * out_index[q*capacity ...] in ascending point index, out_count[q] holds the TOTAL number of neighbours
+ * (which may exceed capacity; only the first `capacity` are stored). out_index/out_dist may be NULL with
+ * capacity 0 to only count. */
+int gpp_points_neighbours_host(const gpp_points* p, const float* qlats, const float* qlons, const float* radii,
+                               int nq, int include_match, int capacity, int* out_index, float* out_dist,
+                               int* out_count);
+/* KDTree::get_closest_neighbours(lat, lon, num) (kdtree.cpp:82-103) for nq query points; out_index is
+ * nq*num, padded with -1; sorted by (distance, index). */
+int gpp_points_closest_host(const gpp_points* p, const float* qlats, const float* qlons, int nq, int num,
+                            int include_match, int* out_index);
+
+/* gridpp::nearest(...) (nearest.cpp:7-222): for nq output points take the value of the nearest input point.
+ * ivalues is n_fields x n_in (row-major), out is n_fields x nq. An empty input set yields NaN. */
+int gpp_nearest_host(const gpp_points* ipoints, const float* qlats, const float* qlons, int nq,
+                     const float* ivalues, int n_fields, float* out);
+
+/* ---------------------------------------------------------------- optimal interpolation -------------- */
+/* Opaque, reusable observation-side state for OI: the cell index over the valid observations with their
+ * innovations and variance ratios resident on the device. */
+typedef struct gpp_oi_obs gpp_oi_obs;
+
+/* gridpp::optimal_interpolation_full(Points...) oi.cpp:138-341 (and, with bvariance = NULL,
+ * bvariance_at_points = NULL and obs_variance = the variance ratios, gridpp::optimal_interpolation(Points...)
+ * oi.cpp:89-136; the Grid overloads oi.cpp:26-87,342-412 flatten to this). All pointers are HOST memory.
+ *   bpoints            background points (a flattened grid), size nB
+ *   background[nB]     background field
+ *   bvariance[nB]      background variance or NULL (= 1)
+ *   opoints            observation points, size nS
+ *   pobs, obs_variance, pbackground [nS]; bvariance_at_points [nS] or NULL (= 1)
+ *   max_points         0 = unlimited
+ *   analysis[nB]       output; analysis_variance[nB] output or NULL
+ * Argument checks and their order follow oi.cpp:151-186. */
+int gpp_optimal_interpolation_host(const gpp_points* bpoints, const float* background, const float* bvariance,
+                                   const gpp_points* opoints, const float* pobs, const float* obs_variance,
+                                   const float* pbackground, const float* bvariance_at_points,
+                                   const gpp_structure* structure, int max_points, int allow_extrapolation,
+                                   float* analysis, float* analysis_variance);
+
+/* Device-resident form of the same call, split so that the observation side is prepared once and the
+ * (row-sharded) background side streams through: build the observation state from HOST observation arrays,
+ * then analyse background points [first, first+count) of `bpoints` reading d_background[first...] and writing
+ * d_analysis[first...] (device pointers indexed like the full field). d_bvariance / d_analysis_variance may
+ * be NULL. */
+int gpp_oi_obs_create(const gpp_points* opoints, const float* pobs, const float* obs_variance,
+                      const float* pbackground, const float* bvariance_at_points, const gpp_structure* structure,
+                      gpp_oi_obs** out);
+void gpp_oi_obs_destroy(gpp_oi_obs* obs);
+int gpp_optimal_interpolation_device(const gpp_points* bpoints, int first, int count, const float* d_background,
+                                     const float* d_bvariance, const gpp_oi_obs* obs,
+                                     const gpp_structure* structure, int max_points, int allow_extrapolation,
+                                     float* d_analysis, float* d_analysis_variance, void* stream);
+
+/* gridpp::optimal_interpolation_ensi(Points...) oi_ensi.cpp:114-568 (the Grid overload :33-112 flattens to
+ * this). background and analysis are nB x nE (member fastest), pbackground is nS x nE. HOST memory. */
+int gpp_optimal_interpolation_ensi_host(const gpp_points* bpoints, const float* background, int nE,
+                                        const gpp_points* opoints, const float* pobs, const float* psigmas,
+                                        const float* pbackground, const gpp_structure* structure, int max_points,
+                                        int allow_extrapolation, float* analysis, int* num_skipped);
+
+/* ---------------------------------------------------------------- neighbourhood filters -------------- */
+/* gridpp::neighbourhood(vec2, halfwidth, statistic) neighbourhood.cpp:28-242 for statistic in
+ * {Mean, Sum, Count, Min, Max}: NaN-aware statistic over the (2*halfwidth+1)^2 window CLIPPED to the domain
+ * (neighbourhood.cpp:104-107,160-167); a window without valid values gives NaN (Count gives 0). */
+int gpp_neighbourhood_host(const float* input, int ny, int nx, int halfwidth, int statistic, float* output);
+/* Device form with explicit row window, for row-tiled multi-GPU use: d_input holds n_rows_in rows (a tile
+ * plus whatever halo rows exist; the domain is taken to be exactly these rows), output rows
+ * [row0, row0 + n_rows_out) are written to d_output[0 .. n_rows_out*nx). */
+int gpp_neighbourhood_device(const float* d_input, int n_rows_in, int nx, int row0, int n_rows_out,
+                             int halfwidth, int statistic, float* d_output, void* stream);
+
+/* gridpp::neighbourhood_quantile_fast(vec2, quantile | vec2 quantile, halfwidth, thresholds)
+ * neighbourhood.cpp:296-409. quantile_field (ny x nx) may be NULL, then `quantile` applies everywhere.
+ * thresholds is a HOST array in both forms. */
+int gpp_neighbourhood_quantile_fast_host(const float* input, int ny, int nx, float quantile,
+                                         const float* quantile_field, int halfwidth, const float* thresholds,
+                                         int num_thresholds, float* output);
+int gpp_neighbourhood_quantile_fast_device(const float* d_input, int n_rows_in, int nx, int row0, int n_rows_out,
+                                           float quantile, const float* d_quantile_field, int halfwidth,
+                                           const float* thresholds, int num_thresholds, float* d_output,
+                                           void* stream);
+
+/* ---------------------------------------------------------------- instrumentation -------------------- */
+/* Number of kernels this library has launched on the calling process so far (bench.py's gpu_launches). */
+unsigned long long gpp_kernel_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,332 @@
+"""ctypes bindings for the two CPU checkers in this directory.
+
+TEST INFRASTRUCTURE ONLY -- importable from tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+``--impl reference`` leg, never from the product package (gridpp_b200/).
+
+  * ``load("ref")``    -> oracle/_ref/libgridpp_ref.so     the unmodified reference sources (prefix ``ref_``)
+  * ``load("oracle")`` -> oracle/_ref/libgridpp_oracle.so  the plain-C restatement (prefix ``orc_``)
+
+Both export the same flat functions (see oracle/ref_capi.cpp for the reference-side definitions and the
+reference file:line each one wraps), so one binder serves both.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+GEODETIC, CARTESIAN = 0, 1
+MEAN, MIN, MAX, SUM, COUNT = 0, 10, 30, 70, 80
+BARNES, CRESSMAN, SOAR, TOAR, POWERLAW, LINEAR = range(6)
+
+
+class StructureTerm(C.Structure):
+    _fields_ = [("type", C.c_int), ("h", C.c_float), ("v", C.c_float), ("w", C.c_float),
+                ("min_rho", C.c_float), ("loc_dist", C.c_float)]
+
+
+class Structure(C.Structure):
+    """Mirror of gpp_structure (include/gridpp_b200.h)."""
+    _fields_ = [("n_terms", C.c_int), ("term", StructureTerm * 3), ("has_cv", C.c_int), ("cv_dist", C.c_float)]
+
+
+_fp = C.POINTER(C.c_float)
+_ip = C.POINTER(C.c_int)
+_dp = C.POINTER(C.c_double)
+
+
+def _f(a, shape=None):
+    """float32 C-contiguous copy (or None)."""
+    if a is None:
+        return None
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    if shape is not None:
+        assert a.shape == tuple(shape), (a.shape, shape)
+    return a
+
+
+def _p(a):
+    if a is None:
+        return None
+    if a.dtype == np.float32:
+        return a.ctypes.data_as(_fp)
+    if a.dtype == np.int32:
+        return a.ctypes.data_as(_ip)
+    raise TypeError(a.dtype)
+
+
+class CpuLib:
+    def __init__(self, path, prefix):
+        self.path = path
+        self.prefix = prefix
+        self.lib = C.CDLL(path)
+        self._fn("last_error").restype = C.c_char_p
+        self._fn("calc_distance").restype = C.c_float
+        self._fn("calc_distance").argtypes = [C.c_float] * 4 + [C.c_int]
+
+    def _fn(self, name):
+        return getattr(self.lib, self.prefix + name)
+
+    def _check(self, rc):
+        if rc != 0:
+            msg = self._fn("last_error")().decode()
+            raise (ValueError if rc == 1 else RuntimeError)(msg)
+
+    # ---- threads
+    def set_omp_threads(self, n):
+        self._fn("set_omp_threads")(C.c_int(n))
+
+    def get_omp_threads(self):
+        return self._fn("get_omp_threads")()
+
+    # ---- coordinates / structure
+    def convert_coordinates(self, lats, lons, ctype):
+        lats, lons = _f(lats).ravel(), _f(lons).ravel()
+        n = lats.size
+        x, y, z = (np.empty(n, np.float32) for _ in range(3))
+        self._check(self._fn("convert_coordinates")(_p(lats), _p(lons), n, ctype, _p(x), _p(y), _p(z)))
+        return x, y, z
+
+    def structure_describe(self, stype, h, v=0.0, w=0.0, hmax=float("nan")):
+        """localization distance of <Type>Structure(h, v, w, hmax) for a point"""
+        out = C.c_float()
+        self._check(self._fn("structure_describe")(stype, C.c_float(h), C.c_float(v), C.c_float(w), C.c_float(hmax),
+                                                   C.byref(out)))
+        return out.value
+
+    def structure_corr(self, s, p1, p2, background=False):
+        p1, p2 = _f(p1).reshape(-1, 5), _f(p2).reshape(-1, 5)
+        n = p1.shape[0]
+        out = np.empty(n, np.float32)
+        self._check(self._fn("structure_corr")(C.byref(s), _p(p1), _p(p2), n, int(background), _p(out)))
+        return out
+
+    def structure_localization_distance(self, s):
+        out = C.c_float()
+        self._check(self._fn("structure_localization_distance")(C.byref(s), C.byref(out)))
+        return out.value
+
+    # ---- index queries
+    def points_nearest(self, lats, lons, ctype, qlats, qlons, include_match=True, timing=None):
+        lats, lons, qlats, qlons = _f(lats).ravel(), _f(lons).ravel(), _f(qlats).ravel(), _f(qlons).ravel()
+        out = np.empty(qlats.size, np.int32)
+        sec = C.c_double()
+        self._check(self._fn("points_nearest")(_p(lats), _p(lons), lats.size, ctype, _p(qlats), _p(qlons), qlats.size,
+                                               int(include_match), _p(out), C.byref(sec)))
+        if timing is not None:
+            timing.append(sec.value)
+        return out
+
+    def points_neighbours(self, lats, lons, ctype, qlats, qlons, radii, include_match=True, capacity=64):
+        lats, lons, qlats, qlons = _f(lats).ravel(), _f(lons).ravel(), _f(qlats).ravel(), _f(qlons).ravel()
+        nq = qlats.size
+        radii = _f(np.broadcast_to(np.asarray(radii, np.float32), (nq,)))
+        idx = np.full((nq, capacity), -1, np.int32)
+        dist = np.full((nq, capacity), np.nan, np.float32)
+        cnt = np.zeros(nq, np.int32)
+        self._check(self._fn("points_neighbours")(_p(lats), _p(lons), lats.size, ctype, _p(qlats), _p(qlons), _p(radii),
+                                                  nq, int(include_match), capacity, _p(idx), _p(dist), _p(cnt)))
+        return idx, dist, cnt
+
+    def points_neighbours_raw(self, lats, lons, ctype, qlat, qlon, radius, include_match=True, capacity=64):
+        lats, lons = _f(lats).ravel(), _f(lons).ravel()
+        idx = np.full(capacity, -1, np.int32)
+        cnt = C.c_int()
+        self._check(self._fn("points_neighbours_raw")(_p(lats), _p(lons), lats.size, ctype, C.c_float(qlat),
+                                                      C.c_float(qlon), C.c_float(radius), int(include_match), capacity,
+                                                      _p(idx), C.byref(cnt)))
+        return idx[:min(cnt.value, capacity)]
+
+    def points_closest(self, lats, lons, ctype, qlats, qlons, num, include_match=True):
+        lats, lons, qlats, qlons = _f(lats).ravel(), _f(lons).ravel(), _f(qlats).ravel(), _f(qlons).ravel()
+        out = np.empty((qlats.size, num), np.int32)
+        self._check(self._fn("points_closest")(_p(lats), _p(lons), lats.size, ctype, _p(qlats), _p(qlons), qlats.size, num,
+                                               int(include_match), _p(out)))
+        return out
+
+    def calc_distance(self, lat1, lon1, lat2, lon2, ctype):
+        return self._fn("calc_distance")(lat1, lon1, lat2, lon2, ctype)
+
+    def nearest(self, ilats, ilons, ctype, qlats, qlons, ivalues, timing=None):
+        ilats, ilons, qlats, qlons = _f(ilats).ravel(), _f(ilons).ravel(), _f(qlats).ravel(), _f(qlons).ravel()
+        iv = _f(ivalues)
+        single = iv.ndim == 1
+        iv2 = iv.reshape(1, -1) if single else iv
+        assert iv2.shape[1] == ilats.size
+        out = np.empty((iv2.shape[0], qlats.size), np.float32)
+        sec = C.c_double()
+        self._check(self._fn("nearest")(_p(ilats), _p(ilons), ilats.size, ctype, _p(qlats), _p(qlons), qlats.size,
+                                        _p(iv2), iv2.shape[0], _p(out), C.byref(sec)))
+        if timing is not None:
+            timing.append(sec.value)
+        return out[0] if single else out
+
+    # ---- OI
+    def optimal_interpolation(self, bpts, background, opts, pobs, obs_variance, pbackground, structure, max_points,
+                              ctype, bvariance=None, bvariance_at_points=None, allow_extrapolation=True,
+                              want_variance=False, timing=None):
+        """bpts / opts: tuples (lats, lons, elevs|None, lafs|None), flattened."""
+        bl, bo, be, bf = (_f(a).ravel() if a is not None else None for a in bpts)
+        pl, po, pe, pf = (_f(a).ravel() if a is not None else None for a in opts)
+        nB, nS = bl.size, pl.size
+        bg = _f(background).ravel()
+        bvar = _f(bvariance).ravel() if bvariance is not None else None
+        obs, ovar, pbg = _f(pobs).ravel(), _f(obs_variance).ravel(), _f(pbackground).ravel()
+        pbvar = _f(bvariance_at_points).ravel() if bvariance_at_points is not None else None
+        assert bg.size == nB and obs.size == nS and ovar.size == nS and pbg.size == nS
+        out = np.empty(nB, np.float32)
+        var = np.empty(nB, np.float32)
+        sec = C.c_double()
+        self._check(self._fn("optimal_interpolation")(
+            _p(bl), _p(bo), _p(be), _p(bf), nB, _p(bg), _p(bvar), _p(pl), _p(po), _p(pe), _p(pf), nS, ctype, _p(obs),
+            _p(ovar), _p(pbg), _p(pbvar), C.byref(structure), max_points, int(allow_extrapolation), _p(out), _p(var),
+            C.byref(sec)))
+        if timing is not None:
+            timing.append(sec.value)
+        return (out, var) if want_variance else out
+
+    def optimal_interpolation_ensi(self, bpts, background, opts, pobs, psigmas, pbackground, structure, max_points, ctype,
+                                   allow_extrapolation=True, timing=None):
+        bl, bo, be, bf = (_f(a).ravel() if a is not None else None for a in bpts)
+        pl, po, pe, pf = (_f(a).ravel() if a is not None else None for a in opts)
+        nB, nS = bl.size, pl.size
+        bg = _f(background).reshape(nB, -1)
+        nE = bg.shape[1]
+        pbg = _f(pbackground).reshape(nS, nE)
+        obs, sig = _f(pobs).ravel(), _f(psigmas).ravel()
+        out = np.empty((nB, nE), np.float32)
+        sec = C.c_double()
+        self._check(self._fn("optimal_interpolation_ensi")(
+            _p(bl), _p(bo), _p(be), _p(bf), nB, _p(bg), nE, _p(pl), _p(po), _p(pe), _p(pf), nS, ctype, _p(obs), _p(sig),
+            _p(pbg), C.byref(structure), max_points, int(allow_extrapolation), _p(out), C.byref(sec)))
+        if timing is not None:
+            timing.append(sec.value)
+        return out
+
+    # ---- neighbourhood
+    def neighbourhood(self, field, halfwidth, statistic, timing=None):
+        f = _f(field)
+        ny, nx = f.shape
+        out = np.full((ny, nx), np.nan, np.float32)
+        sec = C.c_double()
+        self._check(self._fn("neighbourhood")(_p(f), ny, nx, halfwidth, statistic, _p(out), C.byref(sec)))
+        if timing is not None:
+            timing.append(sec.value)
+        return out
+
+    def neighbourhood_brute_force(self, field, halfwidth, statistic):
+        f = _f(field)
+        ny, nx = f.shape
+        out = np.full((ny, nx), np.nan, np.float32)
+        self._check(self._fn("neighbourhood_brute_force")(_p(f), ny, nx, halfwidth, statistic, _p(out)))
+        return out
+
+    def neighbourhood_quantile_fast(self, field, quantile, halfwidth, thresholds, timing=None):
+        f = _f(field)
+        ny, nx = f.shape
+        thr = _f(thresholds).ravel()
+        qf = None
+        q = float("nan")
+        if np.ndim(quantile) == 0:
+            q = float(quantile)
+        else:
+            qf = _f(quantile, (ny, nx))
+        out = np.full((ny, nx), np.nan, np.float32)
+        sec = C.c_double()
+        self._check(self._fn("neighbourhood_quantile_fast")(_p(f), ny, nx, C.c_float(q), _p(qf), halfwidth, _p(thr),
+                                                            thr.size, _p(out), C.byref(sec)))
+        if timing is not None:
+            timing.append(sec.value)
+        return out
+
+    def get_neighbourhood_thresholds(self, field, num):
+        f = _f(field)
+        ny, nx = f.shape
+        out = np.empty(max(num, 1), np.float32)
+        n = C.c_int()
+        self._check(self._fn("get_neighbourhood_thresholds")(_p(f), ny, nx, num, _p(out), C.byref(n)))
+        return out[:n.value].copy()
+
+    def interpolate(self, x, ix, iy):
+        ix, iy = _f(ix).ravel(), _f(iy).ravel()
+        out = C.c_float()
+        self._check(self._fn("interpolate")(C.c_float(x), _p(ix), _p(iy), ix.size, C.byref(out)))
+        return out.value
+
+    def calc_statistic(self, a, statistic):
+        a = _f(a).ravel()
+        out = C.c_float()
+        self._check(self._fn("calc_statistic")(_p(a), a.size, statistic, C.byref(out)))
+        return out.value
+
+    def calc_quantile(self, a, q):
+        a = _f(a).ravel()
+        out = C.c_float()
+        self._check(self._fn("calc_quantile")(_p(a), a.size, C.c_float(q), C.byref(out)))
+        return out.value
+
+
+_PATHS = {"ref": ("libgridpp_ref.so", "ref_"), "oracle": ("libgridpp_oracle.so", "orc_")}
+_cache = {}
+
+
+def available(kind):
+    return os.path.exists(os.path.join(HERE, "_ref", _PATHS[kind][0]))
+
+
+def load(kind):
+    """kind: "ref" (compiled reference) or "oracle" (C restatement)."""
+    if kind not in _cache:
+        fname, prefix = _PATHS[kind]
+        path = os.path.join(HERE, "_ref", fname)
+        if not os.path.exists(path):
+            raise FileNotFoundError(path + " (run `make -C oracle`)")
+        _cache[kind] = CpuLib(path, prefix)
+    return _cache[kind]
+
+
+def make_structure(stype=BARNES, h=0.0, v=0.0, w=0.0, hmax=float("nan"), min_rho=None):
+    """Single-term descriptor. min_rho follows the reference constructors (structure.cpp:143-167, :317-340,
+    :467-490, :618-641, :765-788); loc_dist is left 0 -- both CPU checkers recompute it themselves."""
+    s = Structure()
+    s.n_terms = 1
+    t = s.term[0]
+    t.type, t.h, t.v, t.w = stype, h, v, w
+    if min_rho is None:
+        f32 = np.float32
+        min_rho = f32(0.0013)
+        if not np.isnan(hmax):
+            r = np.float64(f32(hmax) / f32(h))
+            if stype == BARNES:
+                min_rho = f32(np.exp(r ** 2 / -2))
+            elif stype == SOAR:
+                min_rho = f32((1 + f32(hmax) / f32(h)) * f32(np.exp(-(f32(hmax) / f32(h)))))
+            elif stype == TOAR:
+                min_rho = f32((1 + r + r ** 2 / 3) * np.exp(-r))
+            elif stype == POWERLAW:
+                min_rho = f32(1 / (1 + 0.5 * r ** 2))
+    t.min_rho = float(min_rho)
+    t.loc_dist = 0.0
+    s.has_cv = 0
+    s.cv_dist = float("nan")
+    return s
+
+
+def multiple_structure(sh, sv, sw):
+    s = Structure()
+    s.n_terms = 3
+    for i, src in enumerate((sh, sv, sw)):
+        for name, _ in StructureTerm._fields_:
+            setattr(s.term[i], name, getattr(src.term[0], name))
+    s.has_cv = 0
+    s.cv_dist = float("nan")
+    return s
+
+
+def cross_validation(base, dist):
+    s = Structure()
+    C.memmove(C.byref(s), C.byref(base), C.sizeof(Structure))
+    s.has_cv = 1
+    s.cv_dist = dist
+    return s

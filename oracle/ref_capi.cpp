@@ -1,0 +1,321 @@
+// Flat C entry points over the UNMODIFIED reference (metno/gridpp src/api/*.cpp compiled from
+// /root/reference by oracle/Makefile into oracle/_ref/libgridpp_ref.so).
+//
+// TEST INFRASTRUCTURE ONLY: used by tests/ (to pin oracle/gridpp_oracle.c and to check the CUDA path), by
+// tests/golden/make_golden.py (to generate the committed fixtures) and by bench.py's cpu_baseline /
+// --impl reference leg. The product never links or loads this.
+//
+// Every function returns 0 on success, 1 for std::invalid_argument, 2 for any other exception; the message is
+// available from ref_last_error(). Functions that time the reference call (only the gridpp:: call itself, not
+// the construction of Points/Grid or the vector<vector<>> marshalling) return the seconds in *seconds.
+#include "gridpp.h"
+#include "gridpp_b200.h"
+
+#include <chrono>
+#include <cstring>
+#include <memory>
+#include <string>
+
+namespace {
+thread_local std::string g_error;
+
+typedef std::chrono::steady_clock clk;
+double since(clk::time_point t0) { return std::chrono::duration<double>(clk::now() - t0).count(); }
+
+gridpp::vec to_vec(const float* p, int n) { return p ? gridpp::vec(p, p + n) : gridpp::vec(); }
+gridpp::vec2 to_vec2(const float* p, int ny, int nx) {
+    gridpp::vec2 v(ny);
+    for(int y = 0; y < ny; y++) v[y].assign(p + (size_t) y * nx, p + (size_t) (y + 1) * nx);
+    return v;
+}
+void from_vec2(const gridpp::vec2& v, float* out, int ny, int nx) {
+    for(int y = 0; y < ny; y++) std::memcpy(out + (size_t) y * nx, v[y].data(), sizeof(float) * nx);
+}
+gridpp::Points make_points(const float* lats, const float* lons, const float* elevs, const float* lafs, int n, int type) {
+    return gridpp::Points(to_vec(lats, n), to_vec(lons, n), to_vec(elevs, n), to_vec(lafs, n), (gridpp::CoordinateType) type);
+}
+
+gridpp::StructureFunctionPtr make_term(const gpp_structure_term& t) {
+    // hmax is encoded through min_rho: the spatial constructors take min_rho directly and collapse to the
+    // non-spatial case for 1x1 scale arrays (structure.cpp:168-184), which is also what clone() does.
+    gridpp::vec2 h(1, gridpp::vec(1, t.h)), v(1, gridpp::vec(1, t.v)), w(1, gridpp::vec(1, t.w));
+    gridpp::Grid g;
+    switch(t.type) {
+        case GPP_STRUCT_BARNES: return std::make_shared<gridpp::BarnesStructure>(g, h, v, w, t.min_rho);
+        case GPP_STRUCT_CRESSMAN: return std::make_shared<gridpp::CressmanStructure>(t.h, t.v, t.w);
+        case GPP_STRUCT_SOAR: return std::make_shared<gridpp::SoarStructure>(g, h, v, w, t.min_rho);
+        case GPP_STRUCT_TOAR: return std::make_shared<gridpp::ToarStructure>(g, h, v, w, t.min_rho);
+        case GPP_STRUCT_POWERLAW: return std::make_shared<gridpp::PowerlawStructure>(g, h, v, w, t.min_rho);
+        case GPP_STRUCT_LINEAR: return std::make_shared<gridpp::LinearStructure>(g, h, v, w, t.min_rho);
+    }
+    throw std::invalid_argument("unknown structure type");
+}
+gridpp::StructureFunctionPtr make_structure(const gpp_structure* s) {
+    gridpp::StructureFunctionPtr base;
+    if(s->n_terms == 3) {
+        gridpp::StructureFunctionPtr a = make_term(s->term[0]), b = make_term(s->term[1]), c = make_term(s->term[2]);
+        base = std::make_shared<gridpp::MultipleStructure>(*a, *b, *c);
+    }
+    else
+        base = make_term(s->term[0]);
+    if(s->has_cv) return std::make_shared<gridpp::CrossValidation>(*base, s->cv_dist);
+    return base;
+}
+}  // namespace
+
+#define REF_TRY try {
+#define REF_CATCH                                                        \
+    }                                                                    \
+    catch(const std::invalid_argument& e) { g_error = e.what(); return 1; } \
+    catch(const std::exception& e) { g_error = e.what(); return 2; }     \
+    catch(...) { g_error = "unknown exception"; return 2; }              \
+    return 0;
+
+extern "C" {
+
+const char* ref_last_error() { return g_error.c_str(); }
+const char* ref_version() { static std::string v = gridpp::version(); return v.c_str(); }
+void ref_set_omp_threads(int n) { gridpp::set_omp_threads(n); }
+int ref_get_omp_threads() { return gridpp::get_omp_threads(); }
+
+// gridpp::convert_coordinates, util.cpp:583-615
+int ref_convert_coordinates(const float* lats, const float* lons, int n, int type, float* x, float* y, float* z) {
+    REF_TRY
+    for(int i = 0; i < n; i++) gridpp::convert_coordinates(lats[i], lons[i], (gridpp::CoordinateType) type, x[i], y[i], z[i]);
+    REF_CATCH
+}
+
+// Structure function constructors with hmax (structure.cpp:143-167 etc.): fills min_rho/loc_dist of a
+// descriptor from the reference object, so the product's host-side formulas can be checked against it.
+int ref_structure_describe(int type, float h, float v, float w, float hmax, float* loc_dist) {
+    REF_TRY
+    gridpp::StructureFunctionPtr s;
+    switch(type) {
+        case GPP_STRUCT_BARNES: s = std::make_shared<gridpp::BarnesStructure>(h, v, w, hmax); break;
+        case GPP_STRUCT_CRESSMAN: s = std::make_shared<gridpp::CressmanStructure>(h, v, w); break;
+        case GPP_STRUCT_SOAR: s = std::make_shared<gridpp::SoarStructure>(h, v, w, hmax); break;
+        case GPP_STRUCT_TOAR: s = std::make_shared<gridpp::ToarStructure>(h, v, w, hmax); break;
+        case GPP_STRUCT_POWERLAW: s = std::make_shared<gridpp::PowerlawStructure>(h, v, w, hmax); break;
+        case GPP_STRUCT_LINEAR: s = std::make_shared<gridpp::LinearStructure>(h, v, w, hmax); break;
+        default: throw std::invalid_argument("unknown structure type");
+    }
+    *loc_dist = s->localization_distance(gridpp::Point(0, 0, 0, 0, gridpp::Cartesian));
+    REF_CATCH
+}
+
+// StructureFunction::corr / corr_background for n point pairs given as (x,y,z,elev,laf)
+int ref_structure_corr(const gpp_structure* sd, const float* p1, const float* p2, int n, int background, float* out) {
+    REF_TRY
+    gridpp::StructureFunctionPtr s = make_structure(sd);
+    for(int i = 0; i < n; i++) {
+        const float* a = p1 + 5 * i;
+        const float* b = p2 + 5 * i;
+        gridpp::Point q1(a[1], a[0], a[3], a[4], gridpp::Cartesian, a[0], a[1], a[2]);
+        gridpp::Point q2(b[1], b[0], b[3], b[4], gridpp::Cartesian, b[0], b[1], b[2]);
+        out[i] = background ? s->corr_background(q1, q2) : s->corr(q1, q2);
+    }
+    REF_CATCH
+}
+int ref_structure_localization_distance(const gpp_structure* sd, float* out) {
+    REF_TRY
+    *out = make_structure(sd)->localization_distance(gridpp::Point(0, 0, 0, 0, gridpp::Cartesian));
+    REF_CATCH
+}
+
+// ---- KDTree queries (kdtree.cpp:18-106) --------------------------------------------------------------
+int ref_points_nearest(const float* lats, const float* lons, int n, int type, const float* qlats, const float* qlons,
+                       int nq, int include_match, int* out_index, double* seconds) {
+    REF_TRY
+    gridpp::Points p = make_points(lats, lons, NULL, NULL, n, type);
+    if(n > 0) p.get_nearest_neighbour(qlats[0], qlons[0]);   // build the index outside the timed region
+    clk::time_point t0 = clk::now();
+    #pragma omp parallel for
+    for(int q = 0; q < nq; q++) out_index[q] = p.get_nearest_neighbour(qlats[q], qlons[q], include_match);
+    if(seconds) *seconds = since(t0);
+    REF_CATCH
+}
+int ref_points_neighbours(const float* lats, const float* lons, int n, int type, const float* qlats, const float* qlons,
+                          const float* radii, int nq, int include_match, int capacity, int* out_index, float* out_dist,
+                          int* out_count) {
+    REF_TRY
+    gridpp::Points p = make_points(lats, lons, NULL, NULL, n, type);
+    for(int q = 0; q < nq; q++) {
+        gridpp::vec dist;
+        gridpp::ivec I = p.get_neighbours_with_distance(qlats[q], qlons[q], radii[q], dist, include_match);
+        out_count[q] = I.size();
+        // canonical order for comparison: ascending index
+        std::vector<std::pair<int, float> > pairs(I.size());
+        for(size_t i = 0; i < I.size(); i++) pairs[i] = std::make_pair(I[i], dist[i]);
+        std::sort(pairs.begin(), pairs.end());
+        for(int i = 0; i < (int) pairs.size() && i < capacity; i++) {
+            if(out_index) out_index[(size_t) q * capacity + i] = pairs[i].first;
+            if(out_dist) out_dist[(size_t) q * capacity + i] = pairs[i].second;
+        }
+    }
+    REF_CATCH
+}
+// raw (unsorted) order of a single query, to check the small-tree insertion-order contract
+int ref_points_neighbours_raw(const float* lats, const float* lons, int n, int type, float qlat, float qlon, float radius,
+                              int include_match, int capacity, int* out_index, int* out_count) {
+    REF_TRY
+    gridpp::Points p = make_points(lats, lons, NULL, NULL, n, type);
+    gridpp::ivec I = p.get_neighbours(qlat, qlon, radius, include_match);
+    *out_count = I.size();
+    for(int i = 0; i < (int) I.size() && i < capacity; i++) out_index[i] = I[i];
+    REF_CATCH
+}
+int ref_points_closest(const float* lats, const float* lons, int n, int type, const float* qlats, const float* qlons, int nq,
+                       int num, int include_match, int* out_index) {
+    REF_TRY
+    gridpp::Points p = make_points(lats, lons, NULL, NULL, n, type);
+    for(int q = 0; q < nq; q++) {
+        gridpp::ivec I = p.get_closest_neighbours(qlats[q], qlons[q], num, include_match);
+        for(int i = 0; i < num; i++) out_index[(size_t) q * num + i] = i < (int) I.size() ? I[i] : -1;
+    }
+    REF_CATCH
+}
+float ref_calc_distance(float lat1, float lon1, float lat2, float lon2, int type) {
+    return gridpp::KDTree::calc_distance(lat1, lon1, lat2, lon2, (gridpp::CoordinateType) type);
+}
+
+// gridpp::nearest(Grid, Points, vec2) nearest.cpp:124-144 and (Points, Points, vec) :177-197 share the per-point
+// lookup; the Grid index arithmetic (grid.cpp:108-114) is flat = y*nx + x, so a flattened field is equivalent.
+int ref_nearest(const float* ilats, const float* ilons, int n_in, int type, const float* qlats, const float* qlons, int nq,
+                const float* ivalues, int n_fields, float* out, double* seconds) {
+    REF_TRY
+    gridpp::Points ip = make_points(ilats, ilons, NULL, NULL, n_in, type);
+    gridpp::Points op = make_points(qlats, qlons, NULL, NULL, nq, type);
+    if(n_in > 0 && nq > 0) ip.get_nearest_neighbour(qlats[0], qlons[0]);
+    double total = 0;
+    if(n_fields == 1) {
+        gridpp::vec iv = to_vec(ivalues, n_in);
+        clk::time_point t0 = clk::now();
+        gridpp::vec o = gridpp::nearest(ip, op, iv);
+        total = since(t0);
+        std::memcpy(out, o.data(), sizeof(float) * nq);
+    }
+    else {
+        gridpp::vec2 iv = to_vec2(ivalues, n_fields, n_in);
+        clk::time_point t0 = clk::now();
+        gridpp::vec2 o = gridpp::nearest(ip, op, iv);
+        total = since(t0);
+        from_vec2(o, out, n_fields, nq);
+    }
+    if(seconds) *seconds = total;
+    REF_CATCH
+}
+
+// ---- optimal interpolation ----------------------------------------------------------------------------
+// gridpp::optimal_interpolation_full(Points...) oi.cpp:138-341. bvariance / bvariance_at_points NULL = 1.
+int ref_optimal_interpolation(const float* blats, const float* blons, const float* belevs, const float* blafs, int nB,
+                              const float* background, const float* bvariance, const float* plats, const float* plons,
+                              const float* pelevs, const float* plafs, int nS, int type, const float* pobs,
+                              const float* obs_variance, const float* pbackground, const float* bvariance_at_points,
+                              const gpp_structure* sd, int max_points, int allow_extrapolation, float* analysis,
+                              float* analysis_variance, double* seconds) {
+    REF_TRY
+    gridpp::Points bp = make_points(blats, blons, belevs, blafs, nB, type);
+    gridpp::Points op = make_points(plats, plons, pelevs, plafs, nS, type);
+    gridpp::StructureFunctionPtr s = make_structure(sd);
+    gridpp::vec bg = to_vec(background, nB), bvar = bvariance ? to_vec(bvariance, nB) : gridpp::vec(nB, 1.0f);
+    gridpp::vec obs = to_vec(pobs, nS), ovar = to_vec(obs_variance, nS), pbg = to_vec(pbackground, nS);
+    gridpp::vec pbvar = bvariance_at_points ? to_vec(bvariance_at_points, nS) : gridpp::vec(nS, 1.0f);
+    if(nS > 0) op.get_neighbours(plats[0], plons[0], 1.0f);   // build the observation index outside the timed region
+    gridpp::vec avar;
+    clk::time_point t0 = clk::now();
+    gridpp::vec out = gridpp::optimal_interpolation_full(bp, bg, bvar, op, obs, ovar, pbg, pbvar, *s, max_points, avar,
+                                                         allow_extrapolation != 0);
+    if(seconds) *seconds = since(t0);
+    std::memcpy(analysis, out.data(), sizeof(float) * out.size());
+    if(analysis_variance && avar.size() == (size_t) nB) std::memcpy(analysis_variance, avar.data(), sizeof(float) * nB);
+    else if(analysis_variance) std::memcpy(analysis_variance, bvar.data(), sizeof(float) * nB);
+    REF_CATCH
+}
+
+// gridpp::optimal_interpolation_ensi(Points...) oi_ensi.cpp:114-568. background is nB x nE, pbackground nS x nE.
+int ref_optimal_interpolation_ensi(const float* blats, const float* blons, const float* belevs, const float* blafs, int nB,
+                                   const float* background, int nE, const float* plats, const float* plons,
+                                   const float* pelevs, const float* plafs, int nS, int type, const float* pobs,
+                                   const float* psigmas, const float* pbackground, const gpp_structure* sd, int max_points,
+                                   int allow_extrapolation, float* analysis, double* seconds) {
+    REF_TRY
+    gridpp::Points bp = make_points(blats, blons, belevs, blafs, nB, type);
+    gridpp::Points op = make_points(plats, plons, pelevs, plafs, nS, type);
+    gridpp::StructureFunctionPtr s = make_structure(sd);
+    gridpp::vec2 bg = to_vec2(background, nB, nE);
+    gridpp::vec2 pbg = to_vec2(pbackground, nS, nE);
+    gridpp::vec obs = to_vec(pobs, nS), sig = to_vec(psigmas, nS);
+    if(nS > 0) op.get_neighbours(plats[0], plons[0], 1.0f);
+    clk::time_point t0 = clk::now();
+    gridpp::vec2 out = gridpp::optimal_interpolation_ensi(bp, bg, op, obs, sig, pbg, *s, max_points, allow_extrapolation != 0);
+    if(seconds) *seconds = since(t0);
+    from_vec2(out, analysis, nB, nE);
+    REF_CATCH
+}
+
+// ---- neighbourhood ------------------------------------------------------------------------------------
+// gridpp::neighbourhood(vec2, halfwidth, statistic) neighbourhood.cpp:28-242
+int ref_neighbourhood(const float* input, int ny, int nx, int halfwidth, int statistic, float* output, double* seconds) {
+    REF_TRY
+    gridpp::vec2 in = to_vec2(input, ny, nx);
+    clk::time_point t0 = clk::now();
+    gridpp::vec2 out = gridpp::neighbourhood(in, halfwidth, (gridpp::Statistic) statistic);
+    if(seconds) *seconds = since(t0);
+    if(out.size() == (size_t) ny) from_vec2(out, output, ny, nx);
+    REF_CATCH
+}
+// gridpp::neighbourhood_brute_force(vec2, ...) neighbourhood.cpp:528-530 -- the reference's own cross-check
+int ref_neighbourhood_brute_force(const float* input, int ny, int nx, int halfwidth, int statistic, float* output) {
+    REF_TRY
+    gridpp::vec2 in = to_vec2(input, ny, nx);
+    gridpp::vec2 out = gridpp::neighbourhood_brute_force(in, halfwidth, (gridpp::Statistic) statistic);
+    if(out.size() == (size_t) ny) from_vec2(out, output, ny, nx);
+    REF_CATCH
+}
+// gridpp::neighbourhood_quantile_fast(vec2, float | vec2, halfwidth, thresholds) neighbourhood.cpp:296-409
+int ref_neighbourhood_quantile_fast(const float* input, int ny, int nx, float quantile, const float* quantile_field,
+                                    int halfwidth, const float* thresholds, int num_thresholds, float* output,
+                                    double* seconds) {
+    REF_TRY
+    gridpp::vec2 in = to_vec2(input, ny, nx);
+    gridpp::vec thr = to_vec(thresholds, num_thresholds);
+    gridpp::vec2 out;
+    clk::time_point t0 = clk::now();
+    if(quantile_field) {
+        gridpp::vec2 q = to_vec2(quantile_field, ny, nx);
+        t0 = clk::now();
+        out = gridpp::neighbourhood_quantile_fast(in, q, halfwidth, thr);
+    }
+    else
+        out = gridpp::neighbourhood_quantile_fast(in, quantile, halfwidth, thr);
+    if(seconds) *seconds = since(t0);
+    if(out.size() == (size_t) ny) from_vec2(out, output, ny, nx);
+    REF_CATCH
+}
+// gridpp::get_neighbourhood_thresholds(vec2, num) neighbourhood.cpp:243-266
+int ref_get_neighbourhood_thresholds(const float* input, int ny, int nx, int num, float* out, int* out_n) {
+    REF_TRY
+    gridpp::vec t = gridpp::get_neighbourhood_thresholds(to_vec2(input, ny, nx), num);
+    *out_n = t.size();
+    for(size_t i = 0; i < t.size() && (int) i < num; i++) out[i] = t[i];
+    REF_CATCH
+}
+// gridpp::interpolate(float, vec, vec) util.cpp:377-414
+int ref_interpolate(float x, const float* ix, const float* iy, int n, float* out) {
+    REF_TRY
+    *out = gridpp::interpolate(x, to_vec(ix, n), to_vec(iy, n));
+    REF_CATCH
+}
+// gridpp::calc_statistic / calc_quantile util.cpp:19-178
+int ref_calc_statistic(const float* a, int n, int statistic, float* out) {
+    REF_TRY
+    *out = gridpp::calc_statistic(to_vec(a, n), (gridpp::Statistic) statistic);
+    REF_CATCH
+}
+int ref_calc_quantile(const float* a, int n, float q, float* out) {
+    REF_TRY
+    *out = gridpp::calc_quantile(to_vec(a, n), q);
+    REF_CATCH
+}
+
+}  // extern "C"
