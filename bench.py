@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native gridpp hot path.
+
+Metric (BASELINE.json): OI analysis gridpoints/sec on config 3 -- optimal_interpolation over a 4000 x 4000
+Cartesian grid (dx 250 m), 10 000 uniformly placed observations, BarnesStructure(10 km), variance ratio 0.5,
+max_points = 30.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]           our arm (CUDA kernels through the C ABI)
+  python bench.py --impl reference [--steps K] [--warmup W]     the reference's own CPU implementation
+
+One "step" = one full analysis of the grid. For N > 1 (launched by torchrun, one rank per GPU) the output rows
+are split across ranks (every grid point is independent, oi.cpp:221-338): no data-path collective, the
+observations are replicated; `value` = total gridpoints / max-over-ranks device time (strong scaling of the
+fixed 4000 x 4000 grid that the metric names).
+
+Printed JSON (one line, rank 0):
+  value      device-resident throughput: background / analysis already in HBM, CUDA-event timed.
+  e2e        the same analysis through the public host API (gridpp_b200.optimal_interpolation -> C ABI
+             gpp_optimal_interpolation_host) from pinned HOST arrays: H2D of the background, kernels, D2H of
+             the analysis are all inside the timed region.
+  roofline   dominant kernel (oi_fast_kernel). The kernel is bound by the fp64 CUDA cores, not by HBM or the
+             tensor cores; the contract's object reports the HBM view (16 B/gridpoint algorithmic traffic),
+             `roofline_fp64` reports the algorithmic-flop view against a measured fp64 FMA peak.
+  cpu_baseline  the reference's CPU path (oracle/_ref: the unmodified reference sources, all host threads) on
+             a bounded row-strided sample of the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_GRID = 4000
+DX = 250.0
+N_OBS = 10000
+H_SCALE = 10000.0
+MAX_POINTS = 30
+RATIO = 0.5
+SEED = 1000
+WORKLOAD = "C3: optimal_interpolation 4000x4000 grid (dx 250 m), 10000 obs, BarnesStructure(10000), ratio 0.5, max_points 30"
+
+
+def make_workload(row0=0, row1=N_GRID):
+    """Deterministic synthetic inputs; rows [row0, row1) of the grid. Observations are global."""
+    rng = np.random.default_rng(SEED)
+    py = (rng.random(N_OBS) * N_GRID * DX).astype(np.float32)
+    px = (rng.random(N_OBS) * N_GRID * DX).astype(np.float32)
+    noise = rng.standard_normal(N_OBS).astype(np.float32) * 0.5
+    ys = np.arange(row0, row1, dtype=np.float32) * DX
+    xs = np.arange(N_GRID, dtype=np.float32) * DX
+    y, x = np.meshgrid(ys, xs, indexing="ij")
+    # smooth synthetic background (analytic, so every rank can evaluate its own rows and the obs-point values)
+    def field(yy, xx):
+        return (3.0 * np.sin(yy / 37000.0) * np.cos(xx / 53000.0) + 1.5 * np.sin((yy + xx) / 11000.0)).astype(np.float32)
+    bg = field(y, x)
+    # background at the observation points = value at the nearest grid node (what gridpp.nearest returns)
+    iy = np.clip(np.rint(py / DX), 0, N_GRID - 1).astype(np.float32) * DX
+    ix = np.clip(np.rint(px / DX), 0, N_GRID - 1).astype(np.float32) * DX
+    pbg = field(iy, ix)
+    obs = (pbg + noise).astype(np.float32)
+    ratios = np.full(N_OBS, RATIO, np.float32)
+    return dict(y=y, x=x, background=bg, py=py, px=px, pobs=obs, pratios=ratios, pbackground=pbg)
+
+
+def oi_flops_per_gridpoint(w):
+    """F_OI(N_c, k) = 20 (N_c + k(k+1)/2) + 2 (k^3/3 + 2 k^2) + 4 k, averaged over a sample."""
+    from scipy.spatial import cKDTree
+    rng = np.random.default_rng(1)
+    R = float(np.sqrt(np.float32(-2) * np.log(np.float32(0.0013)))) * H_SCALE
+    tree = cKDTree(np.stack([w["py"], w["px"]], axis=1))
+    q = rng.random((20000, 2)) * N_GRID * DX
+    nc = np.array([len(v) for v in tree.query_ball_point(q, R)], dtype=np.float64)
+    k = np.minimum(nc, MAX_POINTS)
+    f = 20 * (nc + k * (k + 1) / 2) + 2 * (k ** 3 / 3 + 2 * k ** 2) + 4 * k
+    return float(f.mean()), float(nc.mean()), float(k.mean())
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (guides/B200_PROFILING.md)."""
+    FIELDS = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, device):
+        self.samples, self.proc, self.device = [], None, device
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append([p.strip() for p in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+        sm = [float(s[0]) for s in self.samples if len(s) >= 6 and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) >= 6 and s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for s in self.samples if len(s) >= 6 for i in range(4) if s[2 + i].lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def cpu_reference_run(w, n_sample, threads=None):
+    """Times the reference's CPU path (oracle/_ref when present, else the C port) on a row-strided sample of the grid
+    (Points overload, oi.cpp:138). Returns (gridpoints/s, kind, threads, seconds, n)."""
+    from oracle import bindings as B
+    kind = "reference" if B.available("ref") else "port"
+    if kind == "port" and not B.available("oracle"):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "oracle"], check=True, capture_output=True)
+    lib = B.load("ref" if kind == "reference" else "oracle")
+    threads = threads or os.cpu_count() or 1
+    lib.set_omp_threads(threads)
+    total = w["y"].size
+    stride = max(1, total // n_sample)
+    sel = np.arange(0, total, stride)[:n_sample]
+    timing = []
+    lib.optimal_interpolation((w["y"].ravel()[sel], w["x"].ravel()[sel], None, None), w["background"].ravel()[sel],
+                              (w["py"], w["px"], None, None), w["pobs"], w["pratios"], w["pbackground"],
+                              B.make_structure(B.BARNES, H_SCALE), MAX_POINTS, B.CARTESIAN, timing=timing)
+    return sel.size / timing[0], kind, threads, timing[0], int(sel.size)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = make_workload()
+    n = 200000
+    gps, kind, threads, sec, n = cpu_reference_run(w, n)            # calibration / first warm-up
+    n = int(min(4_000_000, max(50_000, gps * 8.0)))                  # ~8 s per step
+    for _ in range(max(0, args.warmup - 1)):
+        cpu_reference_run(w, n)
+    t = []
+    for _ in range(args.steps):
+        gps, kind, threads, sec, n = cpu_reference_run(w, n)
+        t.append(sec)
+    value = n * len(t) / sum(t)
+    sample = "%d row-strided gridpoints of the 4000x4000 grid per step (Points overload), %d host threads" % (n, threads)
+    line = {"impl": "reference", "metric": "OI analysis gridpoints/sec", "value": value, "unit": "gridpoints/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(t) / len(t), "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "gridpoints/s", "cores": threads, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": "gridpoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def secondary_metrics(gpp, gd, torch):
+    """Neighbourhood filters of config 2 (4000 x 4000, halfwidth 7), device-resident, as GB/s of the 8 B/pixel
+    algorithmic traffic. Inputs rotate over 4 buffers (256 MB > L2) so every launch reads from HBM."""
+    out = {}
+    n = N_GRID
+    bufs = [torch.rand((n, n), device="cuda") * 10 for _ in range(4)]
+    res = torch.empty((n, n), device="cuda")
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for name, st in (("mean", gpp.Mean), ("min", gpp.Min), ("max", gpp.Max)):
+        for i in range(3):
+            gd.neighbourhood(bufs[i % 4], 7, st, out=res)
+        ev0.record()
+        for i in range(12):
+            gd.neighbourhood(bufs[i % 4], 7, st, out=res)
+        ev1.record()
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1) / 12
+        out["neighbourhood_%s_hw7_4000x4000" % name] = {"ms": ms, "GB/s": 8.0 * n * n / (ms * 1e-3) / 1e9}
+    thr = np.linspace(0, 10, 20).astype(np.float32)
+    for i in range(2):
+        gd.neighbourhood_quantile_fast(bufs[i % 4], 0.5, 15, thr, out=res)
+    ev0.record()
+    for i in range(4):
+        gd.neighbourhood_quantile_fast(bufs[i % 4], 0.5, 15, thr, out=res)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / 4
+    out["quantile_fast_hw15_T20_4000x4000"] = {"ms": ms, "GB/s": 8.0 * n * n / (ms * 1e-3) / 1e9}
+    return out
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import gridpp_b200 as gpp
+    from gridpp_b200 import device as gd
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus != world and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    if gpp.device_count() == 0:
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    gpp.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    # rows of this rank (contiguous block)
+    rows = [N_GRID * r // world for r in range(world + 1)]
+    row0, row1 = rows[rank], rows[rank + 1]
+    w = make_workload(row0, row1)
+    n_local = (row1 - row0) * N_GRID
+    n_total = N_GRID * N_GRID
+
+    grid = gpp.Grid(w["y"], w["x"], type=gpp.Cartesian)
+    points = gpp.Points(w["py"], w["px"], type=gpp.Cartesian)
+    structure = gpp.BarnesStructure(H_SCALE)
+    state = gd.ObservationState(points, w["pobs"], w["pratios"], w["pbackground"], structure)
+    d_bg = torch.from_numpy(w["background"].ravel()).cuda()
+    d_out = torch.empty_like(d_bg)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        gd.optimal_interpolation(grid, d_bg, state, MAX_POINTS, out=d_out)
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = gpp.kernel_launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    barrier()
+    ev[0].record()
+    for i in range(args.steps):
+        step()
+        ev[i + 1].record()
+    barrier()
+    launches = gpp.kernel_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = ev[0].elapsed_time(ev[-1])
+    per_launch_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    value = n_total * args.steps / (total_ms_max * 1e-3)
+
+    # ---- end to end through the public host API, pinned host buffers
+    h_bg = torch.from_numpy(w["background"]).pin_memory()
+    bg_np = h_bg.numpy()
+    e2e_steps = max(2, min(args.steps, 5))
+    out_np = gpp.optimal_interpolation(grid, bg_np, points, w["pobs"], w["pratios"], w["pbackground"], structure, MAX_POINTS)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        out_np = gpp.optimal_interpolation(grid, bg_np, points, w["pobs"], w["pratios"], w["pbackground"], structure, MAX_POINTS)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = n_total * e2e_steps / float(t.item())
+    # the two entry points must agree bit for bit
+    same = bool(np.array_equal(out_np.ravel(), d_out.cpu().numpy(), equal_nan=True))
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except (OSError, ValueError):
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+        kernel_ms = statistics.mean(per_launch_ms)          # one kernel launch per step on this rank
+        bytes_per_launch = 16.0 * n_local                   # bg 4 + analysis 4 + lat/lon 8 per gridpoint
+        achieved_gbs = bytes_per_launch / (kernel_ms * 1e-3) / 1e9
+        line = {
+            "metric": "OI analysis gridpoints/sec", "value": value, "unit": "gridpoints/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "grid_rows_per_gpu": row1 - row0, "parallelism": "rows split over %d GPU(s), observations replicated, no collective" % world,
+                       "l2": "per-step inputs+outputs are %.0f MB per GPU (background, analysis, 5 coordinate planes), larger than the 126 MB L2" % (28.0 * n_local / 1e6),
+                       "device_and_host_entry_points_identical": same},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "gridpoints/s", "h2d_bytes_per_step": int(4 * n_total + 12 * N_OBS),
+                    "d2h_bytes_per_step": int(4 * n_total), "steps": e2e_steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
+                         "traffic": None, "kernel": "oi_fast_kernel", "peak_source": peak_src,
+                         "note": "HBM view only for the contract; the kernel is fp64-CUDA-core bound, see roofline_fp64"},
+        }
+        if not args.quick:
+            try:
+                f_gp, nc_mean, k_mean = oi_flops_per_gridpoint(w if world == 1 else make_workload(0, 1))
+                fp64_peak = gpp.measure_fp64_fma_peak()
+                achieved_tf = f_gp * n_local / (kernel_ms * 1e-3) / 1e12
+                line["roofline_fp64"] = {"bound": "fp64_fma", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+                                         "frac": achieved_tf / fp64_peak, "flops_per_gridpoint": f_gp, "mean_candidates": nc_mean,
+                                         "mean_selected": k_mean, "peak_source": "measured in this run (gpp_measure_fp64_fma_peak)"}
+            except Exception as e:   # never lose the headline over an auxiliary figure
+                line["roofline_fp64"] = {"error": repr(e)}
+            if world == 1:
+                try:
+                    gps, kind, threads, sec, n = cpu_reference_run(w, 100000)
+                    n2 = int(min(3_000_000, max(100_000, gps * 12.0)))
+                    gps, kind, threads, sec, n = cpu_reference_run(w, n2)
+                    line["cpu_baseline"] = {"value": gps, "unit": "gridpoints/s", "cores": threads, "kind": kind, "seconds": sec,
+                                            "sample": "%d row-strided gridpoints of the same 4000x4000 workload (Points overload)" % n}
+                except Exception as e:
+                    line["cpu_baseline"] = {"error": repr(e)}
+                try:
+                    line["secondary"] = secondary_metrics(gpp, gd, torch)
+                except Exception as e:
+                    line["secondary"] = {"error": repr(e)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--quick", action="store_true", help="skip cpu_baseline, fp64 roofline and secondary metrics")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

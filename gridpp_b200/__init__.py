@@ -1,0 +1,537 @@
+"""gridpp_b200 -- B200-native drop-in for the data-parallel hot path of metno/gridpp.
+
+The module mirrors the Python surface the reference generates with SWIG (swig/gridpp.i) for that path: same
+names, argument order, defaults, return types (new float32 / int32 ndarrays) and exception types
+(``ValueError`` for invalid arguments, ``RuntimeError`` otherwise)::
+
+    import gridpp_b200 as gridpp
+    grid = gridpp.Grid(lats, lons)
+    points = gridpp.Points(plats, plons)
+    structure = gridpp.BarnesStructure(10000)
+    pbackground = gridpp.nearest(grid, points, background)
+    analysis = gridpp.optimal_interpolation(grid, background, points, obs, ratios, pbackground, structure, 30)
+    smooth = gridpp.neighbourhood(analysis, 7, gridpp.Mean)
+
+Every function is a thin marshalling layer over the C ABI of ``libgridpp_b200.so`` (include/gridpp_b200.h);
+all computation happens in hand-written sm_100a CUDA kernels. There is no CPU fallback.
+"""
+import ctypes as _C
+
+import numpy as _np
+
+from . import _lib
+from ._lib import NotImplementedOnDevice, check as _check, lib as _libc
+
+__version__ = _libc.gpp_version().decode()
+
+# gridpp::CoordinateType (gridpp.h:120-123)
+Geodetic = 0
+Cartesian = 1
+# gridpp::Statistic (gridpp.h:88-100)
+Mean, Min, Median, Max, Quantile, Std, Variance, Sum, Count, RandomChoice, Unknown = 0, 10, 20, 30, 40, 50, 60, 70, 80, 90, -1
+MV = float("nan")
+_BARNES, _CRESSMAN, _SOAR, _TOAR, _POWERLAW, _LINEAR = range(6)
+
+
+def version():
+    return __version__
+
+
+def device_count():
+    n = _C.c_int()
+    _check(_libc.gpp_device_count(_C.byref(n)))
+    return n.value
+
+
+def set_device(device):
+    _check(_libc.gpp_set_device(int(device)))
+
+
+def synchronize():
+    _check(_libc.gpp_device_synchronize())
+
+
+def kernel_launch_count():
+    return int(_libc.gpp_kernel_launch_count())
+
+
+def measure_fp64_fma_peak():
+    """Measured fp64 FMA throughput of the current device, TFLOP/s."""
+    t = _C.c_double()
+    _check(_libc.gpp_measure_fp64_fma_peak(_C.byref(t)))
+    return t.value
+
+
+# ---------------------------------------------------------------------------------------------------------
+# marshalling helpers (the SWIG typemaps of swig/vector.i: any array-like of any dtype comes in, float32 /
+# int32 C-contiguous arrays go out; a wrong number of dimensions is an error)
+def _farray(a, ndim, name):
+    try:
+        arr = _np.ascontiguousarray(a, dtype=_np.float32)
+    except (TypeError, ValueError) as e:
+        raise ValueError("%s: cannot convert to a float array (%s)" % (name, e))
+    if arr.ndim != ndim:
+        # zero-length inputs such as [] or [[]] are accepted in any rank (tests/test_swig.py:91-107)
+        if arr.size == 0:
+            return arr.reshape((0,) * ndim)
+        raise ValueError("%s must have %d dimension(s), got %d" % (name, ndim, arr.ndim))
+    return arr
+
+
+def _fptr(a):
+    return a.ctypes.data_as(_lib.fp) if a is not None else None
+
+
+def _iptr(a):
+    return a.ctypes.data_as(_lib.ip) if a is not None else None
+
+
+# ---------------------------------------------------------------------------------------------------------
+class _PointSet:
+    """Owner of a gpp_points handle."""
+
+    def __init__(self, lats, lons, elevs, lafs, ctype):
+        n = lats.size
+        self._lats, self._lons = lats, lons
+        self._elevs = elevs if elevs is not None else _np.full(n, _np.nan, _np.float32)
+        self._lafs = lafs if lafs is not None else _np.full(n, _np.nan, _np.float32)
+        self._type = int(ctype)
+        self._handle = _C.c_void_p()
+        _check(_libc.gpp_points_create(_fptr(lats), _fptr(lons), _fptr(elevs), _fptr(lafs), n, self._type,
+                                       _C.byref(self._handle)))
+
+    def __del__(self):
+        h = getattr(self, "_handle", None)
+        if h:
+            _libc.gpp_points_destroy(h)
+            self._handle = None
+
+    @property
+    def n(self):
+        return self._lats.size
+
+    def xyz(self):
+        x, y, z = (_np.empty(self.n, _np.float32) for _ in range(3))
+        _check(_libc.gpp_points_get_xyz(self._handle, _fptr(x), _fptr(y), _fptr(z)))
+        return x, y, z
+
+    def nearest(self, lats, lons, include_match=True):
+        lats, lons = _farray(lats, 1, "lats"), _farray(lons, 1, "lons")
+        out = _np.empty(lats.size, _np.int32)
+        _check(_libc.gpp_points_nearest_host(self._handle, _fptr(lats), _fptr(lons), lats.size, int(include_match), _iptr(out)))
+        return out
+
+    def closest(self, lats, lons, num, include_match=True):
+        lats, lons = _farray(lats, 1, "lats"), _farray(lons, 1, "lons")
+        out = _np.empty((lats.size, num), _np.int32)
+        _check(_libc.gpp_points_closest_host(self._handle, _fptr(lats), _fptr(lons), lats.size, int(num), int(include_match),
+                                             _iptr(out)))
+        return out
+
+    def neighbours(self, lats, lons, radii, include_match=True, capacity=None, with_distance=False):
+        lats, lons = _farray(lats, 1, "lats"), _farray(lons, 1, "lons")
+        nq = lats.size
+        radii = _np.ascontiguousarray(_np.broadcast_to(_np.asarray(radii, _np.float32), (nq,)))
+        count = _np.zeros(nq, _np.int32)
+        if capacity is None:
+            _check(_libc.gpp_points_neighbours_host(self._handle, _fptr(lats), _fptr(lons), _fptr(radii), nq,
+                                                    int(include_match), 0, None, None, _iptr(count)))
+            capacity = int(count.max()) if nq else 0
+        idx = _np.full((nq, capacity), -1, _np.int32)
+        dist = _np.full((nq, capacity), _np.nan, _np.float32) if with_distance else None
+        if capacity > 0:
+            _check(_libc.gpp_points_neighbours_host(self._handle, _fptr(lats), _fptr(lons), _fptr(radii), nq,
+                                                    int(include_match), capacity, _iptr(idx), _fptr(dist), _iptr(count)))
+        return idx, dist, count
+
+
+class Points:
+    """gridpp::Points (gridpp.h:1876-1968, points.cpp)."""
+
+    def __init__(self, lats=None, lons=None, elevs=None, lafs=None, type=Geodetic):
+        lats = _farray([] if lats is None else lats, 1, "lats")
+        lons = _farray([] if lons is None else lons, 1, "lons")
+        n = lats.size
+        if lons.size != n:
+            raise ValueError("Cannot create points with unequal lat and lon sizes")
+        elevs = _farray([] if elevs is None else elevs, 1, "elevs")
+        lafs = _farray([] if lafs is None else lafs, 1, "lafs")
+        if elevs.size not in (0, n):
+            raise ValueError("'elevs' must either be size 0 or the same size at lats/lons")
+        if lafs.size not in (0, n):
+            raise ValueError("'lafs' must either be size 0 or the same size at lats/lons")
+        self._set = _PointSet(lats, lons, elevs if elevs.size == n and n > 0 else None, lafs if lafs.size == n and n > 0 else None, type)
+
+    # -- accessors
+    def get_lats(self):
+        return self._set._lats.copy()
+
+    def get_lons(self):
+        return self._set._lons.copy()
+
+    def get_elevs(self):
+        return self._set._elevs.copy()
+
+    def get_lafs(self):
+        return self._set._lafs.copy()
+
+    def size(self):
+        return self._set.n
+
+    def get_coordinate_type(self):
+        return self._set._type
+
+    # -- queries (points.cpp:40-62)
+    def get_nearest_neighbour(self, lat, lon, include_match=True):
+        return int(self._set.nearest([lat], [lon], include_match)[0])
+
+    def get_closest_neighbours(self, lat, lon, num, include_match=True):
+        row = self._set.closest([lat], [lon], num, include_match)[0]
+        return row[row >= 0].copy()
+
+    def get_neighbours(self, lat, lon, radius, include_match=True):
+        idx, _, count = self._set.neighbours([lat], [lon], radius, include_match)
+        return idx[0, :count[0]].copy()
+
+    def get_neighbours_with_distance(self, lat, lon, radius, include_match=True):
+        idx, dist, count = self._set.neighbours([lat], [lon], radius, include_match, with_distance=True)
+        return idx[0, :count[0]].copy(), dist[0, :count[0]].copy()
+
+    def get_num_neighbours(self, lat, lon, radius, include_match=True):
+        _, _, count = self._set.neighbours([lat], [lon], radius, include_match, capacity=0)
+        return int(count[0])
+
+    def subset(self, indices):
+        indices = _np.asarray(indices, dtype=_np.int64).ravel()
+        if indices.size and indices.max() >= self.size():
+            raise ValueError("Index %d exceeds number of points %d" % (indices.max(), self.size()))
+        s = self._set
+        # points.cpp:132-150: the subset is created with the default (Geodetic) coordinate type
+        return Points(s._lats[indices], s._lons[indices], s._elevs[indices], s._lafs[indices])
+
+
+class Grid:
+    """gridpp::Grid (gridpp.h:1971-2060, grid.cpp): a 2-D array of points, flattened row-major for queries."""
+
+    def __init__(self, lats=None, lons=None, elevs=None, lafs=None, type=Geodetic):
+        lats = _farray([[]] if lats is None else lats, 2, "lats")
+        lons = _farray([[]] if lons is None else lons, 2, "lons")
+        if lats.shape != lons.shape:
+            raise ValueError("Cannot create grid with unequal lat and lon sizes")
+        self._shape = lats.shape if lats.size else (0, 0)
+        elevs = _farray([[]] if elevs is None else elevs, 2, "elevs")
+        lafs = _farray([[]] if lafs is None else lafs, 2, "lafs")
+        # grid.cpp:41-54: elevations / land fractions of the wrong shape are replaced by missing values
+        e = elevs.ravel() if elevs.shape == lats.shape and lats.size else None
+        l = lafs.ravel() if lafs.shape == lats.shape and lats.size else None
+        self._set = _PointSet(lats.ravel(), lons.ravel(), e, l, type)
+
+    def size(self):
+        return _np.array(self._shape, dtype=_np.int32)
+
+    def get_lats(self):
+        return self._set._lats.reshape(self._shape).copy()
+
+    def get_lons(self):
+        return self._set._lons.reshape(self._shape).copy()
+
+    def get_elevs(self):
+        return self._set._elevs.reshape(self._shape).copy()
+
+    def get_lafs(self):
+        return self._set._lafs.reshape(self._shape).copy()
+
+    def get_coordinate_type(self):
+        return self._set._type
+
+    def _unflatten(self, flat):
+        flat = _np.asarray(flat)
+        nx = self._shape[1]
+        return _np.stack([flat // nx, flat % nx], axis=-1).astype(_np.int32)   # grid.cpp:108-114
+
+    def get_nearest_neighbour(self, lat, lon, include_match=True):
+        i = int(self._set.nearest([lat], [lon], include_match)[0])
+        return self._unflatten(i) if i >= 0 else _np.zeros(0, _np.int32)
+
+    def get_closest_neighbours(self, lat, lon, num, include_match=True):
+        row = self._set.closest([lat], [lon], num, include_match)[0]
+        return self._unflatten(row[row >= 0]).reshape(-1, 2)
+
+    def get_neighbours(self, lat, lon, radius, include_match=True):
+        idx, _, count = self._set.neighbours([lat], [lon], radius, include_match)
+        return self._unflatten(idx[0, :count[0]]).reshape(-1, 2)
+
+    def get_neighbours_with_distance(self, lat, lon, radius, include_match=True):
+        idx, dist, count = self._set.neighbours([lat], [lon], radius, include_match, with_distance=True)
+        return self._unflatten(idx[0, :count[0]]).reshape(-1, 2), dist[0, :count[0]].copy()
+
+    def get_num_neighbours(self, lat, lon, radius, include_match=True):
+        _, _, count = self._set.neighbours([lat], [lon], radius, include_match, capacity=0)
+        return int(count[0])
+
+    def to_points(self):
+        p = Points.__new__(Points)
+        p._set = self._set   # grid.cpp:131-145: same tree, elevations and land fractions
+        return p
+
+
+class KDTree(Points):
+    """gridpp::KDTree (gridpp.h:1746-1873): the index without elevation / land-fraction metadata."""
+
+    def __init__(self, lats=None, lons=None, type=Geodetic):
+        Points.__init__(self, lats, lons, None, None, type)
+
+
+# ---------------------------------------------------------------------------------------------------------
+class StructureFunction:
+    """POD-backed replacement for the gridpp::StructureFunction hierarchy (gridpp.h:2069-2343)."""
+
+    def __init__(self, desc):
+        self._desc = desc
+
+    def _points5(self, p):
+        return _np.ascontiguousarray(_np.asarray(p, _np.float32).reshape(-1, 5))
+
+    def corr(self, p1, p2):
+        """p1, p2: arrays (n, 5) of x, y, z, elev, laf. Evaluated on the device."""
+        return self._corr(p1, p2, False)
+
+    def corr_background(self, p1, p2):
+        return self._corr(p1, p2, True)
+
+    def _corr(self, p1, p2, background):
+        a, b = self._points5(p1), self._points5(p2)
+        if a.shape != b.shape:
+            raise ValueError("p1 and p2 must have the same shape")
+        out = _np.empty(a.shape[0], _np.float32)
+        _check(_libc.gpp_structure_corr_host(_C.byref(self._desc), _fptr(a), _fptr(b), a.shape[0], int(background), _fptr(out)))
+        return out
+
+    def localization_distance(self, point=None):
+        return float(self._desc.term[0].loc_dist)
+
+    def clone(self):
+        d = _lib.StructureDesc()
+        _C.memmove(_C.byref(d), _C.byref(self._desc), _C.sizeof(d))
+        c = StructureFunction.__new__(type(self))
+        c._desc = d
+        return c
+
+
+def _single(stype, h, v, w, hmax):
+    d = _lib.StructureDesc()
+    _check(_libc.gpp_structure_init(_C.byref(d), stype, float(h), float(v), float(w), float(hmax)))
+    return d
+
+
+class BarnesStructure(StructureFunction):
+    def __init__(self, h, v=0, w=0, hmax=MV):
+        if _np.ndim(h) != 0:
+            raise NotImplementedOnDevice("spatially varying structure functions are not part of the device path yet")
+        StructureFunction.__init__(self, _single(_BARNES, h, v, w, hmax))
+
+
+class CressmanStructure(StructureFunction):
+    def __init__(self, h, v=0, w=0):
+        StructureFunction.__init__(self, _single(_CRESSMAN, h, v, w, MV))
+
+
+class SoarStructure(StructureFunction):
+    def __init__(self, h, v=0, w=0, hmax=MV):
+        StructureFunction.__init__(self, _single(_SOAR, h, v, w, hmax))
+
+
+class ToarStructure(StructureFunction):
+    def __init__(self, h, v=0, w=0, hmax=MV):
+        StructureFunction.__init__(self, _single(_TOAR, h, v, w, hmax))
+
+
+class PowerlawStructure(StructureFunction):
+    def __init__(self, h, v=0, w=0, hmax=MV):
+        StructureFunction.__init__(self, _single(_POWERLAW, h, v, w, hmax))
+
+
+class LinearStructure(StructureFunction):
+    def __init__(self, h, v=0, w=0, hmax=MV):
+        StructureFunction.__init__(self, _single(_LINEAR, h, v, w, hmax))
+
+
+class MultipleStructure(StructureFunction):
+    def __init__(self, structure_h, structure_v, structure_w):
+        d = _lib.StructureDesc()
+        _check(_libc.gpp_structure_multiple(_C.byref(d), _C.byref(structure_h._desc), _C.byref(structure_v._desc),
+                                            _C.byref(structure_w._desc)))
+        StructureFunction.__init__(self, d)
+
+
+class CrossValidation(StructureFunction):
+    def __init__(self, structure, dist=MV):
+        d = _lib.StructureDesc()
+        _check(_libc.gpp_structure_cross_validation(_C.byref(d), _C.byref(structure._desc), float(dist)))
+        StructureFunction.__init__(self, d)
+
+
+# ---------------------------------------------------------------------------------------------------------
+def _is_grid(obj):
+    return isinstance(obj, Grid)
+
+
+def _check_size(cond, msg):
+    if not cond:
+        raise ValueError(msg)
+
+
+def optimal_interpolation(bgrid, background, points, pobs, pratios, pbackground, structure, max_points,
+                          allow_extrapolation=True):
+    """gridpp::optimal_interpolation, oi.cpp:26-136 (Grid and Points overloads)."""
+    out = _oi(bgrid, background, None, points, pobs, pratios, pbackground, None, structure, max_points, allow_extrapolation, False)
+    return out
+
+
+def optimal_interpolation_full(bgrid, background, bvariance, points, obs, obs_variance, background_at_points,
+                               bvariance_at_points, structure, max_points, allow_extrapolation=True):
+    """gridpp::optimal_interpolation_full, oi.cpp:138-412. Returns (analysis, analysis_variance)."""
+    return _oi(bgrid, background, bvariance, points, obs, obs_variance, background_at_points, bvariance_at_points, structure,
+               max_points, allow_extrapolation, True)
+
+
+def _oi(bgrid, background, bvariance, points, pobs, obs_variance, pbackground, bvariance_at_points, structure, max_points,
+        allow_extrapolation, full):
+    if max_points < 0:
+        raise ValueError("max_points must be >= 0")
+    if not isinstance(points, Points):
+        raise ValueError("points must be a Points object")
+    if bgrid.get_coordinate_type() != points.get_coordinate_type():
+        raise ValueError("Both background and observations points must be of same coordinate type (lat/lon or x/y)")
+    grid = _is_grid(bgrid)
+    ndim = 2 if grid else 1
+    bg = _farray(background, ndim, "background")
+    shape = tuple(bgrid.size()) if grid else (bgrid.size(),)
+    _check_size(bg.shape == shape, "input field %s is not the same size as the grid %s" % (bg.shape, shape))
+    bvar = None
+    if bvariance is not None:
+        bvar = _farray(bvariance, ndim, "bvariance")
+        _check_size(bvar.shape == shape, "Input bvariance %s is not the same size as the grid %s" % (bvar.shape, shape))
+    nS = points.size()
+    obs = _farray(pobs, 1, "pobs")
+    ovar = _farray(obs_variance, 1, "obs_variance")
+    pbg = _farray(pbackground, 1, "pbackground")
+    _check_size(obs.size == nS, "Observations (%d) and points (%d) size mismatch" % (obs.size, nS))
+    _check_size(ovar.size == nS, "Ratios (%d) and points (%d) size mismatch" % (ovar.size, nS))
+    _check_size(pbg.size == nS, "Background (%d) and points (%d) size mismatch" % (pbg.size, nS))
+    pbvar = None
+    if bvariance_at_points is not None:
+        pbvar = _farray(bvariance_at_points, 1, "bvariance_at_points")
+        _check_size(pbvar.size == nS, "Background variance (%d) and points (%d) size mismatch" % (pbvar.size, nS))
+    out = _np.empty(shape, _np.float32)
+    var = _np.empty(shape, _np.float32) if full else None
+    _check(_libc.gpp_optimal_interpolation_host(bgrid._set._handle, _fptr(bg), _fptr(bvar), points._set._handle, _fptr(obs),
+                                                _fptr(ovar), _fptr(pbg), _fptr(pbvar), _C.byref(structure._desc),
+                                                int(max_points), int(bool(allow_extrapolation)), _fptr(out), _fptr(var)))
+    return (out, var) if full else out
+
+
+def optimal_interpolation_ensi(bgrid, background, points, pobs, psigmas, pbackground, structure, max_points,
+                               allow_extrapolation=True):
+    """gridpp::optimal_interpolation_ensi, oi_ensi.cpp:33-568. background is (Y, X, E) for a Grid or (N, E) for
+    Points; pbackground is (S, E)."""
+    if max_points < 0:
+        raise ValueError("max_points must be >= 0")
+    grid = _is_grid(bgrid)
+    bg = _farray(background, 3 if grid else 2, "background")
+    nS = points.size()
+    if nS == 0:
+        return bg.copy()   # oi_ensi.cpp:49-51,137-139
+    if bgrid.get_coordinate_type() != points.get_coordinate_type():
+        raise ValueError("Both background and observations points must be of same coorindate type (lat/lon or x/y)")
+    shape = tuple(bgrid.size()) if grid else (bgrid.size(),)
+    if grid and (shape[0] == 0 or shape[1] == 0):
+        raise ValueError("Grid size (%d,%d) cannot be zero" % shape)
+    _check_size(bg.shape[:-1] == shape, "Input field is not the same size as the grid")
+    nE = bg.shape[-1]
+    obs = _farray(pobs, 1, "pobs")
+    sig = _farray(psigmas, 1, "psigmas")
+    pbg = _farray(pbackground, 2, "pbackground")
+    _check_size(obs.size == nS, "Observations and points exception mismatch")
+    _check_size(sig.size == nS, "Sigmas and points size mismatch")
+    _check_size(pbg.shape[0] == nS, "Background and points size mismatch")
+    _check_size(pbg.shape[1] == nE, "Background and points ensemble size mismatch")
+    out = _np.empty(bg.shape, _np.float32)
+    skipped = _C.c_int()
+    _check(_libc.gpp_optimal_interpolation_ensi_host(bgrid._set._handle, _fptr(bg), nE, points._set._handle, _fptr(obs), _fptr(sig),
+                                                     _fptr(pbg), _C.byref(structure._desc), int(max_points),
+                                                     int(bool(allow_extrapolation)), _fptr(out), _C.byref(skipped)))
+    if skipped.value > 0:   # oi_ensi.cpp:557-561
+        print("Warning: Condition number error in %d points. Using raw values in those points." % skipped.value)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+def neighbourhood(input, halfwidth, statistic):
+    """gridpp::neighbourhood(vec2, halfwidth, statistic), neighbourhood.cpp:28-242."""
+    field = _np.asarray(input, dtype=_np.float32)
+    if field.ndim == 3:
+        raise NotImplementedOnDevice("the ensemble (3-D) form of neighbourhood() is not part of the device path yet")
+    field = _farray(field, 2, "input")
+    if halfwidth < 0:
+        raise ValueError("Half width must be > 0")
+    if statistic == Quantile:
+        raise ValueError("Use neighbourhood_quantile for computing neighbourhood quantiles")
+    if field.shape[0] == 0 or field.shape[1] == 0:
+        return _np.zeros((0, 0), _np.float32)
+    out = _np.empty(field.shape, _np.float32)
+    _check(_libc.gpp_neighbourhood_host(_fptr(field), field.shape[0], field.shape[1], int(halfwidth), int(statistic), _fptr(out)))
+    return out
+
+
+def neighbourhood_quantile_fast(input, quantile, halfwidth, thresholds):
+    """gridpp::neighbourhood_quantile_fast(vec2, float | vec2, halfwidth, thresholds), neighbourhood.cpp:296-409."""
+    field = _np.asarray(input, dtype=_np.float32)
+    if field.ndim == 3:
+        raise NotImplementedOnDevice("the ensemble (3-D) form of neighbourhood_quantile_fast() is not part of the device path yet")
+    field = _farray(field, 2, "input")
+    thr = _farray(thresholds, 1, "thresholds")
+    if halfwidth < 0:
+        raise ValueError("Half width must be > 0")
+    if field.shape[0] == 0 or field.shape[1] == 0:
+        return _np.zeros((0, 0), _np.float32)
+    qf = None
+    q = float("nan")
+    if _np.ndim(quantile) == 0:
+        q = float(quantile)
+    else:
+        qf = _farray(quantile, 2, "quantile")
+        if qf.shape == (1, 1):
+            q, qf = float(qf[0, 0]), None
+        elif qf.shape != field.shape:
+            raise ValueError("Quantile must be the same size as input, or size (1, 1)")
+    out = _np.empty(field.shape, _np.float32)
+    _check(_libc.gpp_neighbourhood_quantile_fast_host(_fptr(field), field.shape[0], field.shape[1], q, _fptr(qf), int(halfwidth),
+                                                      _fptr(thr), thr.size, _fptr(out)))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+def nearest(igrid, ogrid, ivalues):
+    """gridpp::nearest, nearest.cpp:7-222 (all eight Grid/Points x Grid/Points x 2-D/3-D overloads)."""
+    in_grid, out_grid = _is_grid(igrid), _is_grid(ogrid)
+    ishape = tuple(igrid.size()) if in_grid else (igrid.size(),)
+    oshape = tuple(ogrid.size()) if out_grid else (ogrid.size(),)
+    base = 2 if in_grid else 1
+    values = _np.asarray(ivalues, dtype=_np.float32)
+    multi = values.ndim == base + 1
+    if values.ndim not in (base, base + 1):
+        raise ValueError("ivalues has the wrong number of dimensions")
+    if multi:
+        _check_size(values.shape[1:] == ishape or values.size == 0, "Grid size is not the same as values")
+        flat = _np.ascontiguousarray(values.reshape(values.shape[0], -1))
+        nf = values.shape[0]
+    else:
+        _check_size(values.shape == ishape, "Grid size is not the same as values" if in_grid else "Points size is not the same as values")
+        flat = _np.ascontiguousarray(values.reshape(1, -1))
+        nf = 1
+    nq = int(_np.prod(oshape))
+    out = _np.empty((nf, nq), _np.float32)
+    _check(_libc.gpp_nearest_host(igrid._set._handle, _fptr(ogrid._set._lats), _fptr(ogrid._set._lons), nq, _fptr(flat), nf,
+                                  _fptr(out)))
+    return out.reshape((nf,) + oshape) if multi else out.reshape(oshape)

@@ -1,0 +1,101 @@
+"""ctypes binding of libgridpp_b200.so (the C ABI declared in include/gridpp_b200.h).
+
+The shared library is the product; this module only loads it and declares the prototypes. There is no CPU
+fallback: if the library is missing, import fails with instructions to build it.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libgridpp_b200.so")
+
+OK, ERR_INVALID_ARGUMENT, ERR_RUNTIME, ERR_NOT_IMPLEMENTED, ERR_CUDA = range(5)
+
+
+class StructureTerm(C.Structure):
+    _fields_ = [("type", C.c_int), ("h", C.c_float), ("v", C.c_float), ("w", C.c_float),
+                ("min_rho", C.c_float), ("loc_dist", C.c_float)]
+
+
+class StructureDesc(C.Structure):
+    """gpp_structure"""
+    _fields_ = [("n_terms", C.c_int), ("term", StructureTerm * 3), ("has_cv", C.c_int), ("cv_dist", C.c_float)]
+
+
+fp = C.POINTER(C.c_float)
+ip = C.POINTER(C.c_int)
+vp = C.c_void_p
+sp = C.POINTER(StructureDesc)
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        "gridpp_b200: %s is missing. Build it with `python -m gridpp_b200.build` (needs nvcc; targets sm_100a). "
+        "There is no CPU fallback." % LIB_PATH)
+
+lib = C.CDLL(LIB_PATH)
+
+
+def _proto(name, restype, *argtypes):
+    fn = getattr(lib, name)
+    fn.restype = restype
+    fn.argtypes = list(argtypes)
+    return fn
+
+
+_proto("gpp_version", C.c_char_p)
+_proto("gpp_last_error", C.c_char_p)
+_proto("gpp_device_count", C.c_int, ip)
+_proto("gpp_set_device", C.c_int, C.c_int)
+_proto("gpp_device_synchronize", C.c_int)
+_proto("gpp_kernel_launch_count", C.c_ulonglong)
+_proto("gpp_measure_fp64_fma_peak", C.c_int, C.POINTER(C.c_double))
+_proto("gpp_structure_init", C.c_int, sp, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float)
+_proto("gpp_structure_multiple", C.c_int, sp, sp, sp, sp)
+_proto("gpp_structure_cross_validation", C.c_int, sp, sp, C.c_float)
+_proto("gpp_structure_corr_host", C.c_int, sp, fp, fp, C.c_int, C.c_int, fp)
+_proto("gpp_points_create", C.c_int, fp, fp, fp, fp, C.c_int, C.c_int, C.POINTER(vp))
+_proto("gpp_points_destroy", None, vp)
+_proto("gpp_points_size", C.c_int, vp)
+_proto("gpp_points_coordinate_type", C.c_int, vp)
+_proto("gpp_points_get_xyz", C.c_int, vp, fp, fp, fp)
+_proto("gpp_points_nearest_host", C.c_int, vp, fp, fp, C.c_int, C.c_int, ip)
+_proto("gpp_points_neighbours_host", C.c_int, vp, fp, fp, fp, C.c_int, C.c_int, C.c_int, ip, fp, ip)
+_proto("gpp_points_closest_host", C.c_int, vp, fp, fp, C.c_int, C.c_int, C.c_int, ip)
+_proto("gpp_nearest_host", C.c_int, vp, fp, fp, C.c_int, fp, C.c_int, fp)
+_proto("gpp_optimal_interpolation_host", C.c_int, vp, fp, fp, vp, fp, fp, fp, fp, sp, C.c_int, C.c_int, fp, fp)
+_proto("gpp_oi_obs_create", C.c_int, vp, fp, fp, fp, fp, sp, C.POINTER(vp))
+_proto("gpp_oi_obs_destroy", None, vp)
+_proto("gpp_optimal_interpolation_device", C.c_int, vp, C.c_int, C.c_int, vp, vp, vp, sp, C.c_int, C.c_int, vp, vp, vp)
+_proto("gpp_optimal_interpolation_ensi_host", C.c_int, vp, fp, C.c_int, vp, fp, fp, fp, sp, C.c_int, C.c_int, fp, ip)
+_proto("gpp_neighbourhood_host", C.c_int, fp, C.c_int, C.c_int, C.c_int, C.c_int, fp)
+_proto("gpp_neighbourhood_device", C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp)
+_proto("gpp_neighbourhood_quantile_fast_host", C.c_int, fp, C.c_int, C.c_int, C.c_float, fp, C.c_int, fp, C.c_int, fp)
+_proto("gpp_neighbourhood_quantile_fast_device", C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, vp, C.c_int,
+       fp, C.c_int, vp, vp)
+
+EXPORTS = [
+    "gpp_version", "gpp_last_error", "gpp_device_count", "gpp_set_device", "gpp_device_synchronize",
+    "gpp_kernel_launch_count", "gpp_measure_fp64_fma_peak", "gpp_structure_init", "gpp_structure_multiple", "gpp_structure_cross_validation",
+    "gpp_structure_corr_host", "gpp_points_create", "gpp_points_destroy", "gpp_points_size",
+    "gpp_points_coordinate_type", "gpp_points_get_xyz", "gpp_points_nearest_host", "gpp_points_neighbours_host",
+    "gpp_points_closest_host", "gpp_nearest_host", "gpp_optimal_interpolation_host", "gpp_oi_obs_create",
+    "gpp_oi_obs_destroy", "gpp_optimal_interpolation_device", "gpp_optimal_interpolation_ensi_host",
+    "gpp_neighbourhood_host", "gpp_neighbourhood_device", "gpp_neighbourhood_quantile_fast_host",
+    "gpp_neighbourhood_quantile_fast_device",
+]
+
+
+class NotImplementedOnDevice(RuntimeError):
+    pass
+
+
+def check(rc):
+    """Maps status codes to the exceptions the reference's SWIG layer raises (swig/gridpp.i:21-40)."""
+    if rc == OK:
+        return
+    msg = lib.gpp_last_error().decode(errors="replace")
+    if rc == ERR_INVALID_ARGUMENT:
+        raise ValueError(msg)
+    if rc == ERR_NOT_IMPLEMENTED:
+        raise NotImplementedOnDevice(msg)
+    raise RuntimeError(msg)

@@ -1,0 +1,641 @@
+// Deterministic optimal interpolation on the device ("K6" in SURVEY.md).
+// Replaces gridpp::optimal_interpolation / optimal_interpolation_full, src/api/oi.cpp:26-412.
+//
+// One warp analyses one background point:
+//   1. gather: scan the bucket-grid cells overlapping the localization box, keep observations strictly inside
+//      the box with straight distance <= R and rho > 0 (oi.cpp:229-258, kdtree.cpp:39-62), streaming top-k by
+//      (rho, index) in shared memory (oi.cpp:262-273);
+//   2. assemble P + R for the k selected observations from pairwise structure-function evaluations
+//      (oi.cpp:298-314), packed over the 32 lanes;
+//   3. eliminate: lane j holds row j of the symmetric augmented matrix [[P+R, rho, d], [rho', 0, 0], [d', 0, 0]]
+//      in registers (fp64). k steps of symmetric Gaussian elimination leave -rho'(P+R)^-1 rho and
+//      -rho'(P+R)^-1 d in the trailing 2x2 block, i.e. the analysis-variance factor and the increment of
+//      oi.cpp:315-317,336-337, without ever forming the inverse.
+// The register path covers symmetric structure functions with k <= 30. Everything else (k > 30, unlimited
+// max_points, non-symmetric structure functions) takes the general kernel: Gauss-Jordan with partial pivoting
+// on a per-warp global-memory scratch matrix.
+#include "oi.cuh"
+
+#include <algorithm>
+#include <cstring>
+
+using namespace gpp;
+
+namespace {
+
+constexpr int FAST_K = 30;          // max observations per point on the register path
+constexpr int WARPS_PER_CTA = 8;
+
+struct OiParams {
+    // background points
+    const float *gx, *gy, *gz, *gelev, *glaf;
+    const float* background;
+    const float* bvariance;          // may be NULL (= 1)
+    float* analysis;
+    float* analysis_variance;        // may be NULL
+    int first, count;
+    ObsView obs;
+    gpp_structure s;
+    float R;
+    int k;                           // max observations per point (> 0)
+    int allow_extrapolation;
+};
+
+// oi.cpp:318-337: optional clamp, then output and analysis variance
+__device__ __forceinline__ void write_result(const OiParams& P, int g, float bg, double dx, double a, double dmax, double dmin) {
+    float increment = (float) dx;                      // oi.cpp:317
+    if(!P.allow_extrapolation) {                       // oi.cpp:318-334
+        float maxInc = (float) dmax, minInc = (float) dmin;
+        if(maxInc > 0 && increment > maxInc) increment = maxInc;
+        else if(maxInc < 0 && increment > 0) increment = maxInc;
+        else if(minInc < 0 && increment < minInc) increment = minInc;
+        else if(minInc > 0 && increment < 0) increment = minInc;
+    }
+    P.analysis[g] = __fadd_rn(bg, increment);          // oi.cpp:335
+    if(P.analysis_variance) {
+        float bv = P.bvariance ? P.bvariance[g] : 1.f;
+        P.analysis_variance[g] = (float) __dmul_rn((double) bv, __dsub_rn(1.0, a));   // oi.cpp:336-337
+    }
+}
+
+struct FastSmem {
+    float cand_rho[64];
+    int cand_pos[64];
+    int cand_orig[64];
+    float sx[32], sy[32], sz[32], selev[32], slaf[32];
+    float sratio[32];
+    double sd[32];
+    double colbuf[2][32];
+    float A[32 * 33];
+};
+
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 2) oi_fast_kernel(const __grid_constant__ OiParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    FastSmem& S = reinterpret_cast<FastSmem*>(smem_raw)[threadIdx.x >> 5];
+    const unsigned lane = lane_id();
+    const int warp_global = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
+    const int warps_total = gridDim.x * WARPS_PER_CTA;
+    CandBuf cb = {S.cand_rho, S.cand_pos, S.cand_orig};
+
+    for(int it = warp_global; it < P.count; it += warps_total) {
+        const int g = P.first + it;
+        const float bg = P.background[g];
+        if(!is_valid(bg)) {   // oi.cpp:223
+            if(lane == 0) {
+                P.analysis[g] = bg;
+                if(P.analysis_variance) P.analysis_variance[g] = P.bvariance ? P.bvariance[g] : 1.f;
+            }
+            continue;
+        }
+        const Pt p1 = {P.gx[g], P.gy[g], P.gz[g], P.gelev[g], P.glaf[g]};
+        const int k = gather_candidates(P.obs, P.s, p1, P.R, P.k, cb);
+        if(k == 0) {          // oi.cpp:234-237,284-287
+            if(lane == 0) {
+                P.analysis[g] = bg;
+                if(P.analysis_variance) P.analysis_variance[g] = P.bvariance ? P.bvariance[g] : 1.f;
+            }
+            continue;
+        }
+        // ---- stage the selected observations
+        if((int) lane < k) {
+            int pos = S.cand_pos[lane];
+            S.sx[lane] = P.obs.x[pos]; S.sy[lane] = P.obs.y[pos]; S.sz[lane] = P.obs.z[pos];
+            S.selev[lane] = P.obs.elev[pos]; S.slaf[lane] = P.obs.laf[pos];
+            S.sratio[lane] = P.obs.ratio[pos];
+            S.sd[lane] = P.obs.innov[pos];
+        }
+        __syncwarp();
+        // ---- pairwise correlations, lower triangle incl. diagonal, packed over the lanes (oi.cpp:298-314)
+        const int npairs = k * (k + 1) / 2;
+        for(int p = (int) lane; p < npairs; p += 32) {
+            int j = (int) ((sqrtf(8.f * (float) p + 1.f) - 1.f) * 0.5f);
+            while(j * (j + 1) / 2 > p) j--;
+            while((j + 1) * (j + 2) / 2 <= p) j++;
+            int i = p - j * (j + 1) / 2;
+            Pt a = {S.sx[j], S.sy[j], S.sz[j], S.selev[j], S.slaf[j]};
+            Pt b = {S.sx[i], S.sy[i], S.sz[i], S.selev[i], S.slaf[i]};
+            S.A[j * 33 + i] = structure_corr(P.s, a, b);
+        }
+        __syncwarp();
+        // ---- row `lane` of the augmented matrix into registers
+        double a[32];
+        {
+            const bool is_row = (int) lane < k;
+            const float my_ratio = is_row ? S.sratio[lane] : 0.f;
+            #pragma unroll
+            for(int i = 0; i < 30; i++) {
+                double v = 0.0;
+                if(i < k) {
+                    if(is_row) {
+                        int hi = max((int) lane, i), lo = min((int) lane, i);
+                        v = (double) S.A[hi * 33 + lo];
+                        if(i == (int) lane) v = __dadd_rn(v, (double) my_ratio);   // lP + lR, oi.cpp:315
+                    }
+                    else if(lane == 30) v = (double) S.cand_rho[i];
+                    else if(lane == 31) v = S.sd[i];
+                }
+                a[i] = v;
+            }
+            a[30] = is_row ? (double) S.cand_rho[lane] : 0.0;
+            a[31] = is_row ? S.sd[lane] : 0.0;
+        }
+        // max / min innovation for the optional clamp (oi.cpp:319-320)
+        double dmax = (int) lane < k ? S.sd[lane] : -INFINITY, dmin = (int) lane < k ? S.sd[lane] : INFINITY;
+        if(!P.allow_extrapolation) {
+            #pragma unroll
+            for(int off = 16; off > 0; off >>= 1) {
+                dmax = fmax(dmax, shfl_double(dmax, lane ^ off));
+                dmin = fmin(dmin, shfl_double(dmin, lane ^ off));
+            }
+        }
+        // ---- symmetric elimination of the k observation rows
+        #pragma unroll
+        for(int c = 0; c < FAST_K; c++) {
+            if(c < k) {
+                const double my = a[c];
+                const double piv = shfl_double(my, c);
+                S.colbuf[c & 1][lane] = my;
+                const double f = my * (1.0 / piv);
+                __syncwarp();
+                #pragma unroll
+                for(int i = c + 1; i < 32; i++)
+                    if(i >= 30 || i < k) a[i] = fma(-f, S.colbuf[c & 1][i], a[i]);
+            }
+        }
+        // lane 30 now holds -rho'(P+R)^-1 rho in a[30] and -rho'(P+R)^-1 d in a[31]
+        if(lane == 30) write_result(P, g, bg, -a[31], -a[30], dmax, dmin);
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------ general path ----------------------
+// Per-warp scratch in global memory: two candidate buffers of (kcap + 32) entries and a kcap x (kcap + 2)
+// row-major fp64 matrix [P+R | d | rho].
+struct GeneralScratch {
+    float* rho[2];
+    int* pos[2];
+    int* orig[2];
+    double* M;
+};
+__device__ __forceinline__ GeneralScratch scratch_for(unsigned char* base, size_t bytes_per_warp, int warp, int kcap) {
+    unsigned char* p = base + (size_t) warp * bytes_per_warp;
+    GeneralScratch s;
+    s.M = reinterpret_cast<double*>(p);
+    p += sizeof(double) * (size_t) kcap * (kcap + 2);
+    int cap = kcap + 32;
+    for(int b = 0; b < 2; b++) {
+        s.rho[b] = reinterpret_cast<float*>(p); p += sizeof(float) * cap;
+        s.pos[b] = reinterpret_cast<int*>(p); p += sizeof(int) * cap;
+        s.orig[b] = reinterpret_cast<int*>(p); p += sizeof(int) * cap;
+    }
+    return s;
+}
+size_t scratch_bytes(int kcap) {
+    size_t b = sizeof(double) * (size_t) kcap * (kcap + 2) + 2 * 3 * sizeof(float) * (size_t) (kcap + 32);
+    return (b + 255) / 256 * 256;
+}
+
+// rank-select the best min(n, k) of src into dst (best-first); any n
+__device__ int general_prune(const GeneralScratch& s, int src, int n, int k) {
+    unsigned lane = lane_id();
+    int dst = src ^ 1;
+    for(int e = (int) lane; e < n; e += 32) {
+        float r = s.rho[src][e];
+        int o = s.orig[src][e];
+        int rank = 0;
+        for(int j = 0; j < n; j++) rank += cand_better(s.rho[src][j], s.orig[src][j], r, o) ? 1 : 0;
+        if(rank < k) { s.rho[dst][rank] = r; s.pos[dst][rank] = s.pos[src][e]; s.orig[dst][rank] = o; }
+    }
+    __syncwarp();
+    return min(n, k);
+}
+
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32) oi_general_kernel(const __grid_constant__ OiParams P, unsigned char* scratch,
+                                                                       size_t bytes_per_warp, int kcap) {
+    const unsigned lane = lane_id();
+    const int warp_global = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
+    const int warps_total = gridDim.x * WARPS_PER_CTA;
+    const GeneralScratch S = scratch_for(scratch, bytes_per_warp, warp_global, kcap);
+    const ObsView& obs = P.obs;
+
+    for(int it = warp_global; it < P.count; it += warps_total) {
+        const int g = P.first + it;
+        const float bg = P.background[g];
+        bool done = !is_valid(bg);
+        int k = 0, cur = 0;
+        Pt p1 = {0, 0, 0, 0, 0};
+        if(!done) {
+            p1 = {P.gx[g], P.gy[g], P.gz[g], P.gelev[g], P.glaf[g]};
+            float lo0 = __fsub_rn(p1.x, P.R), lo1 = __fsub_rn(p1.y, P.R), lo2 = __fsub_rn(p1.z, P.R);
+            float hi0 = __fadd_rn(p1.x, P.R), hi1 = __fadd_rn(p1.y, P.R), hi2 = __fadd_rn(p1.z, P.R);
+            int n = 0;
+            if(lo0 < hi0 && lo1 < hi1 && lo2 < hi2) {
+                int cx0 = cell_coord(obs.geom, 0, lo0), cx1 = cell_coord(obs.geom, 0, hi0);
+                int cy0 = cell_coord(obs.geom, 1, lo1), cy1 = cell_coord(obs.geom, 1, hi1);
+                int cz0 = cell_coord(obs.geom, 2, lo2), cz1 = cell_coord(obs.geom, 2, hi2);
+                for(int cz = cz0; cz <= cz1; cz++)
+                    for(int cy = cy0; cy <= cy1; cy++) {
+                        int base = (cz * obs.geom.n[1] + cy) * obs.geom.n[0];
+                        int s0 = obs.cell_start[base + cx0], s1 = obs.cell_start[base + cx1 + 1];
+                        for(int chunk = s0; chunk < s1; chunk += 32) {
+                            int i = chunk + (int) lane;
+                            float rho = 0.f;
+                            bool ok = i < s1;
+                            if(ok) {
+                                float ox = obs.x[i], oy = obs.y[i], oz = obs.z[i];
+                                ok = ox > lo0 && ox < hi0 && oy > lo1 && oy < hi1 && oz > lo2 && oz < hi2;
+                                if(ok) {
+                                    float dist = straight_distance(ox, oy, oz, p1.x, p1.y, p1.z);
+                                    ok = dist <= P.R;
+                                    if(ok) {
+                                        Pt p2 = {ox, oy, oz, obs.elev[i], obs.laf[i]};
+                                        rho = structure_corr_background(P.s, p1, p2, dist);
+                                        ok = rho > 0.f;
+                                    }
+                                }
+                            }
+                            unsigned mask = __ballot_sync(0xffffffffu, ok);
+                            if(ok) {
+                                int slot = n + __popc(mask & ((1u << lane) - 1u));
+                                S.rho[cur][slot] = rho; S.pos[cur][slot] = i; S.orig[cur][slot] = obs.orig[i];
+                            }
+                            n += __popc(mask);
+                            __syncwarp();
+                            if(n > kcap) { n = general_prune(S, cur, n, P.k); cur ^= 1; }
+                        }
+                    }
+            }
+            if(n > 0) { n = general_prune(S, cur, n, P.k); cur ^= 1; }
+            k = n;
+            done = k == 0;
+        }
+        if(done) {
+            if(lane == 0) {
+                P.analysis[g] = bg;
+                if(P.analysis_variance) P.analysis_variance[g] = P.bvariance ? P.bvariance[g] : 1.f;
+            }
+            continue;
+        }
+        // ---- assemble [P+R | d | rho], k x (k+2), row-major; lP(i,j) = corr(p_i, p_j) (oi.cpp:305-313)
+        const int ld = k + 2;
+        for(int e = (int) lane; e < k * k; e += 32) {
+            int i = e / k, j = e % k;
+            int pi = S.pos[cur][i], pj = S.pos[cur][j];
+            Pt a = {obs.x[pi], obs.y[pi], obs.z[pi], obs.elev[pi], obs.laf[pi]};
+            Pt b = {obs.x[pj], obs.y[pj], obs.z[pj], obs.elev[pj], obs.laf[pj]};
+            double v = (double) structure_corr(P.s, a, b);
+            if(i == j) v = __dadd_rn(v, (double) obs.ratio[pi]);
+            S.M[(size_t) i * ld + j] = v;
+        }
+        double dmax = -INFINITY, dmin = INFINITY;
+        for(int i = (int) lane; i < k; i += 32) {
+            double d = obs.innov[S.pos[cur][i]];
+            S.M[(size_t) i * ld + k] = d;
+            S.M[(size_t) i * ld + k + 1] = (double) S.rho[cur][i];
+            dmax = fmax(dmax, d);
+            dmin = fmin(dmin, d);
+        }
+        #pragma unroll
+        for(int off = 16; off > 0; off >>= 1) {
+            dmax = fmax(dmax, shfl_double(dmax, lane ^ off));
+            dmin = fmin(dmin, shfl_double(dmin, lane ^ off));
+        }
+        __syncwarp();
+        // ---- Gauss-Jordan with partial pivoting
+        bool singular = false;
+        for(int c = 0; c < k; c++) {
+            double best = -1.0;
+            int brow = c;
+            for(int r = c + (int) lane; r < k; r += 32) {
+                double v = fabs(S.M[(size_t) r * ld + c]);
+                if(v > best) { best = v; brow = r; }
+            }
+            #pragma unroll
+            for(int off = 16; off > 0; off >>= 1) {
+                double ob = shfl_double(best, lane ^ off);
+                int orow = __shfl_xor_sync(0xffffffffu, brow, off);
+                if(ob > best || (ob == best && orow < brow)) { best = ob; brow = orow; }
+            }
+            if(!(best > 0.0)) { singular = true; break; }
+            if(brow != c)
+                for(int j = (int) lane; j < ld; j += 32) {
+                    double t = S.M[(size_t) c * ld + j];
+                    S.M[(size_t) c * ld + j] = S.M[(size_t) brow * ld + j];
+                    S.M[(size_t) brow * ld + j] = t;
+                }
+            __syncwarp();
+            const double inv = 1.0 / S.M[(size_t) c * ld + c];
+            __syncwarp();
+            for(int j = (int) lane; j < ld; j += 32) S.M[(size_t) c * ld + j] *= inv;
+            __syncwarp();
+            for(int r = 0; r < k; r++) {
+                if(r == c) continue;
+                const double f = S.M[(size_t) r * ld + c];
+                __syncwarp();
+                if(f != 0.0)
+                    for(int j = (int) lane; j < ld; j += 32) S.M[(size_t) r * ld + j] = fma(-f, S.M[(size_t) c * ld + j], S.M[(size_t) r * ld + j]);
+                __syncwarp();
+            }
+        }
+        if(singular) {   // arma::inv would throw; leave the background
+            if(lane == 0) {
+                P.analysis[g] = bg;
+                if(P.analysis_variance) P.analysis_variance[g] = P.bvariance ? P.bvariance[g] : 1.f;
+            }
+            continue;
+        }
+        // dx = rho . (A^-1 d), a = rho . (A^-1 rho)   (oi.cpp:315-316,336)
+        double dx = 0.0, aa = 0.0;
+        for(int i = (int) lane; i < k; i += 32) {
+            double rho = (double) S.rho[cur][i];
+            dx = fma(rho, S.M[(size_t) i * ld + k], dx);
+            aa = fma(rho, S.M[(size_t) i * ld + k + 1], aa);
+        }
+        #pragma unroll
+        for(int off = 16; off > 0; off >>= 1) {
+            dx += shfl_double(dx, lane ^ off);
+            aa += shfl_double(aa, lane ^ off);
+        }
+        if(lane == 0) write_result(P, g, bg, dx, aa, dmax, dmin);
+        __syncwarp();
+    }
+}
+
+// Largest number of observations inside the localization radius of any background point; sizes the general
+// path when max_points is unlimited. One thread per background point.
+__global__ void oi_count_kernel(const float* __restrict__ gx, const float* __restrict__ gy, const float* __restrict__ gz,
+                                const float* __restrict__ background, int first, int count, ObsView obs, float R,
+                                int* __restrict__ out_max) {
+    int it = blockIdx.x * blockDim.x + threadIdx.x;
+    int n = 0;
+    if(it < count && is_valid(background[first + it])) {
+        int g = first + it;
+        float x = gx[g], y = gy[g], z = gz[g];
+        float lo0 = __fsub_rn(x, R), lo1 = __fsub_rn(y, R), lo2 = __fsub_rn(z, R);
+        float hi0 = __fadd_rn(x, R), hi1 = __fadd_rn(y, R), hi2 = __fadd_rn(z, R);
+        if(lo0 < hi0 && lo1 < hi1 && lo2 < hi2) {
+            int cx0 = cell_coord(obs.geom, 0, lo0), cx1 = cell_coord(obs.geom, 0, hi0);
+            int cy0 = cell_coord(obs.geom, 1, lo1), cy1 = cell_coord(obs.geom, 1, hi1);
+            int cz0 = cell_coord(obs.geom, 2, lo2), cz1 = cell_coord(obs.geom, 2, hi2);
+            for(int cz = cz0; cz <= cz1; cz++)
+                for(int cy = cy0; cy <= cy1; cy++) {
+                    int base = (cz * obs.geom.n[1] + cy) * obs.geom.n[0];
+                    for(int i = obs.cell_start[base + cx0]; i < obs.cell_start[base + cx1 + 1]; i++) {
+                        float ox = obs.x[i], oy = obs.y[i], oz = obs.z[i];
+                        if(ox > lo0 && ox < hi0 && oy > lo1 && oy < hi1 && oz > lo2 && oz < hi2 &&
+                           straight_distance(ox, oy, oz, x, y, z) <= R)
+                            n++;
+                    }
+                }
+        }
+    }
+    #pragma unroll
+    for(int off = 16; off > 0; off >>= 1) n = max(n, __shfl_xor_sync(0xffffffffu, n, off));
+    if(lane_id() == 0 && n > 0) atomicMax(out_max, n);
+}
+
+__global__ void copy_background_kernel(const float* __restrict__ background, const float* __restrict__ bvariance, int first,
+                                       int count, float* __restrict__ analysis, float* __restrict__ analysis_variance) {
+    int it = blockIdx.x * blockDim.x + threadIdx.x;
+    if(it >= count) return;
+    analysis[first + it] = background[first + it];
+    if(analysis_variance) analysis_variance[first + it] = bvariance ? bvariance[first + it] : 1.f;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------
+int gpp::build_obs_table(const gpp_points* op, const std::vector<char>& valid, const std::vector<double>& innov,
+                         const std::vector<float>& ratio, float loc_dist, gpp_oi_obs* out) {
+    const int nS = op->n;
+    out->n_total = nS;
+    out->loc_dist = loc_dist;
+    // bounding box of the valid observations
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    const std::vector<float>* co[3] = {&op->x, &op->y, &op->z};
+    int nv = 0;
+    for(int i = 0; i < nS; i++) {
+        if(!valid[i]) continue;
+        nv++;
+        for(int d = 0; d < 3; d++) {
+            lo[d] = std::min(lo[d], (*co[d])[i]);
+            hi[d] = std::max(hi[d], (*co[d])[i]);
+        }
+    }
+    out->n_valid = nv;
+    CellGeom& g = out->geom;
+    // cell edge = R/2: the box of side 2R then spans at most 5 cells per dimension
+    double edge = (is_valid(loc_dist) && loc_dist > 0) ? 0.5 * (double) loc_dist : 0.0;
+    long long total = 1;
+    double ext[3];
+    for(int d = 0; d < 3; d++) {
+        ext[d] = nv > 0 ? (double) hi[d] - (double) lo[d] : 0.0;
+        int c = 1;
+        if(edge > 0 && ext[d] > 0) c = (int) std::min(2048.0, std::max(1.0, std::ceil(ext[d] / edge)));
+        g.n[d] = c;
+        total *= c;
+    }
+    while(total > (1LL << 22)) {
+        int dmax = 0;
+        for(int d = 1; d < 3; d++) if(g.n[d] > g.n[dmax]) dmax = d;
+        total /= g.n[dmax];
+        g.n[dmax] = (g.n[dmax] + 1) / 2;
+        total *= g.n[dmax];
+    }
+    for(int d = 0; d < 3; d++) {
+        g.lo[d] = nv > 0 ? lo[d] : 0.f;
+        g.edge[d] = ext[d] > 0 ? (float) (ext[d] / g.n[d]) : 1.f;
+        g.inv[d] = ext[d] > 0 ? (float) (g.n[d] / ext[d]) : 0.f;
+    }
+    out->ncells = (int) total;
+    // stable counting sort by cell
+    std::vector<int> start(total + 1, 0), cell(nS, -1);
+    for(int i = 0; i < nS; i++) {
+        if(!valid[i]) continue;
+        int c = (cell_coord(g, 2, op->z[i]) * g.n[1] + cell_coord(g, 1, op->y[i])) * g.n[0] + cell_coord(g, 0, op->x[i]);
+        cell[i] = c;
+        start[c + 1]++;
+    }
+    for(long long c = 0; c < total; c++) start[c + 1] += start[c];
+    std::vector<int> fill(start.begin(), start.end() - 1), orig(std::max(nv, 1));
+    std::vector<float> sx(std::max(nv, 1)), sy(std::max(nv, 1)), sz(std::max(nv, 1)), se(std::max(nv, 1)), sl(std::max(nv, 1)),
+        sr(std::max(nv, 1));
+    std::vector<double> si(std::max(nv, 1));
+    for(int i = 0; i < nS; i++) {
+        if(!valid[i]) continue;
+        int slot = fill[cell[i]]++;
+        orig[slot] = i;
+        sx[slot] = op->x[i]; sy[slot] = op->y[i]; sz[slot] = op->z[i];
+        se[slot] = op->elevs[i]; sl[slot] = op->lafs[i];
+        sr[slot] = ratio[i];
+        si[slot] = innov[i];
+    }
+    GPP_TRY(out->cell_start.upload(start.data(), start.size()));
+    GPP_TRY(out->orig.upload(orig.data(), nv));
+    GPP_TRY(out->x.upload(sx.data(), nv));
+    GPP_TRY(out->y.upload(sy.data(), nv));
+    GPP_TRY(out->z.upload(sz.data(), nv));
+    GPP_TRY(out->elev.upload(se.data(), nv));
+    GPP_TRY(out->laf.upload(sl.data(), nv));
+    GPP_TRY(out->ratio.upload(sr.data(), nv));
+    GPP_TRY(out->innov.upload(si.data(), nv));
+    GPP_CUDA(cudaStreamSynchronize(0));   // the host staging vectors go out of scope
+    return GPP_OK;
+}
+
+namespace {
+int check_structure(const gpp_structure* s) {
+    if(!s) return fail(GPP_ERR_INVALID_ARGUMENT, "structure must not be NULL");
+    if(s->n_terms != 1 && s->n_terms != 3) return fail(GPP_ERR_INVALID_ARGUMENT, "structure.n_terms must be 1 or 3");
+    for(int t = 0; t < s->n_terms; t++)
+        if(s->term[t].type < GPP_STRUCT_BARNES || s->term[t].type > GPP_STRUCT_LINEAR)
+            return fail(GPP_ERR_INVALID_ARGUMENT, "unknown structure function type %d", s->term[t].type);
+    return GPP_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int gpp_oi_obs_create(const gpp_points* opoints, const float* pobs, const float* obs_variance, const float* pbackground,
+                      const float* bvariance_at_points, const gpp_structure* structure, gpp_oi_obs** out) {
+    if(!out) return fail(GPP_ERR_INVALID_ARGUMENT, "out must not be NULL");
+    *out = nullptr;
+    if(!opoints) return fail(GPP_ERR_INVALID_ARGUMENT, "points must not be NULL");
+    GPP_TRY(check_structure(structure));
+    GPP_TRY(ensure_device());
+    const int nS = opoints->n;
+    std::vector<char> valid(nS);
+    std::vector<double> innov(nS);
+    std::vector<float> ratio(nS);
+    for(int i = 0; i < nS; i++) {
+        // oi.cpp:252: observations with an invalid value or background never contribute
+        valid[i] = is_valid(pobs[i]) && is_valid(pbackground[i]);
+        innov[i] = (double) pobs[i] - (double) pbackground[i];                              // lObs - lY, oi.cpp:301-302,316
+        ratio[i] = obs_variance[i] / (bvariance_at_points ? bvariance_at_points[i] : 1.f);  // oi.cpp:192-195
+    }
+    gpp_oi_obs* o = new(std::nothrow) gpp_oi_obs();
+    if(!o) return fail(GPP_ERR_RUNTIME, "out of memory");
+    int rc = build_obs_table(opoints, valid, innov, ratio, structure->term[0].loc_dist, o);
+    if(rc != GPP_OK) { delete o; return rc; }
+    *out = o;
+    return GPP_OK;
+}
+
+void gpp_oi_obs_destroy(gpp_oi_obs* obs) { delete obs; }
+
+int gpp_optimal_interpolation_device(const gpp_points* cbp, int first, int count, const float* d_background,
+                                     const float* d_bvariance, const gpp_oi_obs* obs, const gpp_structure* structure,
+                                     int max_points, int allow_extrapolation, float* d_analysis, float* d_analysis_variance,
+                                     void* stream_) {
+    cudaStream_t stream = (cudaStream_t) stream_;
+    if(max_points < 0) return fail(GPP_ERR_INVALID_ARGUMENT, "max_points must be >= 0");   // oi.cpp:152
+    if(!cbp || !obs) return fail(GPP_ERR_INVALID_ARGUMENT, "points and observation state must not be NULL");
+    GPP_TRY(check_structure(structure));
+    gpp_points* bp = const_cast<gpp_points*>(cbp);
+    if(first < 0 || count < 0 || first + count > bp->n) return fail(GPP_ERR_INVALID_ARGUMENT, "background range out of bounds");
+    if(count == 0) return GPP_OK;
+    GPP_TRY(bp->ensure_on_device());
+    const unsigned blocks_copy = (unsigned) ((count + 255) / 256);
+    if(obs->n_valid == 0) {   // oi.cpp:189-190 and :234-237: nothing to assimilate
+        GPP_LAUNCH(copy_background_kernel, blocks_copy, 256, 0, stream, d_background, d_bvariance, first, count, d_analysis,
+                   d_analysis_variance);
+        return GPP_OK;
+    }
+    OiParams P;
+    P.gx = bp->dx.ptr; P.gy = bp->dy.ptr; P.gz = bp->dz.ptr; P.gelev = bp->delev.ptr; P.glaf = bp->dlaf.ptr;
+    P.background = d_background;
+    P.bvariance = d_bvariance;
+    P.analysis = d_analysis;
+    P.analysis_variance = d_analysis_variance;
+    P.first = first;
+    P.count = count;
+    P.obs = obs->view();
+    P.s = *structure;
+    P.R = structure->term[0].loc_dist;
+    P.allow_extrapolation = allow_extrapolation;
+
+    int kcap = max_points > 0 ? std::min(max_points, obs->n_valid) : obs->n_valid;
+    if(max_points == 0 && kcap > FAST_K) {
+        // unlimited: bound k by the largest neighbourhood actually present
+        DeviceBuffer<int> dmax;
+        GPP_TRY(dmax.alloc(1));
+        GPP_CUDA(cudaMemsetAsync(dmax.ptr, 0, sizeof(int), stream));
+        GPP_LAUNCH(oi_count_kernel, blocks_copy, 256, 0, stream, P.gx, P.gy, P.gz, d_background, first, count, P.obs, P.R, dmax.ptr);
+        int hmax = 0;
+        GPP_CUDA(cudaMemcpyAsync(&hmax, dmax.ptr, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        GPP_CUDA(cudaStreamSynchronize(stream));
+        kcap = std::min(kcap, std::max(hmax, 1));
+    }
+    P.k = kcap;
+    const int sms = sm_count();
+    if(kcap <= FAST_K && structure_is_symmetric(*structure)) {
+        const size_t smem = sizeof(FastSmem) * WARPS_PER_CTA;
+        static bool configured = false;
+        if(!configured) {
+            GPP_CUDA(cudaFuncSetAttribute(oi_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+            configured = true;
+        }
+        long long want = ((long long) count + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+        unsigned grid = (unsigned) std::min<long long>(want, (long long) sms * 2 * 8);   // a multiple of the SM count
+        GPP_LAUNCH(oi_fast_kernel, grid, WARPS_PER_CTA * 32, smem, stream, P);
+        return GPP_OK;
+    }
+    // general path
+    const size_t per_warp = scratch_bytes(kcap);
+    long long warps = (long long) sms * 2 * WARPS_PER_CTA;
+    const size_t budget = (size_t) 4 << 30;
+    if((size_t) warps * per_warp > budget) warps = std::max<long long>(WARPS_PER_CTA, (long long) (budget / per_warp) / WARPS_PER_CTA * WARPS_PER_CTA);
+    if((size_t) warps * per_warp > ((size_t) 64 << 30))
+        return fail(GPP_ERR_RUNTIME, "optimal_interpolation: %d observations per point need %zu bytes of scratch per warp", kcap, per_warp);
+    unsigned grid = (unsigned) std::min<long long>(warps / WARPS_PER_CTA, ((long long) count + WARPS_PER_CTA - 1) / WARPS_PER_CTA);
+    grid = std::max(grid, 1u);
+    unsigned char* scratch = nullptr;
+    GPP_CUDA(cudaMallocAsync((void**) &scratch, (size_t) grid * WARPS_PER_CTA * per_warp, stream));
+    oi_general_kernel<<<grid, WARPS_PER_CTA * 32, 0, stream>>>(P, scratch, per_warp, kcap);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t err = cudaGetLastError();
+    cudaFreeAsync(scratch, stream);
+    if(err != cudaSuccess) return fail(GPP_ERR_CUDA, "CUDA error %s launching oi_general_kernel: %s", cudaGetErrorName(err), cudaGetErrorString(err));
+    return GPP_OK;
+}
+
+int gpp_optimal_interpolation_host(const gpp_points* bpoints, const float* background, const float* bvariance,
+                                   const gpp_points* opoints, const float* pobs, const float* obs_variance,
+                                   const float* pbackground, const float* bvariance_at_points, const gpp_structure* structure,
+                                   int max_points, int allow_extrapolation, float* analysis, float* analysis_variance) {
+    // argument checks in the order of oi.cpp:151-186 (sizes are implied by the flat signature)
+    if(max_points < 0) return fail(GPP_ERR_INVALID_ARGUMENT, "max_points must be >= 0");
+    if(!bpoints || !opoints) return fail(GPP_ERR_INVALID_ARGUMENT, "points must not be NULL");
+    if(bpoints->type != opoints->type)
+        return fail(GPP_ERR_INVALID_ARGUMENT, "Both background points and observations points must be of same coordinate type (lat/lon or x/y)");
+    GPP_TRY(check_structure(structure));
+    GPP_TRY(ensure_device());
+    const int nB = bpoints->n, nS = opoints->n;
+    if(nS == 0 || nB == 0) {   // oi.cpp:189-190: analysis = background (analysis_variance left as bvariance)
+        if(nB > 0) std::memcpy(analysis, background, sizeof(float) * nB);
+        if(analysis_variance)
+            for(int i = 0; i < nB; i++) analysis_variance[i] = bvariance ? bvariance[i] : 1.f;
+        return GPP_OK;
+    }
+    gpp_oi_obs* obs = nullptr;
+    GPP_TRY(gpp_oi_obs_create(opoints, pobs, obs_variance, pbackground, bvariance_at_points, structure, &obs));
+    DeviceBuffer<float> d_bg, d_bvar, d_out, d_var;
+    int rc = d_bg.upload(background, nB);
+    if(rc == GPP_OK && bvariance) rc = d_bvar.upload(bvariance, nB);
+    if(rc == GPP_OK) rc = d_out.alloc(nB);
+    if(rc == GPP_OK && analysis_variance) rc = d_var.alloc(nB);
+    if(rc == GPP_OK)
+        rc = gpp_optimal_interpolation_device(bpoints, 0, nB, d_bg.ptr, bvariance ? d_bvar.ptr : nullptr, obs, structure, max_points,
+                                              allow_extrapolation, d_out.ptr, analysis_variance ? d_var.ptr : nullptr, nullptr);
+    if(rc == GPP_OK) rc = d_out.download(analysis, nB);
+    if(rc == GPP_OK && analysis_variance) rc = d_var.download(analysis_variance, nB);
+    if(rc == GPP_OK) {
+        cudaError_t err = cudaStreamSynchronize(0);
+        if(err != cudaSuccess) rc = fail(GPP_ERR_CUDA, "CUDA error %s: %s", cudaGetErrorName(err), cudaGetErrorString(err));
+    }
+    else cudaStreamSynchronize(0);
+    gpp_oi_obs_destroy(obs);
+    return rc;
+}
+
+}  // extern "C"

@@ -200,6 +200,9 @@ int gpp_neighbourhood_quantile_fast_device(const float* d_input, int n_rows_in, 
 /* ---------------------------------------------------------------- instrumentation -------------------- */
 /* Number of kernels this library has launched on the calling process so far (bench.py's gpu_launches). */
 unsigned long long gpp_kernel_launch_count(void);
+/* Measured fp64 FMA throughput of the current device in TFLOP/s (2 flops per FMA): the roofline denominator of
+ * the OI kernels, whose elimination runs on the fp64 CUDA cores. */
+int gpp_measure_fp64_fma_peak(double* tflops);
 
 #ifdef __cplusplus
 }

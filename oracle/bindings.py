@@ -294,18 +294,11 @@ def make_structure(stype=BARNES, h=0.0, v=0.0, w=0.0, hmax=float("nan"), min_rho
     t = s.term[0]
     t.type, t.h, t.v, t.w = stype, h, v, w
     if min_rho is None:
-        f32 = np.float32
-        min_rho = f32(0.0013)
-        if not np.isnan(hmax):
-            r = np.float64(f32(hmax) / f32(h))
-            if stype == BARNES:
-                min_rho = f32(np.exp(r ** 2 / -2))
-            elif stype == SOAR:
-                min_rho = f32((1 + f32(hmax) / f32(h)) * f32(np.exp(-(f32(hmax) / f32(h)))))
-            elif stype == TOAR:
-                min_rho = f32((1 + r + r ** 2 / 3) * np.exp(-r))
-            elif stype == POWERLAW:
-                min_rho = f32(1 / (1 + 0.5 * r ** 2))
+        # evaluated by the C oracle with the reference's own float/double mix (numpy's float32 exp is not glibc's expf)
+        out = C.c_float()
+        lib = load("oracle")
+        lib._check(lib._fn("structure_min_rho")(stype, C.c_float(h), C.c_float(v), C.c_float(w), C.c_float(hmax), C.byref(out)))
+        min_rho = out.value
     t.min_rho = float(min_rho)
     t.loc_dist = 0.0
     s.has_cv = 0

@@ -413,6 +413,15 @@ static int term_init(orc_term* t, int type, float h, float v, float w, float hma
     t->loc_dist = term_loc_dist(t);
     return 0;
 }
+/* m_min_rho as set by the constructors (not observable through the reference's public API; its effect, the
+ * localization distance, is) */
+int orc_structure_min_rho(int type, float h, float v, float w, float hmax, float* min_rho) {
+    orc_term t;
+    int rc = term_init(&t, type, h, v, w, hmax);
+    if(rc) return rc;
+    *min_rho = t.min_rho;
+    return 0;
+}
 int orc_structure_describe(int type, float h, float v, float w, float hmax, float* loc_dist) {
     orc_term t;
     int rc = term_init(&t, type, h, v, w, hmax);

@@ -1,0 +1,143 @@
+"""CPU-side checks of the product library: it loads, exports every symbol include/gridpp_b200.h declares, its
+host-only parts (structure descriptors, coordinate conversion, argument validation) agree with the oracle, and
+every compute entry point FAILS LOUDLY without a GPU (there is no CPU fallback)."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import bindings as B
+from util import assert_bit_exact, golden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+f32 = np.float32
+
+
+def _has_gpu(gpp):
+    return gpp.device_count() > 0
+
+
+def test_header_symbols_are_exported(gpp):
+    header = open(os.path.join(ROOT, "include", "gridpp_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(gpp_[a-z0-9_]+)\s*\(", header)))
+    assert len(declared) >= 25
+    from gridpp_b200 import _lib
+    for name in declared:
+        assert hasattr(_lib.lib, name), "libgridpp_b200.so does not export " + name
+    assert sorted(_lib.EXPORTS) == declared, "python prototypes and header disagree: %s" % (set(_lib.EXPORTS) ^ set(declared))
+
+
+def test_no_oracle_or_cpu_path_in_product():
+    """The product must not import, link or execute anything under oracle/."""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "gridpp_b200")):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                text = open(os.path.join(dirpath, fn)).read()
+                assert "oracle" not in text and "libgridpp_ref" not in text, fn
+                assert not re.search(r"^\s*(from|import)\s+oracle", text, flags=re.M), fn
+
+
+def test_structure_descriptors_match_oracle(gpp, orc):
+    classes = {B.BARNES: gpp.BarnesStructure, B.CRESSMAN: gpp.CressmanStructure, B.SOAR: gpp.SoarStructure,
+               B.TOAR: gpp.ToarStructure, B.POWERLAW: gpp.PowerlawStructure, B.LINEAR: gpp.LinearStructure}
+    rng = np.random.default_rng(3)
+    for st, cls in classes.items():
+        for h in list(rng.uniform(100, 1e5, 40).astype(f32)) + [2000.0, 10000.0]:
+            for hmax in (float("nan"), 0.0, 0.7 * float(h), 3.0 * float(h)):
+                s = cls(float(h), 100.0, 0.5) if st == B.CRESSMAN else cls(float(h), 100.0, 0.5, hmax)
+                want = orc.structure_describe(st, float(h), 100.0, 0.5, hmax)
+                got = s.localization_distance()
+                assert f32(got) == f32(want) or (np.isnan(got) and np.isnan(want)), (st, h, hmax, got, want)
+                o = B.make_structure(st, float(h), 100.0, 0.5, hmax)
+                assert f32(s._desc.term[0].min_rho) == f32(o.term[0].min_rho), (st, h, hmax)
+    # tests/test_structure.py:8-62 of the reference: constructor validation -> ValueError
+    for cls in (gpp.BarnesStructure, gpp.CressmanStructure):
+        for bad in (-1, np.nan):
+            with pytest.raises(ValueError):
+                cls(bad)
+            with pytest.raises(ValueError):
+                cls(2000, bad)
+            with pytest.raises(ValueError):
+                cls(2000, 100, bad)
+    with pytest.raises(ValueError):
+        gpp.BarnesStructure(2000, 100, 0, -1)
+    for dist in (-1, np.nan):
+        with pytest.raises(ValueError):
+            gpp.CrossValidation(gpp.BarnesStructure(2000), dist)
+    g = golden("structure")
+    assert f32(gpp.BarnesStructure(5000, 200, 0.5).localization_distance()) == g["barnes__loc_dist"]
+    m = gpp.MultipleStructure(gpp.BarnesStructure(5000), gpp.CressmanStructure(300, 300, 300), gpp.LinearStructure(0.3, 0.3, 0.3))
+    assert f32(m.localization_distance()) == g["multiple__loc_dist"]
+    assert f32(m.clone().localization_distance()) == g["multiple__loc_dist"]
+
+
+def test_points_coordinates_match_reference(gpp):
+    g = golden("index_queries")
+    for tname, t in (("geodetic", gpp.Geodetic), ("cartesian", gpp.Cartesian)):
+        p = gpp.Points(g[tname + "__lats"], g[tname + "__lons"], type=t)
+        for got, want in zip(p._set.xyz(), (g[tname + "__x"], g[tname + "__y"], g[tname + "__z"])):
+            assert_bit_exact(got, want, tname)
+        assert p.size() == 1500 and p.get_coordinate_type() == t
+        assert np.isnan(p.get_elevs()).all() and np.isnan(p.get_lafs()).all()     # points.cpp:23-30
+    # tests/test_kdtree.py:167-186 of the reference
+    for lat, lon in ((91, 0), (-91, 0), (np.nan, 0), (0, np.nan)):
+        with pytest.raises(ValueError):
+            gpp.KDTree([lat], [lon], gpp.Geodetic)
+    gpp.KDTree([0, 90.000001], [0, 0])
+    with pytest.raises(ValueError):
+        gpp.Points([0, 1], [0])
+    with pytest.raises(ValueError):
+        gpp.Points([0, 1], [0, 1], [1])
+    grid = gpp.Grid([[0, 0], [1, 1], [2, 2]], [[0, 1], [0, 1], [0, 1]])
+    assert grid.size().tolist() == [3, 2] and grid.to_points().size() == 6
+    assert gpp.Grid().size().tolist() == [0, 0] and gpp.Points().size() == 0
+
+
+def test_argument_validation(gpp):
+    """tests/test_optimal_interpolation.py:9-47 of the reference: every size mismatch raises ValueError (checked
+    before any device work, so this runs without a GPU)."""
+    y, x = np.meshgrid(np.arange(3) * 1000.0, np.arange(4) * 1000.0, indexing="ij")
+    grid = gpp.Grid(y, x, type=gpp.Cartesian)
+    points = gpp.Points([0, 1000], [0, 1000], type=gpp.Cartesian)
+    s = gpp.BarnesStructure(2500)
+    ok = dict(bgrid=grid, background=np.zeros((3, 4)), points=points, pobs=[1, 2], pratios=[0.5, 0.5], pbackground=[0, 0],
+              structure=s, max_points=5)
+    bad = dict(background=[np.zeros((3, 3)), np.zeros((2, 4)), np.zeros(12)], pobs=[[1], [1, 2, 3]], pratios=[[1], [1, 2, 3]],
+               pbackground=[[1], [1, 2, 3]], max_points=[-1], points=[gpp.Points([0, 1], [0, 1])])
+    for key, values in bad.items():
+        for v in values:
+            args = dict(ok)
+            args[key] = v
+            with pytest.raises(ValueError):
+                gpp.optimal_interpolation(*args.values())
+    with pytest.raises(ValueError):
+        gpp.neighbourhood(np.ones((5, 5)), -1, gpp.Mean)
+    with pytest.raises(ValueError):
+        gpp.neighbourhood(np.ones((5, 5)), 1, gpp.Quantile)
+    with pytest.raises(ValueError):
+        gpp.neighbourhood_quantile_fast(np.ones((5, 5)), 0.5, -1, [0, 1])
+    assert gpp.neighbourhood([[]], 1, gpp.Mean).shape == (0, 0)
+    assert gpp.neighbourhood_quantile_fast([[]], 0.9, 1, [0, 1]).shape == (0, 0)
+    with pytest.raises(ValueError):
+        gpp.nearest(grid, points, np.zeros((2, 2)))
+
+
+def test_compute_fails_loudly_without_gpu(gpp):
+    if _has_gpu(gpp):
+        pytest.skip("a GPU is present; the no-fallback behaviour is only observable on a CPU box")
+    y, x = np.meshgrid(np.arange(3) * 1000.0, np.arange(4) * 1000.0, indexing="ij")
+    grid = gpp.Grid(y, x, type=gpp.Cartesian)
+    points = gpp.Points([0, 1000], [0, 1000], type=gpp.Cartesian)
+    calls = [
+        lambda: gpp.neighbourhood(np.ones((4, 4)), 1, gpp.Mean),
+        lambda: gpp.neighbourhood_quantile_fast(np.ones((4, 4)), 0.5, 1, [0, 1]),
+        lambda: gpp.optimal_interpolation(grid, np.zeros((3, 4)), points, [1, 2], [0.5, 0.5], [0, 0], gpp.BarnesStructure(2500), 5),
+        lambda: gpp.nearest(grid, points, np.zeros((3, 4))),
+        lambda: points.get_nearest_neighbour(0, 0),
+        lambda: gpp.BarnesStructure(2500).corr([[0, 0, 0, 0, 0]], [[0, 1, 0, 0, 0]]),
+    ]
+    for call in calls:
+        with pytest.raises(RuntimeError, match="no usable CUDA device"):
+            call()
