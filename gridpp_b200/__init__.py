@@ -133,10 +133,11 @@ class _PointSet:
         nq = lats.size
         radii = _np.ascontiguousarray(_np.broadcast_to(_np.asarray(radii, _np.float32), (nq,)))
         count = _np.zeros(nq, _np.int32)
-        if capacity is None:
+        if capacity is None or capacity == 0:
             _check(_libc.gpp_points_neighbours_host(self._handle, _fptr(lats), _fptr(lons), _fptr(radii), nq,
                                                     int(include_match), 0, None, None, _iptr(count)))
-            capacity = int(count.max()) if nq else 0
+            if capacity is None:
+                capacity = int(count.max()) if nq else 0
         idx = _np.full((nq, capacity), -1, _np.int32)
         dist = _np.full((nq, capacity), _np.nan, _np.float32) if with_distance else None
         if capacity > 0:

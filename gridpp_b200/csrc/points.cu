@@ -464,7 +464,10 @@ int gpp_points_neighbours_host(const gpp_points* cp, const float* qlats, const f
     GPP_TRY(dr.upload(radii, nq));
     GPP_TRY(dcount.alloc(nq));
     bool store = capacity > 0 && out_index;
-    if(store) GPP_TRY(dindex.alloc((size_t) nq * capacity));
+    if(store) {
+        GPP_TRY(dindex.alloc((size_t) nq * capacity));
+        GPP_CUDA(cudaMemsetAsync(dindex.ptr, 0xFF, sizeof(int) * (size_t) nq * capacity, 0));   // unused slots read -1
+    }
     const CellIndex& ix = p->index;
     GPP_LAUNCH(radius_kernel, blocks_for(nq, 128), 128, 0, 0, dqx.ptr, dqy.ptr, dqz.ptr, dr.ptr, nq, ix.geom, ix.cell_start.ptr,
                ix.order.ptr, ix.sx.ptr, ix.sy.ptr, ix.sz.ptr, include_match, capacity, store ? dindex.ptr : nullptr, nullptr,
@@ -474,6 +477,7 @@ int gpp_points_neighbours_host(const gpp_points* cp, const float* qlats, const f
         GPP_TRY(dindex.download(out_index, (size_t) nq * capacity));
         if(out_dist) {
             GPP_TRY(ddist.alloc((size_t) nq * capacity));
+            GPP_CUDA(cudaMemsetAsync(ddist.ptr, 0xFF, sizeof(float) * (size_t) nq * capacity, 0));   // unused slots read NaN
             GPP_LAUNCH(radius_dist_kernel, blocks_for((size_t) nq * capacity, 256), 256, 0, 0, dqx.ptr, dqy.ptr, dqz.ptr, nq,
                        p->dx.ptr, p->dy.ptr, p->dz.ptr, capacity, dindex.ptr, dcount.ptr, ddist.ptr);
             GPP_TRY(ddist.download(out_dist, (size_t) nq * capacity));
