@@ -102,7 +102,7 @@ class _PointSet:
 
     def __del__(self):
         h = getattr(self, "_handle", None)
-        if h:
+        if h and _libc is not None:   # _libc is None during interpreter shutdown
             _libc.gpp_points_destroy(h)
             self._handle = None
 

@@ -16,6 +16,17 @@ int ensure_device() {
         return fail(GPP_ERR_CUDA, "no usable CUDA device (%s); libgridpp_b200 has no CPU fallback",
                     err == cudaSuccess ? "device count is 0" : cudaGetErrorString(err));
     }
+    // keep freed blocks in the stream-ordered pool instead of returning them to the driver (once per device)
+    static bool pool_ready[64] = {false};
+    int dev = 0;
+    if(cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64 && !pool_ready[dev]) {
+        cudaMemPool_t pool;
+        if(cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            unsigned long long threshold = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+        }
+        pool_ready[dev] = true;
+    }
     return GPP_OK;
 }
 int sm_count() {

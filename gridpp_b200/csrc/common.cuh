@@ -8,6 +8,8 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
+#include <ctime>
 #include <new>
 #include <string>
 #include <vector>
@@ -52,10 +54,35 @@ inline int fail(int code, const char* fmt, ...) {
         GPP_CUDA(cudaGetLastError());                                     \
     } while(0)
 
+// Opt-in phase timing of the host entry points: GPP_TRACE=1 prints wall-clock milliseconds per phase to stderr.
+struct Trace {
+    bool on;
+    double t0;
+    const char* what;
+    static double now() {
+        timespec ts;
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+    }
+    explicit Trace(const char* w) : what(w) {
+        static const bool enabled = getenv("GPP_TRACE") != nullptr;
+        on = enabled;
+        t0 = on ? now() : 0;
+    }
+    void lap(const char* phase) {
+        if(!on) return;
+        double t = now();
+        fprintf(stderr, "[gpp trace] %s: %s %.3f ms\n", what, phase, t - t0);
+        t0 = t;
+    }
+};
+
 int ensure_device();       // GPP_OK when a CUDA device is usable, else GPP_ERR_CUDA (no CPU fallback exists)
 int sm_count();            // multiprocessors of the current device (148 on B200)
 
-// RAII device buffer
+// RAII device buffer. Allocations come from the device's default stream-ordered memory pool, whose release
+// threshold ensure_device() raises so that freed blocks stay cached: cudaMalloc/cudaFree of 64 MB fields were
+// measured at up to 130 ms per call on the B200 box (profiles/e2e_probe.py), which dwarfed the kernels.
 template <class T>
 struct DeviceBuffer {
     T* ptr = nullptr;
@@ -65,7 +92,7 @@ struct DeviceBuffer {
     DeviceBuffer& operator=(const DeviceBuffer&) = delete;
     ~DeviceBuffer() { release(); }
     void release() {
-        if(ptr) cudaFree(ptr);
+        if(ptr) cudaFreeAsync(ptr, 0);
         ptr = nullptr;
         count = 0;
     }
@@ -73,7 +100,7 @@ struct DeviceBuffer {
         if(n <= count && ptr) return GPP_OK;
         release();
         if(n == 0) n = 1;
-        GPP_CUDA(cudaMalloc((void**) &ptr, n * sizeof(T)));
+        GPP_CUDA(cudaMallocAsync((void**) &ptr, n * sizeof(T), 0));
         count = n;
         return GPP_OK;
     }

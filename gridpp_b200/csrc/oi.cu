@@ -4,13 +4,13 @@
 // One warp analyses one background point:
 //   1. gather: scan the bucket-grid cells overlapping the localization box, keep observations strictly inside
 //      the box with straight distance <= R and rho > 0 (oi.cpp:229-258, kdtree.cpp:39-62), streaming top-k by
-//      (rho, index) in shared memory (oi.cpp:262-273);
-//   2. assemble P + R for the k selected observations from pairwise structure-function evaluations
-//      (oi.cpp:298-314), packed over the 32 lanes;
+//      (rho, index) in shared memory (oi.cpp:262-273); put the selection in canonical (index) order;
+//   2. if the selection differs from the one the warp solved last: assemble P + R from pairwise structure-function
+//      evaluations (oi.cpp:298-314) packed over the 32 lanes, then
 //   3. eliminate: lane j holds row j of the symmetric augmented matrix [[P+R, rho, d], [rho', 0, 0], [d', 0, 0]]
-//      in registers (fp64). k steps of symmetric Gaussian elimination leave -rho'(P+R)^-1 rho and
-//      -rho'(P+R)^-1 d in the trailing 2x2 block, i.e. the analysis-variance factor and the increment of
-//      oi.cpp:315-317,336-337, without ever forming the inverse.
+//      in registers (fp64). k Gauss-Jordan steps give z = (P+R)^-1 d (one component per lane) and leave
+//      -rho'(P+R)^-1 rho in the trailing block (the analysis-variance factor, oi.cpp:336-337);
+//   4. increment = rho . z (oi.cpp:315-317) -- no inverse is ever formed.
 // The register path covers symmetric structure functions with k <= 30. Everything else (k > 30, unlimited
 // max_points, non-symmetric structure functions) takes the general kernel: Gauss-Jordan with partial pivoting
 // on a per-warp global-memory scratch matrix.
@@ -58,113 +58,169 @@ __device__ __forceinline__ void write_result(const OiParams& P, int g, float bg,
     }
 }
 
+constexpr int RUN = 16;             // consecutive background points analysed by one warp (solution reuse, see below)
+constexpr int NPAIR_LUT = 496;      // 31 * 32 / 2 >= FAST_K * (FAST_K + 1) / 2
+
 struct FastSmem {
-    float cand_rho[64];
-    int cand_pos[64];
-    int cand_orig[64];
+    unsigned long long key[64];     // candidate keys (oi.cuh)
+    double M[32 * 33];              // augmented symmetric matrix, row-major with stride 33
+    double colbuf[2][32];           // pivot column broadcast, double-buffered
+    double sd[32];                  // innovations of the selection
+    int pos[64];                    // candidate slots in the observation table
+    int c_pos[32];                  // the selection in canonical order (ascending original index)
+    int c_orig[32];
+    float c_rho[32];
     float sx[32], sy[32], sz[32], selev[32], slaf[32];
     float sratio[32];
-    double sd[32];
-    double colbuf[2][32];
-    float A[32 * 33];
 };
 
+// One warp per background point; a warp walks RUN consecutive points.
+//
+// Solution reuse: neighbouring points usually select the SAME set of observations (the set only changes when the
+// point crosses a boundary of the order-k Voronoi diagram of the observations). With the selection put in a
+// canonical order (ascending original index), z = (P+R)^-1 d depends on the set alone and the increment is the
+// k-term dot product rho . z (oi.cpp:315-316: lG * inv(lP+lR) * (lObs - lY)). The warp keeps (set, z) of the last
+// system it solved; when the next point selects the same set, assembly and elimination are skipped. Every point
+// computes its increment with the same dot product, so results do not depend on where a run starts. The analysis
+// variance needs rho'(P+R)^-1 rho, which depends on the point: when it is requested every point is eliminated.
+template <int SMODE>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 2) oi_fast_kernel(const __grid_constant__ OiParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FastSmem& S = reinterpret_cast<FastSmem*>(smem_raw)[threadIdx.x >> 5];
+    unsigned short* lut = reinterpret_cast<unsigned short*>(smem_raw + sizeof(FastSmem) * WARPS_PER_CTA);
     const unsigned lane = lane_id();
     const int warp_global = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
     const int warps_total = gridDim.x * WARPS_PER_CTA;
-    CandBuf cb = {S.cand_rho, S.cand_pos, S.cand_orig};
+    const CandBuf cb = {S.key, S.pos};
+    const bool need_var = P.analysis_variance != nullptr;
 
-    for(int it = warp_global; it < P.count; it += warps_total) {
-        const int g = P.first + it;
-        const float bg = P.background[g];
-        if(!is_valid(bg)) {   // oi.cpp:223
-            if(lane == 0) {
-                P.analysis[g] = bg;
-                if(P.analysis_variance) P.analysis_variance[g] = P.bvariance ? P.bvariance[g] : 1.f;
+    // pair index p -> (row j, column i <= j) of the lower triangle, packed over the lanes during assembly
+    for(int p = threadIdx.x; p < NPAIR_LUT; p += blockDim.x) {
+        int j = (int) ((sqrtf(8.f * (float) p + 1.f) - 1.f) * 0.5f);
+        while(j * (j + 1) / 2 > p) j--;
+        while((j + 1) * (j + 2) / 2 <= p) j++;
+        lut[p] = (unsigned short) ((j << 8) | (p - j * (j + 1) / 2));
+    }
+    for(int e = (int) lane; e < 32 * 33; e += 32) S.M[e] = 0.0;
+    __syncthreads();
+    int dirty = 0;            // rows / columns [0, dirty) and 30, 31 of M may hold non-zero values
+    int prev_orig = -2, prev_k = -1;
+    double z = 0.0, dmax = 0.0, dmin = 0.0, avar = 0.0;
+
+    const int n_runs = (P.count + RUN - 1) / RUN;
+    for(int run = warp_global; run < n_runs; run += warps_total) {
+        const int it_end = min((run + 1) * RUN, P.count);
+        for(int it = run * RUN; it < it_end; it++) {
+            const int g = P.first + it;
+            const float bg = P.background[g];
+            int k = 0;
+            Pt p1 = {0.f, 0.f, 0.f, 0.f, 0.f};
+            if(is_valid(bg)) {   // oi.cpp:223
+                p1 = {P.gx[g], P.gy[g], P.gz[g], P.gelev[g], P.glaf[g]};
+                k = gather_candidates<SMODE>(P.obs, P.s, p1, P.R, P.k, cb);
             }
-            continue;
-        }
-        const Pt p1 = {P.gx[g], P.gy[g], P.gz[g], P.gelev[g], P.glaf[g]};
-        const int k = gather_candidates(P.obs, P.s, p1, P.R, P.k, cb);
-        if(k == 0) {          // oi.cpp:234-237,284-287
-            if(lane == 0) {
-                P.analysis[g] = bg;
-                if(P.analysis_variance) P.analysis_variance[g] = P.bvariance ? P.bvariance[g] : 1.f;
-            }
-            continue;
-        }
-        // ---- stage the selected observations
-        if((int) lane < k) {
-            int pos = S.cand_pos[lane];
-            S.sx[lane] = P.obs.x[pos]; S.sy[lane] = P.obs.y[pos]; S.sz[lane] = P.obs.z[pos];
-            S.selev[lane] = P.obs.elev[pos]; S.slaf[lane] = P.obs.laf[pos];
-            S.sratio[lane] = P.obs.ratio[pos];
-            S.sd[lane] = P.obs.innov[pos];
-        }
-        __syncwarp();
-        // ---- pairwise correlations, lower triangle incl. diagonal, packed over the lanes (oi.cpp:298-314)
-        const int npairs = k * (k + 1) / 2;
-        for(int p = (int) lane; p < npairs; p += 32) {
-            int j = (int) ((sqrtf(8.f * (float) p + 1.f) - 1.f) * 0.5f);
-            while(j * (j + 1) / 2 > p) j--;
-            while((j + 1) * (j + 2) / 2 <= p) j++;
-            int i = p - j * (j + 1) / 2;
-            Pt a = {S.sx[j], S.sy[j], S.sz[j], S.selev[j], S.slaf[j]};
-            Pt b = {S.sx[i], S.sy[i], S.sz[i], S.selev[i], S.slaf[i]};
-            S.A[j * 33 + i] = structure_corr(P.s, a, b);
-        }
-        __syncwarp();
-        // ---- row `lane` of the augmented matrix into registers
-        double a[32];
-        {
-            const bool is_row = (int) lane < k;
-            const float my_ratio = is_row ? S.sratio[lane] : 0.f;
-            #pragma unroll
-            for(int i = 0; i < 30; i++) {
-                double v = 0.0;
-                if(i < k) {
-                    if(is_row) {
-                        int hi = max((int) lane, i), lo = min((int) lane, i);
-                        v = (double) S.A[hi * 33 + lo];
-                        if(i == (int) lane) v = __dadd_rn(v, (double) my_ratio);   // lP + lR, oi.cpp:315
-                    }
-                    else if(lane == 30) v = (double) S.cand_rho[i];
-                    else if(lane == 31) v = S.sd[i];
+            if(k == 0) {         // oi.cpp:223,234-237,284-287: the analysis stays at the background
+                if(lane == 0) {
+                    P.analysis[g] = bg;
+                    if(need_var) P.analysis_variance[g] = P.bvariance ? P.bvariance[g] : 1.f;
                 }
-                a[i] = v;
+                continue;
             }
-            a[30] = is_row ? (double) S.cand_rho[lane] : 0.0;
-            a[31] = is_row ? S.sd[lane] : 0.0;
-        }
-        // max / min innovation for the optional clamp (oi.cpp:319-320)
-        double dmax = (int) lane < k ? S.sd[lane] : -INFINITY, dmin = (int) lane < k ? S.sd[lane] : INFINITY;
-        if(!P.allow_extrapolation) {
-            #pragma unroll
-            for(int off = 16; off > 0; off >>= 1) {
-                dmax = fmax(dmax, shfl_double(dmax, lane ^ off));
-                dmin = fmin(dmin, shfl_double(dmin, lane ^ off));
-            }
-        }
-        // ---- symmetric elimination of the k observation rows
-        #pragma unroll
-        for(int c = 0; c < FAST_K; c++) {
-            if(c < k) {
-                const double my = a[c];
-                const double piv = shfl_double(my, c);
-                S.colbuf[c & 1][lane] = my;
-                const double f = my * (1.0 / piv);
+            // ---- canonical order of the selection: ascending original index
+            {
+                const unsigned long long my_key = (int) lane < k ? S.key[lane] : 0ull;
+                const int my_pos = (int) lane < k ? S.pos[lane] : 0;
+                const unsigned my_inv = (unsigned) my_key;    // 0x7fffffff - original index
+                int crank = 0;
+                const unsigned* lo_words = reinterpret_cast<const unsigned*>(S.key);
+                #pragma unroll 4
+                for(int m = 0; m < k; m++) crank += lo_words[2 * m] > my_inv;
+                if((int) lane < k) {
+                    S.c_orig[crank] = cand_key_orig(my_key);
+                    S.c_rho[crank] = cand_key_rho(my_key);
+                    S.c_pos[crank] = my_pos;
+                }
                 __syncwarp();
-                #pragma unroll
-                for(int i = c + 1; i < 32; i++)
-                    if(i >= 30 || i < k) a[i] = fma(-f, S.colbuf[c & 1][i], a[i]);
             }
+            const int c_orig = (int) lane < k ? S.c_orig[lane] : -1;
+            const float c_rho = (int) lane < k ? S.c_rho[lane] : 0.f;
+            const bool same = __all_sync(0xffffffffu, c_orig == prev_orig) && k == prev_k;
+            if(!same || need_var) {
+                // ---- stage the selected observations
+                if((int) lane < k) {
+                    const int pos = S.c_pos[lane];
+                    S.sx[lane] = P.obs.x[pos]; S.sy[lane] = P.obs.y[pos]; S.sz[lane] = P.obs.z[pos];
+                    S.selev[lane] = P.obs.elev[pos]; S.slaf[lane] = P.obs.laf[pos];
+                    S.sratio[lane] = P.obs.ratio[pos];
+                    S.sd[lane] = P.obs.innov[pos];
+                }
+                if(k < dirty) {   // keep everything outside [0,k) U {30,31} at zero
+                    for(int i = k; i < dirty; i++) S.M[lane * 33 + i] = 0.0;
+                    if((int) lane >= k && (int) lane < dirty)
+                        for(int i = 0; i < 32; i++) S.M[lane * 33 + i] = 0.0;
+                }
+                dirty = k;
+                __syncwarp();
+                // ---- pairwise correlations (oi.cpp:298-314), lower triangle incl. diagonal packed over the lanes
+                const int npairs = k * (k + 1) / 2;
+                for(int p = (int) lane; p < npairs; p += 32) {
+                    const int code = lut[p];
+                    const int j = code >> 8, i = code & 255;
+                    const Pt a = {S.sx[j], S.sy[j], S.sz[j], S.selev[j], S.slaf[j]};
+                    const Pt b = {S.sx[i], S.sy[i], S.sz[i], S.selev[i], S.slaf[i]};
+                    const float hdist = straight_distance(a.x, a.y, a.z, b.x, b.y, b.z);
+                    double v = (double) corr_mode<SMODE>(P.s, a, b, hdist);
+                    if(i == j) v = __dadd_rn(v, (double) S.sratio[j]);   // lP + lR, oi.cpp:315
+                    S.M[j * 33 + i] = v;
+                    S.M[i * 33 + j] = v;
+                }
+                if((int) lane < k) {
+                    const double r = (double) c_rho, d = S.sd[lane];
+                    S.M[30 * 33 + lane] = r; S.M[lane * 33 + 30] = r;
+                    S.M[31 * 33 + lane] = d; S.M[lane * 33 + 31] = d;
+                }
+                // max / min innovation for the optional clamp (oi.cpp:319-320)
+                dmax = (int) lane < k ? S.sd[lane] : -INFINITY;
+                dmin = (int) lane < k ? S.sd[lane] : INFINITY;
+                #pragma unroll
+                for(int off = 16; off > 0; off >>= 1) {
+                    dmax = fmax(dmax, shfl_double(dmax, lane ^ off));
+                    dmin = fmin(dmin, shfl_double(dmin, lane ^ off));
+                }
+                __syncwarp();
+                // ---- row `lane` of [[P+R, rho, d], [rho', 0, 0], [d', 0, 0]] into registers
+                double a[32];
+                #pragma unroll
+                for(int i = 0; i < 32; i++) a[i] = S.M[lane * 33 + i];
+                // ---- Gauss-Jordan on the k observation rows, pivots on the diagonal (SPD: no pivoting needed).
+                // By symmetry of the not-yet-eliminated block the pivot ROW equals the pivot COLUMN, which is spread
+                // over the lanes: one shared store per lane broadcasts it.
+                double my_inv = 0.0;
+                #pragma unroll
+                for(int c = 0; c < FAST_K; c++) {
+                    if(c < k) {
+                        const double my = a[c];
+                        const double inv = __drcp_rn(shfl_double(my, c));
+                        S.colbuf[c & 1][lane] = my;
+                        const double f = (int) lane == c ? 0.0 : my * inv;
+                        if((int) lane == c) my_inv = inv;
+                        __syncwarp();
+                        #pragma unroll
+                        for(int i = c + 1; i < 32; i++) a[i] = fma(-f, S.colbuf[c & 1][i], a[i]);
+                    }
+                }
+                z = (int) lane < k ? a[31] * my_inv : 0.0;          // z = (P+R)^-1 d, one component per lane
+                if(need_var) avar = -shfl_double(a[30], 30);        // rho'(P+R)^-1 rho (oi.cpp:336)
+                prev_orig = c_orig;
+                prev_k = k;
+            }
+            // ---- increment = rho . z  (oi.cpp:315-317)
+            double dx = (double) c_rho * z;
+            #pragma unroll
+            for(int off = 16; off > 0; off >>= 1) dx += shfl_double(dx, lane ^ off);
+            if(lane == 0) write_result(P, g, bg, dx, avar, dmax, dmin);
+            __syncwarp();
         }
-        // lane 30 now holds -rho'(P+R)^-1 rho in a[30] and -rho'(P+R)^-1 d in a[31]
-        if(lane == 30) write_result(P, g, bg, -a[31], -a[30], dmax, dmin);
-        __syncwarp();
     }
 }
 
@@ -569,15 +625,15 @@ int gpp_optimal_interpolation_device(const gpp_points* cbp, int first, int count
     P.k = kcap;
     const int sms = sm_count();
     if(kcap <= FAST_K && structure_is_symmetric(*structure)) {
-        const size_t smem = sizeof(FastSmem) * WARPS_PER_CTA;
-        static bool configured = false;
-        if(!configured) {
-            GPP_CUDA(cudaFuncSetAttribute(oi_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-            configured = true;
-        }
-        long long want = ((long long) count + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-        unsigned grid = (unsigned) std::min<long long>(want, (long long) sms * 2 * 8);   // a multiple of the SM count
-        GPP_LAUNCH(oi_fast_kernel, grid, WARPS_PER_CTA * 32, smem, stream, P);
+        const size_t smem = sizeof(FastSmem) * WARPS_PER_CTA + sizeof(unsigned short) * 512;
+        const int mode = structure_mode(*structure);
+        GPP_CUDA(cudaFuncSetAttribute(oi_fast_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        GPP_CUDA(cudaFuncSetAttribute(oi_fast_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        const long long runs = ((long long) count + RUN - 1) / RUN;
+        const long long want = (runs + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+        const unsigned grid = (unsigned) std::max<long long>(1, std::min<long long>(want, (long long) sms * 2));   // 2 resident CTAs per SM
+        if(mode == 1) GPP_LAUNCH(oi_fast_kernel<1>, grid, WARPS_PER_CTA * 32, smem, stream, P);
+        else GPP_LAUNCH(oi_fast_kernel<0>, grid, WARPS_PER_CTA * 32, smem, stream, P);
         return GPP_OK;
     }
     // general path
@@ -617,16 +673,20 @@ int gpp_optimal_interpolation_host(const gpp_points* bpoints, const float* backg
             for(int i = 0; i < nB; i++) analysis_variance[i] = bvariance ? bvariance[i] : 1.f;
         return GPP_OK;
     }
+    Trace trace("optimal_interpolation_host");
     gpp_oi_obs* obs = nullptr;
     GPP_TRY(gpp_oi_obs_create(opoints, pobs, obs_variance, pbackground, bvariance_at_points, structure, &obs));
+    trace.lap("observation table");
     DeviceBuffer<float> d_bg, d_bvar, d_out, d_var;
     int rc = d_bg.upload(background, nB);
     if(rc == GPP_OK && bvariance) rc = d_bvar.upload(bvariance, nB);
     if(rc == GPP_OK) rc = d_out.alloc(nB);
     if(rc == GPP_OK && analysis_variance) rc = d_var.alloc(nB);
+    if(trace.on) { cudaStreamSynchronize(0); trace.lap("alloc + H2D"); }
     if(rc == GPP_OK)
         rc = gpp_optimal_interpolation_device(bpoints, 0, nB, d_bg.ptr, bvariance ? d_bvar.ptr : nullptr, obs, structure, max_points,
                                               allow_extrapolation, d_out.ptr, analysis_variance ? d_var.ptr : nullptr, nullptr);
+    if(trace.on) { cudaStreamSynchronize(0); trace.lap("kernels"); }
     if(rc == GPP_OK) rc = d_out.download(analysis, nB);
     if(rc == GPP_OK && analysis_variance) rc = d_var.download(analysis_variance, nB);
     if(rc == GPP_OK) {
@@ -634,7 +694,10 @@ int gpp_optimal_interpolation_host(const gpp_points* bpoints, const float* backg
         if(err != cudaSuccess) rc = fail(GPP_ERR_CUDA, "CUDA error %s: %s", cudaGetErrorName(err), cudaGetErrorString(err));
     }
     else cudaStreamSynchronize(0);
+    trace.lap("D2H");
     gpp_oi_obs_destroy(obs);
+    d_bg.release(); d_bvar.release(); d_out.release(); d_var.release();
+    trace.lap("free");
     return rc;
 }
 

@@ -46,7 +46,7 @@ class ObservationState:
 
     def __del__(self):
         h = getattr(self, "_handle", None)
-        if h:
+        if h and _libc is not None:
             _libc.gpp_oi_obs_destroy(h)
             self._handle = None
 
