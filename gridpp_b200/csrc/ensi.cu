@@ -1,7 +1,379 @@
-// Ensemble optimal interpolation (EnSI) -- placeholder until the kernel lands.
+// Ensemble optimal interpolation (EnSI, Lussana et al. 2019) on the device ("K7"/"K8" in SURVEY.md).
+// Replaces gridpp::optimal_interpolation_ensi, src/api/oi_ensi.cpp:33-568.
+//
+// One warp per background point, lane e <-> valid ensemble member e (E <= 32), at most 64 observations per point:
+//   1. gather / top-k exactly as the deterministic OI (oi_ensi.cpp:207-269; only pobs validity is tested, :232);
+//   2. Pinv = Y' Rinv Y + (E-1) I, E x E symmetric (oi_ensi.cpp:296-385), one row per lane, fp64;
+//   3. ONE symmetric eigen-decomposition Pinv = V L V' (parallel-order cyclic Jacobi in shared memory) replaces the
+//      reference's inv() + eig_sym((E-1) P) pair (oi_ensi.cpp:398-401): P = V L^-1 V', sqrt((E-1) P) = V sqrt((E-1)/L) V';
+//   4. w = P C (obs - yhat), W = sqrtm + w 1' (oi_ensi.cpp:419-444), analysis_e = mean + sum_k X_k W_ke with the
+//      reference's FLOAT accumulation over k (oi_ensi.cpp:506-512), optional clamp (:517-551, including the linear
+//      index lY[e] of :523-524), written to member validEns[e].
+// The reference runs this loop serially (its omp pragma is disabled, oi_ensi.cpp:203-206).
 #include "oi.cuh"
 
-extern "C" int gpp_optimal_interpolation_ensi_host(const gpp_points*, const float*, int, const gpp_points*, const float*,
-                                                   const float*, const float*, const gpp_structure*, int, int, float*, int*) {
-    return gpp::fail(GPP_ERR_NOT_IMPLEMENTED, "optimal_interpolation_ensi is not implemented on the device yet");
+#include <algorithm>
+#include <cstring>
+
+using namespace gpp;
+
+namespace {
+
+constexpr int ENSI_WARPS = 4;
+constexpr int ENSI_KMAX = 64;     // observations per point
+constexpr int ENSI_EMAX = 32;     // valid ensemble members
+constexpr int ENSI_NSLOT = 3;     // candidate buffer = 96 entries
+constexpr int LD = 33;            // leading dimension of the shared matrices
+
+struct EnsiParams {
+    const float *gx, *gy, *gz, *gelev, *glaf;
+    const float* background;      // nB x nE, member fastest
+    float* analysis;              // nB x nE, pre-filled with the background
+    int first, count, nE, E;
+    int valid_ens[ENSI_EMAX];
+    ObsView obs;                  // ratio := psigma, innov := (double) pobs - (double) yhat
+    const float* gY;              // [table slot][E]: pbackground minus its ensemble mean, valid members only
+    gpp_structure s;
+    float R;
+    int k;
+    int allow_extrapolation;
+    int* num_skipped;
+};
+
+struct EnsiSmem {
+    unsigned long long key[32 * ENSI_NSLOT];
+    double Y[ENSI_KMAX * LD];     // lY, k x E
+    double A[ENSI_EMAX * LD];     // Pinv, then its diagonalisation
+    double V[ENSI_EMAX * LD];     // eigenvectors in columns
+    double rinv[ENSI_KMAX], dd[ENSI_KMAX];
+    double b[ENSI_EMAX], t[ENSI_EMAX], lam[ENSI_EMAX], w[ENSI_EMAX], sc[ENSI_EMAX], X[ENSI_EMAX];
+    double cs[ENSI_EMAX / 2], sn[ENSI_EMAX / 2];
+    int pos[32 * ENSI_NSLOT];
+    int spos[ENSI_KMAX];
+    int pp[ENSI_EMAX / 2], qq[ENSI_EMAX / 2];
+    float sval[ENSI_EMAX];
+};
+
+// members with an invalid value anywhere in the background are left untouched (oi_ensi.cpp:187-201)
+__global__ void ensi_invalid_members_kernel(const float* __restrict__ background, size_t n, int nE, int* __restrict__ invalid) {
+    size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) return;
+    if(!is_valid(background[i])) atomicOr(&invalid[i % nE], 1);
+}
+
+template <int SMODE>
+__global__ void __launch_bounds__(ENSI_WARPS * 32) ensi_kernel(const __grid_constant__ EnsiParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    EnsiSmem& S = reinterpret_cast<EnsiSmem*>(smem_raw)[threadIdx.x >> 5];
+    const int lane = (int) lane_id();
+    const int warp_global = blockIdx.x * ENSI_WARPS + (threadIdx.x >> 5);
+    const int warps_total = gridDim.x * ENSI_WARPS;
+    const CandBuf cb = {S.key, S.pos};
+    const int E = P.E;
+    const int Eeven = E + (E & 1), m = Eeven - 1;   // round-robin schedule over an even number of indices
+
+    for(int it = warp_global; it < P.count; it += warps_total) {
+        const int g = P.first + it;
+        const Pt p1 = {P.gx[g], P.gy[g], P.gz[g], P.gelev[g], P.glaf[g]};
+        bool cut = false;
+        const int k = gather_candidates<SMODE, ENSI_NSLOT>(P.obs, P.s, p1, P.R, P.k, cb, &cut);
+        if(k == 0) continue;   // oi_ensi.cpp:210-214,265-269: too few observations, keep the background
+        // ---- order of the local observations: best-first when the selection was cut to max_points
+        // (oi_ensi.cpp:244-255; the prune leaves exactly that order), otherwise the order of the radius query =
+        // ascending index (oi_ensi.cpp:256-263). The order matters for the linear index lY[e] of the clamp.
+        if(!cut) {
+            const unsigned long long k0 = lane < k ? S.key[lane] : 0ull, k1 = lane + 32 < k ? S.key[lane + 32] : 0ull;
+            const int p0 = lane < k ? S.pos[lane] : 0, p1s = lane + 32 < k ? S.pos[lane + 32] : 0;
+            // ascending original index = descending low word of the key
+            const unsigned* lo_words = reinterpret_cast<const unsigned*>(S.key);
+            int r0 = 0, r1 = 0;
+            for(int j = 0; j < k; j++) {
+                const unsigned lw = lo_words[2 * j];
+                r0 += lw > (unsigned) k0;
+                r1 += lw > (unsigned) k1;
+            }
+            __syncwarp();
+            if(lane < k) { S.key[r0] = k0; S.pos[r0] = p0; }
+            if(lane + 32 < k) { S.key[r1] = k1; S.pos[r1] = p1s; }
+            __syncwarp();
+        }
+        // ---- stage lY (oi_ensi.cpp:282-294), Rinv (:296-302), obs - yhat (:434-437)
+        for(int i = lane; i < k; i += 32) {
+            const int pos = S.pos[i];
+            S.spos[i] = pos;
+            const float sigma = P.obs.ratio[pos];
+            S.rinv[i] = (double) cand_key_rho(S.key[i]) / (double) __fmul_rn(sigma, sigma);
+            S.dd[i] = P.obs.innov[pos];
+        }
+        __syncwarp();
+        for(int idx = lane; idx < k * E; idx += 32) {
+            const int i = idx / E, e = idx - i * E;
+            S.Y[i * LD + e] = (double) P.gY[(size_t) S.spos[i] * E + e];
+        }
+        __syncwarp();
+        // ---- Pinv = C * lY + diag * I, C = lY' Rinv (oi_ensi.cpp:379-385); row `lane`
+        {
+            double acc[ENSI_EMAX];
+            #pragma unroll
+            for(int f = 0; f < ENSI_EMAX; f++) acc[f] = 0.0;
+            if(lane < E)
+                for(int i = 0; i < k; i++) {
+                    const double c = S.Y[i * LD + lane] * S.rinv[i];
+                    #pragma unroll
+                    for(int f = 0; f < ENSI_EMAX; f++)
+                        if(f < E) acc[f] = fma(c, S.Y[i * LD + f], acc[f]);
+                }
+            const float diag = (float) (E - 1);   // oi_ensi.cpp:383 with delta = 1
+            #pragma unroll
+            for(int f = 0; f < ENSI_EMAX; f++)
+                if(f < E && lane < E) {
+                    S.A[lane * LD + f] = acc[f] + (f == lane ? (double) diag : 0.0);
+                    S.V[lane * LD + f] = f == lane ? 1.0 : 0.0;
+                }
+        }
+        __syncwarp();
+        // ---- cyclic Jacobi, parallel (round-robin) ordering: E/2 disjoint rotations per round
+        bool bad = false;
+        for(int sweep = 0; sweep < 30; sweep++) {
+            double off = 0.0, dg = 0.0;
+            if(lane < E)
+                for(int f = 0; f < E; f++) {
+                    const double v = S.A[lane * LD + f];
+                    if(f == lane) dg += v * v; else off += v * v;
+                }
+            #pragma unroll
+            for(int o = 16; o > 0; o >>= 1) { off += shfl_double(off, lane ^ o); dg += shfl_double(dg, lane ^ o); }
+            if(!(off == off) || !(dg == dg) || isinf(off) || isinf(dg)) { bad = true; break; }
+            if(off <= 1e-30 * dg) break;
+            for(int r = 0; r < m; r++) {
+                if(lane < Eeven / 2) {
+                    int p, q;
+                    if(lane == 0) { p = m; q = r; }
+                    else { p = (r + lane) % m; q = (r - lane + m) % m; }
+                    if(p > q) { int tmp = p; p = q; q = tmp; }
+                    double c = 1.0, s = 0.0;
+                    if(q < E) {
+                        const double apq = S.A[p * LD + q];
+                        if(apq != 0.0) {
+                            const double theta = (S.A[q * LD + q] - S.A[p * LD + p]) / (2.0 * apq);
+                            const double tt = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                            c = 1.0 / sqrt(tt * tt + 1.0);
+                            s = tt * c;
+                        }
+                    }
+                    else { p = 0; q = 0; }   // pair with the padding index: identity
+                    S.pp[lane] = p; S.qq[lane] = q; S.cs[lane] = c; S.sn[lane] = s;
+                }
+                __syncwarp();
+                if(lane < E)   // rows p, q of A, column `lane`
+                    for(int t = 0; t < Eeven / 2; t++) {
+                        const int p = S.pp[t], q = S.qq[t];
+                        if(p == q) continue;
+                        const double c = S.cs[t], s = S.sn[t];
+                        const double ap = S.A[p * LD + lane], aq = S.A[q * LD + lane];
+                        S.A[p * LD + lane] = c * ap - s * aq;
+                        S.A[q * LD + lane] = s * ap + c * aq;
+                    }
+                __syncwarp();
+                if(lane < E)   // columns p, q of A and of V, row `lane`
+                    for(int t = 0; t < Eeven / 2; t++) {
+                        const int p = S.pp[t], q = S.qq[t];
+                        if(p == q) continue;
+                        const double c = S.cs[t], s = S.sn[t];
+                        const double ap = S.A[lane * LD + p], aq = S.A[lane * LD + q];
+                        S.A[lane * LD + p] = c * ap - s * aq;
+                        S.A[lane * LD + q] = s * ap + c * aq;
+                        const double vp = S.V[lane * LD + p], vq = S.V[lane * LD + q];
+                        S.V[lane * LD + p] = c * vp - s * vq;
+                        S.V[lane * LD + q] = s * vp + c * vq;
+                    }
+                __syncwarp();
+            }
+        }
+        // eigenvalues of Pinv; rcond(Pinv) <= 0 in the reference (oi_ensi.cpp:386-390) <=> not positive definite / not finite
+        double lam = lane < E ? S.A[lane * LD + lane] : 1.0;
+        bad = bad || __any_sync(0xffffffffu, !(lam > 0.0) || isinf(lam));
+        if(bad) {
+            if(lane == 0) atomicAdd(P.num_skipped, 1);
+            continue;
+        }
+        if(lane < E) {
+            S.lam[lane] = lam;
+            S.sc[lane] = sqrt((double) (E - 1) / lam);   // sqrt of the eigenvalues of (E-1) P, oi_ensi.cpp:401,419
+            // b = C (obs - yhat)
+            double b = 0.0;
+            for(int i = 0; i < k; i++) b = fma(S.Y[i * LD + lane] * S.rinv[i], S.dd[i], b);
+            S.b[lane] = b;
+            // X: background perturbations about the ensemble mean (oi_ensi.cpp:447-462), float mean
+            S.sval[lane] = P.background[(size_t) g * P.nE + P.valid_ens[lane]];
+        }
+        __syncwarp();
+        float total = 0.f;
+        for(int e = 0; e < E; e++) total = __fadd_rn(total, S.sval[e]);
+        const float ensMean = __fdiv_rn(total, (float) E);
+        if(lane < E) {
+            S.X[lane] = (double) S.sval[lane] - (double) ensMean;
+            double t = 0.0;   // t = V' b
+            for(int e = 0; e < E; e++) t = fma(S.V[e * LD + lane], S.b[e], t);
+            S.t[lane] = t / lam;
+        }
+        __syncwarp();
+        if(lane < E) {
+            double w = 0.0;   // w = P C (obs - yhat) = V L^-1 V' b  (oi_ensi.cpp:428-437)
+            for(int f = 0; f < E; f++) w = fma(S.V[lane * LD + f], S.t[f], w);
+            S.w[lane] = w;
+        }
+        __syncwarp();
+        if(lane < E) {
+            // analysis for member `lane`: total += X(k) * W(k, e) accumulated in FLOAT (oi_ensi.cpp:506-512),
+            // W(k, e) = sum_f V(k,f) sqrt((E-1)/lam_f) V(e,f) + w(k)  (oi_ensi.cpp:419-444)
+            float tot = 0.f;
+            for(int kk = 0; kk < E; kk++) {
+                double wke = 0.0;
+                for(int f = 0; f < E; f++) wke = fma(S.V[kk * LD + f] * S.sc[f], S.V[lane * LD + f], wke);
+                wke += S.w[kk];
+                tot = (float) ((double) tot + S.X[kk] * wke);
+            }
+            float currIncrement = tot;
+            if(!P.allow_extrapolation) {   // oi_ensi.cpp:517-551
+                // lY[e] is a LINEAR index into the column-major k x E matrix: row e % k, column e / k (:523-524)
+                const double lYe = S.Y[(lane % k) * LD + (lane / k)];
+                double mx = -INFINITY, mn = INFINITY;
+                for(int i = 0; i < k; i++) {
+                    const double v = S.dd[i] - lYe;
+                    mx = fmax(mx, v);
+                    mn = fmin(mn, v);
+                }
+                const float maxInc = (float) mx, minInc = (float) mn;
+                const float memberIncrement = (float) ((double) currIncrement - S.X[lane]);
+                if(maxInc > 0 && memberIncrement > maxInc) currIncrement = (float) ((double) maxInc + S.X[lane]);
+                else if(maxInc < 0 && memberIncrement > 0) currIncrement = (float) (0.0 + S.X[lane]);
+                else if(minInc < 0 && memberIncrement < minInc) currIncrement = (float) ((double) minInc + S.X[lane]);
+                else if(minInc > 0 && memberIncrement < 0) currIncrement = (float) (0.0 + S.X[lane]);
+            }
+            P.analysis[(size_t) g * P.nE + P.valid_ens[lane]] = __fadd_rn(ensMean, currIncrement);
+        }
+        __syncwarp();
+    }
+}
+
+// util.cpp:19-43, Mean branch of calc_statistic: float accumulation over the valid values
+float mean_valid(const float* a, int n) {
+    float total = 0;
+    int count = 0;
+    for(int i = 0; i < n; i++)
+        if(is_valid(a[i])) { total += a[i]; count++; }
+    return count > 0 ? total / count : NAN;
+}
+
+}  // namespace
+
+extern "C" int gpp_optimal_interpolation_ensi_host(const gpp_points* cbp, const float* background, int nE, const gpp_points* opoints,
+                                                   const float* pobs, const float* psigmas, const float* pbackground,
+                                                   const gpp_structure* structure, int max_points, int allow_extrapolation,
+                                                   float* analysis, int* num_skipped) {
+    if(num_skipped) *num_skipped = 0;
+    if(max_points < 0) return fail(GPP_ERR_INVALID_ARGUMENT, "max_points must be >= 0");   // oi_ensi.cpp:124-125
+    if(!cbp || !opoints || !structure) return fail(GPP_ERR_INVALID_ARGUMENT, "NULL argument");
+    if(nE < 0) return fail(GPP_ERR_INVALID_ARGUMENT, "negative ensemble size");
+    gpp_points* bp = const_cast<gpp_points*>(cbp);
+    const int nB = bp->n, nS = opoints->n;
+    const size_t nBE = (size_t) nB * nE;
+    if(nS == 0) {   // oi_ensi.cpp:137-139
+        if(nBE) std::memcpy(analysis, background, sizeof(float) * nBE);
+        return GPP_OK;
+    }
+    if(bp->type != opoints->type)
+        return fail(GPP_ERR_INVALID_ARGUMENT, "Both background and observations points must be of same coorindate type (lat/lon or x/y)");
+    GPP_TRY(ensure_device());
+    if(nBE == 0) return GPP_OK;
+    Trace trace("optimal_interpolation_ensi_host");
+
+    // ---- observation side on the host (oi_ensi.cpp:163-178): remove the ensemble mean at the observation points
+    std::vector<float> gY(pbackground, pbackground + (size_t) nS * nE), gYhat(nS);
+    for(int i = 0; i < nS; i++) {
+        float mean = mean_valid(&gY[(size_t) i * nE], nE);
+        for(int e = 0; e < nE; e++) {
+            float value = gY[(size_t) i * nE + e];
+            if(is_valid(value) && is_valid(mean)) gY[(size_t) i * nE + e] -= mean;
+        }
+        gYhat[i] = mean;
+    }
+    // ---- valid members (oi_ensi.cpp:187-201): a full pass over the background, on the device
+    DeviceBuffer<float> d_bg, d_out, d_gY;
+    DeviceBuffer<int> d_flags;
+    GPP_TRY(d_bg.upload(background, nBE));
+    GPP_TRY(d_flags.alloc(nE + 1));
+    GPP_CUDA(cudaMemsetAsync(d_flags.ptr, 0, sizeof(int) * (nE + 1), 0));
+    GPP_LAUNCH(ensi_invalid_members_kernel, (unsigned) ((nBE + 255) / 256), 256, 0, 0, d_bg.ptr, nBE, nE, d_flags.ptr);
+    std::vector<int> flags(nE + 1);
+    GPP_TRY(d_flags.download(flags.data(), nE + 1));
+    GPP_CUDA(cudaStreamSynchronize(0));
+    trace.lap("H2D + valid-member scan");
+    EnsiParams P;
+    std::memset(&P, 0, sizeof(P));
+    int E = 0;
+    for(int e = 0; e < nE; e++)
+        if(!flags[e]) {
+            if(E >= ENSI_EMAX)
+                return fail(GPP_ERR_NOT_IMPLEMENTED, "optimal_interpolation_ensi supports at most %d valid ensemble members on the device", ENSI_EMAX);
+            P.valid_ens[E++] = e;
+        }
+    GPP_TRY(d_out.alloc(nBE));
+    GPP_CUDA(cudaMemcpyAsync(d_out.ptr, d_bg.ptr, sizeof(float) * nBE, cudaMemcpyDeviceToDevice, 0));   // oi_ensi.cpp:148
+    if(E > 0) {
+        // ---- observation table: only pobs validity is required here (oi_ensi.cpp:232)
+        std::vector<char> valid(nS);
+        std::vector<double> innov(nS);
+        std::vector<float> sig(psigmas, psigmas + nS);
+        for(int i = 0; i < nS; i++) {
+            valid[i] = is_valid(pobs[i]);
+            innov[i] = (double) pobs[i] - (double) gYhat[i];   // lObs - lYhat, oi_ensi.cpp:437
+        }
+        gpp_oi_obs obs;
+        std::vector<int> order;
+        GPP_TRY(build_obs_table(opoints, valid, innov, sig, structure->term[0].loc_dist, &obs, &order));
+        std::vector<float> gYs(std::max<size_t>(1, order.size() * (size_t) E));
+        for(size_t slot = 0; slot < order.size(); slot++)
+            for(int e = 0; e < E; e++) gYs[slot * E + e] = gY[(size_t) order[slot] * nE + P.valid_ens[e]];
+        GPP_TRY(d_gY.upload(gYs.data(), gYs.size()));
+        GPP_TRY(bp->ensure_on_device());
+        if(obs.n_valid > 0) {
+            P.gx = bp->dx.ptr; P.gy = bp->dy.ptr; P.gz = bp->dz.ptr; P.gelev = bp->delev.ptr; P.glaf = bp->dlaf.ptr;
+            P.background = d_bg.ptr;
+            P.analysis = d_out.ptr;
+            P.first = 0; P.count = nB; P.nE = nE; P.E = E;
+            P.obs = obs.view();
+            P.gY = d_gY.ptr;
+            P.s = *structure;
+            P.R = structure->term[0].loc_dist;
+            P.allow_extrapolation = allow_extrapolation;
+            P.num_skipped = d_flags.ptr + nE;
+            int kcap = max_points > 0 ? std::min(max_points, obs.n_valid) : obs.n_valid;
+            if(max_points == 0 && kcap > ENSI_KMAX) {
+                int hmax = 0;
+                GPP_TRY(count_max_candidates(bp, 0, nB, nullptr, P.obs, P.R, 0, &hmax));
+                kcap = std::min(kcap, std::max(hmax, 1));
+            }
+            if(kcap > ENSI_KMAX)
+                return fail(GPP_ERR_NOT_IMPLEMENTED, "optimal_interpolation_ensi supports at most %d observations per point on the device (got %d)", ENSI_KMAX, kcap);
+            P.k = kcap;
+            const size_t smem = sizeof(EnsiSmem) * ENSI_WARPS;
+            GPP_CUDA(cudaFuncSetAttribute(ensi_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+            GPP_CUDA(cudaFuncSetAttribute(ensi_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+            const long long want = ((long long) nB + ENSI_WARPS - 1) / ENSI_WARPS;
+            const unsigned grid = (unsigned) std::max<long long>(1, std::min<long long>(want, (long long) sm_count() * 4));
+            if(structure_mode(*structure) == 1) GPP_LAUNCH(ensi_kernel<1>, grid, ENSI_WARPS * 32, smem, 0, P);
+            else GPP_LAUNCH(ensi_kernel<0>, grid, ENSI_WARPS * 32, smem, 0, P);
+        }
+        if(trace.on) { cudaStreamSynchronize(0); trace.lap("kernel"); }
+        GPP_TRY(d_out.download(analysis, nBE));
+        if(num_skipped) GPP_CUDA(cudaMemcpyAsync(num_skipped, d_flags.ptr + nE, sizeof(int), cudaMemcpyDeviceToHost, 0));
+        GPP_CUDA(cudaStreamSynchronize(0));   // `obs` and the staging vectors go out of scope after this
+        trace.lap("D2H");
+        return GPP_OK;
+    }
+    GPP_TRY(d_out.download(analysis, nBE));
+    GPP_CUDA(cudaStreamSynchronize(0));
+    return GPP_OK;
 }

@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 2) oi_fast_kernel(const __
             Pt p1 = {0.f, 0.f, 0.f, 0.f, 0.f};
             if(is_valid(bg)) {   // oi.cpp:223
                 p1 = {P.gx[g], P.gy[g], P.gz[g], P.gelev[g], P.glaf[g]};
-                k = gather_candidates<SMODE>(P.obs, P.s, p1, P.R, P.k, cb);
+                k = gather_candidates<SMODE, 2>(P.obs, P.s, p1, P.R, P.k, cb);
             }
             if(k == 0) {         // oi.cpp:223,234-237,284-287: the analysis stays at the background
                 if(lane == 0) {
@@ -424,7 +424,7 @@ __global__ void oi_count_kernel(const float* __restrict__ gx, const float* __res
                                 int* __restrict__ out_max) {
     int it = blockIdx.x * blockDim.x + threadIdx.x;
     int n = 0;
-    if(it < count && is_valid(background[first + it])) {
+    if(it < count && (!background || is_valid(background[first + it]))) {
         int g = first + it;
         float x = gx[g], y = gy[g], z = gz[g];
         float lo0 = __fsub_rn(x, R), lo1 = __fsub_rn(y, R), lo2 = __fsub_rn(z, R);
@@ -462,7 +462,7 @@ __global__ void copy_background_kernel(const float* __restrict__ background, con
 
 // ---------------------------------------------------------------------------------------------------------
 int gpp::build_obs_table(const gpp_points* op, const std::vector<char>& valid, const std::vector<double>& innov,
-                         const std::vector<float>& ratio, float loc_dist, gpp_oi_obs* out) {
+                         const std::vector<float>& ratio, float loc_dist, gpp_oi_obs* out, std::vector<int>* order) {
     const int nS = op->n;
     out->n_total = nS;
     out->loc_dist = loc_dist;
@@ -526,6 +526,7 @@ int gpp::build_obs_table(const gpp_points* op, const std::vector<char>& valid, c
         sr[slot] = ratio[i];
         si[slot] = innov[i];
     }
+    if(order) order->assign(orig.begin(), orig.begin() + nv);
     GPP_TRY(out->cell_start.upload(start.data(), start.size()));
     GPP_TRY(out->orig.upload(orig.data(), nv));
     GPP_TRY(out->x.upload(sx.data(), nv));
@@ -536,6 +537,18 @@ int gpp::build_obs_table(const gpp_points* op, const std::vector<char>& valid, c
     GPP_TRY(out->ratio.upload(sr.data(), nv));
     GPP_TRY(out->innov.upload(si.data(), nv));
     GPP_CUDA(cudaStreamSynchronize(0));   // the host staging vectors go out of scope
+    return GPP_OK;
+}
+
+int gpp::count_max_candidates(gpp_points* bp, int first, int count, const float* d_background, const ObsView& obs, float R,
+                              cudaStream_t stream, int* out) {
+    DeviceBuffer<int> dmax;
+    GPP_TRY(dmax.alloc(1));
+    GPP_CUDA(cudaMemsetAsync(dmax.ptr, 0, sizeof(int), stream));
+    GPP_LAUNCH(oi_count_kernel, (unsigned) ((count + 255) / 256), 256, 0, stream, bp->dx.ptr, bp->dy.ptr, bp->dz.ptr, d_background, first,
+               count, obs, R, dmax.ptr);
+    GPP_CUDA(cudaMemcpyAsync(out, dmax.ptr, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    GPP_CUDA(cudaStreamSynchronize(stream));
     return GPP_OK;
 }
 
@@ -613,13 +626,8 @@ int gpp_optimal_interpolation_device(const gpp_points* cbp, int first, int count
     int kcap = max_points > 0 ? std::min(max_points, obs->n_valid) : obs->n_valid;
     if(max_points == 0 && kcap > FAST_K) {
         // unlimited: bound k by the largest neighbourhood actually present
-        DeviceBuffer<int> dmax;
-        GPP_TRY(dmax.alloc(1));
-        GPP_CUDA(cudaMemsetAsync(dmax.ptr, 0, sizeof(int), stream));
-        GPP_LAUNCH(oi_count_kernel, blocks_copy, 256, 0, stream, P.gx, P.gy, P.gz, d_background, first, count, P.obs, P.R, dmax.ptr);
         int hmax = 0;
-        GPP_CUDA(cudaMemcpyAsync(&hmax, dmax.ptr, sizeof(int), cudaMemcpyDeviceToHost, stream));
-        GPP_CUDA(cudaStreamSynchronize(stream));
+        GPP_TRY(count_max_candidates(bp, first, count, d_background, P.obs, P.R, stream, &hmax));
         kcap = std::min(kcap, std::max(hmax, 1));
     }
     P.k = kcap;

@@ -33,42 +33,52 @@ __device__ __forceinline__ float cand_key_rho(unsigned long long key) { return _
 __device__ __forceinline__ int cand_key_orig(unsigned long long key) { return 0x7fffffff - (int) (unsigned) key; }
 __device__ __forceinline__ bool cand_better(float r1, int o1, float r2, int o2) { return r1 > r2 || (r1 == r2 && o1 < o2); }
 
-// Rank-select the best min(n, k) of the first n entries (n <= 64), best first. Each lane owns entries lane, lane+32.
+// Rank-select the best min(n, k) of the first n entries (n <= 32 * NSLOT), best first. Each lane owns entries
+// lane, lane + 32, ...
+template <int NSLOT>
 __device__ __forceinline__ int cand_prune(const CandBuf& b, int n, int k) {
     const unsigned lane = lane_id();
-    const bool h0 = (int) lane < n, h1 = (int) lane + 32 < n;
-    const unsigned long long k0 = h0 ? b.key[lane] : 0ull, k1 = h1 ? b.key[lane + 32] : 0ull;
-    const int p0 = h0 ? b.pos[lane] : 0, p1 = h1 ? b.pos[lane + 32] : 0;
-    int rank0 = 0, rank1 = 0;
-    if(n > 32) {
+    unsigned long long key[NSLOT];
+    int pos[NSLOT], rank[NSLOT];
+    #pragma unroll
+    for(int t = 0; t < NSLOT; t++) {
+        const bool has = (int) lane + 32 * t < n;
+        key[t] = has ? b.key[lane + 32 * t] : 0ull;
+        pos[t] = has ? b.pos[lane + 32 * t] : 0;
+        rank[t] = 0;
+    }
+    if(n <= 32) {
         #pragma unroll 4
-        for(int j = 0; j < n; j++) {
-            const unsigned long long kj = b.key[j];
-            rank0 += kj > k0;
-            rank1 += kj > k1;
-        }
+        for(int j = 0; j < n; j++) rank[0] += b.key[j] > key[0];
     }
     else {
-        #pragma unroll 4
-        for(int j = 0; j < n; j++) rank0 += b.key[j] > k0;
+        #pragma unroll 2
+        for(int j = 0; j < n; j++) {
+            const unsigned long long kj = b.key[j];
+            #pragma unroll
+            for(int t = 0; t < NSLOT; t++) rank[t] += kj > key[t];
+        }
     }
     __syncwarp();
-    if(h0 && rank0 < k) { b.key[rank0] = k0; b.pos[rank0] = p0; }
-    if(h1 && rank1 < k) { b.key[rank1] = k1; b.pos[rank1] = p1; }
+    #pragma unroll
+    for(int t = 0; t < NSLOT; t++)
+        if((int) lane + 32 * t < n && rank[t] < k) { b.key[rank[t]] = key[t]; b.pos[rank[t]] = pos[t]; }
     __syncwarp();
     return min(n, k);
 }
 
-// Scans the bucket-grid cells overlapping the localization box of p1 and keeps the k best observations.
-// Warp-synchronous; every lane returns the same count (<= k <= 32). On return the buffer holds the selection
-// best-first. Invalid observations are not in the table (oi.cpp:252).
-template <int SMODE>
+// Scans the bucket-grid cells overlapping the localization box of p1 and keeps the k best observations
+// (k <= 32 * (NSLOT - 1)). Warp-synchronous; every lane returns the same count. The buffer (capacity 32 * NSLOT)
+// holds the selection on return, best-first when a prune ran. Invalid observations are not in the table.
+template <int SMODE, int NSLOT>
 __device__ __forceinline__ int gather_candidates(const ObsView& obs, const gpp_structure& s, const Pt& p1, float R, int k,
-                                                 const CandBuf& b) {
+                                                 const CandBuf& b, bool* cut = nullptr) {
     const unsigned lane = lane_id();
+    bool did_prune = false;   // more candidates than k: the selection was cut and is sorted best-first
     // kdtree.cpp:46-47: box corners are computed in float
     const float lo0 = __fsub_rn(p1.x, R), lo1 = __fsub_rn(p1.y, R), lo2 = __fsub_rn(p1.z, R);
     const float hi0 = __fadd_rn(p1.x, R), hi1 = __fadd_rn(p1.y, R), hi2 = __fadd_rn(p1.z, R);
+    if(cut) *cut = false;
     if(!(lo0 < hi0 && lo1 < hi1 && lo2 < hi2)) return 0;
     const int cx0 = cell_coord(obs.geom, 0, lo0), cx1 = cell_coord(obs.geom, 0, hi0);
     const int cy0 = cell_coord(obs.geom, 1, lo1), cy1 = cell_coord(obs.geom, 1, hi1);
@@ -104,10 +114,11 @@ __device__ __forceinline__ int gather_candidates(const ObsView& obs, const gpp_s
                 }
                 n += __popc(mask);
                 __syncwarp();
-                if(n > 32) n = cand_prune(b, n, k);   // keep room for the next 32
+                if(n > 32 * (NSLOT - 1)) { n = cand_prune<NSLOT>(b, n, k); did_prune = true; }   // keep room for the next 32
             }
         }
-    if(n > k) n = cand_prune(b, n, k);   // final selection (oi.cpp:262-273)
+    if(n > k) { n = cand_prune<NSLOT>(b, n, k); did_prune = true; }   // final selection (oi.cpp:262-273)
+    if(cut) *cut = did_prune;
     return n;
 }
 
@@ -138,6 +149,11 @@ struct gpp_oi_obs {
 
 namespace gpp {
 // Builds the table from host arrays. `valid[i]` selects the observations that enter the table.
+// Largest number of table observations inside the localization radius of any of the background points
+// [first, first+count) (points with an invalid d_background value are skipped when d_background is given).
+int count_max_candidates(gpp_points* bp, int first, int count, const float* d_background, const ObsView& obs, float R,
+                         cudaStream_t stream, int* out);
+// `order`, when given, receives the original index of every table slot (what `orig` holds on the device).
 int build_obs_table(const gpp_points* opoints, const std::vector<char>& valid, const std::vector<double>& innov,
-                    const std::vector<float>& ratio, float loc_dist, gpp_oi_obs* out);
+                    const std::vector<float>& ratio, float loc_dist, gpp_oi_obs* out, std::vector<int>* order = nullptr);
 }

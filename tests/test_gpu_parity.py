@@ -444,3 +444,71 @@ def test_full_size_oi_subsample_equals_oracle(gpp, orc):
     idx = orc.points_nearest(y[:400, :], x[:400, :], B.CARTESIAN, np.minimum(py[sub], 399 * dx), px[sub])
     got = grid._set.nearest(np.minimum(py[sub], 399 * dx), px[sub])
     assert_bit_exact(got, idx, "nearest on the 16M-node grid")
+
+
+# ------------------------------------------------------------------ ensemble OI (EnSI) ------------------
+def test_ensi_golden(gpp):
+    g = golden("ensi_c5_density")
+    grid = gpp.Grid(g["y"], g["x"], type=gpp.Cartesian)
+    points = gpp.Points(g["py"], g["px"], type=gpp.Cartesian)
+    s = product_structure(gpp, parse_spec(g["structure"]))
+    scale = float(np.std(g["background"]))
+    for name in ("mp20", "mp20_clamp", "unlimited"):
+        mp, extr = (int(v) for v in g[name + "__args"])
+        out = gpp.optimal_interpolation_ensi(grid, g["background"], points, g["pobs"], g["psigmas"], g["pbackground"], s, mp, bool(extr))
+        assert out.shape == g["background"].shape and out.dtype == np.float32
+        assert_close(out, g[name + "__analysis"], scale, RTOL, "EnSI " + name)
+
+
+def test_ensi_known_answers(gpp):
+    # tests/test_optimal_interpolation_ens.py:9-35 of the reference
+    rng = np.random.default_rng(2)
+    y, x = np.meshgrid(np.arange(6) * 1000.0, np.arange(7) * 1000.0, indexing="ij")
+    grid = gpp.Grid(y, x, type=gpp.Cartesian)
+    bg = rng.normal(size=(6, 7, 5)).astype(f32)
+    s = gpp.BarnesStructure(2500)
+    out = gpp.optimal_interpolation_ensi(grid, bg, gpp.Points([], [], type=gpp.Cartesian), [], [], np.zeros((0, 5)), s, 10)
+    assert_bit_exact(out, bg)
+    points = gpp.Points([1000, 3000], [1000, 4000], type=gpp.Cartesian)
+    pbg = rng.normal(size=(2, 5)).astype(f32)
+    out = gpp.optimal_interpolation_ensi(grid, bg, points, [1.0, np.nan], [0.5, 0.5], pbg, s, 10)
+    assert not np.isnan(out).any() and np.abs(out - bg).max() > 0
+    one = gpp.optimal_interpolation_ensi(grid, bg, gpp.Points([1000], [1000], type=gpp.Cartesian), [1.0], [0.5], pbg[:1], s, 10)
+    assert_bit_exact(out, one)
+    # a member with an invalid value anywhere is left untouched (oi_ensi.cpp:187-201)
+    bg2 = bg.copy()
+    bg2[2, 3, 1] = np.nan
+    out2 = gpp.optimal_interpolation_ensi(grid, bg2, points, [1.0, 0.5], [0.5, 0.5], pbg, s, 10)
+    assert_bit_exact(out2[:, :, 1], bg2[:, :, 1])
+    assert np.abs(out2[:, :, 0] - bg2[:, :, 0]).max() > 0
+    with pytest.raises(ValueError):
+        gpp.optimal_interpolation_ensi(grid, bg, points, [1.0, 0.5], [0.5, 0.5], pbg, s, -1)
+
+
+def test_ensi_random_vs_oracle(gpp, orc):
+    """BASELINE.json config 5 density (dx 200 m, 20 members, Barnes 10 km, max_points 50, ~84 candidates) on a sub-grid."""
+    rng = np.random.default_rng(1000)
+    ny, nx, dx, E = 40, 50, 200.0, 20
+    y, x = np.meshgrid(30000 + np.arange(ny) * dx, 30000 + np.arange(nx) * dx, indexing="ij")
+    S = 1400   # 0.02 obs / km^2 around the sub-grid
+    py, px = rng.uniform(-10000, 80000, S).astype(f32), rng.uniform(-10000, 80000, S).astype(f32)
+    bg = (rng.normal(size=(ny, nx, 1)) * 2 + rng.normal(size=(ny, nx, E))).astype(f32)
+    pbg = rng.normal(size=(S, E)).astype(f32)
+    obs = rng.normal(size=S).astype(f32)
+    obs[rng.uniform(size=S) < 0.01] = np.nan
+    sig = np.full(S, 0.5, f32)
+    grid, points = gpp.Grid(y, x, type=gpp.Cartesian), gpp.Points(py, px, type=gpp.Cartesian)
+    for mp, extr in ((50, True), (50, False), (7, True)):
+        got = gpp.optimal_interpolation_ensi(grid, bg, points, obs, sig, pbg, gpp.BarnesStructure(10000), mp, extr)
+        want = orc.optimal_interpolation_ensi((y, x, None, None), bg, (py, px, None, None), obs, sig, pbg,
+                                              B.make_structure(B.BARNES, 10000.0), mp, B.CARTESIAN, allow_extrapolation=extr)
+        assert_close(got.reshape(-1, E), want, 2.0, RTOL, "EnSI mp=%d extr=%s" % (mp, extr))
+    # Points overload, 7 members (odd: exercises the padded rotation schedule), Geodetic
+    la, lo = rng.uniform(59, 60, 300).astype(f32), rng.uniform(10, 12, 300).astype(f32)
+    pla, plo = rng.uniform(59, 60, 150).astype(f32), rng.uniform(10, 12, 150).astype(f32)
+    bgp, pbgp = rng.normal(size=(300, 7)).astype(f32), rng.normal(size=(150, 7)).astype(f32)
+    o, sg = rng.normal(size=150).astype(f32), rng.uniform(0.3, 1.0, 150).astype(f32)
+    got = gpp.optimal_interpolation_ensi(gpp.Points(la, lo), bgp, gpp.Points(pla, plo), o, sg, pbgp, gpp.BarnesStructure(20000), 12)
+    want = orc.optimal_interpolation_ensi((la, lo, None, None), bgp, (pla, plo, None, None), o, sg, pbgp,
+                                          B.make_structure(B.BARNES, 20000.0), 12, B.GEODETIC)
+    assert_close(got, want, 1.0, RTOL, "EnSI points geodetic")
