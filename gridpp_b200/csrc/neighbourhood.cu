@@ -42,77 +42,136 @@ __device__ __forceinline__ float load_cell(const TileArgs& a, int r, int x) {
 // neighbourhood.cpp:45-145. The reference builds a double summed-area table and an int count table; here the
 // window sum is accumulated directly in fp64 (vertical running sum per column over at most CHUNK + 2*hw rows,
 // horizontal sliding sum over at most SEG + 2*hw columns), so no large prefix value ever enters the sum.
-__global__ void __launch_bounds__(NT) nbh_sum_kernel(const TileArgs a, int statistic) {
+struct __align__(16) SumRec {   // one staged column of one output row: vertical window sum and valid count
+    double sum;
+    int cnt;
+    int pad;
+};
+constexpr int RCP_TABLE = 1024;   // 1 / count for count < RCP_TABLE lives in shared memory (halfwidth <= 15)
+
+__device__ __forceinline__ bool finite_f(float v) { return fabsf(v) <= 3.402823466e38f; }   // == is_valid(v)
+
+// Coalesced store of up to RB staged rows (obuf[b * PADW + pad8(column)]) to output rows y0 .. y0+nb-1.
+__device__ __forceinline__ void store_rows(const TileArgs& a, const float* obuf, int y0, int nb, int TX) {
+    const int tid = threadIdx.x;
+    const int x = blockIdx.x * TX + tid;
+    if(tid < TX && x < a.nx) {
+        float* dst = a.out + (long long) (y0 - a.row0) * a.nx + x;
+        const float* ob = obuf + pad8(tid);
+        if(nb == RB) {
+            #pragma unroll
+            for(int b = 0; b < RB; b++) { *dst = ob[b * PADW]; dst += a.nx; }
+        }
+        else
+            for(int b = 0; b < nb; b++) { *dst = ob[b * PADW]; dst += a.nx; }
+    }
+}
+
+// STAT: 0 = Mean, 1 = Sum, 2 = Count
+template <int STAT>
+__global__ void __launch_bounds__(NT) nbh_sum_kernel(const TileArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int w = 2 * a.hw + 1;
     const int TX = NT - 2 * a.hw;
-    double* line_sum = reinterpret_cast<double*>(smem);                          // [RB][PADW]
-    int* line_cnt = reinterpret_cast<int*>(line_sum + RB * PADW);                // [RB][NT]
-    float* obuf = reinterpret_cast<float*>(line_cnt + RB * NT);                  // [RB][NT]
-    float* ring = obuf + RB * NT;                                                // [w][NT]
+    SumRec* line = reinterpret_cast<SumRec*>(smem);                              // [RB][PADW]
+    double* rcp = reinterpret_cast<double*>(line + RB * PADW);                   // [RCP_TABLE]
+    float* obuf = reinterpret_cast<float*>(rcp + RCP_TABLE);                     // [RB][PADW]
+    float* ring = obuf + RB * PADW;                                              // [w][NT]
     const int tid = threadIdx.x;
     const int x_stage = blockIdx.x * TX - a.hw + tid;
+    const bool col_ok = x_stage >= 0 && x_stage < a.nx;
     const int y_begin = a.row0 + blockIdx.y * CHUNK;
     const int y_end = min(y_begin + CHUNK, a.row0 + a.n_rows_out);
+    const bool use_table = w * w < RCP_TABLE;
 
+    if(STAT == 0 && use_table)
+        for(int c = tid; c < RCP_TABLE; c += NT) rcp[c] = c > 0 ? 1.0 / (double) c : 0.0;
+    // records past the last staged column are read (clamped) by the sliding window of pixels that are never
+    // stored; keep them at zero so that their counts stay valid table indices
+    if(tid < RB * (PADW - 287)) {
+        const int tail = PADW - 287;   // pad8(NT - 1) == 286 is the last record the vertical pass writes
+        SumRec zero = {0.0, 0, 0};
+        line[(tid / tail) * PADW + 287 + tid % tail] = zero;
+    }
+    float* const ring_col = ring + tid;
+    for(int s = 0; s < w; s++) ring_col[s * NT] = NAN;
+    const int ring_len = w * NT;
+    // prime the vertical window with rows [y_begin - hw, y_begin + hw - 1]
     double csum = 0.0;
     int ccnt = 0;
-    for(int s = 0; s < w; s++) ring[s * NT + tid] = NAN;
-    // prime the vertical window with rows [y_begin - hw, y_begin + hw - 1]
-    int slot = 0;   // ring slot of the next row to load
-    for(int r = y_begin - a.hw; r < y_begin + a.hw; r++) {
-        float v = load_cell(a, r, x_stage);
-        ring[slot * NT + tid] = v;
-        slot = slot + 1 == w ? 0 : slot + 1;
-        if(is_valid(v)) { csum += (double) v; ccnt++; }
+    int slot = 0;   // ring offset (in floats) of the next row to load
+    int r = y_begin - a.hw;
+    const float* src = a.in + (long long) r * a.nx + x_stage;   // only dereferenced when the cell is inside the domain
+    for(; r < y_begin + a.hw; r++, src += a.nx) {
+        const float v = (col_ok && r >= 0 && r < a.n_rows_in) ? __ldg(src) : NAN;
+        ring_col[slot] = v;
+        slot += NT;
+        if(slot == ring_len) slot = 0;
+        if(finite_f(v)) { csum += (double) v; ccnt++; }
     }
+    __syncthreads();   // the reciprocal table
+    SumRec* const line_col = line + pad8(tid);
     for(int y0 = y_begin; y0 < y_end; y0 += RB) {
         const int nb = min(RB, y_end - y0);
-        for(int b = 0; b < nb; b++) {
-            // row y0+b+hw enters, row y0+b-hw-1 (same ring slot) leaves
-            float v_new = load_cell(a, y0 + b + a.hw, x_stage);
-            float v_old = ring[slot * NT + tid];
-            ring[slot * NT + tid] = v_new;
-            slot = slot + 1 == w ? 0 : slot + 1;
-            if(is_valid(v_new)) { csum += (double) v_new; ccnt++; }
-            if(is_valid(v_old)) { csum -= (double) v_old; ccnt--; }
-            line_sum[b * PADW + pad8(tid)] = csum;
-            line_cnt[b * NT + tid] = ccnt;
+        // ---- vertical pass: 8 rows enter the window one after the other (all 8 loads are issued first); row
+        // y0+b+hw enters, row y0+b-hw-1 (same ring slot) leaves. Rows past the end of the chunk are processed too;
+        // their records are simply not used.
+        float vnew[RB];
+        #pragma unroll
+        for(int b = 0; b < RB; b++) {
+            vnew[b] = (col_ok && r + b >= 0 && r + b < a.n_rows_in) ? __ldg(src) : NAN;
+            src += a.nx;
+        }
+        r += RB;
+        #pragma unroll
+        for(int b = 0; b < RB; b++) {
+            const float v_old = ring_col[slot];
+            ring_col[slot] = vnew[b];
+            slot += NT;
+            if(slot == ring_len) slot = 0;
+            if(finite_f(vnew[b])) { csum += (double) vnew[b]; ccnt++; }
+            if(finite_f(v_old)) { csum -= (double) v_old; ccnt--; }
+            SumRec rec = {csum, ccnt, 0};
+            line_col[b * PADW] = rec;
         }
         __syncthreads();
+        // ---- horizontal pass: 8 rows x 32 segments of 8 pixels; each thread slides along its segment
         {
-            const int b = tid >> 5, seg = tid & 31;
-            const int xo0 = seg * SEG;
+            const int b = tid >> 5, xo0 = (tid & 31) * SEG;
             if(b < nb && xo0 < TX) {
-                const double* ls = line_sum + b * PADW;
-                const int* lc = line_cnt + b * NT;
+                const SumRec* ls = line + b * PADW;
+                const SumRec* lo = ls + pad8(xo0);           // records xo0 .. xo0+7 are contiguous from here
                 double s = 0.0;
                 int c = 0;
-                for(int j = 0; j < w; j++) { s += ls[pad8(xo0 + j)]; c += lc[xo0 + j]; }
+                int t = xo0;
+                #pragma unroll 5
+                for(int j = 0; j < w; j++, t++) {
+                    const SumRec rec = ls[t + (t >> 3)];
+                    s += rec.sum;
+                    c += rec.cnt;
+                }
+                // t == xo0 + w: the next record to enter
+                float* ob = obuf + b * PADW + pad8(xo0);   // xo0 is a multiple of 8: the 8 pixels are contiguous
                 #pragma unroll
                 for(int p = 0; p < SEG; p++) {
-                    const int xo = xo0 + p;
-                    if(xo < TX) {
-                        float o = NAN;   // neighbourhood.cpp:133-142
-                        if(statistic == GPP_COUNT) o = (float) c;
-                        else if(c > 0) o = statistic == GPP_MEAN ? (float) (s / (double) c) : (float) s;
-                        obuf[b * NT + xo] = o;
-                        if(xo + 1 < TX && p + 1 < SEG) {
-                            s += ls[pad8(xo + w)] - ls[pad8(xo)];
-                            c += lc[xo + w] - lc[xo];
-                        }
+                    float o;
+                    if(STAT == 2) o = (float) c;
+                    else if(STAT == 1) o = c > 0 ? (float) s : NAN;
+                    else o = c > 0 ? (use_table ? (float) (s * rcp[c]) : (float) (s / (double) c)) : NAN;   // neighbourhood.cpp:133-142
+                    ob[p] = o;
+                    if(p + 1 < SEG) {
+                        const SumRec in_rec = ls[min(t + (t >> 3), PADW - 1)], out_rec = lo[p];
+                        t++;
+                        s += in_rec.sum - out_rec.sum;
+                        c += in_rec.cnt - out_rec.cnt;
                     }
                 }
             }
         }
         __syncthreads();
-        {
-            const int x = blockIdx.x * TX + tid;
-            if(tid < TX && x < a.nx)
-                for(int b = 0; b < nb; b++) a.out[(size_t) (y0 + b - a.row0) * a.nx + x] = obuf[b * NT + tid];
-        }
-        // the next batch overwrites line_sum/line_cnt only after its own vertical pass, and obuf only after the
-        // next __syncthreads, so no extra barrier is needed here
+        store_rows(a, obuf, y0, nb, TX);
+        // the next batch overwrites `line` only after its own vertical pass, and obuf only after the next
+        // __syncthreads, so no extra barrier is needed here
     }
 }
 
@@ -121,63 +180,105 @@ __global__ void __launch_bounds__(NT) nbh_sum_kernel(const TileArgs a, int stati
 // and its border brute force both reduce to that). Invalid cells are mapped to +inf (min) / -inf (max); an
 // all-invalid window therefore ends at +-inf, which is reported as NaN (infinite inputs are themselves
 // "invalid", util.cpp:16-18, so a genuine result is never infinite).
+//
+// Eight consecutive windows of width w (w >= 8) over v[0 .. w+6] all contain the core v[7 .. w-1]; window i is
+// min(suffix-min of v[i..6], core, prefix-min of v[w .. w+i-1]): (w - 8) + 6 + 6 + 14 operations for eight
+// outputs instead of 8 (w - 1). The vertical pass applies this to the 8 rows of a batch (per column, over a ring
+// of w + 7 rows), the horizontal pass to the 8 pixels of a thread's segment.
 template <bool IS_MAX>
 __device__ __forceinline__ float ext(float x, float y) { return IS_MAX ? fmaxf(x, y) : fminf(x, y); }
+
+// v(j) for j in [0, w + 7) -> eight window extremes. `v` is a callable returning the j-th staged value.
+template <bool IS_MAX, class F>
+__device__ __forceinline__ void eight_windows(F v, int w, float (&out)[RB]) {
+    const float ident = IS_MAX ? -INFINITY : INFINITY;
+    if(w >= RB) {
+        float suf[RB], pre[RB];
+        suf[RB - 1] = ident;
+        #pragma unroll
+        for(int i = RB - 2; i >= 0; i--) suf[i] = ext<IS_MAX>(suf[i + 1], v(i));
+        float core = v(RB - 1);
+        for(int j = RB; j < w; j++) core = ext<IS_MAX>(core, v(j));
+        pre[0] = ident;
+        #pragma unroll
+        for(int i = 1; i < RB; i++) pre[i] = ext<IS_MAX>(pre[i - 1], v(w + i - 1));
+        #pragma unroll
+        for(int i = 0; i < RB; i++) out[i] = ext<IS_MAX>(ext<IS_MAX>(suf[i], core), pre[i]);
+    }
+    else {
+        #pragma unroll
+        for(int i = 0; i < RB; i++) {
+            float m = ident;
+            for(int j = 0; j < w; j++) m = ext<IS_MAX>(m, v(i + j));
+            out[i] = m;
+        }
+    }
+}
 
 template <bool IS_MAX>
 __global__ void __launch_bounds__(NT) nbh_minmax_kernel(const TileArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     const float ident = IS_MAX ? -INFINITY : INFINITY;
     const int w = 2 * a.hw + 1;
+    const int RS = w + RB - 1;                         // ring rows: everything the 8 rows of a batch need
     const int TX = NT - 2 * a.hw;
     float* line = reinterpret_cast<float*>(smem);      // [RB][NT] vertical extremes
-    float* obuf = line + RB * NT;                      // [RB][NT]
-    float* ring = obuf + RB * NT;                      // [w][NT]
+    float* obuf = line + RB * NT;                      // [RB][PADW]
+    float* ring = obuf + RB * PADW;                    // [RS][NT]
     const int tid = threadIdx.x;
     const int x_stage = blockIdx.x * TX - a.hw + tid;
+    const bool col_ok = x_stage >= 0 && x_stage < a.nx;
     const int y_begin = a.row0 + blockIdx.y * CHUNK;
     const int y_end = min(y_begin + CHUNK, a.row0 + a.n_rows_out);
 
-    for(int s = 0; s < w; s++) ring[s * NT + tid] = ident;
+    // ring slot of input row r is (r - (y_begin - hw)) mod RS; prime rows [y_begin - hw, y_begin + hw - 1]
+    int r = y_begin - a.hw;
+    const float* src = a.in + (long long) r * a.nx + x_stage;
     int slot = 0;
-    for(int r = y_begin - a.hw; r < y_begin + a.hw; r++) {
-        float v = load_cell(a, r, x_stage);
-        ring[slot * NT + tid] = is_valid(v) ? v : ident;
-        slot = slot + 1 == w ? 0 : slot + 1;
+    for(; r < y_begin + a.hw; r++, src += a.nx) {
+        const float v = (col_ok && r >= 0 && r < a.n_rows_in) ? __ldg(src) : NAN;
+        ring[slot * NT + tid] = finite_f(v) ? v : ident;
+        slot = slot + 1 == RS ? 0 : slot + 1;
     }
+    int start = 0;   // ring slot of row y0 - hw
     for(int y0 = y_begin; y0 < y_end; y0 += RB) {
         const int nb = min(RB, y_end - y0);
-        for(int b = 0; b < nb; b++) {
-            float v = load_cell(a, y0 + b + a.hw, x_stage);
-            ring[slot * NT + tid] = is_valid(v) ? v : ident;
-            slot = slot + 1 == w ? 0 : slot + 1;
-            float m = ident;
-            for(int s = 0; s < w; s++) m = ext<IS_MAX>(m, ring[s * NT + tid]);
-            line[b * NT + tid] = m;
+        // rows y0+hw .. y0+hw+7 enter (rows beyond the batch are loaded too: they are in the domain or NaN)
+        float vnew[RB];
+        #pragma unroll
+        for(int b = 0; b < RB; b++) {
+            vnew[b] = (col_ok && r + b >= 0 && r + b < a.n_rows_in) ? __ldg(src) : NAN;
+            src += a.nx;
         }
+        r += RB;
+        #pragma unroll
+        for(int b = 0; b < RB; b++) {
+            ring[slot * NT + tid] = finite_f(vnew[b]) ? vnew[b] : ident;
+            slot = slot + 1 == RS ? 0 : slot + 1;
+        }
+        {
+            float out[RB];
+            const float* base = ring + tid;
+            eight_windows<IS_MAX>([&](int j) { int s = start + j; if(s >= RS) s -= RS; return base[s * NT]; }, w, out);
+            #pragma unroll
+            for(int b = 0; b < RB; b++) line[b * NT + tid] = out[b];
+        }
+        start += RB;
+        if(start >= RS) start -= RS;
         __syncthreads();
         {
-            const int b = tid >> 5, seg = tid & 31;
-            const int xo0 = seg * SEG;
+            const int b = tid >> 5, xo0 = (tid & 31) * SEG;
             if(b < nb && xo0 < TX) {
+                // staged columns xo0 .. xo0 + w + 6 (clamped reads beyond the strip only feed pixels that are not stored)
                 const float* l = line + b * NT;
+                float out[RB];
+                eight_windows<IS_MAX>([&](int j) { return l[min(xo0 + j, NT - 1)]; }, w, out);
                 #pragma unroll
-                for(int p = 0; p < SEG; p++) {
-                    const int xo = xo0 + p;
-                    if(xo < TX) {
-                        float m = ident;
-                        for(int j = 0; j < w; j++) m = ext<IS_MAX>(m, l[xo + j]);
-                        obuf[b * NT + xo] = isinf(m) ? NAN : m;
-                    }
-                }
+                for(int p = 0; p < SEG; p++) obuf[b * PADW + pad8(xo0) + p] = fabsf(out[p]) == INFINITY ? NAN : out[p];
             }
         }
         __syncthreads();
-        {
-            const int x = blockIdx.x * TX + tid;
-            if(tid < TX && x < a.nx)
-                for(int b = 0; b < nb; b++) a.out[(size_t) (y0 + b - a.row0) * a.nx + x] = obuf[b * NT + tid];
-        }
+        store_rows(a, obuf, y0, nb, TX);
     }
 }
 
@@ -431,7 +532,7 @@ int gpp_neighbourhood_device(const float* d_input, int n_rows_in, int nx, int ro
         const int w = 2 * halfwidth + 1, TX = NT - 2 * halfwidth;
         dim3 grid((nx + TX - 1) / TX, (n_rows_out + CHUNK - 1) / CHUNK);
         if(minmax) {
-            size_t smem = sizeof(float) * ((size_t) 2 * RB * NT + (size_t) w * NT);
+            size_t smem = sizeof(float) * ((size_t) RB * NT + (size_t) RB * PADW + (size_t) (w + RB - 1) * NT);
             if(statistic == GPP_MAX) {
                 GPP_TRY(opt_in_smem(nbh_minmax_kernel<true>, smem));
                 GPP_LAUNCH(nbh_minmax_kernel<true>, grid, NT, smem, stream, a);
@@ -442,9 +543,10 @@ int gpp_neighbourhood_device(const float* d_input, int n_rows_in, int nx, int ro
             }
         }
         else {
-            size_t smem = sizeof(double) * RB * PADW + sizeof(int) * RB * NT + sizeof(float) * RB * NT + sizeof(float) * (size_t) w * NT;
-            GPP_TRY(opt_in_smem(nbh_sum_kernel, smem));
-            GPP_LAUNCH(nbh_sum_kernel, grid, NT, smem, stream, a, statistic);
+            size_t smem = sizeof(SumRec) * RB * PADW + sizeof(double) * RCP_TABLE + sizeof(float) * RB * PADW + sizeof(float) * (size_t) w * NT;
+            if(statistic == GPP_MEAN) { GPP_TRY(opt_in_smem(nbh_sum_kernel<0>, smem)); GPP_LAUNCH(nbh_sum_kernel<0>, grid, NT, smem, stream, a); }
+            else if(statistic == GPP_SUM) { GPP_TRY(opt_in_smem(nbh_sum_kernel<1>, smem)); GPP_LAUNCH(nbh_sum_kernel<1>, grid, NT, smem, stream, a); }
+            else { GPP_TRY(opt_in_smem(nbh_sum_kernel<2>, smem)); GPP_LAUNCH(nbh_sum_kernel<2>, grid, NT, smem, stream, a); }
         }
         return GPP_OK;
     }
