@@ -58,8 +58,9 @@ __device__ __forceinline__ void write_result(const OiParams& P, int g, float bg,
     }
 }
 
-constexpr int RUN = 16;             // consecutive background points analysed by one warp (solution reuse, see below)
+constexpr int RUN = 16;             // consecutive background points analysed by one warp
 constexpr int NPAIR_LUT = 496;      // 31 * 32 / 2 >= FAST_K * (FAST_K + 1) / 2
+constexpr int NCAND = 64;           // capacity of a run's candidate list (2 slots per lane)
 
 struct FastSmem {
     unsigned long long key[64];     // candidate keys (oi.cuh)
@@ -72,26 +73,172 @@ struct FastSmem {
     float c_rho[32];
     float sx[32], sy[32], sz[32], selev[32], slaf[32];
     float sratio[32];
+    // run path: the run's candidate observations (ascending original index) and its points
+    float cand_x[NCAND], cand_y[NCAND], cand_z[NCAND], cand_elev[NCAND], cand_laf[NCAND];
+    int cand_pos[NCAND], cand_orig[NCAND];
+    float px[RUN], py[RUN], pz[RUN], pelev[RUN], plaf[RUN], pbg[RUN];
 };
 
-// One warp per background point; a warp walks RUN consecutive points.
+// State a warp carries from point to point: the last system it solved.
+//   prev_orig (per lane r: original index of row r of the solved set, -1 beyond k), prev_k, z (per lane r: component r
+//   of (P+R)^-1 d), dmax / dmin (extreme innovations of the set), dirty (non-zero extent of S.M).
+struct WarpState {
+    int prev_orig, prev_k, dirty;
+    double z, dmax, dmin, avar;
+};
+
+// Assemble P + R for the k observations staged in canonical order in S.c_pos / S.c_rho and solve for
+// z = (P+R)^-1 d by Gauss-Jordan in registers (lane j = row j of the symmetric augmented matrix
+// [[P+R, rho, d], [rho', 0, 0], [d', 0, 0]]); also leaves rho'(P+R)^-1 rho in W.avar. oi.cpp:298-317,336.
+template <int SMODE>
+__device__ __noinline__ void solve_selected(const OiParams& P, FastSmem& S, const unsigned short* lut, int k, WarpState& W) {
+    const int lane = (int) lane_id();
+    // ---- stage the selected observations
+    if(lane < k) {
+        const int pos = S.c_pos[lane];
+        S.sx[lane] = P.obs.x[pos]; S.sy[lane] = P.obs.y[pos]; S.sz[lane] = P.obs.z[pos];
+        S.selev[lane] = P.obs.elev[pos]; S.slaf[lane] = P.obs.laf[pos];
+        S.sratio[lane] = P.obs.ratio[pos];
+        S.sd[lane] = P.obs.innov[pos];
+    }
+    if(k < W.dirty) {   // keep everything outside [0,k) U {30,31} at zero
+        for(int i = k; i < W.dirty; i++) S.M[lane * 33 + i] = 0.0;
+        if(lane >= k && lane < W.dirty)
+            for(int i = 0; i < 32; i++) S.M[lane * 33 + i] = 0.0;
+    }
+    W.dirty = k;
+    __syncwarp();
+    // ---- pairwise correlations (oi.cpp:298-314), lower triangle incl. diagonal packed over the lanes
+    const int npairs = k * (k + 1) / 2;
+    for(int p = lane; p < npairs; p += 32) {
+        const int code = lut[p];
+        const int j = code >> 8, i = code & 255;
+        const Pt a = {S.sx[j], S.sy[j], S.sz[j], S.selev[j], S.slaf[j]};
+        const Pt b = {S.sx[i], S.sy[i], S.sz[i], S.selev[i], S.slaf[i]};
+        const float hdist = straight_distance(a.x, a.y, a.z, b.x, b.y, b.z);
+        double v = (double) corr_mode<SMODE>(P.s, a, b, hdist);
+        if(i == j) v = __dadd_rn(v, (double) S.sratio[j]);   // lP + lR, oi.cpp:315
+        S.M[j * 33 + i] = v;
+        S.M[i * 33 + j] = v;
+    }
+    if(lane < k) {
+        const double r = (double) S.c_rho[lane], d = S.sd[lane];
+        S.M[30 * 33 + lane] = r; S.M[lane * 33 + 30] = r;
+        S.M[31 * 33 + lane] = d; S.M[lane * 33 + 31] = d;
+    }
+    // max / min innovation for the optional clamp (oi.cpp:319-320)
+    double dmax = lane < k ? S.sd[lane] : -INFINITY, dmin = lane < k ? S.sd[lane] : INFINITY;
+    #pragma unroll
+    for(int off = 16; off > 0; off >>= 1) {
+        dmax = fmax(dmax, shfl_double(dmax, lane ^ off));
+        dmin = fmin(dmin, shfl_double(dmin, lane ^ off));
+    }
+    W.dmax = dmax;
+    W.dmin = dmin;
+    __syncwarp();
+    double a[32];
+    #pragma unroll
+    for(int i = 0; i < 32; i++) a[i] = S.M[lane * 33 + i];
+    // ---- Gauss-Jordan on the k observation rows, pivots on the diagonal (SPD: no pivoting needed). By symmetry
+    // of the not-yet-eliminated block the pivot ROW equals the pivot COLUMN, which is spread over the lanes: one
+    // shared store per lane broadcasts it.
+    double my_inv = 0.0;
+    #pragma unroll
+    for(int c = 0; c < FAST_K; c++) {
+        if(c < k) {
+            const double my = a[c];
+            const double inv = __drcp_rn(shfl_double(my, c));
+            S.colbuf[c & 1][lane] = my;
+            const double f = lane == c ? 0.0 : my * inv;
+            if(lane == c) my_inv = inv;
+            __syncwarp();
+            #pragma unroll
+            for(int i = c + 1; i < 32; i++) a[i] = fma(-f, S.colbuf[c & 1][i], a[i]);
+        }
+    }
+    W.z = lane < k ? a[31] * my_inv : 0.0;      // z = (P+R)^-1 d, one component per lane
+    W.avar = -shfl_double(a[30], 30);           // rho'(P+R)^-1 rho (oi.cpp:336)
+    W.prev_orig = lane < k ? S.c_orig[lane] : -1;
+    W.prev_k = k;
+}
+
+// increment = rho . z (oi.cpp:315-317) with rho in canonical order in S.c_rho; lane 0 writes the result
+__device__ __forceinline__ void finish_point(const OiParams& P, const FastSmem& S, int g, float bg, int k, const WarpState& W) {
+    const int lane = (int) lane_id();
+    double dx = lane < k ? (double) S.c_rho[lane] * W.z : 0.0;
+    #pragma unroll
+    for(int off = 16; off > 0; off >>= 1) dx += shfl_double(dx, lane ^ off);
+    if(lane == 0) write_result(P, g, bg, dx, W.avar, W.dmax, W.dmin);
+}
+__device__ __forceinline__ void keep_background(const OiParams& P, int g, float bg) {
+    if(lane_id() == 0) {   // oi.cpp:223,234-237,284-287: the analysis stays at the background
+        P.analysis[g] = bg;
+        if(P.analysis_variance) P.analysis_variance[g] = P.bvariance ? P.bvariance[g] : 1.f;
+    }
+}
+
+// Per-point path: gather from the bucket grid, select, canonicalise, reuse or solve. Used when a run's candidate
+// list does not fit NCAND slots (dense observations, scattered points).
+template <int SMODE>
+__device__ __noinline__ void analyse_point(const OiParams& P, FastSmem& S, const unsigned short* lut, int g, WarpState& W) {
+    const int lane = (int) lane_id();
+    const CandBuf cb = {S.key, S.pos};
+    const bool need_var = P.analysis_variance != nullptr;
+    const float bg = P.background[g];
+    int k = 0;
+    if(is_valid(bg)) {   // oi.cpp:223
+        const Pt p1 = {P.gx[g], P.gy[g], P.gz[g], P.gelev[g], P.glaf[g]};
+        k = gather_candidates<SMODE, 2>(P.obs, P.s, p1, P.R, P.k, cb);
+    }
+    if(k == 0) { keep_background(P, g, bg); return; }
+    // ---- canonical order of the selection: ascending original index
+    {
+        const unsigned long long my_key = lane < k ? S.key[lane] : 0ull;
+        const int my_pos = lane < k ? S.pos[lane] : 0;
+        const unsigned my_inv = (unsigned) my_key;    // 0x7fffffff - original index
+        int crank = 0;
+        const unsigned* lo_words = reinterpret_cast<const unsigned*>(S.key);
+        #pragma unroll 4
+        for(int m = 0; m < k; m++) crank += lo_words[2 * m] > my_inv;
+        __syncwarp();
+        if(lane < k) {
+            S.c_orig[crank] = cand_key_orig(my_key);
+            S.c_rho[crank] = cand_key_rho(my_key);
+            S.c_pos[crank] = my_pos;
+        }
+        __syncwarp();
+    }
+    const int c_orig = lane < k ? S.c_orig[lane] : -1;
+    const bool same = __all_sync(0xffffffffu, c_orig == W.prev_orig) && k == W.prev_k;
+    if(!same || need_var) solve_selected<SMODE>(P, S, lut, k, W);
+    finish_point(P, S, g, bg, k, W);
+    __syncwarp();
+}
+
+// One warp walks RUN consecutive background points.
 //
 // Solution reuse: neighbouring points usually select the SAME set of observations (the set only changes when the
-// point crosses a boundary of the order-k Voronoi diagram of the observations). With the selection put in a
-// canonical order (ascending original index), z = (P+R)^-1 d depends on the set alone and the increment is the
-// k-term dot product rho . z (oi.cpp:315-316: lG * inv(lP+lR) * (lObs - lY)). The warp keeps (set, z) of the last
-// system it solved; when the next point selects the same set, assembly and elimination are skipped. Every point
-// computes its increment with the same dot product, so results do not depend on where a run starts. The analysis
-// variance needs rho'(P+R)^-1 rho, which depends on the point: when it is requested every point is eliminated.
+// point crosses a boundary of the order-k Voronoi diagram of the observations). With the selection in canonical
+// order (ascending original index), z = (P+R)^-1 d depends on the set alone and the increment is the k-term dot
+// product rho . z (oi.cpp:315-316: lG * inv(lP+lR) * (lObs - lY)). The warp keeps (set, z) of the last system it
+// solved. Every point computes its increment with the same dot product in the same order, so results do not depend
+// on where a run starts or on which path found the set. The analysis variance needs rho'(P+R)^-1 rho, which depends
+// on the point: when it is requested every point is eliminated.
+//
+// Run path: the observations that can be within R of ANY point of the run (distance to the run's centre
+// <= R + extent) are gathered ONCE, sorted by original index, and kept lane-resident (2 slots per lane). Per point
+// each lane evaluates the reference's exact predicate (strict box, distance <= R, rho > 0, oi.cpp:233-258) for its
+// slots; "the best k are the set solved last" is verified with two warp reductions (worst member key > best
+// non-member key) instead of a selection; only when that fails is the selection redone by ranking.
 template <int SMODE>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 2) oi_fast_kernel(const __grid_constant__ OiParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FastSmem& S = reinterpret_cast<FastSmem*>(smem_raw)[threadIdx.x >> 5];
     unsigned short* lut = reinterpret_cast<unsigned short*>(smem_raw + sizeof(FastSmem) * WARPS_PER_CTA);
-    const unsigned lane = lane_id();
+    const int lane = (int) lane_id();
+    const unsigned lt_mask = (1u << lane) - 1u;
     const int warp_global = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
     const int warps_total = gridDim.x * WARPS_PER_CTA;
-    const CandBuf cb = {S.key, S.pos};
     const bool need_var = P.analysis_variance != nullptr;
 
     // pair index p -> (row j, column i <= j) of the lower triangle, packed over the lanes during assembly
@@ -101,125 +248,197 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 2) oi_fast_kernel(const __
         while((j + 1) * (j + 2) / 2 <= p) j++;
         lut[p] = (unsigned short) ((j << 8) | (p - j * (j + 1) / 2));
     }
-    for(int e = (int) lane; e < 32 * 33; e += 32) S.M[e] = 0.0;
+    for(int e = lane; e < 32 * 33; e += 32) S.M[e] = 0.0;
     __syncthreads();
-    int dirty = 0;            // rows / columns [0, dirty) and 30, 31 of M may hold non-zero values
-    int prev_orig = -2, prev_k = -1;
-    double z = 0.0, dmax = 0.0, dmin = 0.0, avar = 0.0;
+    WarpState W;
+    W.prev_orig = -2; W.prev_k = -1; W.dirty = 0;
+    W.z = 0.0; W.dmax = 0.0; W.dmin = 0.0; W.avar = 0.0;
 
     const int n_runs = (P.count + RUN - 1) / RUN;
     for(int run = warp_global; run < n_runs; run += warps_total) {
-        const int it_end = min((run + 1) * RUN, P.count);
-        for(int it = run * RUN; it < it_end; it++) {
-            const int g = P.first + it;
-            const float bg = P.background[g];
-            int k = 0;
-            Pt p1 = {0.f, 0.f, 0.f, 0.f, 0.f};
-            if(is_valid(bg)) {   // oi.cpp:223
-                p1 = {P.gx[g], P.gy[g], P.gz[g], P.gelev[g], P.glaf[g]};
-                k = gather_candidates<SMODE, 2>(P.obs, P.s, p1, P.R, P.k, cb);
+        const int it0 = run * RUN, npts = min(RUN, P.count - it0);
+        // ---- the run's points, and a bounding sphere (centre = midpoint of first and last point)
+        float ext = 0.f;
+        {
+            float x = 0.f, y = 0.f, z = 0.f;
+            if(lane < npts) {
+                const int g = P.first + it0 + lane;
+                x = P.gx[g]; y = P.gy[g]; z = P.gz[g];
+                S.px[lane] = x; S.py[lane] = y; S.pz[lane] = z;
+                S.pelev[lane] = P.gelev[g]; S.plaf[lane] = P.glaf[g]; S.pbg[lane] = P.background[g];
             }
-            if(k == 0) {         // oi.cpp:223,234-237,284-287: the analysis stays at the background
-                if(lane == 0) {
-                    P.analysis[g] = bg;
-                    if(need_var) P.analysis_variance[g] = P.bvariance ? P.bvariance[g] : 1.f;
-                }
+            __syncwarp();
+            const float cx = 0.5f * (S.px[0] + S.px[npts - 1]), cy = 0.5f * (S.py[0] + S.py[npts - 1]), cz = 0.5f * (S.pz[0] + S.pz[npts - 1]);
+            if(lane < npts) ext = sqrtf((x - cx) * (x - cx) + (y - cy) * (y - cy) + (z - cz) * (z - cz));
+            #pragma unroll
+            for(int off = 16; off > 0; off >>= 1) ext = fmaxf(ext, __shfl_xor_sync(0xffffffffu, ext, off));
+            // ---- candidate list: every table observation within Rs = R + ext (+ rounding slack) of the centre
+            const float Rs = (P.R + ext) * 1.0001f + 1e-3f;
+            int nL = 0;
+            bool overflow = !(Rs < INFINITY);
+            if(!overflow) {
+                const ObsView& obs = P.obs;
+                const int cx0 = cell_coord(obs.geom, 0, cx - Rs), cx1 = cell_coord(obs.geom, 0, cx + Rs);
+                const int cy0 = cell_coord(obs.geom, 1, cy - Rs), cy1 = cell_coord(obs.geom, 1, cy + Rs);
+                const int cz0 = cell_coord(obs.geom, 2, cz - Rs), cz1 = cell_coord(obs.geom, 2, cz + Rs);
+                for(int czi = cz0; czi <= cz1 && !overflow; czi++)
+                    for(int cyi = cy0; cyi <= cy1 && !overflow; cyi++) {
+                        const int base = (czi * obs.geom.n[1] + cyi) * obs.geom.n[0];
+                        const int s0 = obs.cell_start[base + cx0], s1 = obs.cell_start[base + cx1 + 1];
+                        for(int chunk = s0; chunk < s1; chunk += 32) {
+                            const int i = chunk + lane;
+                            bool ok = i < s1;
+                            if(ok) {
+                                const float dx = obs.x[i] - cx, dy = obs.y[i] - cy, dz = obs.z[i] - cz;
+                                ok = sqrtf(dx * dx + dy * dy + dz * dz) <= Rs;
+                            }
+                            const unsigned mask = __ballot_sync(0xffffffffu, ok);
+                            const int add = __popc(mask);
+                            if(nL + add > NCAND) { overflow = true; break; }
+                            if(ok) {
+                                const int slot = nL + __popc(mask & lt_mask);
+                                S.key[slot] = (unsigned long long) (unsigned) obs.orig[i];
+                                S.pos[slot] = i;
+                            }
+                            nL += add;
+                        }
+                    }
+            }
+            __syncwarp();
+            if(overflow) {
+                // too many candidates for the lane-resident list: analyse the run point by point
+                for(int i = 0; i < npts; i++) analyse_point<SMODE>(P, S, lut, P.first + it0 + i, W);
                 continue;
             }
-            // ---- canonical order of the selection: ascending original index
+            // ---- sort the candidates by original index (rank by counting) and load their coordinates
             {
-                const unsigned long long my_key = (int) lane < k ? S.key[lane] : 0ull;
-                const int my_pos = (int) lane < k ? S.pos[lane] : 0;
-                const unsigned my_inv = (unsigned) my_key;    // 0x7fffffff - original index
-                int crank = 0;
+                const unsigned o0 = lane < nL ? (unsigned) S.key[lane] : 0xffffffffu;
+                const unsigned o1 = lane + 32 < nL ? (unsigned) S.key[lane + 32] : 0xffffffffu;
+                const int p0 = lane < nL ? S.pos[lane] : 0, p1 = lane + 32 < nL ? S.pos[lane + 32] : 0;
+                int r0 = 0, r1 = 0;
                 const unsigned* lo_words = reinterpret_cast<const unsigned*>(S.key);
                 #pragma unroll 4
-                for(int m = 0; m < k; m++) crank += lo_words[2 * m] > my_inv;
-                if((int) lane < k) {
-                    S.c_orig[crank] = cand_key_orig(my_key);
-                    S.c_rho[crank] = cand_key_rho(my_key);
-                    S.c_pos[crank] = my_pos;
+                for(int m = 0; m < nL; m++) {
+                    const unsigned om = lo_words[2 * m];
+                    r0 += om < o0;
+                    r1 += om < o1;
+                }
+                if(lane < nL) {
+                    S.cand_orig[r0] = (int) o0; S.cand_pos[r0] = p0;
+                    S.cand_x[r0] = P.obs.x[p0]; S.cand_y[r0] = P.obs.y[p0]; S.cand_z[r0] = P.obs.z[p0];
+                    S.cand_elev[r0] = P.obs.elev[p0]; S.cand_laf[r0] = P.obs.laf[p0];
+                }
+                if(lane + 32 < nL) {
+                    S.cand_orig[r1] = (int) o1; S.cand_pos[r1] = p1;
+                    S.cand_x[r1] = P.obs.x[p1]; S.cand_y[r1] = P.obs.y[p1]; S.cand_z[r1] = P.obs.z[p1];
+                    S.cand_elev[r1] = P.obs.elev[p1]; S.cand_laf[r1] = P.obs.laf[p1];
                 }
                 __syncwarp();
             }
-            const int c_orig = (int) lane < k ? S.c_orig[lane] : -1;
-            const float c_rho = (int) lane < k ? S.c_rho[lane] : 0.f;
-            const bool same = __all_sync(0xffffffffu, c_orig == prev_orig) && k == prev_k;
-            if(!same || need_var) {
-                // ---- stage the selected observations
-                if((int) lane < k) {
-                    const int pos = S.c_pos[lane];
-                    S.sx[lane] = P.obs.x[pos]; S.sy[lane] = P.obs.y[pos]; S.sz[lane] = P.obs.z[pos];
-                    S.selev[lane] = P.obs.elev[pos]; S.slaf[lane] = P.obs.laf[pos];
-                    S.sratio[lane] = P.obs.ratio[pos];
-                    S.sd[lane] = P.obs.innov[pos];
+            // ---- this lane's two candidates, and where the previously solved set sits in the new list
+            const bool h0 = lane < nL, h1 = lane + 32 < nL;
+            const Pt q0 = {h0 ? S.cand_x[lane] : 0.f, h0 ? S.cand_y[lane] : 0.f, h0 ? S.cand_z[lane] : 0.f,
+                           h0 ? S.cand_elev[lane] : 0.f, h0 ? S.cand_laf[lane] : 0.f};
+            const Pt q1 = {h1 ? S.cand_x[lane + 32] : 0.f, h1 ? S.cand_y[lane + 32] : 0.f, h1 ? S.cand_z[lane + 32] : 0.f,
+                           h1 ? S.cand_elev[lane + 32] : 0.f, h1 ? S.cand_laf[lane + 32] : 0.f};
+            const int orig0 = h0 ? S.cand_orig[lane] : -1, orig1 = h1 ? S.cand_orig[lane + 32] : -1;
+            // members of the solved set among the slots (T0/T1), valid only if every member is in the list
+            unsigned T0 = 0, T1 = 0;
+            {
+                bool m0 = false, m1 = false;
+                for(int r = 0; r < 32; r++) {
+                    const int po = __shfl_sync(0xffffffffu, W.prev_orig, r);
+                    if(po < 0) break;
+                    m0 = m0 || po == orig0;
+                    m1 = m1 || po == orig1;
                 }
-                if(k < dirty) {   // keep everything outside [0,k) U {30,31} at zero
-                    for(int i = k; i < dirty; i++) S.M[lane * 33 + i] = 0.0;
-                    if((int) lane >= k && (int) lane < dirty)
-                        for(int i = 0; i < 32; i++) S.M[lane * 33 + i] = 0.0;
-                }
-                dirty = k;
-                __syncwarp();
-                // ---- pairwise correlations (oi.cpp:298-314), lower triangle incl. diagonal packed over the lanes
-                const int npairs = k * (k + 1) / 2;
-                for(int p = (int) lane; p < npairs; p += 32) {
-                    const int code = lut[p];
-                    const int j = code >> 8, i = code & 255;
-                    const Pt a = {S.sx[j], S.sy[j], S.sz[j], S.selev[j], S.slaf[j]};
-                    const Pt b = {S.sx[i], S.sy[i], S.sz[i], S.selev[i], S.slaf[i]};
-                    const float hdist = straight_distance(a.x, a.y, a.z, b.x, b.y, b.z);
-                    double v = (double) corr_mode<SMODE>(P.s, a, b, hdist);
-                    if(i == j) v = __dadd_rn(v, (double) S.sratio[j]);   // lP + lR, oi.cpp:315
-                    S.M[j * 33 + i] = v;
-                    S.M[i * 33 + j] = v;
-                }
-                if((int) lane < k) {
-                    const double r = (double) c_rho, d = S.sd[lane];
-                    S.M[30 * 33 + lane] = r; S.M[lane * 33 + 30] = r;
-                    S.M[31 * 33 + lane] = d; S.M[lane * 33 + 31] = d;
-                }
-                // max / min innovation for the optional clamp (oi.cpp:319-320)
-                dmax = (int) lane < k ? S.sd[lane] : -INFINITY;
-                dmin = (int) lane < k ? S.sd[lane] : INFINITY;
-                #pragma unroll
-                for(int off = 16; off > 0; off >>= 1) {
-                    dmax = fmax(dmax, shfl_double(dmax, lane ^ off));
-                    dmin = fmin(dmin, shfl_double(dmin, lane ^ off));
-                }
-                __syncwarp();
-                // ---- row `lane` of [[P+R, rho, d], [rho', 0, 0], [d', 0, 0]] into registers
-                double a[32];
-                #pragma unroll
-                for(int i = 0; i < 32; i++) a[i] = S.M[lane * 33 + i];
-                // ---- Gauss-Jordan on the k observation rows, pivots on the diagonal (SPD: no pivoting needed).
-                // By symmetry of the not-yet-eliminated block the pivot ROW equals the pivot COLUMN, which is spread
-                // over the lanes: one shared store per lane broadcasts it.
-                double my_inv = 0.0;
-                #pragma unroll
-                for(int c = 0; c < FAST_K; c++) {
-                    if(c < k) {
-                        const double my = a[c];
-                        const double inv = __drcp_rn(shfl_double(my, c));
-                        S.colbuf[c & 1][lane] = my;
-                        const double f = (int) lane == c ? 0.0 : my * inv;
-                        if((int) lane == c) my_inv = inv;
-                        __syncwarp();
-                        #pragma unroll
-                        for(int i = c + 1; i < 32; i++) a[i] = fma(-f, S.colbuf[c & 1][i], a[i]);
+                T0 = __ballot_sync(0xffffffffu, m0);
+                T1 = __ballot_sync(0xffffffffu, m1);
+                if(__popc(T0) + __popc(T1) != W.prev_k) { T0 = 0; T1 = 0; }
+            }
+            // ---- the points of the run
+            for(int i = 0; i < npts; i++) {
+                const int g = P.first + it0 + i;
+                const float bg = S.pbg[i];
+                if(!is_valid(bg)) { keep_background(P, g, bg); continue; }   // oi.cpp:223
+                const Pt p1 = {S.px[i], S.py[i], S.pz[i], S.pelev[i], S.plaf[i]};
+                // the reference's predicate for each of this lane's candidates (kdtree.cpp:46-53,247-260; oi.cpp:250-258)
+                const float lo0 = __fsub_rn(p1.x, P.R), lo1 = __fsub_rn(p1.y, P.R), lo2 = __fsub_rn(p1.z, P.R);
+                const float hi0 = __fadd_rn(p1.x, P.R), hi1 = __fadd_rn(p1.y, P.R), hi2 = __fadd_rn(p1.z, P.R);
+                unsigned long long key0 = 0ull, key1 = 0ull;
+                if(h0 && q0.x > lo0 && q0.x < hi0 && q0.y > lo1 && q0.y < hi1 && q0.z > lo2 && q0.z < hi2) {
+                    const float dist = straight_distance(q0.x, q0.y, q0.z, p1.x, p1.y, p1.z);
+                    if(dist <= P.R) {
+                        const float rho = corr_background_mode<SMODE>(P.s, p1, q0, dist);
+                        if(rho > 0.f) key0 = cand_key(rho, orig0);
                     }
                 }
-                z = (int) lane < k ? a[31] * my_inv : 0.0;          // z = (P+R)^-1 d, one component per lane
-                if(need_var) avar = -shfl_double(a[30], 30);        // rho'(P+R)^-1 rho (oi.cpp:336)
-                prev_orig = c_orig;
-                prev_k = k;
+                if(h1 && q1.x > lo0 && q1.x < hi0 && q1.y > lo1 && q1.y < hi1 && q1.z > lo2 && q1.z < hi2) {
+                    const float dist = straight_distance(q1.x, q1.y, q1.z, p1.x, p1.y, p1.z);
+                    if(dist <= P.R) {
+                        const float rho = corr_background_mode<SMODE>(P.s, p1, q1, dist);
+                        if(rho > 0.f) key1 = cand_key(rho, orig1);
+                    }
+                }
+                const unsigned v0 = __ballot_sync(0xffffffffu, key0 != 0ull), v1 = __ballot_sync(0xffffffffu, key1 != 0ull);
+                const int nv = __popc(v0) + __popc(v1);
+                if(nv == 0) { keep_background(P, g, bg); continue; }   // oi.cpp:234-237,284-287
+                // ---- selection (oi.cpp:262-273) as slot masks
+                unsigned sel0 = v0, sel1 = v1;
+                int k = nv;
+                if(nv > P.k) {
+                    k = P.k;
+                    bool hypothesis = __popc(T0) + __popc(T1) == k && (T0 & ~v0) == 0 && (T1 & ~v1) == 0;
+                    if(hypothesis) {
+                        // worst member vs best valid non-member
+                        const bool in0 = (T0 >> lane) & 1u, in1 = (T1 >> lane) & 1u;
+                        unsigned long long worst_in = ~0ull, best_out = 0ull;
+                        if(in0) worst_in = key0; else best_out = key0;
+                        if(in1) worst_in = min(worst_in, key1); else best_out = max(best_out, key1);
+                        #pragma unroll
+                        for(int off = 16; off > 0; off >>= 1) {
+                            worst_in = min(worst_in, __shfl_xor_sync(0xffffffffu, worst_in, off));
+                            best_out = max(best_out, __shfl_xor_sync(0xffffffffu, best_out, off));
+                        }
+                        hypothesis = worst_in > best_out;
+                    }
+                    if(hypothesis) { sel0 = T0; sel1 = T1; }
+                    else {
+                        // rank the valid keys; the k largest are selected
+                        S.key[lane] = key0;
+                        S.key[lane + 32] = key1;
+                        __syncwarp();
+                        int r0 = 0, r1 = 0;
+                        #pragma unroll 4
+                        for(int m = 0; m < nL; m++) {
+                            const unsigned long long km = S.key[m];
+                            r0 += km > key0;
+                            r1 += km > key1;
+                        }
+                        sel0 = __ballot_sync(0xffffffffu, key0 != 0ull && r0 < k);
+                        sel1 = __ballot_sync(0xffffffffu, key1 != 0ull && r1 < k);
+                        __syncwarp();
+                    }
+                }
+                // ---- rho of the selection in canonical (slot = original index) order
+                const int n_sel0 = __popc(sel0);
+                const int row0 = __popc(sel0 & lt_mask), row1 = n_sel0 + __popc(sel1 & lt_mask);
+                const bool s0 = (sel0 >> lane) & 1u, s1 = (sel1 >> lane) & 1u;
+                if(s0) S.c_rho[row0] = cand_key_rho(key0);
+                if(s1) S.c_rho[row1] = cand_key_rho(key1);
+                const bool same = sel0 == T0 && sel1 == T1;
+                if(!same || need_var) {
+                    if(s0) { S.c_pos[row0] = S.cand_pos[lane]; S.c_orig[row0] = orig0; }
+                    if(s1) { S.c_pos[row1] = S.cand_pos[lane + 32]; S.c_orig[row1] = orig1; }
+                    __syncwarp();
+                    solve_selected<SMODE>(P, S, lut, k, W);
+                    T0 = sel0;
+                    T1 = sel1;
+                }
+                __syncwarp();
+                finish_point(P, S, g, bg, k, W);
+                __syncwarp();
             }
-            // ---- increment = rho . z  (oi.cpp:315-317)
-            double dx = (double) c_rho * z;
-            #pragma unroll
-            for(int off = 16; off > 0; off >>= 1) dx += shfl_double(dx, lane ^ off);
-            if(lane == 0) write_result(P, g, bg, dx, avar, dmax, dmin);
-            __syncwarp();
         }
     }
 }
@@ -634,6 +853,7 @@ int gpp_optimal_interpolation_device(const gpp_points* cbp, int first, int count
     const int sms = sm_count();
     if(kcap <= FAST_K && structure_is_symmetric(*structure)) {
         const size_t smem = sizeof(FastSmem) * WARPS_PER_CTA + sizeof(unsigned short) * 512;
+        static_assert(sizeof(FastSmem) * WARPS_PER_CTA + 1024 <= 113 * 1024, "two CTAs per SM");
         const int mode = structure_mode(*structure);
         GPP_CUDA(cudaFuncSetAttribute(oi_fast_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
         GPP_CUDA(cudaFuncSetAttribute(oi_fast_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
