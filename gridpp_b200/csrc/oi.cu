@@ -65,7 +65,7 @@ constexpr int NCAND = 64;           // capacity of a run's candidate list (2 slo
 struct FastSmem {
     unsigned long long key[64];     // candidate keys (oi.cuh)
     double M[32 * 33];              // augmented symmetric matrix, row-major with stride 33
-    double colbuf[2][32];           // pivot column broadcast, double-buffered
+    double colbuf[2][64];           // pivot column broadcast, double-buffered (entries 32.. are padding for the shifted reads)
     double sd[32];                  // innovations of the selection
     int pos[64];                    // candidate slots in the observation table
     int c_pos[32];                  // the selection in canonical order (ascending original index)
@@ -116,7 +116,7 @@ __device__ __noinline__ void solve_selected(const OiParams& P, FastSmem& S, cons
         const Pt a = {S.sx[j], S.sy[j], S.sz[j], S.selev[j], S.slaf[j]};
         const Pt b = {S.sx[i], S.sy[i], S.sz[i], S.selev[i], S.slaf[i]};
         const float hdist = straight_distance(a.x, a.y, a.z, b.x, b.y, b.z);
-        double v = (double) corr_mode<SMODE>(P.s, a, b, hdist);
+        double v = (double) corr_call<SMODE>(P.s, a, b, hdist);
         if(i == j) v = __dadd_rn(v, (double) S.sratio[j]);   // lP + lR, oi.cpp:315
         S.M[j * 33 + i] = v;
         S.M[i * 33 + j] = v;
@@ -136,28 +136,32 @@ __device__ __noinline__ void solve_selected(const OiParams& P, FastSmem& S, cons
     W.dmax = dmax;
     W.dmin = dmin;
     __syncwarp();
-    double a[32];
-    #pragma unroll
-    for(int i = 0; i < 32; i++) a[i] = S.M[lane * 33 + i];
     // ---- Gauss-Jordan on the k observation rows, pivots on the diagonal (SPD: no pivoting needed). By symmetry
     // of the not-yet-eliminated block the pivot ROW equals the pivot COLUMN, which is spread over the lanes: one
-    // shared store per lane broadcasts it.
-    double my_inv = 0.0;
+    // shared store per lane broadcasts it. The loop is ROLLED (a fully unrolled triangular version is 25 KB of
+    // code and stalls on instruction fetch): the lane's row lives in a register window that shifts left by one
+    // column per step, so that the pivot column is always a[0] and every step runs the same 30-FMA body.
+    double a[FAST_K];
     #pragma unroll
-    for(int c = 0; c < FAST_K; c++) {
-        if(c < k) {
-            const double my = a[c];
-            const double inv = __drcp_rn(shfl_double(my, c));
-            S.colbuf[c & 1][lane] = my;
-            const double f = lane == c ? 0.0 : my * inv;
-            if(lane == c) my_inv = inv;
-            __syncwarp();
-            #pragma unroll
-            for(int i = c + 1; i < 32; i++) a[i] = fma(-f, S.colbuf[c & 1][i], a[i]);
-        }
+    for(int i = 0; i < FAST_K; i++) a[i] = S.M[lane * 33 + i];
+    double rr = S.M[lane * 33 + 30], rd = S.M[lane * 33 + 31];   // the rho and d columns of this lane's row
+    double my_inv = 0.0;
+    for(int c = 0; c < k; c++) {
+        const double my = a[0];
+        const double inv = __drcp_rn(shfl_double(my, c));
+        double* cb = S.colbuf[c & 1];
+        cb[lane] = my;
+        const double f = lane == c ? 0.0 : my * inv;
+        if(lane == c) my_inv = inv;
+        __syncwarp();
+        const double* cbc = cb + c;   // cbc[j] = pivot-row entry of column c + j (columns past 29 feed slots that are never read)
+        #pragma unroll
+        for(int j = 1; j < FAST_K; j++) a[j - 1] = fma(-f, cbc[j], a[j]);
+        rr = fma(-f, cb[30], rr);
+        rd = fma(-f, cb[31], rd);
     }
-    W.z = lane < k ? a[31] * my_inv : 0.0;      // z = (P+R)^-1 d, one component per lane
-    W.avar = -shfl_double(a[30], 30);           // rho'(P+R)^-1 rho (oi.cpp:336)
+    W.z = lane < k ? rd * my_inv : 0.0;       // z = (P+R)^-1 d, one component per lane
+    W.avar = -shfl_double(rr, 30);            // rho'(P+R)^-1 rho (oi.cpp:336)
     W.prev_orig = lane < k ? S.c_orig[lane] : -1;
     W.prev_k = k;
 }
@@ -369,14 +373,14 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 2) oi_fast_kernel(const __
                 if(h0 && q0.x > lo0 && q0.x < hi0 && q0.y > lo1 && q0.y < hi1 && q0.z > lo2 && q0.z < hi2) {
                     const float dist = straight_distance(q0.x, q0.y, q0.z, p1.x, p1.y, p1.z);
                     if(dist <= P.R) {
-                        const float rho = corr_background_mode<SMODE>(P.s, p1, q0, dist);
+                        const float rho = corr_background_call<SMODE>(P.s, p1, q0, dist);
                         if(rho > 0.f) key0 = cand_key(rho, orig0);
                     }
                 }
                 if(h1 && q1.x > lo0 && q1.x < hi0 && q1.y > lo1 && q1.y < hi1 && q1.z > lo2 && q1.z < hi2) {
                     const float dist = straight_distance(q1.x, q1.y, q1.z, p1.x, p1.y, p1.z);
                     if(dist <= P.R) {
-                        const float rho = corr_background_mode<SMODE>(P.s, p1, q1, dist);
+                        const float rho = corr_background_call<SMODE>(P.s, p1, q1, dist);
                         if(rho > 0.f) key1 = cand_key(rho, orig1);
                     }
                 }

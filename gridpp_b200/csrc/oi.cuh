@@ -101,7 +101,7 @@ __device__ __forceinline__ int gather_candidates(const ObsView& obs, const gpp_s
                         ok = dist <= R;   // within_radius, kdtree.cpp:247-260
                         if(ok) {
                             const Pt p2 = {ox, oy, oz, obs.elev[i], obs.laf[i]};
-                            rho = corr_background_mode<SMODE>(s, p1, p2, dist);   // oi.cpp:250
+                            rho = corr_background_call<SMODE>(s, p1, p2, dist);   // oi.cpp:250
                             ok = rho > 0.f;                                        // oi.cpp:253
                         }
                     }

@@ -141,6 +141,16 @@ template <>
 __device__ __forceinline__ float corr_background_mode<1>(const gpp_structure& s, const Pt& p1, const Pt& p2, float hdist) {
     return term_corr_typed(GPP_STRUCT_BARNES, s.term[0], hdist, p1.elev, p1.laf, p2.elev, p2.laf);
 }
+// Out-of-line forms for the OI kernels: the evaluation is ~60 instructions and has several call sites per kernel;
+// inlining every one of them made the hot kernel 119 KB of code, which stalled on instruction fetch.
+template <int SMODE>
+__device__ __noinline__ float corr_call(const gpp_structure& s, const Pt& p1, const Pt& p2, float hdist) {
+    return corr_mode<SMODE>(s, p1, p2, hdist);
+}
+template <int SMODE>
+__device__ __noinline__ float corr_background_call(const gpp_structure& s, const Pt& p1, const Pt& p2, float hdist) {
+    return corr_background_mode<SMODE>(s, p1, p2, hdist);
+}
 inline int structure_mode(const gpp_structure& s) {
     return (s.n_terms == 1 && !s.has_cv && s.term[0].type == GPP_STRUCT_BARNES) ? 1 : 0;
 }
