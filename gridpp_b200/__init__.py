@@ -226,6 +226,8 @@ class Grid:
         e = elevs.ravel() if elevs.shape == lats.shape and lats.size else None
         l = lafs.ravel() if lafs.shape == lats.shape and lats.size else None
         self._set = _PointSet(lats.ravel(), lons.ravel(), e, l, type)
+        if lats.size:
+            _check(_libc.gpp_points_set_shape(self._set._handle, self._shape[0], self._shape[1]))
 
     def size(self):
         return _np.array(self._shape, dtype=_np.int32)

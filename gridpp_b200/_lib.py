@@ -55,6 +55,7 @@ _proto("gpp_structure_cross_validation", C.c_int, sp, sp, C.c_float)
 _proto("gpp_structure_corr_host", C.c_int, sp, fp, fp, C.c_int, C.c_int, fp)
 _proto("gpp_points_create", C.c_int, fp, fp, fp, fp, C.c_int, C.c_int, C.POINTER(vp))
 _proto("gpp_points_destroy", None, vp)
+_proto("gpp_points_set_shape", C.c_int, vp, C.c_int, C.c_int)
 _proto("gpp_points_size", C.c_int, vp)
 _proto("gpp_points_coordinate_type", C.c_int, vp)
 _proto("gpp_points_get_xyz", C.c_int, vp, fp, fp, fp)
@@ -76,7 +77,7 @@ _proto("gpp_neighbourhood_quantile_fast_device", C.c_int, vp, C.c_int, C.c_int, 
 EXPORTS = [
     "gpp_version", "gpp_last_error", "gpp_device_count", "gpp_set_device", "gpp_device_synchronize",
     "gpp_kernel_launch_count", "gpp_measure_fp64_fma_peak", "gpp_structure_init", "gpp_structure_multiple", "gpp_structure_cross_validation",
-    "gpp_structure_corr_host", "gpp_points_create", "gpp_points_destroy", "gpp_points_size",
+    "gpp_structure_corr_host", "gpp_points_create", "gpp_points_destroy", "gpp_points_set_shape", "gpp_points_size",
     "gpp_points_coordinate_type", "gpp_points_get_xyz", "gpp_points_nearest_host", "gpp_points_neighbours_host",
     "gpp_points_closest_host", "gpp_nearest_host", "gpp_optimal_interpolation_host", "gpp_oi_obs_create",
     "gpp_oi_obs_destroy", "gpp_optimal_interpolation_device", "gpp_optimal_interpolation_ensi_host",

@@ -39,6 +39,8 @@ struct OiParams {
     float R;
     int k;                           // max observations per point (> 0)
     int allow_extrapolation;
+    int tile_nx;                     // > 0: the range is whole rows of a grid with this row length -> 4 x 4 tiles
+    unsigned char* lru;              // per-warp cache of solved systems (LRU_ENTRIES x LruEntry), global memory
 };
 
 // oi.cpp:318-337: optional clamp, then output and analysis variance
@@ -77,6 +79,7 @@ struct FastSmem {
     float cand_x[NCAND], cand_y[NCAND], cand_z[NCAND], cand_elev[NCAND], cand_laf[NCAND];
     int cand_pos[NCAND], cand_orig[NCAND];
     float px[RUN], py[RUN], pz[RUN], pelev[RUN], plaf[RUN], pbg[RUN];
+    int pit[RUN];                   // offset of each point of the run inside the range
 };
 
 // State a warp carries from point to point: the last system it solved.
@@ -84,8 +87,55 @@ struct FastSmem {
 //   of (P+R)^-1 d), dmax / dmin (extreme innovations of the set), dirty (non-zero extent of S.M).
 struct WarpState {
     int prev_orig, prev_k, dirty;
+    unsigned clock;
     double z, dmax, dmin, avar;
 };
+
+// A solved system kept for reuse: the set (canonical original indices), z = (P+R)^-1 d and the innovation extremes.
+constexpr int LRU_ENTRIES = 4;
+constexpr int RUNS_PER_CHUNK = 16;   // consecutive runs (tiles) handled by one warp, so that the cache sees neighbours
+struct LruEntry {
+    double z[32];
+    double dmax, dmin;
+    int orig[32];
+    int k;
+    unsigned stamp;    // last use (0 = empty)
+    int pad[2];
+};
+
+// Look the canonical set S.c_orig[0..k) up in the warp's cache; on a hit load its solution into W.
+__device__ __forceinline__ bool lru_lookup(LruEntry* cache, const FastSmem& S, int k, unsigned now, WarpState& W) {
+    const int lane = (int) lane_id();
+    const int mine = lane < k ? S.c_orig[lane] : -1;
+    for(int e = 0; e < LRU_ENTRIES; e++) {
+        LruEntry& E = cache[e];
+        if(E.stamp == 0 || E.k != k) continue;
+        if(__all_sync(0xffffffffu, E.orig[lane] == mine)) {
+            W.z = E.z[lane];
+            W.dmax = E.dmax;
+            W.dmin = E.dmin;
+            W.prev_orig = mine;
+            W.prev_k = k;
+            if(lane == 0) E.stamp = now;
+            __syncwarp();
+            return true;
+        }
+    }
+    return false;
+}
+__device__ __forceinline__ void lru_store(LruEntry* cache, int k, unsigned now, const WarpState& W) {
+    const int lane = (int) lane_id();
+    int victim = 0;
+    unsigned oldest = cache[0].stamp;
+    for(int e = 1; e < LRU_ENTRIES; e++)
+        if(cache[e].stamp < oldest) { oldest = cache[e].stamp; victim = e; }
+    __syncwarp();
+    LruEntry& E = cache[victim];
+    E.z[lane] = W.z;
+    E.orig[lane] = W.prev_orig;
+    if(lane == 0) { E.dmax = W.dmax; E.dmin = W.dmin; E.k = k; E.stamp = now; }
+    __syncwarp();
+}
 
 // Assemble P + R for the k observations staged in canonical order in S.c_pos / S.c_rho and solve for
 // z = (P+R)^-1 d by Gauss-Jordan in registers (lane j = row j of the symmetric augmented matrix
@@ -184,7 +234,7 @@ __device__ __forceinline__ void keep_background(const OiParams& P, int g, float 
 // Per-point path: gather from the bucket grid, select, canonicalise, reuse or solve. Used when a run's candidate
 // list does not fit NCAND slots (dense observations, scattered points).
 template <int SMODE>
-__device__ __noinline__ void analyse_point(const OiParams& P, FastSmem& S, const unsigned short* lut, int g, WarpState& W) {
+__device__ __noinline__ void analyse_point(const OiParams& P, FastSmem& S, const unsigned short* lut, LruEntry* cache, int g, WarpState& W) {
     const int lane = (int) lane_id();
     const CandBuf cb = {S.key, S.pos};
     const bool need_var = P.analysis_variance != nullptr;
@@ -214,7 +264,14 @@ __device__ __noinline__ void analyse_point(const OiParams& P, FastSmem& S, const
     }
     const int c_orig = lane < k ? S.c_orig[lane] : -1;
     const bool same = __all_sync(0xffffffffu, c_orig == W.prev_orig) && k == W.prev_k;
-    if(!same || need_var) solve_selected<SMODE>(P, S, lut, k, W);
+    if(need_var) solve_selected<SMODE>(P, S, lut, k, W);
+    else if(!same) {
+        const unsigned now = ++W.clock;
+        if(!lru_lookup(cache, S, k, now, W)) {
+            solve_selected<SMODE>(P, S, lut, k, W);
+            lru_store(cache, k, now, W);
+        }
+    }
     finish_point(P, S, g, bg, k, W);
     __syncwarp();
 }
@@ -255,24 +312,56 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 2) oi_fast_kernel(const __
     for(int e = lane; e < 32 * 33; e += 32) S.M[e] = 0.0;
     __syncthreads();
     WarpState W;
-    W.prev_orig = -2; W.prev_k = -1; W.dirty = 0;
+    W.prev_orig = -2; W.prev_k = -1; W.dirty = 0; W.clock = 0;
     W.z = 0.0; W.dmax = 0.0; W.dmin = 0.0; W.avar = 0.0;
 
-    const int n_runs = (P.count + RUN - 1) / RUN;
-    for(int run = warp_global; run < n_runs; run += warps_total) {
-        const int it0 = run * RUN, npts = min(RUN, P.count - it0);
-        // ---- the run's points, and a bounding sphere (centre = midpoint of first and last point)
+    LruEntry* cache = reinterpret_cast<LruEntry*>(P.lru) + (size_t) warp_global * LRU_ENTRIES;
+    for(int e = lane; e < LRU_ENTRIES; e += 32) cache[e].stamp = 0;
+    __syncwarp();
+    // Runs: 16-point row segments, or 4 x 4 tiles (serpentine inside the tile) when the range is whole grid rows.
+    // A warp takes RUNS_PER_CHUNK consecutive runs at a time so that its cache of solved systems sees neighbours.
+    const int tiles_x = P.tile_nx > 0 ? (P.tile_nx + 3) / 4 : 0;
+    const int rows = P.tile_nx > 0 ? P.count / P.tile_nx : 0;
+    const int n_runs = P.tile_nx > 0 ? tiles_x * ((rows + 3) / 4) : (P.count + RUN - 1) / RUN;
+    const int n_chunks = (n_runs + RUNS_PER_CHUNK - 1) / RUNS_PER_CHUNK;
+    for(int chunk = warp_global; chunk < n_chunks; chunk += warps_total)
+    for(int run = chunk * RUNS_PER_CHUNK; run < min((chunk + 1) * RUNS_PER_CHUNK, n_runs); run++) {
+        // ---- the run's points (offsets into the range), and a bounding sphere
+        int npts, my_it = 0;
+        if(P.tile_nx > 0) {
+            const int ty = run / tiles_x, tx = run - ty * tiles_x;
+            const int h = min(4, rows - 4 * ty), wdt = min(4, P.tile_nx - 4 * tx);
+            npts = h * wdt;
+            if(lane < npts) {
+                const int i = lane / wdt, j = lane - i * wdt;
+                my_it = (4 * ty + i) * P.tile_nx + 4 * tx + ((i & 1) ? wdt - 1 - j : j);
+            }
+        }
+        else {
+            npts = min(RUN, P.count - run * RUN);
+            my_it = run * RUN + lane;
+        }
         float ext = 0.f;
         {
             float x = 0.f, y = 0.f, z = 0.f;
             if(lane < npts) {
-                const int g = P.first + it0 + lane;
+                const int g = P.first + my_it;
                 x = P.gx[g]; y = P.gy[g]; z = P.gz[g];
                 S.px[lane] = x; S.py[lane] = y; S.pz[lane] = z;
                 S.pelev[lane] = P.gelev[g]; S.plaf[lane] = P.glaf[g]; S.pbg[lane] = P.background[g];
+                S.pit[lane] = my_it;
             }
             __syncwarp();
-            const float cx = 0.5f * (S.px[0] + S.px[npts - 1]), cy = 0.5f * (S.py[0] + S.py[npts - 1]), cz = 0.5f * (S.pz[0] + S.pz[npts - 1]);
+            // centre of the run: mean of its points (any centre is correct; a central one keeps the list short)
+            float sx_ = x, sy_ = y, sz_ = z;
+            #pragma unroll
+            for(int off = 16; off > 0; off >>= 1) {
+                sx_ += __shfl_xor_sync(0xffffffffu, sx_, off);
+                sy_ += __shfl_xor_sync(0xffffffffu, sy_, off);
+                sz_ += __shfl_xor_sync(0xffffffffu, sz_, off);
+            }
+            const float inv_n = 1.f / (float) npts;
+            const float cx = sx_ * inv_n, cy = sy_ * inv_n, cz = sz_ * inv_n;
             if(lane < npts) ext = sqrtf((x - cx) * (x - cx) + (y - cy) * (y - cy) + (z - cz) * (z - cz));
             #pragma unroll
             for(int off = 16; off > 0; off >>= 1) ext = fmaxf(ext, __shfl_xor_sync(0xffffffffu, ext, off));
@@ -311,7 +400,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 2) oi_fast_kernel(const __
             __syncwarp();
             if(overflow) {
                 // too many candidates for the lane-resident list: analyse the run point by point
-                for(int i = 0; i < npts; i++) analyse_point<SMODE>(P, S, lut, P.first + it0 + i, W);
+                for(int i = 0; i < npts; i++) analyse_point<SMODE>(P, S, lut, cache, P.first + S.pit[i], W);
                 continue;
             }
             // ---- sort the candidates by original index (rank by counting) and load their coordinates
@@ -362,7 +451,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 2) oi_fast_kernel(const __
             }
             // ---- the points of the run
             for(int i = 0; i < npts; i++) {
-                const int g = P.first + it0 + i;
+                const int g = P.first + S.pit[i];
                 const float bg = S.pbg[i];
                 if(!is_valid(bg)) { keep_background(P, g, bg); continue; }   // oi.cpp:223
                 const Pt p1 = {S.px[i], S.py[i], S.pz[i], S.pelev[i], S.plaf[i]};
@@ -435,7 +524,14 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 2) oi_fast_kernel(const __
                     if(s0) { S.c_pos[row0] = S.cand_pos[lane]; S.c_orig[row0] = orig0; }
                     if(s1) { S.c_pos[row1] = S.cand_pos[lane + 32]; S.c_orig[row1] = orig1; }
                     __syncwarp();
-                    solve_selected<SMODE>(P, S, lut, k, W);
+                    if(need_var) solve_selected<SMODE>(P, S, lut, k, W);
+                    else {
+                        const unsigned now = ++W.clock;
+                        if(!lru_lookup(cache, S, k, now, W)) {
+                            solve_selected<SMODE>(P, S, lut, k, W);
+                            lru_store(cache, k, now, W);
+                        }
+                    }
                     T0 = sel0;
                     T1 = sel1;
                 }
@@ -845,6 +941,8 @@ int gpp_optimal_interpolation_device(const gpp_points* cbp, int first, int count
     P.s = *structure;
     P.R = structure->term[0].loc_dist;
     P.allow_extrapolation = allow_extrapolation;
+    P.tile_nx = 0;
+    P.lru = nullptr;
 
     int kcap = max_points > 0 ? std::min(max_points, obs->n_valid) : obs->n_valid;
     if(max_points == 0 && kcap > FAST_K) {
@@ -861,11 +959,21 @@ int gpp_optimal_interpolation_device(const gpp_points* cbp, int first, int count
         const int mode = structure_mode(*structure);
         GPP_CUDA(cudaFuncSetAttribute(oi_fast_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
         GPP_CUDA(cudaFuncSetAttribute(oi_fast_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        const long long runs = ((long long) count + RUN - 1) / RUN;
-        const long long want = (runs + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+        // whole rows of a known grid -> 4 x 4 tiles
+        P.tile_nx = (bp->shape_nx > 0 && first % bp->shape_nx == 0 && count % bp->shape_nx == 0) ? bp->shape_nx : 0;
+        const long long runs = P.tile_nx > 0 ? (long long) ((P.tile_nx + 3) / 4) * ((count / P.tile_nx + 3) / 4) : ((long long) count + RUN - 1) / RUN;
+        const long long chunks = (runs + RUNS_PER_CHUNK - 1) / RUNS_PER_CHUNK;
+        const long long want = (chunks + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
         const unsigned grid = (unsigned) std::max<long long>(1, std::min<long long>(want, (long long) sms * 2));   // 2 resident CTAs per SM
-        if(mode == 1) GPP_LAUNCH(oi_fast_kernel<1>, grid, WARPS_PER_CTA * 32, smem, stream, P);
-        else GPP_LAUNCH(oi_fast_kernel<0>, grid, WARPS_PER_CTA * 32, smem, stream, P);
+        unsigned char* lru = nullptr;
+        GPP_CUDA(cudaMallocAsync((void**) &lru, sizeof(LruEntry) * LRU_ENTRIES * (size_t) grid * WARPS_PER_CTA, stream));
+        P.lru = lru;
+        if(mode == 1) oi_fast_kernel<1><<<grid, WARPS_PER_CTA * 32, smem, stream>>>(P);
+        else oi_fast_kernel<0><<<grid, WARPS_PER_CTA * 32, smem, stream>>>(P);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        cudaError_t err = cudaGetLastError();
+        cudaFreeAsync(lru, stream);
+        if(err != cudaSuccess) return fail(GPP_ERR_CUDA, "CUDA error %s launching oi_fast_kernel: %s", cudaGetErrorName(err), cudaGetErrorString(err));
         return GPP_OK;
     }
     // general path

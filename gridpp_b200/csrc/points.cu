@@ -394,6 +394,13 @@ int gpp_points_create(const float* lats, const float* lons, const float* elevs, 
 }
 
 void gpp_points_destroy(gpp_points* p) { delete p; }
+int gpp_points_set_shape(gpp_points* p, int ny, int nx) {
+    if(!p) return fail(GPP_ERR_INVALID_ARGUMENT, "points must not be NULL");
+    if(ny < 0 || nx < 0 || (long long) ny * nx != p->n) return fail(GPP_ERR_INVALID_ARGUMENT, "shape %d x %d does not match %d points", ny, nx, p->n);
+    p->shape_ny = ny;
+    p->shape_nx = nx;
+    return GPP_OK;
+}
 int gpp_points_size(const gpp_points* p) { return p ? p->n : 0; }
 int gpp_points_coordinate_type(const gpp_points* p) { return p ? p->type : GPP_GEODETIC; }
 
