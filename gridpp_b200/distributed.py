@@ -7,8 +7,8 @@
   those rows with point-to-point sends (NCCL over NVLink for CUDA tensors, gloo for CPU tensors in the tests);
   the filter then runs on the tile-with-halo through the ``*_device`` entry points with ``row0`` / ``n_rows_out``.
 
-The compute callables are injectable so that the plumbing can be tested on CPU with the oracle standing in for
-the CUDA kernels (tests/test_distributed_cpu.py).
+The compute callable defaults to the CUDA device entry point; tests/test_distributed_cpu.py injects a stand-in so
+that the exchange plumbing itself can be exercised with gloo on a box without a GPU.
 """
 import torch
 import torch.distributed as dist
