@@ -17,6 +17,11 @@
 
 using namespace gpp;
 
+namespace gpp {
+int nbh_tma_try(const float* d_input, int n_rows_in, int nx, int row0, int n_rows_out, int hw, int statistic, float* d_output,
+                cudaStream_t stream, int* handled);   // neighbourhood_tma.cu
+}
+
 namespace {
 
 constexpr int NT = 256;        // threads per CTA = staged columns per strip
@@ -528,6 +533,11 @@ int gpp_neighbourhood_device(const float* d_input, int n_rows_in, int nx, int ro
     if(n_rows_out == 0 || nx == 0) return GPP_OK;
     TileArgs a = {d_input, d_output, n_rows_in, nx, row0, n_rows_out, halfwidth};
     const bool minmax = statistic == GPP_MIN || statistic == GPP_MAX;
+    {   // copy-engine (TMA) kernels first; they decline shapes they do not cover
+        int handled = 0;
+        GPP_TRY(nbh_tma_try(d_input, n_rows_in, nx, row0, n_rows_out, halfwidth, statistic, d_output, stream, &handled));
+        if(handled) return GPP_OK;
+    }
     if(halfwidth <= HW_FUSED_MAX) {
         const int w = 2 * halfwidth + 1, TX = NT - 2 * halfwidth;
         dim3 grid((nx + TX - 1) / TX, (n_rows_out + CHUNK - 1) / CHUNK);

@@ -343,6 +343,59 @@ def test_neighbourhood_row_tiles_equal_whole(gpp):
         assert_bit_exact(whole.cpu().numpy(), gpp.neighbourhood(f, hw, st))
 
 
+def test_neighbourhood_copy_engine_path(gpp, orc):
+    """Shapes the TMA-staged kernels take (row length a multiple of 4, >= 256): missing values, infinities (invalid,
+    util.cpp:16-18), windows clipped on every edge, chunk/strip seams, and row tiles with halo (multi-GPU form)."""
+    import torch
+    from gridpp_b200 import device as gd
+    rng = np.random.default_rng(77)
+    for shape in ((300, 512), (37, 256), (1000, 260), (9, 1024)):
+        f = (rng.uniform(size=shape) * 10 - 3).astype(f32)
+        f[rng.uniform(size=shape) < 0.02] = np.nan
+        f[rng.uniform(size=shape) < 0.002] = np.inf
+        f[rng.uniform(size=shape) < 0.002] = -np.inf
+        f[5:30, 100:140] = np.nan
+        for hw in (1, 3, 7, 8, 12, 15, 31):
+            for name, st in STATS.items():
+                got, want = gpp.neighbourhood(f, hw, st), orc.neighbourhood(f, hw, st)
+                if name in ("count", "min", "max"):
+                    assert_bit_exact(got, want, "%s hw=%d %s" % (shape, hw, name))
+                else:
+                    w = min(2 * hw + 1, shape[0]) * min(2 * hw + 1, shape[1])
+                    assert_close(got, want, 10.0 * (1 if name == "mean" else w), 1e-6, "%s hw=%d %s" % (shape, hw, name))
+    # no missing values at all: the kernels' analytic-count path
+    f = (rng.uniform(size=(500, 768)) * 10).astype(f32)
+    for hw in (2, 7, 15):
+        for name, st in STATS.items():
+            got, want = gpp.neighbourhood(f, hw, st), orc.neighbourhood(f, hw, st)
+            if name in ("count", "min", "max"):
+                assert_bit_exact(got, want, "clean hw=%d %s" % (hw, name))
+            else:
+                assert_close(got, want, 10.0 * (1 if name == "mean" else (2 * hw + 1) ** 2), 1e-6, "clean hw=%d %s" % (hw, name))
+    # high dynamic range next to ordinary values
+    f = rng.uniform(size=(300, 400)).astype(f32)
+    f[100, 100] = 1e9
+    got, want = gpp.neighbourhood(f, 7, gpp.Mean), orc.neighbourhood(f, 7, gpp.Mean)
+    far = np.ones(f.shape, bool)
+    far[92:109, 92:109] = False
+    assert_close(got[far], want[far], 1.0, 1e-6, "dynamic range (outside the spike's window)")
+    assert_close(got, want, 1e9 / 225, 1e-6, "dynamic range (everywhere)")
+    # row tiles with halo equal the whole field, bit for bit
+    ny, nx, hw = 300, 260, 7
+    f = rng.uniform(size=(ny, nx)).astype(f32)
+    f[rng.uniform(size=f.shape) < 0.01] = np.nan
+    d = torch.from_numpy(f).cuda()
+    for st in (gpp.Mean, gpp.Min, gpp.Max, gpp.Count):
+        whole = gd.neighbourhood(d, hw, st)
+        tiles = []
+        for r0, r1 in ((0, 100), (100, 101), (101, 300)):
+            lo, hi = max(0, r0 - hw), min(ny, r1 + hw)
+            tiles.append(gd.neighbourhood(d[lo:hi].contiguous(), hw, st, row0=r0 - lo, n_rows_out=r1 - r0))
+        torch.cuda.synchronize()
+        got = torch.cat(tiles)
+        assert torch.equal(torch.nan_to_num(got, nan=-777.0), torch.nan_to_num(whole, nan=-777.0))
+
+
 def test_quantile_fast_golden(gpp):
     g = golden("quantile_fast")
     for hw in (1, 7, 15):
