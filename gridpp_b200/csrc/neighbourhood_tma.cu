@@ -5,7 +5,7 @@
 // A CTA of 256 threads owns a strip of 256 staged columns (TX output columns plus `hw` halo columns on each side)
 // and walks down a chunk of output rows. One elected thread keeps a ring of NS stages of 8 rows x 256 columns in
 // flight: each stage is ONE cp.async.bulk.tensor copy that lands in shared memory and completes an mbarrier; cells
-// outside the field arrive as NaN (= gridpp's missing value), which is how the window gets clipped at the domain
+// outside the field arrive as zero (sums) or NaN (extremes), which is how the window gets clipped at the domain
 // edges (neighbourhood.cpp:104-107) without a special case. Thread t owns staged column t:
 //   vertical pass    per row: the entering value is added to the column's window state, the leaving one (still in
 //                    the ring, 2 hw + 1 rows older) removed; the state of each of the 8 rows of a batch is written
@@ -21,7 +21,7 @@ using namespace gpp;
 
 namespace gpp {
 
-int make_field_tensor_map(CUtensorMap* map, const float* base, int rows, int nx, int box_rows, int box_cols) {
+int make_field_tensor_map(CUtensorMap* map, const float* base, int rows, int nx, int box_rows, int box_cols, bool nan_fill) {
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -42,7 +42,7 @@ int make_field_tensor_map(CUtensorMap* map, const float* base, int rows, int nx,
     cuuint32_t estr[2] = {1, 1};
     CUresult rc = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA);
+                         nan_fill ? CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA : CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if(rc != CUDA_SUCCESS) return fail(GPP_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int) rc);
     return GPP_OK;
 }
@@ -54,10 +54,16 @@ namespace {
 constexpr int NT = 256;              // threads per CTA = staged columns per strip
 constexpr int RB = 8;                // rows per stage = output rows per batch
 constexpr int SEG = 8;               // consecutive pixels per thread in the horizontal pass
-constexpr int LROW = NT + NT / 8;    // line-buffer row length: element e lives at e + e / 8 (bank-conflict padding)
 constexpr int PREFETCH = 2;          // stages in flight beyond the ones the window needs
 constexpr int RCP_MAX = 1024;
 constexpr unsigned STAGE_BYTES = RB * NT * sizeof(float);
+// Line buffers (one record per staged column and batch row) are padded against bank conflicts of the horizontal
+// pass, in which lane l starts at column 8 l: 8-byte records get 2 pad records per 8 (lane stride 80 B: conflict-free
+// 16-byte loads), 4-byte records 4 pad records per 8 (lane stride 48 B).
+constexpr int LROW_D = NT + NT / 4;  // doubles (and the int counts that mirror them)
+constexpr int LROW_F = NT + NT / 2;  // floats
+__device__ __forceinline__ int pad_d(int e) { return e + 2 * (e >> 3); }
+__device__ __forceinline__ int pad_f(int e) { return e + 4 * (e >> 3); }
 
 struct TmaArgs {
     float* out;
@@ -66,7 +72,7 @@ struct TmaArgs {
     int TX;              // output columns per strip, a multiple of SEG
     int P;               // stages that must have landed before the first output row: ceil(2 hw / RB)
     int NS;              // stages in the ring: P + 1 + PREFETCH
-    int n_rcp;           // entries of the reciprocal table (0: divide)
+    int n_rcp;           // entries of the reciprocal table
     int HL;              // staged columns to the left of the strip: hw rounded up to a multiple of 4 (the copy engine
                          // needs 16-byte aligned box origins); the first HL - hw of them are not part of any window
 };
@@ -119,25 +125,88 @@ __device__ __forceinline__ void store_segment(const TmaArgs& a, int y, int x, co
 // ------------------------------------------------------------------ mean / sum / count ----------------
 // neighbourhood.cpp:45-145. The reference takes four corners of a double summed-area table and of an int count
 // table; here the clipped-window sum is accumulated directly in fp64 (a running column sum that never holds more
-// than 2 hw + 1 values, then a sliding row sum over at most 2 hw + 8 columns) and divided by the valid count.
-// STAT: 0 = Mean, 1 = Sum, 2 = Count
-template <int STAT>
+// than 2 hw + 1 values, then a row-window sum over 2 hw + 1 columns) and divided by the valid count.
+//
+// The copy engine fills cells outside the field with ZERO for these kernels, so a clipped window sums correctly by
+// itself and its valid count is (rows inside) x (columns inside) as long as no cell of the window is missing.
+// Missing values (NaN, +-inf) are handled by poisoning: the running column sum is updated without any test; a
+// non-finite value makes it non-finite for good (inf - inf = NaN), which is checked once per 8-row batch. Only then
+// is the column rebuilt from the rows still in the ring, this time counting the invalid cells, and the CTA takes the
+// horizontal pass that slides the valid counts along with the sums.
+struct ColumnState {
+    double csum;   // sum of the valid values of rows y0 - hw .. y0 + hw - 1 of the column (the next batch's start)
+    int ninv;      // invalid (non-finite) values among them
+};
+
+// Rebuild (poisoned) / annotate (clean) the records of one column for the batch whose first window starts at ring
+// row `first`. Records: line[b] = sum of the valid values of the window of output row y0 + b, cline[b] = their count.
+__device__ __noinline__ void fix_column(const float* ring_col, int NR, int first, int w, bool poisoned, ColumnState& st,
+                                        double* my_line, int* my_cline, int y0, int hw, int n_rows_in, bool col_ok) {
+    if(poisoned) {
+        double s = 0.0;
+        int nv = 0, slot = first;
+        for(int j = 0; j < w - 1; j++) {
+            const float v = ring_col[slot * NT];
+            if(finite_f(v)) s += (double) v; else nv++;
+            slot = slot + 1 == NR ? 0 : slot + 1;
+        }
+        int lead = first;
+        for(int b = 0; b < RB; b++) {
+            const float vn = ring_col[slot * NT];
+            if(finite_f(vn)) s += (double) vn; else nv++;
+            slot = slot + 1 == NR ? 0 : slot + 1;
+            const int y = y0 + b;
+            const int ch = min(y + hw, n_rows_in - 1) - max(y - hw, 0) + 1;
+            my_line[b * LROW_D] = s;
+            my_cline[b * LROW_D] = col_ok ? max(ch - nv, 0) : 0;
+            const float vo = ring_col[lead * NT];
+            if(finite_f(vo)) s -= (double) vo; else nv--;
+            lead = lead + 1 == NR ? 0 : lead + 1;
+        }
+        st.csum = s;
+        st.ninv = nv;
+    }
+    else {
+        for(int b = 0; b < RB; b++) {
+            const int y = y0 + b;
+            const int ch = min(y + hw, n_rows_in - 1) - max(y - hw, 0) + 1;
+            my_cline[b * LROW_D] = col_ok ? max(ch - st.ninv, 0) : 0;
+        }
+    }
+}
+
+// value / count as the reference forms it (double division rounded to float, neighbourhood.cpp:133-142); counts
+// below n_rcp multiply by a tabulated reciprocal instead (differs from the division by at most one rounding of the
+// double quotient, invisible after the rounding to float but for ~1e-9 of the cases)
+template <bool TABLE_ONLY>
+__device__ __forceinline__ float mean_of(double s, int c, const double* rcp, int n_rcp) {
+    if(TABLE_ONLY || c < n_rcp) return (float) (s * rcp[c]);
+    return (float) (s / (double) c);
+}
+
+// STAT: 0 = Mean, 1 = Sum, 2 = Count.  HW > 0: half-width known at compile time (loops unrolled, the row window held
+// in registers); HW == 0: any half-width (a.hw).
+template <int STAT, int HW>
 __global__ void __launch_bounds__(NT, 3) nbh_sum_tma_kernel(const __grid_constant__ CUtensorMap in_map, const TmaArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
-    const int NR = a.NS * RB;
+    constexpr bool STATIC = HW > 0;
+    constexpr bool TAB = STATIC && (2 * HW + 1) * (2 * HW + 1) < RCP_MAX;   // every possible count is tabulated
+    const int hw = STATIC ? HW : a.hw, w = 2 * hw + 1;
+    const int P = STATIC ? (2 * HW + RB - 1) / RB : a.P;
+    const int NS = STATIC ? P + 1 + PREFETCH : a.NS;
+    const int NR = NS * RB;
     float* ring = reinterpret_cast<float*>(smem);                                 // [NS * RB][NT]
-    double* line = reinterpret_cast<double*>(ring + (size_t) NR * NT);           // [RB][LROW] column sums
-    int* cline = reinterpret_cast<int*>(line + RB * LROW);                       // [RB][LROW] column valid counts
-    double* rcp = reinterpret_cast<double*>(cline + RB * LROW);                  // [n_rcp]
+    double* line = reinterpret_cast<double*>(ring + (size_t) NR * NT);           // [RB][LROW_D] column sums
+    int* cline = reinterpret_cast<int*>(line + RB * LROW_D);                     // [RB][LROW_D] column valid counts
+    double* rcp = reinterpret_cast<double*>(cline + RB * LROW_D);                // [n_rcp]
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(rcp + a.n_rcp);
 
     const int tid = threadIdx.x;
-    const int hw = a.hw, w = 2 * hw + 1;
     const int x0 = blockIdx.x * a.TX;
     const int y_begin = a.row0 + blockIdx.y * a.rows_per_cta;
     const int y_end = min(y_begin + a.rows_per_cta, a.row0 + a.n_rows_out);
     const int n_batches = (y_end - y_begin + RB - 1) / RB;
-    const StageRing R = {ring, bars, &in_map, x0 - a.HL, y_begin + hw - RB * a.P, a.NS, a.P + n_batches};
+    const StageRing R = {ring, bars, &in_map, x0 - a.HL, y_begin + hw - RB * P, NS, P + n_batches};
     R.start();
     for(int c = tid; c < a.n_rcp; c += NT) rcp[c] = c > 0 ? 1.0 / (double) c : 0.0;
 
@@ -146,103 +215,129 @@ __global__ void __launch_bounds__(NT, 3) nbh_sum_tma_kernel(const __grid_constan
     // window column e = tid - (HL - hw) of the strip; the HL - hw leftmost staged columns park their records in the
     // unused tail of the line
     const int ecol = tid >= a.HL - hw ? tid - (a.HL - hw) : NT - (a.HL - hw) + tid;
-    const bool in_window = tid >= a.HL - hw;
-    // ---- prime the column window with rows y_begin - hw .. y_begin + hw - 1
-    double csum = 0.0;
-    int ccnt = 0;
-    int rows_in = 0;                 // rows of the current window that lie inside the field (uniform)
-    const int rel0 = RB * a.P - 2 * hw;   // ring row of input row y_begin - hw
-    for(int k = 0; k < a.P; k++) R.wait(k);
-    for(int rel = rel0; rel < RB * a.P; rel++) {
-        const float v = ring[rel * NT + tid];
-        if(finite_f(v)) { csum += (double) v; ccnt++; }
-        const int r = R.r0 + rel;
-        rows_in += (r >= 0 && r < a.n_rows_in) ? 1 : 0;
+    double* const my_line = line + pad_d(ecol);
+    int* const my_cline = cline + pad_d(ecol);
+    const float* const ring_col = ring + tid;
+    const int rel0 = RB * P - 2 * hw;     // ring row of input row y_begin - hw; 0 <= rel0 < RB
+    // ---- prime the column with rows y_begin - hw .. y_begin + hw - 1
+    ColumnState st = {0.0, 0};
+    for(int k = 0; k < P; k++) R.wait(k);
+    for(int rel = rel0; rel < RB * P; rel++) {
+        const float v = ring_col[rel * NT];
+        if(finite_f(v)) st.csum += (double) v; else st.ninv++;
     }
-    int old_slot = rel0;             // ring row of the row that leaves next; rel0 < RB <= NR
-    double* const my_line = line + ecol + (ecol >> 3);
-    int* const my_cline = cline + ecol + (ecol >> 3);
     const int hb = tid >> 5, seg = tid & 31, xo0 = seg * SEG;
     const bool h_active = xo0 < a.TX && x0 + xo0 < a.nx;
-    // staged column (relative to xo0) entering the row window when it slides from pixel p to p + 1
-    int in_off[SEG - 1];
-    #pragma unroll
-    for(int p = 0; p < SEG - 1; p++) in_off[p] = (w + p) + ((w + p) >> 3);
+    const bool strip_inside = x0 - hw >= 0 && x0 + a.TX - 1 + hw < a.nx;   // no window of the strip is clipped sideways
+    const double rc_full = 1.0 / (double) (w * w);
+    int s_new = P % NS, s_old = 0;        // ring slots of the entering stage and of the stage of the first leaving row
 
     for(int i = 0; i < n_batches; i++) {
         const int y0 = y_begin + RB * i;
-        R.wait(a.P + i);
-        const float* newp = ring + (size_t) ((a.P + i) % a.NS) * RB * NT + tid;
+        R.wait(P + i);
         // ---- vertical pass: row y0 + b + hw enters, the record of output row y0 + b is written, row y0 + b - hw leaves
-        bool missing = false;
-        #pragma unroll
-        for(int b = 0; b < RB; b++) {
-            const float vn = newp[b * NT];
-            if(finite_f(vn)) { csum += (double) vn; ccnt++; }
-            const int rn = y0 + b + hw;
-            rows_in += (rn >= 0 && rn < a.n_rows_in) ? 1 : 0;
-            my_line[b * LROW] = csum;
-            my_cline[b * LROW] = ccnt;
-            missing = missing || (in_window && ccnt != (col_ok ? rows_in : 0));
-            const float vo = ring[old_slot * NT + tid];
-            if(finite_f(vo)) { csum -= (double) vo; ccnt--; }
-            const int ro = y0 + b - hw;
-            rows_in -= (ro >= 0 && ro < a.n_rows_in) ? 1 : 0;
-            old_slot = old_slot + 1 == NR ? 0 : old_slot + 1;
+        {
+            const float* newp = ring_col + s_new * (RB * NT);
+            const int s_old2 = s_old + 1 == NS ? 0 : s_old + 1;
+            const float* oldA = ring_col + (s_old * RB + rel0) * NT;           // leaving rows b < RB - rel0
+            const float* oldB = ring_col + (s_old2 * RB + rel0 - RB) * NT;     // leaving rows b >= RB - rel0
+            double csum = st.csum;
+            #pragma unroll
+            for(int b = 0; b < RB; b++) {
+                csum += (double) newp[b * NT];
+                my_line[b * LROW_D] = csum;
+                csum -= (double) (b < RB - rel0 ? oldA[b * NT] : oldB[b * NT]);
+            }
+            st.csum = csum;
         }
-        // line buffer complete; stage i is dead. "missing": some window of this batch holds a missing value inside
-        // the field, so the counts are not the clipped window areas.
-        const bool any_missing = __syncthreads_or(missing) != 0;
-        R.recycle(i);
+        const bool poisoned = !(fabs(st.csum) < INFINITY);
+        const bool any_missing = __syncthreads_or(poisoned || st.ninv > 0) != 0;
+        if(any_missing) {
+            int first = s_old * RB + rel0;
+            fix_column(ring_col, NR, first, w, poisoned, st, my_line, my_cline, y0, hw, a.n_rows_in, col_ok);
+            __syncthreads();
+        }
+        R.recycle(i);          // stage i is dead: every leaving row of later batches lives in a later stage
+        s_new = s_new + 1 == NS ? 0 : s_new + 1;
+        s_old = s_old + 1 == NS ? 0 : s_old + 1;
         // ---- horizontal pass
         const int y = y0 + hb;
         if(h_active && y < y_end) {
-            const double* l = line + hb * LROW + seg * (SEG + 1);    // staged column xo0 + j at l[j + j / 8]
-            const int* lc = cline + hb * LROW + seg * (SEG + 1);
-            double s = 0.0;
-            {
-                int j = 0;
-                const double* lj = l;
-                for(; j + 8 <= w; j += 8, lj += 9) {
-                    #pragma unroll
-                    for(int u = 0; u < 8; u++) s += lj[u];
-                }
-                for(int u = 0; j + u < w; u++) s += lj[u];
-            }
-            float o[SEG];
             const int x = x0 + xo0;
-            if(!any_missing) {
-                // count = (rows of the window inside the field) x (columns inside the field), neighbourhood.cpp:104-107
-                const int ch = min(y + hw, a.n_rows_in - 1) - max(y - hw, 0) + 1;
+            const double* l = line + hb * LROW_D + seg * (SEG + 2);    // window column xo0 + j at l[pad_d(j)]
+            const int* lc = cline + hb * LROW_D + seg * (SEG + 2);
+            float o[SEG];
+            const int ch = min(y + hw, a.n_rows_in - 1) - max(y - hw, 0) + 1;   // rows of the window inside the field
+            const bool full = strip_inside && ch == w;
+            if constexpr(STATIC && HW <= 8) {
+                constexpr int W = 2 * HW + 1, NV = W + SEG - 1;
+                double v[NV + 1];
                 #pragma unroll
-                for(int p = 0; p < SEG; p++) {
-                    const int cw = min(x + p + hw, a.nx - 1) - max(x + p - hw, 0) + 1;
-                    const int c = ch * cw;
-                    if(STAT == 2) o[p] = (float) c;
-                    else if(STAT == 1) o[p] = (float) s;
-                    else o[p] = c < a.n_rcp ? (float) (s * rcp[c]) : (float) (s / (double) c);   // neighbourhood.cpp:133-142
-                    if(p + 1 < SEG) s += l[in_off[p]] - l[p];
+                for(int q = 0; q < (NV + 1) / 2; q++) {
+                    const double2 t = reinterpret_cast<const double2*>(l)[q + (q >> 2)];
+                    v[2 * q] = t.x;
+                    v[2 * q + 1] = t.y;
+                }
+                double s = 0.0;
+                #pragma unroll
+                for(int j = 0; j < W; j++) s += v[j];
+                if(!any_missing) {
+                    #pragma unroll
+                    for(int p = 0; p < SEG; p++) {
+                        if(STAT == 1) o[p] = (float) s;
+                        else if(full) o[p] = STAT == 2 ? (float) (W * W) : (float) (s * rc_full);
+                        else {
+                            // count = (rows inside the field) x (columns inside the field), neighbourhood.cpp:104-107
+                            const int c = ch * (min(x + p + hw, a.nx - 1) - max(x + p - hw, 0) + 1);
+                            if(STAT == 2) o[p] = (float) c;
+                            else o[p] = mean_of<TAB>(s, c, rcp, a.n_rcp);
+                        }
+                        if(p + 1 < SEG) s += v[W + p] - v[p];
+                    }
+                }
+                else {
+                    int cv[NV + 1];
+                    #pragma unroll
+                    for(int q = 0; q < (NV + 1) / 2; q++) {
+                        const int2 t = reinterpret_cast<const int2*>(lc)[q + (q >> 2)];
+                        cv[2 * q] = t.x;
+                        cv[2 * q + 1] = t.y;
+                    }
+                    int c = 0;
+                    #pragma unroll
+                    for(int j = 0; j < W; j++) c += cv[j];
+                    #pragma unroll
+                    for(int p = 0; p < SEG; p++) {
+                        if(STAT == 2) o[p] = (float) c;
+                        else if(STAT == 1) o[p] = c > 0 ? (float) s : NAN;
+                        else o[p] = c > 0 ? mean_of<TAB>(s, c, rcp, a.n_rcp) : NAN;
+                        if(p + 1 < SEG) {
+                            s += v[W + p] - v[p];
+                            c += cv[W + p] - cv[p];
+                        }
+                    }
                 }
             }
             else {
+                // sliding sums, the records re-read from the line as they enter and leave
+                double s = 0.0;
                 int c = 0;
-                {
-                    int j = 0;
-                    const int* lj = lc;
-                    for(; j + 8 <= w; j += 8, lj += 9) {
-                        #pragma unroll
-                        for(int u = 0; u < 8; u++) c += lj[u];
-                    }
-                    for(int u = 0; j + u < w; u++) c += lj[u];
-                }
+                #pragma unroll 8
+                for(int j = 0; j < w; j++) s += l[pad_d(j)];
+                if(any_missing)
+                    for(int j = 0; j < w; j++) c += lc[pad_d(j)];
                 #pragma unroll
                 for(int p = 0; p < SEG; p++) {
-                    if(STAT == 2) o[p] = (float) c;
-                    else if(STAT == 1) o[p] = c > 0 ? (float) s : NAN;
-                    else o[p] = c > 0 ? (c < a.n_rcp ? (float) (s * rcp[c]) : (float) (s / (double) c)) : NAN;
+                    if(!any_missing && full) o[p] = STAT == 2 ? (float) (w * w) : (STAT == 1 ? (float) s : (float) (s * rc_full));
+                    else {
+                        const int cc = any_missing ? c : ch * (min(x + p + hw, a.nx - 1) - max(x + p - hw, 0) + 1);
+                        if(STAT == 2) o[p] = (float) cc;
+                        else if(STAT == 1) o[p] = cc > 0 ? (float) s : NAN;
+                        else o[p] = cc > 0 ? mean_of<TAB>(s, cc, rcp, a.n_rcp) : NAN;
+                    }
                     if(p + 1 < SEG) {
-                        s += l[in_off[p]] - l[p];
-                        c += lc[in_off[p]] - lc[p];
+                        s += l[pad_d(w + p)] - l[p];
+                        if(any_missing) c += lc[pad_d(w + p)] - lc[p];
                     }
                 }
             }
@@ -254,9 +349,9 @@ __global__ void __launch_bounds__(NT, 3) nbh_sum_tma_kernel(const __grid_constan
 
 // ------------------------------------------------------------------ min / max -------------------------
 // neighbourhood.cpp:146-210: extreme of the valid values in the clipped window. fminf / fmaxf return the other
-// operand when one is NaN, so missing cells (and the NaN the copy engine writes outside the field) drop out by
-// themselves and an all-missing window yields NaN; infinite inputs are "invalid" too (util.cpp:16-18) and are
-// turned into NaN when their stage lands.
+// operand when one is NaN, so missing cells (and the NaN the copy engine writes outside the field for these kernels)
+// drop out by themselves and an all-missing window yields NaN; infinite inputs are "invalid" too (util.cpp:16-18)
+// and are turned into NaN when their stage lands.
 //
 // Eight consecutive windows of width w (w >= 8) over v[0 .. w+6] all contain the core v[7 .. w-1]; window i is
 // ext(suffix-extreme of v[i..6], core, prefix-extreme of v[w .. w+i-1]).
@@ -271,6 +366,7 @@ __device__ __forceinline__ void eight_windows(F v, int w, float (&out)[RB]) {
         #pragma unroll
         for(int i = RB - 2; i >= 0; i--) suf[i] = ext<IS_MAX>(suf[i + 1], v(i));
         float core = v(RB - 1);
+        #pragma unroll
         for(int j = RB; j < w; j++) core = ext<IS_MAX>(core, v(j));
         pre[0] = NAN;
         #pragma unroll
@@ -282,32 +378,36 @@ __device__ __forceinline__ void eight_windows(F v, int w, float (&out)[RB]) {
         #pragma unroll
         for(int i = 0; i < RB; i++) {
             float m = NAN;
+            #pragma unroll
             for(int j = 0; j < w; j++) m = ext<IS_MAX>(m, v(i + j));
             out[i] = m;
         }
     }
 }
 
-template <bool IS_MAX>
+template <bool IS_MAX, int HW>
 __global__ void __launch_bounds__(NT, 3) nbh_minmax_tma_kernel(const __grid_constant__ CUtensorMap in_map, const TmaArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
-    const int NR = a.NS * RB;
+    constexpr bool STATIC = HW > 0;
+    const int hw = STATIC ? HW : a.hw, w = 2 * hw + 1;
+    const int P = STATIC ? (2 * HW + RB - 1) / RB : a.P;
+    const int NS = STATIC ? P + 1 + PREFETCH : a.NS;
+    const int NR = NS * RB;
     float* ring = reinterpret_cast<float*>(smem);                       // [NS * RB][NT]
-    float* line = ring + (size_t) NR * NT;                              // [RB][LROW] column extremes
-    unsigned long long* bars = reinterpret_cast<unsigned long long*>(line + RB * LROW);
+    float* line = ring + (size_t) NR * NT;                              // [RB][LROW_F] column extremes
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(line + RB * LROW_F);
 
     const int tid = threadIdx.x;
-    const int hw = a.hw, w = 2 * hw + 1;
     const int x0 = blockIdx.x * a.TX;
     const int y_begin = a.row0 + blockIdx.y * a.rows_per_cta;
     const int y_end = min(y_begin + a.rows_per_cta, a.row0 + a.n_rows_out);
     const int n_batches = (y_end - y_begin + RB - 1) / RB;
-    const StageRing R = {ring, bars, &in_map, x0 - a.HL, y_begin + hw - RB * a.P, a.NS, a.P + n_batches};
+    const StageRing R = {ring, bars, &in_map, x0 - a.HL, y_begin + hw - RB * P, NS, P + n_batches};
     R.start();
     const int ecol = tid >= a.HL - hw ? tid - (a.HL - hw) : NT - (a.HL - hw) + tid;   // see nbh_sum_tma_kernel
 
-    const int rel0 = RB * a.P - 2 * hw;   // ring row of input row y_begin - hw
-    for(int k = 0; k < a.P; k++) {
+    const int rel0 = RB * P - 2 * hw;     // ring row of input row y_begin - hw
+    for(int k = 0; k < P; k++) {
         R.wait(k);
         float* sp = ring + (size_t) k * RB * NT + tid;
         #pragma unroll
@@ -316,36 +416,61 @@ __global__ void __launch_bounds__(NT, 3) nbh_minmax_tma_kernel(const __grid_cons
     }
     const int hb = tid >> 5, seg = tid & 31, xo0 = seg * SEG;
     const bool h_active = xo0 < a.TX && x0 + xo0 < a.nx;
-    float* const my_line = line + ecol + (ecol >> 3);
+    float* const my_line = line + pad_f(ecol);
     int first = rel0;                     // ring row of the first row of the window of output row y0
+    int s_new = P % NS;
 
     for(int i = 0; i < n_batches; i++) {
         const int y0 = y_begin + RB * i;
-        R.wait(a.P + i);
+        R.wait(P + i);
+        // ---- vertical pass: the windows of the 8 rows of the batch span ring rows first .. first + w + 6, of which
+        // the last 8 are the stage that has just landed (its infinities are replaced on the way)
         {
-            float* sp = ring + (size_t) ((a.P + i) % a.NS) * RB * NT + tid;
+            float* sp = ring + (size_t) s_new * RB * NT + tid;
+            float vnew[RB];
             #pragma unroll
-            for(int b = 0; b < RB; b++)
-                if(fabsf(sp[b * NT]) == INFINITY) sp[b * NT] = NAN;
-        }
-        // ---- vertical pass: the windows of the 8 rows of the batch over ring rows first .. first + w + 6
-        {
+            for(int b = 0; b < RB; b++) {
+                vnew[b] = sp[b * NT];
+                if(fabsf(vnew[b]) == INFINITY) { vnew[b] = NAN; sp[b * NT] = NAN; }
+            }
             float out[RB];
             const float* base = ring + tid;
-            eight_windows<IS_MAX>([&](int j) { int s = first + j; if(s >= NR) s -= NR; return base[s * NT]; }, w, out);
+            if constexpr(STATIC && HW <= 10) {
+                constexpr int W = 2 * HW + 1;
+                float v[W + RB - 1];
+                #pragma unroll
+                for(int j = 0; j < W - 1; j++) { int s = first + j; if(s >= NR) s -= NR; v[j] = base[s * NT]; }
+                #pragma unroll
+                for(int b = 0; b < RB; b++) v[W - 1 + b] = vnew[b];
+                eight_windows<IS_MAX>([&](int j) { return v[j]; }, W, out);
+            }
+            else
+                eight_windows<IS_MAX>([&](int j) { int s = first + j; if(s >= NR) s -= NR; return base[s * NT]; }, w, out);
             #pragma unroll
-            for(int b = 0; b < RB; b++) my_line[b * LROW] = out[b];
+            for(int b = 0; b < RB; b++) my_line[b * LROW_F] = out[b];
         }
         first += RB;
         if(first >= NR) first -= NR;
+        s_new = s_new + 1 == NS ? 0 : s_new + 1;
         __syncthreads();
         R.recycle(i);
-        // ---- horizontal pass over staged columns xo0 .. xo0 + w + 6
+        // ---- horizontal pass over window columns xo0 .. xo0 + w + 6
         const int y = y0 + hb;
         if(h_active && y < y_end) {
-            const float* l = line + hb * LROW + seg * (SEG + 1);
+            const float* l = line + hb * LROW_F + seg * (SEG + 4);
             float o[SEG];
-            eight_windows<IS_MAX>([&](int j) { return l[j + (j >> 3)]; }, w, o);
+            if constexpr(STATIC && HW <= 10) {
+                constexpr int W = 2 * HW + 1, NV = (W + SEG - 1 + 3) / 4 * 4;
+                float v[NV];
+                #pragma unroll
+                for(int q = 0; q < NV / 4; q++) {
+                    const float4 t = reinterpret_cast<const float4*>(l)[q + (q >> 1)];
+                    v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+                }
+                eight_windows<IS_MAX>([&](int j) { return v[j]; }, W, o);
+            }
+            else
+                eight_windows<IS_MAX>([&](int j) { return l[pad_f(j)]; }, w, o);
             store_segment(a, y, x0 + xo0, o);
         }
         __syncthreads();
@@ -353,9 +478,32 @@ __global__ void __launch_bounds__(NT, 3) nbh_minmax_tma_kernel(const __grid_cons
 }
 
 template <class K>
-int prepare_kernel(K kernel, size_t smem) {
+int run_kernel(K kernel, dim3 grid, size_t smem, cudaStream_t stream, const CUtensorMap& map, const TmaArgs& a) {
     GPP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    GPP_LAUNCH(kernel, grid, NT, smem, stream, map, a);
     return GPP_OK;
+}
+
+// half-widths with a fully unrolled instantiation; everything else runs the HW = 0 form
+#define GPP_FOR_STATIC_HW(X) X(1) X(2) X(3) X(5) X(7) X(10) X(15)
+
+template <int STAT>
+int run_sum(int hw, dim3 grid, size_t smem, cudaStream_t stream, const CUtensorMap& map, const TmaArgs& a) {
+    switch(hw) {
+#define X(H) case H: return run_kernel(nbh_sum_tma_kernel<STAT, H>, grid, smem, stream, map, a);
+        GPP_FOR_STATIC_HW(X)
+#undef X
+        default: return run_kernel(nbh_sum_tma_kernel<STAT, 0>, grid, smem, stream, map, a);
+    }
+}
+template <bool IS_MAX>
+int run_minmax(int hw, dim3 grid, size_t smem, cudaStream_t stream, const CUtensorMap& map, const TmaArgs& a) {
+    switch(hw) {
+#define X(H) case H: return run_kernel(nbh_minmax_tma_kernel<IS_MAX, H>, grid, smem, stream, map, a);
+        GPP_FOR_STATIC_HW(X)
+#undef X
+        default: return run_kernel(nbh_minmax_tma_kernel<IS_MAX, 0>, grid, smem, stream, map, a);
+    }
 }
 
 }  // namespace
@@ -382,8 +530,8 @@ int nbh_tma_try(const float* d_input, int n_rows_in, int nx, int row0, int n_row
     a.n_rcp = std::min(RCP_MAX, w * w + 1);
     const bool minmax = statistic == GPP_MIN || statistic == GPP_MAX;
     size_t smem = (size_t) a.NS * STAGE_BYTES + sizeof(unsigned long long) * a.NS;
-    if(minmax) smem += sizeof(float) * RB * LROW;
-    else smem += (sizeof(double) + sizeof(int)) * RB * LROW + sizeof(double) * a.n_rcp;
+    if(minmax) smem += sizeof(float) * RB * LROW_F;
+    else smem += (sizeof(double) + sizeof(int)) * RB * LROW_D + sizeof(double) * a.n_rcp;
     if(smem > 100 * 1024) return GPP_OK;
     // one wave: strips x chunks <= resident CTAs
     const int strips = (nx + a.TX - 1) / a.TX;
@@ -395,14 +543,15 @@ int nbh_tma_try(const float* d_input, int n_rows_in, int nx, int row0, int n_row
     a.rows_per_cta = rows;
     chunks = (n_rows_out + rows - 1) / rows;
     CUtensorMap map;
-    GPP_TRY(make_field_tensor_map(&map, d_input, n_rows_in, nx, RB, NT));
+    // sums: zero fill outside the field; extremes: NaN fill (ignored by fminf / fmaxf)
+    GPP_TRY(make_field_tensor_map(&map, d_input, n_rows_in, nx, RB, NT, minmax));
     dim3 grid(strips, chunks);
     switch(statistic) {
-        case GPP_MEAN: GPP_TRY(prepare_kernel(nbh_sum_tma_kernel<0>, smem)); GPP_LAUNCH(nbh_sum_tma_kernel<0>, grid, NT, smem, stream, map, a); break;
-        case GPP_SUM: GPP_TRY(prepare_kernel(nbh_sum_tma_kernel<1>, smem)); GPP_LAUNCH(nbh_sum_tma_kernel<1>, grid, NT, smem, stream, map, a); break;
-        case GPP_COUNT: GPP_TRY(prepare_kernel(nbh_sum_tma_kernel<2>, smem)); GPP_LAUNCH(nbh_sum_tma_kernel<2>, grid, NT, smem, stream, map, a); break;
-        case GPP_MIN: GPP_TRY(prepare_kernel(nbh_minmax_tma_kernel<false>, smem)); GPP_LAUNCH(nbh_minmax_tma_kernel<false>, grid, NT, smem, stream, map, a); break;
-        case GPP_MAX: GPP_TRY(prepare_kernel(nbh_minmax_tma_kernel<true>, smem)); GPP_LAUNCH(nbh_minmax_tma_kernel<true>, grid, NT, smem, stream, map, a); break;
+        case GPP_MEAN: GPP_TRY(run_sum<0>(hw, grid, smem, stream, map, a)); break;
+        case GPP_SUM: GPP_TRY(run_sum<1>(hw, grid, smem, stream, map, a)); break;
+        case GPP_COUNT: GPP_TRY(run_sum<2>(hw, grid, smem, stream, map, a)); break;
+        case GPP_MIN: GPP_TRY(run_minmax<false>(hw, grid, smem, stream, map, a)); break;
+        case GPP_MAX: GPP_TRY(run_minmax<true>(hw, grid, smem, stream, map, a)); break;
         default: return GPP_OK;
     }
     *handled = 1;

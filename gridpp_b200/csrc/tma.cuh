@@ -10,11 +10,12 @@
 namespace gpp {
 
 // 2-D row-major fp32 tensor of `rows` x `nx` elements at `base`; boxes of box_rows x box_cols elements. Elements of
-// a box that fall outside the tensor are filled with NaN -- exactly gridpp's missing value, so a window clipped at
-// the domain edge (neighbourhood.cpp:104-107) needs no special case in the kernels.
+// a box that fall outside the tensor are filled with NaN (nan_fill: gridpp's missing value) or zero, so a window
+// clipped at the domain edge (neighbourhood.cpp:104-107) needs no special case in the kernels.
 // Requirements of the copy engine: base 16-byte aligned, nx * 4 a multiple of 16, box_cols * 4 a multiple of 16,
-// box dims <= 256.
-int make_field_tensor_map(CUtensorMap* map, const float* base, int rows, int nx, int box_rows, int box_cols);
+// box dims <= 256, and the x coordinate of every box origin a multiple of 4 elements (16 bytes; measured: an
+// unaligned origin raises an illegal-instruction fault).
+int make_field_tensor_map(CUtensorMap* map, const float* base, int rows, int nx, int box_rows, int box_cols, bool nan_fill);
 
 #ifdef __CUDACC__
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned) __cvta_generic_to_shared(p); }
