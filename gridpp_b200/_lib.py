@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libgridpp_b200.so")
+# GPP_B200_LIB: developer override used to A/B kernel builds (profiles/variants.sh); the default is the in-tree library
+LIB_PATH = os.environ.get("GPP_B200_LIB") or os.path.join(HERE, "libgridpp_b200.so")
 
 OK, ERR_INVALID_ARGUMENT, ERR_RUNTIME, ERR_NOT_IMPLEMENTED, ERR_CUDA = range(5)
 

@@ -54,16 +54,30 @@ namespace {
 constexpr int NT = 256;              // threads per CTA = staged columns per strip
 constexpr int RB = 8;                // rows per stage = output rows per batch
 constexpr int SEG = 8;               // consecutive pixels per thread in the horizontal pass
-constexpr int PREFETCH = 2;          // stages in flight beyond the ones the window needs
+#ifndef NBH_PF
+#define NBH_PF 2
+#endif
+#ifndef NBH_MINB_SUM
+#define NBH_MINB_SUM 3
+#endif
+#ifndef NBH_MINB_MM
+#define NBH_MINB_MM 4
+#endif
+constexpr int PREFETCH = NBH_PF;     // stages in flight beyond the ones the window needs
+constexpr int MINB_SUM = NBH_MINB_SUM, MINB_MM = NBH_MINB_MM;   // resident CTAs per SM the kernels are built for
 constexpr int RCP_MAX = 1024;
 constexpr unsigned STAGE_BYTES = RB * NT * sizeof(float);
-// Line buffers (one record per staged column and batch row) are padded against bank conflicts of the horizontal
-// pass, in which lane l starts at column 8 l: 8-byte records get 2 pad records per 8 (lane stride 80 B: conflict-free
-// 16-byte loads), 4-byte records 4 pad records per 8 (lane stride 48 B).
-constexpr int LROW_D = NT + NT / 4;  // doubles (and the int counts that mirror them)
-constexpr int LROW_F = NT + NT / 2;  // floats
-__device__ __forceinline__ int pad_d(int e) { return e + 2 * (e >> 3); }
-__device__ __forceinline__ int pad_f(int e) { return e + 4 * (e >> 3); }
+// Line buffers hold one record per window column and batch row. The vertical pass writes them with consecutive
+// lanes on consecutive columns, the horizontal pass reads them with lane l starting at column 8 l.
+//  * kernels that hold the row window in registers read 16-byte vectors; an XOR swizzle of the 16-byte slots inside
+//    each 128-byte row makes both accesses conflict-free: slot s = 8 r + c is stored at 8 r + (c ^ (r & 7));
+//  * the sliding kernels (large or run-time half-widths) read single records at run-time offsets, where a padded
+//    layout is cheaper to address: 8-byte records get 2 pad records per 8, 4-byte records 4 per 8.
+constexpr int LROW_D = NT + NT / 4;  // doubles per line row (padded form; the swizzled form uses the first NT)
+constexpr int LROW_F = NT + NT / 2;  // floats per line row
+__device__ __forceinline__ int swz_slot(int s) { return (s & ~7) | ((s ^ (s >> 3)) & 7); }
+template <bool SWZ> __device__ __forceinline__ int idx_d(int e) { return SWZ ? ((swz_slot(e >> 1) << 1) | (e & 1)) : e + 2 * (e >> 3); }
+template <bool SWZ> __device__ __forceinline__ int idx_f(int e) { return SWZ ? ((swz_slot(e >> 2) << 2) | (e & 3)) : e + 4 * (e >> 3); }
 
 struct TmaArgs {
     float* out;
@@ -141,7 +155,7 @@ struct ColumnState {
 // Rebuild (poisoned) / annotate (clean) the records of one column for the batch whose first window starts at ring
 // row `first`. Records: line[b] = sum of the valid values of the window of output row y0 + b, cline[b] = their count.
 __device__ __noinline__ void fix_column(const float* ring_col, int NR, int first, int w, bool poisoned, ColumnState& st,
-                                        double* my_line, int* my_cline, int y0, int hw, int n_rows_in, bool col_ok) {
+                                        double* my_line, unsigned char* my_cline, int y0, int hw, int n_rows_in, bool col_ok) {
     if(poisoned) {
         double s = 0.0;
         int nv = 0, slot = first;
@@ -158,7 +172,7 @@ __device__ __noinline__ void fix_column(const float* ring_col, int NR, int first
             const int y = y0 + b;
             const int ch = min(y + hw, n_rows_in - 1) - max(y - hw, 0) + 1;
             my_line[b * LROW_D] = s;
-            my_cline[b * LROW_D] = col_ok ? max(ch - nv, 0) : 0;
+            my_cline[b * LROW_D] = (unsigned char) (col_ok ? max(ch - nv, 0) : 0);
             const float vo = ring_col[lead * NT];
             if(finite_f(vo)) s -= (double) vo; else nv--;
             lead = lead + 1 == NR ? 0 : lead + 1;
@@ -170,7 +184,7 @@ __device__ __noinline__ void fix_column(const float* ring_col, int NR, int first
         for(int b = 0; b < RB; b++) {
             const int y = y0 + b;
             const int ch = min(y + hw, n_rows_in - 1) - max(y - hw, 0) + 1;
-            my_cline[b * LROW_D] = col_ok ? max(ch - st.ninv, 0) : 0;
+            my_cline[b * LROW_D] = (unsigned char) (col_ok ? max(ch - st.ninv, 0) : 0);
         }
     }
 }
@@ -184,22 +198,29 @@ __device__ __forceinline__ float mean_of(double s, int c, const double* rcp, int
     return (float) (s / (double) c);
 }
 
+template <int N>
+__device__ __forceinline__ double tree_sum(const double* v) {
+    if constexpr(N == 1) return v[0];
+    else return tree_sum<N / 2>(v) + tree_sum<N - N / 2>(v + N / 2);
+}
+
 // STAT: 0 = Mean, 1 = Sum, 2 = Count.  HW > 0: half-width known at compile time (loops unrolled, the row window held
 // in registers); HW == 0: any half-width (a.hw).
 template <int STAT, int HW>
-__global__ void __launch_bounds__(NT, 3) nbh_sum_tma_kernel(const __grid_constant__ CUtensorMap in_map, const TmaArgs a) {
+__global__ void __launch_bounds__(NT, MINB_SUM) nbh_sum_tma_kernel(const __grid_constant__ CUtensorMap in_map, const TmaArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr bool STATIC = HW > 0;
     constexpr bool TAB = STATIC && (2 * HW + 1) * (2 * HW + 1) < RCP_MAX;   // every possible count is tabulated
+    constexpr bool REGWIN = STATIC && HW <= 8;                               // row window in registers, swizzled line
     const int hw = STATIC ? HW : a.hw, w = 2 * hw + 1;
     const int P = STATIC ? (2 * HW + RB - 1) / RB : a.P;
     const int NS = STATIC ? P + 1 + PREFETCH : a.NS;
     const int NR = NS * RB;
     float* ring = reinterpret_cast<float*>(smem);                                 // [NS * RB][NT]
     double* line = reinterpret_cast<double*>(ring + (size_t) NR * NT);           // [RB][LROW_D] column sums
-    int* cline = reinterpret_cast<int*>(line + RB * LROW_D);                     // [RB][LROW_D] column valid counts
-    double* rcp = reinterpret_cast<double*>(cline + RB * LROW_D);                // [n_rcp]
-    unsigned long long* bars = reinterpret_cast<unsigned long long*>(rcp + a.n_rcp);
+    double* rcp = line + RB * LROW_D;                                             // [n_rcp]
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(rcp + a.n_rcp);   // [NS]
+    unsigned char* cline = reinterpret_cast<unsigned char*>(bars + NS);           // [RB][LROW_D] column valid counts (<= w)
 
     const int tid = threadIdx.x;
     const int x0 = blockIdx.x * a.TX;
@@ -210,14 +231,14 @@ __global__ void __launch_bounds__(NT, 3) nbh_sum_tma_kernel(const __grid_constan
     R.start();
     for(int c = tid; c < a.n_rcp; c += NT) rcp[c] = c > 0 ? 1.0 / (double) c : 0.0;
 
-    const int x_stage = x0 - a.HL + tid;
+    // thread t owns window column t of the strip = staged column t + (HL - hw); the HL - hw rightmost threads have
+    // no column (they re-read the last one; their records are never used)
+    const int scol = min(tid + (a.HL - hw), NT - 1);
+    const int x_stage = x0 - a.HL + scol;
     const bool col_ok = x_stage >= 0 && x_stage < a.nx;
-    // window column e = tid - (HL - hw) of the strip; the HL - hw leftmost staged columns park their records in the
-    // unused tail of the line
-    const int ecol = tid >= a.HL - hw ? tid - (a.HL - hw) : NT - (a.HL - hw) + tid;
-    double* const my_line = line + pad_d(ecol);
-    int* const my_cline = cline + pad_d(ecol);
-    const float* const ring_col = ring + tid;
+    double* const my_line = line + idx_d<REGWIN>(tid);
+    unsigned char* const my_cline = cline + tid;
+    const float* const ring_col = ring + scol;
     const int rel0 = RB * P - 2 * hw;     // ring row of input row y_begin - hw; 0 <= rel0 < RB
     // ---- prime the column with rows y_begin - hw .. y_begin + hw - 1
     ColumnState st = {0.0, 0};
@@ -241,14 +262,23 @@ __global__ void __launch_bounds__(NT, 3) nbh_sum_tma_kernel(const __grid_constan
             const int s_old2 = s_old + 1 == NS ? 0 : s_old + 1;
             const float* oldA = ring_col + (s_old * RB + rel0) * NT;           // leaving rows b < RB - rel0
             const float* oldB = ring_col + (s_old2 * RB + rel0 - RB) * NT;     // leaving rows b >= RB - rel0
-            double csum = st.csum;
+            // c[b] = column sum before row b enters; the record of row b is c[b] + new[b]; c[b+1] = c[b] + (new[b] -
+            // old[b]). Evaluated as a shallow tree instead of a 16-deep dependent chain.
+            double dn[RB], dd[RB], c[RB + 1];
             #pragma unroll
             for(int b = 0; b < RB; b++) {
-                csum += (double) newp[b * NT];
-                my_line[b * LROW_D] = csum;
-                csum -= (double) (b < RB - rel0 ? oldA[b * NT] : oldB[b * NT]);
+                dn[b] = (double) newp[b * NT];
+                dd[b] = dn[b] - (double) (b < RB - rel0 ? oldA[b * NT] : oldB[b * NT]);
             }
-            st.csum = csum;
+            c[0] = st.csum;
+            #pragma unroll
+            for(int b = 0; b < RB; b += 2) {
+                c[b + 1] = c[b] + dd[b];
+                c[b + 2] = c[b] + (dd[b] + dd[b + 1]);
+            }
+            #pragma unroll
+            for(int b = 0; b < RB; b++) my_line[b * LROW_D] = c[b] + dn[b];
+            st.csum = c[RB];
         }
         const bool poisoned = !(fabs(st.csum) < INFINITY);
         const bool any_missing = __syncthreads_or(poisoned || st.ninv > 0) != 0;
@@ -264,26 +294,34 @@ __global__ void __launch_bounds__(NT, 3) nbh_sum_tma_kernel(const __grid_constan
         const int y = y0 + hb;
         if(h_active && y < y_end) {
             const int x = x0 + xo0;
-            const double* l = line + hb * LROW_D + seg * (SEG + 2);    // window column xo0 + j at l[pad_d(j)]
-            const int* lc = cline + hb * LROW_D + seg * (SEG + 2);
+            const double* l = line + hb * LROW_D;     // window column e at l[idx_d(e)]
+            const unsigned char* lc = cline + hb * LROW_D + xo0;
             float o[SEG];
             const int ch = min(y + hw, a.n_rows_in - 1) - max(y - hw, 0) + 1;   // rows of the window inside the field
             const bool full = strip_inside && ch == w;
-            if constexpr(STATIC && HW <= 8) {
+            if constexpr(REGWIN) {
                 constexpr int W = 2 * HW + 1, NV = W + SEG - 1;
                 double v[NV + 1];
                 #pragma unroll
                 for(int q = 0; q < (NV + 1) / 2; q++) {
-                    const double2 t = reinterpret_cast<const double2*>(l)[q + (q >> 2)];
+                    const double2 t = reinterpret_cast<const double2*>(l)[swz_slot(4 * seg + q)];
                     v[2 * q] = t.x;
                     v[2 * q + 1] = t.y;
                 }
-                double s = 0.0;
+                // window sums of the 8 pixels: sw[0] by a pairwise tree, sw[p+1] = sw[p] + (v[W+p] - v[p]) two at a time
+                double sw[SEG], t[SEG - 1];
+                sw[0] = tree_sum<W>(v);
                 #pragma unroll
-                for(int j = 0; j < W; j++) s += v[j];
+                for(int p = 0; p < SEG - 1; p++) t[p] = v[W + p] - v[p];
+                #pragma unroll
+                for(int p = 0; p + 1 < SEG; p += 2) {
+                    sw[p + 1] = sw[p] + t[p];
+                    if(p + 2 < SEG) sw[p + 2] = sw[p] + (t[p] + t[p + 1]);
+                }
                 if(!any_missing) {
                     #pragma unroll
                     for(int p = 0; p < SEG; p++) {
+                        const double s = sw[p];
                         if(STAT == 1) o[p] = (float) s;
                         else if(full) o[p] = STAT == 2 ? (float) (W * W) : (float) (s * rc_full);
                         else {
@@ -292,40 +330,34 @@ __global__ void __launch_bounds__(NT, 3) nbh_sum_tma_kernel(const __grid_constan
                             if(STAT == 2) o[p] = (float) c;
                             else o[p] = mean_of<TAB>(s, c, rcp, a.n_rcp);
                         }
-                        if(p + 1 < SEG) s += v[W + p] - v[p];
                     }
                 }
                 else {
-                    int cv[NV + 1];
+                    int cv[NV];
                     #pragma unroll
-                    for(int q = 0; q < (NV + 1) / 2; q++) {
-                        const int2 t = reinterpret_cast<const int2*>(lc)[q + (q >> 2)];
-                        cv[2 * q] = t.x;
-                        cv[2 * q + 1] = t.y;
-                    }
+                    for(int j = 0; j < NV; j++) cv[j] = lc[j];
                     int c = 0;
                     #pragma unroll
                     for(int j = 0; j < W; j++) c += cv[j];
                     #pragma unroll
                     for(int p = 0; p < SEG; p++) {
+                        const double s = sw[p];
                         if(STAT == 2) o[p] = (float) c;
                         else if(STAT == 1) o[p] = c > 0 ? (float) s : NAN;
                         else o[p] = c > 0 ? mean_of<TAB>(s, c, rcp, a.n_rcp) : NAN;
-                        if(p + 1 < SEG) {
-                            s += v[W + p] - v[p];
-                            c += cv[W + p] - cv[p];
-                        }
+                        if(p + 1 < SEG) c += cv[W + p] - cv[p];
                     }
                 }
             }
             else {
-                // sliding sums, the records re-read from the line as they enter and leave
+                // sliding sums, the records re-read from the (padded) line as they enter and leave
+                const double* lp = l + seg * (SEG + 2);   // window column xo0 + j at lp[j + 2 (j / 8)]
                 double s = 0.0;
                 int c = 0;
                 #pragma unroll 8
-                for(int j = 0; j < w; j++) s += l[pad_d(j)];
+                for(int j = 0; j < w; j++) s += lp[idx_d<false>(j)];
                 if(any_missing)
-                    for(int j = 0; j < w; j++) c += lc[pad_d(j)];
+                    for(int j = 0; j < w; j++) c += lc[j];
                 #pragma unroll
                 for(int p = 0; p < SEG; p++) {
                     if(!any_missing && full) o[p] = STAT == 2 ? (float) (w * w) : (STAT == 1 ? (float) s : (float) (s * rc_full));
@@ -336,8 +368,8 @@ __global__ void __launch_bounds__(NT, 3) nbh_sum_tma_kernel(const __grid_constan
                         else o[p] = cc > 0 ? mean_of<TAB>(s, cc, rcp, a.n_rcp) : NAN;
                     }
                     if(p + 1 < SEG) {
-                        s += l[pad_d(w + p)] - l[p];
-                        if(any_missing) c += lc[pad_d(w + p)] - lc[p];
+                        s += lp[idx_d<false>(w + p)] - lp[p];
+                        if(any_missing) c += lc[w + p] - lc[p];
                     }
                 }
             }
@@ -386,7 +418,7 @@ __device__ __forceinline__ void eight_windows(F v, int w, float (&out)[RB]) {
 }
 
 template <bool IS_MAX, int HW>
-__global__ void __launch_bounds__(NT, 3) nbh_minmax_tma_kernel(const __grid_constant__ CUtensorMap in_map, const TmaArgs a) {
+__global__ void __launch_bounds__(NT, MINB_MM) nbh_minmax_tma_kernel(const __grid_constant__ CUtensorMap in_map, const TmaArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr bool STATIC = HW > 0;
     const int hw = STATIC ? HW : a.hw, w = 2 * hw + 1;
@@ -404,19 +436,20 @@ __global__ void __launch_bounds__(NT, 3) nbh_minmax_tma_kernel(const __grid_cons
     const int n_batches = (y_end - y_begin + RB - 1) / RB;
     const StageRing R = {ring, bars, &in_map, x0 - a.HL, y_begin + hw - RB * P, NS, P + n_batches};
     R.start();
-    const int ecol = tid >= a.HL - hw ? tid - (a.HL - hw) : NT - (a.HL - hw) + tid;   // see nbh_sum_tma_kernel
+    const int scol = min(tid + (a.HL - hw), NT - 1);   // staged column of window column tid, see nbh_sum_tma_kernel
 
     const int rel0 = RB * P - 2 * hw;     // ring row of input row y_begin - hw
     for(int k = 0; k < P; k++) {
         R.wait(k);
-        float* sp = ring + (size_t) k * RB * NT + tid;
+        float* sp = ring + (size_t) k * RB * NT + scol;
         #pragma unroll
         for(int b = 0; b < RB; b++)
             if(fabsf(sp[b * NT]) == INFINITY) sp[b * NT] = NAN;
     }
     const int hb = tid >> 5, seg = tid & 31, xo0 = seg * SEG;
     const bool h_active = xo0 < a.TX && x0 + xo0 < a.nx;
-    float* const my_line = line + pad_f(ecol);
+    constexpr bool REGWIN = STATIC && HW <= 10;
+    float* const my_line = line + idx_f<REGWIN>(tid);
     int first = rel0;                     // ring row of the first row of the window of output row y0
     int s_new = P % NS;
 
@@ -426,7 +459,7 @@ __global__ void __launch_bounds__(NT, 3) nbh_minmax_tma_kernel(const __grid_cons
         // ---- vertical pass: the windows of the 8 rows of the batch span ring rows first .. first + w + 6, of which
         // the last 8 are the stage that has just landed (its infinities are replaced on the way)
         {
-            float* sp = ring + (size_t) s_new * RB * NT + tid;
+            float* sp = ring + (size_t) s_new * RB * NT + scol;
             float vnew[RB];
             #pragma unroll
             for(int b = 0; b < RB; b++) {
@@ -434,8 +467,8 @@ __global__ void __launch_bounds__(NT, 3) nbh_minmax_tma_kernel(const __grid_cons
                 if(fabsf(vnew[b]) == INFINITY) { vnew[b] = NAN; sp[b * NT] = NAN; }
             }
             float out[RB];
-            const float* base = ring + tid;
-            if constexpr(STATIC && HW <= 10) {
+            const float* base = ring + scol;
+            if constexpr(REGWIN) {
                 constexpr int W = 2 * HW + 1;
                 float v[W + RB - 1];
                 #pragma unroll
@@ -457,20 +490,23 @@ __global__ void __launch_bounds__(NT, 3) nbh_minmax_tma_kernel(const __grid_cons
         // ---- horizontal pass over window columns xo0 .. xo0 + w + 6
         const int y = y0 + hb;
         if(h_active && y < y_end) {
-            const float* l = line + hb * LROW_F + seg * (SEG + 4);
+            const float* l = line + hb * LROW_F;      // window column e at l[idx_f(e)]
             float o[SEG];
-            if constexpr(STATIC && HW <= 10) {
+            if constexpr(REGWIN) {
                 constexpr int W = 2 * HW + 1, NV = (W + SEG - 1 + 3) / 4 * 4;
                 float v[NV];
                 #pragma unroll
                 for(int q = 0; q < NV / 4; q++) {
-                    const float4 t = reinterpret_cast<const float4*>(l)[q + (q >> 1)];
+                    const float4 t = reinterpret_cast<const float4*>(l)[swz_slot(2 * seg + q)];
                     v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
                 }
                 eight_windows<IS_MAX>([&](int j) { return v[j]; }, W, o);
             }
             else
-                eight_windows<IS_MAX>([&](int j) { return l[pad_f(j)]; }, w, o);
+                {
+                const float* lp = l + seg * (SEG + 4);    // window column xo0 + j at lp[j + 4 (j / 8)]
+                eight_windows<IS_MAX>([&](int j) { return lp[idx_f<false>(j)]; }, w, o);
+            }
             store_segment(a, y, x0 + xo0, o);
         }
         __syncthreads();
@@ -531,11 +567,11 @@ int nbh_tma_try(const float* d_input, int n_rows_in, int nx, int row0, int n_row
     const bool minmax = statistic == GPP_MIN || statistic == GPP_MAX;
     size_t smem = (size_t) a.NS * STAGE_BYTES + sizeof(unsigned long long) * a.NS;
     if(minmax) smem += sizeof(float) * RB * LROW_F;
-    else smem += (sizeof(double) + sizeof(int)) * RB * LROW_D + sizeof(double) * a.n_rcp;
+    else smem += (sizeof(double) + 1) * RB * LROW_D + sizeof(double) * a.n_rcp;
     if(smem > 100 * 1024) return GPP_OK;
     // one wave: strips x chunks <= resident CTAs
     const int strips = (nx + a.TX - 1) / a.TX;
-    const int per_sm = std::max(1, std::min(3, (int) ((227 * 1024) / (smem + 1024))));
+    const int per_sm = std::max(1, std::min(minmax ? MINB_MM : MINB_SUM, (int) ((227 * 1024) / (smem + 1024))));
     const int slots = sm_count() * per_sm;
     int chunks = std::max(1, slots / strips);
     int rows = (n_rows_out + chunks - 1) / chunks;

@@ -27,6 +27,8 @@ def timeit(fn, reps=20):
     return ev0.elapsed_time(ev1) / reps
 
 
+ms = timeit(lambda b: out.copy_(b))
+print("torch copy_ (same traffic, the practical ceiling at this size)  %.4f ms  %.0f GB/s" % (ms, 8.0 * n * n / ms / 1e6))
 for hw in (7, 15):
     for name, st in (("mean", gpp.Mean), ("count", gpp.Count), ("min", gpp.Min), ("max", gpp.Max)):
         ms = timeit(lambda b: gd.neighbourhood(b, hw, st, out=out))
