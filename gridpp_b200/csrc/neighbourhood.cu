@@ -20,6 +20,8 @@ using namespace gpp;
 namespace gpp {
 int nbh_tma_try(const float* d_input, int n_rows_in, int nx, int row0, int n_rows_out, int hw, int statistic, float* d_output,
                 cudaStream_t stream, int* handled);   // neighbourhood_tma.cu
+int qf_tma_try(const float* d_input, int n_rows_in, int nx, int row0, int n_rows_out, float quantile, const float* d_quantile_field,
+               int hw, const float* thresholds, int T, float* d_output, cudaStream_t stream, int* handled);   // quantile_tma.cu
 }
 
 namespace {
@@ -612,6 +614,12 @@ int gpp_neighbourhood_quantile_fast_device(const float* d_input, int n_rows_in, 
     if(num_thresholds == 0) {   // neighbourhood.cpp:330-331: no thresholds -> all missing
         GPP_LAUNCH(fill_kernel, (unsigned) ((n_out + 255) / 256), 256, 0, stream, d_output, n_out, NAN);
         return GPP_OK;
+    }
+    {   // packed-counter kernel (ascending thresholds, small half-widths); declines what it does not cover
+        int handled = 0;
+        GPP_TRY(qf_tma_try(d_input, n_rows_in, nx, row0, n_rows_out, quantile, d_quantile_field, halfwidth, thresholds, num_thresholds,
+                           d_output, stream, &handled));
+        if(handled) return GPP_OK;
     }
     if(num_thresholds > QF_MAX_T)
         return fail(GPP_ERR_NOT_IMPLEMENTED, "neighbourhood_quantile_fast supports at most %d thresholds on the device", QF_MAX_T);

@@ -12,12 +12,13 @@
 //                    to a line buffer;
 //   horizontal pass  each thread slides along 8 consecutive pixels of one row of the batch and stores 32 bytes.
 // HBM traffic is the algorithmic 8 B/pixel plus the halo rows/columns of each CTA (L2 hits for the most part).
-#include "tma.cuh"
+#include "stage_ring.cuh"
 
 #include <algorithm>
 #include <cstring>
 
 using namespace gpp;
+using namespace gpp::nbh;
 
 namespace gpp {
 
@@ -51,8 +52,6 @@ int make_field_tensor_map(CUtensorMap* map, const float* base, int rows, int nx,
 
 namespace {
 
-constexpr int NT = 256;              // threads per CTA = staged columns per strip
-constexpr int RB = 8;                // rows per stage = output rows per batch
 constexpr int SEG = 8;               // consecutive pixels per thread in the horizontal pass
 #ifndef NBH_PF
 #define NBH_PF 2
@@ -66,7 +65,6 @@ constexpr int SEG = 8;               // consecutive pixels per thread in the hor
 constexpr int PREFETCH = NBH_PF;     // stages in flight beyond the ones the window needs
 constexpr int MINB_SUM = NBH_MINB_SUM, MINB_MM = NBH_MINB_MM;   // resident CTAs per SM the kernels are built for
 constexpr int RCP_MAX = 1024;
-constexpr unsigned STAGE_BYTES = RB * NT * sizeof(float);
 // Line buffers hold one record per window column and batch row. The vertical pass writes them with consecutive
 // lanes on consecutive columns, the horizontal pass reads them with lane l starting at column 8 l.
 //  * kernels that hold the row window in registers read 16-byte vectors; an XOR swizzle of the 16-byte slots inside
@@ -89,38 +87,6 @@ struct TmaArgs {
     int n_rcp;           // entries of the reciprocal table
     int HL;              // staged columns to the left of the strip: hw rounded up to a multiple of 4 (the copy engine
                          // needs 16-byte aligned box origins); the first HL - hw of them are not part of any window
-};
-
-__device__ __forceinline__ bool finite_f(float v) { return fabsf(v) <= 3.402823466e38f; }   // == is_valid(v), util.cpp:16-18
-
-// The ring of stages. Stage k holds input rows r0 + RB k .. r0 + RB k + RB - 1 of staged columns xs0 .. xs0 + NT - 1
-// in ring slot k % NS; its barrier completes when the copy has landed. r0 = y_begin + hw - RB P, so that the rows
-// entering the window during batch i are exactly stage P + i.
-struct StageRing {
-    float* ring;
-    unsigned long long* bars;
-    const CUtensorMap* map;
-    int xs0, r0, NS, total;
-
-    __device__ __forceinline__ void issue(int k) const {   // one thread
-        const int slot = k % NS;
-        mbar_expect_tx(&bars[slot], STAGE_BYTES);
-        tma_load_2d(ring + (size_t) slot * RB * NT, map, xs0, r0 + RB * k, &bars[slot]);
-    }
-    __device__ __forceinline__ void start() const {
-        if(threadIdx.x == 0) {
-            tma_prefetch_descriptor(map);
-            for(int s = 0; s < NS; s++) mbar_init(&bars[s], 1);
-            mbar_fence_init();
-            for(int k = 0; k < min(NS, total); k++) issue(k);
-        }
-        __syncthreads();
-    }
-    __device__ __forceinline__ void wait(int k) const { mbar_wait(&bars[k % NS], (unsigned) (k / NS) & 1u); }
-    // after every thread is done with stage k (a __syncthreads separates its last read from this call)
-    __device__ __forceinline__ void recycle(int k) const {
-        if(threadIdx.x == 0 && k + NS < total) issue(k + NS);
-    }
 };
 
 __device__ __forceinline__ void store_segment(const TmaArgs& a, int y, int x, const float (&o)[SEG]) {

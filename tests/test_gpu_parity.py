@@ -444,6 +444,57 @@ def test_quantile_fast_random_vs_oracle(gpp, orc):
                                  "thr=%s hw=%d q=%g" % (np.asarray(thr)[:3], hw, q))
 
 
+def test_quantile_fast_packed_counter_path(gpp, orc):
+    """Shapes / thresholds the packed-counter kernel takes (row length a multiple of 4 and >= 256, ascending
+    thresholds, half-width <= 15): plateaus (exact zeros, duplicate thresholds), missing and infinite values,
+    clipped windows, every quantile special case, a quantile field, and row tiles with halo. Bit-exact."""
+    import torch
+    from gridpp_b200 import device as gd
+    rng = np.random.default_rng(5)
+    for shape in ((150, 512), (70, 260)):
+        f = rng.gamma(0.5, 2.0, size=shape).astype(f32)
+        f[rng.uniform(size=shape) < 0.3] = 0
+        f[rng.uniform(size=shape) < 0.02] = np.nan
+        f[rng.uniform(size=shape) < 0.002] = np.inf
+        f[10:40, 100:140] = np.nan                      # windows without any valid value
+        f[50:60, 200:230] = 1.0                         # constant patch: F jumps from 0 to 1
+        for thr in (np.linspace(0, 5, 20), [0, 0, 1, 1, 2], [0.5], np.linspace(0, 8, 31), [0, 1], np.linspace(-1, 3, 11)):
+            for hw in (1, 2, 7, 15):
+                for q in (0.0, 0.25, 0.37, 0.5, 1.0):
+                    got = gpp.neighbourhood_quantile_fast(f, q, hw, thr)
+                    want = orc.neighbourhood_quantile_fast(f, q, hw, thr)
+                    assert_bit_exact(got, want, "%s thr=%s.. (%d) hw=%d q=%g" % (shape, np.asarray(thr)[:2], len(thr), hw, q))
+    # even window counts make F hit the quantile exactly (the plateau rules of gridpp::interpolate)
+    f = (rng.uniform(size=(64, 256)) < 0.5).astype(f32)
+    for hw in (1, 2, 3):
+        for q in (0.0, 0.25, 0.5, 0.75, 1.0):
+            for thr in ([0, 1], [0, 0.5, 1], [-1, 0, 0, 1, 1, 2], [0.5, 0.6, 0.7]):
+                assert_bit_exact(gpp.neighbourhood_quantile_fast(f, q, hw, thr), orc.neighbourhood_quantile_fast(f, q, hw, thr),
+                                 "binary field thr=%s hw=%d q=%g" % (thr, hw, q))
+    # spatially varying quantile (with missing entries)
+    f = rng.gamma(0.5, 2.0, size=(90, 300)).astype(f32)
+    f[rng.uniform(size=f.shape) < 0.05] = np.nan
+    qf = rng.uniform(size=f.shape).astype(f32)
+    qf[rng.uniform(size=f.shape) < 0.05] = np.nan
+    qf[0, :10] = [0, 1, 0, 1, 0.5, 0.5, 0, 1, 0, 1]
+    thr = np.linspace(0, 5, 12).astype(f32)
+    assert_bit_exact(gpp.neighbourhood_quantile_fast(f, qf, 4, thr), orc.neighbourhood_quantile_fast(f, qf, 4, thr), "quantile field")
+    # row tiles with halo equal the whole field
+    ny, nx, hw = 200, 260, 7
+    f = rng.gamma(0.5, 2.0, size=(ny, nx)).astype(f32)
+    f[rng.uniform(size=f.shape) < 0.02] = np.nan
+    d = torch.from_numpy(f).cuda()
+    thr = np.linspace(0, 5, 20).astype(f32)
+    whole = gd.neighbourhood_quantile_fast(d, 0.5, hw, thr)
+    tiles = []
+    for r0, r1 in ((0, 64), (64, 65), (65, 200)):
+        lo, hi = max(0, r0 - hw), min(ny, r1 + hw)
+        tiles.append(gd.neighbourhood_quantile_fast(d[lo:hi].contiguous(), 0.5, hw, thr, row0=r0 - lo, n_rows_out=r1 - r0))
+    torch.cuda.synchronize()
+    assert torch.equal(torch.nan_to_num(torch.cat(tiles), nan=-777.0), torch.nan_to_num(whole, nan=-777.0))
+    assert_bit_exact(whole.cpu().numpy(), orc.neighbourhood_quantile_fast(f, 0.5, hw, thr), "tiles vs oracle")
+
+
 # ------------------------------------------------------------------ full BASELINE.json sizes ------------
 def test_full_size_neighbourhood_properties(gpp, orc):
     """Config 2 (4000 x 4000, halfwidth 7): the stencil is local, so any window of the full-size result must equal
