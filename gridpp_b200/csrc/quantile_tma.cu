@@ -58,50 +58,74 @@ __device__ __forceinline__ int nlt_of(float q, int m) {
 __device__ __forceinline__ unsigned expand_lo(unsigned x) { return __byte_perm(x, 0, 0x4140); }
 __device__ __forceinline__ unsigned expand_hi(unsigned x) { return __byte_perm(x, 0, 0x4342); }
 
-// 16-bit field f of the packed counters (any f; select chain, used off the common path only)
+// a select the compiler cannot turn back into an indexed (local-memory) array access
+__device__ __forceinline__ unsigned sel(int cond, unsigned if_true, unsigned if_false) {
+    unsigned r;
+    asm("{\n .reg .pred p;\n setp.ne.s32 p, %3, 0;\n selp.b32 %0, %1, %2, p;\n}" : "=r"(r) : "r"(if_true), "r"(if_false), "r"(cond));
+    return r;
+}
+// n[idx] for a run-time idx (idx >= N yields 0): a binary tree of selects over the registers
+template <int N>
+__device__ __forceinline__ unsigned pick(const unsigned (&n)[N], int idx) {
+    constexpr int N1 = (N + 1) / 2, N2 = (N1 + 1) / 2, N3 = (N2 + 1) / 2, N4 = (N3 + 1) / 2;
+    static_assert(N4 == 1, "at most 16 words");
+    unsigned t1[N1], t2[N2], t3[N3];
+    #pragma unroll
+    for(int j = 0; j < N1; j++) t1[j] = sel(idx & 1, 2 * j + 1 < N ? n[2 * j + 1] : 0u, n[2 * j]);
+    #pragma unroll
+    for(int j = 0; j < N2; j++) t2[j] = sel(idx & 2, 2 * j + 1 < N1 ? t1[2 * j + 1] : 0u, t1[2 * j]);
+    #pragma unroll
+    for(int j = 0; j < N3; j++) t3[j] = sel(idx & 4, 2 * j + 1 < N2 ? t2[2 * j + 1] : 0u, t2[2 * j]);
+    return sel(idx & 8, N3 > 1 ? t3[N3 > 1 ? 1 : 0] : 0u, t3[0]);
+}
+// 16-bit field f of the packed counters (any f)
 template <int NW16>
 __device__ __forceinline__ int get_field(const unsigned (&n)[NW16], int f) {
-    unsigned w = 0;
-    #pragma unroll
-    for(int k = 0; k < NW16; k++) w = (f >> 1) == k ? n[k] : w;
+    const unsigned w = pick<NW16>(n, f >> 1);
     return (int) ((f & 1) ? (w >> 16) : (w & 0xffffu));
 }
 
-// number of 16-bit fields >= c (all 2 NW16 fields; fields are < 2^15)
+// number of 16-bit fields >= c (all 2 NW16 fields; fields and c are < 2^15): bit 15 of field + 0x8000 - c
 template <int NW16>
 __device__ __forceinline__ int count_ge(const unsigned (&n)[NW16], int c) {
-    const unsigned c2 = (unsigned) c * 0x10001u;
+    const unsigned k2 = 0x80008000u - (unsigned) c * 0x10001u;
     int cnt = 0;
     #pragma unroll
-    for(int k = 0; k < NW16; k++) cnt += __popc(((n[k] | 0x80008000u) - c2) & 0x80008000u);
+    for(int k = 0; k + 1 < NW16; k += 2)      // the sign bytes of two words gathered into one
+        cnt += __popc(__byte_perm(n[k] + k2, n[k + 1] + k2, 0x7531) & 0x80808080u);
+    if(NW16 & 1) cnt += __popc((n[NW16 - 1] + k2) & 0x80008000u);
     return cnt;
+}
+
+// fl(n / m) for integers 0 <= n <= m <= 961 from the correctly rounded reciprocal r = fl(1 / m): Markstein's
+// residual correction. Equal to __fdiv_rn((float) n, (float) m) for every such pair (exhaustively checked in
+// tests/test_capi_cpu.py::test_small_integer_quotients_are_exact).
+__device__ __forceinline__ float quot(int n, float fm, float r) {
+    const float fn = (float) n;
+    const float q0 = __fmul_rn(fn, r);
+    return __fmaf_rn(__fmaf_rn(-q0, fm, fn), r, q0);
 }
 
 // The CDF inversion for one pixel. n: window counters (field 0 = valid count m, field t + 1 = #(v <= thr_t), pad
 // fields = m). neighbourhood.cpp:374-401 and gridpp::interpolate, util.cpp:377-414.
 template <int NW16>
-__device__ __forceinline__ float invert_cdf(const unsigned (&n)[NW16], float q, int nlt, int T, const float* thr) {
+__device__ __forceinline__ float invert_cdf(const unsigned (&n)[NW16], float q, int nlt, float rm, int T, const float* thr) {
     const int m = (int) (n[0] & 0xffffu);
     const float fm = (float) m;
     // a = #(t : F_t < q): the fields below NLT are threshold fields (field 0 and the pads equal m >= NLT)
     const int a = 2 * NW16 - count_ge<NW16>(n, nlt);
     // fields a (F_{a-1}) and a + 1 (F_a) are adjacent 16-bit fields
-    unsigned w0 = 0, w1 = 0;
-    #pragma unroll
-    for(int k = 0; k < NW16; k++) {
-        w0 = (a >> 1) == k ? n[k] : w0;
-        w1 = (a >> 1) + 1 == k ? n[k] : w1;
-    }
+    const unsigned w0 = pick<NW16>(n, a >> 1), w1 = pick<NW16>(n, (a >> 1) + 1);
     const unsigned pair = (a & 1) ? __funnelshift_r(w0, w1, 16) : w0;
     const int lo = (int) (pair & 0xffffu), hi = (int) (pair >> 16);
     if(q == 1.f && (int) (n[0] >> 16) == m) return thr[0];                            // neighbourhood.cpp:396-397
     if(q == 0.f && get_field<NW16>(n, T) == 0) return thr[T - 1];                     // :398-399
     if(a == T) return thr[T - 1];                                                     // util.cpp:386-387: x > iX.back()
-    const float f_hi = __fdiv_rn((float) hi, fm);
+    const float f_hi = quot(hi, fm, rm);
     if(f_hi == q) {
         // plateau at q: lower index = first F == q = a, upper index = last F == q (util.cpp:339-376,394-403)
         int nle = hi;
-        while(nle < m && __fdiv_rn((float) (nle + 1), fm) == q) nle++;
+        while(nle < m && quot(nle + 1, fm, rm) == q) nle++;
         int b = 2 * NW16 - count_ge<NW16>(n, nle + 1);          // fields <= nle ...
         if(m <= nle) b -= 2 * NW16 - T;                         // ... without field 0 and the pads
         const int i1 = b - 1;
@@ -112,7 +136,7 @@ __device__ __forceinline__ float invert_cdf(const unsigned (&n)[NW16], float q, 
         return __fdiv_rn(__fadd_rn(y0, y1), 2.f);
     }
     if(a == 0) return thr[0];                                                         // util.cpp:388-389: x < iX[0]
-    const float f_lo = __fdiv_rn((float) lo, fm);
+    const float f_lo = quot(lo, fm, rm);
     const float y0 = thr[a - 1], y1 = thr[a];
     // y0 + (y1 - y0) * (x - x0) / (x1 - x0), float, left to right (util.cpp:410)
     return __fadd_rn(y0, __fdiv_rn(__fmul_rn(__fsub_rn(y1, y0), __fsub_rn(q, f_lo)), __fsub_rn(f_hi, f_lo)));
@@ -131,8 +155,8 @@ __global__ void __launch_bounds__(NT, 2) qf_tma_kernel(const __grid_constant__ C
     unsigned* therm = grp + RB * NW16 * NGRP;                                        // [NW8][33] thermometer codes
     float* sthr = reinterpret_cast<float*>(therm + NW8 * 34);                        // [32] (34: keeps the barriers 8-byte aligned)
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(sthr + 32);     // [NSF]
-    unsigned short* nlt_tab = reinterpret_cast<unsigned short*>(bars + NSF);         // [w * w + 1]
-    unsigned char* bring = reinterpret_cast<unsigned char*>(nlt_tab + ((w * w + 1 + 7) & ~7));   // [NRB][NT] bins
+    float2* mtab = reinterpret_cast<float2*>(bars + NSF);                            // [w * w + 1]: (NLT(m) as int bits, fl(1 / m))
+    unsigned char* bring = reinterpret_cast<unsigned char*>(mtab + ((w * w + 1 + 1) & ~1));    // [NRB][NT] bins
 
     const int tid = threadIdx.x;
     const int x0 = blockIdx.x * a.TX;
@@ -153,8 +177,8 @@ __global__ void __launch_bounds__(NT, 2) qf_tma_kernel(const __grid_constant__ C
             }
         therm[e] = word;
     }
-    if(!QFIELD)
-        for(int m = tid; m <= w * w; m += NT) nlt_tab[m] = (unsigned short) (m > 0 ? nlt_of(a.quantile, m) : 0);
+    for(int m = tid; m <= w * w; m += NT)
+        mtab[m] = make_float2(__int_as_float(!QFIELD && m > 0 ? nlt_of(a.quantile, m) : 0), m > 0 ? __frcp_rn((float) m) : 0.f);
     // window column tid of the strip = staged column tid + (HL - hw), see nbh_sum_tma_kernel
     const int scol = min(tid + (a.HL - hw), NT - 1);
     unsigned char* const my_bins = bring + scol;
@@ -181,10 +205,11 @@ __global__ void __launch_bounds__(NT, 2) qf_tma_kernel(const __grid_constant__ C
         #pragma unroll
         for(int b = 0; b < RB; b++) {
             const float v = sp[b * NT];
-            int bin = 0;
+            const float* tp = sthr;                       // lower bound: tp - sthr = #(thresholds < v)
             #pragma unroll
             for(int step = 16; step > 0; step >>= 1)
-                if(sthr[bin + step - 1] < v) bin += step;
+                if(tp[step - 1] < v) tp += step;
+            int bin = (int) (tp - sthr);
             if(!finite_f(v)) bin = BIN_INVALID;
             const bool used = batch || RB * s + b >= rel0;
             if(used) {
@@ -269,8 +294,9 @@ __global__ void __launch_bounds__(NT, 2) qf_tma_kernel(const __grid_constant__ C
                 const int m = (int) (n[0] & 0xffffu);
                 float r = NAN;                                           // no valid value / invalid quantile: missing
                 if(m > 0 && finite_f(q)) {
-                    const int nlt = QFIELD ? nlt_of(q, m) : (int) nlt_tab[m];
-                    r = invert_cdf<NW16>(n, q, nlt, T, sthr);
+                    const float2 e = mtab[m];
+                    const int nlt = QFIELD ? nlt_of(q, m) : __float_as_int(e.x);
+                    r = invert_cdf<NW16>(n, q, nlt, e.y, T, sthr);
                 }
                 o[p] = r;
                 if(p + 1 < SEG) {
@@ -345,7 +371,7 @@ int qf_tma_try(const float* d_input, int n_rows_in, int nx, int row0, int n_rows
     const int NW8 = nw8 <= 4 ? nw8 : (nw8 <= 6 ? 6 : 8);
     const int w = 2 * hw + 1;
     size_t smem = (size_t) NSF * STAGE_BYTES + sizeof(unsigned) * ((size_t) RB * NW8 * LROW + (size_t) RB * 2 * NW8 * NGRP + NW8 * 34) +
-                  sizeof(float) * 32 + sizeof(unsigned long long) * NSF + sizeof(unsigned short) * ((w * w + 1 + 7) & ~7) +
+                  sizeof(float) * 32 + sizeof(unsigned long long) * NSF + sizeof(float2) * ((w * w + 1 + 1) & ~1) +
                   (size_t) RB * (a.P + 1) * NT;
     if(smem > 200 * 1024) return GPP_OK;
     const int strips = (nx + a.TX - 1) / a.TX;

@@ -141,3 +141,21 @@ def test_compute_fails_loudly_without_gpu(gpp):
     for call in calls:
         with pytest.raises(RuntimeError, match="no usable CUDA device"):
             call()
+
+
+def test_small_integer_quotients_are_exact():
+    """csrc/quantile_tma.cu evaluates F = fl(n / m) (0 <= n <= m <= 31^2) as q0 = n * r, q = fma(fma(-q0, m, n), r, q0)
+    with r = fl(1 / m) instead of a float division. Exhaustive check that this is the correctly rounded quotient (the
+    value the reference forms, neighbourhood.cpp:374-390). The float64 emulation of the two fma's is exact here: the
+    products have <= 48 significant bits, and n / m with m < 2^10 is never within 2^-44 of a rounding boundary."""
+    f64 = np.float64
+    for m in range(1, 31 * 31 + 1):
+        n = np.arange(0, m + 1)
+        fm = f32(m)
+        r = f32(1) / fm
+        fn = n.astype(f32)
+        q0 = fn * r
+        e = (fn.astype(f64) - q0.astype(f64) * f64(fm)).astype(f32)
+        q = (e.astype(f64) * f64(r) + q0.astype(f64)).astype(f32)
+        want = (n.astype(f64) / f64(m)).astype(f32)
+        assert (q == want).all(), m
