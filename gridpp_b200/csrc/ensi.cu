@@ -19,11 +19,10 @@ using namespace gpp;
 
 namespace {
 
-constexpr int ENSI_WARPS = 4;
+constexpr int ENSI_WARPS = 2;
 constexpr int ENSI_KMAX = 64;     // observations per point
 constexpr int ENSI_EMAX = 32;     // valid ensemble members
 constexpr int ENSI_NSLOT = 3;     // candidate buffer = 96 entries
-constexpr int LD = 33;            // leading dimension of the shared matrices
 
 struct EnsiParams {
     const float *gx, *gy, *gz, *gelev, *glaf;
@@ -38,20 +37,47 @@ struct EnsiParams {
     int k;
     int allow_extrapolation;
     int* num_skipped;
+    int ld;                       // leading dimension of the shared matrices: E rounded up to odd
+    int smem_per_warp;            // bytes, see EnsiSmem::carve
 };
 
+// Per-warp working set, carved from dynamic shared memory for the actual ensemble size and observation cap (a
+// fixed 32 x 64 layout costs 36 KB per warp = 4 warps per SM; E = 20, k = 50 needs 19 KB).
 struct EnsiSmem {
-    unsigned long long key[32 * ENSI_NSLOT];
-    double Y[ENSI_KMAX * LD];     // lY, k x E
-    double A[ENSI_EMAX * LD];     // Pinv, then its diagonalisation
-    double V[ENSI_EMAX * LD];     // eigenvectors in columns
-    double rinv[ENSI_KMAX], dd[ENSI_KMAX];
-    double b[ENSI_EMAX], t[ENSI_EMAX], lam[ENSI_EMAX], w[ENSI_EMAX], sc[ENSI_EMAX], X[ENSI_EMAX];
-    double cs[ENSI_EMAX / 2], sn[ENSI_EMAX / 2];
-    int pos[32 * ENSI_NSLOT];
-    int spos[ENSI_KMAX];
-    int pp[ENSI_EMAX / 2], qq[ENSI_EMAX / 2];
-    float sval[ENSI_EMAX];
+    unsigned long long* key;      // [32 * ENSI_NSLOT] candidate keys
+    double* Y;                    // lY, k x E (leading dimension ld)
+    double* A;                    // Pinv, then its diagonalisation, E x E
+    double* V;                    // eigenvectors in columns
+    double *rinv, *dd;            // [k]
+    double *b, *t, *lam, *w, *sc, *X;   // [E]
+    double *cs, *sn;              // [E / 2 + 1]
+    int* pos;                     // [32 * ENSI_NSLOT]
+    int* spos;                    // [k]
+    int *pp, *qq;                 // [E / 2 + 1]
+    float* sval;                  // [E]
+
+    __host__ __device__ static size_t carve(EnsiSmem* S, unsigned char* base, int E, int kcap, int ld) {
+        size_t off = 0;
+        auto take = [&](size_t bytes) { unsigned char* p = base ? base + off : nullptr; off += (bytes + 15) / 16 * 16; return p; };
+        const int Ee = E + (E & 1), h = Ee / 2 + 1;
+        unsigned char* p;
+        p = take(sizeof(unsigned long long) * 32 * ENSI_NSLOT); if(S) S->key = reinterpret_cast<unsigned long long*>(p);
+        p = take(sizeof(double) * (size_t) kcap * ld); if(S) S->Y = reinterpret_cast<double*>(p);
+        p = take(sizeof(double) * (size_t) Ee * ld); if(S) S->A = reinterpret_cast<double*>(p);
+        p = take(sizeof(double) * (size_t) Ee * ld); if(S) S->V = reinterpret_cast<double*>(p);
+        p = take(sizeof(double) * kcap); if(S) S->rinv = reinterpret_cast<double*>(p);
+        p = take(sizeof(double) * kcap); if(S) S->dd = reinterpret_cast<double*>(p);
+        double** arr[6] = {S ? &S->b : nullptr, S ? &S->t : nullptr, S ? &S->lam : nullptr, S ? &S->w : nullptr, S ? &S->sc : nullptr, S ? &S->X : nullptr};
+        for(int i = 0; i < 6; i++) { p = take(sizeof(double) * Ee); if(S) *arr[i] = reinterpret_cast<double*>(p); }
+        p = take(sizeof(double) * h); if(S) S->cs = reinterpret_cast<double*>(p);
+        p = take(sizeof(double) * h); if(S) S->sn = reinterpret_cast<double*>(p);
+        p = take(sizeof(int) * 32 * ENSI_NSLOT); if(S) S->pos = reinterpret_cast<int*>(p);
+        p = take(sizeof(int) * kcap); if(S) S->spos = reinterpret_cast<int*>(p);
+        p = take(sizeof(int) * h); if(S) S->pp = reinterpret_cast<int*>(p);
+        p = take(sizeof(int) * h); if(S) S->qq = reinterpret_cast<int*>(p);
+        p = take(sizeof(float) * Ee); if(S) S->sval = reinterpret_cast<float*>(p);
+        return off;
+    }
 };
 
 // members with an invalid value anywhere in the background are left untouched (oi_ensi.cpp:187-201)
@@ -64,7 +90,9 @@ __global__ void ensi_invalid_members_kernel(const float* __restrict__ background
 template <int SMODE>
 __global__ void __launch_bounds__(ENSI_WARPS * 32) ensi_kernel(const __grid_constant__ EnsiParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    EnsiSmem& S = reinterpret_cast<EnsiSmem*>(smem_raw)[threadIdx.x >> 5];
+    EnsiSmem S;
+    EnsiSmem::carve(&S, smem_raw + (size_t) (threadIdx.x >> 5) * P.smem_per_warp, P.E, P.k, P.ld);
+    const int LD = P.ld;
     const int lane = (int) lane_id();
     const int warp_global = blockIdx.x * ENSI_WARPS + (threadIdx.x >> 5);
     const int warps_total = gridDim.x * ENSI_WARPS;
@@ -144,7 +172,7 @@ __global__ void __launch_bounds__(ENSI_WARPS * 32) ensi_kernel(const __grid_cons
             #pragma unroll
             for(int o = 16; o > 0; o >>= 1) { off += shfl_double(off, lane ^ o); dg += shfl_double(dg, lane ^ o); }
             if(!(off == off) || !(dg == dg) || isinf(off) || isinf(dg)) { bad = true; break; }
-            if(off <= 1e-30 * dg) break;
+            if(off <= 1e-26 * dg) break;   // off-diagonal rms below 1e-13 of the diagonal: eigenpairs exact to ~1e-13
             for(int r = 0; r < m; r++) {
                 if(lane < Eeven / 2) {
                     int p, q;
@@ -154,7 +182,9 @@ __global__ void __launch_bounds__(ENSI_WARPS * 32) ensi_kernel(const __grid_cons
                     double c = 1.0, s = 0.0;
                     if(q < E) {
                         const double apq = S.A[p * LD + q];
-                        if(apq != 0.0) {
+                        // rotations that could not change anything above 1e-15 relative are skipped (treated as identity)
+                        if(apq * apq <= 1e-30 * fabs(S.A[p * LD + p] * S.A[q * LD + q])) { p = 0; q = 0; }
+                        else {
                             const double theta = (S.A[q * LD + q] - S.A[p * LD + p]) / (2.0 * apq);
                             const double tt = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
                             c = 1.0 / sqrt(tt * tt + 1.0);
@@ -358,11 +388,14 @@ extern "C" int gpp_optimal_interpolation_ensi_host(const gpp_points* cbp, const 
             if(kcap > ENSI_KMAX)
                 return fail(GPP_ERR_NOT_IMPLEMENTED, "optimal_interpolation_ensi supports at most %d observations per point on the device (got %d)", ENSI_KMAX, kcap);
             P.k = kcap;
-            const size_t smem = sizeof(EnsiSmem) * ENSI_WARPS;
+            P.ld = E | 1;
+            P.smem_per_warp = (int) EnsiSmem::carve(nullptr, nullptr, E, kcap, P.ld);
+            const size_t smem = (size_t) P.smem_per_warp * ENSI_WARPS;
             GPP_CUDA(cudaFuncSetAttribute(ensi_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
             GPP_CUDA(cudaFuncSetAttribute(ensi_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
             const long long want = ((long long) nB + ENSI_WARPS - 1) / ENSI_WARPS;
-            const unsigned grid = (unsigned) std::max<long long>(1, std::min<long long>(want, (long long) sm_count() * 4));
+            const int per_sm = (int) std::max<size_t>(1, std::min<size_t>(16, (227 * 1024) / (smem + 1024)));
+            const unsigned grid = (unsigned) std::max<long long>(1, std::min<long long>(want, (long long) sm_count() * per_sm));
             if(structure_mode(*structure) == 1) GPP_LAUNCH(ensi_kernel<1>, grid, ENSI_WARPS * 32, smem, 0, P);
             else GPP_LAUNCH(ensi_kernel<0>, grid, ENSI_WARPS * 32, smem, 0, P);
         }
