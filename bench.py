@@ -37,6 +37,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# NCCL prints its version banner to stdout at some debug levels; the contract is ONE JSON line on stdout
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 N_GRID = 4000
 DX = 250.0
@@ -163,34 +166,105 @@ def run_reference_arm(args):
     print(json.dumps(line))
 
 
-def secondary_metrics(gpp, gd, torch):
-    """Neighbourhood filters of config 2 (4000 x 4000, halfwidth 7), device-resident, as GB/s of the 8 B/pixel
-    algorithmic traffic. Inputs rotate over 4 buffers (256 MB > L2) so every launch reads from HBM."""
+def secondary_metrics(gpp, gd, torch, hbm_peak):
+    """The other configurations of BASELINE.json on this GPU, device-resident, CUDA-event timed:
+    config 2 (neighbourhood mean/min/max, 4000 x 4000, halfwidth 7) and the single-GPU form of config 4
+    (neighbourhood_quantile_fast, halfwidth 15, 20 thresholds, 4000 x 4000 and 8000 x 8000) as GB/s of the 8 B/pixel
+    algorithmic traffic and as a fraction of the measured HBM peak. Inputs rotate over buffers totalling >= 256 MB
+    (> L2) so that every launch reads from HBM."""
     out = {}
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timeit(fn, bufs, reps):
+        for i in range(3):
+            fn(bufs[i % len(bufs)])
+        ev0.record()
+        for i in range(reps):
+            fn(bufs[i % len(bufs)])
+        ev1.record()
+        torch.cuda.synchronize()
+        return ev0.elapsed_time(ev1) / reps
+
+    def entry(ms, n):
+        gbs = 8.0 * n * n / (ms * 1e-3) / 1e9
+        return {"ms": ms, "GB/s": gbs, "frac_of_hbm_peak": gbs / hbm_peak}
+
     n = N_GRID
     bufs = [torch.rand((n, n), device="cuda") * 10 for _ in range(4)]
     res = torch.empty((n, n), device="cuda")
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    out["copy_4000x4000 (torch copy_, the practical ceiling at this size)"] = entry(timeit(lambda b: res.copy_(b), bufs, 20), n)
     for name, st in (("mean", gpp.Mean), ("min", gpp.Min), ("max", gpp.Max)):
-        for i in range(3):
-            gd.neighbourhood(bufs[i % 4], 7, st, out=res)
+        out["neighbourhood_%s_hw7_4000x4000" % name] = entry(timeit(lambda b: gd.neighbourhood(b, 7, st, out=res), bufs, 20), n)
+    thr = np.linspace(0, 10, 20).astype(np.float32)
+    out["quantile_fast_hw15_T20_4000x4000"] = entry(timeit(lambda b: gd.neighbourhood_quantile_fast(b, 0.5, 15, thr, out=res), bufs, 6), n)
+    del bufs, res
+    n = 8000
+    bufs = [torch.rand((n, n), device="cuda") * 10 for _ in range(2)]
+    res = torch.empty((n, n), device="cuda")
+    for name, st in (("mean", gpp.Mean), ("max", gpp.Max)):
+        out["neighbourhood_%s_hw7_8000x8000" % name] = entry(timeit(lambda b: gd.neighbourhood(b, 7, st, out=res), bufs, 10), n)
+    out["quantile_fast_hw15_T20_8000x8000 (config 4 on one GPU)"] = entry(
+        timeit(lambda b: gd.neighbourhood_quantile_fast(b, 0.5, 15, thr, out=res), bufs, 4), n)
+    return out
+
+
+def ensi_metric(gpp):
+    """Config 5 (optimal_interpolation_ensi, 2500 x 2500 grid, dx 200 m, 20 members, 5000 observations, Barnes 10 km,
+    max_points 50) through the host API: one warm-up call, one timed call (H2D of the 500 MB ensemble, kernel, D2H)."""
+    n, dx, E, S = 2500, 200.0, 20, 5000
+    rng = np.random.default_rng(SEED)
+    ax = np.arange(n, dtype=np.float32) * dx
+    y, x = np.meshgrid(ax, ax, indexing="ij")
+    py, px = (rng.random(S) * n * dx).astype(np.float32), (rng.random(S) * n * dx).astype(np.float32)
+    bg = rng.standard_normal((n, n, E), dtype=np.float32)
+    bg += rng.standard_normal((n, n, 1), dtype=np.float32) * 2
+    pbg = rng.standard_normal((S, E)).astype(np.float32)
+    obs = rng.standard_normal(S).astype(np.float32)
+    sig = np.full(S, 0.5, np.float32)
+    grid, points = gpp.Grid(y, x, type=gpp.Cartesian), gpp.Points(py, px, type=gpp.Cartesian)
+    s = gpp.BarnesStructure(H_SCALE)
+    t = []
+    for _ in range(2):
+        t0 = time.perf_counter()
+        out = gpp.optimal_interpolation_ensi(grid, bg, points, obs, sig, pbg, s, 50)
+        t.append(time.perf_counter() - t0)
+    assert out.shape == bg.shape
+    return {"workload": "C5: optimal_interpolation_ensi 2500x2500 grid (dx 200 m), 20 members, 5000 obs, BarnesStructure(10000), max_points 50",
+            "seconds_end_to_end": t[-1], "gridpoints/s": n * n / t[-1],
+            "note": "host API, H2D + kernel + D2H; the reference runs this loop serially (oi_ensi.cpp:203-206), see profiles/ for its rate"}
+
+
+def halo_neighbourhood_metric(gpp, gd, torch, dist, world, rank, hbm_peak):
+    """Config 4 across the ranks: an 8000 x 8000 field row-tiled over the GPUs, `halfwidth` halo rows exchanged with the
+    vertical neighbours over NCCL (gridpp_b200.distributed.exchange_halo), then the filter on tile + halo. Timed per
+    step: exchange + kernel, CUDA events, max over ranks."""
+    from gridpp_b200 import distributed as gdist
+    n, hw = 8000, 15
+    tile = gdist.RowTile(n, n, hw, device="cuda")          # this rank's rows, stored with room for both halos
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(SEED + rank)
+    tile.tile.copy_(torch.rand((tile.rows, n), device="cuda", generator=gen))
+    res = torch.empty((tile.rows, n), device="cuda")
+    thr = np.linspace(0, 1, 20).astype(np.float32)
+    out = {}
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for name, fn, reps in (("neighbourhood_mean_hw15", lambda: gdist.neighbourhood(tile, hw, gpp.Mean, out=res), 10),
+                           ("quantile_fast_hw15_T20", lambda: gdist.neighbourhood_quantile_fast(tile, 0.5, hw, thr, out=res), 5)):
+        for _ in range(2):
+            fn()
+        dist.barrier()
+        torch.cuda.synchronize()
         ev0.record()
-        for i in range(12):
-            gd.neighbourhood(bufs[i % 4], 7, st, out=res)
+        for _ in range(reps):
+            fn()
         ev1.record()
         torch.cuda.synchronize()
-        ms = ev0.elapsed_time(ev1) / 12
-        out["neighbourhood_%s_hw7_4000x4000" % name] = {"ms": ms, "GB/s": 8.0 * n * n / (ms * 1e-3) / 1e9}
-    thr = np.linspace(0, 10, 20).astype(np.float32)
-    for i in range(2):
-        gd.neighbourhood_quantile_fast(bufs[i % 4], 0.5, 15, thr, out=res)
-    ev0.record()
-    for i in range(4):
-        gd.neighbourhood_quantile_fast(bufs[i % 4], 0.5, 15, thr, out=res)
-    ev1.record()
-    torch.cuda.synchronize()
-    ms = ev0.elapsed_time(ev1) / 4
-    out["quantile_fast_hw15_T20_4000x4000"] = {"ms": ms, "GB/s": 8.0 * n * n / (ms * 1e-3) / 1e9}
+        t = torch.tensor([ev0.elapsed_time(ev1) / reps], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        gbs = 8.0 * n * n / (ms * 1e-3) / 1e9
+        out["%s_8000x8000_rows_over_%d_gpus" % (name, world)] = {"ms": ms, "GB/s": gbs, "frac_of_aggregate_hbm_peak": gbs / (hbm_peak * world),
+                                                                 "halo_bytes_per_rank_per_step": int(2 * hw * n * 4)}
     return out
 
 
@@ -276,13 +350,20 @@ def run_ours(args):
     # the two entry points must agree bit for bit
     same = bool(np.array_equal(out_np.ravel(), d_out.cpu().numpy(), equal_nan=True))
 
-    if rank == 0:
-        peaks = {}
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except (OSError, ValueError):
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    halo = None
+    if world > 1 and not args.quick:
+        # every rank takes part: row tiles + NCCL halo exchange for the stencil filters (config 4)
         try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except (OSError, ValueError):
-            pass
-        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+            halo = halo_neighbourhood_metric(gpp, gd, torch, dist, world, rank, hbm_peak)
+        except Exception as e:
+            halo = {"error": repr(e)}
+    if rank == 0:
         peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
         kernel_ms = statistics.mean(per_launch_ms)          # one kernel launch per step on this rank
         bytes_per_launch = 16.0 * n_local                   # bg 4 + analysis 4 + lat/lon 8 per gridpoint
@@ -322,9 +403,15 @@ def run_ours(args):
                 except Exception as e:
                     line["cpu_baseline"] = {"error": repr(e)}
                 try:
-                    line["secondary"] = secondary_metrics(gpp, gd, torch)
+                    line["secondary"] = secondary_metrics(gpp, gd, torch, hbm_peak)
                 except Exception as e:
                     line["secondary"] = {"error": repr(e)}
+                try:
+                    line["secondary"]["ensi"] = ensi_metric(gpp)
+                except Exception as e:
+                    line["secondary"]["ensi"] = {"error": repr(e)}
+        if halo is not None:
+            line["secondary_multi_gpu"] = halo
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

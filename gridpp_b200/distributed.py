@@ -3,9 +3,12 @@
 * OI / EnSI: every output point is independent (oi.cpp:221-338), so each rank analyses a contiguous block of rows
   against the full (replicated, ~0.4 MB) observation table. No data-path collective.
 * Neighbourhood filters: a stencil of radius ``halfwidth``; each rank needs ``halfwidth`` rows from its upper and
-  lower neighbour (true domain edges are clipped, not padded: neighbourhood.cpp:104-107). ``exchange_halo`` moves
-  those rows with point-to-point sends (NCCL over NVLink for CUDA tensors, gloo for CPU tensors in the tests);
-  the filter then runs on the tile-with-halo through the ``*_device`` entry points with ``row0`` / ``n_rows_out``.
+  lower neighbour (true domain edges are clipped, not padded: neighbourhood.cpp:104-107). A ``RowTile`` keeps the
+  rank's rows inside a buffer with room for both halos, so the exchange (point-to-point, NCCL over NVLink for CUDA
+  tensors, gloo for CPU tensors in the tests) lands in place and nothing is concatenated or re-allocated per step.
+  The filter on the rows that need no halo is launched first and overlaps the exchange; the ``halfwidth`` rows at
+  each end follow once the halo is there. All three launches go through the ``*_device`` entry points with
+  ``row0`` / ``n_rows_out``, which evaluate a tile-with-halo exactly like the whole field.
 
 The compute callable defaults to the CUDA device entry point; tests/test_distributed_cpu.py injects a stand-in so
 that the exchange plumbing itself can be exercised with gloo on a box without a GPU.
@@ -19,59 +22,134 @@ def row_block(n_rows, world_size, rank):
     return n_rows * rank // world_size, n_rows * (rank + 1) // world_size
 
 
-def exchange_halo(tile, halfwidth, group=None):
-    """tile: (rows_local, nx) tensor holding this rank's rows. Returns (tile_with_halo, halo_above) where up to
-    `halfwidth` rows of the previous / next rank have been attached above / below. Ranks own consecutive row blocks
-    in rank order; a rank with fewer than `halfwidth` rows forwards what it has (the halo is then shorter, which is
-    only correct when every block has at least `halfwidth` rows -- checked)."""
-    world = dist.get_world_size(group)
-    rank = dist.get_rank(group)
-    if world == 1 or halfwidth == 0:
-        return tile, 0
-    rows, nx = tile.shape
-    n = torch.tensor([rows], dtype=torch.int64, device=tile.device)
-    sizes = [torch.zeros_like(n) for _ in range(world)]
-    dist.all_gather(sizes, n, group=group)
-    sizes = [int(s.item()) for s in sizes]
-    if min(sizes) < halfwidth:
-        raise ValueError("every rank needs at least halfwidth=%d rows for a single-hop halo exchange (got %s)" % (halfwidth, sizes))
-    up, down = rank - 1, rank + 1
-    ops, recv_up, recv_down = [], None, None
-    if up >= 0:
-        recv_up = torch.empty((halfwidth, nx), dtype=tile.dtype, device=tile.device)
-        ops.append(dist.P2POp(dist.isend, tile[:halfwidth].contiguous(), up, group))
-        ops.append(dist.P2POp(dist.irecv, recv_up, up, group))
-    if down < world:
-        recv_down = torch.empty((halfwidth, nx), dtype=tile.dtype, device=tile.device)
-        ops.append(dist.P2POp(dist.isend, tile[rows - halfwidth:].contiguous(), down, group))
-        ops.append(dist.P2POp(dist.irecv, recv_down, down, group))
-    for req in dist.batch_isend_irecv(ops):
+class RowTile:
+    """This rank's rows of a row-sharded (n_rows_global, nx) field, stored with space for `halfwidth` halo rows on
+    each side. `tile` is the view to fill with the rank's own rows (row_block(n_rows_global, world, rank))."""
+
+    def __init__(self, n_rows_global, nx, halfwidth, device=None, dtype=torch.float32, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.hw = int(halfwidth)
+        self.n_rows_global, self.nx = int(n_rows_global), int(nx)
+        self.r0, self.r1 = row_block(self.n_rows_global, self.world, self.rank)
+        self.rows = self.r1 - self.r0
+        if self.world > 1 and self.hw > 0:
+            smallest = min(row_block(self.n_rows_global, self.world, r)[1] - row_block(self.n_rows_global, self.world, r)[0]
+                           for r in range(self.world))
+            if smallest < self.hw:
+                raise ValueError("every rank needs at least halfwidth=%d rows for a single-hop halo exchange (smallest block: %d)"
+                                 % (self.hw, smallest))
+        self.above = self.hw if self.rank > 0 else 0                      # halo rows present above / below the tile
+        self.below = self.hw if self.rank < self.world - 1 else 0
+        self.buf = torch.empty((self.rows + 2 * self.hw, self.nx), dtype=dtype, device=device)
+        self.tile = self.buf[self.hw:self.hw + self.rows]
+
+    @property
+    def with_halo(self):
+        """The tile with the halo rows that exist (domain edges have none)."""
+        return self.buf[self.hw - self.above:self.hw + self.rows + self.below]
+
+    def exchange_async(self):
+        """Starts the halo exchange with the vertical neighbours; returns the requests to wait on."""
+        if self.world == 1 or self.hw == 0:
+            return []
+        hw, ops = self.hw, []
+        if self.rank > 0:
+            ops.append(dist.P2POp(dist.isend, self.tile[:hw], self.rank - 1, self.group))
+            ops.append(dist.P2POp(dist.irecv, self.buf[:hw], self.rank - 1, self.group))
+        if self.rank < self.world - 1:
+            ops.append(dist.P2POp(dist.isend, self.tile[self.rows - hw:], self.rank + 1, self.group))
+            ops.append(dist.P2POp(dist.irecv, self.buf[hw + self.rows:], self.rank + 1, self.group))
+        return dist.batch_isend_irecv(ops)
+
+    def exchange(self):
+        for req in self.exchange_async():
+            req.wait()
+
+
+def _run_tiled(rt, out, launch):
+    """launch(field, row0, n_rows_out, out_rows): evaluates output rows [row0, row0 + n_rows_out) of `field` (whose
+    first and last rows are treated as domain edges) into `out_rows`. The rows whose windows stay inside the tile go
+    first and overlap the exchange; the (at most `halfwidth`) rows at each end follow once the halo is there."""
+    hw, rows = rt.hw, rt.rows
+    reqs = rt.exchange_async()
+    if not reqs:
+        launch(rt.with_halo, rt.above, rows, out)
+        return out
+    top = min(rows, hw if rt.above else 0)             # tile rows [0, top) need the upper halo
+    bot_first = max(top, rows - (hw if rt.below else 0))   # tile rows [bot_first, rows) need the lower halo
+    if bot_first > top:
+        launch(rt.tile, top, bot_first - top, out[top:bot_first])
+    for req in reqs:
         req.wait()
-    parts = [p for p in (recv_up, tile, recv_down) if p is not None]
-    return torch.cat(parts, dim=0), (halfwidth if recv_up is not None else 0)
+    full = rt.with_halo                                # tile row t sits at full[rt.above + t]
+    if top > 0:
+        end = min(rt.above + top + hw, full.shape[0])  # windows reach at most hw rows below the last of these rows
+        launch(full[:end], rt.above, top, out[:top])
+    if rows > bot_first:
+        s0 = max(0, rt.above + bot_first - hw)         # ... and at most hw rows above the first of these
+        launch(full[s0:], rt.above + bot_first - s0, rows - bot_first, out[bot_first:])
+    return out
 
 
-def neighbourhood(tile, halfwidth, statistic, compute=None, group=None):
-    """Row-sharded gridpp.neighbourhood: `tile` holds this rank's rows; returns this rank's rows of the result.
+def neighbourhood(tile, halfwidth, statistic, compute=None, group=None, n_rows_global=None, out=None):
+    """Row-sharded gridpp.neighbourhood. `tile` is either a RowTile (no copies) or a (rows_local, nx) tensor holding
+    this rank's rows (copied into a RowTile; ranks own row_block() blocks). Returns this rank's rows of the result.
     `compute(field_with_halo, halfwidth, statistic, row0, n_rows_out)` defaults to the CUDA device entry point."""
+    rt = _as_row_tile(tile, halfwidth, group, n_rows_global)
+    if out is None:
+        out = torch.empty((rt.rows, rt.nx), dtype=rt.buf.dtype, device=rt.buf.device)
     if compute is None:
         from . import device as gd
 
-        def compute(field, hw, st, row0, n_rows_out):
-            return gd.neighbourhood(field, hw, st, row0=row0, n_rows_out=n_rows_out)
-    ext, above = exchange_halo(tile, halfwidth, group)
-    return compute(ext.contiguous(), halfwidth, statistic, above, tile.shape[0])
+        def launch(field, row0, n_rows_out, out_rows):
+            gd.neighbourhood(field, halfwidth, statistic, out=out_rows, row0=row0, n_rows_out=n_rows_out)
+    else:
+        def launch(field, row0, n_rows_out, out_rows):
+            out_rows.copy_(compute(field.contiguous(), halfwidth, statistic, row0, n_rows_out))
+    return _run_tiled(rt, out, launch)
 
 
-def neighbourhood_quantile_fast(tile, quantile, halfwidth, thresholds, compute=None, group=None):
+def neighbourhood_quantile_fast(tile, quantile, halfwidth, thresholds, compute=None, group=None, n_rows_global=None, out=None):
     """Row-sharded gridpp.neighbourhood_quantile_fast (scalar quantile)."""
+    rt = _as_row_tile(tile, halfwidth, group, n_rows_global)
+    if out is None:
+        out = torch.empty((rt.rows, rt.nx), dtype=rt.buf.dtype, device=rt.buf.device)
     if compute is None:
         from . import device as gd
 
-        def compute(field, q, hw, thr, row0, n_rows_out):
-            return gd.neighbourhood_quantile_fast(field, q, hw, thr, row0=row0, n_rows_out=n_rows_out)
-    ext, above = exchange_halo(tile, halfwidth, group)
-    return compute(ext.contiguous(), quantile, halfwidth, thresholds, above, tile.shape[0])
+        def launch(field, row0, n_rows_out, out_rows):
+            gd.neighbourhood_quantile_fast(field, quantile, halfwidth, thresholds, out=out_rows, row0=row0, n_rows_out=n_rows_out)
+    else:
+        def launch(field, row0, n_rows_out, out_rows):
+            out_rows.copy_(compute(field.contiguous(), quantile, halfwidth, thresholds, row0, n_rows_out))
+    return _run_tiled(rt, out, launch)
+
+
+def _as_row_tile(tile, halfwidth, group, n_rows_global):
+    if isinstance(tile, RowTile):
+        if tile.hw != int(halfwidth):
+            raise ValueError("the RowTile was built for halfwidth %d" % tile.hw)
+        return tile
+    rows, nx = tile.shape
+    if n_rows_global is None:
+        n = torch.tensor([rows], dtype=torch.int64, device=tile.device)
+        if dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(n, group=group)
+        n_rows_global = int(n.item())
+    rt = RowTile(n_rows_global, nx, halfwidth, device=tile.device, dtype=tile.dtype, group=group)
+    if rt.rows != rows:
+        raise ValueError("this rank holds %d rows, row_block() assigns it %d" % (rows, rt.rows))
+    rt.tile.copy_(tile)
+    return rt
+
+
+def exchange_halo(tile, halfwidth, group=None):
+    """Functional form: returns (tile_with_halo, halo_rows_above) for a (rows_local, nx) tensor."""
+    rt = _as_row_tile(tile, halfwidth, group, None)
+    rt.exchange()
+    return rt.with_halo, rt.above
 
 
 def gather_rows(tile, group=None):

@@ -62,7 +62,7 @@ def _worker(rank, world, port, ny, nx, hw, result_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("ny,nx,hw", [(37, 23, 3), (64, 40, 7)])
+@pytest.mark.parametrize("ny,nx,hw", [(37, 23, 3), (64, 40, 7), (20, 16, 7)])
 def test_row_sharded_filters_equal_whole(tmp_path, orc, ny, nx, hw):
     world = 2
     port = _free_port()
