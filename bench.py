@@ -37,9 +37,16 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# NCCL prints its version banner to stdout at some debug levels; the contract is ONE JSON line on stdout
-if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-    os.environ["NCCL_DEBUG"] = "WARN"
+# The contract is ONE JSON line on stdout, but libraries write there too (NCCL prints its version banner at most
+# NCCL_DEBUG levels). Keep a private handle on the real stdout for the result and point fd 1 at stderr.
+_RESULT_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line):
+    _RESULT_OUT.write(json.dumps(line) + "\n")
+    _RESULT_OUT.flush()
+
 
 N_GRID = 4000
 DX = 250.0
@@ -163,7 +170,7 @@ def run_reference_arm(args):
             "config": {"workload": WORKLOAD, "sample": sample},
             "cpu_baseline": {"value": value, "unit": "gridpoints/s", "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "gridpoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def secondary_metrics(gpp, gd, torch, hbm_peak):
@@ -412,7 +419,7 @@ def run_ours(args):
                     line["secondary"]["ensi"] = {"error": repr(e)}
         if halo is not None:
             line["secondary_multi_gpu"] = halo
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
