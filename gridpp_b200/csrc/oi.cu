@@ -18,6 +18,7 @@
 
 #include <algorithm>
 #include <cstring>
+#include <mutex>
 
 using namespace gpp;
 
@@ -41,6 +42,7 @@ struct OiParams {
     int allow_extrapolation;
     int tile_nx;                     // > 0: the range is whole rows of a grid with this row length -> 4 x 4 tiles
     unsigned char* lru;              // per-warp cache of solved systems (LRU_ENTRIES x LruEntry), global memory
+    int* work_counter;               // next chunk of runs to hand out (zeroed before the launch)
 };
 
 // oi.cpp:318-337: optional clamp, then output and analysis variance
@@ -324,7 +326,13 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 2) oi_fast_kernel(const __
     const int rows = P.tile_nx > 0 ? P.count / P.tile_nx : 0;
     const int n_runs = P.tile_nx > 0 ? tiles_x * ((rows + 3) / 4) : (P.count + RUN - 1) / RUN;
     const int n_chunks = (n_runs + RUNS_PER_CHUNK - 1) / RUNS_PER_CHUNK;
-    for(int chunk = warp_global; chunk < n_chunks; chunk += warps_total)
+    // chunks are handed out dynamically: their cost varies with how often the selection changes, and a static split
+    // of a few chunks per warp leaves a long tail
+    for(;;) {
+    int chunk = 0;
+    if(lane == 0) chunk = atomicAdd(P.work_counter, 1);
+    chunk = __shfl_sync(0xffffffffu, chunk, 0);
+    if(chunk >= n_chunks) break;
     for(int run = chunk * RUNS_PER_CHUNK; run < min((chunk + 1) * RUNS_PER_CHUNK, n_runs); run++) {
         // ---- the run's points (offsets into the range), and a bounding sphere
         int npts, my_it = 0;
@@ -540,6 +548,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 2) oi_fast_kernel(const __
                 __syncwarp();
             }
         }
+    }
     }
 }
 
@@ -882,6 +891,79 @@ int check_structure(const gpp_structure* s) {
 }
 }  // namespace
 
+namespace {
+// Pinned staging for pipelined downloads: two slots, grown on demand, kept for the life of the process.
+struct PinnedStage {
+    std::mutex lock;
+    float* slot[2] = {nullptr, nullptr};
+    size_t capacity = 0;   // floats per slot
+    int reserve(size_t n) {
+        if(n <= capacity) return GPP_OK;
+        for(int i = 0; i < 2; i++) {
+            if(slot[i]) cudaFreeHost(slot[i]);
+            slot[i] = nullptr;
+        }
+        capacity = 0;
+        for(int i = 0; i < 2; i++) GPP_CUDA(cudaHostAlloc((void**) &slot[i], n * sizeof(float), cudaHostAllocDefault));
+        capacity = n;
+        return GPP_OK;
+    }
+};
+PinnedStage g_stage;
+
+// Row blocks of the grid are analysed back to back on the default stream; a second stream copies each finished block
+// into a pinned slot, and the host moves it into the caller's array while the next block is being analysed.
+int analyse_pipelined(const gpp_points* bpoints, int nB, int nx, int n_chunks, const float* d_bg, const float* d_bvar, const gpp_oi_obs* obs,
+                      const gpp_structure* structure, int max_points, int allow_extrapolation, float* d_out, float* d_var, float* analysis) {
+    const int n_rows = nB / nx;
+    std::vector<int> row0(n_chunks + 1);
+    for(int c = 0; c <= n_chunks; c++) row0[c] = (int) ((long long) n_rows * c / n_chunks);
+    size_t largest = 0;
+    for(int c = 0; c < n_chunks; c++) largest = std::max(largest, (size_t) (row0[c + 1] - row0[c]) * nx);
+    std::lock_guard<std::mutex> guard(g_stage.lock);
+    GPP_TRY(g_stage.reserve(largest));
+    cudaStream_t copy_stream;
+    GPP_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+    std::vector<cudaEvent_t> analysed(n_chunks), copied(n_chunks);
+    for(int c = 0; c < n_chunks; c++) {
+        cudaEventCreateWithFlags(&analysed[c], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&copied[c], cudaEventDisableTiming);
+    }
+    int rc = GPP_OK;
+    for(int c = 0; c < n_chunks && rc == GPP_OK; c++) {
+        rc = gpp_optimal_interpolation_device(bpoints, row0[c] * nx, (row0[c + 1] - row0[c]) * nx, d_bg, d_bvar, obs, structure, max_points,
+                                              allow_extrapolation, d_out, d_var, nullptr);
+        cudaEventRecord(analysed[c], 0);
+    }
+    // The caller's array is usually fresh (untouched pages): fault it in now, while the device is busy with block 0,
+    // instead of during the copies at the end (first-touch runs at 2-4 GB/s).
+    if(rc == GPP_OK)
+        for(size_t i = 0; i < (size_t) nB; i += 1024) reinterpret_cast<volatile float*>(analysis)[i] = 0.f;
+    auto finish = [&](int c) {   // block c: wait for its copy, move it to the caller's array
+        if(cudaEventSynchronize(copied[c]) != cudaSuccess) return fail(GPP_ERR_CUDA, "CUDA error while downloading the analysis");
+        std::memcpy(analysis + (size_t) row0[c] * nx, g_stage.slot[c & 1], sizeof(float) * (size_t) (row0[c + 1] - row0[c]) * nx);
+        return (int) GPP_OK;
+    };
+    for(int c = 0; c < n_chunks && rc == GPP_OK; c++) {
+        if(c >= 2) rc = finish(c - 2);               // frees slot c & 1
+        if(rc != GPP_OK) break;
+        cudaStreamWaitEvent(copy_stream, analysed[c], 0);
+        cudaMemcpyAsync(g_stage.slot[c & 1], d_out + (size_t) row0[c] * nx, sizeof(float) * (size_t) (row0[c + 1] - row0[c]) * nx,
+                        cudaMemcpyDeviceToHost, copy_stream);
+        cudaEventRecord(copied[c], copy_stream);
+    }
+    for(int c = std::max(0, n_chunks - 2); c < n_chunks && rc == GPP_OK; c++) rc = finish(c);
+    cudaStreamSynchronize(copy_stream);
+    for(int c = 0; c < n_chunks; c++) { cudaEventDestroy(analysed[c]); cudaEventDestroy(copied[c]); }
+    cudaStreamDestroy(copy_stream);
+    if(rc == GPP_OK) {
+        cudaError_t err = cudaGetLastError();
+        if(err != cudaSuccess) rc = fail(GPP_ERR_CUDA, "CUDA error %s: %s", cudaGetErrorName(err), cudaGetErrorString(err));
+    }
+    return rc;
+}
+}  // namespace
+
 extern "C" {
 
 int gpp_oi_obs_create(const gpp_points* opoints, const float* pobs, const float* obs_variance, const float* pbackground,
@@ -943,6 +1025,7 @@ int gpp_optimal_interpolation_device(const gpp_points* cbp, int first, int count
     P.allow_extrapolation = allow_extrapolation;
     P.tile_nx = 0;
     P.lru = nullptr;
+    P.work_counter = nullptr;
 
     int kcap = max_points > 0 ? std::min(max_points, obs->n_valid) : obs->n_valid;
     if(max_points == 0 && kcap > FAST_K) {
@@ -966,8 +1049,11 @@ int gpp_optimal_interpolation_device(const gpp_points* cbp, int first, int count
         const long long want = (chunks + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
         const unsigned grid = (unsigned) std::max<long long>(1, std::min<long long>(want, (long long) sms * 2));   // 2 resident CTAs per SM
         unsigned char* lru = nullptr;
-        GPP_CUDA(cudaMallocAsync((void**) &lru, sizeof(LruEntry) * LRU_ENTRIES * (size_t) grid * WARPS_PER_CTA, stream));
+        const size_t lru_bytes = sizeof(LruEntry) * LRU_ENTRIES * (size_t) grid * WARPS_PER_CTA;
+        GPP_CUDA(cudaMallocAsync((void**) &lru, lru_bytes + 256, stream));
         P.lru = lru;
+        P.work_counter = reinterpret_cast<int*>(lru + lru_bytes);
+        GPP_CUDA(cudaMemsetAsync(P.work_counter, 0, sizeof(int), stream));
         if(mode == 1) oi_fast_kernel<1><<<grid, WARPS_PER_CTA * 32, smem, stream>>>(P);
         else oi_fast_kernel<0><<<grid, WARPS_PER_CTA * 32, smem, stream>>>(P);
         g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -1023,18 +1109,27 @@ int gpp_optimal_interpolation_host(const gpp_points* bpoints, const float* backg
     if(rc == GPP_OK) rc = d_out.alloc(nB);
     if(rc == GPP_OK && analysis_variance) rc = d_var.alloc(nB);
     if(trace.on) { cudaStreamSynchronize(0); trace.lap("alloc + H2D"); }
-    if(rc == GPP_OK)
+    // Large grids: the analysis goes back in row blocks through a pinned staging buffer while later blocks are still
+    // being analysed (a D2H straight into the caller's pageable array runs at ~5 GB/s and would add ~30 % to the call).
+    const int nx = bpoints->shape_nx;
+    const int n_rows = nx > 0 ? nB / nx : 0;
+    const int n_chunks = (rc == GPP_OK && nx > 0 && nB % nx == 0 && nB >= (1 << 21)) ? std::min(4, n_rows) : 1;
+    if(rc == GPP_OK && n_chunks > 1) rc = analyse_pipelined(bpoints, nB, nx, n_chunks, d_bg.ptr, bvariance ? d_bvar.ptr : nullptr, obs, structure,
+                                                            max_points, allow_extrapolation, d_out.ptr, analysis_variance ? d_var.ptr : nullptr,
+                                                            analysis);
+    else if(rc == GPP_OK) {
         rc = gpp_optimal_interpolation_device(bpoints, 0, nB, d_bg.ptr, bvariance ? d_bvar.ptr : nullptr, obs, structure, max_points,
                                               allow_extrapolation, d_out.ptr, analysis_variance ? d_var.ptr : nullptr, nullptr);
-    if(trace.on) { cudaStreamSynchronize(0); trace.lap("kernels"); }
-    if(rc == GPP_OK) rc = d_out.download(analysis, nB);
+        if(trace.on) { cudaStreamSynchronize(0); trace.lap("kernels"); }
+        if(rc == GPP_OK) rc = d_out.download(analysis, nB);
+    }
     if(rc == GPP_OK && analysis_variance) rc = d_var.download(analysis_variance, nB);
     if(rc == GPP_OK) {
         cudaError_t err = cudaStreamSynchronize(0);
         if(err != cudaSuccess) rc = fail(GPP_ERR_CUDA, "CUDA error %s: %s", cudaGetErrorName(err), cudaGetErrorString(err));
     }
     else cudaStreamSynchronize(0);
-    trace.lap("D2H");
+    trace.lap(n_chunks > 1 ? "kernels + D2H (pipelined)" : "D2H");
     gpp_oi_obs_destroy(obs);
     d_bg.release(); d_bvar.release(); d_out.release(); d_var.release();
     trace.lap("free");
