@@ -22,6 +22,7 @@ namespace {
 constexpr int ENSI_WARPS = 2;
 constexpr int ENSI_KMAX = 64;     // observations per point
 constexpr int ENSI_EMAX = 32;     // valid ensemble members
+constexpr int ENSI_GRAB = 32;     // consecutive points a warp takes per grab of the work counter
 constexpr int ENSI_NSLOT = 3;     // candidate buffer = 96 entries
 
 struct EnsiParams {
@@ -37,6 +38,7 @@ struct EnsiParams {
     int k;
     int allow_extrapolation;
     int* num_skipped;
+    int* work_counter;            // next block of ENSI_GRAB points to hand out (zeroed before the launch)
     int ld;                       // leading dimension of the shared matrices: E rounded up to odd
     int smem_per_warp;            // bytes, see EnsiSmem::carve
 };
@@ -46,8 +48,8 @@ struct EnsiParams {
 struct EnsiSmem {
     unsigned long long* key;      // [32 * ENSI_NSLOT] candidate keys
     double* Y;                    // lY, k x E (leading dimension ld)
-    double* A;                    // Pinv, then its diagonalisation, E x E
-    double* V;                    // eigenvectors in columns
+    double* A;                    // Pinv, then its diagonalisation, E x E (aliases Y)
+    double* V;                    // eigenvectors in columns (aliases Y)
     double *rinv, *dd;            // [k]
     double *b, *t, *lam, *w, *sc, *X;   // [E]
     double *cs, *sn;              // [E / 2 + 1]
@@ -62,9 +64,10 @@ struct EnsiSmem {
         const int Ee = E + (E & 1), h = Ee / 2 + 1;
         unsigned char* p;
         p = take(sizeof(unsigned long long) * 32 * ENSI_NSLOT); if(S) S->key = reinterpret_cast<unsigned long long*>(p);
-        p = take(sizeof(double) * (size_t) kcap * ld); if(S) S->Y = reinterpret_cast<double*>(p);
-        p = take(sizeof(double) * (size_t) Ee * ld); if(S) S->A = reinterpret_cast<double*>(p);
-        p = take(sizeof(double) * (size_t) Ee * ld); if(S) S->V = reinterpret_cast<double*>(p);
+        // A and V reuse lY's storage: lY is consumed (Pinv, C d, the clamp's lY[e]) before they are written
+        const size_t ny = (size_t) kcap * ld, nav = (size_t) 2 * Ee * ld;
+        p = take(sizeof(double) * (ny > nav ? ny : nav));
+        if(S) { S->Y = reinterpret_cast<double*>(p); S->A = S->Y; S->V = S->Y + (size_t) Ee * ld; }
         p = take(sizeof(double) * kcap); if(S) S->rinv = reinterpret_cast<double*>(p);
         p = take(sizeof(double) * kcap); if(S) S->dd = reinterpret_cast<double*>(p);
         double** arr[6] = {S ? &S->b : nullptr, S ? &S->t : nullptr, S ? &S->lam : nullptr, S ? &S->w : nullptr, S ? &S->sc : nullptr, S ? &S->X : nullptr};
@@ -80,6 +83,23 @@ struct EnsiSmem {
     }
 };
 
+// 1/x and 1/sqrt(x) from the hardware approximations plus Newton steps (full double accuracy to a few ulp; the
+// rotation angles of the Jacobi sweeps do not need correctly rounded divisions and square roots)
+__device__ __forceinline__ double fast_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(fma(-x, r, 1.0), r, r);
+    r = fma(fma(-x, r, 1.0), r, r);
+    return r;
+}
+__device__ __forceinline__ double fast_rsqrt(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    y = y * fma(-0.5 * x * y, y, 1.5);
+    y = y * fma(-0.5 * x * y, y, 1.5);
+    return y;
+}
+
 // members with an invalid value anywhere in the background are left untouched (oi_ensi.cpp:187-201)
 __global__ void ensi_invalid_members_kernel(const float* __restrict__ background, size_t n, int nE, int* __restrict__ invalid) {
     size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
@@ -87,20 +107,28 @@ __global__ void ensi_invalid_members_kernel(const float* __restrict__ background
     if(!is_valid(background[i])) atomicOr(&invalid[i % nE], 1);
 }
 
+#ifndef ENSI_MINB
+#define ENSI_MINB 10
+#endif
 template <int SMODE>
-__global__ void __launch_bounds__(ENSI_WARPS * 32) ensi_kernel(const __grid_constant__ EnsiParams P) {
+__global__ void __launch_bounds__(ENSI_WARPS * 32, ENSI_MINB) ensi_kernel(const __grid_constant__ EnsiParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     EnsiSmem S;
     EnsiSmem::carve(&S, smem_raw + (size_t) (threadIdx.x >> 5) * P.smem_per_warp, P.E, P.k, P.ld);
     const int LD = P.ld;
     const int lane = (int) lane_id();
-    const int warp_global = blockIdx.x * ENSI_WARPS + (threadIdx.x >> 5);
-    const int warps_total = gridDim.x * ENSI_WARPS;
     const CandBuf cb = {S.key, S.pos};
     const int E = P.E;
     const int Eeven = E + (E & 1), m = Eeven - 1;   // round-robin schedule over an even number of indices
+    const int H = Eeven / 2;                        // rotations per round
 
-    for(int it = warp_global; it < P.count; it += warps_total) {
+    // blocks of consecutive points are handed out dynamically (the cost per point varies with k and the sweep count)
+    for(;;) {
+    int it0 = 0;
+    if(lane == 0) it0 = atomicAdd(P.work_counter, ENSI_GRAB);
+    it0 = __shfl_sync(0xffffffffu, it0, 0);
+    if(it0 >= P.count) break;
+    for(int it = it0; it < min(it0 + ENSI_GRAB, P.count); it++) {
         const int g = P.first + it;
         const Pt p1 = {P.gx[g], P.gy[g], P.gz[g], P.gelev[g], P.glaf[g]};
         bool cut = false;
@@ -139,18 +167,25 @@ __global__ void __launch_bounds__(ENSI_WARPS * 32) ensi_kernel(const __grid_cons
             S.Y[i * LD + e] = (double) P.gY[(size_t) S.spos[i] * E + e];
         }
         __syncwarp();
-        // ---- Pinv = C * lY + diag * I, C = lY' Rinv (oi_ensi.cpp:379-385); row `lane`
+        // ---- Pinv = C * lY + diag * I, C = lY' Rinv (oi_ensi.cpp:379-385), row `lane`; b = C (obs - yhat) (:428-437)
+        double lYe = 0.0;   // the clamp's lY[e]: a LINEAR index into the column-major k x E matrix (oi_ensi.cpp:523-524)
         {
             double acc[ENSI_EMAX];
             #pragma unroll
             for(int f = 0; f < ENSI_EMAX; f++) acc[f] = 0.0;
-            if(lane < E)
+            double b = 0.0;
+            if(lane < E) {
                 for(int i = 0; i < k; i++) {
                     const double c = S.Y[i * LD + lane] * S.rinv[i];
+                    b = fma(c, S.dd[i], b);
                     #pragma unroll
                     for(int f = 0; f < ENSI_EMAX; f++)
                         if(f < E) acc[f] = fma(c, S.Y[i * LD + f], acc[f]);
                 }
+                S.b[lane] = b;
+                lYe = S.Y[(lane % k) * LD + (lane / k)];
+            }
+            __syncwarp();   // lY is dead from here on: A and V take its place
             const float diag = (float) (E - 1);   // oi_ensi.cpp:383 with delta = 1
             #pragma unroll
             for(int f = 0; f < ENSI_EMAX; f++)
@@ -174,20 +209,24 @@ __global__ void __launch_bounds__(ENSI_WARPS * 32) ensi_kernel(const __grid_cons
             if(!(off == off) || !(dg == dg) || isinf(off) || isinf(dg)) { bad = true; break; }
             if(off <= 1e-26 * dg) break;   // off-diagonal rms below 1e-13 of the diagonal: eigenpairs exact to ~1e-13
             for(int r = 0; r < m; r++) {
-                if(lane < Eeven / 2) {
+                if(lane < H) {
                     int p, q;
                     if(lane == 0) { p = m; q = r; }
                     else { p = (r + lane) % m; q = (r - lane + m) % m; }
                     if(p > q) { int tmp = p; p = q; q = tmp; }
                     double c = 1.0, s = 0.0;
                     if(q < E) {
-                        const double apq = S.A[p * LD + q];
+                        const double apq = S.A[p * LD + q], app = S.A[p * LD + p], aqq = S.A[q * LD + q];
                         // rotations that could not change anything above 1e-15 relative are skipped (treated as identity)
-                        if(apq * apq <= 1e-30 * fabs(S.A[p * LD + p] * S.A[q * LD + q])) { p = 0; q = 0; }
+                        if(apq * apq <= 1e-30 * fabs(app * aqq)) { p = 0; q = 0; }
                         else {
-                            const double theta = (S.A[q * LD + q] - S.A[p * LD + p]) / (2.0 * apq);
-                            const double tt = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-                            c = 1.0 / sqrt(tt * tt + 1.0);
+                            // t = sign(theta) / (|theta| + sqrt(theta^2 + 1)), theta = (aqq - app) / (2 apq); c = 1 / sqrt(t^2 + 1)
+                            const double theta = (aqq - app) * (0.5 * fast_rcp(apq));
+                            const double at = fabs(theta);
+                            double tt;
+                            if(at > 1e100) tt = 0.5 * fast_rcp(theta);                  // theta^2 would overflow
+                            else tt = copysign(fast_rcp(at + (at * at + 1.0) * fast_rsqrt(at * at + 1.0)), theta);
+                            c = fast_rsqrt(tt * tt + 1.0);
                             s = tt * c;
                         }
                     }
@@ -196,7 +235,7 @@ __global__ void __launch_bounds__(ENSI_WARPS * 32) ensi_kernel(const __grid_cons
                 }
                 __syncwarp();
                 if(lane < E)   // rows p, q of A, column `lane`
-                    for(int t = 0; t < Eeven / 2; t++) {
+                    for(int t = 0; t < H; t++) {
                         const int p = S.pp[t], q = S.qq[t];
                         if(p == q) continue;
                         const double c = S.cs[t], s = S.sn[t];
@@ -206,7 +245,7 @@ __global__ void __launch_bounds__(ENSI_WARPS * 32) ensi_kernel(const __grid_cons
                     }
                 __syncwarp();
                 if(lane < E)   // columns p, q of A and of V, row `lane`
-                    for(int t = 0; t < Eeven / 2; t++) {
+                    for(int t = 0; t < H; t++) {
                         const int p = S.pp[t], q = S.qq[t];
                         if(p == q) continue;
                         const double c = S.cs[t], s = S.sn[t];
@@ -230,10 +269,6 @@ __global__ void __launch_bounds__(ENSI_WARPS * 32) ensi_kernel(const __grid_cons
         if(lane < E) {
             S.lam[lane] = lam;
             S.sc[lane] = sqrt((double) (E - 1) / lam);   // sqrt of the eigenvalues of (E-1) P, oi_ensi.cpp:401,419
-            // b = C (obs - yhat)
-            double b = 0.0;
-            for(int i = 0; i < k; i++) b = fma(S.Y[i * LD + lane] * S.rinv[i], S.dd[i], b);
-            S.b[lane] = b;
             // X: background perturbations about the ensemble mean (oi_ensi.cpp:447-462), float mean
             S.sval[lane] = P.background[(size_t) g * P.nE + P.valid_ens[lane]];
         }
@@ -267,7 +302,6 @@ __global__ void __launch_bounds__(ENSI_WARPS * 32) ensi_kernel(const __grid_cons
             float currIncrement = tot;
             if(!P.allow_extrapolation) {   // oi_ensi.cpp:517-551
                 // lY[e] is a LINEAR index into the column-major k x E matrix: row e % k, column e / k (:523-524)
-                const double lYe = S.Y[(lane % k) * LD + (lane / k)];
                 double mx = -INFINITY, mn = INFINITY;
                 for(int i = 0; i < k; i++) {
                     const double v = S.dd[i] - lYe;
@@ -284,6 +318,7 @@ __global__ void __launch_bounds__(ENSI_WARPS * 32) ensi_kernel(const __grid_cons
             P.analysis[(size_t) g * P.nE + P.valid_ens[lane]] = __fadd_rn(ensMean, currIncrement);
         }
         __syncwarp();
+    }
     }
 }
 
@@ -333,8 +368,8 @@ extern "C" int gpp_optimal_interpolation_ensi_host(const gpp_points* cbp, const 
     DeviceBuffer<float> d_bg, d_out, d_gY;
     DeviceBuffer<int> d_flags;
     GPP_TRY(d_bg.upload(background, nBE));
-    GPP_TRY(d_flags.alloc(nE + 1));
-    GPP_CUDA(cudaMemsetAsync(d_flags.ptr, 0, sizeof(int) * (nE + 1), 0));
+    GPP_TRY(d_flags.alloc(nE + 2));   // per-member invalid flags, the skipped-point count, the work counter
+    GPP_CUDA(cudaMemsetAsync(d_flags.ptr, 0, sizeof(int) * (nE + 2), 0));
     GPP_LAUNCH(ensi_invalid_members_kernel, (unsigned) ((nBE + 255) / 256), 256, 0, 0, d_bg.ptr, nBE, nE, d_flags.ptr);
     std::vector<int> flags(nE + 1);
     GPP_TRY(d_flags.download(flags.data(), nE + 1));
@@ -394,8 +429,11 @@ extern "C" int gpp_optimal_interpolation_ensi_host(const gpp_points* cbp, const 
             GPP_CUDA(cudaFuncSetAttribute(ensi_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
             GPP_CUDA(cudaFuncSetAttribute(ensi_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
             const long long want = ((long long) nB + ENSI_WARPS - 1) / ENSI_WARPS;
-            const int per_sm = (int) std::max<size_t>(1, std::min<size_t>(16, (227 * 1024) / (smem + 1024)));
-            const unsigned grid = (unsigned) std::max<long long>(1, std::min<long long>(want, (long long) sm_count() * per_sm));
+            int per_sm = 1;   // what actually fits (registers and shared memory): one wave of resident CTAs
+            if(structure_mode(*structure) == 1) GPP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ensi_kernel<1>, ENSI_WARPS * 32, smem));
+            else GPP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ensi_kernel<0>, ENSI_WARPS * 32, smem));
+            const unsigned grid = (unsigned) std::max<long long>(1, std::min<long long>(want, (long long) sm_count() * std::max(per_sm, 1)));
+            P.work_counter = d_flags.ptr + nE + 1;
             if(structure_mode(*structure) == 1) GPP_LAUNCH(ensi_kernel<1>, grid, ENSI_WARPS * 32, smem, 0, P);
             else GPP_LAUNCH(ensi_kernel<0>, grid, ENSI_WARPS * 32, smem, 0, P);
         }

@@ -94,8 +94,14 @@ struct WarpState {
 };
 
 // A solved system kept for reuse: the set (canonical original indices), z = (P+R)^-1 d and the innovation extremes.
-constexpr int LRU_ENTRIES = 4;
-constexpr int RUNS_PER_CHUNK = 16;   // consecutive runs (tiles) handled by one warp, so that the cache sees neighbours
+#ifndef OI_LRU
+#define OI_LRU 4
+#endif
+#ifndef OI_RPC
+#define OI_RPC 16
+#endif
+constexpr int LRU_ENTRIES = OI_LRU;
+constexpr int RUNS_PER_CHUNK = OI_RPC;   // consecutive runs (tiles) handled by one warp, so that the cache sees neighbours
 struct LruEntry {
     double z[32];
     double dmax, dmin;
