@@ -208,18 +208,20 @@ __global__ void __launch_bounds__(ENSI_WARPS * 32, ENSI_MINB) ensi_kernel(const 
             for(int o = 16; o > 0; o >>= 1) { off += shfl_double(off, lane ^ o); dg += shfl_double(dg, lane ^ o); }
             if(!(off == off) || !(dg == dg) || isinf(off) || isinf(dg)) { bad = true; break; }
             if(off <= 1e-26 * dg) break;   // off-diagonal rms below 1e-13 of the diagonal: eigenpairs exact to ~1e-13
+            // round-robin schedule: in round r lane l > 0 pairs (r + l) % m with (r - l) % m, lane 0 pairs m with r
+            int pr = lane % m, qr = (m - lane % m) % m;
             for(int r = 0; r < m; r++) {
+                bool rot = false;
+                int p = 0, q = 0;
+                double c = 1.0, s = 0.0;
                 if(lane < H) {
-                    int p, q;
                     if(lane == 0) { p = m; q = r; }
-                    else { p = (r + lane) % m; q = (r - lane + m) % m; }
+                    else { p = pr; q = qr; }
                     if(p > q) { int tmp = p; p = q; q = tmp; }
-                    double c = 1.0, s = 0.0;
-                    if(q < E) {
+                    if(q < E) {   // (a pair with the padding index of an odd E is the identity)
                         const double apq = S.A[p * LD + q], app = S.A[p * LD + p], aqq = S.A[q * LD + q];
-                        // rotations that could not change anything above 1e-15 relative are skipped (treated as identity)
-                        if(apq * apq <= 1e-30 * fabs(app * aqq)) { p = 0; q = 0; }
-                        else {
+                        // rotations that could not change anything above 1e-15 relative are skipped
+                        if(apq * apq > 1e-30 * fabs(app * aqq)) {
                             // t = sign(theta) / (|theta| + sqrt(theta^2 + 1)), theta = (aqq - app) / (2 apq); c = 1 / sqrt(t^2 + 1)
                             const double theta = (aqq - app) * (0.5 * fast_rcp(apq));
                             const double at = fabs(theta);
@@ -228,34 +230,46 @@ __global__ void __launch_bounds__(ENSI_WARPS * 32, ENSI_MINB) ensi_kernel(const 
                             else tt = copysign(fast_rcp(at + (at * at + 1.0) * fast_rsqrt(at * at + 1.0)), theta);
                             c = fast_rsqrt(tt * tt + 1.0);
                             s = tt * c;
+                            rot = true;
                         }
                     }
-                    else { p = 0; q = 0; }   // pair with the padding index: identity
-                    S.pp[lane] = p; S.qq[lane] = q; S.cs[lane] = c; S.sn[lane] = s;
+                }
+                pr = pr + 1 == m ? 0 : pr + 1;
+                qr = qr + 1 == m ? 0 : qr + 1;
+                // the rotations of this round, compacted
+                const unsigned rmask = __ballot_sync(0xffffffffu, rot);
+                const int nrot = __popc(rmask);
+                if(nrot == 0) continue;
+                if(rot) {
+                    const int slot = __popc(rmask & ((1u << lane) - 1u));
+                    S.pp[slot] = p | (q << 8); S.cs[slot] = c; S.sn[slot] = s;
                 }
                 __syncwarp();
-                if(lane < E)   // rows p, q of A, column `lane`
-                    for(int t = 0; t < H; t++) {
-                        const int p = S.pp[t], q = S.qq[t];
-                        if(p == q) continue;
+                if(lane < E)   // A <- J' A: rows p, q of A, column `lane`
+                    for(int t = 0; t < nrot; t++) {
+                        const int pq = S.pp[t];
+                        double* rp = S.A + (pq & 255) * LD + lane;
+                        double* rq = S.A + (pq >> 8) * LD + lane;
                         const double c = S.cs[t], s = S.sn[t];
-                        const double ap = S.A[p * LD + lane], aq = S.A[q * LD + lane];
-                        S.A[p * LD + lane] = c * ap - s * aq;
-                        S.A[q * LD + lane] = s * ap + c * aq;
+                        const double ap = *rp, aq = *rq;
+                        *rp = c * ap - s * aq;
+                        *rq = s * ap + c * aq;
                     }
                 __syncwarp();
-                if(lane < E)   // columns p, q of A and of V, row `lane`
-                    for(int t = 0; t < H; t++) {
-                        const int p = S.pp[t], q = S.qq[t];
-                        if(p == q) continue;
+                if(lane < E) {   // A <- A J, V <- V J: columns p, q, row `lane`
+                    double* arow = S.A + lane * LD;
+                    double* vrow = S.V + lane * LD;
+                    for(int t = 0; t < nrot; t++) {
+                        const int pq = S.pp[t], p = pq & 255, q = pq >> 8;
                         const double c = S.cs[t], s = S.sn[t];
-                        const double ap = S.A[lane * LD + p], aq = S.A[lane * LD + q];
-                        S.A[lane * LD + p] = c * ap - s * aq;
-                        S.A[lane * LD + q] = s * ap + c * aq;
-                        const double vp = S.V[lane * LD + p], vq = S.V[lane * LD + q];
-                        S.V[lane * LD + p] = c * vp - s * vq;
-                        S.V[lane * LD + q] = s * vp + c * vq;
+                        const double ap = arow[p], aq = arow[q];
+                        arow[p] = c * ap - s * aq;
+                        arow[q] = s * ap + c * aq;
+                        const double vp = vrow[p], vq = vrow[q];
+                        vrow[p] = c * vp - s * vq;
+                        vrow[q] = s * vp + c * vq;
                     }
+                }
                 __syncwarp();
             }
         }
