@@ -474,7 +474,18 @@ def neighbourhood(input, halfwidth, statistic):
     """gridpp::neighbourhood(vec2, halfwidth, statistic), neighbourhood.cpp:28-242."""
     field = _np.asarray(input, dtype=_np.float32)
     if field.ndim == 3:
-        raise NotImplementedOnDevice("the ensemble (3-D) form of neighbourhood() is not part of the device path yet")
+        # gridpp::neighbourhood(vec3, ...), neighbourhood.cpp:12-27: members reduced with calc_statistic first
+        field = _farray(field, 3, "input")
+        if halfwidth < 0:
+            raise ValueError("Half width must be > 0")
+        if statistic == Quantile:
+            raise ValueError("Use neighbourhood_quantile for computing neighbourhood quantiles")
+        ny, nx, ne = field.shape
+        if ny == 0 or nx == 0 or ne == 0:
+            return _np.zeros((0, 0), _np.float32)
+        out = _np.empty((ny, nx), _np.float32)
+        _check(_libc.gpp_neighbourhood_ens_host(_fptr(field), ny, nx, ne, int(halfwidth), int(statistic), _fptr(out)))
+        return out
     field = _farray(field, 2, "input")
     if halfwidth < 0:
         raise ValueError("Half width must be > 0")
@@ -490,13 +501,12 @@ def neighbourhood(input, halfwidth, statistic):
 def neighbourhood_quantile_fast(input, quantile, halfwidth, thresholds):
     """gridpp::neighbourhood_quantile_fast(vec2, float | vec2, halfwidth, thresholds), neighbourhood.cpp:296-409."""
     field = _np.asarray(input, dtype=_np.float32)
-    if field.ndim == 3:
-        raise NotImplementedOnDevice("the ensemble (3-D) form of neighbourhood_quantile_fast() is not part of the device path yet")
-    field = _farray(field, 2, "input")
+    ens = field.ndim == 3     # gridpp::neighbourhood_quantile_fast(vec3, ...), neighbourhood.cpp:411-527
+    field = _farray(field, 3 if ens else 2, "input")
     thr = _farray(thresholds, 1, "thresholds")
     if halfwidth < 0:
         raise ValueError("Half width must be > 0")
-    if field.shape[0] == 0 or field.shape[1] == 0:
+    if 0 in field.shape:
         return _np.zeros((0, 0), _np.float32)
     qf = None
     q = float("nan")
@@ -506,9 +516,13 @@ def neighbourhood_quantile_fast(input, quantile, halfwidth, thresholds):
         qf = _farray(quantile, 2, "quantile")
         if qf.shape == (1, 1):
             q, qf = float(qf[0, 0]), None
-        elif qf.shape != field.shape:
-            raise ValueError("Quantile must be the same size as input, or size (1, 1)")
-    out = _np.empty(field.shape, _np.float32)
+        elif qf.shape != field.shape[:2]:
+            raise ValueError("Quantile must have the same Y, X size as input, or have size (1, 1)")
+    out = _np.empty(field.shape[:2], _np.float32)
+    if ens:
+        _check(_libc.gpp_neighbourhood_quantile_fast_ens_host(_fptr(field), field.shape[0], field.shape[1], field.shape[2], q, _fptr(qf),
+                                                              int(halfwidth), _fptr(thr), thr.size, _fptr(out)))
+        return out
     _check(_libc.gpp_neighbourhood_quantile_fast_host(_fptr(field), field.shape[0], field.shape[1], q, _fptr(qf), int(halfwidth),
                                                       _fptr(thr), thr.size, _fptr(out)))
     return out

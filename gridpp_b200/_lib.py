@@ -75,6 +75,11 @@ _proto("gpp_neighbourhood_quantile_fast_host", C.c_int, fp, C.c_int, C.c_int, C.
 _proto("gpp_neighbourhood_quantile_fast_device", C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, vp, C.c_int,
        fp, C.c_int, vp, vp)
 
+_proto("gpp_neighbourhood_ens_host", C.c_int, fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, fp)
+_proto("gpp_neighbourhood_ens_device", C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp)
+_proto("gpp_neighbourhood_quantile_fast_ens_host", C.c_int, fp, C.c_int, C.c_int, C.c_int, C.c_float, fp, C.c_int, fp, C.c_int, fp)
+_proto("gpp_neighbourhood_quantile_fast_ens_device", C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_float, vp, C.c_int, fp, C.c_int, vp, vp)
+
 EXPORTS = [
     "gpp_version", "gpp_last_error", "gpp_device_count", "gpp_set_device", "gpp_device_synchronize",
     "gpp_kernel_launch_count", "gpp_measure_fp64_fma_peak", "gpp_structure_init", "gpp_structure_multiple", "gpp_structure_cross_validation",
@@ -83,7 +88,8 @@ EXPORTS = [
     "gpp_points_closest_host", "gpp_nearest_host", "gpp_optimal_interpolation_host", "gpp_oi_obs_create",
     "gpp_oi_obs_destroy", "gpp_optimal_interpolation_device", "gpp_optimal_interpolation_ensi_host",
     "gpp_neighbourhood_host", "gpp_neighbourhood_device", "gpp_neighbourhood_quantile_fast_host",
-    "gpp_neighbourhood_quantile_fast_device",
+    "gpp_neighbourhood_quantile_fast_device", "gpp_neighbourhood_ens_host", "gpp_neighbourhood_ens_device",
+    "gpp_neighbourhood_quantile_fast_ens_host", "gpp_neighbourhood_quantile_fast_ens_device",
 ]
 
 

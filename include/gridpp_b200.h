@@ -201,6 +201,20 @@ int gpp_neighbourhood_quantile_fast_device(const float* d_input, int n_rows_in, 
                                            const float* thresholds, int num_thresholds, float* d_output,
                                            void* stream);
 
+/* The ensemble (vec3) forms. input is ny x nx x ne, member fastest.
+ * gridpp::neighbourhood(vec3, halfwidth, statistic) neighbourhood.cpp:12-27: calc_statistic over the members of every
+ * cell (util.cpp:19-110), then the 2-D filter. */
+int gpp_neighbourhood_ens_host(const float* input, int ny, int nx, int ne, int halfwidth, int statistic, float* output);
+int gpp_neighbourhood_ens_device(const float* d_input, int ny, int nx, int ne, int halfwidth, int statistic,
+                                 float* d_output, void* stream);
+/* gridpp::neighbourhood_quantile_fast(vec3, quantile | vec2 quantile, halfwidth, thresholds) neighbourhood.cpp:411-527. */
+int gpp_neighbourhood_quantile_fast_ens_host(const float* input, int ny, int nx, int ne, float quantile,
+                                             const float* quantile_field, int halfwidth, const float* thresholds,
+                                             int num_thresholds, float* output);
+int gpp_neighbourhood_quantile_fast_ens_device(const float* d_input, int ny, int nx, int ne, float quantile,
+                                               const float* d_quantile_field, int halfwidth, const float* thresholds,
+                                               int num_thresholds, float* d_output, void* stream);
+
 /* ---------------------------------------------------------------- instrumentation -------------------- */
 /* Number of kernels this library has launched on the calling process so far (bench.py's gpu_launches). */
 unsigned long long gpp_kernel_launch_count(void);

@@ -240,6 +240,30 @@ class CpuLib:
             timing.append(sec.value)
         return out
 
+    def neighbourhood_ens(self, field, halfwidth, statistic):
+        """gridpp::neighbourhood(vec3, halfwidth, statistic); field is (ny, nx, ne)."""
+        f = _f(field)
+        ny, nx, ne = f.shape
+        out = np.full((ny, nx), np.nan, np.float32)
+        self._check(self._fn("neighbourhood_ens")(_p(f), ny, nx, ne, halfwidth, statistic, _p(out)))
+        return out
+
+    def neighbourhood_quantile_fast_ens(self, field, quantile, halfwidth, thresholds):
+        """gridpp::neighbourhood_quantile_fast(vec3, quantile | vec2, halfwidth, thresholds); field is (ny, nx, ne)."""
+        f = _f(field)
+        ny, nx, ne = f.shape
+        thr = _f(thresholds).ravel()
+        qf = None
+        q = float("nan")
+        if np.ndim(quantile) == 0:
+            q = float(quantile)
+        else:
+            qf = _f(quantile, (ny, nx))
+        out = np.full((ny, nx), np.nan, np.float32)
+        self._check(self._fn("neighbourhood_quantile_fast_ens")(_p(f), ny, nx, ne, C.c_float(q), _p(qf), halfwidth, _p(thr), thr.size,
+                                                                _p(out)))
+        return out
+
     def get_neighbourhood_thresholds(self, field, num):
         f = _f(field)
         ny, nx = f.shape

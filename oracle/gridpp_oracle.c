@@ -1143,6 +1143,75 @@ int orc_neighbourhood_quantile_fast(const float* input, int nY, int nX, float qu
     return 0;
 }
 
+/* gridpp::neighbourhood(vec3, halfwidth, statistic), neighbourhood.cpp:12-27. input is ny x nx x ne, member fastest. */
+int orc_neighbourhood_ens(const float* input, int ny, int nx, int ne, int halfwidth, int statistic, float* output) {
+    if(ny == 0 || nx == 0 || ne == 0) return 0;
+    size_t N = (size_t) ny * nx;
+    float* flat = malloc(sizeof(float) * N);
+    int rc = 0;
+    for(size_t i = 0; i < N && rc == 0; i++) rc = orc_calc_statistic(input + i * ne, ne, statistic, &flat[i]); /* :21-23 */
+    if(rc == 0) rc = orc_neighbourhood(flat, ny, nx, halfwidth, statistic, output, NULL);                       /* :25 */
+    free(flat);
+    return rc;
+}
+
+/* gridpp::neighbourhood_quantile_fast(vec3, quantile | vec2, halfwidth, thresholds), neighbourhood.cpp:411-527 */
+int orc_neighbourhood_quantile_fast_ens(const float* input, int nY, int nX, int nE, float quantile, const float* quantile_field,
+                                        int halfwidth, const float* thresholds, int T, float* output) {
+    if(halfwidth < 0) FAIL(1, "Half width must be > 0");
+    if(nY == 0 || nX == 0 || nE == 0) return 0;
+    size_t N = (size_t) nY * nX;
+    if(quantile_field) {
+        for(size_t i = 0; i < N; i++)
+            if(is_valid(quantile_field[i]) && (quantile_field[i] < 0 || quantile_field[i] > 1))
+                FAIL(1, "All quantiles must be >= 0 and <= 1");
+    }
+    else if(is_valid(quantile) && (quantile < 0 || quantile > 1)) FAIL(1, "All quantiles must be >= 0 and <= 1");
+    for(size_t i = 0; i < N; i++) output[i] = NAN;
+    if(T == 0) return 0;
+    float* stats = malloc(sizeof(float) * N * (size_t) T);
+    float* temp = malloc(sizeof(float) * N);
+    for(int t = 0; t < T; t++) { /* :456-472 */
+        for(size_t i = 0; i < N; i++) {
+            int sum = 0, count = 0;
+            temp[i] = NAN;
+            for(int e = 0; e < nE; e++) {
+                float v = input[i * nE + e];
+                if(is_valid(v)) { if(v <= thresholds[t]) sum++; count++; }
+            }
+            if(count > 0) temp[i] = (float) sum / count;
+        }
+        neighbourhood_sat(temp, nY, nX, halfwidth, MEAN, stats + (size_t) t * N);
+    }
+    free(temp);
+    float* yarray = malloc(sizeof(float) * (size_t) T);
+    for(size_t i = 0; i < N; i++) { /* :483-521 */
+        float curr_quantile = quantile_field ? quantile_field[i] : quantile;
+        int is_missing = 0;
+        for(int t = 0; t < T; t++) {
+            float sum = 0;
+            int count = 0;
+            float st = stats[(size_t) t * N + i];
+            for(int e = 0; e < nE; e++)
+                if(is_valid(st)) { sum += st; count++; }
+            if(count > 0) {
+                yarray[t] = sum / count;
+                if(yarray[t] > 1) yarray[t] = 1;
+                else if(yarray[t] < 0) yarray[t] = 0;
+            }
+            else is_missing = 1;
+        }
+        if(!is_missing) {
+            if(curr_quantile == 1 && yarray[0] == 1) output[i] = thresholds[0];
+            else if(curr_quantile == 0 && yarray[T - 1] == 0) output[i] = thresholds[T - 1];
+            else output[i] = interpolate(curr_quantile, yarray, thresholds, T);
+        }
+    }
+    free(yarray);
+    free(stats);
+    return 0;
+}
+
 /* util.cpp:261-338 */
 static int calc_even_quantiles(const float* sorted, int size, int num, float* q) {
     int nq = 0;

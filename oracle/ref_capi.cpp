@@ -292,6 +292,32 @@ int ref_neighbourhood_quantile_fast(const float* input, int ny, int nx, float qu
     if(out.size() == (size_t) ny) from_vec2(out, output, ny, nx);
     REF_CATCH
 }
+// gridpp::neighbourhood(vec3, ...) neighbourhood.cpp:12-27 and neighbourhood_quantile_fast(vec3, ...) :411-527
+static gridpp::vec3 to_vec3(const float* in, int ny, int nx, int ne) {
+    gridpp::vec3 out(ny);
+    for(int y = 0; y < ny; y++) {
+        out[y].resize(nx);
+        for(int x = 0; x < nx; x++) out[y][x].assign(in + ((size_t) y * nx + x) * ne, in + ((size_t) y * nx + x + 1) * ne);
+    }
+    return out;
+}
+int ref_neighbourhood_ens(const float* input, int ny, int nx, int ne, int halfwidth, int statistic, float* output) {
+    REF_TRY
+    gridpp::vec2 out = gridpp::neighbourhood(to_vec3(input, ny, nx, ne), halfwidth, (gridpp::Statistic) statistic);
+    if(out.size() == (size_t) ny) from_vec2(out, output, ny, nx);
+    REF_CATCH
+}
+int ref_neighbourhood_quantile_fast_ens(const float* input, int ny, int nx, int ne, float quantile, const float* quantile_field,
+                                        int halfwidth, const float* thresholds, int num_thresholds, float* output) {
+    REF_TRY
+    gridpp::vec3 in = to_vec3(input, ny, nx, ne);
+    gridpp::vec thr = to_vec(thresholds, num_thresholds);
+    gridpp::vec2 out;
+    if(quantile_field) out = gridpp::neighbourhood_quantile_fast(in, to_vec2(quantile_field, ny, nx), halfwidth, thr);
+    else out = gridpp::neighbourhood_quantile_fast(in, quantile, halfwidth, thr);
+    if(out.size() == (size_t) ny) from_vec2(out, output, ny, nx);
+    REF_CATCH
+}
 // gridpp::get_neighbourhood_thresholds(vec2, num) neighbourhood.cpp:243-266
 int ref_get_neighbourhood_thresholds(const float* input, int ny, int nx, int num, float* out, int* out_n) {
     REF_TRY

@@ -495,6 +495,48 @@ def test_quantile_fast_packed_counter_path(gpp, orc):
     assert_bit_exact(whole.cpu().numpy(), orc.neighbourhood_quantile_fast(f, 0.5, hw, thr), "tiles vs oracle")
 
 
+def test_ensemble_forms(gpp, orc):
+    """gridpp::neighbourhood(vec3, ...) (neighbourhood.cpp:12-27) and neighbourhood_quantile_fast(vec3, ...) (:411-527)
+    against the golden fixture of the compiled reference and against the oracle on shapes that take the TMA kernels."""
+    g = golden("ensemble_forms")
+    f = g["field"]
+    for hw in (0, 1, 4, 9):
+        for name, st in STATS.items():
+            got, want = gpp.neighbourhood(f, hw, st), g["nbh_hw%d__%s" % (hw, name)]
+            if name in ("count", "min", "max"):
+                assert_bit_exact(got, want, "ens nbh hw=%d %s" % (hw, name))
+            else:
+                assert_close(got, want, 4.0 * (1 if name == "mean" else (2 * hw + 1) ** 2), 1e-6, "ens nbh hw=%d %s" % (hw, name))
+    for hw in (0, 2, 6):
+        for q in (0.0, 0.3, 0.5, 0.9, 1.0):
+            got, want = gpp.neighbourhood_quantile_fast(f, q, hw, g["thresholds"]), g["qf_hw%d__q%g" % (hw, q)]
+            assert_close(got, want, 1.0, 1e-5, "ens qfast hw=%d q=%g" % (hw, q), allow_outliers=2)
+    got = gpp.neighbourhood_quantile_fast(f, g["qfield"], 3, g["thresholds"])
+    assert_close(got, g["qf_hw3__qfield"], 1.0, 1e-5, "ens qfast field", allow_outliers=2)
+    # larger, TMA-eligible shape against the oracle
+    rng = np.random.default_rng(11)
+    f = (rng.gamma(0.5, 2.0, size=(120, 260, 1)) + rng.normal(size=(120, 260, 6)) * 0.3).astype(f32)
+    f[rng.uniform(size=f.shape) < 0.03] = np.nan
+    for st_name, st in (("mean", gpp.Mean), ("max", gpp.Max)):
+        got, want = gpp.neighbourhood(f, 7, st), orc.neighbourhood_ens(f, 7, st)
+        if st_name == "max":
+            assert_bit_exact(got, want, "ens max 260")
+        else:
+            assert_close(got, want, 4.0, 1e-6, "ens mean 260")
+    thr = np.linspace(0, 6, 13).astype(f32)
+    got, want = gpp.neighbourhood_quantile_fast(f, 0.5, 7, thr), orc.neighbourhood_quantile_fast_ens(f, 0.5, 7, thr)
+    assert_close(got, want, 1.0, 1e-5, "ens qfast 260", allow_outliers=3)
+    # identical members reproduce the 2-D result (tests/test_neighbourhood.py:133-144 of the reference)
+    v = rng.uniform(size=(80, 64)).astype(f32)
+    v3 = np.repeat(v[:, :, None], 5, axis=2)
+    np.testing.assert_array_almost_equal(gpp.neighbourhood(v, 5, gpp.Mean), gpp.neighbourhood(v3, 5, gpp.Mean), 5)
+    np.testing.assert_array_almost_equal(gpp.neighbourhood_quantile_fast(v, 0.5, 5, [0, 0.25, 0.5, 0.75, 1]),
+                                         gpp.neighbourhood_quantile_fast(v3, 0.5, 5, [0, 0.25, 0.5, 0.75, 1]))
+    assert gpp.neighbourhood(np.zeros((0, 0, 3), f32), 1, gpp.Mean).shape == (0, 0)
+    with pytest.raises(ValueError):
+        gpp.neighbourhood_quantile_fast(v3, 1.5, 1, [0, 1])
+
+
 # ------------------------------------------------------------------ full BASELINE.json sizes ------------
 def test_full_size_neighbourhood_properties(gpp, orc):
     """Config 2 (4000 x 4000, halfwidth 7): the stencil is local, so any window of the full-size result must equal

@@ -298,6 +298,30 @@ def test_golden_quantile_fast(orc):
 
 
 # ------------------------------------------------------------------ 3. live against the compiled reference
+def test_golden_ensemble_forms(orc):
+    """gridpp::neighbourhood(vec3, ...) neighbourhood.cpp:12-27 and neighbourhood_quantile_fast(vec3, ...) :411-527:
+    the C restatement against fixtures generated from the compiled reference (tests/golden/make_golden_ensemble.py)."""
+    g = golden("ensemble_forms")
+    f = g["field"]
+    for hw in (0, 1, 4, 9):
+        for name, st in (("mean", B.MEAN), ("sum", B.SUM), ("count", B.COUNT), ("min", B.MIN), ("max", B.MAX)):
+            assert_bit_exact(orc.neighbourhood_ens(f, hw, st), g["nbh_hw%d__%s" % (hw, name)], "ens nbh hw=%d %s" % (hw, name))
+    for hw in (0, 2, 6):
+        for q in (0.0, 0.3, 0.5, 0.9, 1.0):
+            assert_bit_exact(orc.neighbourhood_quantile_fast_ens(f, q, hw, g["thresholds"]), g["qf_hw%d__q%g" % (hw, q)],
+                             "ens qfast hw=%d q=%g" % (hw, q))
+    assert_bit_exact(orc.neighbourhood_quantile_fast_ens(f, g["qfield"], 3, g["thresholds"]), g["qf_hw3__qfield"], "ens qfast field")
+    # tests/test_neighbourhood.py:133-144 and tests/test_neighbourhood_quantile_fast.py:92-104 of the reference:
+    # identical members reproduce the 2-D result
+    rng = np.random.RandomState(1000)
+    values = rng.rand(60, 50).astype(np.float32)
+    values3 = np.repeat(values[:, :, None], 5, axis=2)
+    for hw in (0, 1, 5):
+        np.testing.assert_array_almost_equal(orc.neighbourhood(values, hw, B.MEAN), orc.neighbourhood_ens(values3, hw, B.MEAN), 5)
+        np.testing.assert_array_almost_equal(orc.neighbourhood_quantile_fast(values, 0.5, hw, [0, 0.25, 0.5, 0.75, 1]),
+                                             orc.neighbourhood_quantile_fast_ens(values3, 0.5, hw, [0, 0.25, 0.5, 0.75, 1]))
+
+
 def test_live_against_reference(orc, ref):
     rng = np.random.default_rng(7)
     ny = nx = 30
