@@ -104,7 +104,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.FIELDS,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
             self.proc = None
@@ -315,12 +315,15 @@ def run_ours(args):
     def step():
         gd.optimal_interpolation(grid, d_bg, state, MAX_POINTS, out=d_out)
 
-    for _ in range(max(3, args.warmup)):
-        step()
-    barrier()
+    # clocks / throttle reasons are sampled from before the warm-up steps (the same load) to the end of the timed steps:
+    # the timed region alone (10 x 39 ms) is too short for more than a couple of nvidia-smi samples
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        time.sleep(0.3)
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
     launches0 = gpp.kernel_launch_count()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     barrier()
@@ -387,7 +390,9 @@ def run_ours(args):
                     "d2h_bytes_per_step": int(4 * n_total), "steps": e2e_steps},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
-                         "traffic": None, "kernel": "oi_fast_kernel", "peak_source": peak_src,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one full-grid launch (ncu --set full,
+                         # profiles/r1_oi_fast_kernel_v5.txt): 391.2 + 58.1 MB, scaled to this rank's share of the grid
+                         "traffic": 449.3e6 * n_local / n_total, "kernel": "oi_fast_kernel", "peak_source": peak_src,
                          "note": "HBM view only for the contract; the kernel is fp64-CUDA-core bound, see roofline_fp64"},
         }
         if not args.quick:
