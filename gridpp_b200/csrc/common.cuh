@@ -127,6 +127,22 @@ __device__ __forceinline__ float straight_distance(float x0, float y0, float z0,
     return __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
 }
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
+// 1/x and 1/sqrt(x) from the hardware approximations plus two Newton steps: full double accuracy to a few ulp, a
+// fraction of the cost of the correctly rounded forms. For pivots and rotation angles, whose last bit does not matter.
+__device__ __forceinline__ double fast_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(fma(-x, r, 1.0), r, r);
+    r = fma(fma(-x, r, 1.0), r, r);
+    return r;
+}
+__device__ __forceinline__ double fast_rsqrt(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    y = y * fma(-0.5 * x * y, y, 1.5);
+    y = y * fma(-0.5 * x * y, y, 1.5);
+    return y;
+}
 __device__ __forceinline__ double shfl_double(double v, int src) {
     int lo = __double2loint(v), hi = __double2hiint(v);
     lo = __shfl_sync(0xffffffffu, lo, src);

@@ -83,23 +83,6 @@ struct EnsiSmem {
     }
 };
 
-// 1/x and 1/sqrt(x) from the hardware approximations plus Newton steps (full double accuracy to a few ulp; the
-// rotation angles of the Jacobi sweeps do not need correctly rounded divisions and square roots)
-__device__ __forceinline__ double fast_rcp(double x) {
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    r = fma(fma(-x, r, 1.0), r, r);
-    r = fma(fma(-x, r, 1.0), r, r);
-    return r;
-}
-__device__ __forceinline__ double fast_rsqrt(double x) {
-    double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    y = y * fma(-0.5 * x * y, y, 1.5);
-    y = y * fma(-0.5 * x * y, y, 1.5);
-    return y;
-}
-
 // members with an invalid value anywhere in the background are left untouched (oi_ensi.cpp:187-201)
 __global__ void ensi_invalid_members_kernel(const float* __restrict__ background, size_t n, int nE, int* __restrict__ invalid) {
     size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;

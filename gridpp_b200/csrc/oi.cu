@@ -69,7 +69,7 @@ constexpr int NCAND = 64;           // capacity of a run's candidate list (2 slo
 struct FastSmem {
     unsigned long long key[64];     // candidate keys (oi.cuh)
     double M[32 * 33];              // augmented symmetric matrix, row-major with stride 33
-    double colbuf[2][64];           // pivot column broadcast, double-buffered (entries 32.. are padding for the shifted reads)
+    __align__(16) double colbuf[2][64];   // pivot column broadcast: [0] as is, [1] shifted by one entry (entries 32.. are padding for the shifted reads)
     double sd[32];                  // innovations of the selection
     int pos[64];                    // candidate slots in the observation table
     int c_pos[32];                  // the selection in canonical order (ascending original index)
@@ -206,17 +206,25 @@ __device__ __noinline__ void solve_selected(const OiParams& P, FastSmem& S, cons
     double my_inv = 0.0;
     for(int c = 0; c < k; c++) {
         const double my = a[0];
-        const double inv = __drcp_rn(shfl_double(my, c));
-        double* cb = S.colbuf[c & 1];
-        cb[lane] = my;
+        const double inv = fast_rcp(shfl_double(my, c));
+        // the pivot column is published twice, the second copy shifted by one entry, so that the entries of columns
+        // c+1 .. c+29 can always be read as aligned 16-byte pairs
+        S.colbuf[0][lane] = my;
+        if(lane > 0) S.colbuf[1][lane - 1] = my;
         const double f = lane == c ? 0.0 : my * inv;
         if(lane == c) my_inv = inv;
         __syncwarp();
-        const double* cbc = cb + c;   // cbc[j] = pivot-row entry of column c + j (columns past 29 feed slots that are never read)
+        const int base = c + 1;       // pivot-row entry of column base + t (columns past 29 feed slots that are never read)
+        const double2* src = reinterpret_cast<const double2*>((base & 1) ? &S.colbuf[1][base - 1] : &S.colbuf[0][base]);
         #pragma unroll
-        for(int j = 1; j < FAST_K; j++) a[j - 1] = fma(-f, cbc[j], a[j]);
-        rr = fma(-f, cb[30], rr);
-        rd = fma(-f, cb[31], rd);
+        for(int q = 0; q < FAST_K / 2; q++) {
+            const double2 t = src[q];
+            a[2 * q] = fma(-f, t.x, a[2 * q + 1]);
+            if(2 * q + 2 < FAST_K) a[2 * q + 1] = fma(-f, t.y, a[2 * q + 2]);
+        }
+        rr = fma(-f, S.colbuf[0][30], rr);
+        rd = fma(-f, S.colbuf[0][31], rd);
+        __syncwarp();                 // the next step overwrites the buffers
     }
     W.z = lane < k ? rd * my_inv : 0.0;       // z = (P+R)^-1 d, one component per lane
     W.avar = -shfl_double(rr, 30);            // rho'(P+R)^-1 rho (oi.cpp:336)
