@@ -1,7 +1,7 @@
 // neighbourhood_quantile_fast with packed counters ("K3" in SURVEY.md), input staged by the copy engine (TMA).
 // Replaces gridpp::neighbourhood_quantile_fast, src/api/neighbourhood.cpp:302-409, for ascending thresholds
-// (T <= 31, no NaN), half-widths <= 15 and row lengths that are multiples of four; every other case takes the
-// general kernel in neighbourhood.cu.
+// (T <= 31, no NaN) and half-widths <= 15; every other case takes the general kernel in neighbourhood.cu. Row
+// lengths that are not a multiple of four (or narrower than one box) run the same kernel with plain loads.
 //
 // The reference needs, per pixel, F_t = #(valid v <= thr_t) / #(valid v) over the clipped window for every
 // threshold (one summed-area table per threshold), then inverts the CDF with gridpp::interpolate. Here:
@@ -35,10 +35,12 @@ constexpr int MAX_T = 31;
 constexpr int MAX_HW = 15;
 
 struct QArgs {
+    const float* in;                       // the field (plain-load form)
     float* out;
     const float* qfield;                   // may be NULL (scalar quantile)
     int n_rows_in, nx, row0, n_rows_out, hw;
     int rows_per_cta, TX, P, HL, T;
+    int vec_ok;                            // rows of the output are 16-byte aligned: 32-byte vector stores
     float quantile;
     float thr[32];                         // thresholds (ascending), padded with +inf
 };
@@ -143,7 +145,9 @@ __device__ __forceinline__ float invert_cdf(const unsigned (&n)[NW16], float q, 
 }
 
 // NW8 words of 4 byte fields cover fields 0 .. 4 NW8 - 1 (field 0 = valid, 1 .. T = thresholds, the rest pads)
-template <int NW8, bool QFIELD>
+// TMA: the input rows are staged by the copy engine (row length a multiple of 4); otherwise every thread loads its
+// column's 8 values of a stage with plain coalesced loads (any row length, narrow fields).
+template <int NW8, bool QFIELD, bool TMA>
 __global__ void __launch_bounds__(NT, 2) qf_tma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ QArgs a) {
     constexpr int NW16 = 2 * NW8;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -164,7 +168,7 @@ __global__ void __launch_bounds__(NT, 2) qf_tma_kernel(const __grid_constant__ C
     const int y_end = min(y_begin + a.rows_per_cta, a.row0 + a.n_rows_out);
     const int n_batches = (y_end - y_begin + RB - 1) / RB;
     const StageRing R = {fring, bars, &in_map, x0 - a.HL, y_begin + hw - RB * P, NSF, P + n_batches};
-    R.start();
+    if(TMA) R.start();
     // ---- tables
     if(tid < 32) sthr[tid] = a.thr[tid];
     for(int e = tid; e < NW8 * 33; e += NT) {
@@ -194,8 +198,21 @@ __global__ void __launch_bounds__(NT, 2) qf_tma_kernel(const __grid_constant__ C
 
     int brow = 0;                            // bin-ring row of the first row of the current stage
     for(int s = 0; s < P + n_batches; s++) {
-        R.wait(s);
-        const float* sp = fring + (size_t) (s % NSF) * RB * NT + scol;
+        float vals[RB];
+        if(TMA) {
+            R.wait(s);
+            const float* sp = fring + (size_t) (s % NSF) * RB * NT + scol;
+            #pragma unroll
+            for(int b = 0; b < RB; b++) vals[b] = sp[b * NT];
+        }
+        else {
+            const int xg = x0 - a.HL + scol;                        // field column of this thread
+            const int rg = y_begin + hw - RB * P + RB * s;          // field row of the stage's first row
+            const bool col_ok = xg >= 0 && xg < a.nx;
+            #pragma unroll
+            for(int b = 0; b < RB; b++)
+                vals[b] = (col_ok && rg + b >= 0 && rg + b < a.n_rows_in) ? __ldg(a.in + (size_t) (rg + b) * a.nx + xg) : NAN;
+        }
         const bool batch = s >= P;
         // bin-ring row of the row that leaves when row b of this stage enters: (8 s + b) - w + ... = the row 2 hw + 1
         // rows older; as an index: brow + b - w (mod NRB). NRB = 8 (P + 1) >= w + 7.
@@ -204,7 +221,7 @@ __global__ void __launch_bounds__(NT, 2) qf_tma_kernel(const __grid_constant__ C
         // ---- vertical pass: classify the 8 landed values, slide the column counters, record them
         #pragma unroll
         for(int b = 0; b < RB; b++) {
-            const float v = sp[b * NT];
+            const float v = vals[b];
             const float* tp = sthr;                       // lower bound: tp - sthr = #(thresholds < v)
             #pragma unroll
             for(int step = 16; step > 0; step >>= 1)
@@ -229,7 +246,7 @@ __global__ void __launch_bounds__(NT, 2) qf_tma_kernel(const __grid_constant__ C
         brow += RB;
         if(brow == NRB) brow = 0;
         __syncthreads();
-        R.recycle(s);                        // the float stage has been classified
+        if(TMA) R.recycle(s);                // the float stage has been classified
         if(!batch) continue;
         const int y0 = y_begin + RB * (s - P);
         // ---- group sums: thread (row hb, group seg) adds the 8 columns of its group (bytes, <= 248) and expands
@@ -311,7 +328,7 @@ __global__ void __launch_bounds__(NT, 2) qf_tma_kernel(const __grid_constant__ C
                 }
             }
             float* dst = a.out + (size_t) (y - a.row0) * a.nx + x;
-            if(x + SEG <= a.nx) {
+            if(a.vec_ok && x + SEG <= a.nx) {
                 reinterpret_cast<float4*>(dst)[0] = make_float4(o[0], o[1], o[2], o[3]);
                 reinterpret_cast<float4*>(dst)[1] = make_float4(o[4], o[5], o[6], o[7]);
             }
@@ -326,17 +343,11 @@ __global__ void __launch_bounds__(NT, 2) qf_tma_kernel(const __grid_constant__ C
 }
 
 template <int NW8>
-int launch_qf(bool qfield, dim3 grid, size_t smem, cudaStream_t stream, const CUtensorMap& map, const QArgs& a) {
-    if(qfield) {
-        auto kernel = qf_tma_kernel<NW8, true>;
-        GPP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        GPP_LAUNCH(kernel, grid, NT, smem, stream, map, a);
-    }
-    else {
-        auto kernel = qf_tma_kernel<NW8, false>;
-        GPP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        GPP_LAUNCH(kernel, grid, NT, smem, stream, map, a);
-    }
+int launch_qf(bool qfield, bool tma, dim3 grid, size_t smem, cudaStream_t stream, const CUtensorMap& map, const QArgs& a) {
+    auto kernel = tma ? (qfield ? qf_tma_kernel<NW8, true, true> : qf_tma_kernel<NW8, false, true>)
+                      : (qfield ? qf_tma_kernel<NW8, true, false> : qf_tma_kernel<NW8, false, false>);
+    GPP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    GPP_LAUNCH(kernel, grid, NT, smem, stream, map, a);
     return GPP_OK;
 }
 
@@ -349,8 +360,9 @@ int qf_tma_try(const float* d_input, int n_rows_in, int nx, int row0, int n_rows
                int hw, const float* thresholds, int T, float* d_output, cudaStream_t stream, int* handled) {
     *handled = 0;
     if(getenv("GPP_NO_TMA")) return GPP_OK;
-    if(nx % 4 != 0 || nx < NT || hw < 1 || hw > MAX_HW || T < 1 || T > MAX_T) return GPP_OK;
-    if(((uintptr_t) d_input & 15) != 0 || ((uintptr_t) d_output & 15) != 0) return GPP_OK;
+    if(hw < 1 || hw > MAX_HW || T < 1 || T > MAX_T) return GPP_OK;
+    // the copy engine needs 16-byte row pitches and a field at least one box wide; other shapes load directly
+    const bool tma = nx % 4 == 0 && nx >= NT && ((uintptr_t) d_input & 15) == 0;
     for(int t = 0; t < T; t++) {
         if(std::isnan(thresholds[t])) return GPP_OK;
         if(t > 0 && thresholds[t] < thresholds[t - 1]) return GPP_OK;
@@ -358,7 +370,9 @@ int qf_tma_try(const float* d_input, int n_rows_in, int nx, int row0, int n_rows
     if(!d_quantile_field && std::isnan(quantile)) return GPP_OK;      // all-missing output: the general kernel's job
     QArgs a;
     std::memset(&a, 0, sizeof(a));
+    a.in = d_input;
     a.out = d_output;
+    a.vec_ok = nx % 4 == 0 && ((uintptr_t) d_output & 15) == 0;
     a.qfield = d_quantile_field;
     a.n_rows_in = n_rows_in; a.nx = nx; a.row0 = row0; a.n_rows_out = n_rows_out; a.hw = hw;
     a.HL = (hw + 3) / 4 * 4;
@@ -383,16 +397,17 @@ int qf_tma_try(const float* d_input, int n_rows_in, int nx, int row0, int n_rows
     a.rows_per_cta = rows;
     chunks = (n_rows_out + rows - 1) / rows;
     CUtensorMap map;
-    GPP_TRY(make_field_tensor_map(&map, d_input, n_rows_in, nx, RB, NT, true));
+    std::memset(&map, 0, sizeof(map));
+    if(tma) GPP_TRY(make_field_tensor_map(&map, d_input, n_rows_in, nx, RB, NT, true));
     dim3 grid(strips, chunks);
     const bool qf = d_quantile_field != nullptr;
     switch(NW8) {
-        case 1: GPP_TRY(launch_qf<1>(qf, grid, smem, stream, map, a)); break;
-        case 2: GPP_TRY(launch_qf<2>(qf, grid, smem, stream, map, a)); break;
-        case 3: GPP_TRY(launch_qf<3>(qf, grid, smem, stream, map, a)); break;
-        case 4: GPP_TRY(launch_qf<4>(qf, grid, smem, stream, map, a)); break;
-        case 6: GPP_TRY(launch_qf<6>(qf, grid, smem, stream, map, a)); break;
-        default: GPP_TRY(launch_qf<8>(qf, grid, smem, stream, map, a)); break;
+        case 1: GPP_TRY(launch_qf<1>(qf, tma, grid, smem, stream, map, a)); break;
+        case 2: GPP_TRY(launch_qf<2>(qf, tma, grid, smem, stream, map, a)); break;
+        case 3: GPP_TRY(launch_qf<3>(qf, tma, grid, smem, stream, map, a)); break;
+        case 4: GPP_TRY(launch_qf<4>(qf, tma, grid, smem, stream, map, a)); break;
+        case 6: GPP_TRY(launch_qf<6>(qf, tma, grid, smem, stream, map, a)); break;
+        default: GPP_TRY(launch_qf<8>(qf, tma, grid, smem, stream, map, a)); break;
     }
     *handled = 1;
     return GPP_OK;

@@ -451,7 +451,7 @@ def test_quantile_fast_packed_counter_path(gpp, orc):
     import torch
     from gridpp_b200 import device as gd
     rng = np.random.default_rng(5)
-    for shape in ((150, 512), (70, 260)):
+    for shape in ((150, 512), (70, 260), (90, 333), (45, 70)):   # the last two: plain-load form (odd / narrow rows)
         f = rng.gamma(0.5, 2.0, size=shape).astype(f32)
         f[rng.uniform(size=shape) < 0.3] = 0
         f[rng.uniform(size=shape) < 0.02] = np.nan
