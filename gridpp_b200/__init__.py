@@ -528,6 +528,22 @@ def neighbourhood_quantile_fast(input, quantile, halfwidth, thresholds):
     return out
 
 
+def get_neighbourhood_thresholds(input, num_thresholds):
+    """gridpp::get_neighbourhood_thresholds(vec2 | vec3, num_thresholds), neighbourhood.cpp:243-295."""
+    field = _np.asarray(input, dtype=_np.float32)
+    if field.ndim not in (2, 3):
+        raise ValueError("input must have 2 or 3 dimensions")
+    if num_thresholds <= 0:
+        raise ValueError("num_thresholds must be > 0")
+    if field.size == 0:
+        return _np.zeros(0, _np.float32)
+    flat = _np.ascontiguousarray(field.ravel())
+    out = _np.empty(int(num_thresholds), _np.float32)
+    n = _C.c_int()
+    _check(_libc.gpp_get_neighbourhood_thresholds_host(_fptr(flat), flat.size, int(num_thresholds), _fptr(out), _C.byref(n)))
+    return out[:n.value].copy()
+
+
 # ---------------------------------------------------------------------------------------------------------
 def nearest(igrid, ogrid, ivalues):
     """gridpp::nearest, nearest.cpp:7-222 (all eight Grid/Points x Grid/Points x 2-D/3-D overloads)."""

@@ -80,6 +80,8 @@ _proto("gpp_neighbourhood_ens_device", C.c_int, vp, C.c_int, C.c_int, C.c_int, C
 _proto("gpp_neighbourhood_quantile_fast_ens_host", C.c_int, fp, C.c_int, C.c_int, C.c_int, C.c_float, fp, C.c_int, fp, C.c_int, fp)
 _proto("gpp_neighbourhood_quantile_fast_ens_device", C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_float, vp, C.c_int, fp, C.c_int, vp, vp)
 
+_proto("gpp_get_neighbourhood_thresholds_host", C.c_int, fp, C.c_longlong, C.c_int, fp, ip)
+
 EXPORTS = [
     "gpp_version", "gpp_last_error", "gpp_device_count", "gpp_set_device", "gpp_device_synchronize",
     "gpp_kernel_launch_count", "gpp_measure_fp64_fma_peak", "gpp_structure_init", "gpp_structure_multiple", "gpp_structure_cross_validation",
@@ -90,6 +92,7 @@ EXPORTS = [
     "gpp_neighbourhood_host", "gpp_neighbourhood_device", "gpp_neighbourhood_quantile_fast_host",
     "gpp_neighbourhood_quantile_fast_device", "gpp_neighbourhood_ens_host", "gpp_neighbourhood_ens_device",
     "gpp_neighbourhood_quantile_fast_ens_host", "gpp_neighbourhood_quantile_fast_ens_device",
+    "gpp_get_neighbourhood_thresholds_host",
 ]
 
 

@@ -215,6 +215,11 @@ int gpp_neighbourhood_quantile_fast_ens_device(const float* d_input, int ny, int
                                                const float* d_quantile_field, int halfwidth, const float* thresholds,
                                                int num_thresholds, float* d_output, void* stream);
 
+/* gridpp::get_neighbourhood_thresholds(vec2 | vec3, num_thresholds) neighbourhood.cpp:243-295 (both forms pool every
+ * valid value, so the field is passed flattened): up to num_thresholds values are written, *num_out tells how many. */
+int gpp_get_neighbourhood_thresholds_host(const float* input, long long n_values, int num_thresholds, float* thresholds,
+                                          int* num_out);
+
 /* ---------------------------------------------------------------- instrumentation -------------------- */
 /* Number of kernels this library has launched on the calling process so far (bench.py's gpu_launches). */
 unsigned long long gpp_kernel_launch_count(void);

@@ -537,6 +537,40 @@ def test_ensemble_forms(gpp, orc):
         gpp.neighbourhood_quantile_fast(v3, 1.5, 1, [0, 1])
 
 
+def test_get_neighbourhood_thresholds(gpp, orc):
+    """gridpp::get_neighbourhood_thresholds, neighbourhood.cpp:243-295 / calc_even_quantiles util.cpp:261-338: the
+    reference's known answers (tests/test_get_neighbourhood_thresholds.py:8-51) and the oracle on random fields with
+    missing values, long runs of the lowest value, more thresholds than values, and the 3-D form. Bit-exact."""
+    for num in (-1, 0):
+        with pytest.raises(ValueError):
+            gpp.get_neighbourhood_thresholds(np.ones([5, 5]), num)
+    for num in (1, 5):
+        assert gpp.get_neighbourhood_thresholds(np.zeros((0, 0)), num).size == 0
+    field = np.reshape(np.arange(4), [2, 2])
+    for num in (4, 5, 6):
+        np.testing.assert_array_equal(gpp.get_neighbourhood_thresholds(field, num), [0, 1, 2, 3])
+    field = np.reshape([0, 0, 2, 3, 4, 5, 6, 11, 8, 9, 10, 11], [3, 4]).astype(f32)
+    for num in range(1, 6):
+        assert_bit_exact(gpp.get_neighbourhood_thresholds(field, num), orc.get_neighbourhood_thresholds(field, num), "duplicates num=%d" % num)
+    rng = np.random.default_rng(21)
+    f = rng.gamma(0.5, 2.0, size=(300, 257)).astype(f32)
+    f[rng.uniform(size=f.shape) < 0.05] = np.nan
+    f[3, 3] = np.inf
+    g = f.copy()
+    g[rng.uniform(size=f.shape) < 0.4] = 0          # a long run of the lowest value (util.cpp:302-308)
+    for name, fld in (("gamma", f), ("zeros", g), ("constant", np.full((20, 30), 2.5, f32)), ("all missing", np.full((4, 4), np.nan, f32))):
+        for num in (1, 2, 3, 11, 20, 64):
+            assert_bit_exact(gpp.get_neighbourhood_thresholds(fld, num), orc.get_neighbourhood_thresholds(fld, num), "%s num=%d" % (name, num))
+    v = rng.uniform(size=(10, 10)).astype(f32)
+    v3 = np.repeat(v[:, :, None], 5, axis=2)
+    for num in (1, 5):
+        np.testing.assert_array_almost_equal(gpp.get_neighbourhood_thresholds(v, num), gpp.get_neighbourhood_thresholds(v3, num))
+    # thresholds from the device feed quantile_fast exactly like the oracle's
+    thr = gpp.get_neighbourhood_thresholds(f, 11)
+    assert_bit_exact(gpp.neighbourhood_quantile_fast(f, 0.9, 2, thr), orc.neighbourhood_quantile_fast(f, 0.9, 2, orc.get_neighbourhood_thresholds(f, 11)),
+                     "quantile_fast on device thresholds")
+
+
 # ------------------------------------------------------------------ full BASELINE.json sizes ------------
 def test_full_size_neighbourhood_properties(gpp, orc):
     """Config 2 (4000 x 4000, halfwidth 7): the stencil is local, so any window of the full-size result must equal
