@@ -62,7 +62,11 @@ constexpr int SEG = 8;               // consecutive pixels per thread in the hor
 #ifndef NBH_MINB_MM
 #define NBH_MINB_MM 4
 #endif
-constexpr int PREFETCH = NBH_PF;     // stages in flight beyond the ones the window needs
+#ifndef NBH_PF_MM
+#define NBH_PF_MM NBH_PF
+#endif
+constexpr int PREFETCH = NBH_PF;     // stages in flight beyond the ones the window needs (sums)
+constexpr int PREFETCH_MM = NBH_PF_MM;   // ... (extremes)
 constexpr int MINB_SUM = NBH_MINB_SUM, MINB_MM = NBH_MINB_MM;   // resident CTAs per SM the kernels are built for
 constexpr int RCP_MAX = 1024;
 // Line buffers hold one record per window column and batch row. The vertical pass writes them with consecutive
@@ -213,6 +217,11 @@ __global__ void __launch_bounds__(NT, MINB_SUM) nbh_sum_tma_kernel(const __grid_
         const float v = ring_col[rel * NT];
         if(finite_f(v)) st.csum += (double) v; else st.ninv++;
     }
+    float hist[REGWIN ? 2 * HW : 1];   // register-window form: rows y0 - hw .. y0 + hw - 1 of the column
+    if constexpr(REGWIN) {
+        #pragma unroll
+        for(int j = 0; j < 2 * HW; j++) hist[j] = ring_col[(rel0 + j) * NT];
+    }
     const int hb = tid >> 5, seg = tid & 31, xo0 = seg * SEG;
     const bool h_active = xo0 < a.TX && x0 + xo0 < a.nx;
     const bool strip_inside = x0 - hw >= 0 && x0 + a.TX - 1 + hw < a.nx;   // no window of the strip is clipped sideways
@@ -225,16 +234,28 @@ __global__ void __launch_bounds__(NT, MINB_SUM) nbh_sum_tma_kernel(const __grid_
         // ---- vertical pass: row y0 + b + hw enters, the record of output row y0 + b is written, row y0 + b - hw leaves
         {
             const float* newp = ring_col + s_new * (RB * NT);
-            const int s_old2 = s_old + 1 == NS ? 0 : s_old + 1;
-            const float* oldA = ring_col + (s_old * RB + rel0) * NT;           // leaving rows b < RB - rel0
-            const float* oldB = ring_col + (s_old2 * RB + rel0 - RB) * NT;     // leaving rows b >= RB - rel0
-            // c[b] = column sum before row b enters; the record of row b is c[b] + new[b]; c[b+1] = c[b] + (new[b] -
-            // old[b]). Evaluated as a shallow tree instead of a 16-deep dependent chain.
             double dn[RB], dd[RB], c[RB + 1];
-            #pragma unroll
-            for(int b = 0; b < RB; b++) {
-                dn[b] = (double) newp[b * NT];
-                dd[b] = dn[b] - (double) (b < RB - rel0 ? oldA[b * NT] : oldB[b * NT]);
+            if constexpr(REGWIN) {
+                // the 2 hw rows above the entering stage are kept in registers: the leaving rows are hist[0 .. 7]
+                float vn[RB];
+                #pragma unroll
+                for(int b = 0; b < RB; b++) {
+                    vn[b] = newp[b * NT];
+                    dn[b] = (double) vn[b];
+                    dd[b] = dn[b] - (double) (b < 2 * HW ? hist[b] : vn[b - 2 * HW]);
+                }
+                #pragma unroll
+                for(int j = 0; j < 2 * HW; j++) hist[j] = j + RB < 2 * HW ? hist[j + RB] : vn[j + RB - 2 * HW];
+            }
+            else {
+                const int s_old2 = s_old + 1 == NS ? 0 : s_old + 1;
+                const float* oldA = ring_col + (s_old * RB + rel0) * NT;           // leaving rows b < RB - rel0
+                const float* oldB = ring_col + (s_old2 * RB + rel0 - RB) * NT;     // leaving rows b >= RB - rel0
+                #pragma unroll
+                for(int b = 0; b < RB; b++) {
+                    dn[b] = (double) newp[b * NT];
+                    dd[b] = dn[b] - (double) (b < RB - rel0 ? oldA[b * NT] : oldB[b * NT]);
+                }
             }
             c[0] = st.csum;
             #pragma unroll
@@ -389,7 +410,7 @@ __global__ void __launch_bounds__(NT, MINB_MM) nbh_minmax_tma_kernel(const __gri
     constexpr bool STATIC = HW > 0;
     const int hw = STATIC ? HW : a.hw, w = 2 * hw + 1;
     const int P = STATIC ? (2 * HW + RB - 1) / RB : a.P;
-    const int NS = STATIC ? P + 1 + PREFETCH : a.NS;
+    const int NS = STATIC ? P + 1 + PREFETCH_MM : a.NS;
     const int NR = NS * RB;
     float* ring = reinterpret_cast<float*>(smem);                       // [NS * RB][NT]
     float* line = ring + (size_t) NR * NT;                              // [RB][LROW_F] column extremes
@@ -418,6 +439,13 @@ __global__ void __launch_bounds__(NT, MINB_MM) nbh_minmax_tma_kernel(const __gri
     float* const my_line = line + idx_f<REGWIN>(tid);
     int first = rel0;                     // ring row of the first row of the window of output row y0
     int s_new = P % NS;
+    // register-window form: the 2 hw rows above the entering stage stay in registers from batch to batch (14 moves
+    // instead of 14 shared-memory loads per batch and thread; the kernel is bound by the L1/shared data pipe)
+    float hist[REGWIN ? 2 * HW : 1];
+    if constexpr(REGWIN) {
+        #pragma unroll
+        for(int j = 0; j < 2 * HW; j++) hist[j] = ring[(rel0 + j) * NT + scol];   // rows y_begin - hw .. y_begin + hw - 1 (sanitised above)
+    }
 
     for(int i = 0; i < n_batches; i++) {
         const int y0 = y_begin + RB * i;
@@ -438,10 +466,13 @@ __global__ void __launch_bounds__(NT, MINB_MM) nbh_minmax_tma_kernel(const __gri
                 constexpr int W = 2 * HW + 1;
                 float v[W + RB - 1];
                 #pragma unroll
-                for(int j = 0; j < W - 1; j++) { int s = first + j; if(s >= NR) s -= NR; v[j] = base[s * NT]; }
+                for(int j = 0; j < W - 1; j++) v[j] = hist[j];
                 #pragma unroll
                 for(int b = 0; b < RB; b++) v[W - 1 + b] = vnew[b];
                 eight_windows<IS_MAX>([&](int j) { return v[j]; }, W, out);
+                #pragma unroll
+                for(int j = 0; j < W - 1; j++) hist[j] = v[j + RB];
+                (void) base;
             }
             else
                 eight_windows<IS_MAX>([&](int j) { int s = first + j; if(s >= NR) s -= NR; return base[s * NT]; }, w, out);
@@ -527,7 +558,7 @@ int nbh_tma_try(const float* d_input, int n_rows_in, int nx, int row0, int n_row
     a.TX = (NT - a.HL - hw) / SEG * SEG;
     if(a.TX < NT / 2) return GPP_OK;
     a.P = (2 * hw + RB - 1) / RB;
-    a.NS = a.P + 1 + PREFETCH;
+    a.NS = a.P + 1 + (statistic == GPP_MIN || statistic == GPP_MAX ? PREFETCH_MM : PREFETCH);
     const int w = 2 * hw + 1;
     a.n_rcp = std::min(RCP_MAX, w * w + 1);
     const bool minmax = statistic == GPP_MIN || statistic == GPP_MAX;
