@@ -327,11 +327,112 @@ def _single(stype, h, v, w, hmax):
     return d
 
 
-class BarnesStructure(StructureFunction):
-    def __init__(self, h, v=0, w=0, hmax=MV):
-        if _np.ndim(h) != 0:
-            raise NotImplementedOnDevice("spatially varying structure functions are not part of the device path yet")
-        StructureFunction.__init__(self, _single(_BARNES, h, v, w, hmax))
+_DEFAULT_MIN_RHO = 0.0013   # StructureFunction::default_min_rho, structure.cpp:5
+
+
+def _recompute_loc_dist(stype, h, min_rho):
+    """localization_distance(h) for an explicit min_rho (the (1, 1)-field constructors), float arithmetic as the reference."""
+    f = _np.float32
+    m, h = f(min_rho), f(h)
+    if stype == _BARNES:
+        return float(_np.sqrt(f(-2) * _np.log(m)) * h)
+    if stype == _SOAR:
+        l = _np.log(m)
+        return float((-l + _np.log(-l)) * h)
+    if stype == _TOAR:
+        l = _np.log(m)
+        ll = _np.log(-_np.log(m))
+        return float(f((float(-l + ll) + 0.5 * float(ll)) * float(h)))
+    if stype == _POWERLAW:
+        return float(_np.sqrt(f(2) * (f(1) - m) / m) * h)
+    return 0.0
+
+
+class _SpatialField:
+    """Scales h, v, w on the nodes of a Grid (gpp_structure_field): <Family>Structure(Grid, vec2 h, vec2 v, vec2 w, min_rho),
+    structure.cpp:168-184 (Barnes), :342 (Soar), :492 (Toar), :643 (Powerlaw), :790 (Linear)."""
+
+    def __init__(self, grid, h, v, w):
+        if not isinstance(grid, Grid):
+            raise ValueError("the first argument of a spatially varying structure function must be a Grid")
+        shape = tuple(grid.size())
+        arrays = []
+        for name, a in (("h", h), ("v", v), ("w", w)):
+            a = _farray(a, 2, name)
+            if a.shape != shape:
+                raise ValueError("Grid size not the same as scale size")
+            arrays.append(a)
+        self.grid = grid          # keeps the grid (and its device index) alive
+        self._handle = _C.c_void_p()
+        _check(_libc.gpp_structure_field_create(grid._set._handle, _fptr(arrays[0]), _fptr(arrays[1]), _fptr(arrays[2]),
+                                                _C.byref(self._handle)))
+
+    def __del__(self):
+        h = getattr(self, "_handle", None)
+        if h and _libc is not None:
+            _libc.gpp_structure_field_destroy(h)
+            self._handle = None
+
+
+class _Family(StructureFunction):
+    _TYPE = None
+
+    def __init__(self, *args):
+        self._field = None
+        if len(args) > 0 and isinstance(args[0], Grid):
+            if len(args) < 4 or len(args) > 5:
+                raise ValueError("expected (grid, h, v, w[, min_rho])")
+            grid, h, v, w = args[:4]
+            min_rho = float(args[4]) if len(args) == 5 else _DEFAULT_MIN_RHO
+            h2, v2, w2 = (_np.asarray(a, _np.float32) for a in (h, v, w))
+            if h2.shape == (1, 1) and v2.shape == (1, 1) and w2.shape == (1, 1):
+                # not spatial (structure.cpp:174-176): constant scales with the given min_rho
+                d = _single(self._TYPE, float(h2[0, 0]), float(v2[0, 0]), float(w2[0, 0]), MV)
+                d.term[0].min_rho = min_rho
+                d.term[0].loc_dist = _recompute_loc_dist(self._TYPE, float(h2[0, 0]), min_rho)
+                StructureFunction.__init__(self, d)
+                return
+            self._field = _SpatialField(grid, h2, v2, w2)
+            self._min_rho = min_rho
+            d = _lib.StructureDesc()
+            d.n_terms = 1
+            d.term[0].type = self._TYPE
+            d.term[0].min_rho = min_rho
+            StructureFunction.__init__(self, d)
+            return
+        h = args[0]
+        v = args[1] if len(args) > 1 else 0
+        w = args[2] if len(args) > 2 else 0
+        hmax = args[3] if len(args) > 3 else MV
+        StructureFunction.__init__(self, _single(self._TYPE, h, v, w, hmax))
+
+    def localization_distance(self, point=None):
+        if self._field is None:
+            return StructureFunction.localization_distance(self, point)
+        if point is None:
+            raise ValueError("a spatially varying structure function needs the point (lat, lon)")
+        lat, lon = (point.lat, point.lon) if hasattr(point, "lat") else (point[0], point[1])
+        out = _C.c_float()
+        _check(_libc.gpp_structure_field_localization_distance(self._field._handle, self._TYPE, self._min_rho, float(lat), float(lon),
+                                                               _C.byref(out)))
+        return float(out.value)
+
+    def _corr(self, p1, p2, background):
+        if self._field is not None:
+            raise NotImplementedOnDevice("corr() of a spatially varying structure function is only evaluated inside optimal_interpolation()")
+        return StructureFunction._corr(self, p1, p2, background)
+
+    def clone(self):
+        c = StructureFunction.clone(self)
+        c._field = self._field
+        if self._field is not None:
+            c._min_rho = self._min_rho
+        return c
+
+
+class BarnesStructure(_Family):
+    """BarnesStructure(h, v=0, w=0, hmax=MV) or BarnesStructure(grid, h, v, w, min_rho=0.0013)."""
+    _TYPE = _BARNES
 
 
 class CressmanStructure(StructureFunction):
@@ -339,28 +440,31 @@ class CressmanStructure(StructureFunction):
         StructureFunction.__init__(self, _single(_CRESSMAN, h, v, w, MV))
 
 
-class SoarStructure(StructureFunction):
-    def __init__(self, h, v=0, w=0, hmax=MV):
-        StructureFunction.__init__(self, _single(_SOAR, h, v, w, hmax))
+class SoarStructure(_Family):
+    _TYPE = _SOAR
 
 
-class ToarStructure(StructureFunction):
-    def __init__(self, h, v=0, w=0, hmax=MV):
-        StructureFunction.__init__(self, _single(_TOAR, h, v, w, hmax))
+class ToarStructure(_Family):
+    _TYPE = _TOAR
 
 
-class PowerlawStructure(StructureFunction):
-    def __init__(self, h, v=0, w=0, hmax=MV):
-        StructureFunction.__init__(self, _single(_POWERLAW, h, v, w, hmax))
+class PowerlawStructure(_Family):
+    _TYPE = _POWERLAW
 
 
-class LinearStructure(StructureFunction):
-    def __init__(self, h, v=0, w=0, hmax=MV):
-        StructureFunction.__init__(self, _single(_LINEAR, h, v, w, hmax))
+class LinearStructure(_Family):
+    _TYPE = _LINEAR
+
+
+def _reject_spatial(*structures):
+    for st in structures:
+        if getattr(st, "_field", None) is not None:
+            raise NotImplementedOnDevice("spatially varying structure functions cannot be nested in MultipleStructure / CrossValidation on the device")
 
 
 class MultipleStructure(StructureFunction):
     def __init__(self, structure_h, structure_v, structure_w):
+        _reject_spatial(structure_h, structure_v, structure_w)
         d = _lib.StructureDesc()
         _check(_libc.gpp_structure_multiple(_C.byref(d), _C.byref(structure_h._desc), _C.byref(structure_v._desc),
                                             _C.byref(structure_w._desc)))
@@ -369,6 +473,7 @@ class MultipleStructure(StructureFunction):
 
 class CrossValidation(StructureFunction):
     def __init__(self, structure, dist=MV):
+        _reject_spatial(structure)
         d = _lib.StructureDesc()
         _check(_libc.gpp_structure_cross_validation(_C.byref(d), _C.byref(structure._desc), float(dist)))
         StructureFunction.__init__(self, d)
@@ -428,6 +533,13 @@ def _oi(bgrid, background, bvariance, points, pobs, obs_variance, pbackground, b
         _check_size(pbvar.size == nS, "Background variance (%d) and points (%d) size mismatch" % (pbvar.size, nS))
     out = _np.empty(shape, _np.float32)
     var = _np.empty(shape, _np.float32) if full else None
+    field = getattr(structure, "_field", None)
+    if field is not None:
+        _check(_libc.gpp_optimal_interpolation_spatial_host(bgrid._set._handle, _fptr(bg), _fptr(bvar), points._set._handle, _fptr(obs),
+                                                            _fptr(ovar), _fptr(pbg), _fptr(pbvar), int(structure._TYPE), field._handle,
+                                                            float(structure._min_rho), int(max_points), int(bool(allow_extrapolation)),
+                                                            _fptr(out), _fptr(var)))
+        return (out, var) if full else out
     _check(_libc.gpp_optimal_interpolation_host(bgrid._set._handle, _fptr(bg), _fptr(bvar), points._set._handle, _fptr(obs),
                                                 _fptr(ovar), _fptr(pbg), _fptr(pbvar), _C.byref(structure._desc),
                                                 int(max_points), int(bool(allow_extrapolation)), _fptr(out), _fptr(var)))

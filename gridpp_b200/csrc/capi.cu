@@ -62,6 +62,24 @@ float term_loc_dist(int type, float h, float m) {
     }
 }
 
+}  // namespace
+namespace gpp {
+// Constants of <Family>Structure::localization_distance(h) for a spatially varying h: loc_c * h in float, or for Toar
+// (float) (loc_d * h) (the reference's expression mixes float and double, structure.cpp:603-609). Evaluated here with the
+// host libm, like the constant-scale case.
+int spatial_loc_constants(int type, float min_rho, float* loc_c, double* loc_d) {
+    *loc_c = 0.f;
+    *loc_d = 0.0;
+    switch(type) {
+        case GPP_STRUCT_BARNES: case GPP_STRUCT_SOAR: case GPP_STRUCT_POWERLAW: *loc_c = term_loc_dist(type, 1.f, min_rho); return GPP_OK;
+        case GPP_STRUCT_TOAR: { float l = logf(min_rho); float ll = logf(-logf(min_rho)); *loc_d = (-l + ll + 0.5 * ll); return GPP_OK; }
+        case GPP_STRUCT_LINEAR: return GPP_OK;   // structure.cpp:902-904: always 0
+        default: return fail(GPP_ERR_INVALID_ARGUMENT, "structure function type %d has no spatially varying form", type);
+    }
+}
+float spatial_loc_dist_host(int type, float h, float loc_c, double loc_d) { return type == GPP_STRUCT_TOAR ? (float) (loc_d * h) : loc_c * h; }
+}  // namespace gpp
+namespace {
 // fp64 FMA peak probe: 8 independent dependent-chains per thread, 2 flops per DFMA
 __global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, double seed) {
     double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;

@@ -15,6 +15,7 @@
 // max_points, non-symmetric structure functions) takes the general kernel: Gauss-Jordan with partial pivoting
 // on a per-warp global-memory scratch matrix.
 #include "oi.cuh"
+#include "structure_field.cuh"
 
 #include <algorithm>
 #include <cstring>
@@ -43,6 +44,11 @@ struct OiParams {
     int tile_nx;                     // > 0: the range is whole rows of a grid with this row length -> 4 x 4 tiles
     unsigned char* lru;              // per-warp cache of solved systems (LRU_ENTRIES x LruEntry), global memory
     int* work_counter;               // next chunk of runs to hand out (zeroed before the launch)
+    // spatially varying structure function (general kernel only): scales at every background point, and the constants of
+    // localization_distance(h) = loc_c * h (Toar: (float) (loc_d * h), structure.cpp:603-609)
+    const float *sbh, *sbv, *sbw;
+    float loc_c;
+    double loc_d;
 };
 
 // oi.cpp:318-337: optional clamp, then output and analysis variance
@@ -566,6 +572,12 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 2) oi_fast_kernel(const __
     }
 }
 
+// <Family>Structure::localization_distance(h) for a spatially varying scale (structure.cpp:280-282, 454-459, 603-609,
+// 755-757, 902-904): a constant of min_rho times h, evaluated with the reference's float / double mix
+__device__ __forceinline__ float spatial_loc_dist(const OiParams& P, float h) {
+    return P.s.term[0].type == GPP_STRUCT_TOAR ? (float) __dmul_rn(P.loc_d, (double) h) : __fmul_rn(P.loc_c, h);
+}
+
 // ------------------------------------------------------------------ general path ----------------------
 // Per-warp scratch in global memory: two candidate buffers of (kcap + 32) entries and a kcap x (kcap + 2)
 // row-major fp64 matrix [P+R | d | rho].
@@ -624,8 +636,15 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) oi_general_kernel(const __
         Pt p1 = {0, 0, 0, 0, 0};
         if(!done) {
             p1 = {P.gx[g], P.gy[g], P.gz[g], P.gelev[g], P.glaf[g]};
-            float lo0 = __fsub_rn(p1.x, P.R), lo1 = __fsub_rn(p1.y, P.R), lo2 = __fsub_rn(p1.z, P.R);
-            float hi0 = __fadd_rn(p1.x, P.R), hi1 = __fadd_rn(p1.y, P.R), hi2 = __fadd_rn(p1.z, P.R);
+            // the structure function as this point sees it (structure.cpp:189-199: the scales of the nearest node)
+            gpp_structure sp = P.s;
+            float R = P.R;
+            if(P.sbh) {
+                R = spatial_loc_dist(P, P.sbh[g]);
+                sp.term[0].h = P.sbh[g]; sp.term[0].v = P.sbv[g]; sp.term[0].w = P.sbw[g]; sp.term[0].loc_dist = R;
+            }
+            float lo0 = __fsub_rn(p1.x, R), lo1 = __fsub_rn(p1.y, R), lo2 = __fsub_rn(p1.z, R);
+            float hi0 = __fadd_rn(p1.x, R), hi1 = __fadd_rn(p1.y, R), hi2 = __fadd_rn(p1.z, R);
             int n = 0;
             if(lo0 < hi0 && lo1 < hi1 && lo2 < hi2) {
                 int cx0 = cell_coord(obs.geom, 0, lo0), cx1 = cell_coord(obs.geom, 0, hi0);
@@ -644,10 +663,10 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) oi_general_kernel(const __
                                 ok = ox > lo0 && ox < hi0 && oy > lo1 && oy < hi1 && oz > lo2 && oz < hi2;
                                 if(ok) {
                                     float dist = straight_distance(ox, oy, oz, p1.x, p1.y, p1.z);
-                                    ok = dist <= P.R;
+                                    ok = dist <= R;
                                     if(ok) {
                                         Pt p2 = {ox, oy, oz, obs.elev[i], obs.laf[i]};
-                                        rho = structure_corr_background(P.s, p1, p2, dist);
+                                        rho = structure_corr_background(sp, p1, p2, dist);
                                         ok = rho > 0.f;
                                     }
                                 }
@@ -681,7 +700,14 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) oi_general_kernel(const __
             int pi = S.pos[cur][i], pj = S.pos[cur][j];
             Pt a = {obs.x[pi], obs.y[pi], obs.z[pi], obs.elev[pi], obs.laf[pi]};
             Pt b = {obs.x[pj], obs.y[pj], obs.z[pj], obs.elev[pj], obs.laf[pj]};
-            double v = (double) structure_corr(P.s, a, b);
+            double v;
+            if(obs.sh) {   // corr(obs_i, obs_j) uses the scales at obs_i (structure.cpp:185-213): P is not symmetric
+                gpp_structure si = P.s;
+                si.term[0].h = obs.sh[pi]; si.term[0].v = obs.sv[pi]; si.term[0].w = obs.sw[pi];
+                si.term[0].loc_dist = spatial_loc_dist(P, obs.sh[pi]);
+                v = (double) structure_corr(si, a, b);
+            }
+            else v = (double) structure_corr(P.s, a, b);
             if(i == j) v = __dadd_rn(v, (double) obs.ratio[pi]);
             S.M[(size_t) i * ld + j] = v;
         }
@@ -804,7 +830,8 @@ __global__ void copy_background_kernel(const float* __restrict__ background, con
 
 // ---------------------------------------------------------------------------------------------------------
 int gpp::build_obs_table(const gpp_points* op, const std::vector<char>& valid, const std::vector<double>& innov,
-                         const std::vector<float>& ratio, float loc_dist, gpp_oi_obs* out, std::vector<int>* order) {
+                         const std::vector<float>& ratio, float loc_dist, gpp_oi_obs* out, std::vector<int>* order,
+                         const std::vector<float>* scales) {
     const int nS = op->n;
     out->n_total = nS;
     out->loc_dist = loc_dist;
@@ -869,6 +896,16 @@ int gpp::build_obs_table(const gpp_points* op, const std::vector<char>& valid, c
         si[slot] = innov[i];
     }
     if(order) order->assign(orig.begin(), orig.begin() + nv);
+    if(scales) {   // h, v, w of every observation, in table order
+        std::vector<float> t(std::max(nv, 1));
+        gpp::DeviceBuffer<float>* dst[3] = {&out->sh, &out->sv, &out->sw};
+        for(int c = 0; c < 3; c++) {
+            for(int slot = 0; slot < nv; slot++) t[slot] = scales[c][orig[slot]];
+            GPP_TRY(dst[c]->upload(t.data(), nv));
+            GPP_CUDA(cudaStreamSynchronize(0));
+        }
+        out->has_scales = true;
+    }
     GPP_TRY(out->cell_start.upload(start.data(), start.size()));
     GPP_TRY(out->orig.upload(orig.data(), nv));
     GPP_TRY(out->x.upload(sx.data(), nv));
@@ -978,6 +1015,29 @@ int analyse_pipelined(const gpp_points* bpoints, int nB, int nx, int n_chunks, c
 }
 }  // namespace
 
+namespace {
+// The general kernel on the background range in P, with per-warp scratch for up to kcap observations per point.
+int launch_general(const OiParams& P, int kcap, int count, cudaStream_t stream) {
+    const int sms = sm_count();
+    const size_t per_warp = scratch_bytes(kcap);
+    long long warps = (long long) sms * 2 * WARPS_PER_CTA;
+    const size_t budget = (size_t) 4 << 30;
+    if((size_t) warps * per_warp > budget) warps = std::max<long long>(WARPS_PER_CTA, (long long) (budget / per_warp) / WARPS_PER_CTA * WARPS_PER_CTA);
+    if((size_t) warps * per_warp > ((size_t) 64 << 30))
+        return fail(GPP_ERR_RUNTIME, "optimal_interpolation: %d observations per point need %zu bytes of scratch per warp", kcap, per_warp);
+    unsigned grid = (unsigned) std::min<long long>(warps / WARPS_PER_CTA, ((long long) count + WARPS_PER_CTA - 1) / WARPS_PER_CTA);
+    grid = std::max(grid, 1u);
+    unsigned char* scratch = nullptr;
+    GPP_CUDA(cudaMallocAsync((void**) &scratch, (size_t) grid * WARPS_PER_CTA * per_warp, stream));
+    oi_general_kernel<<<grid, WARPS_PER_CTA * 32, 0, stream>>>(P, scratch, per_warp, kcap);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t err = cudaGetLastError();
+    cudaFreeAsync(scratch, stream);
+    if(err != cudaSuccess) return fail(GPP_ERR_CUDA, "CUDA error %s launching oi_general_kernel: %s", cudaGetErrorName(err), cudaGetErrorString(err));
+    return GPP_OK;
+}
+}  // namespace
+
 extern "C" {
 
 int gpp_oi_obs_create(const gpp_points* opoints, const float* pobs, const float* obs_variance, const float* pbackground,
@@ -1040,6 +1100,9 @@ int gpp_optimal_interpolation_device(const gpp_points* cbp, int first, int count
     P.tile_nx = 0;
     P.lru = nullptr;
     P.work_counter = nullptr;
+    P.sbh = P.sbv = P.sbw = nullptr;
+    P.loc_c = 0.f;
+    P.loc_d = 0.0;
 
     int kcap = max_points > 0 ? std::min(max_points, obs->n_valid) : obs->n_valid;
     if(max_points == 0 && kcap > FAST_K) {
@@ -1076,22 +1139,143 @@ int gpp_optimal_interpolation_device(const gpp_points* cbp, int first, int count
         if(err != cudaSuccess) return fail(GPP_ERR_CUDA, "CUDA error %s launching oi_fast_kernel: %s", cudaGetErrorName(err), cudaGetErrorString(err));
         return GPP_OK;
     }
-    // general path
-    const size_t per_warp = scratch_bytes(kcap);
-    long long warps = (long long) sms * 2 * WARPS_PER_CTA;
-    const size_t budget = (size_t) 4 << 30;
-    if((size_t) warps * per_warp > budget) warps = std::max<long long>(WARPS_PER_CTA, (long long) (budget / per_warp) / WARPS_PER_CTA * WARPS_PER_CTA);
-    if((size_t) warps * per_warp > ((size_t) 64 << 30))
-        return fail(GPP_ERR_RUNTIME, "optimal_interpolation: %d observations per point need %zu bytes of scratch per warp", kcap, per_warp);
-    unsigned grid = (unsigned) std::min<long long>(warps / WARPS_PER_CTA, ((long long) count + WARPS_PER_CTA - 1) / WARPS_PER_CTA);
-    grid = std::max(grid, 1u);
-    unsigned char* scratch = nullptr;
-    GPP_CUDA(cudaMallocAsync((void**) &scratch, (size_t) grid * WARPS_PER_CTA * per_warp, stream));
-    oi_general_kernel<<<grid, WARPS_PER_CTA * 32, 0, stream>>>(P, scratch, per_warp, kcap);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    cudaError_t err = cudaGetLastError();
-    cudaFreeAsync(scratch, stream);
-    if(err != cudaSuccess) return fail(GPP_ERR_CUDA, "CUDA error %s launching oi_general_kernel: %s", cudaGetErrorName(err), cudaGetErrorString(err));
+    return launch_general(P, kcap, count, stream);
+}
+
+// ---- spatially varying structure functions (structure.cpp:168-184 and the sibling constructors) ------------
+int gpp_structure_field_create(const gpp_points* grid, const float* h, const float* v, const float* w, gpp_structure_field** out) {
+    if(!out) return fail(GPP_ERR_INVALID_ARGUMENT, "out must not be NULL");
+    *out = nullptr;
+    if(!grid || !h || !v || !w) return fail(GPP_ERR_INVALID_ARGUMENT, "NULL argument");
+    if(grid->n <= 0) return fail(GPP_ERR_INVALID_ARGUMENT, "Grid size not the same as scale size");
+    gpp_structure_field* f = new(std::nothrow) gpp_structure_field();
+    if(!f) return fail(GPP_ERR_RUNTIME, "out of memory");
+    f->grid = grid;
+    f->h.assign(h, h + grid->n);
+    f->v.assign(v, v + grid->n);
+    f->w.assign(w, w + grid->n);
+    *out = f;
+    return GPP_OK;
+}
+void gpp_structure_field_destroy(gpp_structure_field* f) { delete f; }
+
+int gpp_structure_field_lookup_host(const gpp_structure_field* f, const float* lats, const float* lons, int n, float* h, float* v, float* w) {
+    if(!f) return fail(GPP_ERR_INVALID_ARGUMENT, "NULL field");
+    if(n <= 0) return GPP_OK;
+    std::vector<int> index(n);
+    GPP_TRY(gpp_points_nearest_host(f->grid, lats, lons, n, 1, index.data()));    // m_grid.get_nearest_neighbour, structure.cpp:189
+    for(int i = 0; i < n; i++) {
+        const int k = index[i];
+        if(k < 0 || k >= f->grid->n) return fail(GPP_ERR_RUNTIME, "Invalid I[0]");
+        h[i] = f->h[k]; v[i] = f->v[k]; w[i] = f->w[k];
+    }
+    return GPP_OK;
+}
+
+int gpp_structure_field_localization_distance(const gpp_structure_field* f, int type, float min_rho, float lat, float lon, float* out) {
+    float h, v, w, lc;
+    double ld;
+    GPP_TRY(spatial_loc_constants(type, min_rho, &lc, &ld));
+    GPP_TRY(gpp_structure_field_lookup_host(f, &lat, &lon, 1, &h, &v, &w));
+    *out = spatial_loc_dist_host(type, h, lc, ld);
+    return GPP_OK;
+}
+
+// gridpp::optimal_interpolation / _full (oi.cpp:26-412) with a structure function whose scales vary in space: every
+// point evaluates corr() with the scales of the field node nearest to it (its own position for corr_background, the
+// first observation's for the observation-observation matrix, which is therefore not symmetric). General kernel.
+int gpp_optimal_interpolation_spatial_host(const gpp_points* bpoints, const float* background, const float* bvariance,
+                                           const gpp_points* opoints, const float* pobs, const float* obs_variance,
+                                           const float* pbackground, const float* bvariance_at_points, int structure_type,
+                                           const gpp_structure_field* field, float min_rho, int max_points,
+                                           int allow_extrapolation, float* analysis, float* analysis_variance) {
+    if(max_points < 0) return fail(GPP_ERR_INVALID_ARGUMENT, "max_points must be >= 0");
+    if(!bpoints || !opoints || !field) return fail(GPP_ERR_INVALID_ARGUMENT, "NULL argument");
+    if(bpoints->type != opoints->type)
+        return fail(GPP_ERR_INVALID_ARGUMENT, "Both background points and observations points must be of same coordinate type (lat/lon or x/y)");
+    float loc_c;
+    double loc_d;
+    GPP_TRY(spatial_loc_constants(structure_type, min_rho, &loc_c, &loc_d));
+    GPP_TRY(ensure_device());
+    const int nB = bpoints->n, nS = opoints->n;
+    if(nS == 0 || nB == 0) {
+        if(nB > 0) std::memcpy(analysis, background, sizeof(float) * nB);
+        if(analysis_variance)
+            for(int i = 0; i < nB; i++) analysis_variance[i] = bvariance ? bvariance[i] : 1.f;
+        return GPP_OK;
+    }
+    // the descriptor the kernel specialises per point
+    gpp_structure s;
+    std::memset(&s, 0, sizeof(s));
+    s.n_terms = 1;
+    s.has_cv = 0;
+    s.cv_dist = NAN;
+    s.term[0].type = structure_type;
+    s.term[0].min_rho = min_rho;
+    // scales at the observations and at the background points
+    std::vector<float> oscale[3], bscale[3];
+    for(int c = 0; c < 3; c++) { oscale[c].resize(nS); bscale[c].resize(nB); }
+    GPP_TRY(gpp_structure_field_lookup_host(field, opoints->lats.data(), opoints->lons.data(), nS, oscale[0].data(), oscale[1].data(), oscale[2].data()));
+    GPP_TRY(gpp_structure_field_lookup_host(field, bpoints->lats.data(), bpoints->lons.data(), nB, bscale[0].data(), bscale[1].data(), bscale[2].data()));
+    float max_R = 0.f;
+    for(int i = 0; i < nB; i++) {
+        const float R = spatial_loc_dist_host(structure_type, bscale[0][i], loc_c, loc_d);
+        if(is_valid(R)) max_R = std::max(max_R, R);
+    }
+    s.term[0].loc_dist = max_R;
+    std::vector<char> valid(nS);
+    std::vector<double> innov(nS);
+    std::vector<float> ratio(nS);
+    for(int i = 0; i < nS; i++) {
+        valid[i] = is_valid(pobs[i]) && is_valid(pbackground[i]);
+        innov[i] = (double) pobs[i] - (double) pbackground[i];
+        ratio[i] = obs_variance[i] / (bvariance_at_points ? bvariance_at_points[i] : 1.f);
+    }
+    gpp_oi_obs obs;
+    GPP_TRY(build_obs_table(opoints, valid, innov, ratio, max_R, &obs, nullptr, oscale));
+    gpp_points* bp = const_cast<gpp_points*>(bpoints);
+    GPP_TRY(bp->ensure_on_device());
+    DeviceBuffer<float> d_bg, d_bvar, d_out, d_var, d_sc[3];
+    GPP_TRY(d_bg.upload(background, nB));
+    if(bvariance) GPP_TRY(d_bvar.upload(bvariance, nB));
+    GPP_TRY(d_out.alloc(nB));
+    if(analysis_variance) GPP_TRY(d_var.alloc(nB));
+    for(int c = 0; c < 3; c++) GPP_TRY(d_sc[c].upload(bscale[c].data(), nB));
+    if(obs.n_valid == 0) {
+        GPP_LAUNCH(copy_background_kernel, (unsigned) ((nB + 255) / 256), 256, 0, 0, d_bg.ptr, bvariance ? d_bvar.ptr : nullptr, 0, nB, d_out.ptr,
+                   analysis_variance ? d_var.ptr : nullptr);
+    }
+    else {
+        OiParams P;
+        P.gx = bp->dx.ptr; P.gy = bp->dy.ptr; P.gz = bp->dz.ptr; P.gelev = bp->delev.ptr; P.glaf = bp->dlaf.ptr;
+        P.background = d_bg.ptr;
+        P.bvariance = bvariance ? d_bvar.ptr : nullptr;
+        P.analysis = d_out.ptr;
+        P.analysis_variance = analysis_variance ? d_var.ptr : nullptr;
+        P.first = 0;
+        P.count = nB;
+        P.obs = obs.view();
+        P.s = s;
+        P.R = max_R;
+        P.allow_extrapolation = allow_extrapolation;
+        P.tile_nx = 0;
+        P.lru = nullptr;
+        P.work_counter = nullptr;
+        P.sbh = d_sc[0].ptr; P.sbv = d_sc[1].ptr; P.sbw = d_sc[2].ptr;
+        P.loc_c = loc_c;
+        P.loc_d = loc_d;
+        int kcap = max_points > 0 ? std::min(max_points, obs.n_valid) : obs.n_valid;
+        if(max_points == 0) {   // unlimited: bound k by the largest neighbourhood of the largest radius
+            int hmax = 0;
+            GPP_TRY(count_max_candidates(bp, 0, nB, d_bg.ptr, P.obs, max_R, 0, &hmax));
+            kcap = std::min(kcap, std::max(hmax, 1));
+        }
+        P.k = kcap;
+        GPP_TRY(launch_general(P, kcap, nB, 0));
+    }
+    GPP_TRY(d_out.download(analysis, nB));
+    if(analysis_variance) GPP_TRY(d_var.download(analysis_variance, nB));
+    GPP_CUDA(cudaStreamSynchronize(0));
     return GPP_OK;
 }
 

@@ -15,6 +15,7 @@ struct ObsView {
     const double* innov;     // (double) pobs - (double) pbackground            (oi.cpp:301-302,316)
     const float* ratio;      // obs_variance / bvariance_at_points, float       (oi.cpp:192-195)
     const int* orig;         // original observation index (selection tie-break, EnSI member lookup)
+    const float *sh, *sv, *sw;   // spatially varying structure function: the scales at each observation (else NULL)
     int n;                   // number of valid observations
 };
 
@@ -133,6 +134,8 @@ struct gpp_oi_obs {
     int ncells = 0;
     gpp::DeviceBuffer<int> cell_start, orig;
     gpp::DeviceBuffer<float> x, y, z, elev, laf, ratio;
+    gpp::DeviceBuffer<float> sh, sv, sw;   // only for spatially varying structure functions
+    bool has_scales = false;
     gpp::DeviceBuffer<double> innov;
     gpp::ObsView view() const {
         gpp::ObsView v;
@@ -142,6 +145,7 @@ struct gpp_oi_obs {
         v.innov = innov.ptr;
         v.ratio = ratio.ptr;
         v.orig = orig.ptr;
+        v.sh = has_scales ? sh.ptr : nullptr; v.sv = has_scales ? sv.ptr : nullptr; v.sw = has_scales ? sw.ptr : nullptr;
         v.n = n_valid;
         return v;
     }
@@ -155,5 +159,6 @@ int count_max_candidates(gpp_points* bp, int first, int count, const float* d_ba
                          cudaStream_t stream, int* out);
 // `order`, when given, receives the original index of every table slot (what `orig` holds on the device).
 int build_obs_table(const gpp_points* opoints, const std::vector<char>& valid, const std::vector<double>& innov,
-                    const std::vector<float>& ratio, float loc_dist, gpp_oi_obs* out, std::vector<int>* order = nullptr);
+                    const std::vector<float>& ratio, float loc_dist, gpp_oi_obs* out, std::vector<int>* order = nullptr,
+                    const std::vector<float>* scales = nullptr /* h, v, w per observation, original order */);
 }

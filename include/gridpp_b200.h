@@ -179,6 +179,26 @@ int gpp_optimal_interpolation_ensi_host(const gpp_points* bpoints, const float* 
                                         const float* pbackground, const gpp_structure* structure, int max_points,
                                         int allow_extrapolation, float* analysis, int* num_skipped);
 
+/* Spatially varying structure functions: gridpp::BarnesStructure(Grid, vec2 h, vec2 v, vec2 w, min_rho)
+ * structure.cpp:168-184 and the Soar (:342), Toar (:492), Powerlaw (:643), Linear (:790) siblings. h, v, w hold one
+ * value per node of `grid` (row-major); a point uses the scales of its nearest node (structure.cpp:189-199). The grid
+ * must outlive the field. */
+typedef struct gpp_structure_field gpp_structure_field;
+int gpp_structure_field_create(const gpp_points* grid, const float* h, const float* v, const float* w, gpp_structure_field** out);
+void gpp_structure_field_destroy(gpp_structure_field* field);
+int gpp_structure_field_lookup_host(const gpp_structure_field* field, const float* lats, const float* lons, int n,
+                                    float* h, float* v, float* w);
+/* <Family>Structure::localization_distance(Point) for the spatial form (structure.cpp:271-282) */
+int gpp_structure_field_localization_distance(const gpp_structure_field* field, int type, float min_rho, float lat, float lon,
+                                              float* out);
+/* gridpp::optimal_interpolation / optimal_interpolation_full (oi.cpp:26-412) with such a structure function
+ * (type: GPP_STRUCT_BARNES, _SOAR, _TOAR, _POWERLAW or _LINEAR). Other arguments as gpp_optimal_interpolation_host. */
+int gpp_optimal_interpolation_spatial_host(const gpp_points* bpoints, const float* background, const float* bvariance,
+                                           const gpp_points* opoints, const float* pobs, const float* obs_variance,
+                                           const float* pbackground, const float* bvariance_at_points, int structure_type,
+                                           const gpp_structure_field* field, float min_rho, int max_points,
+                                           int allow_extrapolation, float* analysis, float* analysis_variance);
+
 /* ---------------------------------------------------------------- neighbourhood filters -------------- */
 /* gridpp::neighbourhood(vec2, halfwidth, statistic) neighbourhood.cpp:28-242 for statistic in
  * {Mean, Sum, Count, Min, Max}: NaN-aware statistic over the (2*halfwidth+1)^2 window CLIPPED to the domain

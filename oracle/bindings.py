@@ -204,6 +204,22 @@ class CpuLib:
             timing.append(sec.value)
         return out
 
+    def optimal_interpolation_spatial(self, bpts, background, opts, pobs, pratios, pbackground, stype, sgrid, h, v, w, min_rho,
+                                      max_points, ctype, allow_extrapolation=True, want_variance=False):
+        """optimal_interpolation_full with <Family>Structure(Grid, h, v, w, min_rho) (compiled reference only)."""
+        bl, bo, be, bf = (_f(a).ravel() if a is not None else None for a in bpts)
+        pl, po, pe, pf = (_f(a).ravel() if a is not None else None for a in opts)
+        nB, nS = bl.size, pl.size
+        glats, glons = _f(sgrid[0]), _f(sgrid[1])
+        gny, gnx = glats.shape
+        out = np.empty(nB, np.float32)
+        var = np.empty(nB, np.float32)
+        self._check(self._fn("optimal_interpolation_spatial")(
+            _p(bl), _p(bo), _p(be), _p(bf), nB, _p(_f(background).ravel()), _p(pl), _p(po), _p(pe), _p(pf), nS, ctype, _p(_f(pobs).ravel()),
+            _p(_f(pratios).ravel()), _p(_f(pbackground).ravel()), int(stype), _p(glats), _p(glons), gny, gnx, _p(_f(h, (gny, gnx))),
+            _p(_f(v, (gny, gnx))), _p(_f(w, (gny, gnx))), C.c_float(min_rho), max_points, int(allow_extrapolation), _p(out), _p(var)))
+        return (out, var) if want_variance else out
+
     # ---- neighbourhood
     def neighbourhood(self, field, halfwidth, statistic, timing=None):
         f = _f(field)

@@ -232,6 +232,39 @@ int ref_optimal_interpolation(const float* blats, const float* blons, const floa
     REF_CATCH
 }
 
+// gridpp::optimal_interpolation_full(Points...) with a SPATIALLY VARYING structure function: <Family>Structure(Grid, vec2 h,
+// vec2 v, vec2 w, min_rho), structure.cpp:168-184 (Barnes), :342 (Soar), :492 (Toar), :643 (Powerlaw), :790 (Linear).
+// The scale grid is gny x gnx (glats/glons/h/v/w row-major).
+int ref_optimal_interpolation_spatial(const float* blats, const float* blons, const float* belevs, const float* blafs, int nB,
+                                      const float* background, const float* plats, const float* plons, const float* pelevs,
+                                      const float* plafs, int nS, int type, const float* pobs, const float* obs_variance,
+                                      const float* pbackground, int stype, const float* glats, const float* glons, int gny, int gnx,
+                                      const float* h, const float* v, const float* w, float min_rho, int max_points,
+                                      int allow_extrapolation, float* analysis, float* analysis_variance) {
+    REF_TRY
+    gridpp::Points bp = make_points(blats, blons, belevs, blafs, nB, type);
+    gridpp::Points op = make_points(plats, plons, pelevs, plafs, nS, type);
+    gridpp::Grid sg(to_vec2(glats, gny, gnx), to_vec2(glons, gny, gnx), gridpp::vec2(), gridpp::vec2(), (gridpp::CoordinateType) type);
+    gridpp::vec2 h2 = to_vec2(h, gny, gnx), v2 = to_vec2(v, gny, gnx), w2 = to_vec2(w, gny, gnx);
+    gridpp::StructureFunctionPtr s;
+    switch(stype) {
+        case GPP_STRUCT_BARNES: s = std::make_shared<gridpp::BarnesStructure>(sg, h2, v2, w2, min_rho); break;
+        case GPP_STRUCT_SOAR: s = std::make_shared<gridpp::SoarStructure>(sg, h2, v2, w2, min_rho); break;
+        case GPP_STRUCT_TOAR: s = std::make_shared<gridpp::ToarStructure>(sg, h2, v2, w2, min_rho); break;
+        case GPP_STRUCT_POWERLAW: s = std::make_shared<gridpp::PowerlawStructure>(sg, h2, v2, w2, min_rho); break;
+        case GPP_STRUCT_LINEAR: s = std::make_shared<gridpp::LinearStructure>(sg, h2, v2, w2, min_rho); break;
+        default: throw std::invalid_argument("unknown structure type");
+    }
+    gridpp::vec bg = to_vec(background, nB), bvar(nB, 1.0f);
+    gridpp::vec obs = to_vec(pobs, nS), ovar = to_vec(obs_variance, nS), pbg = to_vec(pbackground, nS), pbvar(nS, 1.0f);
+    gridpp::vec avar;
+    gridpp::vec out = gridpp::optimal_interpolation_full(bp, bg, bvar, op, obs, ovar, pbg, pbvar, *s, max_points, avar, allow_extrapolation != 0);
+    std::memcpy(analysis, out.data(), sizeof(float) * out.size());
+    if(analysis_variance && avar.size() == (size_t) nB) std::memcpy(analysis_variance, avar.data(), sizeof(float) * nB);
+    else if(analysis_variance) std::memcpy(analysis_variance, bvar.data(), sizeof(float) * nB);
+    REF_CATCH
+}
+
 // gridpp::optimal_interpolation_ensi(Points...) oi_ensi.cpp:114-568. background is nB x nE, pbackground nS x nE.
 int ref_optimal_interpolation_ensi(const float* blats, const float* blons, const float* belevs, const float* blafs, int nB,
                                    const float* background, int nE, const float* plats, const float* plons,

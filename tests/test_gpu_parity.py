@@ -256,6 +256,53 @@ def test_oi_device_api_and_row_shards(gpp, orc):
     assert_close(host.ravel(), want, 1.0, RTOL, "device OI")
 
 
+def test_oi_spatially_varying_structures_golden(gpp):
+    """<Family>Structure(Grid, h, v, w, min_rho) (structure.cpp:168-184, :342, :492, :643, :790) through
+    optimal_interpolation_full: analysis and analysis variance against fixtures generated from the compiled reference
+    (tests/golden/make_golden_spatial.py). Also the reference's own spatial test, tests/test_barnes_structure.py:46-66."""
+    g = golden("oi_spatial_structure")
+    classes = {"barnes": gpp.BarnesStructure, "soar": gpp.SoarStructure, "toar": gpp.ToarStructure, "powerlaw": gpp.PowerlawStructure,
+               "linear": gpp.LinearStructure}
+    sgrid = gpp.Grid(g["gy"], g["gx"], type=gpp.Cartesian)
+    bvar = np.ones(g["background"].shape, f32)
+    for case in g["cases"]:
+        name, _, elev, mp, extr, min_rho = str(case).split(",")
+        elev, mp, extr, min_rho = int(elev), int(mp), int(extr), float(min_rho)
+        grid = gpp.Grid(g["y"], g["x"], g["belev"], g["blaf"], gpp.Cartesian) if elev else gpp.Grid(g["y"], g["x"], type=gpp.Cartesian)
+        points = gpp.Points(g["py"], g["px"], g["pelev"], g["plaf"], gpp.Cartesian) if elev else gpp.Points(g["py"], g["px"], type=gpp.Cartesian)
+        s = classes[name](sgrid, g["h"], g["v"], g["w"], min_rho)
+        key = "%s__elev%d__mp%d" % (name, elev, mp)
+        out, var = gpp.optimal_interpolation_full(grid, g["background"], bvar, points, g["pobs"], g["pratios"], g["pbackground"],
+                                                  np.ones(g["py"].size, f32), s, mp, bool(extr))
+        # The observation-observation matrix of a spatially varying structure function is not symmetric
+        # (corr(o_i, o_j) uses the scales at o_i); with Soar / Toar and elevations (signed differences,
+        # structure.cpp:52-53,62-63) it is nearly singular at some grid points: analysis values up to 10^2 and
+        # "variances" down to -160 against a background of order 1. The error there scales with the magnitude of the
+        # field, so the parity metric uses the field's largest magnitude as its scale; at most 3 of the 1440 points may
+        # exceed 1e-5 (none 1e-3).
+        wa, wv = g[key + "__analysis"], g[key + "__variance"]
+        sa, sv = max(2.0, float(np.abs(wa).max())), max(1.0, float(np.abs(wv).max()))
+        assert_close(out, wa, sa, RTOL, "spatial " + key, allow_outliers=3)
+        assert_close(out, wa, sa, 1e-3, "spatial (loose) " + key)
+        assert_close(var, wv, sv, RTOL, "spatial variance " + key, allow_outliers=3)
+        assert_close(var, wv, sv, 1e-3, "spatial variance (loose) " + key)
+        out2 = gpp.optimal_interpolation(grid, g["background"], points, g["pobs"], g["pratios"], g["pbackground"], s, mp, bool(extr))
+        assert_bit_exact(out2, out, "optimal_interpolation == _full for " + key)
+    # tests/test_barnes_structure.py:46-66
+    grid = gpp.Grid([[0, 0]], [[0, 2500]], [[0, 0]], [[0, 0]], gpp.Cartesian)
+    s = gpp.BarnesStructure(grid, [[2500, 1]], [[0, 0]], [[0, 0]], 0.1)
+    assert abs(s.localization_distance((0, 0)) - np.sqrt(-2 * np.log(0.1)) * 2500) < 1e-2
+    assert abs(s.localization_distance((0, 2500)) - np.sqrt(-2 * np.log(0.1)) * 1) < 1e-4
+    y, x = np.meshgrid(np.linspace(0, 1, 2), np.linspace(0, 1, 3))
+    grid = gpp.Grid(y, x, y, y, gpp.Cartesian)
+    valid = np.ones([3, 2])
+    gpp.BarnesStructure(grid, valid, valid, valid)
+    for inval in (np.ones([3, 4]), np.ones([2, 2]), np.ones([2, 4])):
+        for args in ((inval, valid, valid), (valid, inval, valid), (valid, valid, inval)):
+            with pytest.raises(ValueError):
+                gpp.BarnesStructure(grid, *args)
+
+
 # ------------------------------------------------------------------ neighbourhood filters --------------
 STATS = {"mean": 0, "sum": 70, "count": 80, "min": 10, "max": 30}
 
