@@ -321,7 +321,6 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 2) oi_fast_kernel(const __
     const int lane = (int) lane_id();
     const unsigned lt_mask = (1u << lane) - 1u;
     const int warp_global = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
-    const int warps_total = gridDim.x * WARPS_PER_CTA;
     const bool need_var = P.analysis_variance != nullptr;
 
     // pair index p -> (row j, column i <= j) of the lower triangle, packed over the lanes during assembly
@@ -569,6 +568,198 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 2) oi_fast_kernel(const __
             }
         }
     }
+    }
+}
+
+// ------------------------------------------------------------------ Cholesky path: 30 < k <= 64 --------
+// Symmetric structure functions with more than FAST_K and at most CHOL_K observations per point: one warp per grid
+// point, the selection from gather_candidates (oi.cpp:229-273), P + R assembled as a packed lower triangle in shared
+// memory (fp64, k (k + 1) / 2 entries, oi.cpp:298-314) and factorised in place, A = L L'. With y = L^-1 d and
+// u = L^-1 rho the increment is u . y and rho' A^-1 rho is u . u (oi.cpp:315-317,336): no inverse, no back-substitution.
+// (The general kernel keeps its k x (k + 2) matrix in global memory and eliminates with partial pivoting; it is the
+// fallback for non-symmetric structure functions and larger k, two orders of magnitude slower.)
+constexpr int CHOL_K = 128;            // largest k of the Cholesky path (instantiated for 64 and 128)
+constexpr int CHOL_WARPS = 2;
+template <int KMAX>
+struct CholSmem {
+    static constexpr int CHOL_PAIRS = KMAX * (KMAX + 1) / 2;
+    double A[CHOL_PAIRS];                  // packed lower triangle, row-major: (i, m <= i) at i (i + 1) / 2 + m
+    double d[KMAX], r[KMAX];               // innovations -> y -> z = A^-1 d (kept for reuse); rho -> u
+    unsigned long long key[KMAX + 32];
+    int pos[KMAX + 32];
+    int c_pos[KMAX], c_orig[KMAX];         // the selection in canonical order (ascending original index)
+    int prev_orig[KMAX];                   // the set whose z is in d
+    float sx[KMAX], sy[KMAX], sz[KMAX], selev[KMAX], slaf[KMAX], sratio[KMAX];
+};
+
+template <int SMODE, int KMAX>
+__global__ void __launch_bounds__(CHOL_WARPS * 32) oi_chol_kernel(const __grid_constant__ OiParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    typedef CholSmem<KMAX> Smem;
+    constexpr int CHOL_PAIRS = Smem::CHOL_PAIRS, NSLOT = KMAX / 32 + 1;
+    Smem& S = reinterpret_cast<Smem*>(smem_raw)[threadIdx.x >> 5];
+    unsigned short* lut = reinterpret_cast<unsigned short*>(smem_raw + sizeof(Smem) * CHOL_WARPS);   // pair -> (i << 8) | m
+    const int lane = (int) lane_id();
+    const bool need_var = P.analysis_variance != nullptr;
+    for(int p = threadIdx.x; p < CHOL_PAIRS; p += blockDim.x) {
+        int i = (int) ((sqrtf(8.f * (float) p + 1.f) - 1.f) * 0.5f);
+        while(i * (i + 1) / 2 > p) i--;
+        while((i + 1) * (i + 2) / 2 <= p) i++;
+        lut[p] = (unsigned short) ((i << 8) | (p - i * (i + 1) / 2));
+    }
+    __syncthreads();
+    const CandBuf cb = {S.key, S.pos};
+    // the system solved last: neighbouring points usually select the same observations, and with the set in canonical
+    // order z = (P + R)^-1 d depends on the set alone (see oi_fast_kernel); the increment is then rho . z
+    int prev_k = -1;
+    double prev_dmax = 0.0, prev_dmin = 0.0;
+    for(;;) {
+        int it0 = 0;
+        if(lane == 0) it0 = atomicAdd(P.work_counter, 32);
+        it0 = __shfl_sync(0xffffffffu, it0, 0);
+        if(it0 >= P.count) break;
+        for(int it = it0; it < min(it0 + 32, P.count); it++) {
+            const int g = P.first + it;
+            const float bg = P.background[g];
+            int k = 0;
+            if(is_valid(bg)) {   // oi.cpp:223
+                const Pt p1 = {P.gx[g], P.gy[g], P.gz[g], P.gelev[g], P.glaf[g]};
+                k = gather_candidates<SMODE, NSLOT>(P.obs, P.s, p1, P.R, P.k, cb);
+            }
+            if(k == 0) { keep_background(P, g, bg); continue; }
+            // ---- canonical order: ascending original index = descending low word of the key
+            {
+                unsigned long long kk[KMAX / 32];
+                int pp[KMAX / 32], rk[KMAX / 32];
+                #pragma unroll
+                for(int t = 0; t < KMAX / 32; t++) {
+                    const bool has = lane + 32 * t < k;
+                    kk[t] = has ? S.key[lane + 32 * t] : 0ull;
+                    pp[t] = has ? S.pos[lane + 32 * t] : 0;
+                    rk[t] = 0;
+                }
+                const unsigned* lo_words = reinterpret_cast<const unsigned*>(S.key);
+                for(int j = 0; j < k; j++) {
+                    const unsigned lw = lo_words[2 * j];
+                    #pragma unroll
+                    for(int t = 0; t < KMAX / 32; t++) rk[t] += lw > (unsigned) kk[t];
+                }
+                #pragma unroll
+                for(int t = 0; t < KMAX / 32; t++)
+                    if(lane + 32 * t < k) { S.c_pos[rk[t]] = pp[t]; S.c_orig[rk[t]] = cand_key_orig(kk[t]); S.r[rk[t]] = (double) cand_key_rho(kk[t]); }
+                __syncwarp();
+            }
+            bool same = k == prev_k && !need_var;
+            if(same) {
+                bool eq = true;
+                for(int i = lane; i < k; i += 32) eq = eq && S.c_orig[i] == S.prev_orig[i];
+                same = __all_sync(0xffffffffu, eq);
+            }
+            double avar = 0.0;
+            if(!same) {
+                // ---- stage the selection
+                double dmax = -INFINITY, dmin = INFINITY;
+                for(int i = lane; i < k; i += 32) {
+                    const int pos = S.c_pos[i];
+                    S.sx[i] = P.obs.x[pos]; S.sy[i] = P.obs.y[pos]; S.sz[i] = P.obs.z[pos];
+                    S.selev[i] = P.obs.elev[pos]; S.slaf[i] = P.obs.laf[pos]; S.sratio[i] = P.obs.ratio[pos];
+                    const double dd = P.obs.innov[pos];
+                    S.d[i] = dd;
+                    S.prev_orig[i] = S.c_orig[i];
+                    dmax = fmax(dmax, dd);
+                    dmin = fmin(dmin, dd);
+                }
+                #pragma unroll
+                for(int off = 16; off > 0; off >>= 1) {
+                    dmax = fmax(dmax, shfl_double(dmax, lane ^ off));
+                    dmin = fmin(dmin, shfl_double(dmin, lane ^ off));
+                }
+                prev_dmax = dmax; prev_dmin = dmin; prev_k = k;
+                __syncwarp();
+                // ---- P + R, lower triangle (oi.cpp:298-315)
+                const int npairs = k * (k + 1) / 2;
+                for(int p = lane; p < npairs; p += 32) {
+                    const int code = lut[p], i = code >> 8, m = code & 255;
+                    const Pt a = {S.sx[i], S.sy[i], S.sz[i], S.selev[i], S.slaf[i]};
+                    const Pt b = {S.sx[m], S.sy[m], S.sz[m], S.selev[m], S.slaf[m]};
+                    const float hdist = straight_distance(a.x, a.y, a.z, b.x, b.y, b.z);
+                    double v = (double) corr_call<SMODE>(P.s, a, b, hdist);
+                    if(i == m) v = __dadd_rn(v, (double) S.sratio[i]);
+                    S.A[p] = v;
+                }
+                __syncwarp();
+                // ---- left-looking Cholesky: column j of L from the columns before it; lanes own rows
+                bool ok = true;
+                for(int j = 0; j < k && ok; j++) {
+                    const double* rowj = S.A + j * (j + 1) / 2;
+                    double inv = 0.0;
+                    for(int i0 = j; i0 < k; i0 += 32) {
+                        const int i = i0 + lane;
+                        double acc = 0.0;
+                        double* rowi = S.A + (i < k ? i * (i + 1) / 2 : 0);
+                        if(i < k) {
+                            acc = rowi[j];
+                            for(int p = 0; p < j; p++) acc = fma(-rowi[p], rowj[p], acc);
+                        }
+                        if(i0 == j) {   // the diagonal entry sits in lane 0 of the first chunk: L_jj = a_jj / sqrt(a_jj)
+                            const double ajj = shfl_double(acc, 0);
+                            ok = ajj > 0.0 && ajj < INFINITY;
+                            inv = ok ? fast_rsqrt(ajj) : 0.0;
+                        }
+                        __syncwarp();
+                        if(i < k) rowi[j] = acc * inv;
+                    }
+                    __syncwarp();
+                }
+                if(!ok) { prev_k = -1; keep_background(P, g, bg); continue; }   // not positive definite (arma::inv would throw)
+                // ---- y = L^-1 d (and u = L^-1 rho when the variance is wanted): forward substitution
+                for(int j = 0; j < k; j++) {
+                    const double inv = fast_rcp(S.A[j * (j + 1) / 2 + j]);
+                    const double yj = S.d[j] * inv, uj = need_var ? S.r[j] * inv : 0.0;
+                    __syncwarp();
+                    if(lane == 0) { S.d[j] = yj; if(need_var) S.r[j] = uj; }
+                    for(int i = j + 1 + lane; i < k; i += 32) {
+                        const double lij = S.A[i * (i + 1) / 2 + j];
+                        S.d[i] = fma(-lij, yj, S.d[i]);
+                        if(need_var) S.r[i] = fma(-lij, uj, S.r[i]);
+                    }
+                    __syncwarp();
+                }
+                if(need_var) {
+                    // rho' A^-1 rho = u . u and the increment u . y (every point is solved when the variance is wanted)
+                    double dx = 0.0, aa = 0.0;
+                    for(int i = lane; i < k; i += 32) {
+                        dx = fma(S.r[i], S.d[i], dx);
+                        aa = fma(S.r[i], S.r[i], aa);
+                    }
+                    #pragma unroll
+                    for(int off = 16; off > 0; off >>= 1) {
+                        dx += shfl_double(dx, lane ^ off);
+                        aa += shfl_double(aa, lane ^ off);
+                    }
+                    prev_k = -1;   // d holds y, not z
+                    if(lane == 0) write_result(P, g, bg, dx, aa, dmax, dmin);
+                    __syncwarp();
+                    continue;
+                }
+                // ---- z = L'^-1 y: back substitution, in place
+                for(int j = k - 1; j >= 0; j--) {
+                    const double* rowj = S.A + j * (j + 1) / 2;
+                    const double zj = S.d[j] * fast_rcp(rowj[j]);
+                    __syncwarp();
+                    if(lane == 0) S.d[j] = zj;
+                    for(int i = lane; i < j; i += 32) S.d[i] = fma(-rowj[i], zj, S.d[i]);
+                    __syncwarp();
+                }
+            }
+            // ---- increment = rho . z, the same dot product whether the system was solved here or reused
+            double dx = 0.0;
+            for(int i = lane; i < k; i += 32) dx = fma(S.r[i], S.d[i], dx);
+            #pragma unroll
+            for(int off = 16; off > 0; off >>= 1) dx += shfl_double(dx, lane ^ off);
+            if(lane == 0) write_result(P, g, bg, dx, avar, prev_dmax, prev_dmin);
+            __syncwarp();
+        }
     }
 }
 
@@ -1137,6 +1328,30 @@ int gpp_optimal_interpolation_device(const gpp_points* cbp, int first, int count
         cudaError_t err = cudaGetLastError();
         cudaFreeAsync(lru, stream);
         if(err != cudaSuccess) return fail(GPP_ERR_CUDA, "CUDA error %s launching oi_fast_kernel: %s", cudaGetErrorName(err), cudaGetErrorString(err));
+        return GPP_OK;
+    }
+    if(kcap <= CHOL_K && structure_is_symmetric(*structure)) {
+        // 30 < k <= 128: packed Cholesky in shared memory, dynamic blocks of 32 points
+        const int mode = structure_mode(*structure);
+        const bool small = kcap <= 64;
+        void (*kernel)(OiParams) = small ? (mode == 1 ? oi_chol_kernel<1, 64> : oi_chol_kernel<0, 64>)
+                                         : (mode == 1 ? oi_chol_kernel<1, 128> : oi_chol_kernel<0, 128>);
+        const size_t smem = small ? sizeof(CholSmem<64>) * CHOL_WARPS + sizeof(unsigned short) * CholSmem<64>::CHOL_PAIRS
+                                  : sizeof(CholSmem<128>) * CHOL_WARPS + sizeof(unsigned short) * CholSmem<128>::CHOL_PAIRS;
+        int per_sm = 1;
+        GPP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        GPP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, CHOL_WARPS * 32, smem));
+        const long long want = ((long long) count + 32 * CHOL_WARPS - 1) / (32 * CHOL_WARPS);
+        const unsigned grid = (unsigned) std::max<long long>(1, std::min<long long>(want, (long long) sms * std::max(per_sm, 1)));
+        int* counter = nullptr;
+        GPP_CUDA(cudaMallocAsync((void**) &counter, 256, stream));
+        GPP_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), stream));
+        P.work_counter = counter;
+        kernel<<<grid, CHOL_WARPS * 32, smem, stream>>>(P);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        cudaError_t err = cudaGetLastError();
+        cudaFreeAsync(counter, stream);
+        if(err != cudaSuccess) return fail(GPP_ERR_CUDA, "CUDA error %s launching oi_chol_kernel: %s", cudaGetErrorName(err), cudaGetErrorString(err));
         return GPP_OK;
     }
     return launch_general(P, kcap, count, stream);

@@ -217,6 +217,15 @@ def test_oi_random_vs_oracle(gpp, orc):
         want = orc.optimal_interpolation((y[sub], x[sub], None, None), bg[sub], (py, px, None, None), obs, ratios, pbg,
                                          B.make_structure(B.BARNES, 10000.0), mp, B.CARTESIAN)
         assert_close(got.ravel(), want, 3.0, RTOL, "OI general mp=%d" % mp)
+    # 30 < max_points <= 64 with a symmetric structure function: the shared-memory Cholesky kernel (analysis, variance, clamp)
+    for mp, extr, s_gpu, s_orc in ((31, True, gpp.BarnesStructure(10000), B.make_structure(B.BARNES, 10000.0)),
+                                   (50, False, gpp.BarnesStructure(10000), B.make_structure(B.BARNES, 10000.0)),
+                                   (64, True, gpp.PowerlawStructure(8000), B.make_structure(B.POWERLAW, 8000.0))):
+        got, gvar = gpp.optimal_interpolation_full(gsub, bg[sub], np.ones(bg[sub].shape), points, obs, ratios, pbg, np.ones(S), s_gpu, mp, extr)
+        want, wvar = orc.optimal_interpolation((y[sub], x[sub], None, None), bg[sub], (py, px, None, None), obs, ratios, pbg, s_orc, mp,
+                                               B.CARTESIAN, allow_extrapolation=extr, want_variance=True)
+        assert_close(got.ravel(), want, 3.0, RTOL, "OI Cholesky path mp=%d" % mp)
+        assert_close(gvar.ravel(), wvar, 1.0, RTOL, "OI Cholesky path variance mp=%d" % mp)
     belev, pelev = rng.uniform(0, 300, y[sub].shape).astype(f32), rng.uniform(0, 300, S).astype(f32)
     got = gpp.optimal_interpolation(gpp.Grid(y[sub], x[sub], belev, type=gpp.Cartesian), bg[sub], gpp.Points(py, px, pelev, type=gpp.Cartesian),
                                     obs, ratios, pbg, gpp.CressmanStructure(30000, 200), 12)
