@@ -811,12 +811,17 @@ __device__ int general_prune(const GeneralScratch& s, int src, int n, int k) {
     return min(n, k);
 }
 
+// smem_matrix_bytes > 0: the k x (k + 2) matrix of each warp lives in dynamic shared memory (k <= 64) instead of its
+// global scratch slab; the elimination is a chain of dependent row operations, so the memory latency is what it costs.
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32) oi_general_kernel(const __grid_constant__ OiParams P, unsigned char* scratch,
-                                                                       size_t bytes_per_warp, int kcap) {
+                                                                       size_t bytes_per_warp, int kcap, int smem_matrix_bytes) {
+    extern __shared__ __align__(16) unsigned char general_smem[];
     const unsigned lane = lane_id();
-    const int warp_global = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
-    const int warps_total = gridDim.x * WARPS_PER_CTA;
-    const GeneralScratch S = scratch_for(scratch, bytes_per_warp, warp_global, kcap);
+    const int warps_per_cta = blockDim.x >> 5;
+    const int warp_global = blockIdx.x * warps_per_cta + (threadIdx.x >> 5);
+    const int warps_total = gridDim.x * warps_per_cta;
+    GeneralScratch S = scratch_for(scratch, bytes_per_warp, warp_global, kcap);
+    if(smem_matrix_bytes > 0) S.M = reinterpret_cast<double*>(general_smem + (size_t) (threadIdx.x >> 5) * smem_matrix_bytes);
     const ObsView& obs = P.obs;
 
     for(int it = warp_global; it < P.count; it += warps_total) {
@@ -1211,16 +1216,27 @@ namespace {
 int launch_general(const OiParams& P, int kcap, int count, cudaStream_t stream) {
     const int sms = sm_count();
     const size_t per_warp = scratch_bytes(kcap);
-    long long warps = (long long) sms * 2 * WARPS_PER_CTA;
+    // k <= 64: the matrix goes to shared memory, 2 warps per CTA (34 KB each at k = 64)
+    const bool in_smem = kcap <= 64;
+    const int warps_per_cta = in_smem ? 2 : WARPS_PER_CTA;
+    const int matrix_bytes = in_smem ? (int) ((sizeof(double) * (size_t) kcap * (kcap + 2) + 15) / 16 * 16) : 0;
+    const size_t smem = (size_t) matrix_bytes * warps_per_cta;
+    int per_sm = 2;
+    if(in_smem) {
+        GPP_CUDA(cudaFuncSetAttribute(oi_general_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        GPP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, oi_general_kernel, warps_per_cta * 32, smem));
+        per_sm = std::max(per_sm, 1);
+    }
+    long long warps = (long long) sms * per_sm * warps_per_cta;
     const size_t budget = (size_t) 4 << 30;
-    if((size_t) warps * per_warp > budget) warps = std::max<long long>(WARPS_PER_CTA, (long long) (budget / per_warp) / WARPS_PER_CTA * WARPS_PER_CTA);
+    if((size_t) warps * per_warp > budget) warps = std::max<long long>(warps_per_cta, (long long) (budget / per_warp) / warps_per_cta * warps_per_cta);
     if((size_t) warps * per_warp > ((size_t) 64 << 30))
         return fail(GPP_ERR_RUNTIME, "optimal_interpolation: %d observations per point need %zu bytes of scratch per warp", kcap, per_warp);
-    unsigned grid = (unsigned) std::min<long long>(warps / WARPS_PER_CTA, ((long long) count + WARPS_PER_CTA - 1) / WARPS_PER_CTA);
+    unsigned grid = (unsigned) std::min<long long>(warps / warps_per_cta, ((long long) count + warps_per_cta - 1) / warps_per_cta);
     grid = std::max(grid, 1u);
     unsigned char* scratch = nullptr;
-    GPP_CUDA(cudaMallocAsync((void**) &scratch, (size_t) grid * WARPS_PER_CTA * per_warp, stream));
-    oi_general_kernel<<<grid, WARPS_PER_CTA * 32, 0, stream>>>(P, scratch, per_warp, kcap);
+    GPP_CUDA(cudaMallocAsync((void**) &scratch, (size_t) grid * warps_per_cta * per_warp, stream));
+    oi_general_kernel<<<grid, warps_per_cta * 32, smem, stream>>>(P, scratch, per_warp, kcap, matrix_bytes);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     cudaError_t err = cudaGetLastError();
     cudaFreeAsync(scratch, stream);

@@ -23,7 +23,13 @@ ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=
 for name, s, mp in (("Barnes mp=30 (register kernel)", gpp.BarnesStructure(bench.H_SCALE), 30),
                     ("Barnes mp=50 (Cholesky kernel, k <= 64)", gpp.BarnesStructure(bench.H_SCALE), 50),
                     ("Barnes unlimited (Cholesky kernel, k <= 128)", gpp.BarnesStructure(bench.H_SCALE), 0),
-                    ("Cressman mp=30 (register kernel: no elevations)", gpp.CressmanStructure(36000.0), 30)):
+                    ("Cressman mp=30 (register kernel: no elevations)", gpp.CressmanStructure(36000.0), 30),
+                    ("Soar h=10 km, v=200 m with elevations, mp=30 (general kernel: P not symmetric)", "soar", 30)):
+    if s == "soar":
+        rng = np.random.default_rng(3)
+        grid = gpp.Grid(w["y"], w["x"], rng.uniform(0, 300, w["y"].shape).astype(np.float32), type=gpp.Cartesian)
+        points = gpp.Points(w["py"], w["px"], rng.uniform(0, 300, w["py"].size).astype(np.float32), type=gpp.Cartesian)
+        s = gpp.SoarStructure(bench.H_SCALE, 200.0)
     state = gd.ObservationState(points, w["pobs"], w["pratios"], w["pbackground"], s)
     gd.optimal_interpolation(grid, bg, state, mp, out=out)
     torch.cuda.synchronize()
