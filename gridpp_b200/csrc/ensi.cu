@@ -374,6 +374,7 @@ extern "C" int gpp_optimal_interpolation_ensi_host(const gpp_points* cbp, const 
     trace.lap("H2D + valid-member scan");
     EnsiParams P;
     std::memset(&P, 0, sizeof(P));
+    bool downloaded = false;
     int E = 0;
     for(int e = 0; e < nE; e++)
         if(!flags[e]) {
@@ -431,11 +432,29 @@ extern "C" int gpp_optimal_interpolation_ensi_host(const gpp_points* cbp, const 
             else GPP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ensi_kernel<0>, ENSI_WARPS * 32, smem));
             const unsigned grid = (unsigned) std::max<long long>(1, std::min<long long>(want, (long long) sm_count() * std::max(per_sm, 1)));
             P.work_counter = d_flags.ptr + nE + 1;
-            if(structure_mode(*structure) == 1) GPP_LAUNCH(ensi_kernel<1>, grid, ENSI_WARPS * 32, smem, 0, P);
-            else GPP_LAUNCH(ensi_kernel<0>, grid, ENSI_WARPS * 32, smem, 0, P);
+            // blocks of points, each returned to the host (through pinned staging) while the next one is analysed
+            const int n_chunks = nB >= (1 << 18) ? 8 : 1;
+            std::vector<size_t> bounds(n_chunks + 1);
+            for(int c = 0; c <= n_chunks; c++) bounds[c] = (size_t) ((long long) nB * c / n_chunks) * nE;
+            const int mode = structure_mode(*structure);
+            int* counter = P.work_counter;
+            auto launch = [&](int c) {
+                EnsiParams Q = P;
+                Q.first = (int) (bounds[c] / nE);
+                Q.count = (int) ((bounds[c + 1] - bounds[c]) / nE);
+                GPP_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), 0));
+                if(mode == 1) GPP_LAUNCH(ensi_kernel<1>, grid, ENSI_WARPS * 32, smem, 0, Q);
+                else GPP_LAUNCH(ensi_kernel<0>, grid, ENSI_WARPS * 32, smem, 0, Q);
+                return (int) GPP_OK;
+            };
+            if(n_chunks > 1) {
+                GPP_TRY(pipelined_download(bounds, launch, d_out.ptr, analysis));
+                downloaded = true;
+            }
+            else GPP_TRY(launch(0));
         }
-        if(trace.on) { cudaStreamSynchronize(0); trace.lap("kernel"); }
-        GPP_TRY(d_out.download(analysis, nBE));
+        if(trace.on) { cudaStreamSynchronize(0); trace.lap(downloaded ? "kernel + D2H (pipelined)" : "kernel"); }
+        if(!downloaded) GPP_TRY(d_out.download(analysis, nBE));
         if(num_skipped) GPP_CUDA(cudaMemcpyAsync(num_skipped, d_flags.ptr + nE, sizeof(int), cudaMemcpyDeviceToHost, 0));
         GPP_CUDA(cudaStreamSynchronize(0));   // `obs` and the staging vectors go out of scope after this
         trace.lap("D2H");

@@ -19,6 +19,7 @@
 
 #include <algorithm>
 #include <cstring>
+#include <functional>
 #include <mutex>
 
 using namespace gpp;
@@ -1138,7 +1139,7 @@ int check_structure(const gpp_structure* s) {
 }
 }  // namespace
 
-namespace {
+namespace gpp {
 // Pinned staging for pipelined downloads: two slots, grown on demand, kept for the life of the process.
 struct PinnedStage {
     std::mutex lock;
@@ -1158,56 +1159,66 @@ struct PinnedStage {
 };
 PinnedStage g_stage;
 
-// Row blocks of the grid are analysed back to back on the default stream; a second stream copies each finished block
-// into a pinned slot, and the host moves it into the caller's array while the next block is being analysed.
-int analyse_pipelined(const gpp_points* bpoints, int nB, int nx, int n_chunks, const float* d_bg, const float* d_bvar, const gpp_oi_obs* obs,
-                      const gpp_structure* structure, int max_points, int allow_extrapolation, float* d_out, float* d_var, float* analysis) {
-    const int n_rows = nB / nx;
-    std::vector<int> row0(n_chunks + 1);
-    for(int c = 0; c <= n_chunks; c++) row0[c] = (int) ((long long) n_rows * c / n_chunks);
+// Blocks [bounds[c], bounds[c+1]) (in floats) of d_out are produced back to back on the default stream by launch(c); a
+// second stream copies each finished block into a pinned slot, and the host moves it into the caller's array while the
+// next block is being computed. A D2H straight into a pageable array runs at ~5 GB/s, first-touch page faults included.
+int pipelined_download(const std::vector<size_t>& bounds, const std::function<int(int)>& launch, const float* d_out, float* host_out) {
+    const int n_chunks = (int) bounds.size() - 1;
     size_t largest = 0;
-    for(int c = 0; c < n_chunks; c++) largest = std::max(largest, (size_t) (row0[c + 1] - row0[c]) * nx);
+    for(int c = 0; c < n_chunks; c++) largest = std::max(largest, bounds[c + 1] - bounds[c]);
     std::lock_guard<std::mutex> guard(g_stage.lock);
     GPP_TRY(g_stage.reserve(largest));
     cudaStream_t copy_stream;
     GPP_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
-    std::vector<cudaEvent_t> analysed(n_chunks), copied(n_chunks);
+    std::vector<cudaEvent_t> produced(n_chunks), copied(n_chunks);
     for(int c = 0; c < n_chunks; c++) {
-        cudaEventCreateWithFlags(&analysed[c], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&produced[c], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&copied[c], cudaEventDisableTiming);
     }
     int rc = GPP_OK;
     for(int c = 0; c < n_chunks && rc == GPP_OK; c++) {
-        rc = gpp_optimal_interpolation_device(bpoints, row0[c] * nx, (row0[c + 1] - row0[c]) * nx, d_bg, d_bvar, obs, structure, max_points,
-                                              allow_extrapolation, d_out, d_var, nullptr);
-        cudaEventRecord(analysed[c], 0);
+        rc = launch(c);
+        cudaEventRecord(produced[c], 0);
     }
     // The caller's array is usually fresh (untouched pages): fault it in now, while the device is busy with block 0,
     // instead of during the copies at the end (first-touch runs at 2-4 GB/s).
     if(rc == GPP_OK)
-        for(size_t i = 0; i < (size_t) nB; i += 1024) reinterpret_cast<volatile float*>(analysis)[i] = 0.f;
+        for(size_t i = bounds[0]; i < bounds[n_chunks]; i += 1024) reinterpret_cast<volatile float*>(host_out)[i] = 0.f;
     auto finish = [&](int c) {   // block c: wait for its copy, move it to the caller's array
-        if(cudaEventSynchronize(copied[c]) != cudaSuccess) return fail(GPP_ERR_CUDA, "CUDA error while downloading the analysis");
-        std::memcpy(analysis + (size_t) row0[c] * nx, g_stage.slot[c & 1], sizeof(float) * (size_t) (row0[c + 1] - row0[c]) * nx);
+        if(cudaEventSynchronize(copied[c]) != cudaSuccess) return fail(GPP_ERR_CUDA, "CUDA error while downloading a result block");
+        std::memcpy(host_out + bounds[c], g_stage.slot[c & 1], sizeof(float) * (bounds[c + 1] - bounds[c]));
         return (int) GPP_OK;
     };
     for(int c = 0; c < n_chunks && rc == GPP_OK; c++) {
         if(c >= 2) rc = finish(c - 2);               // frees slot c & 1
         if(rc != GPP_OK) break;
-        cudaStreamWaitEvent(copy_stream, analysed[c], 0);
-        cudaMemcpyAsync(g_stage.slot[c & 1], d_out + (size_t) row0[c] * nx, sizeof(float) * (size_t) (row0[c + 1] - row0[c]) * nx,
-                        cudaMemcpyDeviceToHost, copy_stream);
+        cudaStreamWaitEvent(copy_stream, produced[c], 0);
+        cudaMemcpyAsync(g_stage.slot[c & 1], d_out + bounds[c], sizeof(float) * (bounds[c + 1] - bounds[c]), cudaMemcpyDeviceToHost, copy_stream);
         cudaEventRecord(copied[c], copy_stream);
     }
     for(int c = std::max(0, n_chunks - 2); c < n_chunks && rc == GPP_OK; c++) rc = finish(c);
     cudaStreamSynchronize(copy_stream);
-    for(int c = 0; c < n_chunks; c++) { cudaEventDestroy(analysed[c]); cudaEventDestroy(copied[c]); }
+    for(int c = 0; c < n_chunks; c++) { cudaEventDestroy(produced[c]); cudaEventDestroy(copied[c]); }
     cudaStreamDestroy(copy_stream);
     if(rc == GPP_OK) {
         cudaError_t err = cudaGetLastError();
         if(err != cudaSuccess) rc = fail(GPP_ERR_CUDA, "CUDA error %s: %s", cudaGetErrorName(err), cudaGetErrorString(err));
     }
     return rc;
+}
+}  // namespace gpp
+
+namespace {
+// Row blocks of the grid are analysed back to back and returned through the pinned staging buffer.
+int analyse_pipelined(const gpp_points* bpoints, int nB, int nx, int n_chunks, const float* d_bg, const float* d_bvar, const gpp_oi_obs* obs,
+                      const gpp_structure* structure, int max_points, int allow_extrapolation, float* d_out, float* d_var, float* analysis) {
+    const int n_rows = nB / nx;
+    std::vector<size_t> bounds(n_chunks + 1);
+    for(int c = 0; c <= n_chunks; c++) bounds[c] = (size_t) ((long long) n_rows * c / n_chunks) * nx;
+    return pipelined_download(bounds, [&](int c) {
+        return gpp_optimal_interpolation_device(bpoints, (int) bounds[c], (int) (bounds[c + 1] - bounds[c]), d_bg, d_bvar, obs, structure,
+                                                max_points, allow_extrapolation, d_out, d_var, nullptr);
+    }, d_out, analysis);
 }
 }  // namespace
 
