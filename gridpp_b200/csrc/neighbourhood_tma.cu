@@ -424,6 +424,7 @@ __global__ void __launch_bounds__(NT, MINB_MM) nbh_minmax_tma_kernel(const __gri
     const StageRing R = {ring, bars, &in_map, x0 - a.HL, y_begin + hw - RB * P, NS, P + n_batches};
     R.start();
     const int scol = min(tid + (a.HL - hw), NT - 1);   // staged column of window column tid, see nbh_sum_tma_kernel
+    const bool has_col = tid + (a.HL - hw) < NT;       // only the owner of a staged column rewrites its infinities
 
     const int rel0 = RB * P - 2 * hw;     // ring row of input row y_begin - hw
     for(int k = 0; k < P; k++) {
@@ -431,7 +432,7 @@ __global__ void __launch_bounds__(NT, MINB_MM) nbh_minmax_tma_kernel(const __gri
         float* sp = ring + (size_t) k * RB * NT + scol;
         #pragma unroll
         for(int b = 0; b < RB; b++)
-            if(fabsf(sp[b * NT]) == INFINITY) sp[b * NT] = NAN;
+            if(has_col && fabsf(sp[b * NT]) == INFINITY) sp[b * NT] = NAN;
     }
     const int hb = tid >> 5, seg = tid & 31, xo0 = seg * SEG;
     const bool h_active = xo0 < a.TX && x0 + xo0 < a.nx;
@@ -458,7 +459,7 @@ __global__ void __launch_bounds__(NT, MINB_MM) nbh_minmax_tma_kernel(const __gri
             #pragma unroll
             for(int b = 0; b < RB; b++) {
                 vnew[b] = sp[b * NT];
-                if(fabsf(vnew[b]) == INFINITY) { vnew[b] = NAN; sp[b * NT] = NAN; }
+                if(fabsf(vnew[b]) == INFINITY) { vnew[b] = NAN; if(has_col) sp[b * NT] = NAN; }
             }
             float out[RB];
             const float* base = ring + scol;

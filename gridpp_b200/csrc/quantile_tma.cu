@@ -185,6 +185,7 @@ __global__ void __launch_bounds__(NT, 2) qf_tma_kernel(const __grid_constant__ C
         mtab[m] = make_float2(__int_as_float(!QFIELD && m > 0 ? nlt_of(a.quantile, m) : 0), m > 0 ? __frcp_rn((float) m) : 0.f);
     // window column tid of the strip = staged column tid + (HL - hw), see nbh_sum_tma_kernel
     const int scol = min(tid + (a.HL - hw), NT - 1);
+    const bool has_col = tid + (a.HL - hw) < NT;   // the last HL - hw threads have no window column: they must not touch a shared one
     unsigned char* const my_bins = bring + scol;
     unsigned* const my_line = line + pc(tid);
     const int rel0 = RB * P - 2 * hw;        // ring row of input row y_begin - hw (earlier rows of stage 0 are not used)
@@ -228,7 +229,7 @@ __global__ void __launch_bounds__(NT, 2) qf_tma_kernel(const __grid_constant__ C
                 if(tp[step - 1] < v) tp += step;
             int bin = (int) (tp - sthr);
             if(!finite_f(v)) bin = BIN_INVALID;
-            const bool used = batch || RB * s + b >= rel0;
+            const bool used = has_col && (batch || RB * s + b >= rel0);
             if(used) {
                 my_bins[(brow + b) * NT] = (unsigned char) bin;
                 #pragma unroll
@@ -237,7 +238,7 @@ __global__ void __launch_bounds__(NT, 2) qf_tma_kernel(const __grid_constant__ C
             if(batch) {
                 #pragma unroll
                 for(int k = 0; k < NW8; k++) my_line[(b * NW8 + k) * LROW] = C[k];
-                const int bo = my_bins[orow * NT];
+                const int bo = has_col ? my_bins[orow * NT] : BIN_INVALID;
                 #pragma unroll
                 for(int k = 0; k < NW8; k++) C[k] -= therm[k * 33 + bo];
                 orow = orow + 1 == NRB ? 0 : orow + 1;
