@@ -217,10 +217,12 @@ __global__ void __launch_bounds__(NT, MINB_SUM) nbh_sum_tma_kernel(const __grid_
         const float v = ring_col[rel * NT];
         if(finite_f(v)) st.csum += (double) v; else st.ninv++;
     }
-    float hist[REGWIN ? 2 * HW : 1];   // register-window form: rows y0 - hw .. y0 + hw - 1 of the column
+    // register-window form: rows y0 - hw .. y0 + hw - 1 of the column, already converted (each value is converted to
+    // double once: the conversions run on the 16-lane XU pipe)
+    double hist[REGWIN ? 2 * HW : 1];
     if constexpr(REGWIN) {
         #pragma unroll
-        for(int j = 0; j < 2 * HW; j++) hist[j] = ring_col[(rel0 + j) * NT];
+        for(int j = 0; j < 2 * HW; j++) hist[j] = (double) ring_col[(rel0 + j) * NT];
     }
     const int hb = tid >> 5, seg = tid & 31, xo0 = seg * SEG;
     const bool h_active = xo0 < a.TX && x0 + xo0 < a.nx;
@@ -237,15 +239,12 @@ __global__ void __launch_bounds__(NT, MINB_SUM) nbh_sum_tma_kernel(const __grid_
             double dn[RB], dd[RB], c[RB + 1];
             if constexpr(REGWIN) {
                 // the 2 hw rows above the entering stage are kept in registers: the leaving rows are hist[0 .. 7]
-                float vn[RB];
                 #pragma unroll
-                for(int b = 0; b < RB; b++) {
-                    vn[b] = newp[b * NT];
-                    dn[b] = (double) vn[b];
-                    dd[b] = dn[b] - (double) (b < 2 * HW ? hist[b] : vn[b - 2 * HW]);
-                }
+                for(int b = 0; b < RB; b++) dn[b] = (double) newp[b * NT];
                 #pragma unroll
-                for(int j = 0; j < 2 * HW; j++) hist[j] = j + RB < 2 * HW ? hist[j + RB] : vn[j + RB - 2 * HW];
+                for(int b = 0; b < RB; b++) dd[b] = dn[b] - (b < 2 * HW ? hist[b] : dn[b - 2 * HW]);
+                #pragma unroll
+                for(int j = 0; j < 2 * HW; j++) hist[j] = j + RB < 2 * HW ? hist[j + RB] : dn[j + RB - 2 * HW];
             }
             else {
                 const int s_old2 = s_old + 1 == NS ? 0 : s_old + 1;
