@@ -26,20 +26,35 @@ def needs_build():
 
 
 def build(force=False, verbose=False):
+    """Compiles every source to an object file in parallel (one nvcc per file), then links the shared library."""
     if not force and not needs_build():
         return LIB
+    import concurrent.futures
+    import tempfile
     srcs = [os.path.join(HERE, "csrc", s) for s in SOURCES if os.path.exists(os.path.join(HERE, "csrc", s))]
-    cmd = [nvcc_path(), "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-           "-ccbin", "/usr/bin/g++", "-Xcompiler", "-fPIC,-fopenmp,-O2", "-shared",
-           "-I", os.path.join(ROOT, "include"), "-I", os.path.join(HERE, "csrc"), "-o", LIB] + srcs + ["-lgomp"]
+    common = [nvcc_path(), "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-ccbin", "/usr/bin/g++",
+              "-Xcompiler", "-fPIC,-fopenmp,-O2", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(HERE, "csrc")]
     if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        sys.stderr.write(res.stdout + res.stderr)
-        raise RuntimeError("nvcc failed building libgridpp_b200.so")
-    if verbose:
-        sys.stderr.write(res.stderr)
+        common.insert(1, "-Xptxas=-v")
+    with tempfile.TemporaryDirectory(prefix="gridpp_b200_build_") as tmp:
+        def compile_one(src):
+            obj = os.path.join(tmp, os.path.basename(src) + ".o")
+            res = subprocess.run(common + ["-c", src, "-o", obj], capture_output=True, text=True)
+            return src, obj, res
+        objs = []
+        with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, len(srcs))) as pool:
+            for src, obj, res in pool.map(compile_one, srcs):
+                if res.returncode != 0:
+                    sys.stderr.write(res.stdout + res.stderr)
+                    raise RuntimeError("nvcc failed compiling " + os.path.basename(src))
+                if verbose:
+                    sys.stderr.write(res.stderr)
+                objs.append(obj)
+        res = subprocess.run([nvcc_path(), "-shared", "-ccbin", "/usr/bin/g++", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-lgomp"],
+                             capture_output=True, text=True)
+        if res.returncode != 0:
+            sys.stderr.write(res.stdout + res.stderr)
+            raise RuntimeError("nvcc failed linking libgridpp_b200.so")
     return LIB
 
 
