@@ -330,24 +330,6 @@ def _single(stype, h, v, w, hmax):
 _DEFAULT_MIN_RHO = 0.0013   # StructureFunction::default_min_rho, structure.cpp:5
 
 
-def _recompute_loc_dist(stype, h, min_rho):
-    """localization_distance(h) for an explicit min_rho (the (1, 1)-field constructors), float arithmetic as the reference."""
-    f = _np.float32
-    m, h = f(min_rho), f(h)
-    if stype == _BARNES:
-        return float(_np.sqrt(f(-2) * _np.log(m)) * h)
-    if stype == _SOAR:
-        l = _np.log(m)
-        return float((-l + _np.log(-l)) * h)
-    if stype == _TOAR:
-        l = _np.log(m)
-        ll = _np.log(-_np.log(m))
-        return float(f((float(-l + ll) + 0.5 * float(ll)) * float(h)))
-    if stype == _POWERLAW:
-        return float(_np.sqrt(f(2) * (f(1) - m) / m) * h)
-    return 0.0
-
-
 class _SpatialField:
     """Scales h, v, w on the nodes of a Grid (gpp_structure_field): <Family>Structure(Grid, vec2 h, vec2 v, vec2 w, min_rho),
     structure.cpp:168-184 (Barnes), :342 (Soar), :492 (Toar), :643 (Powerlaw), :790 (Linear)."""
@@ -387,9 +369,8 @@ class _Family(StructureFunction):
             h2, v2, w2 = (_np.asarray(a, _np.float32) for a in (h, v, w))
             if h2.shape == (1, 1) and v2.shape == (1, 1) and w2.shape == (1, 1):
                 # not spatial (structure.cpp:174-176): constant scales with the given min_rho
-                d = _single(self._TYPE, float(h2[0, 0]), float(v2[0, 0]), float(w2[0, 0]), MV)
-                d.term[0].min_rho = min_rho
-                d.term[0].loc_dist = _recompute_loc_dist(self._TYPE, float(h2[0, 0]), min_rho)
+                d = _lib.StructureDesc()
+                _check(_libc.gpp_structure_init_min_rho(_C.byref(d), self._TYPE, float(h2[0, 0]), float(v2[0, 0]), float(w2[0, 0]), min_rho))
                 StructureFunction.__init__(self, d)
                 return
             self._field = _SpatialField(grid, h2, v2, w2)

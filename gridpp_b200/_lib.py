@@ -51,6 +51,7 @@ _proto("gpp_device_synchronize", C.c_int)
 _proto("gpp_kernel_launch_count", C.c_ulonglong)
 _proto("gpp_measure_fp64_fma_peak", C.c_int, C.POINTER(C.c_double))
 _proto("gpp_structure_init", C.c_int, sp, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float)
+_proto("gpp_structure_init_min_rho", C.c_int, sp, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float)
 _proto("gpp_structure_multiple", C.c_int, sp, sp, sp, sp)
 _proto("gpp_structure_cross_validation", C.c_int, sp, sp, C.c_float)
 _proto("gpp_structure_corr_host", C.c_int, sp, fp, fp, C.c_int, C.c_int, fp)
@@ -60,6 +61,7 @@ _proto("gpp_points_set_shape", C.c_int, vp, C.c_int, C.c_int)
 _proto("gpp_points_size", C.c_int, vp)
 _proto("gpp_points_coordinate_type", C.c_int, vp)
 _proto("gpp_points_get_xyz", C.c_int, vp, fp, fp, fp)
+_proto("gpp_convert_coordinates", C.c_int, fp, fp, C.c_int, C.c_int, fp, fp, fp)
 _proto("gpp_points_nearest_host", C.c_int, vp, fp, fp, C.c_int, C.c_int, ip)
 _proto("gpp_points_neighbours_host", C.c_int, vp, fp, fp, fp, C.c_int, C.c_int, C.c_int, ip, fp, ip)
 _proto("gpp_points_closest_host", C.c_int, vp, fp, fp, C.c_int, C.c_int, C.c_int, ip)
@@ -89,9 +91,9 @@ _proto("gpp_get_neighbourhood_thresholds_host", C.c_int, fp, C.c_longlong, C.c_i
 
 EXPORTS = [
     "gpp_version", "gpp_last_error", "gpp_device_count", "gpp_set_device", "gpp_device_synchronize",
-    "gpp_kernel_launch_count", "gpp_measure_fp64_fma_peak", "gpp_structure_init", "gpp_structure_multiple", "gpp_structure_cross_validation",
+    "gpp_kernel_launch_count", "gpp_measure_fp64_fma_peak", "gpp_structure_init", "gpp_structure_init_min_rho", "gpp_structure_multiple", "gpp_structure_cross_validation",
     "gpp_structure_corr_host", "gpp_points_create", "gpp_points_destroy", "gpp_points_set_shape", "gpp_points_size",
-    "gpp_points_coordinate_type", "gpp_points_get_xyz", "gpp_points_nearest_host", "gpp_points_neighbours_host",
+    "gpp_points_coordinate_type", "gpp_points_get_xyz", "gpp_convert_coordinates", "gpp_points_nearest_host", "gpp_points_neighbours_host",
     "gpp_points_closest_host", "gpp_nearest_host", "gpp_optimal_interpolation_host", "gpp_oi_obs_create",
     "gpp_oi_obs_destroy", "gpp_optimal_interpolation_device", "gpp_optimal_interpolation_ensi_host",
     "gpp_neighbourhood_host", "gpp_neighbourhood_device", "gpp_neighbourhood_quantile_fast_host",

@@ -187,6 +187,14 @@ int gpp_structure_init(gpp_structure* out, int type, float h, float v, float w, 
     return GPP_OK;
 }
 
+int gpp_structure_init_min_rho(gpp_structure* out, int type, float h, float v, float w, float min_rho) {
+    if(type == GPP_STRUCT_CRESSMAN) return fail(GPP_ERR_INVALID_ARGUMENT, "CressmanStructure has no (grid, h, v, w, min_rho) form");
+    GPP_TRY(gpp_structure_init(out, type, h, v, w, NAN));
+    out->term[0].min_rho = min_rho;
+    out->term[0].loc_dist = term_loc_dist(type, h, min_rho);
+    return GPP_OK;
+}
+
 int gpp_structure_multiple(gpp_structure* out, const gpp_structure* sh, const gpp_structure* sv, const gpp_structure* sw) {
     if(!out || !sh || !sv || !sw) return fail(GPP_ERR_INVALID_ARGUMENT, "NULL structure");
     if(sh->n_terms != 1 || sv->n_terms != 1 || sw->n_terms != 1 || sh->has_cv || sv->has_cv || sw->has_cv)

@@ -394,6 +394,15 @@ int gpp_points_create(const float* lats, const float* lons, const float* elevs, 
 }
 
 void gpp_points_destroy(gpp_points* p) { delete p; }
+int gpp_convert_coordinates(const float* lats, const float* lons, int n, int coordinate_type, float* x, float* y, float* z) {
+    if(n < 0 || (n > 0 && (!lats || !lons || !x || !y || !z))) return fail(GPP_ERR_INVALID_ARGUMENT, "invalid arguments");
+    if(coordinate_type != GPP_GEODETIC && coordinate_type != GPP_CARTESIAN)
+        return fail(GPP_ERR_INVALID_ARGUMENT, "unknown coordinate type %d", coordinate_type);
+    for(int i = 0; i < n; i++)
+        if(!convert_one(lats[i], lons[i], coordinate_type, x[i], y[i], z[i]))
+            return fail(GPP_ERR_INVALID_ARGUMENT, "Invalid coords: %g,%g", lats[i], lons[i]);   // util.cpp:596-600
+    return GPP_OK;
+}
 int gpp_points_set_shape(gpp_points* p, int ny, int nx) {
     if(!p) return fail(GPP_ERR_INVALID_ARGUMENT, "points must not be NULL");
     if(ny < 0 || nx < 0 || (long long) ny * nx != p->n) return fail(GPP_ERR_INVALID_ARGUMENT, "shape %d x %d does not match %d points", ny, nx, p->n);

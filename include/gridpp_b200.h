@@ -84,6 +84,9 @@ int gpp_device_synchronize(void);
  * ToarStructure :467-490, PowerlawStructure :618-641, LinearStructure :765-788. hmax = NaN -> default
  * min_rho. Validation errors match the constructors (GPP_ERR_INVALID_ARGUMENT). */
 int gpp_structure_init(gpp_structure* out, int type, float h, float v, float w, float hmax);
+/* The constant-scale case of <Family>Structure(Grid, vec2 h, vec2 v, vec2 w, min_rho) with (1, 1) fields
+ * (structure.cpp:168-176 and siblings): scales h, v, w with an explicit truncation correlation. */
+int gpp_structure_init_min_rho(gpp_structure* out, int type, float h, float v, float w, float min_rho);
 /* MultipleStructure(structure_h, structure_v, structure_w), structure.cpp:90-94. Each input must be a
  * single-term structure. */
 int gpp_structure_multiple(gpp_structure* out, const gpp_structure* sh, const gpp_structure* sv, const gpp_structure* sw);
@@ -111,6 +114,10 @@ int gpp_points_coordinate_type(const gpp_points* p);
 int gpp_points_set_shape(gpp_points* p, int ny, int nx);
 /* KDTree::get_x/get_y/get_z (kdtree.cpp:213-221): copies n floats each; any pointer may be NULL */
 int gpp_points_get_xyz(const gpp_points* p, float* x, float* y, float* z);
+/* gridpp::convert_coordinates(lats, lons, type, x, y, z), util.cpp:583-615: host arithmetic, the same the point
+ * sets use (Geodetic -> earth-centred metres, Cartesian -> x = lon, y = lat, z = 0). Invalid coordinates ->
+ * INVALID_ARGUMENT (util.cpp:596-600). Needs no device. */
+int gpp_convert_coordinates(const float* lats, const float* lons, int n, int coordinate_type, float* x, float* y, float* z);
 
 /* KDTree::get_closest_neighbours(lat,lon,1) for nq query points at once (kdtree.cpp:82-106; the per-point
  * loop of nearest.cpp:7-222). out_index[q] = index of the nearest point, -1 if none. Ties resolve to the
