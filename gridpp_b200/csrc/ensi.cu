@@ -24,6 +24,7 @@ constexpr int ENSI_KMAX = 64;     // observations per point
 constexpr int ENSI_EMAX = 32;     // valid ensemble members
 constexpr int ENSI_GRAB = 32;     // consecutive points a warp takes per grab of the work counter
 constexpr int ENSI_NSLOT = 3;     // candidate buffer = 96 entries
+constexpr int ENSI_CHUNKS = 8;    // blocks of the field returned to the host while the next ones are analysed
 
 struct EnsiParams {
     const float *gx, *gy, *gz, *gelev, *glaf;
@@ -40,48 +41,82 @@ struct EnsiParams {
     int* num_skipped;
     int* work_counter;            // next block of ENSI_GRAB points to hand out (zeroed before the launch)
     int ld;                       // leading dimension of the shared matrices: E rounded up to odd
-    int smem_per_warp;            // bytes, see EnsiSmem::carve
+    int smem_per_warp;            // bytes, see EnsiSmem::layout
+    int off[20];                  // byte offsets of the per-warp arrays (EnsiSmem::layout), read from constant memory
 };
 
 // Per-warp working set, carved from dynamic shared memory for the actual ensemble size and observation cap (a
-// fixed 32 x 64 layout costs 36 KB per warp = 4 warps per SM; E = 20, k = 50 needs 19 KB).
+// fixed 32 x 64 layout costs 36 KB per warp = 4 warps per SM; E = 20, k = 50 needs 19 KB). The host lays the arrays
+// out once (byte offsets in EnsiParams::off); the kernel only adds them to its warp's base.
 struct EnsiSmem {
     unsigned long long* key;      // [32 * ENSI_NSLOT] candidate keys
     double* Y;                    // lY, k x E (leading dimension ld)
     double* A;                    // Pinv, then its diagonalisation, E x E (aliases Y)
-    double* V;                    // eigenvectors in columns (aliases Y)
+    double* T;                    // Pinv V of the warm start, E x E (aliases Y, behind A)
+    double* V;                    // eigenvectors in columns; kept from one point to the next (warm start)
     double *rinv, *dd;            // [k]
     double *b, *t, *lam, *w, *sc, *X;   // [E]
     double *cs, *sn;              // [E / 2 + 1]
     int* pos;                     // [32 * ENSI_NSLOT]
     int* spos;                    // [k]
-    int *pp, *qq;                 // [E / 2 + 1]
+    int* pp;                      // [E / 2 + 1]
     float* sval;                  // [E]
 
-    __host__ __device__ static size_t carve(EnsiSmem* S, unsigned char* base, int E, int kcap, int ld) {
-        size_t off = 0;
-        auto take = [&](size_t bytes) { unsigned char* p = base ? base + off : nullptr; off += (bytes + 15) / 16 * 16; return p; };
+    enum { O_KEY, O_Y, O_V, O_RINV, O_DD, O_B, O_T, O_LAM, O_W, O_SC, O_X, O_CS, O_SN, O_POS, O_SPOS, O_PP, O_SVAL, O_COUNT };
+
+    // fills off[O_COUNT] and returns the bytes per warp
+    static size_t layout(int* off, int E, int kcap, int ld) {
+        size_t at = 0;
+        auto take = [&](int which, size_t bytes) { off[which] = (int) at; at += (bytes + 15) / 16 * 16; };
         const int Ee = E + (E & 1), h = Ee / 2 + 1;
-        unsigned char* p;
-        p = take(sizeof(unsigned long long) * 32 * ENSI_NSLOT); if(S) S->key = reinterpret_cast<unsigned long long*>(p);
-        // A and V reuse lY's storage: lY is consumed (Pinv, C d, the clamp's lY[e]) before they are written
-        const size_t ny = (size_t) kcap * ld, nav = (size_t) 2 * Ee * ld;
-        p = take(sizeof(double) * (ny > nav ? ny : nav));
-        if(S) { S->Y = reinterpret_cast<double*>(p); S->A = S->Y; S->V = S->Y + (size_t) Ee * ld; }
-        p = take(sizeof(double) * kcap); if(S) S->rinv = reinterpret_cast<double*>(p);
-        p = take(sizeof(double) * kcap); if(S) S->dd = reinterpret_cast<double*>(p);
-        double** arr[6] = {S ? &S->b : nullptr, S ? &S->t : nullptr, S ? &S->lam : nullptr, S ? &S->w : nullptr, S ? &S->sc : nullptr, S ? &S->X : nullptr};
-        for(int i = 0; i < 6; i++) { p = take(sizeof(double) * Ee); if(S) *arr[i] = reinterpret_cast<double*>(p); }
-        p = take(sizeof(double) * h); if(S) S->cs = reinterpret_cast<double*>(p);
-        p = take(sizeof(double) * h); if(S) S->sn = reinterpret_cast<double*>(p);
-        p = take(sizeof(int) * 32 * ENSI_NSLOT); if(S) S->pos = reinterpret_cast<int*>(p);
-        p = take(sizeof(int) * kcap); if(S) S->spos = reinterpret_cast<int*>(p);
-        p = take(sizeof(int) * h); if(S) S->pp = reinterpret_cast<int*>(p);
-        p = take(sizeof(int) * h); if(S) S->qq = reinterpret_cast<int*>(p);
-        p = take(sizeof(float) * Ee); if(S) S->sval = reinterpret_cast<float*>(p);
-        return off;
+        take(O_KEY, sizeof(unsigned long long) * 32 * ENSI_NSLOT);
+        // A and T reuse lY's storage: lY is consumed (Pinv, C d, the clamp's lY[e]) before they are written
+        take(O_Y, sizeof(double) * std::max((size_t) kcap * ld, (size_t) 2 * Ee * ld));
+        take(O_V, sizeof(double) * Ee * ld);
+        take(O_RINV, sizeof(double) * kcap);
+        take(O_DD, sizeof(double) * kcap);
+        const int per_member[6] = {O_B, O_T, O_LAM, O_W, O_SC, O_X};
+        for(int i = 0; i < 6; i++) take(per_member[i], sizeof(double) * Ee);
+        take(O_CS, sizeof(double) * h);
+        take(O_SN, sizeof(double) * h);
+        take(O_POS, sizeof(int) * 32 * ENSI_NSLOT);
+        take(O_SPOS, sizeof(int) * kcap);
+        take(O_PP, sizeof(int) * h);
+        take(O_SVAL, sizeof(float) * Ee);
+        return at;
+    }
+    __device__ __forceinline__ void bind(unsigned char* base, const int* off, int E, int ld) {
+        const int Ee = E + (E & 1);
+        key = reinterpret_cast<unsigned long long*>(base + off[O_KEY]);
+        Y = reinterpret_cast<double*>(base + off[O_Y]);
+        A = Y;
+        T = Y + Ee * ld;
+        V = reinterpret_cast<double*>(base + off[O_V]);
+        rinv = reinterpret_cast<double*>(base + off[O_RINV]);
+        dd = reinterpret_cast<double*>(base + off[O_DD]);
+        b = reinterpret_cast<double*>(base + off[O_B]);
+        t = reinterpret_cast<double*>(base + off[O_T]);
+        lam = reinterpret_cast<double*>(base + off[O_LAM]);
+        w = reinterpret_cast<double*>(base + off[O_W]);
+        sc = reinterpret_cast<double*>(base + off[O_SC]);
+        X = reinterpret_cast<double*>(base + off[O_X]);
+        cs = reinterpret_cast<double*>(base + off[O_CS]);
+        sn = reinterpret_cast<double*>(base + off[O_SN]);
+        pos = reinterpret_cast<int*>(base + off[O_POS]);
+        spos = reinterpret_cast<int*>(base + off[O_SPOS]);
+        pp = reinterpret_cast<int*>(base + off[O_PP]);
+        sval = reinterpret_cast<float*>(base + off[O_SVAL]);
     }
 };
+static_assert(EnsiSmem::O_COUNT <= 20, "EnsiParams::off is too small");
+
+#ifdef ENSI_STATS
+// debug build only (profiles/variants.sh -DENSI_STATS): [0] points, [1] sweeps, [2] rotations, [3] warm starts
+__device__ unsigned long long g_ensi_stats[4];
+#define ENSI_COUNT(i, n) do { if(lane_id() == 0) atomicAdd(&g_ensi_stats[i], (unsigned long long) (n)); } while(0)
+#else
+#define ENSI_COUNT(i, n) do {} while(0)
+#endif
 
 // members with an invalid value anywhere in the background are left untouched (oi_ensi.cpp:187-201)
 __global__ void ensi_invalid_members_kernel(const float* __restrict__ background, size_t n, int nE, int* __restrict__ invalid) {
@@ -97,7 +132,7 @@ template <int SMODE>
 __global__ void __launch_bounds__(ENSI_WARPS * 32, ENSI_MINB) ensi_kernel(const __grid_constant__ EnsiParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     EnsiSmem S;
-    EnsiSmem::carve(&S, smem_raw + (size_t) (threadIdx.x >> 5) * P.smem_per_warp, P.E, P.k, P.ld);
+    S.bind(smem_raw + (size_t) (threadIdx.x >> 5) * P.smem_per_warp, P.off, P.E, P.ld);
     const int LD = P.ld;
     const int lane = (int) lane_id();
     const CandBuf cb = {S.key, S.pos};
@@ -105,14 +140,22 @@ __global__ void __launch_bounds__(ENSI_WARPS * 32, ENSI_MINB) ensi_kernel(const 
     const int Eeven = E + (E & 1), m = Eeven - 1;   // round-robin schedule over an even number of indices
     const int H = Eeven / 2;                        // rotations per round
 
-    // blocks of consecutive points are handed out dynamically (the cost per point varies with k and the sweep count)
+    // Blocks of ENSI_GRAB consecutive points are handed out dynamically (the cost per point varies with k and the
+    // sweep count). Inside a block every point starts its Jacobi iteration from the eigenvectors of the point before
+    // it (neighbouring points have nearly the same Pinv). The blocks are aligned to ABSOLUTE point indices, and a
+    // range that begins inside a block replays the block's earlier points without writing them, so that a point's
+    // result does not depend on how the field was cut into ranges.
+    const int blk0 = P.first / ENSI_GRAB;
+    const int n_blk = (P.first + P.count + ENSI_GRAB - 1) / ENSI_GRAB - blk0;
     for(;;) {
-    int it0 = 0;
-    if(lane == 0) it0 = atomicAdd(P.work_counter, ENSI_GRAB);
-    it0 = __shfl_sync(0xffffffffu, it0, 0);
-    if(it0 >= P.count) break;
-    for(int it = it0; it < min(it0 + ENSI_GRAB, P.count); it++) {
-        const int g = P.first + it;
+    int blk = 0;
+    if(lane == 0) blk = atomicAdd(P.work_counter, 1);
+    blk = __shfl_sync(0xffffffffu, blk, 0);
+    if(blk >= n_blk) break;
+    const int g_begin = (blk0 + blk) * ENSI_GRAB, g_end = min(g_begin + ENSI_GRAB, P.first + P.count);
+    bool warm = false;   // S.V holds the eigenvectors of an earlier point of this block
+    for(int g = g_begin; g < g_end; g++) {
+        const bool emit = g >= P.first;
         const Pt p1 = {P.gx[g], P.gy[g], P.gz[g], P.gelev[g], P.glaf[g]};
         bool cut = false;
         const int k = gather_candidates<SMODE, ENSI_NSLOT>(P.obs, P.s, p1, P.R, P.k, cb, &cut);
@@ -168,14 +211,48 @@ __global__ void __launch_bounds__(ENSI_WARPS * 32, ENSI_MINB) ensi_kernel(const 
                 S.b[lane] = b;
                 lYe = S.Y[(lane % k) * LD + (lane / k)];
             }
-            __syncwarp();   // lY is dead from here on: A and V take its place
-            const float diag = (float) (E - 1);   // oi_ensi.cpp:383 with delta = 1
+            __syncwarp();   // lY is dead from here on: A and T take its place
+            const double diag = (double) (float) (E - 1);   // oi_ensi.cpp:383 with delta = 1
             #pragma unroll
             for(int f = 0; f < ENSI_EMAX; f++)
-                if(f < E && lane < E) {
-                    S.A[lane * LD + f] = acc[f] + (f == lane ? (double) diag : 0.0);
-                    S.V[lane * LD + f] = f == lane ? 1.0 : 0.0;
+                if(f == lane) acc[f] += diag;
+            ENSI_COUNT(0, 1);
+            ENSI_COUNT(3, warm ? 1 : 0);
+#ifdef ENSI_COLD
+            warm = false;
+#endif
+            if(!warm) {
+                #pragma unroll
+                for(int f = 0; f < ENSI_EMAX; f++)
+                    if(f < E && lane < E) {
+                        S.A[lane * LD + f] = acc[f];
+                        S.V[lane * LD + f] = f == lane ? 1.0 : 0.0;
+                    }
+            }
+            else {
+                // warm start: A = V' Pinv V with the previous point's V, which leaves only small off-diagonal elements
+                if(lane < E)
+                    for(int j = 0; j < E; j++) {   // T = Pinv V, row `lane`
+                        double t = 0.0;
+                        #pragma unroll
+                        for(int f = 0; f < ENSI_EMAX; f++)
+                            if(f < E) t = fma(acc[f], S.V[f * LD + j], t);
+                        S.T[lane * LD + j] = t;
+                    }
+                __syncwarp();
+                if(lane < E) {
+                    #pragma unroll
+                    for(int f = 0; f < ENSI_EMAX; f++)
+                        if(f < E) acc[f] = S.V[f * LD + lane];   // column `lane` of V
+                    for(int j = 0; j < E; j++) {   // A = V' T, row `lane`
+                        double t = 0.0;
+                        #pragma unroll
+                        for(int f = 0; f < ENSI_EMAX; f++)
+                            if(f < E) t = fma(acc[f], S.T[f * LD + j], t);
+                        S.A[lane * LD + j] = t;
+                    }
                 }
+            }
         }
         __syncwarp();
         // ---- cyclic Jacobi, parallel (round-robin) ordering: E/2 disjoint rotations per round
@@ -191,6 +268,7 @@ __global__ void __launch_bounds__(ENSI_WARPS * 32, ENSI_MINB) ensi_kernel(const 
             for(int o = 16; o > 0; o >>= 1) { off += shfl_double(off, lane ^ o); dg += shfl_double(dg, lane ^ o); }
             if(!(off == off) || !(dg == dg) || isinf(off) || isinf(dg)) { bad = true; break; }
             if(off <= 1e-26 * dg) break;   // off-diagonal rms below 1e-13 of the diagonal: eigenpairs exact to ~1e-13
+            ENSI_COUNT(1, 1);
             // round-robin schedule: in round r lane l > 0 pairs (r + l) % m with (r - l) % m, lane 0 pairs m with r
             int pr = lane % m, qr = (m - lane % m) % m;
             for(int r = 0; r < m; r++) {
@@ -223,6 +301,7 @@ __global__ void __launch_bounds__(ENSI_WARPS * 32, ENSI_MINB) ensi_kernel(const 
                 const unsigned rmask = __ballot_sync(0xffffffffu, rot);
                 const int nrot = __popc(rmask);
                 if(nrot == 0) continue;
+                ENSI_COUNT(2, nrot);
                 if(rot) {
                     const int slot = __popc(rmask & ((1u << lane) - 1u));
                     S.pp[slot] = p | (q << 8); S.cs[slot] = c; S.sn[slot] = s;
@@ -259,10 +338,12 @@ __global__ void __launch_bounds__(ENSI_WARPS * 32, ENSI_MINB) ensi_kernel(const 
         // eigenvalues of Pinv; rcond(Pinv) <= 0 in the reference (oi_ensi.cpp:386-390) <=> not positive definite / not finite
         double lam = lane < E ? S.A[lane * LD + lane] : 1.0;
         bad = bad || __any_sync(0xffffffffu, !(lam > 0.0) || isinf(lam));
+        warm = !bad;
         if(bad) {
-            if(lane == 0) atomicAdd(P.num_skipped, 1);
+            if(lane == 0 && emit) atomicAdd(P.num_skipped, 1);
             continue;
         }
+        if(!emit) continue;   // replayed for the warm-start chain only
         if(lane < E) {
             S.lam[lane] = lam;
             S.sc[lane] = sqrt((double) (E - 1) / lam);   // sqrt of the eigenvalues of (E-1) P, oi_ensi.cpp:401,419
@@ -290,9 +371,14 @@ __global__ void __launch_bounds__(ENSI_WARPS * 32, ENSI_MINB) ensi_kernel(const 
             // analysis for member `lane`: total += X(k) * W(k, e) accumulated in FLOAT (oi_ensi.cpp:506-512),
             // W(k, e) = sum_f V(k,f) sqrt((E-1)/lam_f) V(e,f) + w(k)  (oi_ensi.cpp:419-444)
             float tot = 0.f;
+            double vs[ENSI_EMAX];   // row `lane` of V scaled by sqrt((E-1) / lambda)
+            #pragma unroll
+            for(int f = 0; f < ENSI_EMAX; f++) vs[f] = f < E ? S.V[lane * LD + f] * S.sc[f] : 0.0;
             for(int kk = 0; kk < E; kk++) {
                 double wke = 0.0;
-                for(int f = 0; f < E; f++) wke = fma(S.V[kk * LD + f] * S.sc[f], S.V[lane * LD + f], wke);
+                #pragma unroll
+                for(int f = 0; f < ENSI_EMAX; f++)
+                    if(f < E) wke = fma(S.V[kk * LD + f], vs[f], wke);
                 wke += S.w[kk];
                 tot = (float) ((double) tot + S.X[kk] * wke);
             }
@@ -365,8 +451,8 @@ extern "C" int gpp_optimal_interpolation_ensi_host(const gpp_points* cbp, const 
     DeviceBuffer<float> d_bg, d_out, d_gY;
     DeviceBuffer<int> d_flags;
     GPP_TRY(d_bg.upload(background, nBE));
-    GPP_TRY(d_flags.alloc(nE + 2));   // per-member invalid flags, the skipped-point count, the work counter
-    GPP_CUDA(cudaMemsetAsync(d_flags.ptr, 0, sizeof(int) * (nE + 2), 0));
+    GPP_TRY(d_flags.alloc(nE + 1 + ENSI_CHUNKS));   // per-member invalid flags, the skipped-point count, the work counters
+    GPP_CUDA(cudaMemsetAsync(d_flags.ptr, 0, sizeof(int) * (nE + 1 + ENSI_CHUNKS), 0));
     GPP_LAUNCH(ensi_invalid_members_kernel, (unsigned) ((nBE + 255) / 256), 256, 0, 0, d_bg.ptr, nBE, nE, d_flags.ptr);
     std::vector<int> flags(nE + 1);
     GPP_TRY(d_flags.download(flags.data(), nE + 1));
@@ -422,7 +508,7 @@ extern "C" int gpp_optimal_interpolation_ensi_host(const gpp_points* cbp, const 
                 return fail(GPP_ERR_NOT_IMPLEMENTED, "optimal_interpolation_ensi supports at most %d observations per point on the device (got %d)", ENSI_KMAX, kcap);
             P.k = kcap;
             P.ld = E | 1;
-            P.smem_per_warp = (int) EnsiSmem::carve(nullptr, nullptr, E, kcap, P.ld);
+            P.smem_per_warp = (int) EnsiSmem::layout(P.off, E, kcap, P.ld);
             const size_t smem = (size_t) P.smem_per_warp * ENSI_WARPS;
             GPP_CUDA(cudaFuncSetAttribute(ensi_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
             GPP_CUDA(cudaFuncSetAttribute(ensi_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
@@ -431,27 +517,27 @@ extern "C" int gpp_optimal_interpolation_ensi_host(const gpp_points* cbp, const 
             if(structure_mode(*structure) == 1) GPP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ensi_kernel<1>, ENSI_WARPS * 32, smem));
             else GPP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ensi_kernel<0>, ENSI_WARPS * 32, smem));
             const unsigned grid = (unsigned) std::max<long long>(1, std::min<long long>(want, (long long) sm_count() * std::max(per_sm, 1)));
-            P.work_counter = d_flags.ptr + nE + 1;
-            // blocks of points, each returned to the host (through pinned staging) while the next one is analysed
-            const int n_chunks = nB >= (1 << 18) ? 8 : 1;
+            // blocks of points, each returned to the host (through pinned staging) while the next ones are analysed; every
+            // block has its own work counter because consecutive blocks overlap on the device
+            const int n_chunks = nB >= (1 << 18) ? ENSI_CHUNKS : 1;
             std::vector<size_t> bounds(n_chunks + 1);
             for(int c = 0; c <= n_chunks; c++) bounds[c] = (size_t) ((long long) nB * c / n_chunks) * nE;
             const int mode = structure_mode(*structure);
-            int* counter = P.work_counter;
-            auto launch = [&](int c) {
+            int* counters = d_flags.ptr + nE + 1;
+            auto launch = [&](int c, cudaStream_t stream) {
                 EnsiParams Q = P;
                 Q.first = (int) (bounds[c] / nE);
                 Q.count = (int) ((bounds[c + 1] - bounds[c]) / nE);
-                GPP_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), 0));
-                if(mode == 1) GPP_LAUNCH(ensi_kernel<1>, grid, ENSI_WARPS * 32, smem, 0, Q);
-                else GPP_LAUNCH(ensi_kernel<0>, grid, ENSI_WARPS * 32, smem, 0, Q);
+                Q.work_counter = counters + c;
+                if(mode == 1) GPP_LAUNCH(ensi_kernel<1>, grid, ENSI_WARPS * 32, smem, stream, Q);
+                else GPP_LAUNCH(ensi_kernel<0>, grid, ENSI_WARPS * 32, smem, stream, Q);
                 return (int) GPP_OK;
             };
             if(n_chunks > 1) {
-                GPP_TRY(pipelined_download(bounds, launch, d_out.ptr, analysis));
+                GPP_TRY(pipelined_download(bounds, launch, d_out.ptr, analysis, true));
                 downloaded = true;
             }
-            else GPP_TRY(launch(0));
+            else GPP_TRY(launch(0, 0));
         }
         if(trace.on) { cudaStreamSynchronize(0); trace.lap(downloaded ? "kernel + D2H (pipelined)" : "kernel"); }
         if(!downloaded) GPP_TRY(d_out.download(analysis, nBE));
@@ -464,3 +550,15 @@ extern "C" int gpp_optimal_interpolation_ensi_host(const gpp_points* cbp, const 
     GPP_CUDA(cudaStreamSynchronize(0));
     return GPP_OK;
 }
+
+#ifdef ENSI_STATS
+extern "C" int gpp_debug_ensi_stats(unsigned long long* out, int reset) {
+    GPP_CUDA(cudaDeviceSynchronize());
+    GPP_CUDA(cudaMemcpyFromSymbol(out, g_ensi_stats, sizeof(unsigned long long) * 4));
+    if(reset) {
+        unsigned long long zero[4] = {0, 0, 0, 0};
+        GPP_CUDA(cudaMemcpyToSymbol(g_ensi_stats, zero, sizeof(zero)));
+    }
+    return GPP_OK;
+}
+#endif

@@ -107,6 +107,13 @@ struct WarpState {
 #ifndef OI_RPC
 #define OI_RPC 16
 #endif
+#ifdef OI_STATS
+// debug build only (profiles/variants.sh -DOI_STATS): [0] points on the run path, [1] selection changes, [2] systems solved
+__device__ unsigned long long g_oi_stats[4];
+#define OI_COUNT(i) do { if(lane_id() == 0) atomicAdd(&g_oi_stats[i], 1ull); } while(0)
+#else
+#define OI_COUNT(i) do {} while(0)
+#endif
 constexpr int LRU_ENTRIES = OI_LRU;
 constexpr int RUNS_PER_CHUNK = OI_RPC;   // consecutive runs (tiles) handled by one warp, so that the cache sees neighbours
 struct LruEntry {
@@ -548,7 +555,9 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 2) oi_fast_kernel(const __
                 if(s0) S.c_rho[row0] = cand_key_rho(key0);
                 if(s1) S.c_rho[row1] = cand_key_rho(key1);
                 const bool same = sel0 == T0 && sel1 == T1;
+                OI_COUNT(0);
                 if(!same || need_var) {
+                    OI_COUNT(1);
                     if(s0) { S.c_pos[row0] = S.cand_pos[lane]; S.c_orig[row0] = orig0; }
                     if(s1) { S.c_pos[row1] = S.cand_pos[lane + 32]; S.c_orig[row1] = orig1; }
                     __syncwarp();
@@ -556,6 +565,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 2) oi_fast_kernel(const __
                     else {
                         const unsigned now = ++W.clock;
                         if(!lru_lookup(cache, S, k, now, W)) {
+                            OI_COUNT(2);
                             solve_selected<SMODE>(P, S, lut, k, W);
                             lru_store(cache, k, now, W);
                         }
@@ -1162,7 +1172,12 @@ PinnedStage g_stage;
 // Blocks [bounds[c], bounds[c+1]) (in floats) of d_out are produced back to back on the default stream by launch(c); a
 // second stream copies each finished block into a pinned slot, and the host moves it into the caller's array while the
 // next block is being computed. A D2H straight into a pageable array runs at ~5 GB/s, first-touch page faults included.
-int pipelined_download(const std::vector<size_t>& bounds, const std::function<int(int)>& launch, const float* d_out, float* host_out) {
+//
+// overlap_blocks: launch(c, stream) is given two alternating streams (ordered after the default stream's earlier work), so
+// that block c + 1 starts filling the multiprocessors while the last CTAs of block c drain. For kernels whose work items are
+// long (EnSI: tens of milliseconds per item) the drain of every block is otherwise idle time.
+int pipelined_download(const std::vector<size_t>& bounds, const std::function<int(int, cudaStream_t)>& launch, const float* d_out, float* host_out,
+                       bool overlap_blocks) {
     const int n_chunks = (int) bounds.size() - 1;
     size_t largest = 0;
     for(int c = 0; c < n_chunks; c++) largest = std::max(largest, bounds[c + 1] - bounds[c]);
@@ -1176,9 +1191,20 @@ int pipelined_download(const std::vector<size_t>& bounds, const std::function<in
         cudaEventCreateWithFlags(&copied[c], cudaEventDisableTiming);
     }
     int rc = GPP_OK;
+    cudaStream_t compute[2] = {0, 0};
+    if(overlap_blocks) {
+        cudaEvent_t ready;
+        cudaEventCreateWithFlags(&ready, cudaEventDisableTiming);
+        cudaEventRecord(ready, 0);
+        for(int i = 0; i < 2; i++) {
+            GPP_CUDA(cudaStreamCreateWithFlags(&compute[i], cudaStreamNonBlocking));
+            cudaStreamWaitEvent(compute[i], ready, 0);
+        }
+        cudaEventDestroy(ready);
+    }
     for(int c = 0; c < n_chunks && rc == GPP_OK; c++) {
-        rc = launch(c);
-        cudaEventRecord(produced[c], 0);
+        rc = launch(c, compute[c & 1]);
+        cudaEventRecord(produced[c], compute[c & 1]);
     }
     // The caller's array is usually fresh (untouched pages): fault it in now, while the device is busy with block 0,
     // instead of during the copies at the end (first-touch runs at 2-4 GB/s).
@@ -1198,6 +1224,11 @@ int pipelined_download(const std::vector<size_t>& bounds, const std::function<in
     }
     for(int c = std::max(0, n_chunks - 2); c < n_chunks && rc == GPP_OK; c++) rc = finish(c);
     cudaStreamSynchronize(copy_stream);
+    if(overlap_blocks)
+        for(int i = 0; i < 2; i++) {
+            cudaStreamSynchronize(compute[i]);
+            cudaStreamDestroy(compute[i]);
+        }
     for(int c = 0; c < n_chunks; c++) { cudaEventDestroy(produced[c]); cudaEventDestroy(copied[c]); }
     cudaStreamDestroy(copy_stream);
     if(rc == GPP_OK) {
@@ -1215,10 +1246,10 @@ int analyse_pipelined(const gpp_points* bpoints, int nB, int nx, int n_chunks, c
     const int n_rows = nB / nx;
     std::vector<size_t> bounds(n_chunks + 1);
     for(int c = 0; c <= n_chunks; c++) bounds[c] = (size_t) ((long long) n_rows * c / n_chunks) * nx;
-    return pipelined_download(bounds, [&](int c) {
+    return pipelined_download(bounds, [&](int c, cudaStream_t stream) {
         return gpp_optimal_interpolation_device(bpoints, (int) bounds[c], (int) (bounds[c + 1] - bounds[c]), d_bg, d_bvar, obs, structure,
-                                                max_points, allow_extrapolation, d_out, d_var, nullptr);
-    }, d_out, analysis);
+                                                max_points, allow_extrapolation, d_out, d_var, stream);
+    }, d_out, analysis, true);
 }
 }  // namespace
 
@@ -1577,3 +1608,15 @@ int gpp_optimal_interpolation_host(const gpp_points* bpoints, const float* backg
 }
 
 }  // extern "C"
+
+#ifdef OI_STATS
+extern "C" int gpp_debug_oi_stats(unsigned long long* out, int reset) {
+    GPP_CUDA(cudaDeviceSynchronize());
+    GPP_CUDA(cudaMemcpyFromSymbol(out, g_oi_stats, sizeof(unsigned long long) * 4));
+    if(reset) {
+        unsigned long long zero[4] = {0, 0, 0, 0};
+        GPP_CUDA(cudaMemcpyToSymbol(g_oi_stats, zero, sizeof(zero)));
+    }
+    return GPP_OK;
+}
+#endif

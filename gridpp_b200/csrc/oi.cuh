@@ -156,7 +156,8 @@ struct gpp_oi_obs {
 namespace gpp {
 // oi.cu: blocks [bounds[c], bounds[c+1]) of d_out are produced by launch(c) on the default stream and returned to host_out
 // through a pinned staging buffer while later blocks are still being computed.
-int pipelined_download(const std::vector<size_t>& bounds, const std::function<int(int)>& launch, const float* d_out, float* host_out);
+int pipelined_download(const std::vector<size_t>& bounds, const std::function<int(int, cudaStream_t)>& launch, const float* d_out, float* host_out,
+                       bool overlap_blocks);
 // Builds the table from host arrays. `valid[i]` selects the observations that enter the table.
 // Largest number of table observations inside the localization radius of any of the background points
 // [first, first+count) (points with an invalid d_background value are skipped when d_background is given).
