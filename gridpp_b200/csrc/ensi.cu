@@ -447,17 +447,39 @@ extern "C" int gpp_optimal_interpolation_ensi_host(const gpp_points* cbp, const 
         }
         gYhat[i] = mean;
     }
-    // ---- valid members (oi_ensi.cpp:187-201): a full pass over the background, on the device
+    // ---- valid members (oi_ensi.cpp:187-201): a member with an invalid value anywhere in the background is left alone.
+    // Large fields are scanned on the host (threads) so that their upload can be pipelined with the analysis, block by
+    // block; small ones are uploaded at once and scanned on the device.
     DeviceBuffer<float> d_bg, d_out, d_gY;
     DeviceBuffer<int> d_flags;
-    GPP_TRY(d_bg.upload(background, nBE));
+    const int n_chunks = nB >= (1 << 18) ? ENSI_CHUNKS : 1;
+    std::vector<int> flags(nE + 1, 0);
     GPP_TRY(d_flags.alloc(nE + 1 + ENSI_CHUNKS));   // per-member invalid flags, the skipped-point count, the work counters
     GPP_CUDA(cudaMemsetAsync(d_flags.ptr, 0, sizeof(int) * (nE + 1 + ENSI_CHUNKS), 0));
-    GPP_LAUNCH(ensi_invalid_members_kernel, (unsigned) ((nBE + 255) / 256), 256, 0, 0, d_bg.ptr, nBE, nE, d_flags.ptr);
-    std::vector<int> flags(nE + 1);
-    GPP_TRY(d_flags.download(flags.data(), nE + 1));
-    GPP_CUDA(cudaStreamSynchronize(0));
-    trace.lap("H2D + valid-member scan");
+    if(n_chunks > 1) {
+        GPP_TRY(d_bg.alloc(nBE));
+        std::vector<unsigned char> bad((size_t) nE, 0);
+        #pragma omp parallel
+        {
+            std::vector<unsigned char> mine((size_t) nE, 0);
+            #pragma omp for schedule(static) nowait
+            for(long long p = 0; p < (long long) nB; p++) {
+                const float* row = background + (size_t) p * nE;
+                for(int e = 0; e < nE; e++) mine[e] |= (unsigned char) !is_valid(row[e]);
+            }
+            #pragma omp critical
+            for(int e = 0; e < nE; e++) bad[e] |= mine[e];
+        }
+        for(int e = 0; e < nE; e++) flags[e] = bad[e];
+        trace.lap("valid-member scan (host)");
+    }
+    else {
+        GPP_TRY(d_bg.upload(background, nBE));
+        GPP_LAUNCH(ensi_invalid_members_kernel, (unsigned) ((nBE + 255) / 256), 256, 0, 0, d_bg.ptr, nBE, nE, d_flags.ptr);
+        GPP_TRY(d_flags.download(flags.data(), nE + 1));
+        GPP_CUDA(cudaStreamSynchronize(0));
+        trace.lap("H2D + valid-member scan");
+    }
     EnsiParams P;
     std::memset(&P, 0, sizeof(P));
     bool downloaded = false;
@@ -469,7 +491,7 @@ extern "C" int gpp_optimal_interpolation_ensi_host(const gpp_points* cbp, const 
             P.valid_ens[E++] = e;
         }
     GPP_TRY(d_out.alloc(nBE));
-    GPP_CUDA(cudaMemcpyAsync(d_out.ptr, d_bg.ptr, sizeof(float) * nBE, cudaMemcpyDeviceToDevice, 0));   // oi_ensi.cpp:148
+    if(n_chunks == 1) GPP_CUDA(cudaMemcpyAsync(d_out.ptr, d_bg.ptr, sizeof(float) * nBE, cudaMemcpyDeviceToDevice, 0));   // oi_ensi.cpp:148
     if(E > 0) {
         // ---- observation table: only pobs validity is required here (oi_ensi.cpp:232)
         std::vector<char> valid(nS);
@@ -519,7 +541,6 @@ extern "C" int gpp_optimal_interpolation_ensi_host(const gpp_points* cbp, const 
             const unsigned grid = (unsigned) std::max<long long>(1, std::min<long long>(want, (long long) sm_count() * std::max(per_sm, 1)));
             // blocks of points, each returned to the host (through pinned staging) while the next ones are analysed; every
             // block has its own work counter because consecutive blocks overlap on the device
-            const int n_chunks = nB >= (1 << 18) ? ENSI_CHUNKS : 1;
             std::vector<size_t> bounds(n_chunks + 1);
             for(int c = 0; c <= n_chunks; c++) bounds[c] = (size_t) ((long long) nB * c / n_chunks) * nE;
             const int mode = structure_mode(*structure);
@@ -529,6 +550,11 @@ extern "C" int gpp_optimal_interpolation_ensi_host(const gpp_points* cbp, const 
                 Q.first = (int) (bounds[c] / nE);
                 Q.count = (int) ((bounds[c + 1] - bounds[c]) / nE);
                 Q.work_counter = counters + c;
+                if(n_chunks > 1) {   // this block's slice of the background comes in on the stream that analyses it
+                    const size_t n = bounds[c + 1] - bounds[c];
+                    GPP_CUDA(cudaMemcpyAsync(d_bg.ptr + bounds[c], background + bounds[c], sizeof(float) * n, cudaMemcpyHostToDevice, stream));
+                    GPP_CUDA(cudaMemcpyAsync(d_out.ptr + bounds[c], d_bg.ptr + bounds[c], sizeof(float) * n, cudaMemcpyDeviceToDevice, stream));
+                }
                 if(mode == 1) GPP_LAUNCH(ensi_kernel<1>, grid, ENSI_WARPS * 32, smem, stream, Q);
                 else GPP_LAUNCH(ensi_kernel<0>, grid, ENSI_WARPS * 32, smem, stream, Q);
                 return (int) GPP_OK;
@@ -539,14 +565,20 @@ extern "C" int gpp_optimal_interpolation_ensi_host(const gpp_points* cbp, const 
             }
             else GPP_TRY(launch(0, 0));
         }
-        if(trace.on) { cudaStreamSynchronize(0); trace.lap(downloaded ? "kernel + D2H (pipelined)" : "kernel"); }
-        if(!downloaded) GPP_TRY(d_out.download(analysis, nBE));
+        if(trace.on) { cudaStreamSynchronize(0); trace.lap(downloaded ? "H2D + kernel + D2H (pipelined)" : "kernel"); }
+        if(!downloaded) {
+            // nothing was analysed (no valid observation): the analysis is the background (oi_ensi.cpp:148)
+            if(n_chunks > 1) std::memcpy(analysis, background, sizeof(float) * nBE);
+            else GPP_TRY(d_out.download(analysis, nBE));
+        }
         if(num_skipped) GPP_CUDA(cudaMemcpyAsync(num_skipped, d_flags.ptr + nE, sizeof(int), cudaMemcpyDeviceToHost, 0));
         GPP_CUDA(cudaStreamSynchronize(0));   // `obs` and the staging vectors go out of scope after this
         trace.lap("D2H");
         return GPP_OK;
     }
-    GPP_TRY(d_out.download(analysis, nBE));
+    // no valid member: the analysis is the background
+    if(n_chunks > 1) std::memcpy(analysis, background, sizeof(float) * nBE);
+    else GPP_TRY(d_out.download(analysis, nBE));
     GPP_CUDA(cudaStreamSynchronize(0));
     return GPP_OK;
 }

@@ -1240,15 +1240,21 @@ int pipelined_download(const std::vector<size_t>& bounds, const std::function<in
 }  // namespace gpp
 
 namespace {
-// Row blocks of the grid are analysed back to back and returned through the pinned staging buffer.
-int analyse_pipelined(const gpp_points* bpoints, int nB, int nx, int n_chunks, const float* d_bg, const float* d_bvar, const gpp_oi_obs* obs,
-                      const gpp_structure* structure, int max_points, int allow_extrapolation, float* d_out, float* d_var, float* analysis) {
+// Row blocks of the grid go through upload, analysis and download as a pipeline: block c's rows of the background (and
+// of its variance) are copied in on the stream that then analyses them, the two streams alternate, and the results
+// return through the pinned staging buffer. A point reads no background value but its own, so a block needs no halo.
+int analyse_pipelined(const gpp_points* bpoints, int nB, int nx, int n_chunks, const float* background, const float* bvariance, float* d_bg,
+                      float* d_bvar, const gpp_oi_obs* obs, const gpp_structure* structure, int max_points, int allow_extrapolation, float* d_out,
+                      float* d_var, float* analysis) {
     const int n_rows = nB / nx;
     std::vector<size_t> bounds(n_chunks + 1);
     for(int c = 0; c <= n_chunks; c++) bounds[c] = (size_t) ((long long) n_rows * c / n_chunks) * nx;
     return pipelined_download(bounds, [&](int c, cudaStream_t stream) {
-        return gpp_optimal_interpolation_device(bpoints, (int) bounds[c], (int) (bounds[c + 1] - bounds[c]), d_bg, d_bvar, obs, structure,
-                                                max_points, allow_extrapolation, d_out, d_var, stream);
+        const size_t first = bounds[c], count = bounds[c + 1] - bounds[c];
+        GPP_CUDA(cudaMemcpyAsync(d_bg + first, background + first, sizeof(float) * count, cudaMemcpyHostToDevice, stream));
+        if(bvariance) GPP_CUDA(cudaMemcpyAsync(d_bvar + first, bvariance + first, sizeof(float) * count, cudaMemcpyHostToDevice, stream));
+        return gpp_optimal_interpolation_device(bpoints, (int) first, (int) count, d_bg, bvariance ? d_bvar : nullptr, obs, structure, max_points,
+                                                allow_extrapolation, d_out, d_var, stream);
     }, d_out, analysis, true);
 }
 }  // namespace
@@ -1575,17 +1581,17 @@ int gpp_optimal_interpolation_host(const gpp_points* bpoints, const float* backg
     GPP_TRY(gpp_oi_obs_create(opoints, pobs, obs_variance, pbackground, bvariance_at_points, structure, &obs));
     trace.lap("observation table");
     DeviceBuffer<float> d_bg, d_bvar, d_out, d_var;
-    int rc = d_bg.upload(background, nB);
-    if(rc == GPP_OK && bvariance) rc = d_bvar.upload(bvariance, nB);
-    if(rc == GPP_OK) rc = d_out.alloc(nB);
-    if(rc == GPP_OK && analysis_variance) rc = d_var.alloc(nB);
-    if(trace.on) { cudaStreamSynchronize(0); trace.lap("alloc + H2D"); }
-    // Large grids: the analysis goes back in row blocks through a pinned staging buffer while later blocks are still
-    // being analysed (a D2H straight into the caller's pageable array runs at ~5 GB/s and would add ~30 % to the call).
+    // Large grids: row blocks are uploaded, analysed and sent back as a pipeline (the results through a pinned staging
+    // buffer: a D2H straight into the caller's pageable array runs at ~5 GB/s and would add ~30 % to the call).
     const int nx = bpoints->shape_nx;
     const int n_rows = nx > 0 ? nB / nx : 0;
-    const int n_chunks = (rc == GPP_OK && nx > 0 && nB % nx == 0 && nB >= (1 << 21)) ? std::min(4, n_rows) : 1;
-    if(rc == GPP_OK && n_chunks > 1) rc = analyse_pipelined(bpoints, nB, nx, n_chunks, d_bg.ptr, bvariance ? d_bvar.ptr : nullptr, obs, structure,
+    const int n_chunks = (nx > 0 && nB % nx == 0 && nB >= (1 << 21)) ? std::min(4, n_rows) : 1;
+    int rc = n_chunks > 1 ? d_bg.alloc(nB) : d_bg.upload(background, nB);
+    if(rc == GPP_OK && bvariance) rc = n_chunks > 1 ? d_bvar.alloc(nB) : d_bvar.upload(bvariance, nB);
+    if(rc == GPP_OK) rc = d_out.alloc(nB);
+    if(rc == GPP_OK && analysis_variance) rc = d_var.alloc(nB);
+    if(trace.on) { cudaStreamSynchronize(0); trace.lap(n_chunks > 1 ? "alloc" : "alloc + H2D"); }
+    if(rc == GPP_OK && n_chunks > 1) rc = analyse_pipelined(bpoints, nB, nx, n_chunks, background, bvariance, d_bg.ptr, d_bvar.ptr, obs, structure,
                                                             max_points, allow_extrapolation, d_out.ptr, analysis_variance ? d_var.ptr : nullptr,
                                                             analysis);
     else if(rc == GPP_OK) {
@@ -1600,7 +1606,7 @@ int gpp_optimal_interpolation_host(const gpp_points* bpoints, const float* backg
         if(err != cudaSuccess) rc = fail(GPP_ERR_CUDA, "CUDA error %s: %s", cudaGetErrorName(err), cudaGetErrorString(err));
     }
     else cudaStreamSynchronize(0);
-    trace.lap(n_chunks > 1 ? "kernels + D2H (pipelined)" : "D2H");
+    trace.lap(n_chunks > 1 ? "H2D + kernels + D2H (pipelined)" : "D2H");
     gpp_oi_obs_destroy(obs);
     d_bg.release(); d_bvar.release(); d_out.release(); d_var.release();
     trace.lap("free");

@@ -748,3 +748,33 @@ def test_ensi_random_vs_oracle(gpp, orc):
     want = orc.optimal_interpolation_ensi((la, lo, None, None), bgp, (pla, plo, None, None), o, sg, pbgp,
                                           B.make_structure(B.BARNES, 20000.0), 12, B.GEODETIC)
     assert_close(got, want, 1.0, RTOL, "EnSI points geodetic")
+
+
+def test_ensi_pipelined_path_equals_whole_field_path(gpp, orc):
+    """Fields of 2^18 points or more go through the pipelined host path (member scan on the host, per-block upload,
+    overlapping block kernels, staged download); every point is independent, so its result must equal what the
+    small-field path gives on the two halves of the grid, and the oracle on a sample. One member carries a NaN and
+    must come back untouched (oi_ensi.cpp:187-201)."""
+    rng = np.random.default_rng(11)
+    ny, nx, dx, E, S = 520, 520, 500.0, 6, 400
+    assert ny * nx >= 1 << 18 and ny * nx // 2 < 1 << 18
+    y, x = np.meshgrid(np.arange(ny) * dx, np.arange(nx) * dx, indexing="ij")
+    y, x = y.astype(f32), x.astype(f32)
+    py, px = rng.uniform(0, ny * dx, S).astype(f32), rng.uniform(0, nx * dx, S).astype(f32)
+    bg = (rng.normal(size=(ny, nx, 1)) + rng.normal(size=(ny, nx, E))).astype(f32)
+    bg[400, 17, 3] = np.nan
+    pbg = rng.normal(size=(S, E)).astype(f32)
+    obs, sig = rng.normal(size=S).astype(f32), np.full(S, 0.6, f32)
+    points, s = gpp.Points(py, px, type=gpp.Cartesian), gpp.BarnesStructure(12000)
+    whole = gpp.optimal_interpolation_ensi(gpp.Grid(y, x, type=gpp.Cartesian), bg, points, obs, sig, pbg, s, 12)
+    assert_bit_exact(whole[:, :, 3], bg[:, :, 3], "member with a missing value is left untouched")
+    h = ny // 2
+    # the lower half holds the missing value, so it also runs with five valid members
+    lower = gpp.optimal_interpolation_ensi(gpp.Grid(y[h:], x[h:], type=gpp.Cartesian), bg[h:], points, obs, sig, pbg, s, 12)
+    keep = [e for e in range(E) if e != 3]
+    assert_close(whole[h:][:, :, keep], lower[:, :, keep], 1.0, 1e-6, "pipelined vs whole-field path")
+    pick = rng.choice(h * nx, 300, replace=False)
+    pick[0] = (400 - h) * nx + 17   # the sample must see the missing value too, or it would analyse six members
+    want = orc.optimal_interpolation_ensi((y[h:].ravel()[pick], x[h:].ravel()[pick], None, None), bg[h:].reshape(-1, E)[pick], (py, px, None, None),
+                                          obs, sig, pbg, B.make_structure(B.BARNES, 12000.0), 12, B.CARTESIAN)
+    assert_close(whole[h:].reshape(-1, E)[pick][:, keep], want[:, keep], 1.0, RTOL, "pipelined path vs oracle")
