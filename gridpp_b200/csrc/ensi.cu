@@ -56,13 +56,13 @@ struct EnsiSmem {
     double* V;                    // eigenvectors in columns; kept from one point to the next (warm start)
     double *rinv, *dd;            // [k]
     double *b, *t, *lam, *w, *sc, *X;   // [E]
-    double *cs, *sn;              // [E / 2 + 1]
+    double2* cs;                  // [E / 2 + 1] (cos, sin) of the rotations of a round
     int* pos;                     // [32 * ENSI_NSLOT]
     int* spos;                    // [k]
     int* pp;                      // [E / 2 + 1]
     float* sval;                  // [E]
 
-    enum { O_KEY, O_Y, O_V, O_RINV, O_DD, O_B, O_T, O_LAM, O_W, O_SC, O_X, O_CS, O_SN, O_POS, O_SPOS, O_PP, O_SVAL, O_COUNT };
+    enum { O_KEY, O_Y, O_V, O_RINV, O_DD, O_B, O_T, O_LAM, O_W, O_SC, O_X, O_CS, O_POS, O_SPOS, O_PP, O_SVAL, O_COUNT };
 
     // fills off[O_COUNT] and returns the bytes per warp
     static size_t layout(int* off, int E, int kcap, int ld) {
@@ -77,8 +77,7 @@ struct EnsiSmem {
         take(O_DD, sizeof(double) * kcap);
         const int per_member[6] = {O_B, O_T, O_LAM, O_W, O_SC, O_X};
         for(int i = 0; i < 6; i++) take(per_member[i], sizeof(double) * Ee);
-        take(O_CS, sizeof(double) * h);
-        take(O_SN, sizeof(double) * h);
+        take(O_CS, sizeof(double2) * h);
         take(O_POS, sizeof(int) * 32 * ENSI_NSLOT);
         take(O_SPOS, sizeof(int) * kcap);
         take(O_PP, sizeof(int) * h);
@@ -100,8 +99,7 @@ struct EnsiSmem {
         w = reinterpret_cast<double*>(base + off[O_W]);
         sc = reinterpret_cast<double*>(base + off[O_SC]);
         X = reinterpret_cast<double*>(base + off[O_X]);
-        cs = reinterpret_cast<double*>(base + off[O_CS]);
-        sn = reinterpret_cast<double*>(base + off[O_SN]);
+        cs = reinterpret_cast<double2*>(base + off[O_CS]);
         pos = reinterpret_cast<int*>(base + off[O_POS]);
         spos = reinterpret_cast<int*>(base + off[O_SPOS]);
         pp = reinterpret_cast<int*>(base + off[O_PP]);
@@ -128,15 +126,18 @@ __global__ void ensi_invalid_members_kernel(const float* __restrict__ background
 #ifndef ENSI_MINB
 #define ENSI_MINB 10
 #endif
-template <int SMODE>
+// EC > 0: the number of valid members is the compile-time constant EC (loops over the members unroll without guards, the
+// strides of the shared matrices are immediates); EC == 0: any number up to ENSI_EMAX.
+template <int SMODE, int EC>
 __global__ void __launch_bounds__(ENSI_WARPS * 32, ENSI_MINB) ensi_kernel(const __grid_constant__ EnsiParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     EnsiSmem S;
     S.bind(smem_raw + (size_t) (threadIdx.x >> 5) * P.smem_per_warp, P.off, P.E, P.ld);
-    const int LD = P.ld;
+    const int LD = EC > 0 ? (EC | 1) : P.ld;
     const int lane = (int) lane_id();
     const CandBuf cb = {S.key, S.pos};
-    const int E = P.E;
+    const int E = EC > 0 ? EC : P.E;
+    constexpr int EU = EC > 0 ? EC : ENSI_EMAX;   // trip count of the unrolled member loops
     const int Eeven = E + (E & 1), m = Eeven - 1;   // round-robin schedule over an even number of indices
     const int H = Eeven / 2;                        // rotations per round
 
@@ -196,17 +197,17 @@ __global__ void __launch_bounds__(ENSI_WARPS * 32, ENSI_MINB) ensi_kernel(const 
         // ---- Pinv = C * lY + diag * I, C = lY' Rinv (oi_ensi.cpp:379-385), row `lane`; b = C (obs - yhat) (:428-437)
         double lYe = 0.0;   // the clamp's lY[e]: a LINEAR index into the column-major k x E matrix (oi_ensi.cpp:523-524)
         {
-            double acc[ENSI_EMAX];
+            double acc[EU];
             #pragma unroll
-            for(int f = 0; f < ENSI_EMAX; f++) acc[f] = 0.0;
+            for(int f = 0; f < EU; f++) acc[f] = 0.0;
             double b = 0.0;
             if(lane < E) {
                 for(int i = 0; i < k; i++) {
                     const double c = S.Y[i * LD + lane] * S.rinv[i];
                     b = fma(c, S.dd[i], b);
                     #pragma unroll
-                    for(int f = 0; f < ENSI_EMAX; f++)
-                        if(f < E) acc[f] = fma(c, S.Y[i * LD + f], acc[f]);
+                    for(int f = 0; f < EU; f++)
+                        if(EC > 0 || f < E) acc[f] = fma(c, S.Y[i * LD + f], acc[f]);
                 }
                 S.b[lane] = b;
                 lYe = S.Y[(lane % k) * LD + (lane / k)];
@@ -214,7 +215,7 @@ __global__ void __launch_bounds__(ENSI_WARPS * 32, ENSI_MINB) ensi_kernel(const 
             __syncwarp();   // lY is dead from here on: A and T take its place
             const double diag = (double) (float) (E - 1);   // oi_ensi.cpp:383 with delta = 1
             #pragma unroll
-            for(int f = 0; f < ENSI_EMAX; f++)
+            for(int f = 0; f < EU; f++)
                 if(f == lane) acc[f] += diag;
             ENSI_COUNT(0, 1);
             ENSI_COUNT(3, warm ? 1 : 0);
@@ -223,8 +224,8 @@ __global__ void __launch_bounds__(ENSI_WARPS * 32, ENSI_MINB) ensi_kernel(const 
 #endif
             if(!warm) {
                 #pragma unroll
-                for(int f = 0; f < ENSI_EMAX; f++)
-                    if(f < E && lane < E) {
+                for(int f = 0; f < EU; f++)
+                    if((EC > 0 || f < E) && lane < E) {
                         S.A[lane * LD + f] = acc[f];
                         S.V[lane * LD + f] = f == lane ? 1.0 : 0.0;
                     }
@@ -235,20 +236,20 @@ __global__ void __launch_bounds__(ENSI_WARPS * 32, ENSI_MINB) ensi_kernel(const 
                     for(int j = 0; j < E; j++) {   // T = Pinv V, row `lane`
                         double t = 0.0;
                         #pragma unroll
-                        for(int f = 0; f < ENSI_EMAX; f++)
-                            if(f < E) t = fma(acc[f], S.V[f * LD + j], t);
+                        for(int f = 0; f < EU; f++)
+                            if(EC > 0 || f < E) t = fma(acc[f], S.V[f * LD + j], t);
                         S.T[lane * LD + j] = t;
                     }
                 __syncwarp();
                 if(lane < E) {
                     #pragma unroll
-                    for(int f = 0; f < ENSI_EMAX; f++)
-                        if(f < E) acc[f] = S.V[f * LD + lane];   // column `lane` of V
+                    for(int f = 0; f < EU; f++)
+                        if(EC > 0 || f < E) acc[f] = S.V[f * LD + lane];   // column `lane` of V
                     for(int j = 0; j < E; j++) {   // A = V' T, row `lane`
                         double t = 0.0;
                         #pragma unroll
-                        for(int f = 0; f < ENSI_EMAX; f++)
-                            if(f < E) t = fma(acc[f], S.T[f * LD + j], t);
+                        for(int f = 0; f < EU; f++)
+                            if(EC > 0 || f < E) t = fma(acc[f], S.T[f * LD + j], t);
                         S.A[lane * LD + j] = t;
                     }
                 }
@@ -304,7 +305,7 @@ __global__ void __launch_bounds__(ENSI_WARPS * 32, ENSI_MINB) ensi_kernel(const 
                 ENSI_COUNT(2, nrot);
                 if(rot) {
                     const int slot = __popc(rmask & ((1u << lane) - 1u));
-                    S.pp[slot] = p | (q << 8); S.cs[slot] = c; S.sn[slot] = s;
+                    S.pp[slot] = p | (q << 8); S.cs[slot] = make_double2(c, s);
                 }
                 __syncwarp();
                 if(lane < E)   // A <- J' A: rows p, q of A, column `lane`
@@ -312,7 +313,8 @@ __global__ void __launch_bounds__(ENSI_WARPS * 32, ENSI_MINB) ensi_kernel(const 
                         const int pq = S.pp[t];
                         double* rp = S.A + (pq & 255) * LD + lane;
                         double* rq = S.A + (pq >> 8) * LD + lane;
-                        const double c = S.cs[t], s = S.sn[t];
+                        const double2 rot2 = S.cs[t];
+                        const double c = rot2.x, s = rot2.y;
                         const double ap = *rp, aq = *rq;
                         *rp = c * ap - s * aq;
                         *rq = s * ap + c * aq;
@@ -323,7 +325,8 @@ __global__ void __launch_bounds__(ENSI_WARPS * 32, ENSI_MINB) ensi_kernel(const 
                     double* vrow = S.V + lane * LD;
                     for(int t = 0; t < nrot; t++) {
                         const int pq = S.pp[t], p = pq & 255, q = pq >> 8;
-                        const double c = S.cs[t], s = S.sn[t];
+                        const double2 rot2 = S.cs[t];
+                        const double c = rot2.x, s = rot2.y;
                         const double ap = arow[p], aq = arow[q];
                         arow[p] = c * ap - s * aq;
                         arow[q] = s * ap + c * aq;
@@ -371,14 +374,14 @@ __global__ void __launch_bounds__(ENSI_WARPS * 32, ENSI_MINB) ensi_kernel(const 
             // analysis for member `lane`: total += X(k) * W(k, e) accumulated in FLOAT (oi_ensi.cpp:506-512),
             // W(k, e) = sum_f V(k,f) sqrt((E-1)/lam_f) V(e,f) + w(k)  (oi_ensi.cpp:419-444)
             float tot = 0.f;
-            double vs[ENSI_EMAX];   // row `lane` of V scaled by sqrt((E-1) / lambda)
+            double vs[EU];   // row `lane` of V scaled by sqrt((E-1) / lambda)
             #pragma unroll
-            for(int f = 0; f < ENSI_EMAX; f++) vs[f] = f < E ? S.V[lane * LD + f] * S.sc[f] : 0.0;
+            for(int f = 0; f < EU; f++) vs[f] = (EC > 0 || f < E) ? S.V[lane * LD + f] * S.sc[f] : 0.0;
             for(int kk = 0; kk < E; kk++) {
                 double wke = 0.0;
                 #pragma unroll
-                for(int f = 0; f < ENSI_EMAX; f++)
-                    if(f < E) wke = fma(S.V[kk * LD + f], vs[f], wke);
+                for(int f = 0; f < EU; f++)
+                    if(EC > 0 || f < E) wke = fma(S.V[kk * LD + f], vs[f], wke);
                 wke += S.w[kk];
                 tot = (float) ((double) tot + S.X[kk] * wke);
             }
@@ -532,18 +535,23 @@ extern "C" int gpp_optimal_interpolation_ensi_host(const gpp_points* cbp, const 
             P.ld = E | 1;
             P.smem_per_warp = (int) EnsiSmem::layout(P.off, E, kcap, P.ld);
             const size_t smem = (size_t) P.smem_per_warp * ENSI_WARPS;
-            GPP_CUDA(cudaFuncSetAttribute(ensi_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-            GPP_CUDA(cudaFuncSetAttribute(ensi_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+            const int mode = structure_mode(*structure);
+            void (*kernel)(EnsiParams) = nullptr;
+            switch(E) {   // the common ensemble sizes get their own instantiation
+                case 10: kernel = mode == 1 ? ensi_kernel<1, 10> : ensi_kernel<0, 10>; break;
+                case 20: kernel = mode == 1 ? ensi_kernel<1, 20> : ensi_kernel<0, 20>; break;
+                case 30: kernel = mode == 1 ? ensi_kernel<1, 30> : ensi_kernel<0, 30>; break;
+                default: kernel = mode == 1 ? ensi_kernel<1, 0> : ensi_kernel<0, 0>; break;
+            }
+            GPP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
             const long long want = ((long long) nB + ENSI_WARPS - 1) / ENSI_WARPS;
             int per_sm = 1;   // what actually fits (registers and shared memory): one wave of resident CTAs
-            if(structure_mode(*structure) == 1) GPP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ensi_kernel<1>, ENSI_WARPS * 32, smem));
-            else GPP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ensi_kernel<0>, ENSI_WARPS * 32, smem));
+            GPP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, ENSI_WARPS * 32, smem));
             const unsigned grid = (unsigned) std::max<long long>(1, std::min<long long>(want, (long long) sm_count() * std::max(per_sm, 1)));
             // blocks of points, each returned to the host (through pinned staging) while the next ones are analysed; every
             // block has its own work counter because consecutive blocks overlap on the device
             std::vector<size_t> bounds(n_chunks + 1);
             for(int c = 0; c <= n_chunks; c++) bounds[c] = (size_t) ((long long) nB * c / n_chunks) * nE;
-            const int mode = structure_mode(*structure);
             int* counters = d_flags.ptr + nE + 1;
             auto launch = [&](int c, cudaStream_t stream) {
                 EnsiParams Q = P;
@@ -555,8 +563,7 @@ extern "C" int gpp_optimal_interpolation_ensi_host(const gpp_points* cbp, const 
                     GPP_CUDA(cudaMemcpyAsync(d_bg.ptr + bounds[c], background + bounds[c], sizeof(float) * n, cudaMemcpyHostToDevice, stream));
                     GPP_CUDA(cudaMemcpyAsync(d_out.ptr + bounds[c], d_bg.ptr + bounds[c], sizeof(float) * n, cudaMemcpyDeviceToDevice, stream));
                 }
-                if(mode == 1) GPP_LAUNCH(ensi_kernel<1>, grid, ENSI_WARPS * 32, smem, stream, Q);
-                else GPP_LAUNCH(ensi_kernel<0>, grid, ENSI_WARPS * 32, smem, stream, Q);
+                GPP_LAUNCH(kernel, grid, ENSI_WARPS * 32, smem, stream, Q);
                 return (int) GPP_OK;
             };
             if(n_chunks > 1) {

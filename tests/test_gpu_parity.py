@@ -739,6 +739,15 @@ def test_ensi_random_vs_oracle(gpp, orc):
         want = orc.optimal_interpolation_ensi((y, x, None, None), bg, (py, px, None, None), obs, sig, pbg,
                                               B.make_structure(B.BARNES, 10000.0), mp, B.CARTESIAN, allow_extrapolation=extr)
         assert_close(got.reshape(-1, E), want, 2.0, RTOL, "EnSI mp=%d extr=%s" % (mp, extr))
+    # the other ensemble sizes with their own kernel instantiation (10, 30) and the largest generic one (31)
+    for E2 in (10, 30, 31):
+        sub = (slice(0, 12), slice(0, 15))
+        bg2 = (rng.normal(size=(12, 15, 1)) * 2 + rng.normal(size=(12, 15, E2))).astype(f32)
+        pbg2 = rng.normal(size=(S, E2)).astype(f32)
+        got = gpp.optimal_interpolation_ensi(gpp.Grid(y[sub], x[sub], type=gpp.Cartesian), bg2, points, obs, sig, pbg2, gpp.BarnesStructure(10000), 40)
+        want = orc.optimal_interpolation_ensi((y[sub], x[sub], None, None), bg2, (py, px, None, None), obs, sig, pbg2,
+                                              B.make_structure(B.BARNES, 10000.0), 40, B.CARTESIAN)
+        assert_close(got.reshape(-1, E2), want, 2.0, RTOL, "EnSI %d members" % E2)
     # Points overload, 7 members (odd: exercises the padded rotation schedule), Geodetic
     la, lo = rng.uniform(59, 60, 300).astype(f32), rng.uniform(10, 12, 300).astype(f32)
     pla, plo = rng.uniform(59, 60, 150).astype(f32), rng.uniform(10, 12, 150).astype(f32)
