@@ -12,6 +12,8 @@
 // The reference runs this loop serially (its omp pragma is disabled, oi_ensi.cpp:203-206).
 #include "oi.cuh"
 
+#include <omp.h>
+
 #include <algorithm>
 #include <cstring>
 
@@ -462,7 +464,9 @@ extern "C" int gpp_optimal_interpolation_ensi_host(const gpp_points* cbp, const 
     if(n_chunks > 1) {
         GPP_TRY(d_bg.alloc(nBE));
         std::vector<unsigned char> bad((size_t) nE, 0);
-        #pragma omp parallel
+        // (an explicit team size: launchers such as torchrun export OMP_NUM_THREADS=1)
+        const int scan_threads = std::max(1, std::min(8, omp_get_num_procs()));
+        #pragma omp parallel num_threads(scan_threads)
         {
             std::vector<unsigned char> mine((size_t) nE, 0);
             #pragma omp for schedule(static) nowait
