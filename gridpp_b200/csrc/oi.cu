@@ -102,7 +102,7 @@ struct WarpState {
 
 // A solved system kept for reuse: the set (canonical original indices), z = (P+R)^-1 d and the innovation extremes.
 #ifndef OI_LRU
-#define OI_LRU 4
+#define OI_LRU 8
 #endif
 #ifndef OI_RPC
 #define OI_RPC 16
@@ -116,6 +116,11 @@ __device__ unsigned long long g_oi_stats[4];
 #endif
 constexpr int LRU_ENTRIES = OI_LRU;
 constexpr int RUNS_PER_CHUNK = OI_RPC;   // consecutive runs (tiles) handled by one warp, so that the cache sees neighbours
+#ifndef OI_CHUNK_TY
+#define OI_CHUNK_TY 4
+#endif
+constexpr int CHUNK_TY = OI_CHUNK_TY, CHUNK_TX = RUNS_PER_CHUNK / CHUNK_TY;   // shape of a chunk in tiles (grids)
+static_assert(CHUNK_TY * CHUNK_TX == RUNS_PER_CHUNK, "OI_CHUNK_TY must divide OI_RPC");
 struct LruEntry {
     double z[32];
     double dmax, dmin;
@@ -352,7 +357,12 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 2) oi_fast_kernel(const __
     const int tiles_x = P.tile_nx > 0 ? (P.tile_nx + 3) / 4 : 0;
     const int rows = P.tile_nx > 0 ? P.count / P.tile_nx : 0;
     const int n_runs = P.tile_nx > 0 ? tiles_x * ((rows + 3) / 4) : (P.count + RUN - 1) / RUN;
-    const int n_chunks = (n_runs + RUNS_PER_CHUNK - 1) / RUNS_PER_CHUNK;
+    // tile mode: a chunk is a block of CHUNK_TY x CHUNK_TX tiles walked in serpentine order. The region over which one
+    // observation set is selected is a few points across (C3: ~30 points), so the squarer the chunk, the fewer regions
+    // are cut by a chunk edge and solved again by another warp.
+    const int tiles_y = (rows + 3) / 4;
+    const int chunks_x = (tiles_x + CHUNK_TX - 1) / CHUNK_TX;
+    const int n_chunks = P.tile_nx > 0 ? chunks_x * ((tiles_y + CHUNK_TY - 1) / CHUNK_TY) : (n_runs + RUNS_PER_CHUNK - 1) / RUNS_PER_CHUNK;
     // chunks are handed out dynamically: their cost varies with how often the selection changes, and a static split
     // of a few chunks per warp leaves a long tail
     for(;;) {
@@ -360,11 +370,15 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 2) oi_fast_kernel(const __
     if(lane == 0) chunk = atomicAdd(P.work_counter, 1);
     chunk = __shfl_sync(0xffffffffu, chunk, 0);
     if(chunk >= n_chunks) break;
-    for(int run = chunk * RUNS_PER_CHUNK; run < min((chunk + 1) * RUNS_PER_CHUNK, n_runs); run++) {
+    for(int j_run = 0; j_run < RUNS_PER_CHUNK; j_run++) {
         // ---- the run's points (offsets into the range), and a bounding sphere
         int npts, my_it = 0;
+        const int run = chunk * RUNS_PER_CHUNK + j_run;
         if(P.tile_nx > 0) {
-            const int ty = run / tiles_x, tx = run - ty * tiles_x;
+            const int cy = chunk / chunks_x, cx = chunk - cy * chunks_x;
+            const int tyy = j_run / CHUNK_TX, txx = j_run - tyy * CHUNK_TX;
+            const int ty = cy * CHUNK_TY + tyy, tx = cx * CHUNK_TX + ((tyy & 1) ? CHUNK_TX - 1 - txx : txx);
+            if(ty >= tiles_y || tx >= tiles_x) continue;
             const int h = min(4, rows - 4 * ty), wdt = min(4, P.tile_nx - 4 * tx);
             npts = h * wdt;
             if(lane < npts) {
@@ -373,6 +387,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 2) oi_fast_kernel(const __
             }
         }
         else {
+            if(run >= n_runs) break;
             npts = min(RUN, P.count - run * RUN);
             my_it = run * RUN + lane;
         }
@@ -1384,7 +1399,8 @@ int gpp_optimal_interpolation_device(const gpp_points* cbp, int first, int count
         // whole rows of a known grid -> 4 x 4 tiles
         P.tile_nx = (bp->shape_nx > 0 && first % bp->shape_nx == 0 && count % bp->shape_nx == 0) ? bp->shape_nx : 0;
         const long long runs = P.tile_nx > 0 ? (long long) ((P.tile_nx + 3) / 4) * ((count / P.tile_nx + 3) / 4) : ((long long) count + RUN - 1) / RUN;
-        const long long chunks = (runs + RUNS_PER_CHUNK - 1) / RUNS_PER_CHUNK;
+        const long long chunks = P.tile_nx > 0 ? (long long) (((P.tile_nx + 3) / 4 + CHUNK_TX - 1) / CHUNK_TX) * (((count / P.tile_nx + 3) / 4 + CHUNK_TY - 1) / CHUNK_TY)
+                                               : (runs + RUNS_PER_CHUNK - 1) / RUNS_PER_CHUNK;
         const long long want = (chunks + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
         const unsigned grid = (unsigned) std::max<long long>(1, std::min<long long>(want, (long long) sms * 2));   // 2 resident CTAs per SM
         unsigned char* lru = nullptr;
