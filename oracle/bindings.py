@@ -206,7 +206,7 @@ class CpuLib:
 
     def optimal_interpolation_spatial(self, bpts, background, opts, pobs, pratios, pbackground, stype, sgrid, h, v, w, min_rho,
                                       max_points, ctype, allow_extrapolation=True, want_variance=False):
-        """optimal_interpolation_full with <Family>Structure(Grid, h, v, w, min_rho) (compiled reference only)."""
+        """optimal_interpolation_full with <Family>Structure(Grid, h, v, w, min_rho); both checkers export it."""
         bl, bo, be, bf = (_f(a).ravel() if a is not None else None for a in bpts)
         pl, po, pe, pf = (_f(a).ravel() if a is not None else None for a in opts)
         nB, nS = bl.size, pl.size

@@ -587,13 +587,18 @@ static int cmp_cand(const void* a, const void* b) {
     return (x->index > y->index) - (x->index < y->index);
 }
 
-/* oi.cpp:138-341. bvariance / bvariance_at_points may be NULL (= 1, as set by oi.cpp:123-132). */
-int orc_optimal_interpolation(const float* blats, const float* blons, const float* belevs, const float* blafs, int nB,
-                              const float* background, const float* bvariance, const float* plats, const float* plons,
-                              const float* pelevs, const float* plafs, int nS, int type, const float* pobs,
-                              const float* obs_variance, const float* pbackground, const float* bvariance_at_points,
-                              const orc_structure* s, int max_points, int allow_extrapolation, float* analysis,
-                              float* analysis_variance, double* seconds) {
+/* oi.cpp:138-341. bvariance / bvariance_at_points may be NULL (= 1, as set by oi.cpp:123-132).
+ * Spatially varying structure functions (<Family>Structure(Grid, h, v, w, min_rho), structure.cpp:168-184 and the Soar
+ * :342, Toar :492, Powerlaw :643, Linear :790 siblings): bterm / oterm hold, per background point and per observation,
+ * the term with the scales of the point's nearest node of the scale grid. corr(p1, p2) then uses the term of p1
+ * (structure.cpp:188-212), so the background correlations use the grid point's scales and row i of P uses those of
+ * observation i; the localization radius is that of the grid point (oi.cpp:229 -> structure.cpp:271-279). */
+static int oi_core(const float* blats, const float* blons, const float* belevs, const float* blafs, int nB,
+                   const float* background, const float* bvariance, const float* plats, const float* plons,
+                   const float* pelevs, const float* plafs, int nS, int type, const float* pobs,
+                   const float* obs_variance, const float* pbackground, const float* bvariance_at_points,
+                   const orc_structure* s, const orc_term* bterm, const orc_term* oterm, int max_points, int allow_extrapolation,
+                   float* analysis, float* analysis_variance, double* seconds) {
     if(max_points < 0) FAIL(1, "max_points must be >= 0"); /* oi.cpp:152 */
     pts_t bp, op;
     int rc = pts_make(&bp, blats, blons, belevs, blafs, nB, type);
@@ -610,7 +615,10 @@ int orc_optimal_interpolation(const float* blats, const float* blons, const floa
     float* pratios = malloc(sizeof(float) * (size_t) nS);
     for(int i = 0; i < nS; i++) pratios[i] = obs_variance[i] / (bvariance_at_points ? bvariance_at_points[i] : 1.0f); /* :192-195 */
     cells_t cells;
-    float R = structure_loc_dist(s);
+    float R = bterm ? 0.f : structure_loc_dist(s);
+    if(bterm)
+        for(int y = 0; y < nB; y++)
+            if(bterm[y].loc_dist > R) R = bterm[y].loc_dist;
     cells_build(&cells, &op, R > 0 ? 0.5 * R : 0);
 
     double t0 = now_seconds();
@@ -624,7 +632,7 @@ int orc_optimal_interpolation(const float* blats, const float* blons, const floa
         for(int y = 0; y < nB; y++) {
             if(!is_valid(background[y])) continue; /* oi.cpp:223 */
             pt_t p1 = {bp.x[y], bp.y[y], bp.z[y], bp.elev[y], bp.laf[y]};
-            float localizationRadius = structure_loc_dist(s); /* oi.cpp:229 */
+            float localizationRadius = bterm ? bterm[y].loc_dist : structure_loc_dist(s); /* oi.cpp:229 */
             int n0 = radius_query(&op, &cells, p1.x, p1.y, p1.z, localizationRadius, 1, &nb, &nb_cap); /* :233 */
             if(n0 == 0) continue;
             if(n0 > cand_cap) { cand_cap = 2 * n0; cand = realloc(cand, sizeof(cand_t) * (size_t) cand_cap); }
@@ -632,7 +640,7 @@ int orc_optimal_interpolation(const float* blats, const float* blons, const floa
             for(int i = 0; i < n0; i++) { /* oi.cpp:244-258 */
                 int index = nb[i];
                 pt_t p2 = {op.x[index], op.y[index], op.z[index], op.elev[index], op.laf[index]};
-                float rho = structure_corr_background(s, p1, p2);
+                float rho = bterm ? term_corr(&bterm[y], p1, p2) : structure_corr_background(s, p1, p2);
                 if(is_valid(pobs[index]) && is_valid(pbackground[index]) && rho > 0) {
                     cand[nc].rho = rho; cand[nc].pos = i; cand[nc].index = index; nc++;
                 }
@@ -656,7 +664,7 @@ int orc_optimal_interpolation(const float* blats, const float* blons, const floa
                 for(int j = 0; j < lS; j++) {
                     int index_j = cand[j].index;
                     pt_t pj = {op.x[index_j], op.y[index_j], op.z[index_j], op.elev[index_j], op.laf[index_j]};
-                    lP[i + j * lS] = structure_corr(s, pi, pj);
+                    lP[i + j * lS] = oterm ? term_corr(&oterm[index], pi, pj) : structure_corr(s, pi, pj);
                 }
                 lP[i + i * lS] += (double) pratios[index];
             }
@@ -694,6 +702,62 @@ int orc_optimal_interpolation(const float* blats, const float* blons, const floa
     pts_free(&bp);
     pts_free(&op);
     return 0;
+}
+
+int orc_optimal_interpolation(const float* blats, const float* blons, const float* belevs, const float* blafs, int nB,
+                              const float* background, const float* bvariance, const float* plats, const float* plons,
+                              const float* pelevs, const float* plafs, int nS, int type, const float* pobs,
+                              const float* obs_variance, const float* pbackground, const float* bvariance_at_points,
+                              const orc_structure* s, int max_points, int allow_extrapolation, float* analysis,
+                              float* analysis_variance, double* seconds) {
+    return oi_core(blats, blons, belevs, blafs, nB, background, bvariance, plats, plons, pelevs, plafs, nS, type, pobs, obs_variance,
+                   pbackground, bvariance_at_points, s, NULL, NULL, max_points, allow_extrapolation, analysis, analysis_variance, seconds);
+}
+
+/* The term a spatially varying structure function uses at (lat, lon): the scales of the nearest node of its grid
+ * (structure.cpp:189-199; Grid::get_nearest_neighbour, grid.cpp:76-82; ties resolve to the lowest node index here),
+ * with localization_distance(h) of that node (structure.cpp:280-282 and siblings). */
+static int spatial_terms(orc_term* out, const float* lats, const float* lons, int n, int type, const pts_t* nodes, int stype,
+                         const float* h, const float* v, const float* w, float min_rho) {
+    int err = 0;
+    #pragma omp parallel for
+    for(int i = 0; i < n; i++) {
+        float x, y, z;
+        int node = 0;
+        if(convert_one(lats[i], lons[i], type, &x, &y, &z) || !closest_query(nodes, x, y, z, 1, 1, &node)) { err = 1; continue; }
+        out[i].type = stype;
+        out[i].h = h[node]; out[i].v = v[node]; out[i].w = w[node];
+        out[i].min_rho = min_rho;
+        out[i].loc_dist = term_loc_dist(&out[i]);
+    }
+    if(err) FAIL(1, "Invalid coords or empty scale grid");
+    return 0;
+}
+
+/* optimal_interpolation_full(Points...) (oi.cpp:138-341) with unit background variances and a spatially varying
+ * structure function: h, v, w on the gny x gnx nodes (glats, glons) of its grid. Same flat signature as
+ * ref_optimal_interpolation_spatial in ref_capi.cpp. */
+int orc_optimal_interpolation_spatial(const float* blats, const float* blons, const float* belevs, const float* blafs, int nB,
+                                      const float* background, const float* plats, const float* plons, const float* pelevs,
+                                      const float* plafs, int nS, int type, const float* pobs, const float* obs_variance,
+                                      const float* pbackground, int stype, const float* glats, const float* glons, int gny, int gnx,
+                                      const float* h, const float* v, const float* w, float min_rho, int max_points,
+                                      int allow_extrapolation, float* analysis, float* analysis_variance) {
+    if(stype == CRESSMAN || stype < BARNES || stype > LINEAR) FAIL(1, "structure function type has no spatially varying form");
+    pts_t nodes;
+    int rc = pts_make(&nodes, glats, glons, NULL, NULL, gny * gnx, type);
+    if(rc) return rc;
+    orc_term* bterm = malloc(sizeof(orc_term) * (size_t) (nB > 0 ? nB : 1));
+    orc_term* oterm = malloc(sizeof(orc_term) * (size_t) (nS > 0 ? nS : 1));
+    rc = spatial_terms(bterm, blats, blons, nB, type, &nodes, stype, h, v, w, min_rho);
+    if(!rc) rc = spatial_terms(oterm, plats, plons, nS, type, &nodes, stype, h, v, w, min_rho);
+    if(!rc)
+        rc = oi_core(blats, blons, belevs, blafs, nB, background, NULL, plats, plons, pelevs, plafs, nS, type, pobs, obs_variance, pbackground,
+                     NULL, NULL, bterm, oterm, max_points, allow_extrapolation, analysis, analysis_variance, NULL);
+    free(bterm);
+    free(oterm);
+    pts_free(&nodes);
+    return rc;
 }
 
 /* util.cpp:19-43 (Mean branch of calc_statistic): float accumulation */

@@ -350,3 +350,52 @@ def test_live_against_reference(orc, ref):
         for stt in (B.MEAN, B.SUM, B.COUNT, B.MIN, B.MAX):
             assert_bit_exact(ref.neighbourhood(f, hw, stt), orc.neighbourhood(f, hw, stt))
         assert_bit_exact(ref.neighbourhood_quantile_fast(f, 0.3, hw, np.linspace(0, 1, 7)), orc.neighbourhood_quantile_fast(f, 0.3, hw, np.linspace(0, 1, 7)))
+
+
+def test_golden_spatially_varying_structures(orc):
+    """<Family>Structure(Grid, h, v, w, min_rho) (structure.cpp:168-184, :342, :492, :643, :790) through
+    optimal_interpolation_full: the C restatement against the fixtures generated from the compiled reference
+    (tests/golden/make_golden_spatial.py). The metric is the one of the GPU test: with Soar / Toar and elevations the
+    systems are nearly singular at a few grid points, so the scale is the field's largest magnitude and at most 3 of the
+    1440 points may exceed 1e-5 (none 1e-3)."""
+    g = golden("oi_spatial_structure")
+    for case in g["cases"]:
+        name, stype, elev, mp, extr, min_rho = str(case).split(",")
+        stype, elev, mp, extr, min_rho = int(stype), int(elev), int(mp), int(extr), float(min_rho)
+        bpts = (g["y"], g["x"], g["belev"] if elev else None, g["blaf"] if elev else None)
+        opts = (g["py"], g["px"], g["pelev"] if elev else None, g["plaf"] if elev else None)
+        out, var = orc.optimal_interpolation_spatial(bpts, g["background"], opts, g["pobs"], g["pratios"], g["pbackground"], stype,
+                                                     (g["gy"], g["gx"]), g["h"], g["v"], g["w"], min_rho, mp, B.CARTESIAN,
+                                                     allow_extrapolation=bool(extr), want_variance=True)
+        key = "%s__elev%d__mp%d" % (name, elev, mp)
+        wa, wv = g[key + "__analysis"].ravel(), g[key + "__variance"].ravel()
+        sa, sv = max(2.0, float(np.abs(wa).max())), max(1.0, float(np.abs(wv).max()))
+        assert_close(out, wa, sa, 1e-5, "oracle spatial " + key, allow_outliers=3)
+        assert_close(out, wa, sa, 1e-3, "oracle spatial (loose) " + key)
+        assert_close(var, wv, sv, 1e-5, "oracle spatial variance " + key, allow_outliers=3)
+        assert_close(var, wv, sv, 1e-3, "oracle spatial variance (loose) " + key)
+
+
+def test_spatially_varying_structures_live_against_reference(orc, ref):
+    """Fresh inputs, horizontal scales only (well-conditioned systems): the restatement and the compiled reference agree
+    to 1e-5 everywhere, for every family, limited and unlimited max_points, with and without extrapolation."""
+    rng = np.random.default_rng(31)
+    f32 = np.float32
+    ny, nx, dx, S = 14, 17, 2000.0, 60
+    yy, xx = np.meshgrid(np.arange(ny) * dx, np.arange(nx) * dx, indexing="ij")
+    py, px = rng.uniform(0, ny * dx, S).astype(f32), rng.uniform(0, nx * dx, S).astype(f32)
+    bg = rng.normal(size=(ny, nx)).astype(f32)
+    pbg = rng.normal(size=S).astype(f32)
+    obs = (pbg + rng.normal(size=S)).astype(f32)
+    ratios = rng.uniform(0.3, 1.0, S).astype(f32)
+    gy, gx = np.meshgrid(np.linspace(0, ny * dx, 4), np.linspace(0, nx * dx, 5), indexing="ij")
+    h = rng.uniform(4000, 9000, size=(4, 5)).astype(f32)
+    zero = np.zeros((4, 5), f32)
+    bpts, opts = (yy, xx, None, None), (py, px, None, None)
+    for stype in (B.BARNES, B.SOAR, B.TOAR, B.POWERLAW, B.LINEAR):
+        for mp, extr, min_rho in ((8, True, 0.0013), (0, False, 0.1)):
+            args = (bpts, bg, opts, obs, ratios, pbg, stype, (gy, gx), h, zero, zero, min_rho, mp, B.CARTESIAN)
+            a, av = ref.optimal_interpolation_spatial(*args, allow_extrapolation=extr, want_variance=True)
+            b, bv = orc.optimal_interpolation_spatial(*args, allow_extrapolation=extr, want_variance=True)
+            assert_close(b, a, 1.0, 1e-5, "spatial family %d mp=%d" % (stype, mp))
+            assert_close(bv, av, 1.0, 1e-5, "spatial variance family %d mp=%d" % (stype, mp))
