@@ -1475,8 +1475,8 @@ int gpp_structure_field_lookup_host(const gpp_structure_field* f, const float* l
 }
 
 int gpp_structure_field_localization_distance(const gpp_structure_field* f, int type, float min_rho, float lat, float lon, float* out) {
-    float h, v, w, lc;
-    double ld;
+    float h = 0.f, v = 0.f, w = 0.f, lc = 0.f;
+    double ld = 0.0;
     GPP_TRY(spatial_loc_constants(type, min_rho, &lc, &ld));
     GPP_TRY(gpp_structure_field_lookup_host(f, &lat, &lon, 1, &h, &v, &w));
     *out = spatial_loc_dist_host(type, h, lc, ld);
