@@ -159,3 +159,39 @@ def test_small_integer_quotients_are_exact():
         q = (e.astype(f64) * f64(r) + q0.astype(f64)).astype(f32)
         want = (n.astype(f64) / f64(m)).astype(f32)
         assert (q == want).all(), m
+
+
+def test_convert_coordinates_and_min_rho_constructors(gpp, orc):
+    """The two host-only entry points the C++ layer needs: gpp_convert_coordinates (util.cpp:583-615, what Point's
+    constructor calls) against the oracle bit for bit, and gpp_structure_init_min_rho (the (1, 1)-field form of
+    <Family>Structure(Grid, h, v, w, min_rho), structure.cpp:168-176) against localization_distance(h) of each family."""
+    import ctypes as C
+    from gridpp_b200 import _lib
+    rng = np.random.default_rng(17)
+    lats, lons = rng.uniform(-90, 90, 500).astype(f32), rng.uniform(-360, 360, 500).astype(f32)
+    for ctype in (gpp.Geodetic, gpp.Cartesian):
+        got = [np.empty(500, f32) for _ in range(3)]
+        rc = _lib.lib.gpp_convert_coordinates(lats.ctypes.data_as(_lib.fp), lons.ctypes.data_as(_lib.fp), 500, ctype,
+                                              *[a.ctypes.data_as(_lib.fp) for a in got])
+        assert rc == 0
+        for a, b, axis in zip(got, orc.convert_coordinates(lats, lons, ctype), "xyz"):
+            assert_bit_exact(a, b, "convert_coordinates " + axis)
+    bad = np.array([95.0], f32)
+    out = [np.empty(1, f32) for _ in range(3)]
+    rc = _lib.lib.gpp_convert_coordinates(bad.ctypes.data_as(_lib.fp), bad.ctypes.data_as(_lib.fp), 1, gpp.Geodetic,
+                                          *[a.ctypes.data_as(_lib.fp) for a in out])
+    assert rc == 1 and b"Invalid coords" in _lib.lib.gpp_last_error()      # util.cpp:596-600 -> std::invalid_argument
+    # tests/test_barnes_structure.py:46-66 of the reference: sqrt(-2 log(0.1)) * 2500
+    grid = gpp.Grid([[0.0]], [[0.0]], type=gpp.Cartesian)
+    s = gpp.BarnesStructure(grid, [[2500]], [[0]], [[0]], 0.1)
+    assert abs(s.localization_distance() - np.sqrt(-2 * np.log(0.1)) * 2500) < 1e-2
+    for st, cls in ((B.BARNES, gpp.BarnesStructure), (B.SOAR, gpp.SoarStructure), (B.TOAR, gpp.ToarStructure),
+                    (B.POWERLAW, gpp.PowerlawStructure), (B.LINEAR, gpp.LinearStructure)):
+        for h, min_rho in ((2500.0, 0.1), (10000.0, 0.0013), (731.5, 0.4)):
+            got = cls(grid, [[h]], [[100]], [[0.5]], min_rho).localization_distance()
+            o = B.make_structure(st, h, 100.0, 0.5, min_rho=min_rho)
+            want = C.c_float()
+            orc._check(orc._fn("structure_localization_distance")(C.byref(o), C.byref(want)))
+            assert f32(got) == f32(want.value), (st, h, min_rho, got, want.value)
+    d = _lib.StructureDesc()
+    assert _lib.lib.gpp_structure_init_min_rho(C.byref(d), B.CRESSMAN, 1000.0, 0.0, 0.0, 0.1) == 1   # no such constructor
