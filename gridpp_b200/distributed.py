@@ -1,7 +1,9 @@
 """Row-sharded multi-GPU drivers: one process per GPU, ``torch.distributed`` for the plumbing.
 
 * OI / EnSI: every output point is independent (oi.cpp:221-338), so each rank analyses a contiguous block of rows
-  against the full (replicated, ~0.4 MB) observation table. No data-path collective.
+  against the full (replicated, ~0.4 MB) observation table. No data-path collective: `optimal_interpolation` /
+  `optimal_interpolation_ensi` below build the rank's Grid from its rows and call the ordinary entry points; only
+  `gather=True` (every rank wants the whole field) adds an all-gather of the results.
 * Neighbourhood filters: a stencil of radius ``halfwidth``; each rank needs ``halfwidth`` rows from its upper and
   lower neighbour (true domain edges are clipped, not padded: neighbourhood.cpp:104-107). A ``RowTile`` keeps the
   rank's rows inside a buffer with room for both halos, so the exchange (point-to-point, NCCL over NVLink for CUDA
@@ -167,3 +169,72 @@ def gather_rows(tile, group=None):
     out = [torch.empty_like(padded) for _ in range(world)]
     dist.all_gather(out, padded, group=group)
     return torch.cat([o[:s] for o, s in zip(out, sizes)], dim=0)
+
+
+def _rows_of(a, r0, r1):
+    return None if a is None else a[r0:r1]
+
+
+def _gather_result(rows, group):
+    """All-gather of this rank's result rows (a numpy array) into the whole field, on the backend's device."""
+    import numpy as np
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return rows
+    t = torch.from_numpy(np.ascontiguousarray(rows))
+    flat = t.reshape(t.shape[0], -1)
+    if dist.get_backend(group) == "nccl":
+        flat = flat.cuda()
+    return gather_rows(flat, group).cpu().numpy().reshape((-1,) + tuple(rows.shape[1:]))
+
+
+def optimal_interpolation(lats, lons, background, points, pobs, pratios, pbackground, structure, max_points,
+                          allow_extrapolation=True, elevs=None, lafs=None, type=0, group=None, gather=False, compute=None):
+    """Row-sharded gridpp.optimal_interpolation over the (Y, X) grid given by `lats`, `lons` (and optional `elevs`,
+    `lafs`): this rank analyses rows row_block(Y, world, rank) of `background` with the full observation set and
+    returns them (the whole field on every rank with gather=True). Every rank passes the same arguments; the caller
+    selects the rank's device beforehand (gridpp_b200.set_device). `compute(lats, lons, elevs, lafs, background)`, all
+    restricted to the rank's rows, defaults to the CUDA path."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    r0, r1 = row_block(len(lats), world, rank)
+    args = [_rows_of(a, r0, r1) for a in (lats, lons, elevs, lafs, background)]
+    if compute is None:
+        import gridpp_b200 as gpp
+        grid = gpp.Grid(args[0], args[1], args[2], args[3], type)
+        rows = gpp.optimal_interpolation(grid, args[4], points, pobs, pratios, pbackground, structure, max_points, allow_extrapolation)
+    else:
+        rows = compute(*args)
+    return _gather_result(rows, group) if gather else rows
+
+
+def optimal_interpolation_ensi(lats, lons, background, points, pobs, psigmas, pbackground, structure, max_points,
+                               allow_extrapolation=True, elevs=None, lafs=None, type=0, group=None, gather=False, compute=None):
+    """Row-sharded gridpp.optimal_interpolation_ensi; `background` is (Y, X, E). A member with an invalid value anywhere
+    in the WHOLE field is left untouched (oi_ensi.cpp:187-201), so the per-member flags of the ranks are combined with
+    one all-reduce before the rows are analysed: members invalid elsewhere are masked in this rank's rows for the call
+    and restored afterwards."""
+    import numpy as np
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    r0, r1 = row_block(len(lats), world, rank)
+    args = [_rows_of(a, r0, r1) for a in (lats, lons, elevs, lafs)]
+    mine = np.array(background[r0:r1], dtype=np.float32)
+    invalid = (~np.isfinite(mine)).reshape(-1, mine.shape[-1]).any(axis=0)
+    if world > 1:
+        flags = torch.from_numpy(invalid.astype(np.int32))
+        if dist.get_backend(group) == "nccl":
+            flags = flags.cuda()
+        dist.all_reduce(flags, op=dist.ReduceOp.MAX, group=group)
+        invalid = flags.cpu().numpy().astype(bool)
+    masked = mine.copy()
+    masked[..., invalid] = np.nan         # marks the member invalid for this rank's call too
+    if compute is None:
+        import gridpp_b200 as gpp
+        grid = gpp.Grid(args[0], args[1], args[2], args[3], type)
+        rows = gpp.optimal_interpolation_ensi(grid, masked, points, pobs, psigmas, pbackground, structure, max_points, allow_extrapolation)
+    else:
+        rows = compute(*args, masked)
+    rows = np.array(rows, dtype=np.float32)
+    rows[..., invalid] = mine[..., invalid]
+    return _gather_result(rows, group) if gather else rows

@@ -90,3 +90,65 @@ def test_row_block_partition():
         assert all(a[1] == b[0] for a, b in zip(blocks[:-1], blocks[1:]))
         sizes = [b - a for a, b in blocks]
         assert max(sizes) - min(sizes) <= 1
+
+
+def _oi_inputs():
+    rng = np.random.default_rng(5)
+    ny, nx, S, E = 22, 17, 60, 5
+    y, x = np.meshgrid(np.arange(ny) * 1000.0, np.arange(nx) * 1000.0, indexing="ij")
+    y, x = y.astype(np.float32), x.astype(np.float32)
+    py, px = rng.uniform(0, ny * 1000, S).astype(np.float32), rng.uniform(0, nx * 1000, S).astype(np.float32)
+    bg = rng.normal(size=(ny, nx)).astype(np.float32)
+    ens = (bg[:, :, None] + rng.normal(size=(ny, nx, E))).astype(np.float32)
+    ens[3, 4, 2] = np.nan                      # lives in rank 0's rows only: rank 1 must learn about it
+    pbg, pens = rng.normal(size=S).astype(np.float32), rng.normal(size=(S, E)).astype(np.float32)
+    obs = (pbg + rng.normal(size=S)).astype(np.float32)
+    return dict(y=y, x=x, py=py, px=px, bg=bg, ens=ens, pbg=pbg, pens=pens, obs=obs, ratios=np.full(S, 0.5, np.float32),
+                sig=np.full(S, 0.7, np.float32))
+
+
+def _oi_worker(rank, world, port, result_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import sys
+    sys.path.insert(0, ROOT)
+    from gridpp_b200 import distributed as gdist
+    d = _oi_inputs()
+    orc = B.load("oracle")
+    s = B.make_structure(B.BARNES, 5000.0)
+
+    def oi_rows(lats, lons, elevs, lafs, background):
+        out = orc.optimal_interpolation((lats, lons, None, None), background, (d["py"], d["px"], None, None), d["obs"], d["ratios"],
+                                        d["pbg"], s, 10, B.CARTESIAN)
+        return out.reshape(background.shape)
+
+    def ensi_rows(lats, lons, elevs, lafs, background):
+        out = orc.optimal_interpolation_ensi((lats, lons, None, None), background.reshape(-1, background.shape[-1]),
+                                             (d["py"], d["px"], None, None), d["obs"], d["sig"], d["pens"], s, 10, B.CARTESIAN)
+        return out.reshape(background.shape)
+
+    oi = gdist.optimal_interpolation(d["y"], d["x"], d["bg"], None, d["obs"], d["ratios"], d["pbg"], None, 10, type=1, gather=True, compute=oi_rows)
+    ensi = gdist.optimal_interpolation_ensi(d["y"], d["x"], d["ens"], None, d["obs"], d["sig"], d["pens"], None, 10, type=1, gather=True,
+                                            compute=ensi_rows)
+    np.savez(os.path.join(result_dir, "oi_rank%d.npz" % rank), oi=oi, ensi=ensi)
+    dist.destroy_process_group()
+
+
+def test_row_sharded_oi_and_ensi_equal_whole(tmp_path, orc):
+    """OI and EnSI sharded by rows over two ranks (the oracle standing in for the kernels) equal the whole-field result,
+    including the EnSI rule that a member with an invalid value ANYWHERE is left untouched on every rank."""
+    world = 2
+    mp.spawn(_oi_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    d = _oi_inputs()
+    s = B.make_structure(B.BARNES, 5000.0)
+    want_oi = orc.optimal_interpolation((d["y"], d["x"], None, None), d["bg"], (d["py"], d["px"], None, None), d["obs"], d["ratios"], d["pbg"],
+                                        s, 10, B.CARTESIAN).reshape(d["bg"].shape)
+    E = d["ens"].shape[-1]
+    want_ensi = orc.optimal_interpolation_ensi((d["y"], d["x"], None, None), d["ens"].reshape(-1, E), (d["py"], d["px"], None, None), d["obs"],
+                                               d["sig"], d["pens"], s, 10, B.CARTESIAN).reshape(d["ens"].shape)
+    for rank in range(world):
+        got = np.load(os.path.join(str(tmp_path), "oi_rank%d.npz" % rank))
+        assert np.array_equal(got["oi"], want_oi, equal_nan=True), rank
+        assert np.array_equal(got["ensi"], want_ensi, equal_nan=True), rank
+        assert np.array_equal(got["ensi"][:, :, 2], d["ens"][:, :, 2], equal_nan=True)   # the member with the missing value
