@@ -286,29 +286,63 @@ class KDTree(Points):
 
 
 # ---------------------------------------------------------------------------------------------------------
+class Point:
+    """gridpp::Point (gridpp.h:1713-1743, point.cpp:5-26): Point(lat, lon, elev=MV, laf=MV, type=Geodetic) or, with the
+    3-D coordinates given, Point(lat, lon, elev, laf, type, x, y, z)."""
+
+    def __init__(self, lat, lon, elev=MV, laf=MV, type=Geodetic, x=None, y=None, z=None):
+        self.lat, self.lon, self.elev, self.laf, self.type = float(lat), float(lon), float(elev), float(laf), int(type)
+        if x is not None:
+            self.x, self.y, self.z = float(x), float(y), float(z)
+        elif self.type == Geodetic:
+            xyz = [_np.empty(1, _np.float32) for _ in range(3)]
+            la, lo = _np.array([lat], _np.float32), _np.array([lon], _np.float32)
+            _check(_libc.gpp_convert_coordinates(_fptr(la), _fptr(lo), 1, Geodetic, _fptr(xyz[0]), _fptr(xyz[1]), _fptr(xyz[2])))
+            self.x, self.y, self.z = (float(a[0]) for a in xyz)
+        else:
+            # point.cpp:18-22: x = lat, y = lon (not the x = lon, y = lat of convert_coordinates) and no validity check
+            self.x, self.y, self.z = float(_np.float32(lat)), float(_np.float32(lon)), 0.0
+
+    def _row(self):
+        return [self.x, self.y, self.z, self.elev, self.laf]
+
+
 class StructureFunction:
     """POD-backed replacement for the gridpp::StructureFunction hierarchy (gridpp.h:2069-2343)."""
 
     def __init__(self, desc):
         self._desc = desc
 
-    def _points5(self, p):
+    @staticmethod
+    def _points5(p):
+        if isinstance(p, Point):
+            p = [p._row()]
+        elif isinstance(p, (list, tuple)) and len(p) > 0 and isinstance(p[0], Point):
+            p = [q._row() for q in p]
         return _np.ascontiguousarray(_np.asarray(p, _np.float32).reshape(-1, 5))
 
     def corr(self, p1, p2):
-        """p1, p2: arrays (n, 5) of x, y, z, elev, laf. Evaluated on the device."""
+        """corr(Point, Point) -> float and corr(Point, [Point, ...]) -> array, as the reference (structure.cpp:13-24); also
+        arrays (n, 5) of x, y, z, elev, laf for both arguments -> array. Evaluated on the device."""
         return self._corr(p1, p2, False)
 
     def corr_background(self, p1, p2):
         return self._corr(p1, p2, True)
 
+    def _descriptor_at(self, p1):
+        return self._desc
+
     def _corr(self, p1, p2, background):
+        scalar = isinstance(p1, Point) and isinstance(p2, Point)
+        desc = self._descriptor_at(p1)
         a, b = self._points5(p1), self._points5(p2)
+        if isinstance(p1, Point) and a.shape[0] == 1 and b.shape[0] != 1:
+            a = _np.ascontiguousarray(_np.repeat(a, b.shape[0], axis=0))
         if a.shape != b.shape:
             raise ValueError("p1 and p2 must have the same shape")
         out = _np.empty(a.shape[0], _np.float32)
-        _check(_libc.gpp_structure_corr_host(_C.byref(self._desc), _fptr(a), _fptr(b), a.shape[0], int(background), _fptr(out)))
-        return out
+        _check(_libc.gpp_structure_corr_host(_C.byref(desc), _fptr(a), _fptr(b), a.shape[0], int(background), _fptr(out)))
+        return float(out[0]) if scalar else out
 
     def localization_distance(self, point=None):
         return float(self._desc.term[0].loc_dist)
@@ -398,10 +432,19 @@ class _Family(StructureFunction):
                                                                _C.byref(out)))
         return float(out.value)
 
-    def _corr(self, p1, p2, background):
-        if self._field is not None:
-            raise NotImplementedOnDevice("corr() of a spatially varying structure function is only evaluated inside optimal_interpolation()")
-        return StructureFunction._corr(self, p1, p2, background)
+    def _descriptor_at(self, p1):
+        """The constant-scale descriptor corr(p1, .) uses: for a spatially varying structure function the scales of the
+        node nearest to p1 (structure.cpp:189-199), which needs p1's lat / lon, i.e. a Point."""
+        if self._field is None:
+            return self._desc
+        if not isinstance(p1, Point):
+            raise ValueError("corr() of a spatially varying structure function needs p1 as a Point (its lat / lon select the scales)")
+        la, lo = _np.array([p1.lat], _np.float32), _np.array([p1.lon], _np.float32)
+        h, v, w = (_np.empty(1, _np.float32) for _ in range(3))
+        _check(_libc.gpp_structure_field_lookup_host(self._field._handle, _fptr(la), _fptr(lo), 1, _fptr(h), _fptr(v), _fptr(w)))
+        d = _lib.StructureDesc()
+        _check(_libc.gpp_structure_init_min_rho(_C.byref(d), self._TYPE, float(h[0]), float(v[0]), float(w[0]), self._min_rho))
+        return d
 
     def clone(self):
         c = StructureFunction.clone(self)

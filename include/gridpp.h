@@ -136,8 +136,15 @@ inline bool convert_coordinates(const vec& lats, const vec& lons, CoordinateType
 
 class Point {
 public:
+    // point.cpp:5-23: geodetic points are converted; for Cartesian ones x = lat, y = lon (not the x = lon, y = lat of
+    // convert_coordinates) and nothing is validated
     Point(float lat, float lon, float elev = MV, float laf = MV, CoordinateType type = Geodetic) : lat(lat), lon(lon), elev(elev), laf(laf), type(type) {
-        b200::check(gpp_convert_coordinates(&lat, &lon, 1, (int) type, &x, &y, &z));
+        if(type == Geodetic) b200::check(gpp_convert_coordinates(&lat, &lon, 1, (int) type, &x, &y, &z));
+        else {
+            x = lat;
+            y = lon;
+            z = 0;
+        }
     }
     Point(float lat, float lon, float elev, float laf, CoordinateType type, float x, float y, float z) :
             lat(lat), lon(lon), elev(elev), laf(laf), type(type), x(x), y(y), z(z) {}
@@ -232,6 +239,11 @@ protected:
                                                    distances ? distances->data() : nullptr, &count));
         return index;
     }
+    Point point_at(size_t i, float elev, float laf) const {
+        float x, y, z;
+        b200::check(gpp_convert_coordinates(&m_lats[i], &m_lons[i], 1, (int) m_type, &x, &y, &z));
+        return Point(m_lats[i], m_lons[i], elev, laf, m_type, x, y, z);
+    }
     vec xyz(int which) const {
         vec out((size_t) size());
         b200::check(gpp_points_get_xyz(m_handle.get(), which == 0 ? out.data() : nullptr, which == 1 ? out.data() : nullptr,
@@ -275,7 +287,7 @@ public:
     CoordinateType get_coordinate_type() const { return m_tree.get_coordinate_type(); }
     Point get_point(int index) const {
         b200::require(index >= 0 && index < size(), "Point index out of range");
-        return Point(m_tree.m_lats[index], m_tree.m_lons[index], m_elevs[index], m_lafs[index], get_coordinate_type());
+        return m_tree.point_at((size_t) index, m_elevs[index], m_lafs[index]);   // points.cpp:128-130: the index's coordinates
     }
     Points subset(const ivec& indices) const {
         vec lats, lons, elevs, lafs;
@@ -342,7 +354,7 @@ public:
     Point get_point(int y_index, int x_index) const {
         b200::require(y_index >= 0 && y_index < m_ny && x_index >= 0 && x_index < m_nx, "Grid index out of range");
         const size_t i = (size_t) y_index * m_nx + x_index;
-        return Point(m_tree.m_lats[i], m_tree.m_lons[i], m_elevs[i], m_lafs[i], get_coordinate_type());
+        return m_tree.point_at(i, m_elevs[i], m_lafs[i]);   // grid.cpp:232-235
     }
     const gpp_points* b200_handle() const { return m_tree.b200_handle(); }
     // the flattened coordinates (no copy), for callers that query every node
@@ -392,7 +404,13 @@ public:
 protected:
     StructureFunction() { m_desc = gpp_structure(); }
     vec evaluate(const Point& p1, const std::vector<Point>& p2, bool background) const {
-        if(m_field) throw not_implemented_exception("corr() of a spatially varying structure function is only evaluated inside optimal_interpolation()");
+        gpp_structure desc = m_desc;
+        if(m_field) {
+            // the scales of the node nearest to p1 (structure.cpp:189-199), then the constant-scale evaluation
+            float h = 0, v = 0, w = 0;
+            b200::check(gpp_structure_field_lookup_host(m_field.get(), &p1.lat, &p1.lon, 1, &h, &v, &w));
+            b200::check(gpp_structure_init_min_rho(&desc, m_desc.term[0].type, h, v, w, m_desc.term[0].min_rho));
+        }
         const int n = (int) p2.size();
         vec a((size_t) 5 * n), b((size_t) 5 * n), out((size_t) n);
         for(int i = 0; i < n; i++) {
@@ -402,7 +420,7 @@ protected:
                 b[5 * i + c] = pb[c];
             }
         }
-        b200::check(gpp_structure_corr_host(&m_desc, a.data(), b.data(), n, background, out.data()));
+        b200::check(gpp_structure_corr_host(&desc, a.data(), b.data(), n, background, out.data()));
         return out;
     }
     // <Family>Structure(h, v, w, hmax)

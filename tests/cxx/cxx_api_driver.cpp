@@ -60,7 +60,11 @@ static int checks() {
     EXPECT(grid.to_points().size() == 6 && grid.to_points().get_coordinate_type() == Cartesian);
     EXPECT_THROW(Grid({{0, 0}}, {{0, 1, 2}}), std::invalid_argument);
     Point p = grid.get_point(1, 2);
-    EXPECT(p.x == 2 && p.y == 1 && p.z == 0);
+    EXPECT(p.x == 2 && p.y == 1 && p.z == 0);                               // the index's coordinates (grid.cpp:232-235)
+    Point direct(1, 2, 0, 0, Cartesian);
+    EXPECT(direct.x == 1 && direct.y == 2 && direct.z == 0);                // point.cpp:18-22: x = lat, y = lon
+    EXPECT(std::isnan(Point(MV, 0, 0, 0, Cartesian).x));                    // ... and no validation for Cartesian points
+    EXPECT_THROW(Point(95, 0), std::invalid_argument);
     Point q(0, 90);   // on the equator at 90 E: x ~ 0, y = earth radius
     EXPECT(std::fabs(q.y - 6.378137e6f) < 1 && std::fabs(q.x) < 1 && q.z == 0);
     EXPECT(KDTree::calc_distance(0, 0, 3, 4, Cartesian) == 5);

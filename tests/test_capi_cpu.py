@@ -195,3 +195,25 @@ def test_convert_coordinates_and_min_rho_constructors(gpp, orc):
             assert f32(got) == f32(want.value), (st, h, min_rho, got, want.value)
     d = _lib.StructureDesc()
     assert _lib.lib.gpp_structure_init_min_rho(C.byref(d), B.CRESSMAN, 1000.0, 0.0, 0.0, 0.1) == 1   # no such constructor
+
+
+def test_point_constructor_follows_the_reference(gpp, orc):
+    """gridpp::Point (point.cpp:5-26): geodetic points carry the converted coordinates (util.cpp:583-615, invalid latitudes
+    throw), Cartesian ones x = lat, y = lon without any check; the eight-argument form stores what it is given."""
+    p = gpp.Point(60, 10, 100, 0.5)
+    x, y, z = orc.convert_coordinates([60], [10], gpp.Geodetic)
+    assert (f32(p.x), f32(p.y), f32(p.z)) == (x[0], y[0], z[0]) and p.elev == 100 and p.laf == 0.5 and p.type == gpp.Geodetic
+    q = gpp.Point(1, 2, 0, 0, gpp.Cartesian)
+    assert (q.x, q.y, q.z) == (1, 2, 0)
+    assert np.isnan(gpp.Point(np.nan, 0, 0, 0, gpp.Cartesian).x) and np.isnan(gpp.Point(1, 2).elev)
+    with pytest.raises(ValueError):
+        gpp.Point(95, 0)
+    r = gpp.Point(1, 2, 3, 4, gpp.Cartesian, 7, 8, 9)
+    assert (r.x, r.y, r.z, r.lat, r.lon) == (7, 8, 9, 1, 2)
+    # Point arguments become rows of (x, y, z, elev, laf); a spatially varying structure function needs a Point for p1
+    rows = gpp.StructureFunction._points5([q, r])
+    assert rows.shape == (2, 5) and rows[1].tolist() == [7, 8, 9, 3, 4]
+    grid = gpp.Grid([[0, 0]], [[0, 2500]], type=gpp.Cartesian)
+    s = gpp.BarnesStructure(grid, [[2500, 1]], [[0, 0]], [[0, 0]], 0.1)
+    with pytest.raises(ValueError):
+        s.corr(np.zeros((1, 5)), np.zeros((1, 5)))

@@ -787,3 +787,32 @@ def test_ensi_pipelined_path_equals_whole_field_path(gpp, orc):
     want = orc.optimal_interpolation_ensi((y[h:].ravel()[pick], x[h:].ravel()[pick], None, None), bg[h:].reshape(-1, E)[pick], (py, px, None, None),
                                           obs, sig, pbg, B.make_structure(B.BARNES, 12000.0), 12, B.CARTESIAN)
     assert_close(whole[h:].reshape(-1, E)[pick][:, keep], want[:, keep], 1.0, RTOL, "pipelined path vs oracle")
+
+
+def test_structure_functions_with_point_objects(gpp):
+    """tests/test_barnes_structure.py:8-33 and :46-66 of the reference as written there: gridpp.Point arguments, scalar
+    results, the vector overload, and corr() of a spatially varying structure function (scales of the node nearest to p1)."""
+    x = [0, 1000, 2000, 3000, np.nan]
+    barnes = gpp.BarnesStructure(2000)
+    cases = [(barnes, [1, 0.8824968934059143, 0.6065306663513184, 0.32465246319770813, 0], False),
+             (gpp.CressmanStructure(2000), [1, 0.6, 0, 0, 0], False),
+             (gpp.CrossValidation(barnes, 1000), [0, 0, 0.6065306663513184, 0.32465246319770813, 0], True)]
+    for s, want, is_cv in cases:
+        for xi, w in zip(x, want):
+            p1 = gpp.Point(0, 0, 0, 0, gpp.Cartesian)
+            p2 = gpp.Point(xi, 0, 0, 0, gpp.Cartesian)
+            for func in ([s.corr_background] if is_cv else [s.corr, s.corr_background]):
+                assert abs(func(p1, p2) - w) < 1e-7, (type(s).__name__, xi)
+                assert abs(func(p2, p1) - w) < 1e-7, (type(s).__name__, xi)
+                if not is_cv and not np.isnan(xi):
+                    assert abs(func(p2, p2) - 1) < 1e-7
+    others = [gpp.Point(v, 0, 0, 0, gpp.Cartesian) for v in x[:4]]
+    np.testing.assert_array_equal(barnes.corr(gpp.Point(0, 0, 0, 0, gpp.Cartesian), others),
+                                  np.array([1, 0.8824968934059143, 0.6065306663513184, 0.32465246319770813], f32))
+    grid = gpp.Grid([[0, 0]], [[0, 2500]], [[0, 0]], [[0, 0]], gpp.Cartesian)
+    s = gpp.BarnesStructure(grid, [[2500, 1]], [[0, 0]], [[0, 0]], 0.1)
+    p1, p2 = gpp.Point(0, 0, 0, 0, gpp.Cartesian), gpp.Point(0, 2500, 0, 0, gpp.Cartesian)
+    assert abs(s.localization_distance(p1) - np.sqrt(-2 * np.log(0.1)) * 2500) < 1e-2      # the scale at p1 is 2500
+    assert abs(s.corr(p1, p2) - 0.6065306663513184) < 1e-6
+    assert abs(s.localization_distance(p2) - np.sqrt(-2 * np.log(0.1)) * 1) < 1e-4         # the scale at p2 is 1
+    assert s.corr(p2, p1) == 0
