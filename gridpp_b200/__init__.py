@@ -16,6 +16,7 @@ Every function is a thin marshalling layer over the C ABI of ``libgridpp_b200.so
 all computation happens in hand-written sm_100a CUDA kernels. There is no CPU fallback.
 """
 import ctypes as _C
+import math as _math
 
 import numpy as _np
 
@@ -283,6 +284,83 @@ class KDTree(Points):
 
     def __init__(self, lats=None, lons=None, type=Geodetic):
         Points.__init__(self, lats, lons, None, None, type)
+
+    def get_x(self):
+        return self._set.xyz()[0]
+
+    def get_y(self):
+        return self._set.xyz()[1]
+
+    def get_z(self):
+        return self._set.xyz()[2]
+
+    # ---- scalar helpers of kdtree.cpp:107-200 (host arithmetic with the reference's float / double mix; SWIG also
+    # exposes them flat as gridpp.KDTree_calc_distance etc., tests/test_kdtree.py:56,111)
+    @staticmethod
+    def deg2rad(deg):
+        return float(_np.float32(float(_np.float32(deg)) * _math.pi / 180))
+
+    @staticmethod
+    def rad2deg(rad):
+        return float(_np.float32(float(_np.float32(rad)) * 180 / _math.pi))
+
+    @staticmethod
+    def calc_straight_distance(x0, y0=None, z0=None, x1=None, y1=None, z1=None):
+        if y0 is not None and z0 is None:                       # (Point, Point), kdtree.cpp:189-191
+            p1, p2 = x0, y0
+            x0, y0, z0, x1, y1, z1 = p1.x, p1.y, p1.z, p2.x, p2.y, p2.z
+        f = _np.float32
+        dx, dy, dz = f(x0) - f(x1), f(y0) - f(y1), f(z0) - f(z1)
+        return float(_np.sqrt(dx * dx + dy * dy + dz * dz))
+
+    @staticmethod
+    def calc_distance(lat1, lon1, lat2=None, lon2=None, type=Geodetic):
+        if lat2 is None:                                        # (Point, Point), kdtree.cpp:183-188
+            p1, p2 = lat1, lon1
+            if p1.type != p2.type:
+                raise RuntimeError("Coordinate types must be the same")
+            lat1, lon1, lat2, lon2, type = p1.lat, p1.lon, p2.lat, p2.lon, p1.type
+        f = _np.float32
+        lat1, lon1, lat2, lon2 = f(lat1), f(lon1), f(lat2), f(lon2)
+        if type == Cartesian:
+            dx, dy = lon1 - lon2, lat1 - lat2
+            return float(_np.sqrt(dx * dx + dy * dy))
+        if lat1 == lat2 and lon1 == lon2:
+            return 0.0
+        a1, a2, o1, o2 = KDTree.deg2rad(lat1), KDTree.deg2rad(lat2), KDTree.deg2rad(lon1), KDTree.deg2rad(lon2)
+        cos, sin = _math.cos, _math.sin
+        ratio = cos(a1) * cos(o1) * cos(a2) * cos(o2) + cos(a1) * sin(o1) * cos(a2) * sin(o2) + sin(a1) * sin(a2)
+        try:
+            dist = _math.acos(ratio) * 6.378137e6
+        except ValueError:                                      # ratio a rounding above 1: acos gives NaN in C
+            dist = float("nan")
+        return float(f(dist))
+
+
+KDTree_deg2rad, KDTree_rad2deg = KDTree.deg2rad, KDTree.rad2deg
+KDTree_calc_distance, KDTree_calc_straight_distance = KDTree.calc_distance, KDTree.calc_straight_distance
+
+
+def is_valid(value):
+    """gridpp::is_valid, util.cpp:16-18."""
+    return not (_math.isnan(value) or _math.isinf(value))
+
+
+# gridpp.cpp:45-68. The device path has no host thread team; the value is kept so that code which sets it and reads it
+# back behaves as before.
+_omp_threads = [1]
+
+
+def set_omp_threads(num):
+    _omp_threads[0] = int(num)
+
+
+def get_omp_threads():
+    return _omp_threads[0]
+
+
+def initialize_omp():
+    pass
 
 
 # ---------------------------------------------------------------------------------------------------------

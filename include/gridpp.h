@@ -200,12 +200,11 @@ public:
             return std::sqrt(dx * dx + dy * dy);
         }
         if(lat1 == lat2 && lon1 == lon2) return 0;
-        // great-circle distance from the spherical law of cosines, in double, argument clamped into acos' domain
+        // great-circle distance from the spherical law of cosines, in double (kdtree.cpp:121-131; like the reference, no
+        // clamping of the cosine: a rounding above 1 gives NaN)
         const double a1 = deg2rad(lat1), a2 = deg2rad(lat2), o1 = deg2rad(lon1), o2 = deg2rad(lon2);
-        double c = std::cos(a1) * std::cos(o1) * std::cos(a2) * std::cos(o2) + std::cos(a1) * std::sin(o1) * std::cos(a2) * std::sin(o2) +
-                   std::sin(a1) * std::sin(a2);
-        if(c > 1) c = 1;
-        if(c < -1) c = -1;
+        const double c = std::cos(a1) * std::cos(o1) * std::cos(a2) * std::cos(o2) + std::cos(a1) * std::sin(o1) * std::cos(a2) * std::sin(o2) +
+                         std::sin(a1) * std::sin(a2);
         return (float) (std::acos(c) * 6.378137e6);
     }
     static float calc_distance(const Point& p1, const Point& p2) {

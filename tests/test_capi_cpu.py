@@ -217,3 +217,33 @@ def test_point_constructor_follows_the_reference(gpp, orc):
     s = gpp.BarnesStructure(grid, [[2500, 1]], [[0, 0]], [[0, 0]], 0.1)
     with pytest.raises(ValueError):
         s.corr(np.zeros((1, 5)), np.zeros((1, 5)))
+
+
+def test_scalar_helpers_match_reference(gpp, orc):
+    """KDTree::calc_distance / calc_straight_distance / deg2rad / rad2deg (kdtree.cpp:107-200), also under their flat SWIG
+    names, is_valid (util.cpp:16-18) and the thread-count functions (gridpp.cpp:45-68)."""
+    rng = np.random.default_rng(23)
+    for ctype, lo, hi in ((gpp.Geodetic, -90, 90), (gpp.Cartesian, -1e5, 1e5)):
+        for _ in range(300):
+            a, c = rng.uniform(lo, hi, 2).astype(f32)
+            b, d = rng.uniform(2 * lo, 2 * hi, 2).astype(f32)
+            want = orc.calc_distance(float(a), float(b), float(c), float(d), ctype)
+            got = gpp.KDTree.calc_distance(a, b, c, d, ctype)
+            assert f32(got) == f32(want), (ctype, a, b, c, d, got, want)
+    # tests/test_kdtree.py:108-112 and :50-58 of the reference
+    assert abs(gpp.KDTree_calc_distance(0, 0, 0.001, 0.001) - 157.42953491210938) < 1e-5
+    p0, p1 = gpp.Point(0, 0), gpp.Point(0.001, 0.001)
+    assert abs(gpp.KDTree_calc_straight_distance(p0.x, p0.y, p0.z, p1.x, p1.y, p1.z) - 157.42953491210938) < 0.5
+    assert gpp.KDTree.calc_distance(p0, p1) == gpp.KDTree_calc_distance(0, 0, 0.001, 0.001)
+    assert gpp.KDTree.calc_distance(60, 10, 60, 10) == 0
+    assert abs(gpp.KDTree_rad2deg(1) - 180 / 3.14159265) < 1e-5 and abs(gpp.KDTree_deg2rad(180) - 3.14159265) < 1e-5
+    with pytest.raises(RuntimeError):
+        gpp.KDTree.calc_distance(gpp.Point(0, 0), gpp.Point(0, 0, 0, 0, gpp.Cartesian))
+    assert gpp.is_valid(1.0) and not gpp.is_valid(float("nan")) and not gpp.is_valid(float("inf"))
+    gpp.set_omp_threads(3)
+    assert gpp.get_omp_threads() == 3
+    gpp.initialize_omp()
+    tree = gpp.KDTree([60, 61], [10, 11])
+    x, y, z = orc.convert_coordinates([60, 61], [10, 11], gpp.Geodetic)
+    assert_bit_exact(tree.get_x(), x, "get_x")
+    assert_bit_exact(tree.get_z(), z, "get_z")
