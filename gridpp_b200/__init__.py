@@ -203,6 +203,14 @@ class Points:
         _, _, count = self._set.neighbours([lat], [lon], radius, include_match, capacity=0)
         return int(count[0])
 
+    def get_point(self, index):
+        """points.cpp:128-130: the point with the coordinates of the index."""
+        s = self._set
+        if not 0 <= index < s.n:
+            raise ValueError("Point index %d out of range" % index)
+        _, x, y, z = convert_coordinates(s._lats[index], s._lons[index], s._type)
+        return Point(s._lats[index], s._lons[index], s._elevs[index], s._lafs[index], s._type, x, y, z)
+
     def subset(self, indices):
         indices = _np.asarray(indices, dtype=_np.int64).ravel()
         if indices.size and indices.max() >= self.size():
@@ -272,6 +280,12 @@ class Grid:
     def get_num_neighbours(self, lat, lon, radius, include_match=True):
         _, _, count = self._set.neighbours([lat], [lon], radius, include_match, capacity=0)
         return int(count[0])
+
+    def get_point(self, y_index, x_index):
+        """grid.cpp:232-235."""
+        if not (0 <= y_index < self._shape[0] and 0 <= x_index < self._shape[1]):
+            raise ValueError("Grid index (%d, %d) out of range" % (y_index, x_index))
+        return Points.get_point(self, y_index * self._shape[1] + x_index)
 
     def to_points(self):
         p = Points.__new__(Points)
@@ -364,6 +378,20 @@ def initialize_omp():
 
 
 # ---------------------------------------------------------------------------------------------------------
+def convert_coordinates(lats, lons, type):
+    """gridpp::convert_coordinates, util.cpp:583-615. As the SWIG module, returns (status, x, y, z): floats for scalar
+    arguments (tests/test_points.py:130), arrays for array arguments."""
+    scalar = _np.ndim(lats) == 0 and _np.ndim(lons) == 0
+    la, lo = _farray(_np.atleast_1d(lats), 1, "lats"), _farray(_np.atleast_1d(lons), 1, "lons")
+    if la.size != lo.size:
+        raise ValueError("Cannot convert coordinates with unequal lat and lon sizes")
+    x, y, z = (_np.empty(la.size, _np.float32) for _ in range(3))
+    _check(_libc.gpp_convert_coordinates(_fptr(la), _fptr(lo), la.size, int(type), _fptr(x), _fptr(y), _fptr(z)))
+    if scalar:
+        return True, float(x[0]), float(y[0]), float(z[0])
+    return True, x, y, z
+
+
 class Point:
     """gridpp::Point (gridpp.h:1713-1743, point.cpp:5-26): Point(lat, lon, elev=MV, laf=MV, type=Geodetic) or, with the
     3-D coordinates given, Point(lat, lon, elev, laf, type, x, y, z)."""

@@ -247,3 +247,22 @@ def test_scalar_helpers_match_reference(gpp, orc):
     x, y, z = orc.convert_coordinates([60, 61], [10, 11], gpp.Geodetic)
     assert_bit_exact(tree.get_x(), x, "get_x")
     assert_bit_exact(tree.get_z(), z, "get_z")
+
+
+def test_get_point_and_convert_coordinates(gpp):
+    """tests/test_points.py:115-134 and tests/test_grid.py:80-90 of the reference."""
+    points = gpp.Points([0, 1, 2], [3, 4, 5], [6, 7, 8], [9, 10, 11])
+    p = points.get_point(1)
+    assert (p.lat, p.lon, p.elev, p.laf) == (1, 4, 7, 10)
+    s, x, y, z = gpp.convert_coordinates(1, 4, gpp.Geodetic)
+    assert s and (p.x, p.y, p.z) == (x, y, z)
+    grid = gpp.Grid([[0, 0], [1, 1]], [[0, 0.25], [0, 0.25]], [[1, 2], [3, 4]], [[0, 0.1], [0.2, 0.3]])
+    q = grid.get_point(1, 1)
+    s, x, y, z = gpp.convert_coordinates(1, 0.25, gpp.Geodetic)
+    assert (q.lat, q.lon, q.elev) == (1, 0.25, 4) and abs(q.laf - 0.3) < 1e-7 and (q.x, q.y, q.z) == (x, y, z)
+    s, xs, ys, zs = gpp.convert_coordinates([0, 1], [3, 4], gpp.Cartesian)
+    assert xs.tolist() == [3, 4] and ys.tolist() == [0, 1] and zs.tolist() == [0, 0]
+    with pytest.raises(ValueError):
+        points.get_point(3)
+    with pytest.raises(ValueError):
+        gpp.convert_coordinates(91, 0, gpp.Geodetic)
