@@ -128,10 +128,136 @@ __global__ void ensi_invalid_members_kernel(const float* __restrict__ background
 #ifndef ENSI_MINB
 #define ENSI_MINB 10
 #endif
+#ifdef ENSI_REGISTER_JACOBI
+// EXPERIMENTAL, NOT COMPILED BY DEFAULT (profiles/variants.sh regj "-DENSI_REGISTER_JACOBI"; unverified on a GPU so
+// far). The Jacobi iteration with row `lane` of A and of V in registers, for an even compile-time E <= 20: the M = E - 1
+// rounds of the round-robin schedule are unrolled, so the columns a round rotates are static register indices; the two
+// lanes of a pair exchange their rows with shuffles. Index formulas, phase order and signs are those checked lane by lane
+// against numpy in profiles/jacobi_systolic_sim.py:
+//   partner(r, i) = r if i == M; M if i == r; else (2 r - i) mod M       slot = 0 | min(l, M - l), l = (i - r) mod M
+//   pair of slot t: t == 0 -> (r, M), else ((r + t) mod M, (r - t) mod M), smaller index first
+// Shared memory only carries what needs a lane-dependent index: the off-diagonal element of each pair (written by the
+// pair's first lane with a static predicated store) and the (cos, sin) of the round's rotations.
+template <int E>
+struct RegisterJacobi {
+    static constexpr int M = E - 1, H = E / 2;
+    // one round; R is the compile-time round number
+    template <int R>
+    static __device__ __forceinline__ void round(double (&a)[E], double (&v)[E], double& dgl, double2* cs, double* apq_s, int lane) {
+        // ---- this lane's pair
+        int partner = lane, slot = H;
+        if(lane < E) {
+            if(lane == M) { partner = R; slot = 0; }
+            else if(lane == R) { partner = M; slot = 0; }
+            else {
+                int l = lane - R;
+                if(l < 0) l += M;
+                partner = (2 * R - lane + 2 * M) % M;
+                slot = l < M - l ? l : M - l;
+            }
+        }
+        const bool first = lane < partner;   // the pair's smaller index p; the other lane is q
+        // ---- the pairs' off-diagonal elements: lane p holds a[p][q] at the static index q of slot t
+        #pragma unroll
+        for(int t = 0; t < H; t++) {
+            constexpr int dummy = 0; (void) dummy;
+            const int p0 = t == 0 ? R : (R + t) % M, q0 = t == 0 ? M : (R - t + M) % M;
+            const int pt = p0 < q0 ? p0 : q0, qt = p0 < q0 ? q0 : p0;
+            if(lane == pt) apq_s[t] = a[qt];
+        }
+        __syncwarp();
+        const double other = shfl_double(dgl, partner);
+        double c = 1.0, s = 0.0, tq = 0.0;
+        if(lane < E) {
+            const double apq = apq_s[slot];
+            const double app = first ? dgl : other, aqq = first ? other : dgl;
+            if(apq * apq > 1e-30 * fabs(app * aqq)) {   // rotations that could not change anything above 1e-15 relative are skipped
+                const double theta = (aqq - app) * (0.5 * fast_rcp(apq));
+                const double at = fabs(theta);
+                double tt;
+                if(at > 1e100) tt = 0.5 * fast_rcp(theta);
+                else tt = copysign(fast_rcp(at + (at * at + 1.0) * fast_rsqrt(at * at + 1.0)), theta);
+                c = fast_rsqrt(tt * tt + 1.0);
+                s = tt * c;
+                tq = tt * apq;
+            }
+            if(first) cs[slot] = make_double2(c, s);
+        }
+        __syncwarp();
+        // ---- columns p_t, q_t of A and V (static indices), every lane its own two elements
+        #pragma unroll
+        for(int t = 0; t < H; t++) {
+            const int p0 = t == 0 ? R : (R + t) % M, q0 = t == 0 ? M : (R - t + M) % M;
+            const int pt = p0 < q0 ? p0 : q0, qt = p0 < q0 ? q0 : p0;
+            const double2 r2 = cs[t];
+            const double ap = a[pt], aq = a[qt], vp = v[pt], vq = v[qt];
+            a[pt] = r2.x * ap - r2.y * aq;
+            a[qt] = r2.y * ap + r2.x * aq;
+            v[pt] = r2.x * vp - r2.y * vq;
+            v[qt] = r2.y * vp + r2.x * vq;
+        }
+        // ---- rows p, q of A: new_p = c row_p - s row_q, new_q = s row_p + c row_q (the partner's row by shuffle)
+        const double ss = first ? -s : s;
+        #pragma unroll
+        for(int j = 0; j < E; j++) {
+            const double o = shfl_double(a[j], partner);
+            a[j] = c * a[j] + ss * o;
+        }
+        dgl = first ? dgl - tq : dgl + tq;   // a_pp - t a_pq, a_qq + t a_pq
+        __syncwarp();                         // cs / apq_s are rewritten by the next round
+    }
+    template <int R>
+    static __device__ __forceinline__ void rounds(double (&a)[E], double (&v)[E], double& dgl, double2* cs, double* apq_s, int lane) {
+        if constexpr(R < M) {
+            round<R>(a, v, dgl, cs, apq_s, lane);
+            rounds<R + 1>(a, v, dgl, cs, apq_s, lane);
+        }
+    }
+    // A (rows in S_A) is diagonalised, V (rows in S_V) accumulates the rotations; returns false when A is not finite
+    static __device__ __noinline__ bool run(double* S_A, double* S_V, int LD, double2* cs, double* apq_s, int lane) {
+        double a[E], v[E];
+        #pragma unroll
+        for(int f = 0; f < E; f++) {
+            a[f] = lane < E ? S_A[lane * LD + f] : 0.0;
+            v[f] = lane < E ? S_V[lane * LD + f] : 0.0;
+        }
+        bool ok = true;
+        for(int sweep = 0; sweep < 30; sweep++) {
+            double off = 0.0, dg = 0.0, dgl = 0.0;
+            #pragma unroll
+            for(int f = 0; f < E; f++) {
+                const double sq = a[f] * a[f];
+                if(f == lane) { dg += sq; dgl = a[f]; }
+                else off += sq;
+            }
+            #pragma unroll
+            for(int o = 16; o > 0; o >>= 1) { off += shfl_double(off, lane ^ o); dg += shfl_double(dg, lane ^ o); }
+            if(!(off == off) || !(dg == dg) || isinf(off) || isinf(dg)) { ok = false; break; }
+            if(off <= 1e-26 * dg) break;
+            rounds<0>(a, v, dgl, cs, apq_s, lane);
+        }
+        if(lane < E) {
+            #pragma unroll
+            for(int f = 0; f < E; f++) {
+                S_V[lane * LD + f] = v[f];
+                if(f == lane) S_A[lane * LD + f] = a[f];
+            }
+        }
+        __syncwarp();
+        return ok;
+    }
+};
+#endif
+
 // EC > 0: the number of valid members is the compile-time constant EC (loops over the members unroll without guards, the
 // strides of the shared matrices are immediates); EC == 0: any number up to ENSI_EMAX.
+#ifdef ENSI_REGISTER_JACOBI
+#define ENSI_MINB_FOR(EC) (((EC) > 0 && (EC) <= 20 && (EC) % 2 == 0) ? 7 : ENSI_MINB)
+#else
+#define ENSI_MINB_FOR(EC) ENSI_MINB
+#endif
 template <int SMODE, int EC>
-__global__ void __launch_bounds__(ENSI_WARPS * 32, ENSI_MINB) ensi_kernel(const __grid_constant__ EnsiParams P) {
+__global__ void __launch_bounds__(ENSI_WARPS * 32, ENSI_MINB_FOR(EC)) ensi_kernel(const __grid_constant__ EnsiParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     EnsiSmem S;
     S.bind(smem_raw + (size_t) (threadIdx.x >> 5) * P.smem_per_warp, P.off, P.E, P.ld);
@@ -260,6 +386,17 @@ __global__ void __launch_bounds__(ENSI_WARPS * 32, ENSI_MINB) ensi_kernel(const 
         __syncwarp();
         // ---- cyclic Jacobi, parallel (round-robin) ordering: E/2 disjoint rotations per round
         bool bad = false;
+#ifdef ENSI_REGISTER_JACOBI
+        constexpr bool REGJ = EC > 0 && EC <= 20 && EC % 2 == 0;
+#else
+        constexpr bool REGJ = false;
+#endif
+        if constexpr(REGJ) {
+#ifdef ENSI_REGISTER_JACOBI
+            bad = !RegisterJacobi<REGJ ? EC : 2>::run(S.A, S.V, LD, S.cs, S.t, lane);   // S.t: [E] doubles, free until after the eigenvalues
+#endif
+        }
+        else
         for(int sweep = 0; sweep < 30; sweep++) {
             double off = 0.0, dg = 0.0;
             if(lane < E)
