@@ -214,7 +214,7 @@ struct RegisterJacobi {
         }
     }
     // A (rows in S_A) is diagonalised, V (rows in S_V) accumulates the rotations; returns false when A is not finite
-    static __device__ __noinline__ bool run(double* S_A, double* S_V, int LD, double2* cs, double* apq_s, int lane) {
+    static __device__ __forceinline__ bool run(double* S_A, double* S_V, int LD, double2* cs, double* apq_s, int lane) {
         double a[E], v[E];
         #pragma unroll
         for(int f = 0; f < E; f++) {
