@@ -519,6 +519,9 @@ class _Family(StructureFunction):
             d.n_terms = 1
             d.term[0].type = self._TYPE
             d.term[0].min_rho = min_rho
+            # placeholder: the scales live in the field. NaN scales make every entry point that takes a plain descriptor
+            # (EnSI, the device-resident forms) refuse it instead of analysing with a localization distance of 0.
+            d.term[0].h = d.term[0].v = d.term[0].w = d.term[0].loc_dist = float("nan")
             StructureFunction.__init__(self, d)
             return
         h = args[0]

@@ -70,6 +70,12 @@ _proto("gpp_optimal_interpolation_host", C.c_int, vp, fp, fp, vp, fp, fp, fp, fp
 _proto("gpp_oi_obs_create", C.c_int, vp, fp, fp, fp, fp, sp, C.POINTER(vp))
 _proto("gpp_oi_obs_destroy", None, vp)
 _proto("gpp_optimal_interpolation_device", C.c_int, vp, C.c_int, C.c_int, vp, vp, vp, sp, C.c_int, C.c_int, vp, vp, vp)
+_proto("gpp_oi_workspace_bytes", C.c_size_t)
+_proto("gpp_optimal_interpolation_device_ws", C.c_int, vp, C.c_int, C.c_int, vp, vp, vp, sp, C.c_int, C.c_int, vp, vp, vp, C.c_size_t, vp)
+_proto("gpp_ensi_obs_create", C.c_int, vp, fp, fp, fp, C.c_int, ip, sp, C.POINTER(vp))
+_proto("gpp_ensi_obs_destroy", None, vp)
+_proto("gpp_ensi_valid_members_device", C.c_int, vp, C.c_longlong, C.c_int, ip, vp)
+_proto("gpp_optimal_interpolation_ensi_device", C.c_int, vp, C.c_int, C.c_int, vp, C.c_int, vp, sp, C.c_int, C.c_int, vp, vp, vp)
 _proto("gpp_optimal_interpolation_ensi_host", C.c_int, vp, fp, C.c_int, vp, fp, fp, fp, sp, C.c_int, C.c_int, fp, ip)
 _proto("gpp_neighbourhood_host", C.c_int, fp, C.c_int, C.c_int, C.c_int, C.c_int, fp)
 _proto("gpp_neighbourhood_device", C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp)
@@ -96,6 +102,8 @@ EXPORTS = [
     "gpp_points_coordinate_type", "gpp_points_get_xyz", "gpp_convert_coordinates", "gpp_points_nearest_host", "gpp_points_neighbours_host",
     "gpp_points_closest_host", "gpp_nearest_host", "gpp_optimal_interpolation_host", "gpp_oi_obs_create",
     "gpp_oi_obs_destroy", "gpp_optimal_interpolation_device", "gpp_optimal_interpolation_ensi_host",
+    "gpp_oi_workspace_bytes", "gpp_optimal_interpolation_device_ws", "gpp_ensi_obs_create", "gpp_ensi_obs_destroy",
+    "gpp_ensi_valid_members_device", "gpp_optimal_interpolation_ensi_device",
     "gpp_neighbourhood_host", "gpp_neighbourhood_device", "gpp_neighbourhood_quantile_fast_host",
     "gpp_neighbourhood_quantile_fast_device", "gpp_neighbourhood_ens_host", "gpp_neighbourhood_ens_device",
     "gpp_neighbourhood_quantile_fast_ens_host", "gpp_neighbourhood_quantile_fast_ens_device",

@@ -41,7 +41,8 @@ struct EnsiParams {
     int k;
     int allow_extrapolation;
     int* num_skipped;
-    int* work_counter;            // next block of ENSI_GRAB points to hand out (zeroed before the launch)
+    int* work_counter;            // [0] next block of ENSI_GRAB points to hand out, [1] warps that ran out of work; both zero
+                                  // between launches (the last warp of a launch resets them)
     int ld;                       // leading dimension of the shared matrices: E rounded up to odd
     int smem_per_warp;            // bytes, see EnsiSmem::layout
     int off[20];                  // byte offsets of the per-warp arrays (EnsiSmem::layout), read from constant memory
@@ -482,7 +483,7 @@ __global__ void __launch_bounds__(ENSI_WARPS * 32, ENSI_MINB_FOR(EC)) ensi_kerne
         bad = bad || __any_sync(0xffffffffu, !(lam > 0.0) || isinf(lam));
         warm = !bad;
         if(bad) {
-            if(lane == 0 && emit) atomicAdd(P.num_skipped, 1);
+            if(lane == 0 && emit && P.num_skipped) atomicAdd(P.num_skipped, 1);
             continue;
         }
         if(!emit) continue;   // replayed for the warm-start chain only
@@ -545,6 +546,14 @@ __global__ void __launch_bounds__(ENSI_WARPS * 32, ENSI_MINB_FOR(EC)) ensi_kerne
         __syncwarp();
     }
     }
+    if(lane == 0) {   // the last warp to run out of work leaves the counters ready for the next launch
+        __threadfence();
+        if(atomicAdd(P.work_counter + 1, 1) == (int) (gridDim.x * ENSI_WARPS) - 1) {
+            P.work_counter[0] = 0;
+            P.work_counter[1] = 0;
+            __threadfence();
+        }
+    }
 }
 
 // util.cpp:19-43, Mean branch of calc_statistic: float accumulation over the valid values
@@ -556,7 +565,174 @@ float mean_valid(const float* a, int n) {
     return count > 0 ? total / count : NAN;
 }
 
+constexpr unsigned ENSI_COUNTER_SLOTS = 16;
 }  // namespace
+
+// Observation side of an EnSI call, resident on the device: the bucket grid over the observations with a valid value
+// (oi_ensi.cpp:232), sigma and obs - yhat per observation, and the perturbations of the background at the observation
+// points about their ensemble mean (oi_ensi.cpp:163-178) for the valid members.
+struct gpp_ensi_obs {
+    gpp_oi_obs table;
+    gpp::DeviceBuffer<float> gY;          // [table slot][E]
+    gpp::DeviceBuffer<int> counters;      // ENSI_COUNTER_SLOTS x {next block, warps done}, zero between launches
+    mutable std::atomic<unsigned> next_slot{0};
+    int nE = 0, E = 0;
+    int valid_ens[ENSI_EMAX];
+};
+
+namespace {
+int build_ensi_obs(gpp_ensi_obs& st, const gpp_points* opoints, const float* pobs, const float* psigmas, const float* pbackground, int nE,
+                   const int* member_valid, const gpp_structure* structure) {
+    const int nS = opoints->n;
+    st.nE = nE;
+    st.E = 0;
+    for(int e = 0; e < nE; e++)
+        if(!member_valid || member_valid[e]) {
+            if(st.E >= ENSI_EMAX)
+                return fail(GPP_ERR_NOT_IMPLEMENTED, "optimal_interpolation_ensi supports at most %d valid ensemble members on the device", ENSI_EMAX);
+            st.valid_ens[st.E++] = e;
+        }
+    // ---- oi_ensi.cpp:163-178: remove the ensemble mean at the observation points
+    std::vector<float> gY(pbackground, pbackground + (size_t) nS * nE), gYhat(nS);
+    for(int i = 0; i < nS; i++) {
+        float mean = mean_valid(&gY[(size_t) i * nE], nE);
+        for(int e = 0; e < nE; e++) {
+            float value = gY[(size_t) i * nE + e];
+            if(is_valid(value) && is_valid(mean)) gY[(size_t) i * nE + e] -= mean;
+        }
+        gYhat[i] = mean;
+    }
+    // ---- observation table: only pobs validity is required here (oi_ensi.cpp:232)
+    std::vector<char> valid(nS);
+    std::vector<double> innov(nS);
+    std::vector<float> sig(psigmas, psigmas + nS);
+    for(int i = 0; i < nS; i++) {
+        valid[i] = is_valid(pobs[i]);
+        innov[i] = (double) pobs[i] - (double) gYhat[i];   // lObs - lYhat, oi_ensi.cpp:437
+    }
+    std::vector<int> order;
+    GPP_TRY(build_obs_table(opoints, valid, innov, sig, structure->term[0].loc_dist, &st.table, &order));
+    const int E = st.E;
+    std::vector<float> gYs(std::max<size_t>(1, order.size() * (size_t) std::max(E, 1)));
+    for(size_t slot = 0; slot < order.size(); slot++)
+        for(int e = 0; e < E; e++) gYs[slot * E + e] = gY[(size_t) order[slot] * nE + st.valid_ens[e]];
+    GPP_TRY(st.gY.upload(gYs.data(), gYs.size()));
+    GPP_TRY(st.counters.alloc(2 * ENSI_COUNTER_SLOTS));
+    GPP_CUDA(cudaMemsetAsync(st.counters.ptr, 0, sizeof(int) * 2 * ENSI_COUNTER_SLOTS, 0));
+    GPP_CUDA(cudaStreamSynchronize(0));   // the staging vectors go out of scope
+    return GPP_OK;
+}
+
+// Largest number of observations per point the kernel must hold (0 = nothing to do); max_points == 0 needs a counting pass
+int ensi_kcap(const gpp_ensi_obs& st, gpp_points* bp, int first, int count, const gpp_structure* structure, int max_points, cudaStream_t stream, int* out) {
+    int kcap = max_points > 0 ? std::min(max_points, st.table.n_valid) : st.table.n_valid;
+    if(max_points == 0 && kcap > ENSI_KMAX) {
+        int hmax = 0;
+        GPP_TRY(count_max_candidates(bp, first, count, nullptr, st.table.view(), structure->term[0].loc_dist, stream, &hmax));
+        kcap = std::min(kcap, std::max(hmax, 1));
+    }
+    if(kcap > ENSI_KMAX)
+        return fail(GPP_ERR_NOT_IMPLEMENTED, "optimal_interpolation_ensi supports at most %d observations per point on the device (got %d)", ENSI_KMAX, kcap);
+    *out = kcap;
+    return GPP_OK;
+}
+
+// Analyses points [first, first + count): d_analysis must already hold the background there. One kernel launch.
+int ensi_launch(const gpp_ensi_obs& st, gpp_points* bp, int first, int count, const float* d_background, float* d_analysis,
+                const gpp_structure* structure, int kcap, int allow_extrapolation, int* d_num_skipped, int* counter_pair, cudaStream_t stream) {
+    if(st.E == 0 || st.table.n_valid == 0 || count == 0) return GPP_OK;
+    EnsiParams P;
+    std::memset(&P, 0, sizeof(P));
+    for(int e = 0; e < st.E; e++) P.valid_ens[e] = st.valid_ens[e];
+    P.gx = bp->dx.ptr; P.gy = bp->dy.ptr; P.gz = bp->dz.ptr; P.gelev = bp->delev.ptr; P.glaf = bp->dlaf.ptr;
+    P.background = d_background;
+    P.analysis = d_analysis;
+    P.first = first; P.count = count; P.nE = st.nE; P.E = st.E;
+    P.obs = st.table.view();
+    P.gY = st.gY.ptr;
+    P.s = *structure;
+    P.R = structure->term[0].loc_dist;
+    P.allow_extrapolation = allow_extrapolation;
+    P.num_skipped = d_num_skipped;
+    P.work_counter = counter_pair;
+    P.k = kcap;
+    const int E = st.E;
+    P.ld = E | 1;
+    P.smem_per_warp = (int) EnsiSmem::layout(P.off, E, kcap, P.ld);
+    const size_t smem = (size_t) P.smem_per_warp * ENSI_WARPS;
+    const int mode = structure_mode(*structure);
+    void (*kernel)(EnsiParams) = nullptr;
+    switch(E) {   // the common ensemble sizes get their own instantiation
+        case 10: kernel = mode == 1 ? ensi_kernel<1, 10> : ensi_kernel<0, 10>; break;
+        case 20: kernel = mode == 1 ? ensi_kernel<1, 20> : ensi_kernel<0, 20>; break;
+        case 30: kernel = mode == 1 ? ensi_kernel<1, 30> : ensi_kernel<0, 30>; break;
+        default: kernel = mode == 1 ? ensi_kernel<1, 0> : ensi_kernel<0, 0>; break;
+    }
+    GPP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    const long long want = ((long long) count + ENSI_WARPS - 1) / ENSI_WARPS;
+    int per_sm = 1;   // what actually fits (registers and shared memory): one wave of resident CTAs
+    GPP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, ENSI_WARPS * 32, smem));
+    const unsigned grid = (unsigned) std::max<long long>(1, std::min<long long>(want, (long long) sm_count() * std::max(per_sm, 1)));
+    GPP_LAUNCH(kernel, grid, ENSI_WARPS * 32, smem, stream, P);
+    return GPP_OK;
+}
+}  // namespace
+
+extern "C" int gpp_ensi_obs_create(const gpp_points* opoints, const float* pobs, const float* psigmas, const float* pbackground, int nE,
+                                   const int* member_valid, const gpp_structure* structure, gpp_ensi_obs** out) {
+    if(!out) return fail(GPP_ERR_INVALID_ARGUMENT, "out must not be NULL");
+    *out = nullptr;
+    if(!opoints || !structure || !pobs || !psigmas || !pbackground) return fail(GPP_ERR_INVALID_ARGUMENT, "NULL argument");
+    if(nE < 0) return fail(GPP_ERR_INVALID_ARGUMENT, "negative ensemble size");
+    GPP_TRY(reject_unset_scales(structure));
+    GPP_TRY(ensure_device());
+    gpp_ensi_obs* st = new(std::nothrow) gpp_ensi_obs();
+    if(!st) return fail(GPP_ERR_RUNTIME, "out of memory");
+    const int rc = build_ensi_obs(*st, opoints, pobs, psigmas, pbackground, nE, member_valid, structure);
+    if(rc != GPP_OK) { delete st; return rc; }
+    *out = st;
+    return GPP_OK;
+}
+extern "C" void gpp_ensi_obs_destroy(gpp_ensi_obs* obs) { delete obs; }
+
+extern "C" int gpp_ensi_valid_members_device(const float* d_background, long long n_points, int nE, int* member_valid, void* stream_) {
+    cudaStream_t stream = (cudaStream_t) stream_;
+    if(nE < 0 || n_points < 0 || !member_valid) return fail(GPP_ERR_INVALID_ARGUMENT, "bad argument");
+    GPP_TRY(ensure_device());
+    if(nE == 0) return GPP_OK;
+    DeviceBuffer<int> d_flags;
+    GPP_TRY(d_flags.alloc(nE));
+    GPP_CUDA(cudaMemsetAsync(d_flags.ptr, 0, sizeof(int) * nE, stream));
+    const size_t n = (size_t) n_points * nE;
+    if(n) GPP_LAUNCH(ensi_invalid_members_kernel, (unsigned) ((n + 255) / 256), 256, 0, stream, d_background, n, nE, d_flags.ptr);
+    std::vector<int> flags(nE);
+    GPP_TRY(d_flags.download(flags.data(), nE, stream));
+    GPP_CUDA(cudaStreamSynchronize(stream));
+    for(int e = 0; e < nE; e++) member_valid[e] = !flags[e];
+    return GPP_OK;
+}
+
+extern "C" int gpp_optimal_interpolation_ensi_device(const gpp_points* cbp, int first, int count, const float* d_background, int nE,
+                                                     const gpp_ensi_obs* obs, const gpp_structure* structure, int max_points,
+                                                     int allow_extrapolation, float* d_analysis, int* d_num_skipped, void* stream_) {
+    cudaStream_t stream = (cudaStream_t) stream_;
+    if(max_points < 0) return fail(GPP_ERR_INVALID_ARGUMENT, "max_points must be >= 0");   // oi_ensi.cpp:124-125
+    if(!cbp || !obs || !structure) return fail(GPP_ERR_INVALID_ARGUMENT, "NULL argument");
+    if(nE != obs->nE) return fail(GPP_ERR_INVALID_ARGUMENT, "the observation state was built for %d members, not %d", obs->nE, nE);
+    gpp_points* bp = const_cast<gpp_points*>(cbp);
+    if(first < 0 || count < 0 || first + count > bp->n) return fail(GPP_ERR_INVALID_ARGUMENT, "background range out of bounds");
+    GPP_TRY(reject_unset_scales(structure));
+    if(count == 0 || nE == 0) return GPP_OK;
+    GPP_TRY(bp->ensure_on_device());
+    if(d_analysis != d_background)   // oi_ensi.cpp:148: the analysis starts as the background
+        GPP_CUDA(cudaMemcpyAsync(d_analysis + (size_t) first * nE, d_background + (size_t) first * nE, sizeof(float) * (size_t) count * nE,
+                                 cudaMemcpyDeviceToDevice, stream));
+    if(obs->E == 0 || obs->table.n_valid == 0) return GPP_OK;
+    int kcap = 0;
+    GPP_TRY(ensi_kcap(*obs, bp, first, count, structure, max_points, stream, &kcap));
+    int* pair = obs->counters.ptr + 2 * (obs->next_slot.fetch_add(1, std::memory_order_relaxed) % ENSI_COUNTER_SLOTS);
+    return ensi_launch(*obs, bp, first, count, d_background, d_analysis, structure, kcap, allow_extrapolation, d_num_skipped, pair, stream);
+}
 
 extern "C" int gpp_optimal_interpolation_ensi_host(const gpp_points* cbp, const float* background, int nE, const gpp_points* opoints,
                                                    const float* pobs, const float* psigmas, const float* pbackground,
@@ -575,29 +751,20 @@ extern "C" int gpp_optimal_interpolation_ensi_host(const gpp_points* cbp, const 
     }
     if(bp->type != opoints->type)
         return fail(GPP_ERR_INVALID_ARGUMENT, "Both background and observations points must be of same coorindate type (lat/lon or x/y)");
+    GPP_TRY(reject_unset_scales(structure));
     GPP_TRY(ensure_device());
     if(nBE == 0) return GPP_OK;
     Trace trace("optimal_interpolation_ensi_host");
 
-    // ---- observation side on the host (oi_ensi.cpp:163-178): remove the ensemble mean at the observation points
-    std::vector<float> gY(pbackground, pbackground + (size_t) nS * nE), gYhat(nS);
-    for(int i = 0; i < nS; i++) {
-        float mean = mean_valid(&gY[(size_t) i * nE], nE);
-        for(int e = 0; e < nE; e++) {
-            float value = gY[(size_t) i * nE + e];
-            if(is_valid(value) && is_valid(mean)) gY[(size_t) i * nE + e] -= mean;
-        }
-        gYhat[i] = mean;
-    }
     // ---- valid members (oi_ensi.cpp:187-201): a member with an invalid value anywhere in the background is left alone.
     // Large fields are scanned on the host (threads) so that their upload can be pipelined with the analysis, block by
     // block; small ones are uploaded at once and scanned on the device.
-    DeviceBuffer<float> d_bg, d_out, d_gY;
-    DeviceBuffer<int> d_flags;
+    DeviceBuffer<float> d_bg, d_out;
+    DeviceBuffer<int> d_skipped;
     const int n_chunks = nB >= (1 << 18) ? ENSI_CHUNKS : 1;
-    std::vector<int> flags(nE + 1, 0);
-    GPP_TRY(d_flags.alloc(nE + 1 + ENSI_CHUNKS));   // per-member invalid flags, the skipped-point count, the work counters
-    GPP_CUDA(cudaMemsetAsync(d_flags.ptr, 0, sizeof(int) * (nE + 1 + ENSI_CHUNKS), 0));
+    std::vector<int> member_valid(std::max(nE, 1), 1);
+    GPP_TRY(d_skipped.alloc(1));
+    GPP_CUDA(cudaMemsetAsync(d_skipped.ptr, 0, sizeof(int), 0));
     if(n_chunks > 1) {
         GPP_TRY(d_bg.alloc(nBE));
         std::vector<unsigned char> bad((size_t) nE, 0);
@@ -614,120 +781,53 @@ extern "C" int gpp_optimal_interpolation_ensi_host(const gpp_points* cbp, const 
             #pragma omp critical
             for(int e = 0; e < nE; e++) bad[e] |= mine[e];
         }
-        for(int e = 0; e < nE; e++) flags[e] = bad[e];
+        for(int e = 0; e < nE; e++) member_valid[e] = !bad[e];
         trace.lap("valid-member scan (host)");
     }
     else {
         GPP_TRY(d_bg.upload(background, nBE));
-        GPP_LAUNCH(ensi_invalid_members_kernel, (unsigned) ((nBE + 255) / 256), 256, 0, 0, d_bg.ptr, nBE, nE, d_flags.ptr);
-        GPP_TRY(d_flags.download(flags.data(), nE + 1));
-        GPP_CUDA(cudaStreamSynchronize(0));
+        GPP_TRY(gpp_ensi_valid_members_device(d_bg.ptr, nB, nE, member_valid.data(), nullptr));
         trace.lap("H2D + valid-member scan");
     }
-    EnsiParams P;
-    std::memset(&P, 0, sizeof(P));
-    bool downloaded = false;
-    int E = 0;
-    for(int e = 0; e < nE; e++)
-        if(!flags[e]) {
-            if(E >= ENSI_EMAX)
-                return fail(GPP_ERR_NOT_IMPLEMENTED, "optimal_interpolation_ensi supports at most %d valid ensemble members on the device", ENSI_EMAX);
-            P.valid_ens[E++] = e;
-        }
+    gpp_ensi_obs st;
+    GPP_TRY(build_ensi_obs(st, opoints, pobs, psigmas, pbackground, nE, member_valid.data(), structure));
     GPP_TRY(d_out.alloc(nBE));
     if(n_chunks == 1) GPP_CUDA(cudaMemcpyAsync(d_out.ptr, d_bg.ptr, sizeof(float) * nBE, cudaMemcpyDeviceToDevice, 0));   // oi_ensi.cpp:148
-    if(E > 0) {
-        // ---- observation table: only pobs validity is required here (oi_ensi.cpp:232)
-        std::vector<char> valid(nS);
-        std::vector<double> innov(nS);
-        std::vector<float> sig(psigmas, psigmas + nS);
-        for(int i = 0; i < nS; i++) {
-            valid[i] = is_valid(pobs[i]);
-            innov[i] = (double) pobs[i] - (double) gYhat[i];   // lObs - lYhat, oi_ensi.cpp:437
-        }
-        gpp_oi_obs obs;
-        std::vector<int> order;
-        GPP_TRY(build_obs_table(opoints, valid, innov, sig, structure->term[0].loc_dist, &obs, &order));
-        std::vector<float> gYs(std::max<size_t>(1, order.size() * (size_t) E));
-        for(size_t slot = 0; slot < order.size(); slot++)
-            for(int e = 0; e < E; e++) gYs[slot * E + e] = gY[(size_t) order[slot] * nE + P.valid_ens[e]];
-        GPP_TRY(d_gY.upload(gYs.data(), gYs.size()));
+    bool downloaded = false;
+    if(st.E > 0 && st.table.n_valid > 0) {
         GPP_TRY(bp->ensure_on_device());
-        if(obs.n_valid > 0) {
-            P.gx = bp->dx.ptr; P.gy = bp->dy.ptr; P.gz = bp->dz.ptr; P.gelev = bp->delev.ptr; P.glaf = bp->dlaf.ptr;
-            P.background = d_bg.ptr;
-            P.analysis = d_out.ptr;
-            P.first = 0; P.count = nB; P.nE = nE; P.E = E;
-            P.obs = obs.view();
-            P.gY = d_gY.ptr;
-            P.s = *structure;
-            P.R = structure->term[0].loc_dist;
-            P.allow_extrapolation = allow_extrapolation;
-            P.num_skipped = d_flags.ptr + nE;
-            int kcap = max_points > 0 ? std::min(max_points, obs.n_valid) : obs.n_valid;
-            if(max_points == 0 && kcap > ENSI_KMAX) {
-                int hmax = 0;
-                GPP_TRY(count_max_candidates(bp, 0, nB, nullptr, P.obs, P.R, 0, &hmax));
-                kcap = std::min(kcap, std::max(hmax, 1));
+        int kcap = 0;
+        GPP_TRY(ensi_kcap(st, bp, 0, nB, structure, max_points, 0, &kcap));   // once for the whole field: every block takes the same kernel
+        // blocks of points, each returned to the host (through pinned staging) while the next ones are analysed; every
+        // block has its own work counter because consecutive blocks overlap on the device
+        std::vector<size_t> bounds(n_chunks + 1);
+        for(int c = 0; c <= n_chunks; c++) bounds[c] = (size_t) ((long long) nB * c / n_chunks) * nE;
+        static_assert(ENSI_CHUNKS <= (int) ENSI_COUNTER_SLOTS, "one counter pair per block in flight");
+        auto launch = [&](int c, cudaStream_t stream) {
+            const int first = (int) (bounds[c] / nE), count = (int) ((bounds[c + 1] - bounds[c]) / nE);
+            if(n_chunks > 1) {   // this block's slice of the background comes in on the stream that analyses it
+                const size_t n = bounds[c + 1] - bounds[c];
+                GPP_CUDA(cudaMemcpyAsync(d_bg.ptr + bounds[c], background + bounds[c], sizeof(float) * n, cudaMemcpyHostToDevice, stream));
+                GPP_CUDA(cudaMemcpyAsync(d_out.ptr + bounds[c], d_bg.ptr + bounds[c], sizeof(float) * n, cudaMemcpyDeviceToDevice, stream));
             }
-            if(kcap > ENSI_KMAX)
-                return fail(GPP_ERR_NOT_IMPLEMENTED, "optimal_interpolation_ensi supports at most %d observations per point on the device (got %d)", ENSI_KMAX, kcap);
-            P.k = kcap;
-            P.ld = E | 1;
-            P.smem_per_warp = (int) EnsiSmem::layout(P.off, E, kcap, P.ld);
-            const size_t smem = (size_t) P.smem_per_warp * ENSI_WARPS;
-            const int mode = structure_mode(*structure);
-            void (*kernel)(EnsiParams) = nullptr;
-            switch(E) {   // the common ensemble sizes get their own instantiation
-                case 10: kernel = mode == 1 ? ensi_kernel<1, 10> : ensi_kernel<0, 10>; break;
-                case 20: kernel = mode == 1 ? ensi_kernel<1, 20> : ensi_kernel<0, 20>; break;
-                case 30: kernel = mode == 1 ? ensi_kernel<1, 30> : ensi_kernel<0, 30>; break;
-                default: kernel = mode == 1 ? ensi_kernel<1, 0> : ensi_kernel<0, 0>; break;
-            }
-            GPP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-            const long long want = ((long long) nB + ENSI_WARPS - 1) / ENSI_WARPS;
-            int per_sm = 1;   // what actually fits (registers and shared memory): one wave of resident CTAs
-            GPP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, ENSI_WARPS * 32, smem));
-            const unsigned grid = (unsigned) std::max<long long>(1, std::min<long long>(want, (long long) sm_count() * std::max(per_sm, 1)));
-            // blocks of points, each returned to the host (through pinned staging) while the next ones are analysed; every
-            // block has its own work counter because consecutive blocks overlap on the device
-            std::vector<size_t> bounds(n_chunks + 1);
-            for(int c = 0; c <= n_chunks; c++) bounds[c] = (size_t) ((long long) nB * c / n_chunks) * nE;
-            int* counters = d_flags.ptr + nE + 1;
-            auto launch = [&](int c, cudaStream_t stream) {
-                EnsiParams Q = P;
-                Q.first = (int) (bounds[c] / nE);
-                Q.count = (int) ((bounds[c + 1] - bounds[c]) / nE);
-                Q.work_counter = counters + c;
-                if(n_chunks > 1) {   // this block's slice of the background comes in on the stream that analyses it
-                    const size_t n = bounds[c + 1] - bounds[c];
-                    GPP_CUDA(cudaMemcpyAsync(d_bg.ptr + bounds[c], background + bounds[c], sizeof(float) * n, cudaMemcpyHostToDevice, stream));
-                    GPP_CUDA(cudaMemcpyAsync(d_out.ptr + bounds[c], d_bg.ptr + bounds[c], sizeof(float) * n, cudaMemcpyDeviceToDevice, stream));
-                }
-                GPP_LAUNCH(kernel, grid, ENSI_WARPS * 32, smem, stream, Q);
-                return (int) GPP_OK;
-            };
-            if(n_chunks > 1) {
-                GPP_TRY(pipelined_download(bounds, launch, d_out.ptr, analysis, true));
-                downloaded = true;
-            }
-            else GPP_TRY(launch(0, 0));
+            return ensi_launch(st, bp, first, count, d_bg.ptr, d_out.ptr, structure, kcap, allow_extrapolation, d_skipped.ptr,
+                               st.counters.ptr + 2 * c, stream);
+        };
+        if(n_chunks > 1) {
+            GPP_TRY(pipelined_download(bounds, launch, d_out.ptr, analysis, true));
+            downloaded = true;
         }
+        else GPP_TRY(launch(0, 0));
         if(trace.on) { cudaStreamSynchronize(0); trace.lap(downloaded ? "H2D + kernel + D2H (pipelined)" : "kernel"); }
-        if(!downloaded) {
-            // nothing was analysed (no valid observation): the analysis is the background (oi_ensi.cpp:148)
-            if(n_chunks > 1) std::memcpy(analysis, background, sizeof(float) * nBE);
-            else GPP_TRY(d_out.download(analysis, nBE));
-        }
-        if(num_skipped) GPP_CUDA(cudaMemcpyAsync(num_skipped, d_flags.ptr + nE, sizeof(int), cudaMemcpyDeviceToHost, 0));
-        GPP_CUDA(cudaStreamSynchronize(0));   // `obs` and the staging vectors go out of scope after this
-        trace.lap("D2H");
-        return GPP_OK;
     }
-    // no valid member: the analysis is the background
-    if(n_chunks > 1) std::memcpy(analysis, background, sizeof(float) * nBE);
-    else GPP_TRY(d_out.download(analysis, nBE));
-    GPP_CUDA(cudaStreamSynchronize(0));
+    if(!downloaded) {
+        // one block, or nothing was analysed (no valid member / observation): the analysis is d_out or the background (oi_ensi.cpp:148)
+        if(n_chunks > 1) std::memcpy(analysis, background, sizeof(float) * nBE);
+        else GPP_TRY(d_out.download(analysis, nBE));
+    }
+    if(num_skipped) GPP_CUDA(cudaMemcpyAsync(num_skipped, d_skipped.ptr, sizeof(int), cudaMemcpyDeviceToHost, 0));
+    GPP_CUDA(cudaStreamSynchronize(0));   // `st` and the staging vectors go out of scope after this
+    trace.lap("D2H");
     return GPP_OK;
 }
 

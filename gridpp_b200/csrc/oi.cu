@@ -29,8 +29,33 @@ namespace {
 constexpr int FAST_K = 30;          // max observations per point on the register path
 constexpr int WARPS_PER_CTA = 8;
 
+#ifndef OI_LRU
+#define OI_LRU 8
+#endif
+#ifndef OI_TOP_SHIFT
+#define OI_TOP_SHIFT 2
+#endif
+constexpr int LRU_ENTRIES = OI_LRU;           // solved systems a warp remembers
+constexpr int TOP_SHIFT = OI_TOP_SHIFT;       // the largest work unit is (1 << TOP_SHIFT)^2 tiles of 4 x 4 points
+constexpr int N_LEVELS = TOP_SHIFT + 1;       // unit sizes (1 << TOP_SHIFT)^2, ..., 4, 1 tiles
+static_assert(TOP_SHIFT >= 0 && TOP_SHIFT <= 3, "unit sizes up to 8 x 8 tiles");
+
+// Work units of the register path, largest first: level l holds units of (1 << (TOP_SHIFT - l))^2 tiles (grids) or that
+// many 16-point runs (point sets). end[l] = number of units of levels 0..l, base[l] = first tile row (run) of level l,
+// cols[l] = units per row of units.
+struct UnitPlan {
+    int n_units;
+    int end[4], base[4], cols[4];
+};
+// Head of the launch workspace; both counters are zero between launches (the kernel resets them as it ends).
+struct OiWorkHeader {
+    int next_unit;
+    int warps_done;
+};
+constexpr size_t OI_WORK_HEADER_BYTES = 256;
+
 struct OiParams {
-    // background points
+    // background points; gz / gelev / glaf may be NULL: z = 0 (Cartesian), no elevations / land fractions (NaN)
     const float *gx, *gy, *gz, *gelev, *glaf;
     const float* background;
     const float* bvariance;          // may be NULL (= 1)
@@ -43,8 +68,9 @@ struct OiParams {
     int k;                           // max observations per point (> 0)
     int allow_extrapolation;
     int tile_nx;                     // > 0: the range is whole rows of a grid with this row length -> 4 x 4 tiles
-    unsigned char* lru;              // per-warp cache of solved systems (LRU_ENTRIES x LruEntry), global memory
-    int* work_counter;               // next chunk of runs to hand out (zeroed before the launch)
+    unsigned char* workspace;        // register path: OiWorkHeader + one LruBlock per warp (gpp_oi_workspace_bytes)
+    UnitPlan plan;                   // register path: how the range is cut into work units (oi_plan_units)
+    int* work_counter;               // Cholesky path: next block of points to hand out (zeroed before the launch)
     // spatially varying structure function (general kernel only): scales at every background point, and the constants of
     // localization_distance(h) = loc_c * h (Toar: (float) (loc_d * h), structure.cpp:603-609)
     const float *sbh, *sbv, *sbw;
@@ -69,9 +95,21 @@ __device__ __forceinline__ void write_result(const OiParams& P, int g, float bg,
     }
 }
 
+// background point g; planes the point set does not have are not read (20 -> 8 bytes per point for a Cartesian grid
+// without elevations and land fractions)
+__device__ __forceinline__ Pt bg_point(const OiParams& P, int g) {
+    Pt p;
+    p.x = P.gx[g]; p.y = P.gy[g];
+    p.z = P.gz ? P.gz[g] : 0.f;
+    p.elev = P.gelev ? P.gelev[g] : NAN;
+    p.laf = P.glaf ? P.glaf[g] : NAN;
+    return p;
+}
+
 constexpr int RUN = 16;             // consecutive background points analysed by one warp
 constexpr int NPAIR_LUT = 496;      // 31 * 32 / 2 >= FAST_K * (FAST_K + 1) / 2
 constexpr int NCAND = 64;           // capacity of a run's candidate list (2 slots per lane)
+constexpr unsigned FULL = 0xffffffffu;
 
 struct FastSmem {
     unsigned long long key[64];     // candidate keys (oi.cuh)
@@ -100,68 +138,73 @@ struct WarpState {
     double z, dmax, dmin, avar;
 };
 
-// A solved system kept for reuse: the set (canonical original indices), z = (P+R)^-1 d and the innovation extremes.
-#ifndef OI_LRU
-#define OI_LRU 8
-#endif
-#ifndef OI_RPC
-#define OI_RPC 16
-#endif
 #ifdef OI_STATS
-// debug build only (profiles/variants.sh -DOI_STATS): [0] points on the run path, [1] selection changes, [2] systems solved
+// debug build only (profiles/variants.sh -DOI_STATS): [0] points on the run path, [1] selection changes, [2] systems solved,
+// [3] selections that needed the full ranking
 __device__ unsigned long long g_oi_stats[4];
 #define OI_COUNT(i) do { if(lane_id() == 0) atomicAdd(&g_oi_stats[i], 1ull); } while(0)
 #else
 #define OI_COUNT(i) do {} while(0)
 #endif
-constexpr int LRU_ENTRIES = OI_LRU;
-constexpr int RUNS_PER_CHUNK = OI_RPC;   // consecutive runs (tiles) handled by one warp, so that the cache sees neighbours
-#ifndef OI_CHUNK_TY
-#define OI_CHUNK_TY 4
-#endif
-constexpr int CHUNK_TY = OI_CHUNK_TY, CHUNK_TX = RUNS_PER_CHUNK / CHUNK_TY;   // shape of a chunk in tiles (grids)
-static_assert(CHUNK_TY * CHUNK_TX == RUNS_PER_CHUNK, "OI_CHUNK_TY must divide OI_RPC");
-struct LruEntry {
-    double z[32];
-    double dmax, dmin;
-    int orig[32];
-    int k;
-    unsigned stamp;    // last use (0 = empty)
-    int pad[2];
+
+// A warp's cache of solved systems, in the launch workspace (global memory; 2368 warps x 3.4 KB stay L2-resident): the set
+// (canonical original indices), z = (P+R)^-1 d and the innovation extremes. `sig` is an order-independent hash of the set,
+// so a lookup compares one word per entry and reads an entry's indices only when the hash matches.
+struct LruBlock {
+    double z[LRU_ENTRIES][32];
+    double dmax[LRU_ENTRIES], dmin[LRU_ENTRIES];
+    int orig[LRU_ENTRIES][32];
+    unsigned sig[LRU_ENTRIES], stamp[LRU_ENTRIES];   // stamp: last use (0 = empty)
+    int k[LRU_ENTRIES];
 };
+static_assert(LRU_ENTRIES <= 32, "one lane per cache entry");
 
 // Look the canonical set S.c_orig[0..k) up in the warp's cache; on a hit load its solution into W.
-__device__ __forceinline__ bool lru_lookup(LruEntry* cache, const FastSmem& S, int k, unsigned now, WarpState& W) {
+__device__ __forceinline__ bool lru_lookup(LruBlock* C, const FastSmem& S, int k, unsigned now, WarpState& W, unsigned& sig) {
     const int lane = (int) lane_id();
     const int mine = lane < k ? S.c_orig[lane] : -1;
-    for(int e = 0; e < LRU_ENTRIES; e++) {
-        LruEntry& E = cache[e];
-        if(E.stamp == 0 || E.k != k) continue;
-        if(__all_sync(0xffffffffu, E.orig[lane] == mine)) {
-            W.z = E.z[lane];
-            W.dmax = E.dmax;
-            W.dmin = E.dmin;
+    sig = __reduce_add_sync(FULL, (unsigned) (mine + 1) * 0x9E3779B1u);
+    unsigned m = __ballot_sync(FULL, lane < LRU_ENTRIES && C->stamp[lane] != 0 && C->sig[lane] == sig && C->k[lane] == k);
+    while(m) {
+        const int e = __ffs(m) - 1;
+        m &= m - 1;
+        if(__all_sync(FULL, C->orig[e][lane] == mine)) {
+            W.z = C->z[e][lane];
+            W.dmax = C->dmax[e];
+            W.dmin = C->dmin[e];
             W.prev_orig = mine;
             W.prev_k = k;
-            if(lane == 0) E.stamp = now;
+            if(lane == 0) C->stamp[e] = now;
             __syncwarp();
             return true;
         }
     }
     return false;
 }
-__device__ __forceinline__ void lru_store(LruEntry* cache, int k, unsigned now, const WarpState& W) {
+__device__ __forceinline__ void lru_store(LruBlock* C, int k, unsigned now, const WarpState& W, unsigned sig) {
     const int lane = (int) lane_id();
-    int victim = 0;
-    unsigned oldest = cache[0].stamp;
-    for(int e = 1; e < LRU_ENTRIES; e++)
-        if(cache[e].stamp < oldest) { oldest = cache[e].stamp; victim = e; }
+    // victim: the least recently used entry (empty ones first)
+    const unsigned age = lane < LRU_ENTRIES ? (C->stamp[lane] << 5) | (unsigned) lane : 0xffffffffu;
+    const int victim = (int) (__reduce_min_sync(FULL, age) & 31u);
+    C->z[victim][lane] = W.z;
+    C->orig[victim][lane] = W.prev_orig;
+    if(lane == 0) { C->dmax[victim] = W.dmax; C->dmin[victim] = W.dmin; C->k[victim] = k; C->sig[victim] = sig; C->stamp[victim] = now; }
     __syncwarp();
-    LruEntry& E = cache[victim];
-    E.z[lane] = W.z;
-    E.orig[lane] = W.prev_orig;
-    if(lane == 0) { E.dmax = W.dmax; E.dmin = W.dmin; E.k = k; E.stamp = now; }
-    __syncwarp();
+}
+
+// max / min of a 64-bit key over the warp with the single-instruction 32-bit reductions (REDUX): the high words first,
+// then the low words of the lanes that hold the extreme high word. Keys are unique, so the result identifies one slot.
+__device__ __forceinline__ unsigned long long warp_max64(unsigned long long x) {
+    const unsigned hi = (unsigned) (x >> 32), lo = (unsigned) x;
+    const unsigned H = __reduce_max_sync(FULL, hi);
+    const unsigned L = __reduce_max_sync(FULL, hi == H ? lo : 0u);
+    return ((unsigned long long) H << 32) | L;
+}
+__device__ __forceinline__ unsigned long long warp_min64(unsigned long long x) {
+    const unsigned hi = (unsigned) (x >> 32), lo = (unsigned) x;
+    const unsigned H = __reduce_min_sync(FULL, hi);
+    const unsigned L = __reduce_min_sync(FULL, hi == H ? lo : 0xffffffffu);
+    return ((unsigned long long) H << 32) | L;
 }
 
 // Assemble P + R for the k observations staged in canonical order in S.c_pos / S.c_rho and solve for
@@ -269,14 +312,14 @@ __device__ __forceinline__ void keep_background(const OiParams& P, int g, float 
 // Per-point path: gather from the bucket grid, select, canonicalise, reuse or solve. Used when a run's candidate
 // list does not fit NCAND slots (dense observations, scattered points).
 template <int SMODE>
-__device__ __noinline__ void analyse_point(const OiParams& P, FastSmem& S, const unsigned short* lut, LruEntry* cache, int g, WarpState& W) {
+__device__ __noinline__ void analyse_point(const OiParams& P, FastSmem& S, const unsigned short* lut, LruBlock* cache, int g, WarpState& W) {
     const int lane = (int) lane_id();
     const CandBuf cb = {S.key, S.pos};
     const bool need_var = P.analysis_variance != nullptr;
     const float bg = P.background[g];
     int k = 0;
     if(is_valid(bg)) {   // oi.cpp:223
-        const Pt p1 = {P.gx[g], P.gy[g], P.gz[g], P.gelev[g], P.glaf[g]};
+        const Pt p1 = bg_point(P, g);
         k = gather_candidates<SMODE, 2>(P.obs, P.s, p1, P.R, P.k, cb);
     }
     if(k == 0) { keep_background(P, g, bg); return; }
@@ -298,17 +341,64 @@ __device__ __noinline__ void analyse_point(const OiParams& P, FastSmem& S, const
         __syncwarp();
     }
     const int c_orig = lane < k ? S.c_orig[lane] : -1;
-    const bool same = __all_sync(0xffffffffu, c_orig == W.prev_orig) && k == W.prev_k;
+    const bool same = __all_sync(FULL, c_orig == W.prev_orig) && k == W.prev_k;
     if(need_var) solve_selected<SMODE>(P, S, lut, k, W);
     else if(!same) {
         const unsigned now = ++W.clock;
-        if(!lru_lookup(cache, S, k, now, W)) {
+        unsigned sig;
+        if(!lru_lookup(cache, S, k, now, W, sig)) {
             solve_selected<SMODE>(P, S, lut, k, W);
-            lru_store(cache, k, now, W);
+            lru_store(cache, k, now, W, sig);
         }
     }
     finish_point(P, S, g, bg, k, W);
     __syncwarp();
+}
+
+// The reference's predicate and correlation (kdtree.cpp:46-53,247-260; oi.cpp:250-258) for the two candidates a lane holds,
+// as selection keys (0 = not a candidate of this point). SMODE 1 (one Barnes term with an active horizontal scale, no
+// cross-validation) is evaluated in straight-line code for both slots at once: no call, no divergent branch, two
+// independent exp() chains in flight.
+template <int SMODE>
+__device__ __forceinline__ void slot_keys(const OiParams& P, const Pt& p1, const Pt& q0, const Pt& q1, bool h0, bool h1, int orig0,
+                                          int orig1, unsigned long long& key0, unsigned long long& key1) {
+    const float lo0 = __fsub_rn(p1.x, P.R), lo1 = __fsub_rn(p1.y, P.R), lo2 = __fsub_rn(p1.z, P.R);
+    const float hi0 = __fadd_rn(p1.x, P.R), hi1 = __fadd_rn(p1.y, P.R), hi2 = __fadd_rn(p1.z, P.R);
+    const bool b0 = h0 && q0.x > lo0 && q0.x < hi0 && q0.y > lo1 && q0.y < hi1 && q0.z > lo2 && q0.z < hi2;
+    const bool b1 = h1 && q1.x > lo0 && q1.x < hi0 && q1.y > lo1 && q1.y < hi1 && q1.z > lo2 && q1.z < hi2;
+    const float d0 = straight_distance(q0.x, q0.y, q0.z, p1.x, p1.y, p1.z);
+    const float d1 = straight_distance(q1.x, q1.y, q1.z, p1.x, p1.y, p1.z);
+    key0 = 0ull;
+    key1 = 0ull;
+    if(SMODE == 1) {
+        // BarnesStructure::corr, structure.cpp:214-228 with barnes_rho :26-34. P.R is the term's localization distance, so the
+        // `hdist > localization_distance` test is the d <= R below; the horizontal scale is valid and positive
+        // (structure_mode), the distance of an accepted candidate is finite: barnes_rho's early returns cannot trigger.
+        const gpp_structure_term& t = P.s.term[0];
+        const double v0 = (double) __fdiv_rn(d0, t.h), v1 = (double) __fdiv_rn(d1, t.h);
+        float rho0 = (float) exp_nonpos(__dmul_rn(__dmul_rn(-0.5, v0), v0));
+        float rho1 = (float) exp_nonpos(__dmul_rn(__dmul_rn(-0.5, v1), v1));
+        if(is_valid(t.v) && t.v != 0.f && is_valid(p1.elev)) {   // vertical term (uniform over the warp)
+            if(is_valid(q0.elev)) rho0 = __fmul_rn(rho0, term_rho(GPP_STRUCT_BARNES, __fsub_rn(p1.elev, q0.elev), t.v));
+            if(is_valid(q1.elev)) rho1 = __fmul_rn(rho1, term_rho(GPP_STRUCT_BARNES, __fsub_rn(p1.elev, q1.elev), t.v));
+        }
+        if(is_valid(t.w) && t.w != 0.f && is_valid(p1.laf)) {     // land / sea term
+            if(is_valid(q0.laf)) rho0 = __fmul_rn(rho0, term_rho(GPP_STRUCT_BARNES, __fsub_rn(p1.laf, q0.laf), t.w));
+            if(is_valid(q1.laf)) rho1 = __fmul_rn(rho1, term_rho(GPP_STRUCT_BARNES, __fsub_rn(p1.laf, q1.laf), t.w));
+        }
+        if(b0 && d0 <= P.R && rho0 > 0.f) key0 = cand_key(rho0, orig0);
+        if(b1 && d1 <= P.R && rho1 > 0.f) key1 = cand_key(rho1, orig1);
+    }
+    else {
+        if(b0 && d0 <= P.R) {
+            const float rho = corr_background_call<SMODE>(P.s, p1, q0, d0);
+            if(rho > 0.f) key0 = cand_key(rho, orig0);
+        }
+        if(b1 && d1 <= P.R) {
+            const float rho = corr_background_call<SMODE>(P.s, p1, q1, d1);
+            if(rho > 0.f) key1 = cand_key(rho, orig1);
+        }
+    }
 }
 
 // One warp walks RUN consecutive background points.
@@ -324,8 +414,14 @@ __device__ __noinline__ void analyse_point(const OiParams& P, FastSmem& S, const
 // Run path: the observations that can be within R of ANY point of the run (distance to the run's centre
 // <= R + extent) are gathered ONCE, sorted by original index, and kept lane-resident (2 slots per lane). Per point
 // each lane evaluates the reference's exact predicate (strict box, distance <= R, rho > 0, oi.cpp:233-258) for its
-// slots; "the best k are the set solved last" is verified with two warp reductions (worst member key > best
-// non-member key) instead of a selection; only when that fails is the selection redone by ranking.
+// slots. The selection (oi.cpp:262-273) is MAINTAINED rather than recomputed: it starts from the set solved last and is
+// repaired by exchanges -- while the worst member's key is below the best outsider's, the two trade places; each test is
+// four single-instruction warp reductions -- and the full ranking only runs when the set has changed by more than a few
+// members.
+//
+// Work distribution: units of (1 << s)^2 tiles, s = TOP_SHIFT .. 0, handed out through an atomic counter, the largest
+// units first (oi_plan_units): the last rows of the range are cut into ever smaller units so that the warps run out of
+// work at about the same time, while most of the grid is walked in large units, which is what the reuse wants.
 template <int SMODE>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 2) oi_fast_kernel(const __grid_constant__ OiParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -349,35 +445,36 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 2) oi_fast_kernel(const __
     W.prev_orig = -2; W.prev_k = -1; W.dirty = 0; W.clock = 0;
     W.z = 0.0; W.dmax = 0.0; W.dmin = 0.0; W.avar = 0.0;
 
-    LruEntry* cache = reinterpret_cast<LruEntry*>(P.lru) + (size_t) warp_global * LRU_ENTRIES;
-    for(int e = lane; e < LRU_ENTRIES; e += 32) cache[e].stamp = 0;
+    OiWorkHeader* hdr = reinterpret_cast<OiWorkHeader*>(P.workspace);
+    LruBlock* cache = reinterpret_cast<LruBlock*>(P.workspace + OI_WORK_HEADER_BYTES) + warp_global;
+    if(lane < LRU_ENTRIES) cache->stamp[lane] = 0;
     __syncwarp();
-    // Runs: 16-point row segments, or 4 x 4 tiles (serpentine inside the tile) when the range is whole grid rows.
-    // A warp takes RUNS_PER_CHUNK consecutive runs at a time so that its cache of solved systems sees neighbours.
     const int tiles_x = P.tile_nx > 0 ? (P.tile_nx + 3) / 4 : 0;
     const int rows = P.tile_nx > 0 ? P.count / P.tile_nx : 0;
-    const int n_runs = P.tile_nx > 0 ? tiles_x * ((rows + 3) / 4) : (P.count + RUN - 1) / RUN;
-    // tile mode: a chunk is a block of CHUNK_TY x CHUNK_TX tiles walked in serpentine order. The region over which one
-    // observation set is selected is a few points across (C3: ~30 points), so the squarer the chunk, the fewer regions
-    // are cut by a chunk edge and solved again by another warp.
     const int tiles_y = (rows + 3) / 4;
-    const int chunks_x = (tiles_x + CHUNK_TX - 1) / CHUNK_TX;
-    const int n_chunks = P.tile_nx > 0 ? chunks_x * ((tiles_y + CHUNK_TY - 1) / CHUNK_TY) : (n_runs + RUNS_PER_CHUNK - 1) / RUNS_PER_CHUNK;
-    // chunks are handed out dynamically: their cost varies with how often the selection changes, and a static split
-    // of a few chunks per warp leaves a long tail
+    const int n_runs = P.tile_nx > 0 ? tiles_x * tiles_y : (P.count + RUN - 1) / RUN;
     for(;;) {
-    int chunk = 0;
-    if(lane == 0) chunk = atomicAdd(P.work_counter, 1);
-    chunk = __shfl_sync(0xffffffffu, chunk, 0);
-    if(chunk >= n_chunks) break;
-    for(int j_run = 0; j_run < RUNS_PER_CHUNK; j_run++) {
+    int unit = 0;
+    if(lane == 0) unit = atomicAdd(&hdr->next_unit, 1);
+    unit = __shfl_sync(FULL, unit, 0);
+    if(unit >= P.plan.n_units) break;
+    // ---- the unit's level (size), and where it lies
+    int level = 0;
+    #pragma unroll
+    for(int l = 0; l < N_LEVELS - 1; l++) level += unit >= P.plan.end[l];
+    const int local = unit - (level > 0 ? P.plan.end[level - 1] : 0);
+    const int sh = TOP_SHIFT - level;                     // the unit is (1 << sh) x (1 << sh) tiles, or 1 << 2 sh runs
+    const int n_sub = 1 << (2 * sh);
+    const int ucy = P.tile_nx > 0 ? local / P.plan.cols[level] : 0, ucx = local - ucy * P.plan.cols[level];
+    for(int j_run = 0; j_run < n_sub; j_run++) {
         // ---- the run's points (offsets into the range), and a bounding sphere
         int npts, my_it = 0;
-        const int run = chunk * RUNS_PER_CHUNK + j_run;
         if(P.tile_nx > 0) {
-            const int cy = chunk / chunks_x, cx = chunk - cy * chunks_x;
-            const int tyy = j_run / CHUNK_TX, txx = j_run - tyy * CHUNK_TX;
-            const int ty = cy * CHUNK_TY + tyy, tx = cx * CHUNK_TX + ((tyy & 1) ? CHUNK_TX - 1 - txx : txx);
+            // a unit is walked in serpentine order. The region over which one observation set is selected is a few points
+            // across (C3: ~30 points), so the squarer the unit, the fewer regions are cut by its edge and solved again by
+            // another warp.
+            const int tyy = j_run >> sh, txx = j_run & ((1 << sh) - 1);
+            const int ty = P.plan.base[level] + (ucy << sh) + tyy, tx = (ucx << sh) + ((tyy & 1) ? (1 << sh) - 1 - txx : txx);
             if(ty >= tiles_y || tx >= tiles_x) continue;
             const int h = min(4, rows - 4 * ty), wdt = min(4, P.tile_nx - 4 * tx);
             npts = h * wdt;
@@ -387,6 +484,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 2) oi_fast_kernel(const __
             }
         }
         else {
+            const int run = P.plan.base[level] + (local << (2 * sh)) + j_run;
             if(run >= n_runs) break;
             npts = min(RUN, P.count - run * RUN);
             my_it = run * RUN + lane;
@@ -396,9 +494,10 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 2) oi_fast_kernel(const __
             float x = 0.f, y = 0.f, z = 0.f;
             if(lane < npts) {
                 const int g = P.first + my_it;
-                x = P.gx[g]; y = P.gy[g]; z = P.gz[g];
+                const Pt p = bg_point(P, g);
+                x = p.x; y = p.y; z = p.z;
                 S.px[lane] = x; S.py[lane] = y; S.pz[lane] = z;
-                S.pelev[lane] = P.gelev[g]; S.plaf[lane] = P.glaf[g]; S.pbg[lane] = P.background[g];
+                S.pelev[lane] = p.elev; S.plaf[lane] = p.laf; S.pbg[lane] = P.background[g];
                 S.pit[lane] = my_it;
             }
             __syncwarp();
@@ -406,15 +505,15 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 2) oi_fast_kernel(const __
             float sx_ = x, sy_ = y, sz_ = z;
             #pragma unroll
             for(int off = 16; off > 0; off >>= 1) {
-                sx_ += __shfl_xor_sync(0xffffffffu, sx_, off);
-                sy_ += __shfl_xor_sync(0xffffffffu, sy_, off);
-                sz_ += __shfl_xor_sync(0xffffffffu, sz_, off);
+                sx_ += __shfl_xor_sync(FULL, sx_, off);
+                sy_ += __shfl_xor_sync(FULL, sy_, off);
+                sz_ += __shfl_xor_sync(FULL, sz_, off);
             }
             const float inv_n = 1.f / (float) npts;
             const float cx = sx_ * inv_n, cy = sy_ * inv_n, cz = sz_ * inv_n;
             if(lane < npts) ext = sqrtf((x - cx) * (x - cx) + (y - cy) * (y - cy) + (z - cz) * (z - cz));
             #pragma unroll
-            for(int off = 16; off > 0; off >>= 1) ext = fmaxf(ext, __shfl_xor_sync(0xffffffffu, ext, off));
+            for(int off = 16; off > 0; off >>= 1) ext = fmaxf(ext, __shfl_xor_sync(FULL, ext, off));
             // ---- candidate list: every table observation within Rs = R + ext (+ rounding slack) of the centre
             const float Rs = (P.R + ext) * 1.0001f + 1e-3f;
             int nL = 0;
@@ -435,7 +534,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 2) oi_fast_kernel(const __
                                 const float dx = obs.x[i] - cx, dy = obs.y[i] - cy, dz = obs.z[i] - cz;
                                 ok = sqrtf(dx * dx + dy * dy + dz * dz) <= Rs;
                             }
-                            const unsigned mask = __ballot_sync(0xffffffffu, ok);
+                            const unsigned mask = __ballot_sync(FULL, ok);
                             const int add = __popc(mask);
                             if(nL + add > NCAND) { overflow = true; break; }
                             if(ok) {
@@ -490,13 +589,13 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 2) oi_fast_kernel(const __
             {
                 bool m0 = false, m1 = false;
                 for(int r = 0; r < 32; r++) {
-                    const int po = __shfl_sync(0xffffffffu, W.prev_orig, r);
+                    const int po = __shfl_sync(FULL, W.prev_orig, r);
                     if(po < 0) break;
                     m0 = m0 || po == orig0;
                     m1 = m1 || po == orig1;
                 }
-                T0 = __ballot_sync(0xffffffffu, m0);
-                T1 = __ballot_sync(0xffffffffu, m1);
+                T0 = __ballot_sync(FULL, m0);
+                T1 = __ballot_sync(FULL, m1);
                 if(__popc(T0) + __popc(T1) != W.prev_k) { T0 = 0; T1 = 0; }
             }
             // ---- the points of the run
@@ -505,25 +604,9 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 2) oi_fast_kernel(const __
                 const float bg = S.pbg[i];
                 if(!is_valid(bg)) { keep_background(P, g, bg); continue; }   // oi.cpp:223
                 const Pt p1 = {S.px[i], S.py[i], S.pz[i], S.pelev[i], S.plaf[i]};
-                // the reference's predicate for each of this lane's candidates (kdtree.cpp:46-53,247-260; oi.cpp:250-258)
-                const float lo0 = __fsub_rn(p1.x, P.R), lo1 = __fsub_rn(p1.y, P.R), lo2 = __fsub_rn(p1.z, P.R);
-                const float hi0 = __fadd_rn(p1.x, P.R), hi1 = __fadd_rn(p1.y, P.R), hi2 = __fadd_rn(p1.z, P.R);
-                unsigned long long key0 = 0ull, key1 = 0ull;
-                if(h0 && q0.x > lo0 && q0.x < hi0 && q0.y > lo1 && q0.y < hi1 && q0.z > lo2 && q0.z < hi2) {
-                    const float dist = straight_distance(q0.x, q0.y, q0.z, p1.x, p1.y, p1.z);
-                    if(dist <= P.R) {
-                        const float rho = corr_background_call<SMODE>(P.s, p1, q0, dist);
-                        if(rho > 0.f) key0 = cand_key(rho, orig0);
-                    }
-                }
-                if(h1 && q1.x > lo0 && q1.x < hi0 && q1.y > lo1 && q1.y < hi1 && q1.z > lo2 && q1.z < hi2) {
-                    const float dist = straight_distance(q1.x, q1.y, q1.z, p1.x, p1.y, p1.z);
-                    if(dist <= P.R) {
-                        const float rho = corr_background_call<SMODE>(P.s, p1, q1, dist);
-                        if(rho > 0.f) key1 = cand_key(rho, orig1);
-                    }
-                }
-                const unsigned v0 = __ballot_sync(0xffffffffu, key0 != 0ull), v1 = __ballot_sync(0xffffffffu, key1 != 0ull);
+                unsigned long long key0, key1;
+                slot_keys<SMODE>(P, p1, q0, q1, h0, h1, orig0, orig1, key0, key1);
+                const unsigned v0 = __ballot_sync(FULL, key0 != 0ull), v1 = __ballot_sync(FULL, key1 != 0ull);
                 const int nv = __popc(v0) + __popc(v1);
                 if(nv == 0) { keep_background(P, g, bg); continue; }   // oi.cpp:234-237,284-287
                 // ---- selection (oi.cpp:262-273) as slot masks
@@ -531,23 +614,32 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 2) oi_fast_kernel(const __
                 int k = nv;
                 if(nv > P.k) {
                     k = P.k;
-                    bool hypothesis = __popc(T0) + __popc(T1) == k && (T0 & ~v0) == 0 && (T1 & ~v1) == 0;
-                    if(hypothesis) {
-                        // worst member vs best valid non-member
-                        const bool in0 = (T0 >> lane) & 1u, in1 = (T1 >> lane) & 1u;
-                        unsigned long long worst_in = ~0ull, best_out = 0ull;
-                        if(in0) worst_in = key0; else best_out = key0;
-                        if(in1) worst_in = min(worst_in, key1); else best_out = max(best_out, key1);
-                        #pragma unroll
-                        for(int off = 16; off > 0; off >>= 1) {
-                            worst_in = min(worst_in, __shfl_xor_sync(0xffffffffu, worst_in, off));
-                            best_out = max(best_out, __shfl_xor_sync(0xffffffffu, best_out, off));
+                    // start from the members of the solved set that are still candidates and repair by exchanges
+                    sel0 = T0 & v0;
+                    sel1 = T1 & v1;
+                    int cnt = __popc(sel0) + __popc(sel1);
+                    bool settled = false;
+                    if(cnt + 3 >= k) {
+                        for(int it = 0; it < 8; it++) {
+                            const bool in0 = (sel0 >> lane) & 1u, in1 = (sel1 >> lane) & 1u;
+                            const unsigned long long out_best = max(in0 ? 0ull : key0, in1 ? 0ull : key1);
+                            const unsigned long long BO = warp_max64(out_best);   // never 0: more candidates than members
+                            if(cnt < k) {   // a member dropped out of reach: the best outsider takes its place
+                                sel0 |= __ballot_sync(FULL, !in0 && key0 == BO);
+                                sel1 |= __ballot_sync(FULL, !in1 && key1 == BO);
+                                cnt++;
+                                continue;
+                            }
+                            const unsigned long long in_worst = min(in0 ? key0 : ~0ull, in1 ? key1 : ~0ull);
+                            const unsigned long long WI = warp_min64(in_worst);
+                            if(WI > BO) { settled = true; break; }
+                            sel0 = (sel0 & ~__ballot_sync(FULL, in0 && key0 == WI)) | __ballot_sync(FULL, !in0 && key0 == BO);
+                            sel1 = (sel1 & ~__ballot_sync(FULL, in1 && key1 == WI)) | __ballot_sync(FULL, !in1 && key1 == BO);
                         }
-                        hypothesis = worst_in > best_out;
                     }
-                    if(hypothesis) { sel0 = T0; sel1 = T1; }
-                    else {
+                    if(!settled) {
                         // rank the valid keys; the k largest are selected
+                        OI_COUNT(3);
                         S.key[lane] = key0;
                         S.key[lane + 32] = key1;
                         __syncwarp();
@@ -558,8 +650,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 2) oi_fast_kernel(const __
                             r0 += km > key0;
                             r1 += km > key1;
                         }
-                        sel0 = __ballot_sync(0xffffffffu, key0 != 0ull && r0 < k);
-                        sel1 = __ballot_sync(0xffffffffu, key1 != 0ull && r1 < k);
+                        sel0 = __ballot_sync(FULL, key0 != 0ull && r0 < k);
+                        sel1 = __ballot_sync(FULL, key1 != 0ull && r1 < k);
                         __syncwarp();
                     }
                 }
@@ -579,10 +671,11 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 2) oi_fast_kernel(const __
                     if(need_var) solve_selected<SMODE>(P, S, lut, k, W);
                     else {
                         const unsigned now = ++W.clock;
-                        if(!lru_lookup(cache, S, k, now, W)) {
+                        unsigned sig;
+                        if(!lru_lookup(cache, S, k, now, W, sig)) {
                             OI_COUNT(2);
                             solve_selected<SMODE>(P, S, lut, k, W);
-                            lru_store(cache, k, now, W);
+                            lru_store(cache, k, now, W, sig);
                         }
                     }
                     T0 = sel0;
@@ -594,6 +687,15 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 2) oi_fast_kernel(const __
             }
         }
     }
+    }
+    // the last warp to run out of work leaves the workspace ready for the next launch (no memset between launches)
+    if(lane == 0) {
+        __threadfence();
+        if(atomicAdd(&hdr->warps_done, 1) == (int) (gridDim.x * WARPS_PER_CTA) - 1) {
+            hdr->next_unit = 0;
+            hdr->warps_done = 0;
+            __threadfence();
+        }
     }
 }
 
@@ -649,7 +751,7 @@ __global__ void __launch_bounds__(CHOL_WARPS * 32) oi_chol_kernel(const __grid_c
             const float bg = P.background[g];
             int k = 0;
             if(is_valid(bg)) {   // oi.cpp:223
-                const Pt p1 = {P.gx[g], P.gy[g], P.gz[g], P.gelev[g], P.glaf[g]};
+                const Pt p1 = bg_point(P, g);
                 k = gather_candidates<SMODE, NSLOT>(P.obs, P.s, p1, P.R, P.k, cb);
             }
             if(k == 0) { keep_background(P, g, bg); continue; }
@@ -857,7 +959,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) oi_general_kernel(const __
         int k = 0, cur = 0;
         Pt p1 = {0, 0, 0, 0, 0};
         if(!done) {
-            p1 = {P.gx[g], P.gy[g], P.gz[g], P.gelev[g], P.glaf[g]};
+            p1 = bg_point(P, g);
             // the structure function as this point sees it (structure.cpp:189-199: the scales of the nearest node)
             gpp_structure sp = P.s;
             float R = P.R;
@@ -1154,13 +1256,60 @@ int gpp::count_max_candidates(gpp_points* bp, int first, int count, const float*
 }
 
 namespace {
+// How the range is cut into work units (UnitPlan): most of it in the largest units; the last rows in units a quarter the
+// size, then a quarter of that, ... each level holding enough work (half a unit of the level above per resident warp) to
+// even out the spread of finishing times the level above leaves behind. The tail of a launch is then one smallest unit
+// (16 points) instead of one largest (256): what limited the strong scaling over 8 GPUs, where a rank has only ~3 large
+// units per warp.
+UnitPlan oi_plan_units(int tile_nx, int count, long long warps) {
+    UnitPlan u;
+    std::memset(&u, 0, sizeof(u));
+    const bool tiles = tile_nx > 0;
+    const long long width = tiles ? (tile_nx + 3) / 4 : 1;                                       // tiles per tile row
+    long long rem = tiles ? (count / tile_nx + 3) / 4 : ((long long) count + RUN - 1) / RUN;   // tile rows, or runs
+    long long rows[4] = {0, 0, 0, 0};
+    auto unit_rows = [&](int l) { const int sh = TOP_SHIFT - l; return (long long) (tiles ? (1 << sh) : (1 << (2 * sh))); };
+    for(int l = N_LEVELS - 1; l >= 1; l--) {
+        const int sh = TOP_SHIFT - l;
+        const long long area = (warps / 2 + 1) << (2 * (sh + 1));   // tiles (runs) wanted at this level
+        long long want = (area + width - 1) / width;
+        want = (want + unit_rows(l) - 1) / unit_rows(l) * unit_rows(l);
+        long long r = std::min(rem, want);
+        r -= r % unit_rows(l);
+        rows[l] = r;
+        rem -= r;
+    }
+    rows[0] = rem - rem % unit_rows(0);
+    rem -= rows[0];
+    for(int l = 1; l < N_LEVELS; l++) {   // what does not fill a unit goes to the finer levels (the finest takes single rows)
+        const long long r = rem - rem % unit_rows(l);
+        rows[l] += r;
+        rem -= r;
+    }
+    long long base = 0, end = 0;
+    for(int l = 0; l < 4; l++) {
+        if(l < N_LEVELS) {
+            const int sh = TOP_SHIFT - l;
+            const long long cols = tiles ? (width + (1 << sh) - 1) >> sh : 1;
+            u.base[l] = (int) base;
+            u.cols[l] = (int) cols;
+            end += rows[l] / unit_rows(l) * cols;
+            base += rows[l];
+        }
+        u.end[l] = (int) end;
+    }
+    u.n_units = (int) end;
+    return u;
+}
+size_t oi_workspace_bytes() { return OI_WORK_HEADER_BYTES + sizeof(LruBlock) * (size_t) sm_count() * 2 * WARPS_PER_CTA; }
+
 int check_structure(const gpp_structure* s) {
     if(!s) return fail(GPP_ERR_INVALID_ARGUMENT, "structure must not be NULL");
     if(s->n_terms != 1 && s->n_terms != 3) return fail(GPP_ERR_INVALID_ARGUMENT, "structure.n_terms must be 1 or 3");
     for(int t = 0; t < s->n_terms; t++)
         if(s->term[t].type < GPP_STRUCT_BARNES || s->term[t].type > GPP_STRUCT_LINEAR)
             return fail(GPP_ERR_INVALID_ARGUMENT, "unknown structure function type %d", s->term[t].type);
-    return GPP_OK;
+    return reject_unset_scales(s);
 }
 }  // namespace
 
@@ -1337,6 +1486,14 @@ int gpp_oi_obs_create(const gpp_points* opoints, const float* pobs, const float*
     gpp_oi_obs* o = new(std::nothrow) gpp_oi_obs();
     if(!o) return fail(GPP_ERR_RUNTIME, "out of memory");
     int rc = build_obs_table(opoints, valid, innov, ratio, structure->term[0].loc_dist, o);
+    // launch workspaces of the register path (work counter + per-warp caches of solved systems): OI_WORK_SLOTS of them, used
+    // round-robin, so that a step is one kernel launch with no allocation or memset around it
+    if(rc == GPP_OK) {
+        o->work_slot_bytes = oi_workspace_bytes();
+        rc = o->work.alloc(o->work_slot_bytes * OI_WORK_SLOTS);
+        if(rc == GPP_OK && cudaMemsetAsync(o->work.ptr, 0, o->work_slot_bytes * OI_WORK_SLOTS, 0) != cudaSuccess) rc = fail(GPP_ERR_CUDA, "cudaMemsetAsync failed");
+        if(rc == GPP_OK && cudaStreamSynchronize(0) != cudaSuccess) rc = fail(GPP_ERR_CUDA, "cudaStreamSynchronize failed");
+    }
     if(rc != GPP_OK) { delete o; return rc; }
     *out = o;
     return GPP_OK;
@@ -1344,10 +1501,23 @@ int gpp_oi_obs_create(const gpp_points* opoints, const float* pobs, const float*
 
 void gpp_oi_obs_destroy(gpp_oi_obs* obs) { delete obs; }
 
+size_t gpp_oi_workspace_bytes(void) {
+    if(ensure_device() != GPP_OK) return 0;
+    return oi_workspace_bytes();
+}
+
 int gpp_optimal_interpolation_device(const gpp_points* cbp, int first, int count, const float* d_background,
                                      const float* d_bvariance, const gpp_oi_obs* obs, const gpp_structure* structure,
                                      int max_points, int allow_extrapolation, float* d_analysis, float* d_analysis_variance,
                                      void* stream_) {
+    return gpp_optimal_interpolation_device_ws(cbp, first, count, d_background, d_bvariance, obs, structure, max_points, allow_extrapolation,
+                                               d_analysis, d_analysis_variance, nullptr, 0, stream_);
+}
+
+int gpp_optimal_interpolation_device_ws(const gpp_points* cbp, int first, int count, const float* d_background,
+                                        const float* d_bvariance, const gpp_oi_obs* obs, const gpp_structure* structure,
+                                        int max_points, int allow_extrapolation, float* d_analysis, float* d_analysis_variance,
+                                        void* d_workspace, size_t workspace_bytes, void* stream_) {
     cudaStream_t stream = (cudaStream_t) stream_;
     if(max_points < 0) return fail(GPP_ERR_INVALID_ARGUMENT, "max_points must be >= 0");   // oi.cpp:152
     if(!cbp || !obs) return fail(GPP_ERR_INVALID_ARGUMENT, "points and observation state must not be NULL");
@@ -1363,7 +1533,10 @@ int gpp_optimal_interpolation_device(const gpp_points* cbp, int first, int count
         return GPP_OK;
     }
     OiParams P;
-    P.gx = bp->dx.ptr; P.gy = bp->dy.ptr; P.gz = bp->dz.ptr; P.gelev = bp->delev.ptr; P.glaf = bp->dlaf.ptr;
+    P.gx = bp->dx.ptr; P.gy = bp->dy.ptr;
+    P.gz = bp->type == GPP_CARTESIAN ? nullptr : bp->dz.ptr;   // util.cpp:583-615: z = 0 for Cartesian points
+    P.gelev = bp->has_elevs ? bp->delev.ptr : nullptr;           // points.cpp:23-30: NaN when not given
+    P.glaf = bp->has_lafs ? bp->dlaf.ptr : nullptr;
     P.background = d_background;
     P.bvariance = d_bvariance;
     P.analysis = d_analysis;
@@ -1375,7 +1548,8 @@ int gpp_optimal_interpolation_device(const gpp_points* cbp, int first, int count
     P.R = structure->term[0].loc_dist;
     P.allow_extrapolation = allow_extrapolation;
     P.tile_nx = 0;
-    P.lru = nullptr;
+    P.workspace = nullptr;
+    std::memset(&P.plan, 0, sizeof(P.plan));
     P.work_counter = nullptr;
     P.sbh = P.sbv = P.sbw = nullptr;
     P.loc_c = 0.f;
@@ -1398,22 +1572,29 @@ int gpp_optimal_interpolation_device(const gpp_points* cbp, int first, int count
         GPP_CUDA(cudaFuncSetAttribute(oi_fast_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
         // whole rows of a known grid -> 4 x 4 tiles
         P.tile_nx = (bp->shape_nx > 0 && first % bp->shape_nx == 0 && count % bp->shape_nx == 0) ? bp->shape_nx : 0;
-        const long long runs = P.tile_nx > 0 ? (long long) ((P.tile_nx + 3) / 4) * ((count / P.tile_nx + 3) / 4) : ((long long) count + RUN - 1) / RUN;
-        const long long chunks = P.tile_nx > 0 ? (long long) (((P.tile_nx + 3) / 4 + CHUNK_TX - 1) / CHUNK_TX) * (((count / P.tile_nx + 3) / 4 + CHUNK_TY - 1) / CHUNK_TY)
-                                               : (runs + RUNS_PER_CHUNK - 1) / RUNS_PER_CHUNK;
-        const long long want = (chunks + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-        const unsigned grid = (unsigned) std::max<long long>(1, std::min<long long>(want, (long long) sms * 2));   // 2 resident CTAs per SM
-        unsigned char* lru = nullptr;
-        const size_t lru_bytes = sizeof(LruEntry) * LRU_ENTRIES * (size_t) grid * WARPS_PER_CTA;
-        GPP_CUDA(cudaMallocAsync((void**) &lru, lru_bytes + 256, stream));
-        P.lru = lru;
-        P.work_counter = reinterpret_cast<int*>(lru + lru_bytes);
-        GPP_CUDA(cudaMemsetAsync(P.work_counter, 0, sizeof(int), stream));
+        const long long max_warps = (long long) sms * 2 * WARPS_PER_CTA;   // 2 resident CTAs per SM
+        P.plan = oi_plan_units(P.tile_nx, count, max_warps);
+        const unsigned grid = (unsigned) std::max<long long>(1, std::min<long long>(((long long) P.plan.n_units + WARPS_PER_CTA - 1) / WARPS_PER_CTA, (long long) sms * 2));
+        // the launch workspace: the caller's, else one of the slots the observation state owns, else a stream-ordered
+        // allocation (observation states built on the stack by other entry points have no slots)
+        const size_t need = OI_WORK_HEADER_BYTES + sizeof(LruBlock) * (size_t) grid * WARPS_PER_CTA;
+        unsigned char* temp = nullptr;
+        if(d_workspace) {
+            if(workspace_bytes < need) return fail(GPP_ERR_INVALID_ARGUMENT, "workspace of %zu bytes given, %zu needed (gpp_oi_workspace_bytes)", workspace_bytes, need);
+            P.workspace = static_cast<unsigned char*>(d_workspace);
+        }
+        else if(obs->work.ptr && obs->work_slot_bytes >= need)
+            P.workspace = obs->work.ptr + obs->work_slot_bytes * (obs->work_next.fetch_add(1, std::memory_order_relaxed) % OI_WORK_SLOTS);
+        else {
+            GPP_CUDA(cudaMallocAsync((void**) &temp, need, stream));
+            GPP_CUDA(cudaMemsetAsync(temp, 0, OI_WORK_HEADER_BYTES, stream));
+            P.workspace = temp;
+        }
         if(mode == 1) oi_fast_kernel<1><<<grid, WARPS_PER_CTA * 32, smem, stream>>>(P);
         else oi_fast_kernel<0><<<grid, WARPS_PER_CTA * 32, smem, stream>>>(P);
         g_launches.fetch_add(1, std::memory_order_relaxed);
         cudaError_t err = cudaGetLastError();
-        cudaFreeAsync(lru, stream);
+        if(temp) cudaFreeAsync(temp, stream);
         if(err != cudaSuccess) return fail(GPP_ERR_CUDA, "CUDA error %s launching oi_fast_kernel: %s", cudaGetErrorName(err), cudaGetErrorString(err));
         return GPP_OK;
     }
@@ -1561,7 +1742,8 @@ int gpp_optimal_interpolation_spatial_host(const gpp_points* bpoints, const floa
         P.R = max_R;
         P.allow_extrapolation = allow_extrapolation;
         P.tile_nx = 0;
-        P.lru = nullptr;
+        P.workspace = nullptr;
+        std::memset(&P.plan, 0, sizeof(P.plan));
         P.work_counter = nullptr;
         P.sbh = d_sc[0].ptr; P.sbv = d_sc[1].ptr; P.sbw = d_sc[2].ptr;
         P.loc_c = loc_c;

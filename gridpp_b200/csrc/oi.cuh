@@ -125,6 +125,8 @@ __device__ __forceinline__ int gather_candidates(const ObsView& obs, const gpp_s
 
 }  // namespace gpp
 
+constexpr unsigned OI_WORK_SLOTS = 4;
+
 // Host-side owner of the observation table.
 struct gpp_oi_obs {
     int n_total = 0;          // observations given
@@ -137,6 +139,11 @@ struct gpp_oi_obs {
     gpp::DeviceBuffer<float> sh, sv, sw;   // only for spatially varying structure functions
     bool has_scales = false;
     gpp::DeviceBuffer<double> innov;
+    // launch workspaces of the register OI kernel (gpp_oi_obs_create): OI_WORK_SLOTS slots handed out round-robin, so at most
+    // that many analyses sharing this state may be in flight at once (more: gpp_optimal_interpolation_device_ws)
+    gpp::DeviceBuffer<unsigned char> work;
+    size_t work_slot_bytes = 0;
+    mutable std::atomic<unsigned> work_next{0};
     gpp::ObsView view() const {
         gpp::ObsView v;
         v.geom = geom;

@@ -371,6 +371,8 @@ int gpp_points_create(const float* lats, const float* lons, const float* elevs, 
     // points.cpp:23-30 / grid.cpp:41-54: missing elevations and land fractions are NaN
     if(elevs) p->elevs.assign(elevs, elevs + n); else p->elevs.assign(n, NAN);
     if(lafs) p->lafs.assign(lafs, lafs + n); else p->lafs.assign(n, NAN);
+    p->has_elevs = elevs != nullptr;
+    p->has_lafs = lafs != nullptr;
     p->x.resize(n); p->y.resize(n); p->z.resize(n);
     int bad = -1;
     #pragma omp parallel for

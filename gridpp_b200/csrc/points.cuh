@@ -39,6 +39,7 @@ struct gpp_points {
     int n = 0;
     int type = GPP_GEODETIC;
     int shape_ny = 0, shape_nx = 0;                        // set when the points are a flattened ny x nx grid
+    bool has_elevs = false, has_lafs = false;              // given at creation (else all NaN: points.cpp:23-30, grid.cpp:41-54)
     std::vector<float> lats, lons, elevs, lafs, x, y, z;   // host copies
     float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};             // bounding box of x/y/z
     int device = -1;

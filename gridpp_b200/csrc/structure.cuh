@@ -151,8 +151,21 @@ template <int SMODE>
 __device__ __noinline__ float corr_background_call(const gpp_structure& s, const Pt& p1, const Pt& p2, float hdist) {
     return corr_background_mode<SMODE>(s, p1, p2, hdist);
 }
+// (mode 1 also requires an active horizontal scale: the kernels' inlined Barnes evaluation skips barnes_rho's
+// "length invalid or zero" early return, structure.cpp:27-29)
 inline int structure_mode(const gpp_structure& s) {
-    return (s.n_terms == 1 && !s.has_cv && s.term[0].type == GPP_STRUCT_BARNES) ? 1 : 0;
+    return (s.n_terms == 1 && !s.has_cv && s.term[0].type == GPP_STRUCT_BARNES && is_valid(s.term[0].h) && s.term[0].h > 0.f) ? 1 : 0;
+}
+
+// A descriptor whose horizontal scale is NaN is the placeholder the host layers build for a spatially varying
+// <Family>Structure(Grid, h, v, w) (the scales live in a gpp_structure_field, not in the descriptor). Entry points that
+// take a plain descriptor must refuse it instead of analysing with a localization distance of NaN / 0.
+inline int reject_unset_scales(const gpp_structure* s) {
+    for(int t = 0; s && t < s->n_terms && t < 3; t++)
+        if(isnan(s->term[t].h))
+            return fail(GPP_ERR_NOT_IMPLEMENTED, "spatially varying structure functions are only supported by optimal_interpolation / optimal_interpolation_full "
+                                                 "(gpp_optimal_interpolation_spatial_host)");
+    return GPP_OK;
 }
 
 // True when corr(p1, p2) == corr(p2, p1) for every pair, so that P + R is symmetric (positive definite) and

@@ -69,6 +69,98 @@ def optimal_interpolation(bgrid, background, obs_state, max_points, allow_extrap
     return out
 
 
+class Workspace:
+    """Explicit launch workspace of the register OI path (gpp_oi_workspace_bytes): zero-filled once, then owned by
+    one launch in flight at a time. With it gpp_optimal_interpolation_device_ws performs no allocation at all."""
+
+    def __init__(self, device=None):
+        self.bytes = int(_libc.gpp_oi_workspace_bytes())
+        self.buf = torch.zeros(max(self.bytes, 1), dtype=torch.uint8, device=device or "cuda")
+
+
+def optimal_interpolation_ws(bgrid, background, obs_state, max_points, workspace, allow_extrapolation=True, out=None, bvariance=None,
+                             out_variance=None, first=0, count=None):
+    """optimal_interpolation with a caller-owned Workspace (one per launch in flight)."""
+    n = bgrid._set.n
+    if background.numel() != n:
+        raise ValueError("background has %d elements, the grid %d" % (background.numel(), n))
+    if out is None:
+        out = torch.empty_like(background)
+    if count is None:
+        count = n - first
+    _check(_libc.gpp_optimal_interpolation_device_ws(bgrid._set._handle, int(first), int(count), _ptr(background), _ptr(bvariance),
+                                                     obs_state._handle, _C.byref(obs_state.structure._desc), int(max_points),
+                                                     int(bool(allow_extrapolation)), _ptr(out), _ptr(out_variance),
+                                                     _C.c_void_p(workspace.buf.data_ptr()), workspace.bytes, _stream_ptr()))
+    return out
+
+
+class EnsembleObservationState:
+    """Observation side of optimal_interpolation_ensi, resident on the device (gpp_ensi_obs). `member_valid`: per-member
+    flags (False = the member has an invalid value somewhere in the background and is left untouched,
+    oi_ensi.cpp:187-201); None = all valid; `valid_members(background)` computes them from a device-resident field."""
+
+    def __init__(self, points, pobs, psigmas, pbackground, structure, member_valid=None):
+        if not isinstance(points, Points):
+            raise ValueError("points must be a Points object")
+        n = points.size()
+        obs, sig = _farray(pobs, 1, "pobs"), _farray(psigmas, 1, "psigmas")
+        pbg = _farray(pbackground, 2, "pbackground")
+        if obs.size != n or sig.size != n or pbg.shape[0] != n:
+            raise ValueError("Observations / sigmas / background and points size mismatch")
+        self.nE = int(pbg.shape[1])
+        flags = None
+        if member_valid is not None:
+            flags = _np.ascontiguousarray(_np.asarray(member_valid).astype(_np.int32))
+            if flags.size != self.nE:
+                raise ValueError("member_valid must have one flag per ensemble member")
+        self.points = points
+        self.structure = structure
+        self._handle = _C.c_void_p()
+        _check(_libc.gpp_ensi_obs_create(points._set._handle, _fptr(obs), _fptr(sig), _fptr(pbg), self.nE,
+                                         flags.ctypes.data_as(_lib.ip) if flags is not None else None, _C.byref(structure._desc),
+                                         _C.byref(self._handle)))
+
+    def __del__(self):
+        h = getattr(self, "_handle", None)
+        if h and _libc is not None:
+            _libc.gpp_ensi_obs_destroy(h)
+            self._handle = None
+
+
+def valid_members(background):
+    """Per-member flags of a device-resident (..., E) ensemble: False where the member has an invalid value anywhere."""
+    nE = int(background.shape[-1])
+    flags = _np.zeros(max(nE, 1), _np.int32)
+    _check(_libc.gpp_ensi_valid_members_device(_ptr(background), background.numel() // max(nE, 1), nE, flags.ctypes.data_as(_lib.ip),
+                                               _stream_ptr()))
+    return flags[:nE].astype(bool)
+
+
+def optimal_interpolation_ensi(bgrid, background, obs_state, max_points, allow_extrapolation=True, out=None, num_skipped=None,
+                               first=0, count=None):
+    """Analyses background points [first, first+count) of `bgrid`; `background` / `out` are float32 CUDA tensors of the WHOLE
+    (points, E) ensemble (they may be the same tensor). One kernel launch on the current stream, no synchronisation.
+    `num_skipped`: optional int32 CUDA tensor (1 element) counting the points skipped for a numerically bad Pinv."""
+    n = bgrid._set.n
+    nE = obs_state.nE
+    if background.numel() != n * nE:
+        raise ValueError("background has %d elements, the grid x members %d" % (background.numel(), n * nE))
+    if out is None:
+        out = torch.empty_like(background)
+    if count is None:
+        count = n - first
+    skipped = None
+    if num_skipped is not None:
+        if not (num_skipped.is_cuda and num_skipped.dtype == torch.int32):
+            raise ValueError("num_skipped must be an int32 CUDA tensor")
+        skipped = _C.c_void_p(num_skipped.data_ptr())
+    _check(_libc.gpp_optimal_interpolation_ensi_device(bgrid._set._handle, int(first), int(count), _ptr(background), nE, obs_state._handle,
+                                                       _C.byref(obs_state.structure._desc), int(max_points), int(bool(allow_extrapolation)),
+                                                       _ptr(out), skipped, _stream_ptr()))
+    return out
+
+
 def neighbourhood(field, halfwidth, statistic, out=None, row0=0, n_rows_out=None):
     """field: (rows, nx) float32 CUDA tensor (a tile plus its halo rows); computes output rows
     [row0, row0 + n_rows_out) into `out` (n_rows_out, nx)."""

@@ -444,6 +444,8 @@ protected:
         m_desc.n_terms = 1;
         m_desc.term[0].type = family;
         m_desc.term[0].min_rho = min_rho;
+        // placeholder descriptor: the scales live in the field; NaN makes the C entry points that take a plain descriptor refuse it
+        m_desc.term[0].h = m_desc.term[0].v = m_desc.term[0].w = m_desc.term[0].loc_dist = MV;
     }
     friend class MultipleStructure;
     friend class CrossValidation;

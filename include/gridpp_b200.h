@@ -179,12 +179,44 @@ int gpp_optimal_interpolation_device(const gpp_points* bpoints, int first, int c
                                      const gpp_structure* structure, int max_points, int allow_extrapolation,
                                      float* d_analysis, float* d_analysis_variance, void* stream);
 
+/* The same call with an explicit launch workspace instead of the slots the observation state owns (4 of them, used
+ * round-robin: enough for one stream or the library's own two-stream pipeline, not for more than 4 concurrent analyses
+ * sharing one state). d_workspace: gpp_oi_workspace_bytes() bytes of device memory, zero-filled ONCE before its first
+ * use (the kernels leave it ready for the next launch); one workspace per launch in flight. With it the register path
+ * (symmetric structure function, max_points 1..30) performs no allocation and no memset: a step is one kernel launch. */
+size_t gpp_oi_workspace_bytes(void);
+int gpp_optimal_interpolation_device_ws(const gpp_points* bpoints, int first, int count, const float* d_background,
+                                        const float* d_bvariance, const gpp_oi_obs* obs,
+                                        const gpp_structure* structure, int max_points, int allow_extrapolation,
+                                        float* d_analysis, float* d_analysis_variance, void* d_workspace,
+                                        size_t workspace_bytes, void* stream);
+
 /* gridpp::optimal_interpolation_ensi(Points...) oi_ensi.cpp:114-568 (the Grid overload :33-112 flattens to
  * this). background and analysis are nB x nE (member fastest), pbackground is nS x nE. HOST memory. */
 int gpp_optimal_interpolation_ensi_host(const gpp_points* bpoints, const float* background, int nE,
                                         const gpp_points* opoints, const float* pobs, const float* psigmas,
                                         const float* pbackground, const gpp_structure* structure, int max_points,
                                         int allow_extrapolation, float* analysis, int* num_skipped);
+
+/* Device-resident form of optimal_interpolation_ensi, split like the deterministic one. The observation side is built
+ * once from HOST arrays (oi_ensi.cpp:163-178: perturbations of pbackground about its ensemble mean; :232: only
+ * observations with a valid value enter). member_valid: nE flags (0 = the member has an invalid value somewhere in the
+ * background and is left untouched, oi_ensi.cpp:187-201), or NULL = every member is valid;
+ * gpp_ensi_valid_members_device computes the flags of a device-resident nB x nE background (it synchronises `stream`).
+ * gpp_optimal_interpolation_ensi_device analyses points [first, first+count) of `bpoints`: d_background and d_analysis
+ * are nB x nE device arrays indexed like the full field (they may be the same array); one kernel launch, no
+ * synchronisation, no allocation (max_points = 0 with more than 64 observations in reach adds a counting pass that
+ * synchronises). d_num_skipped: device int incremented once per point skipped for a numerically bad Pinv
+ * (oi_ensi.cpp:386-390), or NULL. At most 16 analyses sharing one observation state may be in flight at once. */
+typedef struct gpp_ensi_obs gpp_ensi_obs;
+int gpp_ensi_obs_create(const gpp_points* opoints, const float* pobs, const float* psigmas, const float* pbackground,
+                        int nE, const int* member_valid, const gpp_structure* structure, gpp_ensi_obs** out);
+void gpp_ensi_obs_destroy(gpp_ensi_obs* obs);
+int gpp_ensi_valid_members_device(const float* d_background, long long n_points, int nE, int* member_valid, void* stream);
+int gpp_optimal_interpolation_ensi_device(const gpp_points* bpoints, int first, int count, const float* d_background,
+                                          int nE, const gpp_ensi_obs* obs, const gpp_structure* structure,
+                                          int max_points, int allow_extrapolation, float* d_analysis,
+                                          int* d_num_skipped, void* stream);
 
 /* Spatially varying structure functions: gridpp::BarnesStructure(Grid, vec2 h, vec2 v, vec2 w, min_rho)
  * structure.cpp:168-184 and the Soar (:342), Toar (:492), Powerlaw (:643), Linear (:790) siblings. h, v, w hold one

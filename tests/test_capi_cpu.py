@@ -266,3 +266,22 @@ def test_get_point_and_convert_coordinates(gpp):
         points.get_point(3)
     with pytest.raises(ValueError):
         gpp.convert_coordinates(91, 0, gpp.Geodetic)
+
+
+def test_spatial_structure_descriptor_is_refused_by_plain_entry_points(gpp):
+    """the placeholder descriptor of a spatially varying <Family>Structure(grid, h, v, w) carries NaN
+    scales, and every entry point that takes a plain descriptor refuses it (before touching the device) instead of
+    analysing with a localization distance of zero."""
+    from gridpp_b200._lib import NotImplementedOnDevice
+    y, x = np.meshgrid(np.arange(6, dtype=f32) * 1000, np.arange(7, dtype=f32) * 1000, indexing="ij")
+    grid = gpp.Grid(y, x, type=gpp.Cartesian)
+    spatial = gpp.BarnesStructure(grid, np.full((6, 7), 2500, f32), np.zeros((6, 7), f32), np.zeros((6, 7), f32))
+    assert np.isnan(spatial._desc.term[0].h) and np.isnan(spatial._desc.term[0].loc_dist)
+    points = gpp.Points([1000, 3000], [1000, 4000], type=gpp.Cartesian)
+    with pytest.raises(NotImplementedOnDevice):
+        gpp.optimal_interpolation_ensi(grid, np.zeros((6, 7, 5), f32), points, [1.0, 2.0], [0.5, 0.5], np.zeros((2, 5), f32), spatial, 10)
+    from gridpp_b200 import device as gd
+    with pytest.raises(NotImplementedOnDevice):
+        gd.ObservationState(points, [1.0, 2.0], [0.5, 0.5], [0.0, 0.0], spatial)
+    with pytest.raises(NotImplementedOnDevice):
+        gd.EnsembleObservationState(points, [1.0, 2.0], [0.5, 0.5], np.zeros((2, 5), f32), spatial)

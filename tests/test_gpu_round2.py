@@ -1,0 +1,221 @@
+"""GPU parity tests added in round 2: the work-unit scheduler and launch workspace of the register OI kernel, the
+device-resident EnSI entry point, and configs 4 and 5 of BASELINE.json at their full sizes."""
+import numpy as np
+import pytest
+
+from oracle import bindings as B
+from util import assert_bit_exact, assert_close
+
+pytestmark = pytest.mark.gpu
+f32 = np.float32
+RTOL = 1e-5
+
+
+def _c3_like(rng, ny, nx, dx, density=0.01):
+    """C3 geometry on an ny x nx grid: `density` observations per km^2 over the area the grid can reach."""
+    y, x = np.meshgrid(np.arange(ny, dtype=f32) * dx, np.arange(nx, dtype=f32) * dx, indexing="ij")
+    pad = 40000.0
+    S = int(density * (ny * dx + 2 * pad) * (nx * dx + 2 * pad) / 1e6)
+    py = rng.uniform(-pad, ny * dx + pad, S).astype(f32)
+    px = rng.uniform(-pad, nx * dx + pad, S).astype(f32)
+    bg = (rng.standard_normal((ny, nx)) * 3).astype(f32)
+    pbg = (rng.standard_normal(S) * 3).astype(f32)
+    obs = (pbg + rng.standard_normal(S) * 0.5).astype(f32)
+    return y, x, py, px, bg, pbg, obs, np.full(S, 0.5, f32)
+
+
+def test_oi_work_units_workspace_and_traversal(gpp, orc):
+    """The register kernel hands work out in units of 16, 4 and 1 tiles (the last rows of a range in the small ones) from
+    a counter in a launch workspace that the kernel itself resets. A 700 x 704 grid has all three unit sizes. Checked:
+    a sample against the oracle; the Grid traversal (4 x 4 tiles) against the Points traversal (16-point runs) and
+    against ranges cut at arbitrary rows -- bit for bit; repeated launches on the same observation state (the workspace
+    must come back clean); the explicit-workspace entry point."""
+    import torch
+    from gridpp_b200 import device as gd
+    rng = np.random.default_rng(77)
+    ny, nx, dx = 700, 704, 250.0
+    y, x, py, px, bg, pbg, obs, ratios = _c3_like(rng, ny, nx, dx)
+    bg[rng.uniform(size=bg.shape) < 0.001] = np.nan
+    grid, points, s = gpp.Grid(y, x, type=gpp.Cartesian), gpp.Points(py, px, type=gpp.Cartesian), gpp.BarnesStructure(10000)
+    state = gd.ObservationState(points, obs, ratios, pbg, s)
+    d_bg = torch.from_numpy(bg.ravel()).cuda()
+    whole = gd.optimal_interpolation(grid, d_bg, state, 30)
+    pick = rng.choice(ny * nx, 5000, replace=False)
+    pick[:4] = [0, nx - 1, nx * (ny - 1), ny * nx - 1]
+    want = orc.optimal_interpolation((y.ravel()[pick], x.ravel()[pick], None, None), bg.ravel()[pick], (py, px, None, None), obs, ratios,
+                                     pbg, B.make_structure(B.BARNES, 10000.0), 30, B.CARTESIAN)
+    assert_close(whole.cpu().numpy()[pick], want, 3.0, RTOL, "work units vs oracle")
+    # the same launch again and again: 7 launches cycle through the 4 workspace slots of the state
+    for _ in range(7):
+        again = gd.optimal_interpolation(grid, d_bg, state, 30)
+    assert torch.equal(torch.nan_to_num(whole, nan=-7.0), torch.nan_to_num(again, nan=-7.0))
+    # ranges cut inside tiles and units (a range that is not whole rows takes the 16-point-run traversal)
+    parts = torch.full_like(d_bg, -1.0)
+    cuts = [0, 3 * nx, 3 * nx + 5, 250 * nx, 251 * nx, 500 * nx + 17, ny * nx]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        gd.optimal_interpolation(grid, d_bg, state, 30, out=parts, first=a, count=b - a)
+    assert torch.equal(torch.nan_to_num(whole, nan=-7.0), torch.nan_to_num(parts, nan=-7.0))
+    # the Points traversal of the same nodes
+    as_points = gpp.Points(y.ravel(), x.ravel(), type=gpp.Cartesian)
+    runs = gd.optimal_interpolation(as_points, d_bg, state, 30)
+    assert torch.equal(torch.nan_to_num(whole, nan=-7.0), torch.nan_to_num(runs, nan=-7.0))
+    # caller-owned workspace
+    ws = gd.Workspace()
+    assert ws.bytes > 0
+    for _ in range(2):
+        mine = gd.optimal_interpolation_ws(grid, d_bg, state, 30, ws)
+    assert torch.equal(torch.nan_to_num(whole, nan=-7.0), torch.nan_to_num(mine, nan=-7.0))
+    # small and ragged shapes: every unit is a single tile, partial tiles on both edges
+    for (sy, sx) in ((1, 1), (3, 5), (9, 130), (33, 37)):
+        sub = (slice(0, sy), slice(0, sx))
+        got = gpp.optimal_interpolation(gpp.Grid(y[sub], x[sub], type=gpp.Cartesian), bg[sub], points, obs, ratios, pbg, s, 30)
+        assert_bit_exact(got, whole.cpu().numpy().reshape(ny, nx)[sub], "sub-grid %dx%d" % (sy, sx))
+
+
+def test_oi_with_elevations_and_geodetic(gpp, orc):
+    """The inlined Barnes evaluation with the vertical and land/sea terms active, on a Geodetic grid (three coordinate
+    planes are read) and on a Cartesian one with elevations only."""
+    rng = np.random.default_rng(5)
+    ny, nx = 60, 70
+    lats, lons = np.meshgrid(np.linspace(59, 60, ny).astype(f32), np.linspace(10, 12, nx).astype(f32), indexing="ij")
+    elev = rng.uniform(0, 800, (ny, nx)).astype(f32)
+    laf = rng.uniform(0, 1, (ny, nx)).astype(f32)
+    elev[rng.uniform(size=elev.shape) < 0.02] = np.nan
+    S = 400
+    pla, plo = rng.uniform(58.9, 60.1, S).astype(f32), rng.uniform(9.8, 12.2, S).astype(f32)
+    pel, plaf = rng.uniform(0, 800, S).astype(f32), rng.uniform(0, 1, S).astype(f32)
+    pel[rng.uniform(size=S) < 0.05] = np.nan
+    bg = rng.standard_normal((ny, nx)).astype(f32)
+    pbg = rng.standard_normal(S).astype(f32)
+    obs = (pbg + rng.standard_normal(S)).astype(f32)
+    ratios = rng.uniform(0.2, 1.0, S).astype(f32)
+    for mp, extr in ((30, True), (12, False)):
+        got = gpp.optimal_interpolation(gpp.Grid(lats, lons, elev, laf), bg, gpp.Points(pla, plo, pel, plaf), obs, ratios, pbg,
+                                        gpp.BarnesStructure(30000, 300, 0.5), mp, extr)
+        want = orc.optimal_interpolation((lats, lons, elev, laf), bg, (pla, plo, pel, plaf), obs, ratios, pbg,
+                                         B.make_structure(B.BARNES, 30000.0, 300.0, 0.5), mp, B.GEODETIC, allow_extrapolation=extr)
+        assert_close(got.ravel(), want, 1.0, RTOL, "geodetic OI with elevation and laf terms mp=%d" % mp)
+    y, x = np.meshgrid(np.arange(ny, dtype=f32) * 1000, np.arange(nx, dtype=f32) * 1000, indexing="ij")
+    py, px = rng.uniform(0, ny * 1000, S).astype(f32), rng.uniform(0, nx * 1000, S).astype(f32)
+    got = gpp.optimal_interpolation(gpp.Grid(y, x, elev, type=gpp.Cartesian), bg, gpp.Points(py, px, pel, type=gpp.Cartesian), obs, ratios,
+                                    pbg, gpp.BarnesStructure(15000, 200), 30)
+    want = orc.optimal_interpolation((y, x, elev, None), bg, (py, px, pel, None), obs, ratios, pbg,
+                                     B.make_structure(B.BARNES, 15000.0, 200.0), 30, B.CARTESIAN)
+    assert_close(got.ravel(), want, 1.0, RTOL, "cartesian OI with elevation term")
+
+
+def test_ensi_device_entry_point(gpp, orc):
+    """gpp_optimal_interpolation_ensi_device (observation state built once, device-resident ensemble, one launch per
+    range) against the host entry point and the oracle; ranges, in-place analysis and the valid-member flags."""
+    import torch
+    from gridpp_b200 import device as gd
+    rng = np.random.default_rng(21)
+    ny, nx, dx, E, S = 48, 64, 200.0, 20, 900
+    y, x = np.meshgrid(30000 + np.arange(ny, dtype=f32) * dx, 30000 + np.arange(nx, dtype=f32) * dx, indexing="ij")
+    py, px = rng.uniform(0, 72000, S).astype(f32), rng.uniform(0, 76000, S).astype(f32)
+    bg = (rng.normal(size=(ny, nx, 1)) * 2 + rng.normal(size=(ny, nx, E))).astype(f32)
+    pbg = rng.normal(size=(S, E)).astype(f32)
+    obs, sig = rng.normal(size=S).astype(f32), np.full(S, 0.5, f32)
+    obs[3] = np.nan
+    grid, points, s = gpp.Grid(y, x, type=gpp.Cartesian), gpp.Points(py, px, type=gpp.Cartesian), gpp.BarnesStructure(10000)
+    host = gpp.optimal_interpolation_ensi(grid, bg, points, obs, sig, pbg, s, 50)
+    d_bg = torch.from_numpy(bg).cuda()
+    flags = gd.valid_members(d_bg)
+    assert flags.all()
+    state = gd.EnsembleObservationState(points, obs, sig, pbg, s, member_valid=flags)
+    skipped = torch.zeros(1, dtype=torch.int32, device="cuda")
+    whole = gd.optimal_interpolation_ensi(grid, d_bg, state, 50, num_skipped=skipped)
+    torch.cuda.synchronize()
+    assert int(skipped.item()) == 0
+    assert_bit_exact(whole.cpu().numpy(), host, "EnSI device vs host entry point")
+    want = orc.optimal_interpolation_ensi((y, x, None, None), bg, (py, px, None, None), obs, sig, pbg,
+                                          B.make_structure(B.BARNES, 10000.0), 50, B.CARTESIAN)
+    assert_close(whole.cpu().numpy().reshape(-1, E), want, 2.0, RTOL, "EnSI device entry vs oracle")
+    # two ranges cut inside a warm-start block, written into one output; then in place
+    parts = torch.full_like(d_bg, -5.0)
+    n = ny * nx
+    for a, b in ((0, 1000), (1000, n)):
+        gd.optimal_interpolation_ensi(grid, d_bg, state, 50, out=parts, first=a, count=b - a)
+    assert torch.equal(whole, parts)
+    inplace = d_bg.clone()
+    gd.optimal_interpolation_ensi(grid, inplace, state, 50, out=inplace)
+    assert torch.equal(whole, inplace)
+    # a member with a missing value is flagged and left untouched
+    bg2 = bg.copy()
+    bg2[5, 6, 7] = np.nan
+    d_bg2 = torch.from_numpy(bg2).cuda()
+    flags2 = gd.valid_members(d_bg2)
+    assert flags2.sum() == E - 1 and not flags2[7]
+    state2 = gd.EnsembleObservationState(points, obs, sig, pbg, s, member_valid=flags2)
+    out2 = gd.optimal_interpolation_ensi(grid, d_bg2, state2, 50).cpu().numpy()
+    assert_bit_exact(out2[..., 7], bg2[..., 7], "invalid member untouched")
+    host2 = gpp.optimal_interpolation_ensi(grid, bg2, points, obs, sig, pbg, s, 50)
+    assert_bit_exact(out2, host2, "EnSI device vs host with an invalid member")
+
+
+def test_spatial_structure_is_refused_where_unsupported(gpp):
+    """a spatially varying structure function handed to an entry point that takes a plain descriptor must raise,
+    not analyse with a localization distance of zero."""
+    from gridpp_b200 import device as gd
+    from gridpp_b200._lib import NotImplementedOnDevice
+    y, x = np.meshgrid(np.arange(6, dtype=f32) * 1000, np.arange(7, dtype=f32) * 1000, indexing="ij")
+    grid = gpp.Grid(y, x, type=gpp.Cartesian)
+    spatial = gpp.BarnesStructure(grid, np.full((6, 7), 2500, f32), np.zeros((6, 7), f32), np.zeros((6, 7), f32))
+    points = gpp.Points([1000, 3000], [1000, 4000], type=gpp.Cartesian)
+    bg = np.zeros((6, 7, 5), f32)
+    with pytest.raises(NotImplementedOnDevice):
+        gpp.optimal_interpolation_ensi(grid, bg, points, [1.0, 2.0], [0.5, 0.5], np.zeros((2, 5), f32), spatial, 10)
+    with pytest.raises(NotImplementedOnDevice):
+        gd.ObservationState(points, [1.0, 2.0], [0.5, 0.5], [0.0, 0.0], spatial)
+    with pytest.raises(NotImplementedOnDevice):
+        gd.EnsembleObservationState(points, [1.0, 2.0], [0.5, 0.5], np.zeros((2, 5), f32), spatial)
+    # ... while optimal_interpolation itself supports it
+    out = gpp.optimal_interpolation(grid, bg[..., 0], points, [1.0, 2.0], [0.5, 0.5], [0.0, 0.0], spatial, 10)
+    assert np.abs(out).max() > 0
+
+
+# ------------------------------------------------------------------ full BASELINE.json sizes ------------
+def test_full_size_c4_quantile_fast_windows(gpp, orc):
+    """Config 4 at full size (8000 x 8000, halfwidth 15, 20 thresholds, quantile 0.5): the filter is local, so any window
+    of the full-size result must equal the oracle run on that window plus its halo -- bit for bit -- at the four corners,
+    across the middle, and on a block of missing values."""
+    rng = np.random.default_rng(1000)
+    n, hw = 8000, 15
+    f = rng.random((n, n), dtype=f32)
+    f[4000:4040, 3000:3040] = np.nan
+    f[rng.random((n, n), dtype=f32) < 0.002] = np.nan
+    thr = np.linspace(0, 1, 20).astype(f32)
+    res = gpp.neighbourhood_quantile_fast(f, 0.5, hw, thr)
+    assert res.shape == (n, n) and res.dtype == np.float32
+    for (r, c) in ((0, 0), (0, n - 90), (n - 90, 0), (n - 90, n - 90), (3990, 2990), (5000, 1234)):
+        r0, r1, c0, c1 = max(0, r - hw), min(n, r + 90 + hw), max(0, c - hw), min(n, c + 90 + hw)
+        want = orc.neighbourhood_quantile_fast(f[r0:r1, c0:c1], 0.5, hw, thr)[r - r0:r - r0 + 90, c - c0:c - c0 + 90]
+        assert_bit_exact(res[r:r + 90, c:c + 90], want, "C4 window (%d,%d)" % (r, c))
+    assert np.isnan(res[4016:4024, 3016:3024]).all()          # windows without a valid value
+    inner = res[100:-100, 100:-100]
+    ok = ~np.isnan(inner)
+    assert 0.3 < float(inner[ok].mean()) < 0.7               # the median of uniform noise
+
+
+def test_full_size_c5_ensi_subsample(gpp, orc):
+    """Config 5 at full size (2500 x 2500 grid, dx 200 m, 20 members, 5000 observations, Barnes 10 km, max_points 50):
+    every grid point is independent, so a sample of the full-grid analysis must match the oracle at just those points
+    (the Points overload, oi_ensi.cpp:114)."""
+    rng = np.random.default_rng(1000)
+    n, dx, E, S = 2500, 200.0, 20, 5000
+    y, x = np.meshgrid(np.arange(n, dtype=f32) * dx, np.arange(n, dtype=f32) * dx, indexing="ij")
+    py, px = (rng.random(S) * n * dx).astype(f32), (rng.random(S) * n * dx).astype(f32)
+    bg = rng.standard_normal((n, n, E), dtype=f32)
+    bg += rng.standard_normal((n, n, 1), dtype=f32) * 2
+    pbg = rng.standard_normal((S, E)).astype(f32)
+    obs = rng.standard_normal(S).astype(f32)
+    sig = np.full(S, 0.5, f32)
+    grid, points = gpp.Grid(y, x, type=gpp.Cartesian), gpp.Points(py, px, type=gpp.Cartesian)
+    out = gpp.optimal_interpolation_ensi(grid, bg, points, obs, sig, pbg, gpp.BarnesStructure(10000), 50)
+    assert out.shape == bg.shape and not np.isnan(out).any()
+    pick = rng.choice(n * n, 3000, replace=False)
+    pick[:4] = [0, n - 1, n * (n - 1), n * n - 1]
+    want = orc.optimal_interpolation_ensi((y.ravel()[pick], x.ravel()[pick], None, None), bg.reshape(-1, E)[pick], (py, px, None, None), obs,
+                                          sig, pbg, B.make_structure(B.BARNES, 10000.0), 50, B.CARTESIAN)
+    assert_close(out.reshape(-1, E)[pick], want, 2.0, RTOL, "C5 subsample")
+    assert np.abs(out - bg).max() > 0.1
