@@ -30,7 +30,7 @@ constexpr int FAST_K = 30;          // max observations per point on the registe
 constexpr int WARPS_PER_CTA = 8;
 
 #ifndef OI_LRU
-#define OI_LRU 8
+#define OI_LRU 16
 #endif
 #ifndef OI_TOP_SHIFT
 #define OI_TOP_SHIFT 2

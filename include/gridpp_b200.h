@@ -279,6 +279,25 @@ int gpp_neighbourhood_quantile_fast_ens_device(const float* d_input, int ny, int
 int gpp_get_neighbourhood_thresholds_host(const float* input, long long n_values, int num_thresholds, float* thresholds,
                                           int* num_out);
 
+/* ---------------------------------------------------------------- row statistics ---------------------- */
+#define GPP_MEDIAN 20
+#define GPP_QUANTILE 40
+#define GPP_STD 50
+#define GPP_VARIANCE 60
+#define GPP_RANDOMCHOICE 90
+/* gridpp::calc_statistic(vec2, statistic) util.cpp:208-215 (and, with n_rows = 1, the vec form :19-110): `array` holds
+ * n_rows rows of row_length values; out[r] = statistic of the valid values of row r (Mean, Min, Median, Max, Std,
+ * Variance, Sum, Count; float accumulation in element order as the reference). RandomChoice -> NOT_IMPLEMENTED (the
+ * reference draws from rand()). The device form is what the ensemble filters chain (member fastest). */
+int gpp_calc_statistic_host(const float* array, long long n_rows, int row_length, int statistic, float* out);
+int gpp_calc_statistic_device(const float* d_array, long long n_rows, int row_length, int statistic, float* d_out, void* stream);
+/* gridpp::calc_quantile(vec, q) util.cpp:111-178, (vec2, q) :179-186 and (vec3, vec2 q) :187-207: quantile_rows (one level
+ * per row) may be NULL, then `quantile` applies to every row. A level outside [0, 1] -> INVALID_ARGUMENT. */
+int gpp_calc_quantile_host(const float* array, long long n_rows, int row_length, float quantile, const float* quantile_rows, float* out);
+/* gridpp::interpolate(vec x, iX, iY) util.cpp:377-431 (n = 1: the scalar form): piecewise-linear with the reference's
+ * plateau rules (get_lower_index / get_upper_index, util.cpp:339-376). */
+int gpp_interpolate_host(const float* x, long long n, const float* iX, const float* iY, int m, float* out);
+
 /* ---------------------------------------------------------------- instrumentation -------------------- */
 /* Number of kernels this library has launched on the calling process so far (bench.py's gpu_launches). */
 unsigned long long gpp_kernel_launch_count(void);

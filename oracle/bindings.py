@@ -186,6 +186,23 @@ class CpuLib:
             timing.append(sec.value)
         return (out, var) if want_variance else out
 
+    def optimal_interpolation_grid(self, lats, lons, background, opts, pobs, pratios, pbackground, structure, max_points, ctype,
+                                   allow_extrapolation=True, timing=None):
+        """gridpp::optimal_interpolation(Grid...) oi.cpp:26-87 (compiled reference only): lats / lons / background are (Y, X)."""
+        la, lo, bg = _f(lats), _f(lons), _f(background)
+        ny, nx = la.shape
+        pl, po = _f(opts[0]).ravel(), _f(opts[1]).ravel()
+        nS = pl.size
+        obs, rat, pbg = _f(pobs).ravel(), _f(pratios).ravel(), _f(pbackground).ravel()
+        out = np.empty((ny, nx), np.float32)
+        sec = C.c_double()
+        self._check(self._fn("optimal_interpolation_grid")(_p(la), _p(lo), ny, nx, _p(bg), _p(pl), _p(po), nS, ctype, _p(obs), _p(rat),
+                                                           _p(pbg), C.byref(structure), max_points, int(allow_extrapolation), _p(out),
+                                                           C.byref(sec)))
+        if timing is not None:
+            timing.append(sec.value)
+        return out
+
     def optimal_interpolation_ensi(self, bpts, background, opts, pobs, psigmas, pbackground, structure, max_points, ctype,
                                    allow_extrapolation=True, timing=None):
         bl, bo, be, bf = (_f(a).ravel() if a is not None else None for a in bpts)

@@ -232,6 +232,27 @@ int ref_optimal_interpolation(const float* blats, const float* blons, const floa
     REF_CATCH
 }
 
+// gridpp::optimal_interpolation(Grid...) oi.cpp:26-87: the overload a user of the README example calls, with its
+// to_points() copy of the grid and the two full-field vec2 <-> vec copies inside the timed region (the Grid itself is
+// built outside it). Used by bench.py --impl reference for one full pass over the 4000 x 4000 grid of config 3.
+int ref_optimal_interpolation_grid(const float* blats, const float* blons, int ny, int nx, const float* background,
+                                   const float* plats, const float* plons, int nS, int type, const float* pobs,
+                                   const float* pratios, const float* pbackground, const gpp_structure* sd, int max_points,
+                                   int allow_extrapolation, float* analysis, double* seconds) {
+    REF_TRY
+    gridpp::Grid grid(to_vec2(blats, ny, nx), to_vec2(blons, ny, nx), gridpp::vec2(), gridpp::vec2(), (gridpp::CoordinateType) type);
+    gridpp::Points op = make_points(plats, plons, nullptr, nullptr, nS, type);
+    gridpp::StructureFunctionPtr s = make_structure(sd);
+    gridpp::vec2 bg = to_vec2(background, ny, nx);
+    gridpp::vec obs = to_vec(pobs, nS), ratios = to_vec(pratios, nS), pbg = to_vec(pbackground, nS);
+    if(nS > 0) op.get_neighbours(plats[0], plons[0], 1.0f);   // build the observation index outside the timed region
+    clk::time_point t0 = clk::now();
+    gridpp::vec2 out = gridpp::optimal_interpolation(grid, bg, op, obs, ratios, pbg, *s, max_points, allow_extrapolation != 0);
+    if(seconds) *seconds = since(t0);
+    from_vec2(out, analysis, ny, nx);
+    REF_CATCH
+}
+
 // gridpp::optimal_interpolation_full(Points...) with a SPATIALLY VARYING structure function: <Family>Structure(Grid, vec2 h,
 // vec2 v, vec2 w, min_rho), structure.cpp:168-184 (Barnes), :342 (Soar), :492 (Toar), :643 (Powerlaw), :790 (Linear).
 // The scale grid is gny x gnx (glats/glons/h/v/w row-major).
