@@ -211,6 +211,15 @@ class Points:
         _, x, y, z = convert_coordinates(s._lats[index], s._lons[index], s._type)
         return Point(s._lats[index], s._lons[index], s._elevs[index], s._lafs[index], s._type, x, y, z)
 
+    def get_in_domain_indices(self, grid):
+        """Points::get_in_domain_indices, points.cpp:77-92: the points that lie inside a cell of `grid` (Grid::get_box)."""
+        found = grid._boxes(self._set._lats, self._set._lons)[0]
+        return _np.nonzero(found)[0].astype(_np.int32)
+
+    def get_in_domain(self, grid):
+        """Points::get_in_domain, points.cpp:93-110 (the new set has the default coordinate type, like subset())."""
+        return self.subset(self.get_in_domain_indices(grid))
+
     def subset(self, indices):
         indices = _np.asarray(indices, dtype=_np.int64).ravel()
         if indices.size and indices.max() >= self.size():
@@ -292,6 +301,51 @@ class Grid:
         p._set = self._set   # grid.cpp:131-145: same tree, elevations and land fractions
         return p
 
+    def _boxes(self, lats, lons):
+        """Grid::get_box (grid.cpp:149-231) for many locations: the grid cell (Y1, X1, Y2, X2) containing each one, found
+        from its nearest node (one batched device query) and the reference's point_in_rectangle test
+        (util.cpp:566-578, float arithmetic) on the up to four cells around that node. Returns (found, Y1, X1, Y2, X2)."""
+        f = _np.float32
+        lats, lons = _np.asarray(lats, f).ravel(), _np.asarray(lons, f).ravel()
+        n = lats.size
+        found = _np.zeros(n, bool)
+        box = _np.full((4, n), -1, _np.int32)
+        nY, nX = self._shape
+        if n == 0 or self._set.n == 0 or nX <= 1 or nY <= 1:
+            return (found,) + tuple(box)
+        nn = self._set.nearest(lats, lons, True).astype(_np.int64)
+        ok = nn >= 0
+        Y, X = nn // nX, nn % nX
+        la, lo = self._set._lats.reshape(self._shape), self._set._lons.reshape(self._shape)
+
+        def side(a_lat, a_lon, b_lat, b_lon):   # D = (AB.lat * m.lon + AB.lon * m.lat) + C, AB = vect2d(A, B)
+            ab_lon, ab_lat = f(b_lon - a_lon), f(f(-1) * f(b_lat - a_lat))
+            c = f(f(-1) * f(f(ab_lat * a_lon) + f(ab_lon * a_lat)))
+            return f(f(f(ab_lat * lons) + f(ab_lon * lats)) + c)
+
+        for it in range(4):                     # the reference's order: (ydir, xdir) = (1,-1), (1,1), (-1,-1), (-1,1)
+            xdir, ydir = -1 + 2 * (it % 2), -1 + 2 * (it < 2)
+            cand = ok & ~found & ~((Y == 0) & (ydir == -1)) & ~((Y == nY - 1) & (ydir == 1)) & ~((X == 0) & (xdir == -1)) & ~((X == nX - 1) & (xdir == 1))
+            if not cand.any():
+                continue
+            Yc, Xc = _np.clip(Y + ydir, 0, nY - 1), _np.clip(X + xdir, 0, nX - 1)
+            A = (la[Y, X], lo[Y, X]); B = (la[Yc, X], lo[Yc, X]); C = (la[Yc, Xc], lo[Yc, Xc]); D = (la[Y, Xc], lo[Y, Xc])
+            with _np.errstate(all="ignore"):
+                d1, d2, d3, d4 = side(*A, *B), side(*A, *D), side(*B, *C), side(*C, *D)
+            inside = ((0 >= d1) & (0 >= d4) & (0 <= d2) & (0 >= d3)) | ((0 <= d1) & (0 <= d4) & (0 >= d2) & (0 <= d3))
+            hit = cand & inside
+            box[0][hit] = _np.where(ydir == 1, Y, Y - 1)[hit]
+            box[2][hit] = _np.where(ydir == 1, Y + 1, Y)[hit]
+            box[1][hit] = _np.where(xdir == 1, X, X - 1)[hit]
+            box[3][hit] = _np.where(xdir == 1, X + 1, X)[hit]
+            found |= hit
+        return (found,) + tuple(box)
+
+    def get_box(self, lat, lon):
+        """Grid::get_box: (found, Y1, X1, Y2, X2), as the SWIG wrapper returns the reference's output arguments."""
+        found, y1, x1, y2, x2 = self._boxes([lat], [lon])
+        return bool(found[0]), int(y1[0]), int(x1[0]), int(y2[0]), int(x2[0])
+
 
 class KDTree(Points):
     """gridpp::KDTree (gridpp.h:1746-1873): the index without elevation / land-fraction metadata."""
@@ -351,6 +405,30 @@ class KDTree(Points):
         return float(f(dist))
 
 
+def _calc_distance_fast(lat1, lon1, lat2=None, lon2=None, type=Geodetic):
+    """KDTree::calc_distance_fast, kdtree.cpp:134-180 (equirectangular approximation; (Point, Point) form :181-186)."""
+    if lat2 is None:
+        p1, p2 = lat1, lon1
+        if p1.type != p2.type:
+            raise RuntimeError("Coordinate types must be the same")
+        lat1, lon1, lat2, lon2, type = p1.lat, p1.lon, p2.lat, p2.lon, p1.type
+    f = _np.float32
+    lat1, lon1, lat2, lon2 = f(lat1), f(lon1), f(lat2), f(lon2)
+    if type == Cartesian:
+        dx, dy = lon1 - lon2, lat1 - lat2
+        return float(_np.sqrt(dx * dx + dy * dy))
+    lat1r, lat2r, lon1r, lon2r = KDTree.deg2rad(lat1), KDTree.deg2rad(lat2), KDTree.deg2rad(lon1), KDTree.deg2rad(lon2)
+    dlon = _math.fmod(abs(lon1r - lon2r), 2 * _math.pi)
+    if dlon > _math.pi:
+        dlon = 2 * _math.pi - dlon
+    max_lat = lat2r if abs(lat2r) > abs(lat1r) else lat1r
+    dx2 = f(_math.cos(max_lat) ** 2 * dlon * dlon)
+    dy2 = f((lat1r - lat2r) * (lat1r - lat2r))
+    return float(f(6.378137e6 * _math.sqrt(float(f(dx2 + dy2)))))
+
+
+KDTree.calc_distance_fast = staticmethod(_calc_distance_fast)
+KDTree_calc_distance_fast = _calc_distance_fast
 KDTree_deg2rad, KDTree_rad2deg = KDTree.deg2rad, KDTree.rad2deg
 KDTree_calc_distance, KDTree_calc_straight_distance = KDTree.calc_distance, KDTree.calc_straight_distance
 
@@ -743,6 +821,47 @@ def neighbourhood(input, halfwidth, statistic):
     return out
 
 
+def _brute_force(input, halfwidth, statistic, quantile):
+    field = _np.asarray(input, dtype=_np.float32)
+    if field.ndim not in (2, 3):
+        raise ValueError("input must have 2 or 3 dimensions")
+    field = _farray(field, field.ndim, "input")
+    if halfwidth < 0:
+        raise ValueError("Half width must be > 0")
+    if 0 in field.shape:
+        return _np.zeros((0, 0), _np.float32)
+    ny, nx = field.shape[:2]
+    ne = field.shape[2] if field.ndim == 3 else 1
+    out = _np.empty((ny, nx), _np.float32)
+    _check(_libc.gpp_neighbourhood_brute_force_host(_fptr(field), ny, nx, ne, int(halfwidth), int(statistic), float(quantile), _fptr(out)))
+    return out
+
+
+def neighbourhood_brute_force(input, halfwidth, statistic):
+    """gridpp::neighbourhood_brute_force(vec2 | vec3, halfwidth, statistic), neighbourhood.cpp:528-533."""
+    return _brute_force(input, halfwidth, statistic, 0.0)
+
+
+def neighbourhood_quantile(input, quantile, halfwidth):
+    """gridpp::neighbourhood_quantile(vec2 | vec3, quantile, halfwidth), neighbourhood.cpp:534-539: the exact quantile."""
+    return _brute_force(input, halfwidth, Quantile, quantile)
+
+
+def neighbourhood_ens(input, halfwidth, statistic):
+    future_deprecation_warning("neighbourhood_ens", "neighbourhood")                 # neighbourhood.cpp:541-544
+    return neighbourhood(input, halfwidth, statistic)
+
+
+def neighbourhood_quantile_ens(input, quantile, halfwidth):
+    future_deprecation_warning("neighbourhood_quantile_ens", "neighbourhood_quantile")
+    return neighbourhood_quantile(input, quantile, halfwidth)
+
+
+def neighbourhood_quantile_ens_fast(input, quantile, halfwidth, thresholds):
+    future_deprecation_warning("neighbourhood_quantile_ens_fast", "neighbourhood_quantile_fast")
+    return neighbourhood_quantile_fast(input, quantile, halfwidth, thresholds)
+
+
 def neighbourhood_quantile_fast(input, quantile, halfwidth, thresholds):
     """gridpp::neighbourhood_quantile_fast(vec2, float | vec2, halfwidth, thresholds), neighbourhood.cpp:296-409."""
     field = _np.asarray(input, dtype=_np.float32)
@@ -776,6 +895,8 @@ def neighbourhood_quantile_fast(input, quantile, halfwidth, thresholds):
 def get_neighbourhood_thresholds(input, num_thresholds):
     """gridpp::get_neighbourhood_thresholds(vec2 | vec3, num_thresholds), neighbourhood.cpp:243-295."""
     field = _np.asarray(input, dtype=_np.float32)
+    if field.size == 0 and num_thresholds > 0:
+        return _np.zeros(0, _np.float32)          # neighbourhood.cpp:247-248 (an empty list arrives as an empty vec2)
     if field.ndim not in (2, 3):
         raise ValueError("input must have 2 or 3 dimensions")
     if num_thresholds <= 0:
@@ -787,6 +908,188 @@ def get_neighbourhood_thresholds(input, num_thresholds):
     n = _C.c_int()
     _check(_libc.gpp_get_neighbourhood_thresholds_host(_fptr(flat), flat.size, int(num_thresholds), _fptr(out), _C.byref(n)))
     return out[:n.value].copy()
+
+
+# ---------------------------------------------------------------------------------------------------------
+_STATISTIC_NAMES = {"mean": Mean, "min": Min, "max": Max, "median": Median, "quantile": Quantile, "std": Std, "sum": Sum,
+                    "count": Count, "randomchoice": RandomChoice}
+
+
+def get_statistic(name):
+    """gridpp::get_statistic, gridpp.cpp:11-44 (note: no "variance" entry in the reference)."""
+    return _STATISTIC_NAMES.get(name, Unknown)
+
+
+def calc_statistic(array, statistic):
+    """gridpp::calc_statistic: (vec, statistic) -> float (util.cpp:19-110), (vec2, statistic) -> vec (:208-215)."""
+    a = _np.asarray(array, dtype=_np.float32)
+    if a.ndim not in (1, 2):
+        raise ValueError("array must be 1- or 2-dimensional")
+    rows = _np.ascontiguousarray(a.reshape(1, -1) if a.ndim == 1 else a)
+    out = _np.empty(rows.shape[0], _np.float32)
+    if rows.shape[0] > 0:
+        _check(_libc.gpp_calc_statistic_host(_fptr(rows), rows.shape[0], rows.shape[1], int(statistic), _fptr(out)))
+    return float(out[0]) if a.ndim == 1 else out
+
+
+def calc_quantile(array, quantile=MV):
+    """gridpp::calc_quantile: (vec, q) -> float (util.cpp:111-178), (vec2, q) -> vec (:179-186), (vec3, vec2 q) -> vec2 (:187-207)."""
+    a = _np.asarray(array, dtype=_np.float32)
+    if a.ndim == 3:
+        q = _farray(quantile, 2, "quantile")
+        if a.shape[:2] != q.shape:
+            raise ValueError("Dimension mismatch between array and quantile")
+        if a.shape[0] == 0 or a.shape[1] == 0:
+            return _np.zeros(a.shape[:2], _np.float32)
+        if a.shape[2] == 0:
+            return _np.full(a.shape[:2], MV, _np.float32)
+        rows = _np.ascontiguousarray(a.reshape(-1, a.shape[2]))
+        out = _np.empty(rows.shape[0], _np.float32)
+        _check(_libc.gpp_calc_quantile_host(_fptr(rows), rows.shape[0], rows.shape[1], float("nan"), _fptr(_np.ascontiguousarray(q.ravel())), _fptr(out)))
+        return out.reshape(a.shape[:2])
+    if a.ndim not in (1, 2):
+        raise ValueError("array must be 1-, 2- or 3-dimensional")
+    q = float(quantile)
+    if q < 0 or q > 1:
+        raise ValueError("calc_quantile: Quantile must be between 0 and 1 inclusive")
+    rows = _np.ascontiguousarray(a.reshape(1, -1) if a.ndim == 1 else a)
+    out = _np.empty(rows.shape[0], _np.float32)
+    if rows.shape[0] > 0:
+        _check(_libc.gpp_calc_quantile_host(_fptr(rows), rows.shape[0], rows.shape[1], q, None, _fptr(out)))
+    return float(out[0]) if a.ndim == 1 else out
+
+
+def interpolate(x, iX, iY):
+    """gridpp::interpolate: (float, vec, vec) -> float (util.cpp:377-414), (vec, vec, vec) -> vec (:415-431)."""
+    ix, iy = _farray(iX, 1, "iX"), _farray(iY, 1, "iY")
+    if ix.size != iy.size:
+        raise ValueError("Dimension mismatch. Cannot interpolate.")
+    xs = _np.asarray(x, dtype=_np.float32)
+    scalar = xs.ndim == 0
+    flat = _np.ascontiguousarray(xs.reshape(-1))
+    out = _np.empty(flat.size, _np.float32)
+    if flat.size > 0:
+        _check(_libc.gpp_interpolate_host(_fptr(flat), flat.size, _fptr(ix), _fptr(iy), ix.size, _fptr(out)))
+    return float(out[0]) if scalar else out
+
+
+def calc_even_quantiles(values, num):
+    """gridpp::calc_even_quantiles, util.cpp:261-338: evenly spaced quantiles among the distinct values (the selection
+    gpp_get_neighbourhood_thresholds_host makes after its device sort)."""
+    v = _farray(values, 1, "values")
+    if int(num) == 0 or v.size == 0:
+        return _np.zeros(0, _np.float32)
+    out = _np.empty(int(num), _np.float32)
+    n = _C.c_int()
+    _check(_libc.gpp_get_neighbourhood_thresholds_host(_fptr(v), v.size, int(num), _fptr(out), _C.byref(n)))
+    return out[:n.value].copy()
+
+
+def get_lower_index(x, values):
+    """gridpp::get_lower_index, util.cpp:339-357: last index whose value is <= x (first of an exact match)."""
+    index = None
+    for i, c in enumerate(_np.asarray(values, _np.float32)):
+        if not is_valid(float(c)):
+            continue
+        if c < x:
+            index = i
+        elif c == x:
+            index = i
+            break
+        else:
+            break
+    if index is None:
+        raise RuntimeError("get_lower_index: no valid value at or below x")   # the reference returns an undefined int
+    return index
+
+
+def get_upper_index(x, values):
+    """gridpp::get_upper_index, util.cpp:358-376."""
+    index = None
+    vals = _np.asarray(values, _np.float32)
+    for i in range(len(vals) - 1, -1, -1):
+        c = vals[i]
+        if not is_valid(float(c)):
+            continue
+        if c > x:
+            index = i
+        elif c == x:
+            index = i
+            break
+        else:
+            break
+    if index is None:
+        raise RuntimeError("get_upper_index: no valid value at or above x")
+    return index
+
+
+def num_missing_values(array):
+    """gridpp::num_missing_values, util.cpp:216-224"""
+    return int((~_np.isfinite(_np.asarray(array, _np.float32))).sum())
+
+
+def is_valid_lat(lat, type):
+    """util.cpp:617-621"""
+    if type == Cartesian:
+        return is_valid(lat)
+    return is_valid(lat) and -90.001 <= lat <= 90.001
+
+
+def is_valid_lon(lon, type):
+    """util.cpp:622-624"""
+    return is_valid(lon)
+
+
+def compatible_size(a, b):
+    """gridpp::compatible_size, util.cpp:421-474 (Grid | Points | array against an array)."""
+    bb = _np.asarray(b)
+    if isinstance(a, Grid):
+        shape = tuple(a.size())
+        if bb.ndim == 2:
+            return bb.shape == shape
+        return bb.size == 0 or bb.shape[1:] == shape        # (T, Y, X)
+    if isinstance(a, Points):
+        if bb.ndim == 1:
+            return a.size() == bb.shape[0]
+        return bb.shape[0] == 0 or a.size() == bb.shape[1]   # (T, N)
+    aa = _np.asarray(a)
+    if aa.ndim == 2 and bb.ndim == 3:
+        return aa.shape == bb.shape[:2] or (aa.size == 0 and bb.size == 0)
+    return aa.shape == bb.shape
+
+
+_debug_level = 0
+
+
+def set_debug_level(level):
+    global _debug_level
+    _debug_level = int(level)
+
+
+def get_debug_level():
+    return _debug_level
+
+
+def debug(string):
+    print(string)
+
+
+def warning(string):
+    print("Warning: " + string)
+
+
+def error(string):
+    print("Error: " + string)
+    raise RuntimeError(string)
+
+
+def future_deprecation_warning(function, other=""):
+    print("Future deprecation warning: %s will be deprecated%s" % (function, (", use %s instead." % other) if other != "" else "."))
+
+
+def clock():
+    import time
+    return time.time()
 
 
 # ---------------------------------------------------------------------------------------------------------

@@ -90,6 +90,8 @@ _proto("gpp_neighbourhood_quantile_fast_ens_device", C.c_int, vp, C.c_int, C.c_i
 
 _proto("gpp_calc_statistic_host", C.c_int, fp, C.c_longlong, C.c_int, C.c_int, fp)
 _proto("gpp_calc_statistic_device", C.c_int, vp, C.c_longlong, C.c_int, C.c_int, vp, vp)
+_proto("gpp_neighbourhood_brute_force_host", C.c_int, fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, fp)
+_proto("gpp_neighbourhood_brute_force_device", C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, vp, vp)
 _proto("gpp_calc_quantile_host", C.c_int, fp, C.c_longlong, C.c_int, C.c_float, fp, fp)
 _proto("gpp_interpolate_host", C.c_int, fp, C.c_longlong, fp, fp, C.c_int, fp)
 _proto("gpp_structure_field_create", C.c_int, vp, fp, fp, fp, C.POINTER(vp))
@@ -112,6 +114,7 @@ EXPORTS = [
     "gpp_neighbourhood_quantile_fast_device", "gpp_neighbourhood_ens_host", "gpp_neighbourhood_ens_device",
     "gpp_neighbourhood_quantile_fast_ens_host", "gpp_neighbourhood_quantile_fast_ens_device",
     "gpp_calc_statistic_host", "gpp_calc_statistic_device", "gpp_calc_quantile_host", "gpp_interpolate_host",
+    "gpp_neighbourhood_brute_force_host", "gpp_neighbourhood_brute_force_device",
     "gpp_get_neighbourhood_thresholds_host", "gpp_structure_field_create", "gpp_structure_field_destroy",
     "gpp_structure_field_lookup_host", "gpp_structure_field_localization_distance", "gpp_optimal_interpolation_spatial_host",
 ]

@@ -141,17 +141,19 @@ int gpp_neighbourhood_ens_device(const float* d_input, int ny, int nx, int ne, i
                                  void* stream_) {
     cudaStream_t stream = (cudaStream_t) stream_;
     if(halfwidth < 0) return fail(GPP_ERR_INVALID_ARGUMENT, "Half width must be > 0");                       // neighbourhood.cpp:29-30
-    if(statistic == 40) return fail(GPP_ERR_INVALID_ARGUMENT, "Use neighbourhood_quantile for computing neighbourhood quantiles");
-    if(statistic != GPP_MEAN && statistic != GPP_SUM && statistic != GPP_COUNT && statistic != GPP_MIN && statistic != GPP_MAX)
-        return fail(GPP_ERR_NOT_IMPLEMENTED, "neighbourhood statistic %d is outside the device hot path (Mean, Sum, Count, Min, Max)", statistic);
+    if(statistic == GPP_QUANTILE) return fail(GPP_ERR_INVALID_ARGUMENT, "Use neighbourhood_quantile for computing neighbourhood quantiles");
     GPP_TRY(ensure_device());
     if(ny <= 0 || nx <= 0 || ne <= 0) return GPP_OK;
     const size_t n = (size_t) ny * nx;
     float* flat = nullptr;
     GPP_CUDA(cudaMallocAsync((void**) &flat, sizeof(float) * n, stream));
-    ens_statistic_kernel<<<blocks_for(n), 256, 0, stream>>>(d_input, n, ne, statistic, flat);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    int rc = gpp_neighbourhood_device(flat, ny, nx, 0, ny, halfwidth, statistic, d_output, stream_);
+    int rc = GPP_OK;
+    if(statistic == GPP_MEAN || statistic == GPP_SUM || statistic == GPP_COUNT || statistic == GPP_MIN || statistic == GPP_MAX) {
+        ens_statistic_kernel<<<blocks_for(n), 256, 0, stream>>>(d_input, n, ne, statistic, flat);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
+    else rc = gpp_calc_statistic_device(d_input, (long long) n, ne, statistic, flat, stream_);   // Median, Std, Variance, RandomChoice
+    if(rc == GPP_OK) rc = gpp_neighbourhood_device(flat, ny, nx, 0, ny, halfwidth, statistic, d_output, stream_);
     cudaFreeAsync(flat, stream);
     if(rc == GPP_OK) GPP_CUDA(cudaGetLastError());
     return rc;

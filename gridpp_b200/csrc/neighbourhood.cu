@@ -521,18 +521,53 @@ int opt_in_smem(K kernel, size_t bytes) {
 
 }  // namespace
 
+namespace {
+__global__ void square_kernel(const float* __restrict__ in, size_t n, float* __restrict__ out) {
+    const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if(i < n) out[i] = __fmul_rn(in[i], in[i]);
+}
+// neighbourhood.cpp:221-234: float arithmetic, no clamp of a negative difference (the square root of one is NaN)
+__global__ void variance_kernel(const float* __restrict__ mean, const float* __restrict__ mean2, size_t n, bool want_std, float* __restrict__ out) {
+    const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) return;
+    const float var = __fsub_rn(mean2[i], __fmul_rn(mean[i], mean[i]));
+    out[i] = want_std ? __fsqrt_rn(var) : var;
+}
+}  // namespace
+
 extern "C" {
 
 int gpp_neighbourhood_device(const float* d_input, int n_rows_in, int nx, int row0, int n_rows_out, int halfwidth, int statistic,
                              float* d_output, void* stream_) {
     cudaStream_t stream = (cudaStream_t) stream_;
     GPP_TRY(check_tile(d_input, n_rows_in, nx, row0, n_rows_out, halfwidth, d_output));
-    if(statistic != GPP_MEAN && statistic != GPP_SUM && statistic != GPP_COUNT && statistic != GPP_MIN && statistic != GPP_MAX) {
-        if(statistic == 40) return fail(GPP_ERR_INVALID_ARGUMENT, "Use neighbourhood_quantile for computing neighbourhood quantiles");   // :31-32
-        return fail(GPP_ERR_NOT_IMPLEMENTED, "neighbourhood statistic %d is outside the device hot path (Mean, Sum, Count, Min, Max)", statistic);
-    }
+    if(statistic == GPP_QUANTILE) return fail(GPP_ERR_INVALID_ARGUMENT, "Use neighbourhood_quantile for computing neighbourhood quantiles");   // :31-32
     GPP_TRY(ensure_device());
     if(n_rows_out == 0 || nx == 0) return GPP_OK;
+    if(statistic == GPP_STD || statistic == GPP_VARIANCE) {
+        // neighbourhood.cpp:211-235: mean2 - mean * mean from two Mean filters (of the field and of its float square)
+        const size_t n_in = (size_t) n_rows_in * nx, n_out = (size_t) n_rows_out * nx;
+        float *sq = nullptr, *mean = nullptr, *mean2 = nullptr;
+        GPP_CUDA(cudaMallocAsync((void**) &sq, sizeof(float) * n_in, stream));
+        GPP_CUDA(cudaMallocAsync((void**) &mean, sizeof(float) * n_out, stream));
+        GPP_CUDA(cudaMallocAsync((void**) &mean2, sizeof(float) * n_out, stream));
+        square_kernel<<<(unsigned) ((n_in + 255) / 256), 256, 0, stream>>>(d_input, n_in, sq);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        int rc = gpp_neighbourhood_device(d_input, n_rows_in, nx, row0, n_rows_out, halfwidth, GPP_MEAN, mean, stream_);
+        if(rc == GPP_OK) rc = gpp_neighbourhood_device(sq, n_rows_in, nx, row0, n_rows_out, halfwidth, GPP_MEAN, mean2, stream_);
+        if(rc == GPP_OK) {
+            variance_kernel<<<(unsigned) ((n_out + 255) / 256), 256, 0, stream>>>(mean, mean2, n_out, statistic == GPP_STD, d_output);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+        }
+        cudaFreeAsync(sq, stream);
+        cudaFreeAsync(mean, stream);
+        cudaFreeAsync(mean2, stream);
+        if(rc == GPP_OK) GPP_CUDA(cudaGetLastError());
+        return rc;
+    }
+    if(statistic != GPP_MEAN && statistic != GPP_SUM && statistic != GPP_COUNT && statistic != GPP_MIN && statistic != GPP_MAX)
+        // neighbourhood.cpp:237-238: everything else (Median, RandomChoice) gathers the window and calls calc_statistic
+        return gpp_neighbourhood_brute_force_device(d_input, n_rows_in, nx, 1, row0, n_rows_out, halfwidth, statistic, 0.f, d_output, stream_);
     TileArgs a = {d_input, d_output, n_rows_in, nx, row0, n_rows_out, halfwidth};
     const bool minmax = statistic == GPP_MIN || statistic == GPP_MAX;
     {   // copy-engine (TMA) kernels first; they decline shapes they do not cover
@@ -586,7 +621,7 @@ int gpp_neighbourhood_device(const float* d_input, int n_rows_in, int nx, int ro
 
 int gpp_neighbourhood_host(const float* input, int ny, int nx, int halfwidth, int statistic, float* output) {
     if(halfwidth < 0) return fail(GPP_ERR_INVALID_ARGUMENT, "Half width must be > 0");
-    if(statistic == 40) return fail(GPP_ERR_INVALID_ARGUMENT, "Use neighbourhood_quantile for computing neighbourhood quantiles");
+    if(statistic == GPP_QUANTILE) return fail(GPP_ERR_INVALID_ARGUMENT, "Use neighbourhood_quantile for computing neighbourhood quantiles");
     GPP_TRY(ensure_device());
     if(ny <= 0 || nx <= 0) return GPP_OK;   // neighbourhood.cpp:33-34: empty in, empty out
     const size_t n = (size_t) ny * nx;

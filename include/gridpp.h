@@ -716,6 +716,42 @@ inline vec2 neighbourhood_quantile_fast(const vec3& input, const vec2& quantile,
     return b200::quantile_fast(b200::flatten(input), ny, nx, ne, MV, &quantile, halfwidth, thresholds);
 }
 
+// neighbourhood_brute_force / neighbourhood_quantile (exact), neighbourhood.cpp:528-539, and the deprecated names :540-552
+namespace b200 {
+inline vec2 brute_force(const vec& flat, int ny, int nx, int ne, int halfwidth, int statistic, float quantile) {
+    require(halfwidth >= 0, "Half width must be > 0");
+    if(ny == 0 || nx == 0 || ne == 0) return vec2();
+    vec out((size_t) ny * nx);
+    check(gpp_neighbourhood_brute_force_host(flat.data(), ny, nx, ne, halfwidth, statistic, quantile, out.data()));
+    return unflatten(out, ny, nx);
+}
+}  // namespace b200
+inline vec2 neighbourhood_brute_force(const vec2& input, int halfwidth, Statistic statistic) {
+    int ny, nx;
+    b200::shape_of(input, ny, nx, "input");
+    return b200::brute_force(b200::flatten(input), ny, nx, 1, halfwidth, (int) statistic, 0.f);
+}
+inline vec2 neighbourhood_brute_force(const vec3& input, int halfwidth, Statistic statistic) {
+    int ny, nx, ne;
+    b200::shape_of(input, ny, nx, ne, "input");
+    return b200::brute_force(b200::flatten(input), ny, nx, ne, halfwidth, (int) statistic, 0.f);
+}
+inline vec2 neighbourhood_quantile(const vec2& input, float quantile, int halfwidth) {
+    int ny, nx;
+    b200::shape_of(input, ny, nx, "input");
+    return b200::brute_force(b200::flatten(input), ny, nx, 1, halfwidth, (int) Quantile, quantile);
+}
+inline vec2 neighbourhood_quantile(const vec3& input, float quantile, int halfwidth) {
+    int ny, nx, ne;
+    b200::shape_of(input, ny, nx, ne, "input");
+    return b200::brute_force(b200::flatten(input), ny, nx, ne, halfwidth, (int) Quantile, quantile);
+}
+inline vec2 neighbourhood_ens(const vec3& input, int halfwidth, Statistic statistic) { return neighbourhood(input, halfwidth, statistic); }
+inline vec2 neighbourhood_quantile_ens(const vec3& input, float quantile, int halfwidth) { return neighbourhood_quantile(input, quantile, halfwidth); }
+inline vec2 neighbourhood_quantile_ens_fast(const vec3& input, float quantile, int halfwidth, const vec& thresholds) {
+    return neighbourhood_quantile_fast(input, quantile, halfwidth, thresholds);
+}
+
 // neighbourhood.cpp:243-295
 namespace b200 {
 inline vec thresholds_of(const vec& flat, int num_thresholds) {
@@ -730,6 +766,78 @@ inline vec thresholds_of(const vec& flat, int num_thresholds) {
 }  // namespace b200
 inline vec get_neighbourhood_thresholds(const vec2& input, int num_thresholds) { return b200::thresholds_of(b200::flatten(input), num_thresholds); }
 inline vec get_neighbourhood_thresholds(const vec3& input, int num_thresholds) { return b200::thresholds_of(b200::flatten(input), num_thresholds); }
+
+// -------------------------------------------------------------------------------------------------------------------
+// Row statistics (util.cpp:19-215,377-431; gridpp.cpp:11-44): calc_statistic, calc_quantile, interpolate, get_statistic.
+inline Statistic get_statistic(std::string name) {
+    static const std::pair<const char*, Statistic> names[] = {{"mean", Mean}, {"min", Min}, {"max", Max}, {"median", Median}, {"quantile", Quantile},
+                                                              {"std", Std}, {"sum", Sum}, {"count", Count}, {"randomchoice", RandomChoice}};
+    for(const auto& n : names)
+        if(name == n.first) return n.second;
+    return Unknown;
+}
+namespace b200 {
+// rows of different lengths cannot go through the flat entry point at once: one call per row then
+inline bool ragged(const vec2& array) {
+    for(const vec& row : array)
+        if(row.size() != array[0].size()) return true;
+    return false;
+}
+}  // namespace b200
+inline float calc_statistic(const vec& array, Statistic statistic) {
+    float out = MV;
+    b200::check(gpp_calc_statistic_host(array.data(), 1, (int) array.size(), (int) statistic, &out));
+    return out;
+}
+inline vec calc_statistic(const vec2& array, Statistic statistic) {
+    vec out(array.size());
+    if(array.empty()) return out;
+    if(b200::ragged(array)) {
+        for(size_t n = 0; n < array.size(); n++) out[n] = calc_statistic(array[n], statistic);
+        return out;
+    }
+    b200::check(gpp_calc_statistic_host(b200::flatten(array).data(), (long long) array.size(), (int) array[0].size(), (int) statistic, out.data()));
+    return out;
+}
+inline float calc_quantile(const vec& array, float quantile) {
+    float out = MV;
+    b200::check(gpp_calc_quantile_host(array.data(), 1, (int) array.size(), quantile, nullptr, &out));
+    return out;
+}
+inline vec calc_quantile(const vec2& array, float quantile = MV) {
+    vec out(array.size());
+    if(array.empty()) return out;
+    if(b200::ragged(array)) {
+        for(size_t n = 0; n < array.size(); n++) out[n] = calc_quantile(array[n], quantile);
+        return out;
+    }
+    b200::check(gpp_calc_quantile_host(b200::flatten(array).data(), (long long) array.size(), (int) array[0].size(), quantile, nullptr, out.data()));
+    return out;
+}
+inline vec2 calc_quantile(const vec3& array, const vec2& quantile) {
+    int ny, nx, nt, qy, qx;
+    b200::shape_of(array, ny, nx, nt, "array");
+    b200::shape_of(quantile, qy, qx, "quantile");
+    b200::require(ny == qy && (ny == 0 || nx == qx), "Dimension mismatch between array and quantile");
+    if(ny == 0 || nx == 0) return vec2();
+    if(nt == 0) return vec2((size_t) ny, vec((size_t) nx, MV));
+    vec out((size_t) ny * nx);
+    b200::check(gpp_calc_quantile_host(b200::flatten(array).data(), (long long) ny * nx, nt, MV, b200::flatten(quantile).data(), out.data()));
+    return b200::unflatten(out, ny, nx);
+}
+inline vec interpolate(const vec& x, const vec& iX, const vec& iY) {
+    b200::require(iX.size() == iY.size(), "Dimension mismatch. Cannot interpolate.");
+    vec out(x.size());
+    if(x.empty()) return out;
+    b200::check(gpp_interpolate_host(x.data(), (long long) x.size(), iX.data(), iY.data(), (int) iX.size(), out.data()));
+    return out;
+}
+inline float interpolate(float x, const vec& iX, const vec& iY) {
+    b200::require(iX.size() == iY.size(), "Dimension mismatch. Cannot interpolate.");
+    float out = MV;
+    b200::check(gpp_interpolate_host(&x, 1, iX.data(), iY.data(), (int) iX.size(), &out));
+    return out;
+}
 
 // -------------------------------------------------------------------------------------------------------------------
 // nearest (nearest.cpp:7-222): all eight overloads gather n_fields flattened input fields at the nearest input node of

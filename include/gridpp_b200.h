@@ -36,12 +36,17 @@ extern "C" {
 #define GPP_GEODETIC 0
 #define GPP_CARTESIAN 1
 
-/* gridpp::Statistic, gridpp.h:88-100 (numeric values kept; only the hot-path statistics run on the device) */
+/* gridpp::Statistic, gridpp.h:88-100 (numeric values kept) */
 #define GPP_MEAN 0
 #define GPP_MIN 10
+#define GPP_MEDIAN 20
 #define GPP_MAX 30
+#define GPP_QUANTILE 40
+#define GPP_STD 50
+#define GPP_VARIANCE 60
 #define GPP_SUM 70
 #define GPP_COUNT 80
+#define GPP_RANDOMCHOICE 90
 
 /* Structure-function families, src/api/structure.cpp */
 #define GPP_STRUCT_BARNES 0   /* structure.cpp:143-282 */
@@ -239,9 +244,10 @@ int gpp_optimal_interpolation_spatial_host(const gpp_points* bpoints, const floa
                                            int allow_extrapolation, float* analysis, float* analysis_variance);
 
 /* ---------------------------------------------------------------- neighbourhood filters -------------- */
-/* gridpp::neighbourhood(vec2, halfwidth, statistic) neighbourhood.cpp:28-242 for statistic in
- * {Mean, Sum, Count, Min, Max}: NaN-aware statistic over the (2*halfwidth+1)^2 window CLIPPED to the domain
- * (neighbourhood.cpp:104-107,160-167); a window without valid values gives NaN (Count gives 0). */
+/* gridpp::neighbourhood(vec2, halfwidth, statistic) neighbourhood.cpp:28-242: NaN-aware statistic over the
+ * (2*halfwidth+1)^2 window CLIPPED to the domain (neighbourhood.cpp:104-107,160-167); a window without valid values gives
+ * NaN (Count gives 0). Mean / Sum / Count / Min / Max run the TMA-staged stencil kernels; Std / Variance are two Mean
+ * filters (:211-235); Median / RandomChoice gather the window (gpp_neighbourhood_brute_force_*). */
 int gpp_neighbourhood_host(const float* input, int ny, int nx, int halfwidth, int statistic, float* output);
 /* Device form with explicit row window, for row-tiled multi-GPU use: d_input holds n_rows_in rows (a tile
  * plus whatever halo rows exist; the domain is taken to be exactly these rows), output rows
@@ -280,17 +286,20 @@ int gpp_get_neighbourhood_thresholds_host(const float* input, long long n_values
                                           int* num_out);
 
 /* ---------------------------------------------------------------- row statistics ---------------------- */
-#define GPP_MEDIAN 20
-#define GPP_QUANTILE 40
-#define GPP_STD 50
-#define GPP_VARIANCE 60
-#define GPP_RANDOMCHOICE 90
 /* gridpp::calc_statistic(vec2, statistic) util.cpp:208-215 (and, with n_rows = 1, the vec form :19-110): `array` holds
  * n_rows rows of row_length values; out[r] = statistic of the valid values of row r (Mean, Min, Median, Max, Std,
- * Variance, Sum, Count; float accumulation in element order as the reference). RandomChoice -> NOT_IMPLEMENTED (the
- * reference draws from rand()). The device form is what the ensemble filters chain (member fastest). */
+ * Variance, Sum, Count; float accumulation in element order as the reference; RandomChoice picks a valid value of the row
+ * with a hash of the call count and the row -- the reference draws from the C library's rand(), whose sequence is not
+ * reproduced). The device form is what the ensemble filters chain (member fastest). */
 int gpp_calc_statistic_host(const float* array, long long n_rows, int row_length, int statistic, float* out);
 int gpp_calc_statistic_device(const float* d_array, long long n_rows, int row_length, int statistic, float* d_out, void* stream);
+/* gridpp::neighbourhood_brute_force(vec2 | vec3, halfwidth, statistic) and gridpp::neighbourhood_quantile(vec2 | vec3,
+ * quantile, halfwidth) (statistic = GPP_QUANTILE), neighbourhood.cpp:528-630: the clipped window of every pixel (all members
+ * for a vec3; ne = 1 for a vec2) is reduced with calc_statistic / calc_quantile. The device form takes a row window like
+ * gpp_neighbourhood_device. Also what gpp_neighbourhood_* run for Median and RandomChoice (neighbourhood.cpp:237-238). */
+int gpp_neighbourhood_brute_force_host(const float* input, int ny, int nx, int ne, int halfwidth, int statistic, float quantile, float* output);
+int gpp_neighbourhood_brute_force_device(const float* d_input, int n_rows_in, int nx, int ne, int row0, int n_rows_out, int halfwidth,
+                                         int statistic, float quantile, float* d_output, void* stream);
 /* gridpp::calc_quantile(vec, q) util.cpp:111-178, (vec2, q) :179-186 and (vec3, vec2 q) :187-207: quantile_rows (one level
  * per row) may be NULL, then `quantile` applies to every row. A level outside [0, 1] -> INVALID_ARGUMENT. */
 int gpp_calc_quantile_host(const float* array, long long n_rows, int row_length, float quantile, const float* quantile_rows, float* out);

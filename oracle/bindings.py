@@ -18,6 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 GEODETIC, CARTESIAN = 0, 1
 MEAN, MIN, MAX, SUM, COUNT = 0, 10, 30, 70, 80
+MEDIAN, QUANTILE, STD, VARIANCE, RANDOMCHOICE = 20, 40, 50, 60, 90
 BARNES, CRESSMAN, SOAR, TOAR, POWERLAW, LINEAR = range(6)
 
 
@@ -253,6 +254,17 @@ class CpuLib:
         ny, nx = f.shape
         out = np.full((ny, nx), np.nan, np.float32)
         self._check(self._fn("neighbourhood_brute_force")(_p(f), ny, nx, halfwidth, statistic, _p(out)))
+        return out
+
+    def neighbourhood_window(self, field, halfwidth, statistic, quantile=0.0):
+        """neighbourhood_brute_force / neighbourhood_quantile (statistic == QUANTILE) of a (Y, X) or (Y, X, E) field."""
+        f = _f(field)
+        ny, nx = f.shape[:2]
+        ne = f.shape[2] if f.ndim == 3 else 1
+        out = np.full((ny, nx), np.nan, np.float32)
+        fn = self._fn("neighbourhood_window_ens")
+        fn.argtypes = [_fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _fp]
+        self._check(fn(_p(f), ny, nx, ne, halfwidth, statistic, float(quantile), _p(out)))
         return out
 
     def neighbourhood_quantile_fast(self, field, quantile, halfwidth, thresholds, timing=None):

@@ -1137,8 +1137,19 @@ int orc_neighbourhood(const float* input, int ny, int nx, int halfwidth, int sta
     double t0 = now_seconds();
     int rc = 0;
     if(statistic == MEAN || statistic == SUM || statistic == COUNT) neighbourhood_sat(input, ny, nx, halfwidth, statistic, output);
-    else if(statistic == MIN || statistic == MAX) rc = neighbourhood_window(input, ny, nx, halfwidth, statistic, output);
-    else FAIL(3, "statistic %d is outside the hot path", statistic);
+    else if(statistic == STD || statistic == VARIANCE) { /* neighbourhood.cpp:211-235: two Mean filters, float arithmetic */
+        size_t N = (size_t) ny * nx;
+        float *mean = malloc(sizeof(float) * N), *input2 = malloc(sizeof(float) * N), *mean2 = malloc(sizeof(float) * N);
+        neighbourhood_sat(input, ny, nx, halfwidth, MEAN, mean);
+        for(size_t i = 0; i < N; i++) input2[i] = input[i] * input[i];
+        neighbourhood_sat(input2, ny, nx, halfwidth, MEAN, mean2);
+        for(size_t i = 0; i < N; i++) {
+            float var = mean2[i] - mean[i] * mean[i];
+            output[i] = statistic == STD ? sqrtf(var) : var;
+        }
+        free(mean); free(input2); free(mean2);
+    }
+    else rc = neighbourhood_window(input, ny, nx, halfwidth, statistic, output);   /* :146-210 (Min/Max) and :237-238 (the rest) */
     if(seconds) *seconds = now_seconds() - t0;
     return rc;
 }
@@ -1146,6 +1157,32 @@ int orc_neighbourhood_brute_force(const float* input, int ny, int nx, int halfwi
     if(halfwidth < 0) FAIL(1, "Half width must be > 0");
     if(ny == 0 || nx == 0) return 0;
     return neighbourhood_window(input, ny, nx, halfwidth, statistic, output);
+}
+/* neighbourhood.cpp:547-630: the brute-force helpers behind neighbourhood_brute_force(vec2 | vec3) (:528-533) and
+ * neighbourhood_quantile(vec2 | vec3) (:534-539, statistic == QUANTILE). input is ny x nx x ne, member fastest. */
+int orc_neighbourhood_window_ens(const float* input, int ny, int nx, int ne, int halfwidth, int statistic, float quantile, float* output) {
+    if(halfwidth < 0) FAIL(1, "Half width must be > 0");
+    if(ny == 0 || nx == 0 || ne == 0) return 0;
+    int rc = 0;
+    #pragma omp parallel
+    {
+        float* hood = malloc(sizeof(float) * (size_t) (2 * halfwidth + 1) * (2 * halfwidth + 1) * ne);
+        #pragma omp for
+        for(int i = 0; i < ny; i++)
+            for(int j = 0; j < nx; j++) {
+                int n = 0;
+                int i0 = i - halfwidth > 0 ? i - halfwidth : 0, i1 = i + halfwidth < ny - 1 ? i + halfwidth : ny - 1;
+                int j0 = j - halfwidth > 0 ? j - halfwidth : 0, j1 = j + halfwidth < nx - 1 ? j + halfwidth : nx - 1;
+                for(int ii = i0; ii <= i1; ii++)
+                    for(int jj = j0; jj <= j1; jj++)
+                        for(int e = 0; e < ne; e++) hood[n++] = input[((size_t) ii * nx + jj) * ne + e];
+                float* o = &output[(size_t) i * nx + j];
+                int r = statistic == QUANTILE ? orc_calc_quantile(hood, n, quantile, o) : orc_calc_statistic(hood, n, statistic, o);
+                if(r) rc = r;
+            }
+        free(hood);
+    }
+    return rc;
 }
 
 /* neighbourhood.cpp:302-409 (scalar quantile: :296-301) */

@@ -326,6 +326,26 @@ int ref_neighbourhood_brute_force(const float* input, int ny, int nx, int halfwi
     if(out.size() == (size_t) ny) from_vec2(out, output, ny, nx);
     REF_CATCH
 }
+// gridpp::neighbourhood_brute_force(vec2 | vec3, ...) and gridpp::neighbourhood_quantile(vec2 | vec3, ...) (statistic ==
+// Quantile), neighbourhood.cpp:528-539. input is ny x nx x ne (ne == 1: the vec2 overloads).
+int ref_neighbourhood_window_ens(const float* input, int ny, int nx, int ne, int halfwidth, int statistic, float quantile, float* output) {
+    REF_TRY
+    gridpp::vec2 out;
+    if(ne == 1) {
+        gridpp::vec2 in = to_vec2(input, ny, nx);
+        out = statistic == gridpp::Quantile ? gridpp::neighbourhood_quantile(in, quantile, halfwidth)
+                                            : gridpp::neighbourhood_brute_force(in, halfwidth, (gridpp::Statistic) statistic);
+    }
+    else {
+        gridpp::vec3 in(ny, gridpp::vec2(nx));
+        for(int y = 0; y < ny; y++)
+            for(int x = 0; x < nx; x++) in[y][x].assign(input + ((size_t) y * nx + x) * ne, input + ((size_t) y * nx + x + 1) * ne);
+        out = statistic == gridpp::Quantile ? gridpp::neighbourhood_quantile(in, quantile, halfwidth)
+                                            : gridpp::neighbourhood_brute_force(in, halfwidth, (gridpp::Statistic) statistic);
+    }
+    if(out.size() == (size_t) ny) from_vec2(out, output, ny, nx);
+    REF_CATCH
+}
 // gridpp::neighbourhood_quantile_fast(vec2, float | vec2, halfwidth, thresholds) neighbourhood.cpp:296-409
 int ref_neighbourhood_quantile_fast(const float* input, int ny, int nx, float quantile, const float* quantile_field,
                                     int halfwidth, const float* thresholds, int num_thresholds, float* output,

@@ -93,6 +93,11 @@ static int checks() {
     EXPECT_THROW(neighbourhood(field, 1, Quantile), std::invalid_argument);
     EXPECT_THROW(nearest(grid, obs_points, vec2{{1, 2}}), std::invalid_argument);
     EXPECT(neighbourhood(vec2(), 1, Mean).empty());                         // neighbourhood.cpp:33-34
+    EXPECT(neighbourhood_brute_force(vec2(), 1, Median).empty() && neighbourhood_quantile(vec2(), 0.5f, 1).empty());
+    EXPECT_THROW(neighbourhood_quantile(field, 0.5f, -1), std::invalid_argument);
+    EXPECT_THROW(interpolate(0.5f, {0, 1, 2}, {0, 1}), std::invalid_argument);   // util.cpp:380-381
+    EXPECT(get_statistic("median") == Median && get_statistic("variance") == Unknown && get_statistic("mean") == Mean);
+    EXPECT(is_valid(1.f) && !is_valid(MV));
     EXPECT(get_neighbourhood_thresholds(vec2(), 5).empty());
     // no observations: EnSI returns the background untouched without touching the device (oi_ensi.cpp:49-51)
     vec3 ens = {{{1, 2}, {3, 4}, {5, 6}}, {{7, 8}, {9, 10}, {11, 12}}};
@@ -166,6 +171,22 @@ static int run() {
     write("qf_field", neighbourhood_quantile_fast(background, quantile_field, hw, thresholds));
     write("qf_ens", neighbourhood_quantile_fast(ensemble, quantile, hw, thresholds));
     write("thresholds", get_neighbourhood_thresholds(background, (int) thresholds.size()));
+    // statistics family (util.cpp:19-215,377-431; neighbourhood.cpp:211-238,528-539)
+    write("nbh_std", neighbourhood(background, hw, Std));
+    write("nbh_median", neighbourhood(background, hw, Median));
+    write("nbh_quantile", neighbourhood_quantile(background, quantile, hw));
+    write("nbh_quantile_ens", neighbourhood_quantile(ensemble, quantile, hw));
+    write("brute_variance", neighbourhood_brute_force(background, hw, Variance));
+    {
+        vec2 rows((size_t) ny * nx);
+        for(int y = 0; y < ny; y++)
+            for(int x = 0; x < nx; x++) rows[(size_t) y * nx + x] = ensemble[y][x];
+        write("member_median", calc_statistic(rows, Median));
+        write("member_q", calc_quantile(rows, quantile));
+        write("member_q_field", calc_quantile(ensemble, quantile_field));
+        write("interp", interpolate(thresholds, thresholds, calc_statistic(vec2(thresholds.size(), thresholds), Sum)));
+        if(calc_statistic(rows[3], Mean) != calc_statistic(vec2(1, rows[3]), Mean)[0]) throw std::runtime_error("calc_statistic(vec) != calc_statistic(vec2)[0]");
+    }
     write("nearest_grid", nearest(points, grid, obs));
 
     // index queries (kdtree.cpp:18-106): integer results, compared bit for bit

@@ -96,6 +96,17 @@ def test_cxx_api_matches_mirror_and_oracle(driver, gpp, orc, tmp_path):
     assert_bit_exact(out("qf_field", (ny, nx)), gpp.neighbourhood_quantile_fast(bg, qfield, hw, thr), "quantile_fast(vec2 quantile)")
     assert_bit_exact(out("qf_ens", (ny, nx)), gpp.neighbourhood_quantile_fast(ens, quantile, hw, thr), "quantile_fast(vec3)")
     assert_bit_exact(out("thresholds"), gpp.get_neighbourhood_thresholds(bg, T), "get_neighbourhood_thresholds")
+    assert_bit_exact(out("nbh_std", (ny, nx)), gpp.neighbourhood(bg, hw, gpp.Std), "neighbourhood Std")
+    assert_bit_exact(out("nbh_median", (ny, nx)), gpp.neighbourhood(bg, hw, gpp.Median), "neighbourhood Median")
+    assert_bit_exact(out("nbh_quantile", (ny, nx)), gpp.neighbourhood_quantile(bg, quantile, hw), "neighbourhood_quantile")
+    assert_bit_exact(out("nbh_quantile_ens", (ny, nx)), gpp.neighbourhood_quantile(ens, quantile, hw), "neighbourhood_quantile(vec3)")
+    assert_bit_exact(out("brute_variance", (ny, nx)), gpp.neighbourhood_brute_force(bg, hw, gpp.Variance), "neighbourhood_brute_force")
+    assert_bit_exact(out("member_median"), gpp.calc_statistic(ens.reshape(-1, E), gpp.Median), "calc_statistic(vec2)")
+    assert_bit_exact(out("member_q"), gpp.calc_quantile(ens.reshape(-1, E), quantile), "calc_quantile(vec2)")
+    assert_bit_exact(out("member_q_field", (ny, nx)), gpp.calc_quantile(ens, qfield), "calc_quantile(vec3, vec2)")
+    assert_bit_exact(out("interp"), gpp.interpolate(thr, thr, np.full(T, thr.sum(dtype=f32), f32) * 0 + gpp.calc_statistic(np.tile(thr, (T, 1)), gpp.Sum)), "interpolate")
+    assert_bit_exact(out("nbh_median", (ny, nx)), orc.neighbourhood(bg, hw, B.MEDIAN), "C++ neighbourhood Median vs oracle")
+    assert_bit_exact(out("nbh_quantile_ens", (ny, nx)), orc.neighbourhood_window(ens, hw, B.QUANTILE, quantile), "C++ neighbourhood_quantile(vec3) vs oracle")
     assert_bit_exact(out("nearest_grid", (ny, nx)), gpp.nearest(points, grid, obs), "nearest(points, grid, values)")
     nn = np.array([points.get_nearest_neighbour(a, b) for a, b in zip(qlat, qlon)], np.int32)
     assert_bit_exact(out("nn", dtype=np.int32), nn, "get_nearest_neighbour")

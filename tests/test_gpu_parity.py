@@ -351,8 +351,8 @@ def test_neighbourhood_known_answers(gpp):
                                   [[0, 0, 2, 4, 4], [0, 0, 3, 6, 6], [2, 3, 5, 7, 6], [4, 6, 7, 8, 6], [4, 6, 6, 6, 4]])
     big = (np.arange(1, 1000, dtype=np.float64) ** 3).astype(f32)[:, None]
     np.testing.assert_array_almost_equal(gpp.neighbourhood(big, 0, gpp.Mean) / big - 1, np.zeros(big.shape), 6)
-    with pytest.raises(RuntimeError):
-        gpp.neighbourhood(values, 1, gpp.Median)    # outside the device hot path: says so, does not fall back
+    # the median of the clipped window (neighbourhood.cpp:237-238 -> brute force -> calc_quantile(., 0.5))
+    assert gpp.neighbourhood(values, 1, gpp.Median)[2, 2] == 12.5   # 8 valid values: half-way between 12 and 13
 
 
 def test_neighbourhood_random_vs_oracle(gpp, orc):

@@ -219,3 +219,71 @@ def test_full_size_c5_ensi_subsample(gpp, orc):
                                           sig, pbg, B.make_structure(B.BARNES, 10000.0), 50, B.CARTESIAN)
     assert_close(out.reshape(-1, E)[pick], want, 2.0, RTOL, "C5 subsample")
     assert np.abs(out - bg).max() > 0.1
+
+
+# ------------------------------------------------------------------ statistics family --
+STAT_NAMES = ("mean", "min", "median", "max", "std", "variance", "sum", "count")
+
+
+def test_statistics_family_golden(gpp):
+    """calc_statistic / calc_quantile / interpolate, neighbourhood with Std / Variance / Median, neighbourhood_brute_force and
+    neighbourhood_quantile (vec2 and vec3) against the fixture generated from the compiled reference: bit for bit, except
+    where a window sum is involved (Std / Variance of neighbourhood() go through the Mean filter: 1e-5)."""
+    from util import golden
+    g = golden("statistics")
+    f, e, rows = g["field"], g["ensemble"], g["rows"]
+    code = {n: getattr(gpp, n.capitalize()) for n in STAT_NAMES}
+    for key in g.files:
+        if key.startswith("nbh_hw"):
+            hw, name = int(key[6:].split("__")[0]), key.split("__")[1]
+            got = gpp.neighbourhood(f, hw, code[name])
+            if name == "median":
+                assert_bit_exact(got, g[key], key)
+            else:
+                # mean2 - mean^2 cancels: the 1e-5 bar applies at the scale of mean2 (max |field|^2), not of the difference
+                want = g[key]
+                scale = float(np.nanmax(np.abs(f))) ** (1 if name == "std" else 2)
+                ok = ~(np.isnan(want) | np.isnan(got))
+                if name == "std":   # sqrt of a tiny negative difference is NaN in either implementation: compare where both are numbers
+                    assert (np.isnan(want) & ~np.isnan(got)).sum() + (~np.isnan(want) & np.isnan(got)).sum() <= 0.01 * want.size, key
+                    assert np.abs(got[ok] ** 2 - want[ok] ** 2).max() <= 4e-5 * scale ** 2, key
+                else:
+                    assert np.array_equal(np.isnan(want), np.isnan(got)), key
+                    assert np.abs(got[ok] - want[ok]).max() <= 4e-5 * scale, key
+        elif key.startswith("brute_ens_hw") or key.startswith("brute_hw"):
+            ens = key.startswith("brute_ens_hw")
+            hw, name = int(key.split("hw")[1].split("__")[0]), key.split("__")[1]
+            assert_bit_exact(gpp.neighbourhood_brute_force(e if ens else f, hw, code[name]), g[key], key)
+        elif key.startswith("quantile_"):
+            ens = key.startswith("quantile_ens_hw")
+            hw, q = int(key.split("hw")[1].split("__")[0]), float(key.split("__q")[1])
+            assert_bit_exact(gpp.neighbourhood_quantile(e if ens else f, q, hw), g[key], key)
+        elif key.startswith("rows__q"):
+            assert_bit_exact(gpp.calc_quantile(rows, float(key[7:])), g[key], key)
+        elif key.startswith("rows__"):
+            assert_bit_exact(gpp.calc_statistic(rows, code[key[6:]]), g[key], key)
+    assert_bit_exact(gpp.interpolate(g["interp_x"], g["interp_ix"], g["interp_iy"]), g["interp_y"], "interpolate")
+    # scalar forms, per-cell quantile levels, error behaviour
+    assert gpp.calc_statistic(rows[0], gpp.Mean) == g["rows__mean"][0]
+    assert gpp.calc_quantile(rows[3], 0.5) == g["rows__q0.5"][3]
+    q2 = np.full((4, 5), 0.25, f32)
+    assert_bit_exact(gpp.calc_quantile(rows[:20].reshape(4, 5, -1), q2).ravel(), g["rows__q0.25"][:20], "calc_quantile(vec3, vec2)")
+    with pytest.raises(ValueError):
+        gpp.calc_quantile(rows[0], 1.1)
+    with pytest.raises(ValueError):
+        gpp.interpolate(0.5, [0, 1, 2], [0, 1])
+    assert np.isnan(gpp.interpolate(0.5, [], []))
+    # RandomChoice: any valid value of the row / window is a correct outcome
+    picks = gpp.calc_statistic(rows, gpp.RandomChoice)
+    for r, p in zip(rows, picks):
+        assert (np.isnan(p) and not np.isfinite(r).any()) or p in r
+    rc = gpp.neighbourhood(f, 1, gpp.RandomChoice)
+    assert np.isnan(rc[12, 23]) and rc[0, 0] in f[0:2, 0:2]
+    # a large window (961 values) and a window that does not fit the shared-memory stage (31 x 31 x 5 values)
+    big = np.random.default_rng(3).random((40, 40)).astype(f32)
+    got = gpp.neighbourhood_quantile(big, 0.5, 15)[5, 20]           # rows 0..20, columns 5..35 of the field
+    assert abs(got - np.quantile(big[0:21, 5:36].astype(np.float64), 0.5)) < 1e-6
+    ens_big = np.random.default_rng(4).random((33, 33, 5)).astype(f32)
+    got = gpp.neighbourhood_quantile(ens_big, 1.0, 15)[16, 16]
+    assert got == ens_big[1:32, 1:32].max()
+    assert gpp.neighbourhood_brute_force(ens_big, 15, gpp.Count)[16, 16] == 31 * 31 * 5

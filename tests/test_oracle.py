@@ -399,3 +399,32 @@ def test_spatially_varying_structures_live_against_reference(orc, ref):
             b, bv = orc.optimal_interpolation_spatial(*args, allow_extrapolation=extr, want_variance=True)
             assert_close(b, a, 1.0, 1e-5, "spatial family %d mp=%d" % (stype, mp))
             assert_close(bv, av, 1.0, 1e-5, "spatial variance family %d mp=%d" % (stype, mp))
+
+
+STAT_CODES = dict(mean=B.MEAN, min=B.MIN, median=B.MEDIAN, max=B.MAX, std=B.STD, variance=B.VARIANCE, sum=B.SUM, count=B.COUNT)
+
+
+def test_golden_statistics(orc):
+    """Round 2: Std / Variance / Median neighbourhoods, the brute-force and exact-quantile neighbourhoods (vec2 and vec3),
+    calc_statistic, calc_quantile and interpolate against the fixture generated from the compiled reference."""
+    g = golden("statistics")
+    f, e, rows = g["field"], g["ensemble"], g["rows"]
+    for key in g.files:
+        if key.startswith("nbh_hw"):
+            hw, name = int(key[6:].split("__")[0]), key.split("__")[1]
+            assert_bit_exact(orc.neighbourhood(f, hw, STAT_CODES[name]), g[key], key)
+        elif key.startswith("brute_ens_hw") or key.startswith("brute_hw"):
+            ens = key.startswith("brute_ens_hw")
+            hw, name = int(key.split("hw")[1].split("__")[0]), key.split("__")[1]
+            assert_bit_exact(orc.neighbourhood_window(e if ens else f, hw, STAT_CODES[name]), g[key], key)
+        elif key.startswith("quantile_"):
+            ens = key.startswith("quantile_ens_hw")
+            hw, q = int(key.split("hw")[1].split("__")[0]), float(key.split("__q")[1])
+            assert_bit_exact(orc.neighbourhood_window(e if ens else f, hw, B.QUANTILE, q), g[key], key)
+        elif key.startswith("rows__q"):
+            q = float(key[7:])
+            assert_bit_exact(np.array([orc.calc_quantile(r, q) for r in rows], np.float32), g[key], key)
+        elif key.startswith("rows__"):
+            assert_bit_exact(np.array([orc.calc_statistic(r, STAT_CODES[key[6:]]) for r in rows], np.float32), g[key], key)
+    got = np.array([orc.interpolate(v, g["interp_ix"], g["interp_iy"]) for v in g["interp_x"]], np.float32)
+    assert_bit_exact(got, g["interp_y"], "interpolate")

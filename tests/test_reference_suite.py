@@ -1,0 +1,69 @@
+"""Runs the reference's own unit tests for the hot path (tests/reference_suite/ref_test_*.py, verbatim copies of the
+metno/gridpp tests) against the product: `import gridpp` inside those files resolves to gridpp_b200. This is the
+drop-in check a user of the reference would make. Needs a GPU (the product has no CPU path).
+
+A test listed in KNOWN_DEVIATIONS is allowed to fail, with the reason stated; any other failure fails this test. The
+per-file pass counts are written to gpurun_out/reference_suite_report.json when that directory exists.
+"""
+import importlib.util
+import io
+import json
+import os
+import sys
+import unittest
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+SUITE = os.path.join(HERE, "reference_suite")
+
+# test id (file::Class.method) -> why the product deviates from the reference there
+KNOWN_DEVIATIONS = {
+}
+
+
+def _run_file(path):
+    name = "refsuite_" + os.path.basename(path)[:-3]
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    suite = unittest.defaultTestLoader.loadTestsFromModule(mod)
+    stream = io.StringIO()
+    result = unittest.TextTestRunner(stream=stream, verbosity=0).run(suite)
+    bad = {}
+    for test, tb in result.failures + result.errors:
+        tid = "%s::%s" % (os.path.basename(path), test.id().split(".", 1)[-1])
+        bad[tid] = tb.strip().splitlines()[-1][:300]
+    return result.testsRun, len(result.skipped), bad
+
+
+def test_reference_unit_tests_pass_against_the_product():
+    import gridpp_b200
+    saved = sys.modules.get("gridpp")
+    sys.modules["gridpp"] = gridpp_b200
+    report, unexpected = {}, {}
+    try:
+        for fn in sorted(os.listdir(SUITE)):
+            if not (fn.startswith("ref_test_") and fn.endswith(".py")):
+                continue
+            run, skipped, bad = _run_file(os.path.join(SUITE, fn))
+            report[fn] = {"run": run, "skipped": skipped, "failed": sorted(bad), "passed": run - len(bad) - skipped}
+            for tid, why in bad.items():
+                if tid not in KNOWN_DEVIATIONS:
+                    unexpected[tid] = why
+    finally:
+        if saved is None:
+            sys.modules.pop("gridpp", None)
+        else:
+            sys.modules["gridpp"] = saved
+    total = {"run": sum(r["run"] for r in report.values()), "passed": sum(r["passed"] for r in report.values()),
+             "known_deviations": len(KNOWN_DEVIATIONS)}
+    out_dir = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(out_dir):
+        with open(os.path.join(out_dir, "reference_suite_report.json"), "w") as f:
+            json.dump({"total": total, "files": report, "unexpected": unexpected}, f, indent=1, sort_keys=True)
+    print("reference suite:", json.dumps(total))
+    assert not unexpected, "reference tests failing against the product:\n" + "\n".join("%s: %s" % kv for kv in sorted(unexpected.items()))
+    assert total["run"] >= 100
