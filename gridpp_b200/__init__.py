@@ -233,11 +233,12 @@ class Grid:
     """gridpp::Grid (gridpp.h:1971-2060, grid.cpp): a 2-D array of points, flattened row-major for queries."""
 
     def __init__(self, lats=None, lons=None, elevs=None, lafs=None, type=Geodetic):
-        lats = _farray([[]] if lats is None else lats, 2, "lats")
-        lons = _farray([[]] if lons is None else lons, 2, "lons")
+        lats = _farray(_np.zeros((0, 0), _np.float32) if lats is None else lats, 2, "lats")
+        lons = _farray(_np.zeros((0, 0), _np.float32) if lons is None else lons, 2, "lons")
         if lats.shape != lons.shape:
             raise ValueError("Cannot create grid with unequal lat and lon sizes")
-        self._shape = lats.shape if lats.size else (0, 0)
+        self._shape = lats.shape if lats.size else (0, 0)      # Grid::size(), grid.cpp:122-130: (0, 0) without nodes
+        self._stored_shape = lats.shape                        # what get_lats() etc. return: the arrays as given (grid.cpp:12-55)
         elevs = _farray([[]] if elevs is None else elevs, 2, "elevs")
         lafs = _farray([[]] if lafs is None else lafs, 2, "lafs")
         # grid.cpp:41-54: elevations / land fractions of the wrong shape are replaced by missing values
@@ -251,16 +252,16 @@ class Grid:
         return _np.array(self._shape, dtype=_np.int32)
 
     def get_lats(self):
-        return self._set._lats.reshape(self._shape).copy()
+        return self._set._lats.reshape(self._stored_shape).copy()
 
     def get_lons(self):
-        return self._set._lons.reshape(self._shape).copy()
+        return self._set._lons.reshape(self._stored_shape).copy()
 
     def get_elevs(self):
-        return self._set._elevs.reshape(self._shape).copy()
+        return self._set._elevs.reshape(self._stored_shape).copy()
 
     def get_lafs(self):
-        return self._set._lafs.reshape(self._shape).copy()
+        return self._set._lafs.reshape(self._stored_shape).copy()
 
     def get_coordinate_type(self):
         return self._set._type
@@ -280,6 +281,8 @@ class Grid:
 
     def get_neighbours(self, lat, lon, radius, include_match=True):
         idx, _, count = self._set.neighbours([lat], [lon], radius, include_match)
+        if count[0] == 0:
+            return _np.zeros((0, 0), _np.int32)     # an empty ivec2
         return self._unflatten(idx[0, :count[0]]).reshape(-1, 2)
 
     def get_neighbours_with_distance(self, lat, lon, radius, include_match=True):
@@ -940,7 +943,7 @@ def calc_quantile(array, quantile=MV):
         if a.shape[:2] != q.shape:
             raise ValueError("Dimension mismatch between array and quantile")
         if a.shape[0] == 0 or a.shape[1] == 0:
-            return _np.zeros(a.shape[:2], _np.float32)
+            return _np.zeros((0, 0), _np.float32)               # util.cpp:190-195: an empty vec2
         if a.shape[2] == 0:
             return _np.full(a.shape[:2], MV, _np.float32)
         rows = _np.ascontiguousarray(a.reshape(-1, a.shape[2]))
@@ -1097,7 +1100,7 @@ def nearest(igrid, ogrid, ivalues):
     """gridpp::nearest, nearest.cpp:7-222 (all eight Grid/Points x Grid/Points x 2-D/3-D overloads)."""
     in_grid, out_grid = _is_grid(igrid), _is_grid(ogrid)
     ishape = tuple(igrid.size()) if in_grid else (igrid.size(),)
-    oshape = tuple(ogrid.size()) if out_grid else (ogrid.size(),)
+    oshape = tuple(ogrid._stored_shape) if out_grid else (ogrid.size(),)   # nearest.cpp:79-82: the output has the shape of get_lats()
     base = 2 if in_grid else 1
     values = _np.asarray(ivalues, dtype=_np.float32)
     multi = values.ndim == base + 1

@@ -514,6 +514,255 @@ __global__ void __launch_bounds__(NT, MINB_MM) nbh_minmax_tma_kernel(const __gri
     }
 }
 
+// ------------------------------------------------------------------ mean / sum in float ---------------
+// The same filter with every accumulation in fp32 and NO running sums, for the unrolled half-widths up to 7 (the
+// metric's configuration). What made the fp64 kernel slow was not arithmetic but pipes and barriers: three
+// f32 <-> f64 conversions per pixel on the 16-lane XU pipe, 8-byte line records, two barriers per batch. Here:
+//   * vertical pass: the 2 hw rows above the entering stage stay in registers; the column sum of every output row is a
+//     FRESH pairwise tree over its 2 hw + 1 rows in a fixed order (top row first). No value is ever subtracted, so a
+//     large value leaves no residue behind (the failure of a float running sum), and the sum of a window does not
+//     depend on where the CTA's chunk or the 8-row batch starts: row tiles reproduce the whole field bit for bit;
+//   * horizontal pass: 8 consecutive pixels per thread from 2 hw + 8 column sums with shared suffix / core / prefix
+//     partial sums. The grouping depends on x mod 8 only, which row tiling does not change;
+//   * the line buffer is double-buffered: one barrier per batch;
+//   * the ring is only read for entering rows, so a stage is handed back to the copy engine as soon as its batch
+//     has read it: NS - 1 stages in flight.
+// Missing values: the sum of a batch's 8 column sums is non-finite iff one of the 22 rows is; then (uniformly for the
+// CTA) the sums are redone over masked values with a validity bit mask per column, and the horizontal pass also
+// slides the valid counts. Error: two pairwise trees of depth <= 4 + 5 and one division, <= ~5e-7 relative to the
+// mean of |v| over the window (the reference accumulates in double, neighbourhood.cpp:45-99); the bar is 1e-5.
+template <int N>
+__device__ __forceinline__ float tree_sum_f(const float* v) {
+    if constexpr(N == 1) return v[0];
+    else return __fadd_rn(tree_sum_f<N / 2>(v), tree_sum_f<N - N / 2>(v + N / 2));
+}
+// s / c for a float s and a small positive integer c from r = fl(1 / c): Markstein's correction of s * r
+__device__ __forceinline__ float quot_f(float s, float fc, float r) {
+    const float q0 = __fmul_rn(s, r);
+    return __fmaf_rn(__fmaf_rn(-q0, fc, s), r, q0);
+}
+
+// two fp32 values in one 64-bit register and the packed IEEE add of sm_100 (FADD2): each half is rounded exactly like a
+// scalar add, so packing changes the instruction count, not the result
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float x, float y) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
+    return r;
+}
+__device__ __forceinline__ float lo2(f32x2 v) { return __uint_as_float((unsigned) v); }
+__device__ __forceinline__ float hi2(f32x2 v) { return __uint_as_float((unsigned) (v >> 32)); }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+template <int N>
+__device__ __forceinline__ f32x2 tree_sum_2(const f32x2* v) {
+    if constexpr(N == 1) return v[0];
+    else return add2(tree_sum_2<N / 2>(v), tree_sum_2<N - N / 2>(v + N / 2));
+}
+
+// STAT: 0 = Mean, 1 = Sum
+template <int STAT, int HW>
+__global__ void __launch_bounds__(NT, MINB_SUM) nbh_sumf_tma_kernel(const __grid_constant__ CUtensorMap in_map, const TmaArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int W = 2 * HW + 1, P = (2 * HW + RB - 1) / RB, NS = P + 1 + PREFETCH, NR = NS * RB, NH = 2 * HW + RB, NV = W + SEG - 1;
+    constexpr int HR = RB / 2, NP = NH - HR;            // output rows b and b + 4 share a packed tree: pairs (h[i], h[i + 4]), i < NP
+    float* ring = reinterpret_cast<float*>(smem);                                 // [NS * RB][NT]
+    float* fline = ring + (size_t) NR * NT;                                      // [2][RB][NT] column sums (swizzled 16-byte slots)
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(fline + 2 * RB * NT);   // [NS]
+    unsigned char* cline = reinterpret_cast<unsigned char*>(bars + NS);           // [2][RB][NT] column valid counts (<= W)
+
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * a.TX;
+    const int y_begin = a.row0 + blockIdx.y * a.rows_per_cta;
+    const int y_end = min(y_begin + a.rows_per_cta, a.row0 + a.n_rows_out);
+    const int n_batches = (y_end - y_begin + RB - 1) / RB;
+    const StageRing R = {ring, bars, &in_map, x0 - a.HL, y_begin + HW - RB * P, NS, P + n_batches};
+    R.start();
+    const int scol = min(tid + (a.HL - HW), NT - 1);      // see nbh_sum_tma_kernel
+    const int x_stage = x0 - a.HL + scol;
+    const bool col_ok = x_stage >= 0 && x_stage < a.nx;
+    const float* const ring_col = ring + scol;
+    const int my_slot = idx_f<true>(tid);
+    constexpr int rel0 = RB * P - 2 * HW;                 // ring row of input row y_begin - hw
+    // ---- prime the register window with rows y_begin - hw .. y_begin + hw - 1: h[0 .. 2 HW), kept as the pairs
+    // hp[i] = (h[i], h[i + 4]); the rows that still wait for their partner are carry[b] = h[2 HW - 4 + b]
+    f32x2 hp[NP];
+    float carry[HR];
+    for(int k = 0; k < P; k++) R.wait(k);
+    {
+        float h0[2 * HW];
+        #pragma unroll
+        for(int j = 0; j < 2 * HW; j++) h0[j] = ring_col[(rel0 + j) * NT];
+        #pragma unroll
+        for(int i = 0; i < NP - RB; i++) hp[i] = pack2(h0[i], h0[i + HR]);
+        #pragma unroll
+        for(int b = 0; b < HR; b++) carry[b] = h0[2 * HW - HR + b];
+    }
+    __syncthreads();
+    for(int k = 0; k < P; k++) R.recycle(k);
+    const int hb = tid >> 5, seg = tid & 31, xo0 = seg * SEG;
+    const bool h_active = xo0 < a.TX && x0 + xo0 < a.nx;
+    const bool strip_inside = x0 - HW >= 0 && x0 + a.TX - 1 + HW < a.nx;   // no window of the strip is clipped sideways
+    const float rc_full = __frcp_rn((float) (W * W));
+    int slot[(NV + 3) / 4];                                // this thread's 16-byte slots of a line row
+    #pragma unroll
+    for(int q = 0; q < (NV + 3) / 4; q++) slot[q] = swz_slot(2 * seg + q);
+    // Software pipeline: between two barriers a thread forms the column sums of batch i + 1 (vertical pass) AND the outputs of
+    // batch i (horizontal pass, from the other line buffer). The two are independent instruction streams, so the latency
+    // of one hides behind the other, and a batch still costs one barrier.
+    auto vertical = [&](int batch, float* fl, float& chk) {
+        const int k_new = P + batch;
+        R.wait(k_new);
+        float nv[RB];
+        {
+            const float* newp = ring_col + (k_new % NS) * (RB * NT);
+            #pragma unroll
+            for(int b = 0; b < RB; b++) nv[b] = newp[b * NT];
+        }
+        #pragma unroll
+        for(int b = 0; b < HR; b++) {
+            hp[NP - RB + b] = pack2(carry[b], nv[b]);      // (h[2 HW - 4 + b], h[2 HW + b])
+            hp[NP - HR + b] = pack2(nv[b], nv[HR + b]);    // (h[2 HW + b], h[2 HW + 4 + b])
+            carry[b] = nv[HR + b];
+        }
+        // a fresh tree per output row, rows b and b + 4 in one packed tree
+        f32x2 cs[HR];
+        #pragma unroll
+        for(int b = 0; b < HR; b++) cs[b] = tree_sum_2<W>(hp + b);
+        const f32x2 chk2 = tree_sum_2<HR>(cs);
+        #pragma unroll
+        for(int b = 0; b < HR; b++) {
+            fl[b * NT + my_slot] = lo2(cs[b]);
+            fl[(b + HR) * NT + my_slot] = hi2(cs[b]);
+        }
+        chk = __fadd_rn(lo2(chk2), hi2(chk2));
+    };
+    // the masked sums and valid counts of the batch whose rows are in hp (before the shift), for a CTA that saw a missing value
+    auto vertical_masked = [&](int batch, float* fl, unsigned char* cl) {
+        const int y0 = y_begin + RB * batch;
+        float mh[NH];
+        unsigned mask = 0;
+        #pragma unroll
+        for(int j = 0; j < NH; j++) {
+            const float hj = j < NP ? lo2(hp[j]) : hi2(hp[j - HR]);
+            const bool ok = finite_f(hj);
+            mh[j] = ok ? hj : 0.f;
+            mask |= (ok ? 1u : 0u) << j;
+        }
+        #pragma unroll
+        for(int b = 0; b < RB; b++) {
+            const int y = y0 + b;
+            const int outside = W - (min(y + HW, a.n_rows_in - 1) - max(y - HW, 0) + 1);   // rows of the window the copy engine zero-filled
+            fl[b * NT + my_slot] = tree_sum_f<W>(mh + b);
+            cl[b * NT + tid] = (unsigned char) (col_ok ? max(__popc((mask >> b) & ((1u << W) - 1u)) - outside, 0) : 0);
+        }
+    };
+    auto shift = [&]() {
+        #pragma unroll
+        for(int j = 0; j < NP - RB; j++) hp[j] = hp[j + RB];
+    };
+    auto horizontal = [&](int batch, const float* fl, const unsigned char* cl, bool any_missing) {
+        const int y = y_begin + RB * batch + hb;
+        if(!(h_active && y < y_end)) return;
+        const int x = x0 + xo0;
+        const float4* l4 = reinterpret_cast<const float4*>(fl + hb * NT);     // window column e in slot swz_slot(e / 4)
+        float v[(NV + 3) / 4 * 4];
+        #pragma unroll
+        for(int q = 0; q < (NV + 3) / 4; q++) {
+            const float4 t = l4[slot[q]];
+            v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+        }
+        float sw[SEG];
+        if constexpr(W >= SEG) {
+            // window p = v[p .. p + W - 1] = suffix(v[p .. 6]) + core(v[7 .. W - 1]) + prefix(v[W .. W + p - 1])
+            float suf[SEG], pre[SEG];
+            suf[SEG - 1] = 0.f;
+            #pragma unroll
+            for(int p = SEG - 2; p >= 0; p--) suf[p] = p == SEG - 2 ? v[p] : __fadd_rn(v[p], suf[p + 1]);
+            const float core = tree_sum_f<W - SEG + 1>(v + SEG - 1);
+            pre[0] = 0.f;
+            #pragma unroll
+            for(int p = 1; p < SEG; p++) pre[p] = p == 1 ? v[W] : __fadd_rn(pre[p - 1], v[W + p - 1]);
+            sw[0] = __fadd_rn(suf[0], core);
+            sw[SEG - 1] = __fadd_rn(core, pre[SEG - 1]);
+            #pragma unroll
+            for(int p = 1; p < SEG - 1; p++) sw[p] = __fadd_rn(__fadd_rn(suf[p], core), pre[p]);
+        }
+        else {
+            #pragma unroll
+            for(int p = 0; p < SEG; p++) sw[p] = tree_sum_f<W>(v + p);
+        }
+        float o[SEG];
+        const int ch = min(y + HW, a.n_rows_in - 1) - max(y - HW, 0) + 1;   // rows of the window inside the field
+        if(!any_missing) {
+            if(STAT == 1) {
+                #pragma unroll
+                for(int p = 0; p < SEG; p++) o[p] = sw[p];
+            }
+            else if(strip_inside && ch == W) {
+                #pragma unroll
+                for(int p = 0; p < SEG; p++) o[p] = quot_f(sw[p], (float) (W * W), rc_full);
+            }
+            else {
+                // count = (rows inside the field) x (columns inside the field), neighbourhood.cpp:104-107
+                #pragma unroll
+                for(int p = 0; p < SEG; p++) {
+                    const float fc = (float) (ch * (min(x + p + HW, a.nx - 1) - max(x + p - HW, 0) + 1));
+                    o[p] = quot_f(sw[p], fc, __frcp_rn(fc));
+                }
+            }
+        }
+        else {
+            const unsigned char* lc = cl + hb * NT + xo0;
+            int cv[NV];
+            #pragma unroll
+            for(int j = 0; j < NV; j++) cv[j] = xo0 + j < NT ? lc[j] : 0;
+            int c = 0;
+            #pragma unroll
+            for(int j = 0; j < W; j++) c += cv[j];
+            #pragma unroll
+            for(int p = 0; p < SEG; p++) {
+                const float fc = (float) c;
+                if(STAT == 1) o[p] = c > 0 ? sw[p] : NAN;
+                else o[p] = c > 0 ? quot_f(sw[p], fc, __frcp_rn(fc)) : NAN;
+                if(p + 1 < SEG) c += cv[W + p] - cv[p];
+            }
+        }
+        store_segment(a, y, x, o);
+    };
+
+    // ---- prologue: the column sums of batch 0
+    float chk;
+    vertical(0, fline, chk);
+    bool missing_cur = __syncthreads_or(!finite_f(chk)) != 0;   // also publishes the line
+    R.recycle(P);
+    if(missing_cur) {
+        vertical_masked(0, fline, cline);
+        __syncthreads();
+    }
+    shift();
+    for(int i = 0; i < n_batches; i++) {
+        const int cur = i & 1, nxt = cur ^ 1;
+        const bool more = i + 1 < n_batches;
+        float chk_next = 0.f;
+        if(more) vertical(i + 1, fline + nxt * (RB * NT), chk_next);
+        horizontal(i, fline + cur * (RB * NT), cline + cur * (RB * NT), missing_cur);
+        if(!more) break;
+        // publishes line `nxt`; every read of line `cur` (this batch) is done before the batch after next overwrites it
+        const bool missing_next = __syncthreads_or(!finite_f(chk_next)) != 0;
+        R.recycle(P + i + 1);                                    // every thread has read the entering stage
+        if(missing_next) {
+            vertical_masked(i + 1, fline + nxt * (RB * NT), cline + nxt * (RB * NT));
+            __syncthreads();
+        }
+        shift();
+        missing_cur = missing_next;
+    }
+}
+
 template <class K>
 int run_kernel(K kernel, dim3 grid, size_t smem, cudaStream_t stream, const CUtensorMap& map, const TmaArgs& a) {
     GPP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
@@ -531,6 +780,17 @@ int run_sum(int hw, dim3 grid, size_t smem, cudaStream_t stream, const CUtensorM
         GPP_FOR_STATIC_HW(X)
 #undef X
         default: return run_kernel(nbh_sum_tma_kernel<STAT, 0>, grid, smem, stream, map, a);
+    }
+}
+// the float kernels: Mean / Sum with an unrolled half-width up to 7
+template <int STAT>
+int run_sumf(int hw, dim3 grid, size_t smem, cudaStream_t stream, const CUtensorMap& map, const TmaArgs& a) {
+    switch(hw) {
+        case 1: return run_kernel(nbh_sumf_tma_kernel<STAT, 1>, grid, smem, stream, map, a);
+        case 2: return run_kernel(nbh_sumf_tma_kernel<STAT, 2>, grid, smem, stream, map, a);
+        case 3: return run_kernel(nbh_sumf_tma_kernel<STAT, 3>, grid, smem, stream, map, a);
+        case 5: return run_kernel(nbh_sumf_tma_kernel<STAT, 5>, grid, smem, stream, map, a);
+        default: return run_kernel(nbh_sumf_tma_kernel<STAT, 7>, grid, smem, stream, map, a);
     }
 }
 template <bool IS_MAX>
@@ -566,8 +826,11 @@ int nbh_tma_try(const float* d_input, int n_rows_in, int nx, int row0, int n_row
     const int w = 2 * hw + 1;
     a.n_rcp = std::min(RCP_MAX, w * w + 1);
     const bool minmax = statistic == GPP_MIN || statistic == GPP_MAX;
+    static const bool no_float = getenv("GPP_NBH_F64") != nullptr;    // A/B switch: the fp64 kernels for every half-width
+    const bool sumf = !no_float && (statistic == GPP_MEAN || statistic == GPP_SUM) && (hw == 1 || hw == 2 || hw == 3 || hw == 5 || hw == 7);
     size_t smem = (size_t) a.NS * STAGE_BYTES + sizeof(unsigned long long) * a.NS;
     if(minmax) smem += sizeof(float) * RB * LROW_F;
+    else if(sumf) smem += (sizeof(float) + 1) * 2 * RB * NT;
     else smem += (sizeof(double) + 1) * RB * LROW_D + sizeof(double) * a.n_rcp;
     if(smem > 100 * 1024) return GPP_OK;
     // one wave: strips x chunks <= resident CTAs
@@ -576,7 +839,9 @@ int nbh_tma_try(const float* d_input, int n_rows_in, int nx, int row0, int n_row
     const int slots = sm_count() * per_sm;
     int chunks = std::max(1, slots / strips);
     int rows = (n_rows_out + chunks - 1) / chunks;
-    rows = std::max(4 * RB, (rows + RB - 1) / RB * RB);
+    // the float kernels take any chunk height (the last batch of a CTA may be partial), so the CTAs can fill the resident
+    // slots evenly; the others want whole batches
+    rows = sumf ? std::max(4 * RB, rows) : std::max(4 * RB, (rows + RB - 1) / RB * RB);
     a.rows_per_cta = rows;
     chunks = (n_rows_out + rows - 1) / rows;
     CUtensorMap map;
@@ -584,8 +849,8 @@ int nbh_tma_try(const float* d_input, int n_rows_in, int nx, int row0, int n_row
     GPP_TRY(make_field_tensor_map(&map, d_input, n_rows_in, nx, RB, NT, minmax));
     dim3 grid(strips, chunks);
     switch(statistic) {
-        case GPP_MEAN: GPP_TRY(run_sum<0>(hw, grid, smem, stream, map, a)); break;
-        case GPP_SUM: GPP_TRY(run_sum<1>(hw, grid, smem, stream, map, a)); break;
+        case GPP_MEAN: GPP_TRY(sumf ? run_sumf<0>(hw, grid, smem, stream, map, a) : run_sum<0>(hw, grid, smem, stream, map, a)); break;
+        case GPP_SUM: GPP_TRY(sumf ? run_sumf<1>(hw, grid, smem, stream, map, a) : run_sum<1>(hw, grid, smem, stream, map, a)); break;
         case GPP_COUNT: GPP_TRY(run_sum<2>(hw, grid, smem, stream, map, a)); break;
         case GPP_MIN: GPP_TRY(run_minmax<false>(hw, grid, smem, stream, map, a)); break;
         case GPP_MAX: GPP_TRY(run_minmax<true>(hw, grid, smem, stream, map, a)); break;

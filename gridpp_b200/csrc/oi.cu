@@ -134,6 +134,7 @@ struct FastSmem {
 //   of (P+R)^-1 d), dmax / dmin (extreme innovations of the set), dirty (non-zero extent of S.M).
 struct WarpState {
     int prev_orig, prev_k, dirty;
+    int inv_off;                    // analysis variance: row j of (P+R)^-1 of the solved set is S.M[33 j + inv_off .. + k)
     unsigned clock;
     double z, dmax, dmin, avar;
 };
@@ -210,7 +211,16 @@ __device__ __forceinline__ unsigned long long warp_min64(unsigned long long x) {
 // Assemble P + R for the k observations staged in canonical order in S.c_pos / S.c_rho and solve for
 // z = (P+R)^-1 d by Gauss-Jordan in registers (lane j = row j of the symmetric augmented matrix
 // [[P+R, rho, d], [rho', 0, 0], [d', 0, 0]]); also leaves rho'(P+R)^-1 rho in W.avar. oi.cpp:298-317,336.
-template <int SMODE>
+// INV (the analysis variance is wanted): the same elimination also leaves (P+R)^-1 behind. The column of the identity
+// that a Gauss-Jordan step would touch in [A | I] takes the place of the eliminated pivot column (it enters the register
+// window at the far end as the window shifts), the pivot row is normalised by the same FMA pass (its factor is
+// 1 - 1/pivot), and because the partly swept matrix stays symmetric up to sign -- the (swept, unswept) block of
+// [[A11^-1, A11^-1 A12], [-A21 A11^-1, S]] is minus the transpose of the (unswept, swept) one -- the pivot ROW is still
+// the broadcast pivot COLUMN, negated for the swept part: the line buffer carries my(lane) at [lane] and -my(lane) at
+// [30 + lane]. After k steps the window holds row `lane` of the inverse in its last k slots. With it the variance
+// factor rho' (P+R)^-1 rho of every further point that selects the same set is a k x k matrix-vector product
+// (variance_factor) instead of a new elimination.
+template <int SMODE, bool INV>
 __device__ __noinline__ void solve_selected(const OiParams& P, FastSmem& S, const unsigned short* lut, int k, WarpState& W) {
     const int lane = (int) lane_id();
     // ---- stage the selected observations
@@ -271,9 +281,20 @@ __device__ __noinline__ void solve_selected(const OiParams& P, FastSmem& S, cons
         const double inv = fast_rcp(shfl_double(my, c));
         // the pivot column is published twice, the second copy shifted by one entry, so that the entries of columns
         // c+1 .. c+29 can always be read as aligned 16-byte pairs
-        S.colbuf[0][lane] = my;
-        if(lane > 0) S.colbuf[1][lane - 1] = my;
-        const double f = lane == c ? 0.0 : my * inv;
+        if(INV) {
+            if(lane < FAST_K) {
+                S.colbuf[0][lane] = my;
+                S.colbuf[0][FAST_K + lane] = -my;
+                if(lane > 0) S.colbuf[1][lane - 1] = my;
+                S.colbuf[1][FAST_K - 1 + lane] = -my;
+            }
+            else S.colbuf[0][32 + lane] = my;    // rows rho and d of the augmented matrix: entries 62, 63
+        }
+        else {
+            S.colbuf[0][lane] = my;
+            if(lane > 0) S.colbuf[1][lane - 1] = my;
+        }
+        const double f = lane == c ? (INV ? 1.0 - inv : 0.0) : my * inv;
         if(lane == c) my_inv = inv;
         __syncwarp();
         const int base = c + 1;       // pivot-row entry of column base + t (columns past 29 feed slots that are never read)
@@ -284,14 +305,39 @@ __device__ __noinline__ void solve_selected(const OiParams& P, FastSmem& S, cons
             a[2 * q] = fma(-f, t.x, a[2 * q + 1]);
             if(2 * q + 2 < FAST_K) a[2 * q + 1] = fma(-f, t.y, a[2 * q + 2]);
         }
-        rr = fma(-f, S.colbuf[0][30], rr);
-        rd = fma(-f, S.colbuf[0][31], rd);
+        if(INV) a[FAST_K - 1] = (lane == c ? 1.0 : 0.0) - f;     // column c of the identity after this step
+        rr = fma(-f, S.colbuf[0][INV ? 62 : 30], rr);
+        rd = fma(-f, S.colbuf[0][INV ? 63 : 31], rd);
         __syncwarp();                 // the next step overwrites the buffers
     }
-    W.z = lane < k ? rd * my_inv : 0.0;       // z = (P+R)^-1 d, one component per lane
+    W.z = lane < k ? (INV ? rd : rd * my_inv) : 0.0;   // z = (P+R)^-1 d, one component per lane (INV: the pivot rows are normalised)
     W.avar = -shfl_double(rr, 30);            // rho'(P+R)^-1 rho (oi.cpp:336)
     W.prev_orig = lane < k ? S.c_orig[lane] : -1;
     W.prev_k = k;
+    if(INV) {
+        // row `lane` of the inverse: window slots FAST_K - k .. FAST_K - 1 (static register indices; the offset is applied on
+        // the shared-memory side). S.M is scratch until the next assembly, which re-zeroes what it needs (dirty = 32).
+        #pragma unroll
+        for(int q = 0; q < FAST_K; q++) S.M[lane * 33 + q] = a[q];
+        W.inv_off = FAST_K - k;
+        W.dirty = 32;
+        __syncwarp();
+    }
+}
+
+// rho' (P+R)^-1 rho (oi.cpp:336) for the point whose correlations are in S.c_rho (canonical order) from the inverse the
+// last elimination left in S.M: lane j forms row j of the product, the warp adds up rho_j times it
+__device__ __forceinline__ double variance_factor(const FastSmem& S, int k, const WarpState& W) {
+    const int lane = (int) lane_id();
+    double u = 0.0;
+    if(lane < k) {
+        const double* row = S.M + lane * 33 + W.inv_off;
+        for(int i = 0; i < k; i++) u = fma(row[i], (double) S.c_rho[i], u);
+        u *= (double) S.c_rho[lane];
+    }
+    #pragma unroll
+    for(int off = 16; off > 0; off >>= 1) u += shfl_double(u, lane ^ off);
+    return u;
 }
 
 // increment = rho . z (oi.cpp:315-317) with rho in canonical order in S.c_rho; lane 0 writes the result
@@ -342,12 +388,15 @@ __device__ __noinline__ void analyse_point(const OiParams& P, FastSmem& S, const
     }
     const int c_orig = lane < k ? S.c_orig[lane] : -1;
     const bool same = __all_sync(FULL, c_orig == W.prev_orig) && k == W.prev_k;
-    if(need_var) solve_selected<SMODE>(P, S, lut, k, W);
+    if(need_var) {
+        if(!same) solve_selected<SMODE, true>(P, S, lut, k, W);
+        else W.avar = variance_factor(S, k, W);
+    }
     else if(!same) {
         const unsigned now = ++W.clock;
         unsigned sig;
         if(!lru_lookup(cache, S, k, now, W, sig)) {
-            solve_selected<SMODE>(P, S, lut, k, W);
+            solve_selected<SMODE, false>(P, S, lut, k, W);
             lru_store(cache, k, now, W, sig);
         }
     }
@@ -409,7 +458,8 @@ __device__ __forceinline__ void slot_keys(const OiParams& P, const Pt& p1, const
 // product rho . z (oi.cpp:315-316: lG * inv(lP+lR) * (lObs - lY)). The warp keeps (set, z) of the last system it
 // solved. Every point computes its increment with the same dot product in the same order, so results do not depend
 // on where a run starts or on which path found the set. The analysis variance needs rho'(P+R)^-1 rho, which depends
-// on the point: when it is requested every point is eliminated.
+// on the point: when it is requested the elimination also leaves (P+R)^-1 behind (solve_selected<.., true>) and every
+// further point with the same set evaluates the quadratic form with it.
 //
 // Run path: the observations that can be within R of ANY point of the run (distance to the run's centre
 // <= R + extent) are gathered ONCE, sorted by original index, and kept lane-resident (2 slots per lane). Per point
@@ -442,7 +492,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 2) oi_fast_kernel(const __
     for(int e = lane; e < 32 * 33; e += 32) S.M[e] = 0.0;
     __syncthreads();
     WarpState W;
-    W.prev_orig = -2; W.prev_k = -1; W.dirty = 0; W.clock = 0;
+    W.prev_orig = -2; W.prev_k = -1; W.dirty = 0; W.clock = 0; W.inv_off = 0;
     W.z = 0.0; W.dmax = 0.0; W.dmin = 0.0; W.avar = 0.0;
 
     OiWorkHeader* hdr = reinterpret_cast<OiWorkHeader*>(P.workspace);
@@ -663,23 +713,27 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 2) oi_fast_kernel(const __
                 if(s1) S.c_rho[row1] = cand_key_rho(key1);
                 const bool same = sel0 == T0 && sel1 == T1;
                 OI_COUNT(0);
-                if(!same || need_var) {
+                if(!same) {
                     OI_COUNT(1);
                     if(s0) { S.c_pos[row0] = S.cand_pos[lane]; S.c_orig[row0] = orig0; }
                     if(s1) { S.c_pos[row1] = S.cand_pos[lane + 32]; S.c_orig[row1] = orig1; }
                     __syncwarp();
-                    if(need_var) solve_selected<SMODE>(P, S, lut, k, W);
+                    if(need_var) solve_selected<SMODE, true>(P, S, lut, k, W);   // (the cache holds no inverses)
                     else {
                         const unsigned now = ++W.clock;
                         unsigned sig;
                         if(!lru_lookup(cache, S, k, now, W, sig)) {
                             OI_COUNT(2);
-                            solve_selected<SMODE>(P, S, lut, k, W);
+                            solve_selected<SMODE, false>(P, S, lut, k, W);
                             lru_store(cache, k, now, W, sig);
                         }
                     }
                     T0 = sel0;
                     T1 = sel1;
+                }
+                else if(need_var) {
+                    __syncwarp();                                             // c_rho of this point
+                    W.avar = variance_factor(S, k, W);
                 }
                 __syncwarp();
                 finish_point(P, S, g, bg, k, W);

@@ -21,6 +21,11 @@ SUITE = os.path.join(HERE, "reference_suite")
 
 # test id (file::Class.method) -> why the product deviates from the reference there
 KNOWN_DEVIATIONS = {
+    "ref_test_nearest.py::Test.test_grid_to_point":
+        "calls gridpp.bilinear, which SURVEY.md 2b lists as out of scope (downscaling)",
+    "ref_test_kdtree.py::KDTreeTest.test_flat":
+        "assertEqual(float32 array, np.float64 scalar): passes under NumPy 1.x value-based casting, fails under NumPy 2 (NEP 50) "
+        "for the reference's own SWIG module as well; the value is the correctly rounded float32 (141.42136)",
 }
 
 
