@@ -914,6 +914,115 @@ def get_neighbourhood_thresholds(input, num_thresholds):
 
 
 # ---------------------------------------------------------------------------------------------------------
+# consumers of the point index: gridding / gridding_nearest / count / distance / fill / fill_missing / doping
+def _out_shape(obj):
+    return tuple(obj._stored_shape) if _is_grid(obj) else (obj.size(),)
+
+
+def gridding(grid, points, values, radius, min_num, statistic):
+    """gridpp::gridding(Grid | Points, Points, values, radius, min_num, statistic), gridding.cpp:6-61."""
+    vals = _farray(values, 1, "values")
+    _check_size(points.size() == vals.size, "Points size is not the same as values")
+    if not is_valid(radius) or radius < 0:
+        raise ValueError("radius must be >= 0")
+    if min_num < 0:
+        raise ValueError("min_num must be >= 0")
+    out = _np.empty(grid._set.n, _np.float32)
+    _check(_libc.gpp_gridding_host(grid._set._handle, points._set._handle, _fptr(vals), float(radius), int(min_num), int(statistic), _fptr(out)))
+    return out.reshape(_out_shape(grid))
+
+
+def gridding_nearest(grid, points, values, min_num, statistic):
+    """gridpp::gridding_nearest(Grid | Points, Points, values, min_num, statistic), gridding.cpp:63-131."""
+    vals = _farray(values, 1, "values")
+    _check_size(points.size() == vals.size, "Points size is not the same as values")
+    if min_num < 0:
+        raise ValueError("min_num must be >= 0")
+    out = _np.empty(grid._set.n, _np.float32)
+    _check(_libc.gpp_gridding_nearest_host(grid._set._handle, points._set._handle, _fptr(vals), int(min_num), int(statistic), _fptr(out)))
+    return out.reshape(_out_shape(grid))
+
+
+def count(iobj, oobj, radius):
+    """gridpp::count (count.cpp:6-66): the number of points / nodes of `iobj` within `radius` of every location of `oobj`."""
+    out = _np.empty(oobj._set.n, _np.float32)
+    _check(_libc.gpp_count_host(iobj._set._handle, oobj._set._handle, float(radius), _fptr(out)))
+    return out.reshape(_out_shape(oobj))
+
+
+def distance(iobj, oobj, num=1):
+    """gridpp::distance (distance.cpp:6-120): the distance from every location of `oobj` to its num-th closest point of `iobj`."""
+    if iobj.get_coordinate_type() != oobj.get_coordinate_type():
+        raise ValueError("Incompatible coordinate types")
+    # distance.cpp:21 (Grid, Points) and :111 (Points, Points) pass the output location first; :52, :83 the input point
+    query_first = not _is_grid(oobj)
+    out = _np.empty(oobj._set.n, _np.float32)
+    _check(_libc.gpp_distance_host(iobj._set._handle, oobj._set._handle, int(num), int(query_first), _fptr(out)))
+    return out.reshape(_out_shape(oobj))
+
+
+def fill(igrid, input, points, radii, value, outside):
+    """gridpp::fill, fill.cpp:6-43."""
+    field = _farray(input, 2, "input")
+    _check_size(field.shape == tuple(igrid._stored_shape), "Grid size is not the same as values")
+    rad = _farray(radii, 1, "radii")
+    _check_size(points.size() == rad.size, "Points size is not the same as radii size")
+    if (rad < 0).any():
+        raise ValueError("All radius sizes must be 0 or greater")
+    out = _np.empty(field.shape, _np.float32)
+    _check(_libc.gpp_fill_host(igrid._set._handle, _fptr(field), points._set._handle, _fptr(rad), float(value), int(bool(outside)), _fptr(out)))
+    return out
+
+
+def fill_missing(values):
+    """gridpp::fill_missing, fill.cpp:44-134."""
+    field = _farray(values, 2, "values")
+    out = _np.empty(field.shape, _np.float32)
+    if field.size:
+        _check(_libc.gpp_fill_missing_host(_fptr(field), field.shape[0], field.shape[1], _fptr(out)))
+    return out
+
+
+def _doping_checks(igrid, background, points, observations, extent, what):
+    field = _farray(background, 2, "background")
+    _check_size(field.shape == tuple(igrid._stored_shape), "Grid size is not the same as observations")
+    obs = _farray(observations, 1, "observations")
+    _check_size(points.size() == obs.size, "Points size is not the same as observations size")
+    _check_size(points.size() == len(extent), "Points size is not the same as %s size" % what)
+    return field, obs
+
+
+def doping_square(igrid, background, points, observations, halfwidths, max_elev_diff=MV):
+    """gridpp::doping_square, doping.cpp:5-51."""
+    hw = _np.ascontiguousarray(_np.asarray(halfwidths, dtype=_np.int32).ravel())
+    field, obs = _doping_checks(igrid, background, points, observations, hw, "halfwidth")
+    if is_valid(max_elev_diff) and max_elev_diff < 0:
+        raise ValueError("max_elev_diff must be greater than or equal to 0")
+    if (hw < 0).any():
+        raise ValueError("All halfwidth must be greater than or equal to 0")
+    out = _np.empty(field.shape, _np.float32)
+    if field.size:
+        _check(_libc.gpp_doping_square_host(igrid._set._handle, _fptr(field), points._set._handle, _fptr(obs), hw.ctypes.data_as(_lib.ip),
+                                            float(max_elev_diff), _fptr(out)))
+    return out
+
+
+def doping_circle(igrid, background, points, observations, radii, max_elev_diff=MV):
+    """gridpp::doping_circle, doping.cpp:52-93."""
+    rad = _farray(radii, 1, "radii")
+    field, obs = _doping_checks(igrid, background, points, observations, rad, "radii")
+    if is_valid(max_elev_diff) and max_elev_diff < 0:
+        raise ValueError("max_elev_diff must be greater than or equal to 0")
+    if (rad < 0).any():
+        raise ValueError("radii must be greater than or equal to 0")
+    out = _np.empty(field.shape, _np.float32)
+    if field.size:
+        _check(_libc.gpp_doping_circle_host(igrid._set._handle, _fptr(field), points._set._handle, _fptr(obs), _fptr(rad), float(max_elev_diff),
+                                            _fptr(out)))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------
 _STATISTIC_NAMES = {"mean": Mean, "min": Min, "max": Max, "median": Median, "quantile": Quantile, "std": Std, "sum": Sum,
                     "count": Count, "randomchoice": RandomChoice}
 

@@ -88,6 +88,14 @@ _proto("gpp_neighbourhood_ens_device", C.c_int, vp, C.c_int, C.c_int, C.c_int, C
 _proto("gpp_neighbourhood_quantile_fast_ens_host", C.c_int, fp, C.c_int, C.c_int, C.c_int, C.c_float, fp, C.c_int, fp, C.c_int, fp)
 _proto("gpp_neighbourhood_quantile_fast_ens_device", C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_float, vp, C.c_int, fp, C.c_int, vp, vp)
 
+_proto("gpp_gridding_host", C.c_int, vp, vp, fp, C.c_float, C.c_int, C.c_int, fp)
+_proto("gpp_gridding_nearest_host", C.c_int, vp, vp, fp, C.c_int, C.c_int, fp)
+_proto("gpp_count_host", C.c_int, vp, vp, C.c_float, fp)
+_proto("gpp_distance_host", C.c_int, vp, vp, C.c_int, C.c_int, fp)
+_proto("gpp_fill_host", C.c_int, vp, fp, vp, fp, C.c_float, C.c_int, fp)
+_proto("gpp_fill_missing_host", C.c_int, fp, C.c_int, C.c_int, fp)
+_proto("gpp_doping_square_host", C.c_int, vp, fp, vp, fp, ip, C.c_float, fp)
+_proto("gpp_doping_circle_host", C.c_int, vp, fp, vp, fp, fp, C.c_float, fp)
 _proto("gpp_calc_statistic_host", C.c_int, fp, C.c_longlong, C.c_int, C.c_int, fp)
 _proto("gpp_calc_statistic_device", C.c_int, vp, C.c_longlong, C.c_int, C.c_int, vp, vp)
 _proto("gpp_neighbourhood_brute_force_host", C.c_int, fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, fp)
@@ -113,6 +121,8 @@ EXPORTS = [
     "gpp_neighbourhood_host", "gpp_neighbourhood_device", "gpp_neighbourhood_quantile_fast_host",
     "gpp_neighbourhood_quantile_fast_device", "gpp_neighbourhood_ens_host", "gpp_neighbourhood_ens_device",
     "gpp_neighbourhood_quantile_fast_ens_host", "gpp_neighbourhood_quantile_fast_ens_device",
+    "gpp_gridding_host", "gpp_gridding_nearest_host", "gpp_count_host", "gpp_distance_host", "gpp_fill_host", "gpp_fill_missing_host",
+    "gpp_doping_square_host", "gpp_doping_circle_host",
     "gpp_calc_statistic_host", "gpp_calc_statistic_device", "gpp_calc_quantile_host", "gpp_interpolate_host",
     "gpp_neighbourhood_brute_force_host", "gpp_neighbourhood_brute_force_device",
     "gpp_get_neighbourhood_thresholds_host", "gpp_structure_field_create", "gpp_structure_field_destroy",

@@ -610,9 +610,6 @@ __global__ void __launch_bounds__(NT, MINB_SUM) nbh_sumf_tma_kernel(const __grid
     int slot[(NV + 3) / 4];                                // this thread's 16-byte slots of a line row
     #pragma unroll
     for(int q = 0; q < (NV + 3) / 4; q++) slot[q] = swz_slot(2 * seg + q);
-    // Software pipeline: between two barriers a thread forms the column sums of batch i + 1 (vertical pass) AND the outputs of
-    // batch i (horizontal pass, from the other line buffer). The two are independent instruction streams, so the latency
-    // of one hides behind the other, and a batch still costs one barrier.
     auto vertical = [&](int batch, float* fl, float& chk) {
         const int k_new = P + batch;
         R.wait(k_new);
@@ -734,32 +731,22 @@ __global__ void __launch_bounds__(NT, MINB_SUM) nbh_sumf_tma_kernel(const __grid
         store_segment(a, y, x, o);
     };
 
-    // ---- prologue: the column sums of batch 0
-    float chk;
-    vertical(0, fline, chk);
-    bool missing_cur = __syncthreads_or(!finite_f(chk)) != 0;   // also publishes the line
-    R.recycle(P);
-    if(missing_cur) {
-        vertical_masked(0, fline, cline);
-        __syncthreads();
-    }
-    shift();
+    // One barrier per batch: the line is double-buffered, so the next batch's vertical pass may overwrite the other buffer
+    // while slower warps still read this one. (Measured: forming the column sums of batch i + 1 BEFORE the outputs of batch i,
+    // so that the two independent streams overlap inside a thread, was slower -- 43.1 against 39.2 us at 4000 x 4000.)
     for(int i = 0; i < n_batches; i++) {
-        const int cur = i & 1, nxt = cur ^ 1;
-        const bool more = i + 1 < n_batches;
-        float chk_next = 0.f;
-        if(more) vertical(i + 1, fline + nxt * (RB * NT), chk_next);
-        horizontal(i, fline + cur * (RB * NT), cline + cur * (RB * NT), missing_cur);
-        if(!more) break;
-        // publishes line `nxt`; every read of line `cur` (this batch) is done before the batch after next overwrites it
-        const bool missing_next = __syncthreads_or(!finite_f(chk_next)) != 0;
-        R.recycle(P + i + 1);                                    // every thread has read the entering stage
-        if(missing_next) {
-            vertical_masked(i + 1, fline + nxt * (RB * NT), cline + nxt * (RB * NT));
+        float* const fl = fline + (i & 1) * (RB * NT);
+        unsigned char* const cl = cline + (i & 1) * (RB * NT);
+        float chk;
+        vertical(i, fl, chk);
+        const bool any_missing = __syncthreads_or(!finite_f(chk)) != 0;   // also publishes the line
+        R.recycle(P + i);                                                 // every thread has read the entering stage
+        if(any_missing) {
+            vertical_masked(i, fl, cl);
             __syncthreads();
         }
         shift();
-        missing_cur = missing_next;
+        horizontal(i, fl, cl, any_missing);
     }
 }
 

@@ -768,6 +768,123 @@ inline vec get_neighbourhood_thresholds(const vec2& input, int num_thresholds) {
 inline vec get_neighbourhood_thresholds(const vec3& input, int num_thresholds) { return b200::thresholds_of(b200::flatten(input), num_thresholds); }
 
 // -------------------------------------------------------------------------------------------------------------------
+// Consumers of the point index: gridding.cpp, count.cpp, distance.cpp, fill.cpp, doping.cpp. A Grid is passed as its flattened
+// nodes; results come back in the shape of the output object.
+namespace b200 {
+inline void check_gridding(const Points& points, const vec& values, float radius, int min_num, bool with_radius) {
+    require(points.size() == (int) values.size(), "Points size is not the same as values");
+    if(with_radius) require(is_valid(radius) && radius >= 0, "radius must be >= 0");
+    require(min_num >= 0, "min_num must be >= 0");
+}
+}  // namespace b200
+inline vec2 gridding(const Grid& grid, const Points& points, const vec& values, float radius, int min_num, Statistic statistic) {
+    b200::check_gridding(points, values, radius, min_num, true);
+    vec out((size_t) grid.size()[0] * grid.size()[1]);
+    b200::check(gpp_gridding_host(grid.b200_handle(), points.b200_handle(), values.data(), radius, min_num, (int) statistic, out.data()));
+    return b200::unflatten(out, grid.size()[0], grid.size()[1]);
+}
+inline vec gridding(const Points& opoints, const Points& ipoints, const vec& values, float radius, int min_num, Statistic statistic) {
+    b200::check_gridding(ipoints, values, radius, min_num, true);
+    vec out((size_t) opoints.size());
+    b200::check(gpp_gridding_host(opoints.b200_handle(), ipoints.b200_handle(), values.data(), radius, min_num, (int) statistic, out.data()));
+    return out;
+}
+inline vec2 gridding_nearest(const Grid& grid, const Points& points, const vec& values, int min_num, Statistic statistic) {
+    b200::check_gridding(points, values, 0, min_num, false);
+    vec out((size_t) grid.size()[0] * grid.size()[1]);
+    b200::check(gpp_gridding_nearest_host(grid.b200_handle(), points.b200_handle(), values.data(), min_num, (int) statistic, out.data()));
+    return b200::unflatten(out, grid.size()[0], grid.size()[1]);
+}
+inline vec gridding_nearest(const Points& opoints, const Points& ipoints, const vec& values, int min_num, Statistic statistic) {
+    b200::check_gridding(ipoints, values, 0, min_num, false);
+    vec out((size_t) opoints.size());
+    b200::check(gpp_gridding_nearest_host(opoints.b200_handle(), ipoints.b200_handle(), values.data(), min_num, (int) statistic, out.data()));
+    return out;
+}
+namespace b200 {
+inline vec count_flat(const gpp_points* in, const gpp_points* out_set, size_t n, float radius) {
+    vec out(n);
+    check(gpp_count_host(in, out_set, radius, out.data()));
+    return out;
+}
+inline vec distance_flat(const gpp_points* in, const gpp_points* out_set, size_t n, int num, bool query_first) {
+    vec out(n);
+    check(gpp_distance_host(in, out_set, num, query_first ? 1 : 0, out.data()));
+    return out;
+}
+inline size_t nodes(const Grid& g) { return (size_t) g.size()[0] * g.size()[1]; }
+}  // namespace b200
+inline vec count(const Grid& grid, const Points& points, float radius) { return b200::count_flat(grid.b200_handle(), points.b200_handle(), (size_t) points.size(), radius); }
+inline vec2 count(const Grid& igrid, const Grid& ogrid, float radius) {
+    return b200::unflatten(b200::count_flat(igrid.b200_handle(), ogrid.b200_handle(), b200::nodes(ogrid), radius), ogrid.size()[0], ogrid.size()[1]);
+}
+inline vec2 count(const Points& points, const Grid& grid, float radius) {
+    return b200::unflatten(b200::count_flat(points.b200_handle(), grid.b200_handle(), b200::nodes(grid), radius), grid.size()[0], grid.size()[1]);
+}
+inline vec count(const Points& ipoints, const Points& opoints, float radius) { return b200::count_flat(ipoints.b200_handle(), opoints.b200_handle(), (size_t) opoints.size(), radius); }
+inline vec distance(const Grid& grid, const Points& points, int num = 1) {
+    b200::require(grid.get_coordinate_type() == points.get_coordinate_type(), "Incompatible coordinate types");
+    return b200::distance_flat(grid.b200_handle(), points.b200_handle(), (size_t) points.size(), num, true);
+}
+inline vec2 distance(const Grid& igrid, const Grid& ogrid, int num = 1) {
+    b200::require(igrid.get_coordinate_type() == ogrid.get_coordinate_type(), "Incompatible coordinate types");
+    return b200::unflatten(b200::distance_flat(igrid.b200_handle(), ogrid.b200_handle(), b200::nodes(ogrid), num, false), ogrid.size()[0], ogrid.size()[1]);
+}
+inline vec2 distance(const Points& points, const Grid& grid, int num = 1) {
+    b200::require(points.get_coordinate_type() == grid.get_coordinate_type(), "Incompatible coordinate types");
+    return b200::unflatten(b200::distance_flat(points.b200_handle(), grid.b200_handle(), b200::nodes(grid), num, false), grid.size()[0], grid.size()[1]);
+}
+inline vec distance(const Points& ipoints, const Points& opoints, int num = 1) {
+    b200::require(ipoints.get_coordinate_type() == opoints.get_coordinate_type(), "Incompatible coordinate types");
+    return b200::distance_flat(ipoints.b200_handle(), opoints.b200_handle(), (size_t) opoints.size(), num, true);
+}
+inline vec2 fill(const Grid& igrid, const vec2& input, const Points& points, const vec& radii, float value, bool outside) {
+    int ny, nx;
+    b200::shape_of(input, ny, nx, "input");
+    b200::require(ny == igrid.size()[0] && nx == igrid.size()[1], "Grid size is not the same as values");
+    b200::require(points.size() == (int) radii.size(), "Points size is not the same as radii size");
+    for(float r : radii) b200::require(!(r < 0), "All radius sizes must be 0 or greater");
+    vec out((size_t) ny * nx);
+    b200::check(gpp_fill_host(igrid.b200_handle(), b200::flatten(input).data(), points.b200_handle(), radii.data(), value, outside ? 1 : 0, out.data()));
+    return b200::unflatten(out, ny, nx);
+}
+inline vec2 fill_missing(const vec2& values) {
+    int ny, nx;
+    b200::shape_of(values, ny, nx, "values");
+    vec out((size_t) ny * nx);
+    if(!out.empty()) b200::check(gpp_fill_missing_host(b200::flatten(values).data(), ny, nx, out.data()));
+    return b200::unflatten(out, ny, nx);
+}
+inline vec2 doping_square(const Grid& igrid, const vec2& background, const Points& points, const vec& observations, const ivec& halfwidth,
+                          float max_elev_diff = MV) {
+    int ny, nx;
+    b200::shape_of(background, ny, nx, "background");
+    b200::require(ny == igrid.size()[0] && nx == igrid.size()[1], "Grid size is not the same as observations");
+    b200::require(points.size() == (int) observations.size(), "Points size is not the same as observations size");
+    b200::require(points.size() == (int) halfwidth.size(), "Points size is not the same as halfwidth size");
+    b200::require(!(is_valid(max_elev_diff) && max_elev_diff < 0), "max_elev_diff must be greater than or equal to 0");
+    vec out((size_t) ny * nx);
+    if(!out.empty())
+        b200::check(gpp_doping_square_host(igrid.b200_handle(), b200::flatten(background).data(), points.b200_handle(), observations.data(), halfwidth.data(),
+                                           max_elev_diff, out.data()));
+    return b200::unflatten(out, ny, nx);
+}
+inline vec2 doping_circle(const Grid& igrid, const vec2& background, const Points& points, const vec& observations, const vec& radii,
+                          float max_elev_diff = MV) {
+    int ny, nx;
+    b200::shape_of(background, ny, nx, "background");
+    b200::require(ny == igrid.size()[0] && nx == igrid.size()[1], "Grid size is not the same as observations");
+    b200::require(points.size() == (int) observations.size(), "Points size is not the same as observations size");
+    b200::require(points.size() == (int) radii.size(), "Points size is not the same as radii size");
+    b200::require(!(is_valid(max_elev_diff) && max_elev_diff < 0), "max_elev_diff must be greater than or equal to 0");
+    vec out((size_t) ny * nx);
+    if(!out.empty())
+        b200::check(gpp_doping_circle_host(igrid.b200_handle(), b200::flatten(background).data(), points.b200_handle(), observations.data(), radii.data(),
+                                           max_elev_diff, out.data()));
+    return b200::unflatten(out, ny, nx);
+}
+
+// -------------------------------------------------------------------------------------------------------------------
 // Row statistics (util.cpp:19-215,377-431; gridpp.cpp:11-44): calc_statistic, calc_quantile, interpolate, get_statistic.
 inline Statistic get_statistic(std::string name) {
     static const std::pair<const char*, Statistic> names[] = {{"mean", Mean}, {"min", Min}, {"max", Max}, {"median", Median}, {"quantile", Quantile},

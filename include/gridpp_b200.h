@@ -285,6 +285,39 @@ int gpp_neighbourhood_quantile_fast_ens_device(const float* d_input, int ny, int
 int gpp_get_neighbourhood_thresholds_host(const float* input, long long n_values, int num_thresholds, float* thresholds,
                                           int* num_out);
 
+/* ---------------------------------------------------------------- consumers of the point index -------- */
+/* All take point sets (a Grid is its flattened nodes; results are flat in the same order) and HOST arrays.
+ * gridpp::gridding (gridding.cpp:6-61): out[o] = statistic of values[i] over the input points i within `radius` of output
+ * location o (KDTree::get_neighbours: strictly inside the box, straight distance <= radius; values taken in ascending
+ * point index); fewer than min_num (> 0) neighbours -> missing. */
+int gpp_gridding_host(const gpp_points* opoints, const gpp_points* ipoints, const float* values, float radius, int min_num,
+                      int statistic, float* output);
+/* gridpp::gridding_nearest (gridding.cpp:63-131): every input point is assigned to its nearest output location; out[o] =
+ * statistic of the values assigned to o (in ascending point index), missing when none (or fewer than min_num > 0). */
+int gpp_gridding_nearest_host(const gpp_points* opoints, const gpp_points* ipoints, const float* values, int min_num,
+                              int statistic, float* output);
+/* gridpp::count (count.cpp:6-66, all four overloads): out[o] = number of input points within `radius` of output location o */
+int gpp_count_host(const gpp_points* ipoints, const gpp_points* opoints, float radius, float* output);
+/* gridpp::distance (distance.cpp:6-120): out[o] = largest KDTree::calc_distance from output location o to its `num` closest
+ * input points (num <= 16). query_first: the argument order of calc_distance in the overload (distance.cpp:21,111 pass the
+ * output location first; :52,83 the input point) -- it only matters for the rounding of the great-circle formula. */
+int gpp_distance_host(const gpp_points* ipoints, const gpp_points* opoints, int num, int query_first, float* output);
+/* gridpp::fill (fill.cpp:6-43): outside == 0: cells of `igrid` within radii[i] of point i take `value`, the others keep
+ * `input`; outside != 0: the reverse. */
+int gpp_fill_host(const gpp_points* igrid, const float* input, const gpp_points* points, const float* radii, float value,
+                  int outside, float* output);
+/* gridpp::fill_missing (fill.cpp:44-134): missing values replaced by the mean of the linear interpolations along x and y */
+int gpp_fill_missing_host(const float* values, int ny, int nx, float* output);
+/* gridpp::doping_square / doping_circle (doping.cpp:5-93): observations[i] is written into the square of half-width
+ * halfwidth[i] cells around the node nearest to point i / into the nodes within radii[i] of it, unless the elevation of the
+ * node differs from the point's by more than max_elev_diff (NaN: no check); where several points claim a cell the one with
+ * the highest index wins (the reference writes them in index order). doping_square needs the grid shape
+ * (gpp_points_set_shape). */
+int gpp_doping_square_host(const gpp_points* igrid, const float* background, const gpp_points* points, const float* observations,
+                           const int* halfwidth, float max_elev_diff, float* output);
+int gpp_doping_circle_host(const gpp_points* igrid, const float* background, const gpp_points* points, const float* observations,
+                           const float* radii, float max_elev_diff, float* output);
+
 /* ---------------------------------------------------------------- row statistics ---------------------- */
 /* gridpp::calc_statistic(vec2, statistic) util.cpp:208-215 (and, with n_rows = 1, the vec form :19-110): `array` holds
  * n_rows rows of row_length values; out[r] = statistic of the valid values of row r (Mean, Min, Median, Max, Std,

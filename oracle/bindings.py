@@ -267,6 +267,86 @@ class CpuLib:
         self._check(fn(_p(f), ny, nx, ne, halfwidth, statistic, float(quantile), _p(out)))
         return out
 
+    # ---- consumers of the point index. Location sets are (lats, lons[, elevs]) arrays: 2-D -> a Grid, 1-D -> Points. The plain-C
+    # oracle takes them flattened; the compiled reference builds the Grid / Points object the overload wants.
+    def _sets(self, *sets):
+        out = []
+        for la, lo in sets:
+            la, lo = _f(la), _f(lo)
+            ny, nx = (la.shape[0], la.shape[1]) if la.ndim == 2 else (la.size, 0)
+            out.append((la, lo, ny, nx))
+        return out
+
+    def gridding(self, oset, iset, values, radius, min_num, statistic, ctype, nearest=False):
+        (ola, olo, ony, onx), (ila, ilo, iny, _) = self._sets(oset, iset)
+        v = _f(values).ravel()
+        out = np.full(ola.shape, np.nan, np.float32)
+        name = "gridding_nearest" if nearest else "gridding"
+        if self.prefix == "ref_":
+            args = [_p(ola), _p(olo), ony, onx, _p(ila), _p(ilo), iny, ctype, _p(v)] + ([] if nearest else [C.c_float(radius)]) + [min_num, statistic, _p(out)]
+        else:
+            args = [_p(ola), _p(olo), ola.size, _p(ila), _p(ilo), iny, ctype, _p(v)] + ([] if nearest else [C.c_float(radius)]) + [min_num, statistic, _p(out)]
+        self._check(self._fn(name)(*args))
+        return out
+
+    def count(self, iset, oset, radius, ctype):
+        (ila, ilo, iny, inx), (ola, olo, ony, onx) = self._sets(iset, oset)
+        out = np.full(ola.shape, np.nan, np.float32)
+        if self.prefix == "ref_":
+            self._check(self._fn("count")(_p(ila), _p(ilo), iny, inx, _p(ola), _p(olo), ony, onx, ctype, C.c_float(radius), _p(out)))
+        else:
+            self._check(self._fn("count")(_p(ila), _p(ilo), ila.size, _p(ola), _p(olo), ola.size, ctype, C.c_float(radius), _p(out)))
+        return out
+
+    def distance(self, iset, oset, num, ctype):
+        (ila, ilo, iny, inx), (ola, olo, ony, onx) = self._sets(iset, oset)
+        out = np.full(ola.shape, np.nan, np.float32)
+        if self.prefix == "ref_":
+            self._check(self._fn("distance")(_p(ila), _p(ilo), iny, inx, _p(ola), _p(olo), ony, onx, ctype, num, _p(out)))
+        else:
+            query_first = int(onx == 0)    # distance.cpp:21,111 vs :52,83
+            self._check(self._fn("distance")(_p(ila), _p(ilo), ila.size, _p(ola), _p(olo), ola.size, ctype, num, query_first, _p(out)))
+        return out
+
+    def fill(self, glats, glons, field, plats, plons, radii, value, outside, ctype):
+        la, lo, f = _f(glats), _f(glons), _f(field)
+        ny, nx = la.shape
+        pl, po, r = _f(plats).ravel(), _f(plons).ravel(), _f(radii).ravel()
+        out = np.full((ny, nx), np.nan, np.float32)
+        if self.prefix == "ref_":
+            self._check(self._fn("fill")(_p(la), _p(lo), ny, nx, _p(f), _p(pl), _p(po), pl.size, ctype, _p(r), C.c_float(value), int(outside), _p(out)))
+        else:
+            self._check(self._fn("fill")(_p(la), _p(lo), ny * nx, _p(f), _p(pl), _p(po), pl.size, ctype, _p(r), C.c_float(value), int(outside), _p(out)))
+        return out
+
+    def fill_missing(self, field):
+        f = _f(field)
+        out = np.full(f.shape, np.nan, np.float32)
+        self._check(self._fn("fill_missing")(_p(f), f.shape[0], f.shape[1], _p(out)))
+        return out
+
+    def doping(self, glats, glons, gelevs, background, plats, plons, pelevs, obs, extent, max_elev_diff, ctype, square):
+        la, lo, bg = _f(glats), _f(glons), _f(background)
+        ny, nx = la.shape
+        ge = _f(gelevs) if gelevs is not None else np.full((ny, nx), np.nan, np.float32)
+        pl, po, o = _f(plats).ravel(), _f(plons).ravel(), _f(obs).ravel()
+        pe = _f(pelevs).ravel() if pelevs is not None else np.full(pl.size, np.nan, np.float32)
+        out = np.full((ny, nx), np.nan, np.float32)
+        if square:
+            ext = np.ascontiguousarray(np.asarray(extent, np.int32).ravel())
+            ext_p = ext.ctypes.data_as(_ip)
+        else:
+            ext = _f(extent).ravel()
+            ext_p = _p(ext)
+        name = "doping_square" if square else "doping_circle"
+        if self.prefix == "ref_" or square:
+            self._check(self._fn(name)(_p(la), _p(lo), _p(ge), ny, nx, _p(bg), _p(pl), _p(po), _p(pe), pl.size, ctype, _p(o), ext_p,
+                                       C.c_float(max_elev_diff), _p(out)))
+        else:
+            self._check(self._fn(name)(_p(la), _p(lo), _p(ge), ny * nx, _p(bg), _p(pl), _p(po), _p(pe), pl.size, ctype, _p(o), ext_p,
+                                       C.c_float(max_elev_diff), _p(out)))
+        return out
+
     def neighbourhood_quantile_fast(self, field, quantile, halfwidth, thresholds, timing=None):
         f = _f(field)
         ny, nx = f.shape

@@ -933,6 +933,7 @@ int orc_optimal_interpolation_ensi(const float* blats, const float* blons, const
 }
 
 /* ------------------------------------------------------------------ statistics ----------------------- */
+int orc_calc_statistic(const float* array, int n, int statistic, float* out);
 static int cmp_float(const void* a, const void* b) { float x = *(const float*) a, y = *(const float*) b; return (x > y) - (x < y); }
 /* util.cpp:111-178 */
 int orc_calc_quantile(const float* array, int T, float quantile, float* out) {
@@ -1365,5 +1366,251 @@ int orc_get_neighbourhood_thresholds(const float* input, int ny, int nx, int num
     *out_n = nq;
     for(int i = 0; i < nq && i < num; i++) out[i] = q[i];
     free(q);
+    return 0;
+}
+
+
+/* ------------------------------------------------------------------ consumers of the point index ----- */
+/* A Grid is its flattened nodes: every function takes flat lat / lon arrays for both sides. */
+/* gridding.cpp:6-61 (both overloads) */
+int orc_gridding(const float* olats, const float* olons, int nO, const float* ilats, const float* ilons, int nI, int type, const float* values,
+                 float radius, int min_num, int statistic, float* output) {
+    if(!is_valid(radius) || radius < 0) FAIL(1, "radius must be >= 0");
+    if(min_num < 0) FAIL(1, "min_num must be >= 0");
+    pts_t ip;
+    int rc = pts_make(&ip, ilats, ilons, NULL, NULL, nI, type);
+    if(rc) return rc;
+    cells_t cells;
+    cells_build(&cells, &ip, radius > 0 ? (double) radius : 1.0);
+    int err = 0;
+    #pragma omp parallel
+    {
+        int* I = NULL;
+        int cap = 0;
+        float* curr = NULL;
+        int ccap = 0;
+        #pragma omp for
+        for(int o = 0; o < nO; o++) {
+            float x, y, z;
+            output[o] = NAN;
+            if(convert_one(olats[o], olons[o], type, &x, &y, &z)) { err = 1; continue; }
+            int n = radius_query(&ip, &cells, x, y, z, radius, 1, &I, &cap);
+            if(min_num <= 0 || n >= min_num) {
+                if(n > ccap) { ccap = n; curr = realloc(curr, sizeof(float) * (size_t) ccap); }
+                for(int i = 0; i < n; i++) curr[i] = values[I[i]];
+                if(orc_calc_statistic(curr, n, statistic, &output[o])) err = 2;
+            }
+        }
+        free(I);
+        free(curr);
+    }
+    cells_free(&cells);
+    pts_free(&ip);
+    if(err == 1) FAIL(1, "Invalid coords in query");
+    if(err == 2) FAIL(2, "Internal error. Cannot compute statistic");
+    return 0;
+}
+/* gridding.cpp:63-131 (both overloads) */
+int orc_gridding_nearest(const float* olats, const float* olons, int nO, const float* ilats, const float* ilons, int nI, int type,
+                         const float* values, int min_num, int statistic, float* output) {
+    if(min_num < 0) FAIL(1, "min_num must be >= 0");
+    pts_t op;
+    int rc = pts_make(&op, olats, olons, NULL, NULL, nO, type);
+    if(rc) return rc;
+    int* node = malloc(sizeof(int) * (size_t) (nI > 0 ? nI : 1));
+    int* count = calloc((size_t) (nO > 0 ? nO : 1), sizeof(int));
+    for(int s = 0; s < nI; s++) {
+        float x, y, z;
+        if(convert_one(ilats[s], ilons[s], type, &x, &y, &z)) { free(node); free(count); pts_free(&op); FAIL(1, "Invalid coords"); }
+        int idx = -1;
+        node[s] = closest_query(&op, x, y, z, 1, 1, &idx) ? idx : -1;
+        if(node[s] >= 0) count[node[s]]++;
+    }
+    float* curr = malloc(sizeof(float) * (size_t) (nI > 0 ? nI : 1));
+    int err = 0;
+    for(int o = 0; o < nO; o++) {
+        output[o] = NAN;
+        if(count[o] == 0) continue;
+        if(min_num > 0 && count[o] < min_num) continue;
+        int n = 0;
+        for(int s = 0; s < nI; s++)
+            if(node[s] == o) curr[n++] = values[s];
+        if(orc_calc_statistic(curr, n, statistic, &output[o])) err = 2;
+    }
+    free(curr); free(node); free(count);
+    pts_free(&op);
+    if(err) FAIL(2, "Internal error. Cannot compute statistic");
+    return 0;
+}
+/* count.cpp:6-66 (all four overloads) */
+int orc_count(const float* ilats, const float* ilons, int nI, const float* olats, const float* olons, int nO, int type, float radius,
+              float* output) {
+    pts_t ip;
+    int rc = pts_make(&ip, ilats, ilons, NULL, NULL, nI, type);
+    if(rc) return rc;
+    cells_t cells;
+    cells_build(&cells, &ip, radius > 0 && is_valid(radius) ? (double) radius : 1.0);
+    int err = 0;
+    #pragma omp parallel
+    {
+        int* I = NULL;
+        int cap = 0;
+        #pragma omp for
+        for(int o = 0; o < nO; o++) {
+            float x, y, z;
+            if(convert_one(olats[o], olons[o], type, &x, &y, &z)) { err = 1; continue; }
+            output[o] = (float) radius_query(&ip, &cells, x, y, z, radius, 1, &I, &cap);
+        }
+        free(I);
+    }
+    cells_free(&cells);
+    pts_free(&ip);
+    if(err) FAIL(1, "Invalid coords in query");
+    return 0;
+}
+/* distance.cpp:6-120; query_first: calc_distance(output location, input point) (:21, :111) or the reverse (:52, :83) */
+int orc_distance(const float* ilats, const float* ilons, int nI, const float* olats, const float* olons, int nO, int type, int num,
+                 int query_first, float* output) {
+    pts_t ip;
+    int rc = pts_make(&ip, ilats, ilons, NULL, NULL, nI, type);
+    if(rc) return rc;
+    int err = 0;
+    #pragma omp parallel
+    {
+        int* idx = malloc(sizeof(int) * (size_t) (num > 0 ? num : 1));
+        #pragma omp for
+        for(int o = 0; o < nO; o++) {
+            float x, y, z;
+            if(convert_one(olats[o], olons[o], type, &x, &y, &z)) { err = 1; continue; }
+            int found = closest_query(&ip, x, y, z, num, 1, idx);
+            float max_dist = 0;
+            for(int k = 0; k < found; k++) {
+                float dist = query_first ? orc_calc_distance(olats[o], olons[o], ilats[idx[k]], ilons[idx[k]], type)
+                                         : orc_calc_distance(ilats[idx[k]], ilons[idx[k]], olats[o], olons[o], type);
+                if(dist > max_dist) max_dist = dist;
+            }
+            output[o] = max_dist;
+        }
+        free(idx);
+    }
+    pts_free(&ip);
+    if(err) FAIL(1, "Invalid coords in query");
+    return 0;
+}
+/* fill.cpp:6-43 (mode 1: inside takes `value`; mode 2: outside takes `value`) and doping_circle, doping.cpp:52-93 (mode 0) */
+static int circles(const float* glats, const float* glons, const float* gelevs, int nG, const float* plats, const float* plons, const float* pelevs,
+                   int nP, int type, const float* radii, int mode, const float* input, const float* obs, float value, float max_elev_diff,
+                   float* output) {
+    pts_t gp;
+    int rc = pts_make(&gp, glats, glons, gelevs, NULL, nG, type);
+    if(rc) return rc;
+    float rmax = 0;
+    for(int i = 0; i < nP; i++) if(radii[i] > rmax) rmax = radii[i];
+    cells_t cells;
+    cells_build(&cells, &gp, rmax > 0 ? (double) rmax : 1.0);
+    for(int c = 0; c < nG; c++) output[c] = mode == 2 ? value : input[c];
+    int* I = NULL;
+    int cap = 0, check_elev = is_valid(max_elev_diff) && mode == 0;
+    for(int i = 0; i < nP; i++) {
+        float x, y, z;
+        if(convert_one(plats[i], plons[i], type, &x, &y, &z)) { cells_free(&cells); pts_free(&gp); free(I); FAIL(1, "Invalid coords"); }
+        int n = radius_query(&gp, &cells, x, y, z, radii[i], 1, &I, &cap);
+        for(int j = 0; j < n; j++) {
+            if(check_elev) {
+                float diff = fabsf(pelevs[i] - gp.elev[I[j]]);
+                if(diff > max_elev_diff) continue;
+            }
+            output[I[j]] = mode == 0 ? obs[i] : (mode == 1 ? value : input[I[j]]);
+        }
+    }
+    free(I);
+    cells_free(&cells);
+    pts_free(&gp);
+    return 0;
+}
+int orc_fill(const float* glats, const float* glons, int nG, const float* input, const float* plats, const float* plons, int nP, int type,
+             const float* radii, float value, int outside, float* output) {
+    for(int i = 0; i < nP; i++) if(radii[i] < 0) FAIL(1, "All radius sizes must be 0 or greater");
+    return circles(glats, glons, NULL, nG, plats, plons, NULL, nP, type, radii, outside ? 2 : 1, input, NULL, value, NAN, output);
+}
+int orc_doping_circle(const float* glats, const float* glons, const float* gelevs, int nG, const float* background, const float* plats,
+                      const float* plons, const float* pelevs, int nP, int type, const float* obs, const float* radii, float max_elev_diff,
+                      float* output) {
+    if(is_valid(max_elev_diff) && max_elev_diff < 0) FAIL(1, "max_elev_diff must be greater than or equal to 0");
+    for(int i = 0; i < nP; i++) if(radii[i] < 0) FAIL(1, "radii must be greater than or equal to 0");
+    return circles(glats, glons, gelevs, nG, plats, plons, pelevs, nP, type, radii, 0, background, obs, 0, max_elev_diff, output);
+}
+/* doping.cpp:5-51 */
+int orc_doping_square(const float* glats, const float* glons, const float* gelevs, int ny, int nx, const float* background, const float* plats,
+                      const float* plons, const float* pelevs, int nP, int type, const float* obs, const int* halfwidth, float max_elev_diff,
+                      float* output) {
+    if(is_valid(max_elev_diff) && max_elev_diff < 0) FAIL(1, "max_elev_diff must be greater than or equal to 0");
+    for(int i = 0; i < nP; i++) if(halfwidth[i] < 0) FAIL(1, "All halfwidth must be greater than or equal to 0");
+    pts_t gp;
+    int rc = pts_make(&gp, glats, glons, gelevs, NULL, ny * nx, type);
+    if(rc) return rc;
+    for(int c = 0; c < ny * nx; c++) output[c] = background[c];
+    int check_elev = is_valid(max_elev_diff);
+    for(int i = 0; i < nP; i++) {
+        float x, y, z;
+        if(convert_one(plats[i], plons[i], type, &x, &y, &z)) { pts_free(&gp); FAIL(1, "Invalid coords"); }
+        int node;
+        if(!closest_query(&gp, x, y, z, 1, 1, &node)) continue;
+        int cy = node / nx, cx = node % nx;
+        for(int yy = cy - halfwidth[i] > 0 ? cy - halfwidth[i] : 0; yy <= (cy + halfwidth[i] < ny - 1 ? cy + halfwidth[i] : ny - 1); yy++)
+            for(int xx = cx - halfwidth[i] > 0 ? cx - halfwidth[i] : 0; xx <= (cx + halfwidth[i] < nx - 1 ? cx + halfwidth[i] : nx - 1); xx++) {
+                if(check_elev) {
+                    float diff = fabsf(pelevs[i] - gp.elev[yy * nx + xx]);
+                    if(diff > max_elev_diff) continue;
+                }
+                output[yy * nx + xx] = obs[i];
+            }
+    }
+    pts_free(&gp);
+    return 0;
+}
+/* fill.cpp:44-134 */
+int orc_fill_missing(const float* values, int Y, int X, float* output) {
+    size_t N = (size_t) Y * X;
+    float *ry = malloc(sizeof(float) * (N ? N : 1)), *rx = malloc(sizeof(float) * (N ? N : 1));
+    for(size_t i = 0; i < N; i++) { ry[i] = NAN; rx[i] = NAN; }
+    for(int y = 0; y < Y; y++) {
+        int last = 0, next = -1;
+        for(int x = 0; x < X; x++) {
+            float curr = values[(size_t) y * X + x];
+            if(!is_valid(curr)) {
+                if(next < x)
+                    for(next = x; next < X; next++)
+                        if(is_valid(values[(size_t) y * X + next])) break;
+                if(next >= X) continue;
+                float value_last = values[(size_t) y * X + last], value_next = values[(size_t) y * X + next];
+                ry[(size_t) y * X + x] = (value_last) + (value_next - value_last) * (x - last) / (next - last);
+            }
+            else { last = x; ry[(size_t) y * X + x] = curr; }
+        }
+    }
+    for(int x = 0; x < X; x++) {
+        int last = 0, next = -1;
+        for(int y = 0; y < Y; y++) {
+            float curr = values[(size_t) y * X + x];
+            if(!is_valid(curr)) {
+                if(next < y)
+                    for(next = y; next < Y; next++)
+                        if(is_valid(values[(size_t) next * X + x])) break;
+                if(next >= Y) continue;
+                float value_last = values[(size_t) last * X + x], value_next = values[(size_t) next * X + x];
+                rx[(size_t) y * X + x] = (value_last) + (value_next - value_last) * (y - last) / (next - last);
+            }
+            else { last = y; rx[(size_t) y * X + x] = curr; }
+        }
+    }
+    for(size_t i = 0; i < N; i++) {
+        int count = 0;
+        float total = 0;
+        if(is_valid(ry[i])) { total += ry[i]; count++; }
+        if(is_valid(rx[i])) { total += rx[i]; count++; }
+        output[i] = count > 0 ? total / count : NAN;
+    }
+    free(ry); free(rx);
     return 0;
 }

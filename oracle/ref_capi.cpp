@@ -418,4 +418,88 @@ int ref_calc_quantile(const float* a, int n, float q, float* out) {
     REF_CATCH
 }
 
+// ---- consumers of the point index: gridding.cpp, count.cpp, distance.cpp, fill.cpp, doping.cpp -----------------------
+// A location set is given as flat lat / lon arrays plus (ny, nx): nx > 0 -> a gridpp::Grid of ny x nx, nx == 0 -> gridpp::Points
+// of ny locations. Results are flat in the same order.
+namespace {
+gridpp::Grid make_grid(const float* lats, const float* lons, const float* elevs, int ny, int nx, int type) {
+    return gridpp::Grid(to_vec2(lats, ny, nx), to_vec2(lons, ny, nx), elevs ? to_vec2(elevs, ny, nx) : gridpp::vec2(), gridpp::vec2(),
+                        (gridpp::CoordinateType) type);
+}
+void from_any(const gridpp::vec2& v, float* out, int ny, int nx) { from_vec2(v, out, ny, nx); }
+}  // namespace
+
+int ref_gridding(const float* olats, const float* olons, int ony, int onx, const float* ilats, const float* ilons, int nI, int type,
+                 const float* values, float radius, int min_num, int statistic, float* output) {
+    REF_TRY
+    gridpp::Points ip = make_points(ilats, ilons, nullptr, nullptr, nI, type);
+    gridpp::vec v = to_vec(values, nI);
+    if(onx > 0) from_any(gridpp::gridding(make_grid(olats, olons, nullptr, ony, onx, type), ip, v, radius, min_num, (gridpp::Statistic) statistic), output, ony, onx);
+    else {
+        gridpp::vec out = gridpp::gridding(make_points(olats, olons, nullptr, nullptr, ony, type), ip, v, radius, min_num, (gridpp::Statistic) statistic);
+        std::memcpy(output, out.data(), sizeof(float) * out.size());
+    }
+    REF_CATCH
+}
+int ref_gridding_nearest(const float* olats, const float* olons, int ony, int onx, const float* ilats, const float* ilons, int nI, int type,
+                         const float* values, int min_num, int statistic, float* output) {
+    REF_TRY
+    gridpp::Points ip = make_points(ilats, ilons, nullptr, nullptr, nI, type);
+    gridpp::vec v = to_vec(values, nI);
+    if(onx > 0) from_any(gridpp::gridding_nearest(make_grid(olats, olons, nullptr, ony, onx, type), ip, v, min_num, (gridpp::Statistic) statistic), output, ony, onx);
+    else {
+        gridpp::vec out = gridpp::gridding_nearest(make_points(olats, olons, nullptr, nullptr, ony, type), ip, v, min_num, (gridpp::Statistic) statistic);
+        std::memcpy(output, out.data(), sizeof(float) * out.size());
+    }
+    REF_CATCH
+}
+// count / distance: (input set, output set), each a Grid (nx > 0) or Points
+int ref_count(const float* ilats, const float* ilons, int iny, int inx, const float* olats, const float* olons, int ony, int onx, int type,
+              float radius, float* output) {
+    REF_TRY
+    if(inx > 0 && onx > 0) from_any(gridpp::count(make_grid(ilats, ilons, nullptr, iny, inx, type), make_grid(olats, olons, nullptr, ony, onx, type), radius), output, ony, onx);
+    else if(inx > 0) { gridpp::vec o = gridpp::count(make_grid(ilats, ilons, nullptr, iny, inx, type), make_points(olats, olons, nullptr, nullptr, ony, type), radius); std::memcpy(output, o.data(), sizeof(float) * o.size()); }
+    else if(onx > 0) from_any(gridpp::count(make_points(ilats, ilons, nullptr, nullptr, iny, type), make_grid(olats, olons, nullptr, ony, onx, type), radius), output, ony, onx);
+    else { gridpp::vec o = gridpp::count(make_points(ilats, ilons, nullptr, nullptr, iny, type), make_points(olats, olons, nullptr, nullptr, ony, type), radius); std::memcpy(output, o.data(), sizeof(float) * o.size()); }
+    REF_CATCH
+}
+int ref_distance(const float* ilats, const float* ilons, int iny, int inx, const float* olats, const float* olons, int ony, int onx, int type,
+                 int num, float* output) {
+    REF_TRY
+    if(inx > 0 && onx > 0) from_any(gridpp::distance(make_grid(ilats, ilons, nullptr, iny, inx, type), make_grid(olats, olons, nullptr, ony, onx, type), num), output, ony, onx);
+    else if(inx > 0) { gridpp::vec o = gridpp::distance(make_grid(ilats, ilons, nullptr, iny, inx, type), make_points(olats, olons, nullptr, nullptr, ony, type), num); std::memcpy(output, o.data(), sizeof(float) * o.size()); }
+    else if(onx > 0) from_any(gridpp::distance(make_points(ilats, ilons, nullptr, nullptr, iny, type), make_grid(olats, olons, nullptr, ony, onx, type), num), output, ony, onx);
+    else { gridpp::vec o = gridpp::distance(make_points(ilats, ilons, nullptr, nullptr, iny, type), make_points(olats, olons, nullptr, nullptr, ony, type), num); std::memcpy(output, o.data(), sizeof(float) * o.size()); }
+    REF_CATCH
+}
+int ref_fill(const float* glats, const float* glons, int ny, int nx, const float* input, const float* plats, const float* plons, int nP, int type,
+             const float* radii, float value, int outside, float* output) {
+    REF_TRY
+    from_any(gridpp::fill(make_grid(glats, glons, nullptr, ny, nx, type), to_vec2(input, ny, nx), make_points(plats, plons, nullptr, nullptr, nP, type),
+                          to_vec(radii, nP), value, outside != 0), output, ny, nx);
+    REF_CATCH
+}
+int ref_fill_missing(const float* values, int ny, int nx, float* output) {
+    REF_TRY
+    from_any(gridpp::fill_missing(to_vec2(values, ny, nx)), output, ny, nx);
+    REF_CATCH
+}
+int ref_doping_square(const float* glats, const float* glons, const float* gelevs, int ny, int nx, const float* background, const float* plats,
+                      const float* plons, const float* pelevs, int nP, int type, const float* obs, const int* halfwidth, float max_elev_diff,
+                      float* output) {
+    REF_TRY
+    from_any(gridpp::doping_square(make_grid(glats, glons, gelevs, ny, nx, type), to_vec2(background, ny, nx),
+                                   make_points(plats, plons, pelevs, nullptr, nP, type), to_vec(obs, nP), gridpp::ivec(halfwidth, halfwidth + nP),
+                                   max_elev_diff), output, ny, nx);
+    REF_CATCH
+}
+int ref_doping_circle(const float* glats, const float* glons, const float* gelevs, int ny, int nx, const float* background, const float* plats,
+                      const float* plons, const float* pelevs, int nP, int type, const float* obs, const float* radii, float max_elev_diff,
+                      float* output) {
+    REF_TRY
+    from_any(gridpp::doping_circle(make_grid(glats, glons, gelevs, ny, nx, type), to_vec2(background, ny, nx),
+                                   make_points(plats, plons, pelevs, nullptr, nP, type), to_vec(obs, nP), to_vec(radii, nP), max_elev_diff), output, ny, nx);
+    REF_CATCH
+}
+
 }  // extern "C"

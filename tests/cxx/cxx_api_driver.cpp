@@ -125,6 +125,7 @@ static int run() {
     const int max_points = (int) meta["max_points"];
     const CoordinateType ctype = (CoordinateType) (int) meta["ctype"];
     const float quantile = (float) meta["quantile"];
+    const float radius = (float) meta["radius"];
 
     Grid grid(b200::unflatten(read_f32("glats"), ny, nx), b200::unflatten(read_f32("glons"), ny, nx), b200::unflatten(read_f32("gelevs"), ny, nx),
               b200::unflatten(read_f32("glafs"), ny, nx), ctype);
@@ -171,6 +172,15 @@ static int run() {
     write("qf_field", neighbourhood_quantile_fast(background, quantile_field, hw, thresholds));
     write("qf_ens", neighbourhood_quantile_fast(ensemble, quantile, hw, thresholds));
     write("thresholds", get_neighbourhood_thresholds(background, (int) thresholds.size()));
+    // consumers of the point index (gridding.cpp, count.cpp, distance.cpp, fill.cpp, doping.cpp)
+    write("gridding", gridding(grid, points, obs, radius, 2, Mean));
+    write("gridding_nearest", gridding_nearest(grid, points, obs, 0, Max));
+    write("count", count(points, grid, radius));
+    write("distance", distance(grid, points, 3));
+    write("fill", fill(grid, background, points, vec((size_t) nS, radius / 3), -1.f, false));
+    write("fill_missing", fill_missing(background));
+    write("doping_circle", doping_circle(grid, background, points, obs, vec((size_t) nS, radius / 3), 100.f));
+    write("doping_square", doping_square(grid, background, points, obs, ivec((size_t) nS, 1)));
     // statistics family (util.cpp:19-215,377-431; neighbourhood.cpp:211-238,528-539)
     write("nbh_std", neighbourhood(background, hw, Std));
     write("nbh_median", neighbourhood(background, hw, Median));
@@ -191,7 +201,6 @@ static int run() {
 
     // index queries (kdtree.cpp:18-106): integer results, compared bit for bit
     const vec qlats = read_f32("qlats"), qlons = read_f32("qlons");
-    const float radius = (float) meta["radius"];
     ivec nn, counts, neighbours, closest, grid_nn;
     vec distances;
     for(size_t i = 0; i < qlats.size(); i++) {

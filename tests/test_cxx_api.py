@@ -96,6 +96,16 @@ def test_cxx_api_matches_mirror_and_oracle(driver, gpp, orc, tmp_path):
     assert_bit_exact(out("qf_field", (ny, nx)), gpp.neighbourhood_quantile_fast(bg, qfield, hw, thr), "quantile_fast(vec2 quantile)")
     assert_bit_exact(out("qf_ens", (ny, nx)), gpp.neighbourhood_quantile_fast(ens, quantile, hw, thr), "quantile_fast(vec3)")
     assert_bit_exact(out("thresholds"), gpp.get_neighbourhood_thresholds(bg, T), "get_neighbourhood_thresholds")
+    rad3 = np.full(S, f32(radius) / f32(3), f32)
+    assert_bit_exact(out("gridding", (ny, nx)), gpp.gridding(grid, points, obs, radius, 2, gpp.Mean), "gridding")
+    assert_bit_exact(out("gridding_nearest", (ny, nx)), gpp.gridding_nearest(grid, points, obs, 0, gpp.Max), "gridding_nearest")
+    assert_bit_exact(out("count", (ny, nx)), gpp.count(points, grid, radius), "count")
+    assert_bit_exact(out("distance"), gpp.distance(grid, points, 3), "distance")
+    assert_bit_exact(out("fill", (ny, nx)), gpp.fill(grid, bg, points, rad3, -1.0, False), "fill")
+    assert_bit_exact(out("fill_missing", (ny, nx)), gpp.fill_missing(bg), "fill_missing")
+    assert_bit_exact(out("doping_circle", (ny, nx)), gpp.doping_circle(grid, bg, points, obs, rad3, 100.0), "doping_circle")
+    assert_bit_exact(out("doping_square", (ny, nx)), gpp.doping_square(grid, bg, points, obs, np.ones(S, np.int32)), "doping_square")
+    assert_bit_exact(out("gridding", (ny, nx)), orc.gridding((y, x), (py, px), obs, radius, 2, B.MEAN, B.CARTESIAN), "C++ gridding vs oracle")
     assert_bit_exact(out("nbh_std", (ny, nx)), gpp.neighbourhood(bg, hw, gpp.Std), "neighbourhood Std")
     assert_bit_exact(out("nbh_median", (ny, nx)), gpp.neighbourhood(bg, hw, gpp.Median), "neighbourhood Median")
     assert_bit_exact(out("nbh_quantile", (ny, nx)), gpp.neighbourhood_quantile(bg, quantile, hw), "neighbourhood_quantile")

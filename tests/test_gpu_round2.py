@@ -280,7 +280,9 @@ def test_statistics_family_golden(gpp):
     for r, p in zip(rows, picks):
         assert (np.isnan(p) and not np.isfinite(r).any()) or p in r
     rc = gpp.neighbourhood(f, 1, gpp.RandomChoice)
-    assert np.isnan(rc[12, 23]) and rc[0, 0] in f[0:2, 0:2]
+    empty = np.isnan(gpp.neighbourhood(f, 1, gpp.Mean))            # windows without a valid value
+    assert empty.any() and np.isnan(rc[empty]).all() and not np.isnan(rc[~empty]).any()
+    assert rc[0, 0] in f[0:2, 0:2]
     # a large window (961 values) and a window that does not fit the shared-memory stage (31 x 31 x 5 values)
     big = np.random.default_rng(3).random((40, 40)).astype(f32)
     got = gpp.neighbourhood_quantile(big, 0.5, 15)[5, 20]           # rows 0..20, columns 5..35 of the field
@@ -289,3 +291,84 @@ def test_statistics_family_golden(gpp):
     got = gpp.neighbourhood_quantile(ens_big, 1.0, 15)[16, 16]
     assert got == ens_big[1:32, 1:32].max()
     assert gpp.neighbourhood_brute_force(ens_big, 15, gpp.Count)[16, 16] == 31 * 31 * 5
+
+
+# ------------------------------------------------------------------ consumers of the point index --
+def test_gridding_family_golden(gpp):
+    """gridding / gridding_nearest / count / distance / fill / fill_missing / doping_square / doping_circle against the fixture
+    generated from the compiled reference. Integer-valued and copied results are bit-exact; sums and the great-circle
+    distance (double trigonometry on the device vs glibc) within 1e-5."""
+    from util import golden
+    import test_oracle
+    g = golden("gridding")
+    stat = {n: getattr(gpp, n.capitalize()) for n in STAT_NAMES}
+    exact_stats = ("min", "max", "median", "count")
+    n = 0
+    for key, tag, ctype, a, sets, func, spec in test_oracle._gridding_cases(g):
+        t = gpp.Cartesian if ctype == B.CARTESIAN else gpp.Geodetic
+        obj = dict(grid=gpp.Grid(a["glats"], a["glons"], a["gelevs"], type=t), points=gpp.Points(a["plats"], a["plons"], a["pelevs"], type=t),
+                   ogrid=gpp.Grid(*sets["ogrid"], type=t), opoints=gpp.Points(*sets["opoints"], type=t))
+        radius = float(a["radius"])
+        want = g[key]
+        if func.startswith("gridding"):
+            nearest = "nearest" in func
+            out = obj["grid"] if func.endswith("grid") else obj["opoints"]
+            name = spec.split("_mn")[0]
+            mn = int(spec.split("_mn")[1]) if "_mn" in spec else (0 if nearest else 1)
+            got = gpp.gridding_nearest(out, obj["points"], a["values"], mn, stat[name]) if nearest else \
+                gpp.gridding(out, obj["points"], a["values"], radius, mn, stat[name])
+            if name in exact_stats or name in ("mean", "sum", "std", "variance"):
+                assert_bit_exact(got, want, key)        # float accumulation in the reference's order: the same bits
+        elif func == "count":
+            i, o = spec.split("_")
+            assert_bit_exact(gpp.count(obj[i], obj[o], radius), want, key)
+        elif func == "distance":
+            i, o, num = spec.split("_")
+            got = gpp.distance(obj[i], obj[o], int(num[1:]))
+            if ctype == B.CARTESIAN:
+                assert_bit_exact(got, want, key)
+            else:
+                assert_close(got, want, 1000.0, RTOL, key)
+        elif func == "fill":
+            assert_bit_exact(gpp.fill(obj["grid"], a["field"], obj["points"], a["radii"], -7.5, bool(int(spec[-1]))), want, key)
+        else:
+            med = np.nan if spec == "nocheck" else 150.0
+            if func == "doping_square":
+                got = gpp.doping_square(obj["grid"], a["field"], obj["points"], a["values"], a["halfwidth"], med)
+            else:
+                got = gpp.doping_circle(obj["grid"], a["field"], obj["points"], a["values"], a["radii"], med)
+            assert_bit_exact(got, want, key)
+        n += 1
+    assert n >= 100
+    assert_bit_exact(gpp.fill_missing(g["fill_missing__in"]), g["fill_missing__out"], "fill_missing")
+    # argument checks (gridding.cpp:7-12, fill.cpp:7-14, doping.cpp:6-28)
+    grid, points = obj["grid"], obj["points"]
+    with pytest.raises(ValueError):
+        gpp.gridding(grid, points, a["values"][:-1], radius, 0, gpp.Mean)
+    with pytest.raises(ValueError):
+        gpp.gridding(grid, points, a["values"], -1, 0, gpp.Mean)
+    with pytest.raises(ValueError):
+        gpp.gridding_nearest(grid, points, a["values"], -1, gpp.Mean)
+    with pytest.raises(ValueError):
+        gpp.fill(grid, a["field"], points, -a["radii"] - 1, 0, False)
+    with pytest.raises(ValueError):
+        gpp.doping_circle(grid, a["field"], points, a["values"], a["radii"], -1.0)
+    with pytest.raises(ValueError):
+        gpp.distance(gpp.Points([0], [0]), gpp.Points([0], [0], type=gpp.Cartesian))
+
+
+def test_gridding_large_random_vs_oracle(gpp, orc):
+    """A denser case than the fixture (many neighbours per node, chunked pair lists): 300 x 300 grid, 20 000 points."""
+    rng = np.random.default_rng(5)
+    ny, nx, S = 300, 300, 20000
+    y, x = np.meshgrid(np.arange(ny, dtype=f32) * 500, np.arange(nx, dtype=f32) * 500, indexing="ij")
+    py, px = rng.uniform(0, ny * 500, S).astype(f32), rng.uniform(0, nx * 500, S).astype(f32)
+    v = rng.normal(size=S).astype(f32)
+    grid, points = gpp.Grid(y, x, type=gpp.Cartesian), gpp.Points(py, px, type=gpp.Cartesian)
+    for st_g, st_o in ((gpp.Mean, B.MEAN), (gpp.Median, B.MEDIAN), (gpp.Count, B.COUNT)):
+        got = gpp.gridding(grid, points, v, 4000.0, 5, st_g)
+        want = orc.gridding((y, x), (py, px), v, 4000.0, 5, st_o, B.CARTESIAN)
+        assert_bit_exact(got, want, "gridding statistic %d" % st_o)
+    assert_bit_exact(gpp.count(points, grid, 2500.0), orc.count((py, px), (y, x), 2500.0, B.CARTESIAN), "count")
+    assert_bit_exact(gpp.gridding_nearest(grid, points, v, 0, gpp.Max), orc.gridding((y, x), (py, px), v, 0, 0, B.MAX, B.CARTESIAN, nearest=True),
+                     "gridding_nearest")

@@ -428,3 +428,49 @@ def test_golden_statistics(orc):
             assert_bit_exact(np.array([orc.calc_statistic(r, STAT_CODES[key[6:]]) for r in rows], np.float32), g[key], key)
     got = np.array([orc.interpolate(v, g["interp_ix"], g["interp_iy"]) for v in g["interp_x"]], np.float32)
     assert_bit_exact(got, g["interp_y"], "interpolate")
+
+
+def _gridding_cases(g):
+    """(key, callable(lib) -> result) for every array of the gridding fixture; shared by the oracle and the GPU tests."""
+    for tag, ctype in (("cart", B.CARTESIAN), ("geo", B.GEODETIC)):
+        a = {k[len(tag) + 2:]: g[k] for k in g.files if k.startswith(tag + "__") and "__" not in k[len(tag) + 2:]}
+        sets = dict(grid=(a["glats"], a["glons"]), points=(a["plats"], a["plons"]),
+                    ogrid=(a["glats"][:9, :11] + np.float32(0.004 if ctype == B.GEODETIC else 400.0), a["glons"][:9, :11]),
+                    opoints=(a["olats"], a["olons"]))
+        for key in g.files:
+            if not key.startswith(tag + "__") or key.count("__") < 2:
+                continue
+            _, func, spec = key.split("__")
+            yield key, tag, ctype, a, sets, func, spec
+
+
+def test_golden_gridding(orc):
+    """Round 2: gridding / gridding_nearest / count / distance / fill / fill_missing / doping against the fixture
+    generated from the compiled reference."""
+    g = golden("gridding")
+    n = 0
+    for key, tag, ctype, a, sets, func, spec in _gridding_cases(g):
+        radius = float(a["radius"])
+        if func.startswith("gridding"):
+            nearest = "nearest" in func
+            oset = sets["grid"] if func.endswith("grid") else sets["opoints"]
+            name = spec.split("_mn")[0]
+            mn = int(spec.split("_mn")[1]) if "_mn" in spec else (0 if nearest else 1)
+            got = orc.gridding(oset, sets["points"], a["values"], radius, mn, STAT_CODES[name], ctype, nearest=nearest)
+        elif func == "count":
+            i, o = spec.split("_")
+            got = orc.count(sets[i], sets[o], radius, ctype)
+        elif func == "distance":
+            i, o, num = spec.split("_")
+            got = orc.distance(sets[i], sets[o], int(num[1:]), ctype)
+        elif func == "fill":
+            got = orc.fill(a["glats"], a["glons"], a["field"], a["plats"], a["plons"], a["radii"], -7.5, int(spec[-1]), ctype)
+        else:
+            med = np.nan if spec == "nocheck" else 150.0
+            square = func == "doping_square"
+            got = orc.doping(a["glats"], a["glons"], a["gelevs"], a["field"], a["plats"], a["plons"], a["pelevs"], a["values"],
+                             a["halfwidth"] if square else a["radii"], med, ctype, square)
+        assert_bit_exact(got, g[key], key)
+        n += 1
+    assert n >= 100
+    assert_bit_exact(orc.fill_missing(g["fill_missing__in"]), g["fill_missing__out"], "fill_missing")
