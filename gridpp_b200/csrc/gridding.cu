@@ -224,7 +224,7 @@ int gridding_radius(gpp_points* op, gpp_points* ip, const float* d_values, float
         GPP_TRY(keys.alloc((size_t) std::max<long long>(total, 1)));
         if(total > 0) {
             GPP_LAUNCH(list_neighbours_kernel, blocks_for(n), 128, 0, stream, ix, op->dx.ptr, op->dy.ptr, op->dz.ptr, q0, n, radius, counts.ptr, keys.ptr);
-            thrust::sort(policy, keys.ptr, keys.ptr + total);   // by query, then ascending point index (the order of the oracle's index)
+            thrust::sort(policy, keys.ptr, keys.ptr + total);   // by query, then ascending point index
             g_launches.fetch_add(2, std::memory_order_relaxed);
         }
         const SegmentRows R = {d_values, keys.ptr, counts.ptr};
