@@ -710,6 +710,14 @@ def optimal_interpolation(bgrid, background, points, pobs, pratios, pbackground,
     return out
 
 
+def optimal_interpolation_multi_gpu(bgrid, background, points, pobs, pratios, pbackground, structure, max_points,
+                                    allow_extrapolation=True, n_devices=0):
+    """gridpp::optimal_interpolation over every visible GPU from ONE process (gpp_optimal_interpolation_multi_gpu_host): the rows of
+    the grid are split into one block per device. Bit-identical to the single-device call. n_devices = 0: all devices."""
+    return _oi(bgrid, background, None, points, pobs, pratios, pbackground, None, structure, max_points, allow_extrapolation, False,
+               n_devices=n_devices)
+
+
 def optimal_interpolation_full(bgrid, background, bvariance, points, obs, obs_variance, background_at_points,
                                bvariance_at_points, structure, max_points, allow_extrapolation=True):
     """gridpp::optimal_interpolation_full, oi.cpp:138-412. Returns (analysis, analysis_variance)."""
@@ -718,7 +726,7 @@ def optimal_interpolation_full(bgrid, background, bvariance, points, obs, obs_va
 
 
 def _oi(bgrid, background, bvariance, points, pobs, obs_variance, pbackground, bvariance_at_points, structure, max_points,
-        allow_extrapolation, full):
+        allow_extrapolation, full, n_devices=None):
     if max_points < 0:
         raise ValueError("max_points must be >= 0")
     if not isinstance(points, Points):
@@ -753,6 +761,11 @@ def _oi(bgrid, background, bvariance, points, pobs, obs_variance, pbackground, b
                                                             _fptr(ovar), _fptr(pbg), _fptr(pbvar), int(structure._TYPE), field._handle,
                                                             float(structure._min_rho), int(max_points), int(bool(allow_extrapolation)),
                                                             _fptr(out), _fptr(var)))
+        return (out, var) if full else out
+    if n_devices is not None:
+        _check(_libc.gpp_optimal_interpolation_multi_gpu_host(int(n_devices), bgrid._set._handle, _fptr(bg), _fptr(bvar), points._set._handle,
+                                                              _fptr(obs), _fptr(ovar), _fptr(pbg), _fptr(pbvar), _C.byref(structure._desc),
+                                                              int(max_points), int(bool(allow_extrapolation)), _fptr(out), _fptr(var)))
         return (out, var) if full else out
     _check(_libc.gpp_optimal_interpolation_host(bgrid._set._handle, _fptr(bg), _fptr(bvar), points._set._handle, _fptr(obs),
                                                 _fptr(ovar), _fptr(pbg), _fptr(pbvar), _C.byref(structure._desc),
@@ -916,7 +929,8 @@ def get_neighbourhood_thresholds(input, num_thresholds):
 # ---------------------------------------------------------------------------------------------------------
 # consumers of the point index: gridding / gridding_nearest / count / distance / fill / fill_missing / doping
 def _out_shape(obj):
-    return tuple(obj._stored_shape) if _is_grid(obj) else (obj.size(),)
+    # gridding.cpp:14-15, count.cpp:20-21, distance.cpp:33: the output is sized by Grid::size(), (0, 0) for a grid without nodes
+    return tuple(obj.size()) if _is_grid(obj) else (obj.size(),)
 
 
 def gridding(grid, points, values, radius, min_num, statistic):

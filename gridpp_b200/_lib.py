@@ -76,6 +76,8 @@ _proto("gpp_ensi_obs_create", C.c_int, vp, fp, fp, fp, C.c_int, ip, sp, C.POINTE
 _proto("gpp_ensi_obs_destroy", None, vp)
 _proto("gpp_ensi_valid_members_device", C.c_int, vp, C.c_longlong, C.c_int, ip, vp)
 _proto("gpp_optimal_interpolation_ensi_device", C.c_int, vp, C.c_int, C.c_int, vp, C.c_int, vp, sp, C.c_int, C.c_int, vp, vp, vp)
+_proto("gpp_optimal_interpolation_multi_gpu_host", C.c_int, C.c_int, vp, fp, fp, vp, fp, fp, fp, fp, sp, C.c_int, C.c_int, fp, fp)
+_proto("gpp_halo_pull_device", C.c_int, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp)
 _proto("gpp_optimal_interpolation_ensi_host", C.c_int, vp, fp, C.c_int, vp, fp, fp, fp, sp, C.c_int, C.c_int, fp, ip)
 _proto("gpp_neighbourhood_host", C.c_int, fp, C.c_int, C.c_int, C.c_int, C.c_int, fp)
 _proto("gpp_neighbourhood_device", C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp)
@@ -116,7 +118,7 @@ EXPORTS = [
     "gpp_points_coordinate_type", "gpp_points_get_xyz", "gpp_convert_coordinates", "gpp_points_nearest_host", "gpp_points_neighbours_host",
     "gpp_points_closest_host", "gpp_nearest_host", "gpp_optimal_interpolation_host", "gpp_oi_obs_create",
     "gpp_oi_obs_destroy", "gpp_optimal_interpolation_device", "gpp_optimal_interpolation_ensi_host",
-    "gpp_oi_workspace_bytes", "gpp_optimal_interpolation_device_ws", "gpp_ensi_obs_create", "gpp_ensi_obs_destroy",
+    "gpp_oi_workspace_bytes", "gpp_optimal_interpolation_device_ws", "gpp_optimal_interpolation_multi_gpu_host", "gpp_halo_pull_device", "gpp_ensi_obs_create", "gpp_ensi_obs_destroy",
     "gpp_ensi_valid_members_device", "gpp_optimal_interpolation_ensi_device",
     "gpp_neighbourhood_host", "gpp_neighbourhood_device", "gpp_neighbourhood_quantile_fast_host",
     "gpp_neighbourhood_quantile_fast_device", "gpp_neighbourhood_ens_host", "gpp_neighbourhood_ens_device",

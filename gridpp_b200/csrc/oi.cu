@@ -1385,7 +1385,14 @@ struct PinnedStage {
         return GPP_OK;
     }
 };
-PinnedStage g_stage;
+// one staging pair per device: host threads driving different devices (gpp_optimal_interpolation_multi_gpu_host) must not
+// serialise on one lock
+PinnedStage g_stages[64];
+PinnedStage& stage_of_current_device() {
+    int dev = 0;
+    if(cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    return g_stages[dev];
+}
 
 // Blocks [bounds[c], bounds[c+1]) (in floats) of d_out are produced back to back on the default stream by launch(c); a
 // second stream copies each finished block into a pinned slot, and the host moves it into the caller's array while the
@@ -1399,6 +1406,7 @@ int pipelined_download(const std::vector<size_t>& bounds, const std::function<in
     const int n_chunks = (int) bounds.size() - 1;
     size_t largest = 0;
     for(int c = 0; c < n_chunks; c++) largest = std::max(largest, bounds[c + 1] - bounds[c]);
+    PinnedStage& g_stage = stage_of_current_device();
     std::lock_guard<std::mutex> guard(g_stage.lock);
     GPP_TRY(g_stage.reserve(largest));
     cudaStream_t copy_stream;

@@ -24,12 +24,31 @@ def row_block(n_rows, world_size, rank):
     return n_rows * rank // world_size, n_rows * (rank + 1) // world_size
 
 
+def peer_halo_available():
+    """True when the halo rows can be read straight out of the neighbours' memory: NCCL process group on CUDA devices and
+    torch's symmetric memory (the allocation + handle exchange; the copy itself is gpp_halo_pull_device)."""
+    if not (dist.is_initialized() and dist.get_world_size() > 1 and dist.get_backend() == "nccl" and torch.cuda.is_available()):
+        return False
+    try:
+        import torch.distributed._symmetric_memory as symm_mem  # noqa: F401
+    except Exception:
+        return False
+    return True
+
+
 class RowTile:
     """This rank's rows of a row-sharded (n_rows_global, nx) field, stored with space for `halfwidth` halo rows on
-    each side. `tile` is the view to fill with the rank's own rows (row_block(n_rows_global, world, rank))."""
+    each side. `tile` is the view to fill with the rank's own rows (row_block(n_rows_global, world, rank)).
 
-    def __init__(self, n_rows_global, nx, halfwidth, device=None, dtype=torch.float32, group=None):
+    halo="nccl": the halo rows travel as a batched isend / irecv with the two vertical neighbours (gloo on CPU tensors in
+    the tests). halo="peer": the buffer lives in symmetric memory, so every rank has its neighbours' buffers mapped;
+    `exchange()` is then a barrier on the signal pad followed by ONE kernel (gpp_halo_pull_device) that reads the 2 x
+    halfwidth boundary rows over NVLink -- no NCCL launch on the data path."""
+
+    def __init__(self, n_rows_global, nx, halfwidth, device=None, dtype=torch.float32, group=None, halo="nccl"):
         self.group = group
+        self.halo = halo
+        self._symm = None
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.hw = int(halfwidth)
@@ -44,7 +63,17 @@ class RowTile:
                                  % (self.hw, smallest))
         self.above = self.hw if self.rank > 0 else 0                      # halo rows present above / below the tile
         self.below = self.hw if self.rank < self.world - 1 else 0
-        self.buf = torch.empty((self.rows + 2 * self.hw, self.nx), dtype=dtype, device=device)
+        if halo == "peer":
+            import torch.distributed._symmetric_memory as symm_mem
+            # symmetric allocations have the same size on every rank: room for the largest block
+            self._rows_of = [row_block(self.n_rows_global, self.world, r)[1] - row_block(self.n_rows_global, self.world, r)[0]
+                             for r in range(self.world)]
+            whole = symm_mem.empty((max(self._rows_of) + 2 * self.hw, self.nx), dtype=dtype, device=device)
+            self._symm = symm_mem.rendezvous(whole, group if group is not None else dist.group.WORLD)
+            self._whole = whole
+            self.buf = whole[:self.rows + 2 * self.hw]
+        else:
+            self.buf = torch.empty((self.rows + 2 * self.hw, self.nx), dtype=dtype, device=device)
         self.tile = self.buf[self.hw:self.hw + self.rows]
 
     @property
@@ -66,8 +95,28 @@ class RowTile:
         return dist.batch_isend_irecv(ops)
 
     def exchange(self):
+        if self.halo == "peer":
+            return self.exchange_peer()
         for req in self.exchange_async():
             req.wait()
+
+    def exchange_peer(self):
+        """Barrier (every rank's tile is complete, every earlier pull is done), then one kernel that copies the boundary rows
+        out of the neighbours' buffers. Asynchronous on the current stream."""
+        import ctypes as C
+        from ._lib import check, lib
+        if self.world == 1 or self.hw == 0:
+            return
+        esize = self.buf.element_size()
+        row_bytes = self.nx * esize
+        above = below = None
+        if self.rank > 0:      # the last hw tile rows of rank - 1: its buffer rows [rows_up, rows_up + hw)
+            above = C.c_void_p(int(self._symm.buffer_ptrs[self.rank - 1]) + self._rows_of[self.rank - 1] * row_bytes)
+        if self.rank < self.world - 1:   # the first hw tile rows of rank + 1: its buffer rows [hw, 2 hw)
+            below = C.c_void_p(int(self._symm.buffer_ptrs[self.rank + 1]) + self.hw * row_bytes)
+        self._symm.barrier(channel=0)
+        check(lib.gpp_halo_pull_device(C.c_void_p(self.buf.data_ptr()), self.rows, self.nx, self.hw, above, below,
+                                       C.c_void_p(torch.cuda.current_stream().cuda_stream)))
 
 
 def _run_tiled(rt, out, launch):
@@ -75,6 +124,11 @@ def _run_tiled(rt, out, launch):
     first and last rows are treated as domain edges) into `out_rows`. The rows whose windows stay inside the tile go
     first and overlap the exchange; the (at most `halfwidth`) rows at each end follow once the halo is there."""
     hw, rows = rt.hw, rt.rows
+    if rt.halo == "peer":
+        # the pull is one short kernel on the same stream: one launch over the tile with its halo follows it
+        rt.exchange_peer()
+        launch(rt.with_halo, rt.above, rows, out)
+        return out
     reqs = rt.exchange_async()
     if not reqs:
         launch(rt.with_halo, rt.above, rows, out)
@@ -95,11 +149,11 @@ def _run_tiled(rt, out, launch):
     return out
 
 
-def neighbourhood(tile, halfwidth, statistic, compute=None, group=None, n_rows_global=None, out=None):
+def neighbourhood(tile, halfwidth, statistic, compute=None, group=None, n_rows_global=None, out=None, halo="nccl"):
     """Row-sharded gridpp.neighbourhood. `tile` is either a RowTile (no copies) or a (rows_local, nx) tensor holding
     this rank's rows (copied into a RowTile; ranks own row_block() blocks). Returns this rank's rows of the result.
     `compute(field_with_halo, halfwidth, statistic, row0, n_rows_out)` defaults to the CUDA device entry point."""
-    rt = _as_row_tile(tile, halfwidth, group, n_rows_global)
+    rt = _as_row_tile(tile, halfwidth, group, n_rows_global, halo)
     if out is None:
         out = torch.empty((rt.rows, rt.nx), dtype=rt.buf.dtype, device=rt.buf.device)
     if compute is None:
@@ -113,9 +167,9 @@ def neighbourhood(tile, halfwidth, statistic, compute=None, group=None, n_rows_g
     return _run_tiled(rt, out, launch)
 
 
-def neighbourhood_quantile_fast(tile, quantile, halfwidth, thresholds, compute=None, group=None, n_rows_global=None, out=None):
+def neighbourhood_quantile_fast(tile, quantile, halfwidth, thresholds, compute=None, group=None, n_rows_global=None, out=None, halo="nccl"):
     """Row-sharded gridpp.neighbourhood_quantile_fast (scalar quantile)."""
-    rt = _as_row_tile(tile, halfwidth, group, n_rows_global)
+    rt = _as_row_tile(tile, halfwidth, group, n_rows_global, halo)
     if out is None:
         out = torch.empty((rt.rows, rt.nx), dtype=rt.buf.dtype, device=rt.buf.device)
     if compute is None:
@@ -129,7 +183,7 @@ def neighbourhood_quantile_fast(tile, quantile, halfwidth, thresholds, compute=N
     return _run_tiled(rt, out, launch)
 
 
-def _as_row_tile(tile, halfwidth, group, n_rows_global):
+def _as_row_tile(tile, halfwidth, group, n_rows_global, halo="nccl"):
     if isinstance(tile, RowTile):
         if tile.hw != int(halfwidth):
             raise ValueError("the RowTile was built for halfwidth %d" % tile.hw)
@@ -140,7 +194,7 @@ def _as_row_tile(tile, halfwidth, group, n_rows_global):
         if dist.is_initialized() and dist.get_world_size(group) > 1:
             dist.all_reduce(n, group=group)
         n_rows_global = int(n.item())
-    rt = RowTile(n_rows_global, nx, halfwidth, device=tile.device, dtype=tile.dtype, group=group)
+    rt = RowTile(n_rows_global, nx, halfwidth, device=tile.device, dtype=tile.dtype, group=group, halo=halo)
     if rt.rows != rows:
         raise ValueError("this rank holds %d rows, row_block() assigns it %d" % (rows, rt.rows))
     rt.tile.copy_(tile)
@@ -149,7 +203,7 @@ def _as_row_tile(tile, halfwidth, group, n_rows_global):
 
 def exchange_halo(tile, halfwidth, group=None):
     """Functional form: returns (tile_with_halo, halo_rows_above) for a (rows_local, nx) tensor."""
-    rt = _as_row_tile(tile, halfwidth, group, None)
+    rt = _as_row_tile(tile, halfwidth, group, None, "nccl")
     rt.exchange()
     return rt.with_halo, rt.above
 

@@ -57,6 +57,14 @@ inline void require(bool ok, const std::string& msg) {
     if(!ok) throw std::invalid_argument(msg);
 }
 // rows x cols of a vec2; every row must have the length of the first
+// How many GPUs optimal_interpolation / optimal_interpolation_full use from this process: 1 (default), n, or 0 = every visible
+// device. The rows of the background grid are split into one block per device; results do not depend on the setting.
+inline int& devices() {
+    static int n = 1;
+    return n;
+}
+inline void use_devices(int n) { devices() = n < 0 ? 1 : n; }
+
 inline void shape_of(const vec2& a, int& rows, int& cols, const char* name) {
     rows = (int) a.size();
     cols = rows ? (int) a[0].size() : 0;
@@ -515,6 +523,12 @@ inline vec run_oi(const Points& bpoints, const vec& background, const float* bva
         check(gpp_optimal_interpolation_spatial_host(bpoints.b200_handle(), background.data(), bvariance, obs_points.b200_handle(), obs.data(), obs_variance.data(),
                                                      background_at_points.data(), bvariance_at_points, t.type, field, t.min_rho, max_points, allow_extrapolation,
                                                      analysis.data(), variance));
+    }
+    else if(devices() != 1) {
+        // several GPUs from this one process: the rows of the grid are split over the devices (use_devices)
+        check(gpp_optimal_interpolation_multi_gpu_host(devices(), bpoints.b200_handle(), background.data(), bvariance, obs_points.b200_handle(), obs.data(),
+                                                       obs_variance.data(), background_at_points.data(), bvariance_at_points, &structure.b200_descriptor(),
+                                                       max_points, allow_extrapolation, analysis.data(), variance));
     }
     else {
         check(gpp_optimal_interpolation_host(bpoints.b200_handle(), background.data(), bvariance, obs_points.b200_handle(), obs.data(), obs_variance.data(),

@@ -196,6 +196,17 @@ int gpp_optimal_interpolation_device_ws(const gpp_points* bpoints, int first, in
                                         float* d_analysis, float* d_analysis_variance, void* d_workspace,
                                         size_t workspace_bytes, void* stream);
 
+/* The same analysis spread over several devices by ONE process: the rows of the background grid (single points of a point
+ * set) are split into contiguous blocks, one per device (n_devices <= 0: every visible device); each device runs
+ * gpp_optimal_interpolation_host on its block from its own host thread against its own copy of the observation table.
+ * Grid points are independent (oi.cpp:221-338): no exchange, results identical to the single-device call bit for bit.
+ * (One process per GPU -- MPI, torch.distributed -- shards the same way with gpp_optimal_interpolation_device.) */
+int gpp_optimal_interpolation_multi_gpu_host(int n_devices, const gpp_points* bpoints, const float* background, const float* bvariance,
+                                             const gpp_points* opoints, const float* pobs, const float* obs_variance,
+                                             const float* pbackground, const float* bvariance_at_points,
+                                             const gpp_structure* structure, int max_points, int allow_extrapolation,
+                                             float* analysis, float* analysis_variance);
+
 /* gridpp::optimal_interpolation_ensi(Points...) oi_ensi.cpp:114-568 (the Grid overload :33-112 flattens to
  * this). background and analysis are nB x nE (member fastest), pbackground is nS x nE. HOST memory. */
 int gpp_optimal_interpolation_ensi_host(const gpp_points* bpoints, const float* background, int nE,
@@ -254,6 +265,15 @@ int gpp_neighbourhood_host(const float* input, int ny, int nx, int halfwidth, in
  * [row0, row0 + n_rows_out) are written to d_output[0 .. n_rows_out*nx). */
 int gpp_neighbourhood_device(const float* d_input, int n_rows_in, int nx, int row0, int n_rows_out,
                              int halfwidth, int statistic, float* d_output, void* stream);
+
+/* Halo exchange of a row-tiled field as one kernel over peer memory. d_buf holds this rank's tile with room for the halos:
+ * [halfwidth rows | rows rows | halfwidth rows] x nx. d_from_above points at the LAST `halfwidth` tile rows of the upper
+ * neighbour, d_from_below at the FIRST `halfwidth` tile rows of the lower neighbour -- device pointers of another GPU mapped
+ * into this process (symmetric memory / CUDA IPC between ranks, peer access inside one process); NULL at a domain edge.
+ * The caller orders the call after the neighbours' tiles are complete (a barrier on the exchange's signal pad) and before
+ * gpp_neighbourhood_device / gpp_neighbourhood_quantile_fast_device on the tile with its halo. */
+int gpp_halo_pull_device(float* d_buf, int rows, int nx, int halfwidth, const float* d_from_above, const float* d_from_below,
+                         void* stream);
 
 /* gridpp::neighbourhood_quantile_fast(vec2, quantile | vec2 quantile, halfwidth, thresholds)
  * neighbourhood.cpp:296-409. quantile_field (ny x nx) may be NULL, then `quantile` applies everywhere.

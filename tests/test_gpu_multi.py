@@ -34,3 +34,29 @@ def test_two_gpu_sharded_results_equal_whole_field():
     failed = [k for k, v in out["checks"].items() if not v]
     assert not failed and res.returncode == 0, "sharded != whole for: %s" % failed
     assert len(out["checks"]) >= 13
+
+
+def test_single_process_multi_gpu_oi_equals_single_device(gpp):
+    """gpp_optimal_interpolation_multi_gpu_host: one process, the rows of the grid split over the visible devices; bit-identical
+    to the single-device call (analysis and, through optimal_interpolation_full's arguments, the variance path is the same code)."""
+    import numpy as np
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (run on a box with >= 2 B200s: gpurun --gpus 2)")
+    rng = np.random.default_rng(3)
+    ny, nx, dx, S = 515, 640, 250.0, 2500
+    y, x = np.meshgrid(np.arange(ny, dtype=np.float32) * dx, np.arange(nx, dtype=np.float32) * dx, indexing="ij")
+    py, px = (rng.random(S) * ny * dx).astype(np.float32), (rng.random(S) * nx * dx).astype(np.float32)
+    bg = rng.standard_normal((ny, nx)).astype(np.float32)
+    pbg = rng.standard_normal(S).astype(np.float32)
+    obs = (pbg + rng.standard_normal(S) * 0.5).astype(np.float32)
+    ratios = np.full(S, 0.5, np.float32)
+    grid, points, s = gpp.Grid(y, x, type=gpp.Cartesian), gpp.Points(py, px, type=gpp.Cartesian), gpp.BarnesStructure(10000)
+    one = gpp.optimal_interpolation(grid, bg, points, obs, ratios, pbg, s, 30)
+    for nd in (0, 2):
+        many = gpp.optimal_interpolation_multi_gpu(grid, bg, points, obs, ratios, pbg, s, 30, n_devices=nd)
+        assert np.array_equal(one, many, equal_nan=True), "n_devices=%d" % nd
+    pts = gpp.Points(y.ravel()[:100001], x.ravel()[:100001], type=gpp.Cartesian)      # a point set: split by points
+    a = gpp.optimal_interpolation(pts, bg.ravel()[:100001], points, obs, ratios, pbg, s, 30)
+    b = gpp.optimal_interpolation_multi_gpu(pts, bg.ravel()[:100001], points, obs, ratios, pbg, s, 30)
+    assert np.array_equal(a, b, equal_nan=True)
