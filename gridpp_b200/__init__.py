@@ -808,6 +808,91 @@ def optimal_interpolation_ensi(bgrid, background, points, pobs, psigmas, pbackgr
     return out
 
 
+def _ensi_multi(kind, bgrid, bratios, background, background_corr, points, pobs, pratios, pbackground, pbackground_corr, structure,
+                max_points, allow_extrapolation):
+    """Shared host side of the three "multi" variants (oi_ensi_multi.cpp:33-327 Grid overloads, :329-1311 Points overloads)."""
+    if max_points < 0:
+        raise ValueError("max_points must be >= 0")
+    grid = _is_grid(bgrid)
+    bg = _farray(background, 3 if grid else 2, "background")
+    nS = points.size()
+    if nS == 0:
+        return bg.copy()
+    shape = tuple(bgrid.size()) if grid else (bgrid.size(),)
+    if grid and (shape[0] == 0 or shape[1] == 0):
+        raise ValueError("Grid size (%d,%d) cannot be zero" % shape)
+    if bgrid.get_coordinate_type() != points.get_coordinate_type():
+        raise ValueError("Both background and observations points must be of same coorindate type (lat/lon or x/y)")
+    _check_size(bg.shape[:-1] == shape, "Input background field is not the same size as the grid")
+    nE = bg.shape[-1]
+    br = _farray(bratios, 2 if grid else 1, "bratios")
+    _check_size(br.shape == shape, "Bratios and grid size mismatch")
+    obs = _farray(pobs, 1 if kind == "utem" else 2, "pobs")
+    pr = _farray(pratios, 1, "pratios")
+    pbg = _farray(pbackground, 2, "pbackground")
+    _check_size(obs.shape[0] == nS and (kind == "utem" or obs.shape[1] == nE), "Observations and points exception mismatch")
+    _check_size(pr.size == nS, "Pratios and points size mismatch")
+    _check_size(pbg.shape == (nS, nE), "Background and points size mismatch")
+    bgc = pbgc = None
+    if kind != "ebesc":
+        bgc = _farray(background_corr, 3 if grid else 2, "background_corr")
+        pbgc = _farray(pbackground_corr, 2, "pbackground_corr")
+        _check_size(bgc.shape == bg.shape, "Input background_corr field is not the same size as the grid")
+        _check_size(pbgc.shape == (nS, nE), "Background_corr and points size mismatch")
+    out = _np.empty(bg.shape, _np.float32)
+    common = (_C.byref(structure._desc), int(max_points), int(bool(allow_extrapolation)), _fptr(out))
+    if kind == "ebesc":
+        _check(_libc.gpp_optimal_interpolation_ensi_multi_ebesc_host(bgrid._set._handle, _fptr(br), _fptr(bg), nE, points._set._handle, _fptr(obs),
+                                                                     _fptr(pr), _fptr(pbg), *common))
+    elif kind == "ebe":
+        _check(_libc.gpp_optimal_interpolation_ensi_multi_ebe_host(bgrid._set._handle, _fptr(br), _fptr(bg), _fptr(bgc), nE, points._set._handle,
+                                                                   _fptr(obs), _fptr(pr), _fptr(pbg), _fptr(pbgc), *common))
+    else:
+        skipped = _C.c_int()
+        _check(_libc.gpp_optimal_interpolation_ensi_multi_utem_host(bgrid._set._handle, _fptr(br), _fptr(bg), _fptr(bgc), nE, points._set._handle,
+                                                                    _fptr(obs), _fptr(pr), _fptr(pbg), _fptr(pbgc), *common, _C.byref(skipped)))
+        if skipped.value > 0:   # oi_ensi_multi.cpp:1300-1304
+            print("Warning: Condition number error in %d points. Using raw values in those points." % skipped.value)
+    return out
+
+
+def optimal_interpolation_ensi_multi_ebe(bgrid, bratios, background, background_corr, points, pobs, pratios, pbackground,
+                                         pbackground_corr, structure, max_points, allow_extrapolation=True):
+    """gridpp::optimal_interpolation_ensi_multi_ebe, oi_ensi_multi.cpp:34-135 (Grid) and :329-627 (Points): member-by-member
+    increments with ensemble-based correlations. background* is (Y, X, E) / (L, E); pobs, pbackground* are (S, E)."""
+    return _ensi_multi("ebe", bgrid, bratios, background, background_corr, points, pobs, pratios, pbackground, pbackground_corr, structure,
+                       max_points, allow_extrapolation)
+
+
+def optimal_interpolation_ensi_multi_ebesc(bgrid, bratios, background, points, pobs, pratios, pbackground, structure, max_points,
+                                           allow_extrapolation=True):
+    """gridpp::optimal_interpolation_ensi_multi_ebesc, oi_ensi_multi.cpp:137-224 (Grid) and :630-859 (Points): member-by-member
+    increments with static correlations."""
+    return _ensi_multi("ebesc", bgrid, bratios, background, None, points, pobs, pratios, pbackground, None, structure, max_points,
+                       allow_extrapolation)
+
+
+def optimal_interpolation_ensi_multi_utem(bgrid, bratios, background, background_corr, points, pobs, pratios, pbackground,
+                                          pbackground_corr, structure, max_points, allow_extrapolation=True):
+    """gridpp::optimal_interpolation_ensi_multi_utem, oi_ensi_multi.cpp:226-327 (Grid) and :862-1311 (Points): the ensemble transform of EnSI computed from
+    the *_corr ensembles, applied to the mean and spread of background. pobs is (S,)."""
+    return _ensi_multi("utem", bgrid, bratios, background, background_corr, points, pobs, pratios, pbackground, pbackground_corr, structure,
+                       max_points, allow_extrapolation)
+
+
+def staticcorr_points(points, knots, structure, max_points):
+    """gridpp::staticcorr_points, corr_points.cpp:26-131 -> (L, K): row l holds structure.corr_background(point l, knot) for the
+    (at most max_points best) knots within the localization radius, 0 elsewhere."""
+    if max_points < 0:
+        raise ValueError("max_points must be >= 0")
+    if points.get_coordinate_type() != knots.get_coordinate_type():
+        raise ValueError("Both background grid and observations points must be of same coordinate type (lat/lon or x/y)")
+    out = _np.zeros((points.size(), knots.size()), _np.float32)
+    if out.size:
+        _check(_libc.gpp_staticcorr_points_host(points._set._handle, knots._set._handle, _C.byref(structure._desc), int(max_points), _fptr(out)))
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------------
 def neighbourhood(input, halfwidth, statistic):
     """gridpp::neighbourhood(vec2, halfwidth, statistic), neighbourhood.cpp:28-242."""

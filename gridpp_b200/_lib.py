@@ -79,6 +79,10 @@ _proto("gpp_optimal_interpolation_ensi_device", C.c_int, vp, C.c_int, C.c_int, v
 _proto("gpp_optimal_interpolation_multi_gpu_host", C.c_int, C.c_int, vp, fp, fp, vp, fp, fp, fp, fp, sp, C.c_int, C.c_int, fp, fp)
 _proto("gpp_halo_pull_device", C.c_int, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp)
 _proto("gpp_optimal_interpolation_ensi_host", C.c_int, vp, fp, C.c_int, vp, fp, fp, fp, sp, C.c_int, C.c_int, fp, ip)
+_proto("gpp_optimal_interpolation_ensi_multi_ebe_host", C.c_int, vp, fp, fp, fp, C.c_int, vp, fp, fp, fp, fp, sp, C.c_int, C.c_int, fp)
+_proto("gpp_optimal_interpolation_ensi_multi_ebesc_host", C.c_int, vp, fp, fp, C.c_int, vp, fp, fp, fp, sp, C.c_int, C.c_int, fp)
+_proto("gpp_optimal_interpolation_ensi_multi_utem_host", C.c_int, vp, fp, fp, fp, C.c_int, vp, fp, fp, fp, fp, sp, C.c_int, C.c_int, fp, ip)
+_proto("gpp_staticcorr_points_host", C.c_int, vp, vp, sp, C.c_int, fp)
 _proto("gpp_neighbourhood_host", C.c_int, fp, C.c_int, C.c_int, C.c_int, C.c_int, fp)
 _proto("gpp_neighbourhood_device", C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp)
 _proto("gpp_neighbourhood_quantile_fast_host", C.c_int, fp, C.c_int, C.c_int, C.c_float, fp, C.c_int, fp, C.c_int, fp)
@@ -120,6 +124,8 @@ EXPORTS = [
     "gpp_oi_obs_destroy", "gpp_optimal_interpolation_device", "gpp_optimal_interpolation_ensi_host",
     "gpp_oi_workspace_bytes", "gpp_optimal_interpolation_device_ws", "gpp_optimal_interpolation_multi_gpu_host", "gpp_halo_pull_device", "gpp_ensi_obs_create", "gpp_ensi_obs_destroy",
     "gpp_ensi_valid_members_device", "gpp_optimal_interpolation_ensi_device",
+    "gpp_optimal_interpolation_ensi_multi_ebe_host", "gpp_optimal_interpolation_ensi_multi_ebesc_host",
+    "gpp_optimal_interpolation_ensi_multi_utem_host", "gpp_staticcorr_points_host",
     "gpp_neighbourhood_host", "gpp_neighbourhood_device", "gpp_neighbourhood_quantile_fast_host",
     "gpp_neighbourhood_quantile_fast_device", "gpp_neighbourhood_ens_host", "gpp_neighbourhood_ens_device",
     "gpp_neighbourhood_quantile_fast_ens_host", "gpp_neighbourhood_quantile_fast_ens_device",

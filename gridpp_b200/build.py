@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-SOURCES = ["capi.cu", "points.cu", "oi.cu", "neighbourhood.cu", "neighbourhood_tma.cu", "quantile_tma.cu", "ensemble_forms.cu", "thresholds.cu", "ensi.cu", "stats.cu", "gridding.cu", "multi_gpu.cu"]
+SOURCES = ["capi.cu", "points.cu", "oi.cu", "neighbourhood.cu", "neighbourhood_tma.cu", "quantile_tma.cu", "ensemble_forms.cu", "thresholds.cu", "ensi.cu", "stats.cu", "gridding.cu", "multi_gpu.cu", "ensi_multi.cu"]
 LIB = os.path.join(HERE, "libgridpp_b200.so")
 
 

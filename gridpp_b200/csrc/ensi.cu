@@ -36,6 +36,10 @@ struct EnsiParams {
     int valid_ens[ENSI_EMAX];
     ObsView obs;                  // ratio := psigma, innov := (double) pobs - (double) yhat
     const float* gY;              // [table slot][E]: pbackground minus its ensemble mean, valid members only
+                                  // (utem: the standardised perturbations of pbackground_corr, oi_ensi_multi.cpp:978-993)
+    const float* gY_raw;          // utem: [table slot][E] pbackground minus its mean (:968-976), for the clamp's lY[e]
+    const float* background_corr; // utem: nB x nE
+    const float* bratios;         // utem: nB
     gpp_structure s;
     float R;
     int k;
@@ -257,7 +261,10 @@ struct RegisterJacobi {
 #else
 #define ENSI_MINB_FOR(EC) ENSI_MINB
 #endif
-template <int SMODE, int EC>
+// UTEM: gridpp::optimal_interpolation_ensi_multi_utem (oi_ensi_multi.cpp:862-1311) -- the same transform computed from the
+// standardised *_corr ensembles (Pinv = C Y_corr + I, Rinv = rho / pratios) and applied to the standardised perturbations
+// of background_corr, scaled by the spread of background and by bratios.
+template <int SMODE, int EC, bool UTEM = false>
 __global__ void __launch_bounds__(ENSI_WARPS * 32, ENSI_MINB_FOR(EC)) ensi_kernel(const __grid_constant__ EnsiParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     EnsiSmem S;
@@ -314,7 +321,7 @@ __global__ void __launch_bounds__(ENSI_WARPS * 32, ENSI_MINB_FOR(EC)) ensi_kerne
             const int pos = S.pos[i];
             S.spos[i] = pos;
             const float sigma = P.obs.ratio[pos];
-            S.rinv[i] = (double) cand_key_rho(S.key[i]) / (double) __fmul_rn(sigma, sigma);
+            S.rinv[i] = (double) cand_key_rho(S.key[i]) / (double) (UTEM ? sigma : __fmul_rn(sigma, sigma));   // oi_ensi_multi.cpp:1094
             S.dd[i] = P.obs.innov[pos];
         }
         __syncwarp();
@@ -339,10 +346,10 @@ __global__ void __launch_bounds__(ENSI_WARPS * 32, ENSI_MINB_FOR(EC)) ensi_kerne
                         if(EC > 0 || f < E) acc[f] = fma(c, S.Y[i * LD + f], acc[f]);
                 }
                 S.b[lane] = b;
-                lYe = S.Y[(lane % k) * LD + (lane / k)];
+                lYe = UTEM ? (double) P.gY_raw[(size_t) S.spos[lane % k] * E + lane / k] : S.Y[(lane % k) * LD + (lane / k)];
             }
             __syncwarp();   // lY is dead from here on: A and T take its place
-            const double diag = (double) (float) (E - 1);   // oi_ensi.cpp:383 with delta = 1
+            const double diag = UTEM ? 1.0 : (double) (float) (E - 1);   // oi_ensi.cpp:383 with delta = 1; oi_ensi_multi.cpp:1105
             #pragma unroll
             for(int f = 0; f < EU; f++)
                 if(f == lane) acc[f] += diag;
@@ -510,6 +517,22 @@ __global__ void __launch_bounds__(ENSI_WARPS * 32, ENSI_MINB_FOR(EC)) ensi_kerne
             S.w[lane] = w;
         }
         __syncwarp();
+        float ensStd = 1.f, bratio = 1.f;
+        if(UTEM) {
+            // oi_ensi_multi.cpp:1160-1198: X_corr, the standardised perturbations of background_corr (into S.t, which is
+            // dead now, as is S.b), and the spread of background
+            float* cval = reinterpret_cast<float*>(S.b);
+            if(lane < E) cval[lane] = P.background_corr[(size_t) g * P.nE + P.valid_ens[lane]];
+            __syncwarp();
+            float mean_c, std_c, unused;
+            seq_mean_std(cval, E, &mean_c, &std_c);
+            seq_mean_std(S.sval, E, &unused, &ensStd);
+            const float const_fact = (float) (1.0 / sqrt((double) (E - 1)));
+            if(lane < E)
+                S.t[lane] = std_c <= 0.0013f ? 0.0 : (double) __fdiv_rn(__fmul_rn(const_fact, __fsub_rn(cval[lane], mean_c)), std_c);
+            bratio = P.bratios[g];
+            __syncwarp();
+        }
         if(lane < E) {
             // analysis for member `lane`: total += X(k) * W(k, e) accumulated in FLOAT (oi_ensi.cpp:506-512),
             // W(k, e) = sum_f V(k,f) sqrt((E-1)/lam_f) V(e,f) + w(k)  (oi_ensi.cpp:419-444)
@@ -522,8 +545,14 @@ __global__ void __launch_bounds__(ENSI_WARPS * 32, ENSI_MINB_FOR(EC)) ensi_kerne
                 #pragma unroll
                 for(int f = 0; f < EU; f++)
                     if(EC > 0 || f < E) wke = fma(S.V[kk * LD + f], vs[f], wke);
-                wke += S.w[kk];
-                tot = (float) ((double) tot + S.X[kk] * wke);
+                if(UTEM) {   // W(e, e2) = ensStd * W(e, e2) + std_ratios_lr * w(e), applied to X_corr (oi_ensi_multi.cpp:1201-1254)
+                    wke = __dadd_rn(__dmul_rn((double) ensStd, wke), __dmul_rn((double) bratio, S.w[kk]));
+                    tot = (float) __dadd_rn((double) tot, __dmul_rn(S.t[kk], wke));
+                }
+                else {
+                    wke += S.w[kk];
+                    tot = (float) ((double) tot + S.X[kk] * wke);
+                }
             }
             float currIncrement = tot;
             if(!P.allow_extrapolation) {   // oi_ensi.cpp:517-551
@@ -574,6 +603,7 @@ constexpr unsigned ENSI_COUNTER_SLOTS = 16;
 struct gpp_ensi_obs {
     gpp_oi_obs table;
     gpp::DeviceBuffer<float> gY;          // [table slot][E]
+    gpp::DeviceBuffer<float> gY_raw;      // utem only: [table slot][E]
     gpp::DeviceBuffer<int> counters;      // ENSI_COUNTER_SLOTS x {next block, warps done}, zero between launches
     mutable std::atomic<unsigned> next_slot{0};
     int nE = 0, E = 0;
@@ -639,7 +669,8 @@ int ensi_kcap(const gpp_ensi_obs& st, gpp_points* bp, int first, int count, cons
 
 // Analyses points [first, first + count): d_analysis must already hold the background there. One kernel launch.
 int ensi_launch(const gpp_ensi_obs& st, gpp_points* bp, int first, int count, const float* d_background, float* d_analysis,
-                const gpp_structure* structure, int kcap, int allow_extrapolation, int* d_num_skipped, int* counter_pair, cudaStream_t stream) {
+                const gpp_structure* structure, int kcap, int allow_extrapolation, int* d_num_skipped, int* counter_pair, cudaStream_t stream,
+                const float* d_background_corr = nullptr, const float* d_bratios = nullptr /* both given: the utem variant */) {
     if(st.E == 0 || st.table.n_valid == 0 || count == 0) return GPP_OK;
     EnsiParams P;
     std::memset(&P, 0, sizeof(P));
@@ -650,6 +681,8 @@ int ensi_launch(const gpp_ensi_obs& st, gpp_points* bp, int first, int count, co
     P.first = first; P.count = count; P.nE = st.nE; P.E = st.E;
     P.obs = st.table.view();
     P.gY = st.gY.ptr;
+    const bool utem = d_background_corr && d_bratios;
+    P.gY_raw = st.gY_raw.ptr; P.background_corr = d_background_corr; P.bratios = d_bratios;
     P.s = *structure;
     P.R = structure->term[0].loc_dist;
     P.allow_extrapolation = allow_extrapolation;
@@ -662,7 +695,8 @@ int ensi_launch(const gpp_ensi_obs& st, gpp_points* bp, int first, int count, co
     const size_t smem = (size_t) P.smem_per_warp * ENSI_WARPS;
     const int mode = structure_mode(*structure);
     void (*kernel)(EnsiParams) = nullptr;
-    switch(E) {   // the common ensemble sizes get their own instantiation
+    if(utem) kernel = mode == 1 ? ensi_kernel<1, 0, true> : ensi_kernel<0, 0, true>;
+    else switch(E) {   // the common ensemble sizes get their own instantiation
         case 10: kernel = mode == 1 ? ensi_kernel<1, 10> : ensi_kernel<0, 10>; break;
         case 20: kernel = mode == 1 ? ensi_kernel<1, 20> : ensi_kernel<0, 20>; break;
         case 30: kernel = mode == 1 ? ensi_kernel<1, 30> : ensi_kernel<0, 30>; break;
@@ -828,6 +862,106 @@ extern "C" int gpp_optimal_interpolation_ensi_host(const gpp_points* cbp, const 
     if(num_skipped) GPP_CUDA(cudaMemcpyAsync(num_skipped, d_skipped.ptr, sizeof(int), cudaMemcpyDeviceToHost, 0));
     GPP_CUDA(cudaStreamSynchronize(0));   // `st` and the staging vectors go out of scope after this
     trace.lap("D2H");
+    return GPP_OK;
+}
+
+// gridpp::optimal_interpolation_ensi_multi_utem, Points overload (oi_ensi_multi.cpp:862-1311)
+extern "C" int gpp_optimal_interpolation_ensi_multi_utem_host(const gpp_points* cbp, const float* bratios, const float* background,
+                                                              const float* background_corr, int nE, const gpp_points* opoints,
+                                                              const float* pobs, const float* pratios, const float* pbackground,
+                                                              const float* pbackground_corr, const gpp_structure* structure, int max_points,
+                                                              int allow_extrapolation, float* analysis, int* num_skipped) {
+    if(num_skipped) *num_skipped = 0;
+    if(max_points < 0) return fail(GPP_ERR_INVALID_ARGUMENT, "max_points must be >= 0");   // :874-875
+    if(!cbp || !opoints || !structure) return fail(GPP_ERR_INVALID_ARGUMENT, "NULL argument");
+    if(nE < 0) return fail(GPP_ERR_INVALID_ARGUMENT, "negative ensemble size");
+    gpp_points* bp = const_cast<gpp_points*>(cbp);
+    const int nB = bp->n, nS = opoints->n;
+    const size_t nBE = (size_t) nB * nE;
+    if(bp->type != opoints->type)
+        return fail(GPP_ERR_INVALID_ARGUMENT, "Both background and observations points must be of same coorindate type (lat/lon or x/y)");
+    if(nS == 0 || nBE == 0) {   // :895-897
+        if(nBE) std::memcpy(analysis, background, sizeof(float) * nBE);
+        return GPP_OK;
+    }
+    if(!bratios || !background || !background_corr || !pobs || !pratios || !pbackground || !pbackground_corr)
+        return fail(GPP_ERR_INVALID_ARGUMENT, "NULL argument");
+    GPP_TRY(reject_unset_scales(structure));
+    GPP_TRY(ensure_device());
+    // ---- members valid in all four ensembles (:929-953)
+    DeviceBuffer<float> d_bg, d_bgc, d_br, d_out;
+    DeviceBuffer<int> d_skipped;
+    GPP_TRY(d_bg.upload(background, nBE));
+    GPP_TRY(d_bgc.upload(background_corr, nBE));
+    std::vector<int> ok(nE, 1), ok2(nE, 1);
+    GPP_TRY(gpp_ensi_valid_members_device(d_bg.ptr, nB, nE, ok.data(), nullptr));
+    GPP_TRY(gpp_ensi_valid_members_device(d_bgc.ptr, nB, nE, ok2.data(), nullptr));
+    gpp_ensi_obs st;
+    st.nE = nE;
+    st.E = 0;
+    for(int e = 0; e < nE; e++) {
+        bool good = ok[e] && ok2[e];
+        for(int i = 0; i < nS && good; i++) good = is_valid(pbackground[(size_t) i * nE + e]) && is_valid(pbackground_corr[(size_t) i * nE + e]);
+        if(!good) continue;
+        if(st.E >= ENSI_EMAX)
+            return fail(GPP_ERR_NOT_IMPLEMENTED, "optimal_interpolation_ensi_multi_utem supports at most %d valid ensemble members on the device", ENSI_EMAX);
+        st.valid_ens[st.E++] = e;
+    }
+    std::memcpy(analysis, background, sizeof(float) * nBE);
+    const int E = st.E;
+    if(E == 0) return GPP_OK;
+    // ---- the observation side (:955-994): perturbations about the mean, standardised *_corr perturbations, obs - yhat
+    std::vector<char> valid(nS);
+    std::vector<double> innov(nS);
+    std::vector<float> ratio(pratios, pratios + nS), gY((size_t) nS * E), gYc((size_t) nS * E), row(E);
+    const float const_fact = (float) (1 / std::sqrt((double) (E - 1)));
+    auto mean_of = [&](const float* v) {   // calc_statistic(Mean), util.cpp:22-37
+        float total = 0;
+        for(int e = 0; e < E; e++) total += v[e];
+        return total / E;
+    };
+    for(int i = 0; i < nS; i++) {
+        for(int e = 0; e < E; e++) row[e] = pbackground[(size_t) i * nE + st.valid_ens[e]];
+        const float mean = mean_of(row.data());
+        for(int e = 0; e < E; e++) gY[(size_t) i * E + e] = row[e] - mean;
+        valid[i] = is_valid(pobs[i]);
+        innov[i] = (double) pobs[i] - (double) mean;   // lObs - lYhat, :1157
+        for(int e = 0; e < E; e++) row[e] = pbackground_corr[(size_t) i * nE + st.valid_ens[e]];
+        const float mean_c = mean_of(row.data());
+        float t1 = 0, t2 = 0;   // calc_statistic(Std), util.cpp:40-73
+        for(int e = 0; e < E; e++) { const float d = row[e] - row[0]; t1 += d; t2 += d * d; }
+        const float m1 = t1 / E, m2 = t2 / E;
+        float var = m2 - m1 * m1;
+        if(var < 0) var = 0;
+        const float std_c = std::sqrt(var);
+        for(int e = 0; e < E; e++) gYc[(size_t) i * E + e] = std_c <= 0.0013f ? 0.f : const_fact * (row[e] - mean_c) / std_c;
+    }
+    std::vector<int> order;
+    GPP_TRY(build_obs_table(opoints, valid, innov, ratio, structure->term[0].loc_dist, &st.table, &order));
+    if(st.table.n_valid == 0) return GPP_OK;
+    std::vector<float> a(order.size() * (size_t) E), b(order.size() * (size_t) E);
+    for(size_t slot = 0; slot < order.size(); slot++)
+        for(int e = 0; e < E; e++) {
+            a[slot * E + e] = gYc[(size_t) order[slot] * E + e];
+            b[slot * E + e] = gY[(size_t) order[slot] * E + e];
+        }
+    GPP_TRY(st.gY.upload(a.data(), a.size()));
+    GPP_TRY(st.gY_raw.upload(b.data(), b.size()));
+    GPP_TRY(st.counters.alloc(2));
+    GPP_CUDA(cudaMemsetAsync(st.counters.ptr, 0, sizeof(int) * 2, 0));
+    GPP_TRY(d_skipped.alloc(1));
+    GPP_CUDA(cudaMemsetAsync(d_skipped.ptr, 0, sizeof(int), 0));
+    GPP_TRY(d_br.upload(bratios, (size_t) nB));
+    GPP_TRY(d_out.alloc(nBE));
+    GPP_CUDA(cudaMemcpyAsync(d_out.ptr, d_bg.ptr, sizeof(float) * nBE, cudaMemcpyDeviceToDevice, 0));
+    GPP_TRY(bp->ensure_on_device());
+    int kcap = 0;
+    GPP_TRY(ensi_kcap(st, bp, 0, nB, structure, max_points, 0, &kcap));
+    GPP_TRY(ensi_launch(st, bp, 0, nB, d_bg.ptr, d_out.ptr, structure, kcap, allow_extrapolation, d_skipped.ptr, st.counters.ptr, 0, d_bgc.ptr,
+                        d_br.ptr));
+    GPP_TRY(d_out.download(analysis, nBE));
+    if(num_skipped) GPP_CUDA(cudaMemcpyAsync(num_skipped, d_skipped.ptr, sizeof(int), cudaMemcpyDeviceToHost, 0));
+    GPP_CUDA(cudaStreamSynchronize(0));
     return GPP_OK;
 }
 

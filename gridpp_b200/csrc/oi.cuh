@@ -123,6 +123,25 @@ __device__ __forceinline__ int gather_candidates(const ObsView& obs, const gpp_s
     return n;
 }
 
+// calc_statistic(Mean) and (Std) of n valid floats (util.cpp:19-73): sequential float accumulation, the variance about the
+// first value. Every lane may call it on the same shared array.
+__device__ __forceinline__ void seq_mean_std(const float* v, int n, float* mean_out, float* std_out) {
+    float total = 0.f;
+    for(int e = 0; e < n; e++) total = __fadd_rn(total, v[e]);
+    *mean_out = __fdiv_rn(total, (float) n);
+    const float K = v[0];
+    float t1 = 0.f, t2 = 0.f;
+    for(int e = 0; e < n; e++) {
+        const float d = __fsub_rn(v[e], K);
+        t1 = __fadd_rn(t1, d);
+        t2 = __fadd_rn(t2, __fmul_rn(d, d));
+    }
+    const float m1 = __fdiv_rn(t1, (float) n), m2 = __fdiv_rn(t2, (float) n);
+    float var = __fsub_rn(m2, __fmul_rn(m1, m1));
+    if(var < 0.f) var = 0.f;
+    *std_out = __fsqrt_rn(var);
+}
+
 }  // namespace gpp
 
 constexpr unsigned OI_WORK_SLOTS = 4;

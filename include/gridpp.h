@@ -660,6 +660,143 @@ inline vec3 optimal_interpolation_ensi(const Grid& bgrid, const vec3& background
                                           structure, max_points, allow_extrapolation), ny, nx, ne);
 }
 
+// The "multi" EnSI variants (oi_ensi_multi.cpp) and staticcorr_points (corr_points.cpp). kind: 0 ebesc, 1 ebe, 2 utem.
+namespace b200 {
+inline vec run_ensi_multi(int kind, const Points& bpoints, const vec& bratios, const vec& background, const vec& background_corr, int nE,
+                          const Points& obs_points, const vec& pobs, const vec& pratios, const vec2& pbackground, const vec2& pbackground_corr,
+                          const StructureFunction& structure, int max_points, bool allow_extrapolation) {
+    require(bpoints.get_coordinate_type() == obs_points.get_coordinate_type(),
+            "Both background and observations points must be of same coorindate type (lat/lon or x/y)");
+    if(structure.b200_field()) throw not_implemented_exception("spatially varying structure functions in optimal_interpolation_ensi_multi");
+    const size_t nS = (size_t) obs_points.size(), nB = (size_t) bpoints.size();
+    if(background.size() != nB * nE) size_error("Input background field", background.size(), "is not the same size as the grid", nB * nE);
+    if(bratios.size() != nB) size_error("Bratios", bratios.size(), "and grid size mismatch", nB);
+    if(pobs.size() != (kind == 2 ? nS : nS * nE)) size_error("Observations", pobs.size(), "and points size mismatch", nS);
+    if(pratios.size() != nS) size_error("Pratios", pratios.size(), "and points size mismatch", nS);
+    int pS, pE;
+    shape_of(pbackground, pS, pE, "pbackground");
+    if((size_t) pS != nS || pE != nE) size_error("Background", (size_t) pS, "and points size mismatch", nS);
+    vec pbc;
+    if(kind != 0) {
+        if(background_corr.size() != background.size()) size_error("Input background_corr field", background_corr.size(), "is not the same size as the grid", background.size());
+        shape_of(pbackground_corr, pS, pE, "pbackground_corr");
+        if((size_t) pS != nS || pE != nE) size_error("Background_corr", (size_t) pS, "and points size mismatch", nS);
+        pbc = flatten(pbackground_corr);
+    }
+    vec analysis(background.size());
+    if(analysis.empty()) return analysis;
+    const vec pb = flatten(pbackground);
+    int skipped = 0;
+    if(kind == 0)
+        check(gpp_optimal_interpolation_ensi_multi_ebesc_host(bpoints.b200_handle(), bratios.data(), background.data(), nE, obs_points.b200_handle(), pobs.data(),
+                                                              pratios.data(), pb.data(), &structure.b200_descriptor(), max_points, allow_extrapolation, analysis.data()));
+    else if(kind == 1)
+        check(gpp_optimal_interpolation_ensi_multi_ebe_host(bpoints.b200_handle(), bratios.data(), background.data(), background_corr.data(), nE,
+                                                            obs_points.b200_handle(), pobs.data(), pratios.data(), pb.data(), pbc.data(),
+                                                            &structure.b200_descriptor(), max_points, allow_extrapolation, analysis.data()));
+    else
+        check(gpp_optimal_interpolation_ensi_multi_utem_host(bpoints.b200_handle(), bratios.data(), background.data(), background_corr.data(), nE,
+                                                             obs_points.b200_handle(), pobs.data(), pratios.data(), pb.data(), pbc.data(),
+                                                             &structure.b200_descriptor(), max_points, allow_extrapolation, analysis.data(), &skipped));
+    if(skipped > 0)   // oi_ensi_multi.cpp:1300-1304
+        std::cout << "Warning: Condition number error in " << skipped << " points. Using raw values in those points." << std::endl;
+    return analysis;
+}
+inline int members_of(const vec2& a) { return a.empty() ? 0 : (int) a[0].size(); }
+inline int members_of(const vec3& a) { return a.empty() || a[0].empty() ? 0 : (int) a[0][0].size(); }
+}  // namespace b200
+
+// oi_ensi_multi.cpp:329-627 (Points) and :34-135 (Grid)
+inline vec2 optimal_interpolation_ensi_multi_ebe(const Points& bpoints, const vec& bratios, const vec2& background, const vec2& background_corr,
+                                                 const Points& obs_points, const vec2& pobs, const vec& pratios, const vec2& pbackground,
+                                                 const vec2& pbackground_corr, const StructureFunction& structure, int max_points,
+                                                 bool allow_extrapolation = true) {
+    b200::require(max_points >= 0, "max_points must be >= 0");
+    if(obs_points.size() == 0) return background;
+    const int nE = b200::members_of(background);
+    return b200::unflatten(b200::run_ensi_multi(1, bpoints, bratios, b200::flatten(background), b200::flatten(background_corr), nE, obs_points,
+                                                b200::flatten(pobs), pratios, pbackground, pbackground_corr, structure, max_points, allow_extrapolation),
+                           (int) background.size(), nE);
+}
+inline vec3 optimal_interpolation_ensi_multi_ebe(const Grid& bgrid, const vec2& bratios, const vec3& background, const vec3& background_corr,
+                                                 const Points& obs_points, const vec2& pobs, const vec& pratios, const vec2& pbackground,
+                                                 const vec2& pbackground_corr, const StructureFunction& structure, int max_points,
+                                                 bool allow_extrapolation = true) {
+    b200::require(max_points >= 0, "max_points must be >= 0");
+    if(obs_points.size() == 0) return background;
+    const ivec shape = bgrid.size();
+    b200::require(shape[0] != 0 && shape[1] != 0, "Grid size cannot be zero");
+    int ny, nx, ne;
+    b200::shape_of(background, ny, nx, ne, "background");
+    b200::require(ny == shape[0] && nx == shape[1], "Input background field is not the same size as the grid");
+    return b200::unflatten(b200::run_ensi_multi(1, bgrid.to_points(), b200::flatten(bratios), b200::flatten(background), b200::flatten(background_corr), ne,
+                                                obs_points, b200::flatten(pobs), pratios, pbackground, pbackground_corr, structure, max_points,
+                                                allow_extrapolation), ny, nx, ne);
+}
+// oi_ensi_multi.cpp:630-859 (Points) and :137-224 (Grid)
+inline vec2 optimal_interpolation_ensi_multi_ebesc(const Points& bpoints, const vec& bratios, const vec2& background, const Points& obs_points,
+                                                   const vec2& pobs, const vec& pratios, const vec2& pbackground, const StructureFunction& structure,
+                                                   int max_points, bool allow_extrapolation = true) {
+    b200::require(max_points >= 0, "max_points must be >= 0");
+    if(obs_points.size() == 0) return background;
+    const int nE = b200::members_of(background);
+    return b200::unflatten(b200::run_ensi_multi(0, bpoints, bratios, b200::flatten(background), vec(), nE, obs_points, b200::flatten(pobs), pratios,
+                                                pbackground, vec2(), structure, max_points, allow_extrapolation), (int) background.size(), nE);
+}
+inline vec3 optimal_interpolation_ensi_multi_ebesc(const Grid& bgrid, const vec2& bratios, const vec3& background, const Points& obs_points,
+                                                   const vec2& pobs, const vec& pratios, const vec2& pbackground, const StructureFunction& structure,
+                                                   int max_points, bool allow_extrapolation = true) {
+    b200::require(max_points >= 0, "max_points must be >= 0");
+    if(obs_points.size() == 0) return background;
+    const ivec shape = bgrid.size();
+    b200::require(shape[0] != 0 && shape[1] != 0, "Grid size cannot be zero");
+    int ny, nx, ne;
+    b200::shape_of(background, ny, nx, ne, "background");
+    b200::require(ny == shape[0] && nx == shape[1], "Input background field is not the same size as the grid");
+    return b200::unflatten(b200::run_ensi_multi(0, bgrid.to_points(), b200::flatten(bratios), b200::flatten(background), vec(), ne, obs_points,
+                                                b200::flatten(pobs), pratios, pbackground, vec2(), structure, max_points, allow_extrapolation), ny, nx, ne);
+}
+// oi_ensi_multi.cpp:862-1311 (Points) and :226-327 (Grid)
+inline vec2 optimal_interpolation_ensi_multi_utem(const Points& bpoints, const vec& bratios, const vec2& background, const vec2& background_corr,
+                                                  const Points& obs_points, const vec& pobs, const vec& pratios, const vec2& pbackground,
+                                                  const vec2& pbackground_corr, const StructureFunction& structure, int max_points,
+                                                  bool allow_extrapolation = true) {
+    b200::require(max_points >= 0, "max_points must be >= 0");
+    if(obs_points.size() == 0) return background;
+    const int nE = b200::members_of(background);
+    return b200::unflatten(b200::run_ensi_multi(2, bpoints, bratios, b200::flatten(background), b200::flatten(background_corr), nE, obs_points, pobs,
+                                                pratios, pbackground, pbackground_corr, structure, max_points, allow_extrapolation),
+                           (int) background.size(), nE);
+}
+inline vec3 optimal_interpolation_ensi_multi_utem(const Grid& bgrid, const vec2& bratios, const vec3& background, const vec3& background_corr,
+                                                  const Points& obs_points, const vec& pobs, const vec& pratios, const vec2& pbackground,
+                                                  const vec2& pbackground_corr, const StructureFunction& structure, int max_points,
+                                                  bool allow_extrapolation = true) {
+    b200::require(max_points >= 0, "max_points must be >= 0");
+    if(obs_points.size() == 0) return background;
+    const ivec shape = bgrid.size();
+    b200::require(shape[0] != 0 && shape[1] != 0, "Grid size cannot be zero");
+    int ny, nx, ne;
+    b200::shape_of(background, ny, nx, ne, "background");
+    b200::require(ny == shape[0] && nx == shape[1], "Input background field is not the same size as the grid");
+    return b200::unflatten(b200::run_ensi_multi(2, bgrid.to_points(), b200::flatten(bratios), b200::flatten(background), b200::flatten(background_corr), ne,
+                                                obs_points, pobs, pratios, pbackground, pbackground_corr, structure, max_points, allow_extrapolation),
+                           ny, nx, ne);
+}
+// corr_points.cpp:26-131
+inline vec2 staticcorr_points(const Points& points, const Points& knots, const StructureFunction& structure, int max_points) {
+    b200::require(max_points >= 0, "max_points must be >= 0");
+    b200::require(points.get_coordinate_type() == knots.get_coordinate_type(),
+                  "Both background grid and observations points must be of same coordinate type (lat/lon or x/y)");
+    if(structure.b200_field()) throw not_implemented_exception("spatially varying structure functions in staticcorr_points");
+    const int nY = points.size(), nS = knots.size();
+    vec out((size_t) nY * nS, 0.f);
+    if(!out.empty()) b200::check(gpp_staticcorr_points_host(points.b200_handle(), knots.b200_handle(), &structure.b200_descriptor(), max_points, out.data()));
+    vec2 result(nY, vec(nS, 0.f));
+    for(int y = 0; y < nY; y++) std::copy(out.begin() + (size_t) y * nS, out.begin() + (size_t) (y + 1) * nS, result[y].begin());
+    return result;
+}
+
 // -------------------------------------------------------------------------------------------------------------------
 // Neighbourhood filters (neighbourhood.cpp:12-527)
 inline vec2 neighbourhood(const vec2& input, int halfwidth, Statistic statistic) {

@@ -367,6 +367,31 @@ unsigned long long gpp_kernel_launch_count(void);
  * the OI kernels, whose elimination runs on the fp64 CUDA cores. */
 int gpp_measure_fp64_fma_peak(double* tflops);
 
+/* ---- the "multi" EnSI variants and the static correlations between two point sets. Points overloads
+ * (the Grid overloads of the reference, oi_ensi_multi.cpp:33-327, only flatten the grid: pass a flattened-grid gpp_points).
+ * Fields are member-fastest: background* [L][nE], pobs (ebe / ebesc) and pbackground* [S][nE]. analysis is [L][nE]. */
+
+/* gridpp::optimal_interpolation_ensi_multi_ebe(Points, ...), src/api/oi_ensi_multi.cpp:329-627 */
+int gpp_optimal_interpolation_ensi_multi_ebe_host(const gpp_points* bpoints, const float* bratios, const float* background,
+                                                  const float* background_corr, int nE, const gpp_points* opoints, const float* pobs,
+                                                  const float* pratios, const float* pbackground, const float* pbackground_corr,
+                                                  const gpp_structure* structure, int max_points, int allow_extrapolation, float* analysis);
+/* gridpp::optimal_interpolation_ensi_multi_ebesc(Points, ...), src/api/oi_ensi_multi.cpp:630-859 */
+int gpp_optimal_interpolation_ensi_multi_ebesc_host(const gpp_points* bpoints, const float* bratios, const float* background, int nE,
+                                                    const gpp_points* opoints, const float* pobs, const float* pratios,
+                                                    const float* pbackground, const gpp_structure* structure, int max_points,
+                                                    int allow_extrapolation, float* analysis);
+/* gridpp::optimal_interpolation_ensi_multi_utem(Points, ...), src/api/oi_ensi_multi.cpp:862-1311. pobs is [S].
+ * *num_skipped (may be NULL) receives the number of points left at their background because rcond(Pinv) <= 0 (:1106-1110). */
+int gpp_optimal_interpolation_ensi_multi_utem_host(const gpp_points* bpoints, const float* bratios, const float* background,
+                                                   const float* background_corr, int nE, const gpp_points* opoints, const float* pobs,
+                                                   const float* pratios, const float* pbackground, const float* pbackground_corr,
+                                                   const gpp_structure* structure, int max_points, int allow_extrapolation, float* analysis,
+                                                   int* num_skipped);
+/* gridpp::staticcorr_points(points, knots, structure, max_points), src/api/corr_points.cpp:26-131. output is [L][K]. */
+int gpp_staticcorr_points_host(const gpp_points* points, const gpp_points* knots, const gpp_structure* structure, int max_points,
+                               float* output);
+
 #ifdef __cplusplus
 }
 #endif

@@ -222,6 +222,40 @@ class CpuLib:
             timing.append(sec.value)
         return out
 
+    def staticcorr_points(self, pts, knots, structure, max_points, ctype):
+        """gridpp::staticcorr_points (corr_points.cpp:26-131) -> (L, K)"""
+        bl, bo, be, bf = (_f(a).ravel() if a is not None else None for a in pts)
+        pl, po, pe, pf = (_f(a).ravel() if a is not None else None for a in knots)
+        out = np.empty((bl.size, pl.size), np.float32)
+        self._check(self._fn("staticcorr_points")(_p(bl), _p(bo), _p(be), _p(bf), bl.size, _p(pl), _p(po), _p(pe), _p(pf), pl.size, ctype,
+                                                  C.byref(structure), max_points, _p(out)))
+        return out
+
+    def ensi_multi(self, kind, bpts, bratios, background, background_corr, opts, pobs, pratios, pbackground, pbackground_corr,
+                   structure, max_points, ctype, allow_extrapolation=True):
+        """optimal_interpolation_ensi_multi_{ebe,ebesc,utem} (Points overloads, oi_ensi_multi.cpp:329-1311); kind names the variant."""
+        bl, bo, be, bf = (_f(a).ravel() if a is not None else None for a in bpts)
+        pl, po, pe, pf = (_f(a).ravel() if a is not None else None for a in opts)
+        nB, nS = bl.size, pl.size
+        bg = _f(background).reshape(nB, -1)
+        nE = bg.shape[1]
+        pbg = _f(pbackground).reshape(nS, nE)
+        bgc = _f(background_corr).reshape(nB, nE) if background_corr is not None else None
+        pbgc = _f(pbackground_corr).reshape(nS, nE) if pbackground_corr is not None else None
+        br, pr = _f(bratios).ravel(), _f(pratios).ravel()
+        out = np.empty((nB, nE), np.float32)
+        if kind == "utem":
+            obs = _f(pobs).ravel()
+            self._check(self._fn("ensi_multi_utem")(
+                _p(bl), _p(bo), _p(be), _p(bf), nB, _p(br), _p(bg), _p(bgc), nE, _p(pl), _p(po), _p(pe), _p(pf), nS, ctype, _p(obs), _p(pr),
+                _p(pbg), _p(pbgc), C.byref(structure), max_points, int(allow_extrapolation), _p(out)))
+        else:
+            obs = _f(pobs).reshape(nS, nE)
+            self._check(self._fn("ensi_multi_ebe")(
+                _p(bl), _p(bo), _p(be), _p(bf), nB, _p(br), _p(bg), _p(bgc), nE, _p(pl), _p(po), _p(pe), _p(pf), nS, ctype, _p(obs), _p(pr),
+                _p(pbg), _p(pbgc), C.byref(structure), max_points, int(allow_extrapolation), int(kind == "ebe"), _p(out)))
+        return out
+
     def optimal_interpolation_spatial(self, bpts, background, opts, pobs, pratios, pbackground, stype, sgrid, h, v, w, min_rho,
                                       max_points, ctype, allow_extrapolation=True, want_variance=False):
         """optimal_interpolation_full with <Family>Structure(Grid, h, v, w, min_rho); both checkers export it."""

@@ -1614,3 +1614,357 @@ int orc_fill_missing(const float* values, int Y, int X, float* output) {
     free(ry); free(rx);
     return 0;
 }
+
+/* ------------------------------------------------------------------ ensi_multi / staticcorr_points ---- */
+/* The observation selection shared by oi_ensi_multi.cpp:436-486,716-767,1008-1056 and corr_points.cpp:61-110: neighbours within
+ * the localization radius in the order of the radius query, those with a valid value (ok[index]) and rho > 0, cut to the
+ * max_points best (best first) when there are more. Returns lS; cand[0..lS) holds the selection. */
+static int select_observations(const pts_t* op, const cells_t* cells, const orc_structure* s, pt_t p1, const char* ok, int max_points,
+                               int** nb, int* nb_cap, cand_t** cand, int* cand_cap) {
+    float localizationRadius = structure_loc_dist(s);
+    int n0 = radius_query(op, cells, p1.x, p1.y, p1.z, localizationRadius, 1, nb, nb_cap);
+    if(n0 == 0) return 0;
+    if(n0 > *cand_cap) { *cand_cap = 2 * n0; *cand = realloc(*cand, sizeof(cand_t) * (size_t) *cand_cap); }
+    int nc = 0;
+    for(int i = 0; i < n0; i++) {
+        int index = (*nb)[i];
+        pt_t p2 = {op->x[index], op->y[index], op->z[index], op->elev[index], op->laf[index]};
+        float rho = structure_corr_background(s, p1, p2);
+        if((!ok || ok[index]) && rho > 0) { (*cand)[nc].rho = rho; (*cand)[nc].pos = i; (*cand)[nc].index = index; nc++; }
+    }
+    if(max_points > 0 && nc > max_points) { qsort(*cand, (size_t) nc, sizeof(cand_t), cmp_cand); return max_points; }
+    return nc;
+}
+
+/* corr_points.cpp:26-131: out is nY x nS, row y holds corr_background(point y, knot) for the selected knots, 0 elsewhere */
+int orc_staticcorr_points(const float* lats, const float* lons, const float* elevs, const float* lafs, int nY, const float* klats,
+                          const float* klons, const float* kelevs, const float* klafs, int nS, int type, const orc_structure* s,
+                          int max_points, float* output) {
+    if(max_points < 0) FAIL(1, "max_points must be >= 0");
+    pts_t bp, op;
+    int rc = pts_make(&bp, lats, lons, elevs, lafs, nY, type);
+    if(rc) return rc;
+    rc = pts_make(&op, klats, klons, kelevs, klafs, nS, type);
+    if(rc) { pts_free(&bp); return rc; }
+    memset(output, 0, sizeof(float) * (size_t) nY * nS);
+    cells_t cells;
+    float R0 = structure_loc_dist(s);
+    cells_build(&cells, &op, R0 > 0 ? 0.5 * R0 : 0);
+    #pragma omp parallel
+    {
+        int* nb = NULL;
+        int nb_cap = 0, cand_cap = 0;
+        cand_t* cand = NULL;
+        #pragma omp for
+        for(int y = 0; y < nY; y++) {
+            pt_t p1 = {bp.x[y], bp.y[y], bp.z[y], bp.elev[y], bp.laf[y]};
+            int lS = select_observations(&op, &cells, s, p1, NULL, max_points, &nb, &nb_cap, &cand, &cand_cap);
+            for(int i = 0; i < lS; i++) output[(size_t) y * nS + cand[i].index] = (float) (double) cand[i].rho; /* lRhos is an arma::vec */
+        }
+        free(nb);
+        free(cand);
+    }
+    cells_free(&cells);
+    pts_free(&bp);
+    pts_free(&op);
+    return 0;
+}
+
+/* members without an invalid value anywhere in the given fields (oi_ensi_multi.cpp:399-421,693-712,933-953); returns their number */
+static int valid_members(const float* a, const float* a2, int nA, const float* b, const float* b2, int nB, int nEns, int* validEns) {
+    int n = 0;
+    for(int e = 0; e < nEns; e++) {
+        int bad = 0;
+        for(int y = 0; y < nA && !bad; y++) bad = !is_valid(a[(size_t) y * nEns + e]) || (a2 && !is_valid(a2[(size_t) y * nEns + e]));
+        for(int i = 0; i < nB && !bad; i++) bad = !is_valid(b[(size_t) i * nEns + e]) || (b2 && !is_valid(b2[(size_t) i * nEns + e]));
+        if(!bad) validEns[n++] = e;
+    }
+    return n;
+}
+/* 1 / sqrt(n - 1) * (v - mean) / std with mean / std from calc_statistic over the valid members (oi_ensi_multi.cpp:427-448,
+ * 501-510): out[e] as a double; zeros when the statistics are invalid or std <= 0.0013 */
+static void normalised_perturbations(const float* row, const int* validEns, int E, double* out) {
+    float* v = malloc(sizeof(float) * (size_t) (E > 0 ? E : 1));
+    for(int e = 0; e < E; e++) v[e] = row[validEns[e]];
+    float mean, std;
+    orc_calc_statistic(v, E, MEAN, &mean);
+    orc_calc_statistic(v, E, STD, &std);
+    float default_min_std = 0.0013;
+    for(int e = 0; e < E; e++) out[e] = 0;
+    if(is_valid(mean) && is_valid(std) && std > default_min_std)
+        for(int e = 0; e < E; e++) out[e] = 1 / sqrt((double) (E - 1)) * (v[e] - mean) / std;
+    free(v);
+}
+/* oi_ensi_multi.cpp:582-609,825-852: the anti-extrapolation filter of ebe / ebesc on one member's increment */
+static double clamp_increment(double dx, double maxIncD, double minIncD) {
+    float increment = dx, maxInc = maxIncD, minInc = minIncD;
+    if(maxInc > 0 && increment > maxInc) increment = maxInc;
+    else if(maxInc < 0 && increment > 0) increment = 0;
+    else if(minInc < 0 && increment < minInc) increment = minInc;
+    else if(minInc > 0 && increment < 0) increment = 0;
+    return increment;
+}
+
+/* oi_ensi_multi.cpp:329-628 (ebe: ensemble-based correlations, with_ens != 0; background_corr / pbackground_corr given) and
+ * :630-860 (ebesc: static correlations, with_ens == 0). background nB x nEns, pobs / pbackground nS x nEns.
+ * The reference addresses the innovation matrix (lS x nValidEns) by the ORIGINAL member index (:564,:808): with an invalid member
+ * that is not the last one it writes past the matrix (Armadillo throws); here that case returns an error as well. */
+int orc_ensi_multi_ebe(const float* blats, const float* blons, const float* belevs, const float* blafs, int nB, const float* bratios,
+                       const float* background, const float* background_corr, int nEns, const float* plats, const float* plons,
+                       const float* pelevs, const float* plafs, int nS, int type, const float* pobs, const float* pratios,
+                       const float* pbackground, const float* pbackground_corr, const orc_structure* s, int max_points,
+                       int allow_extrapolation, int with_ens, float* analysis) {
+    if(max_points < 0) FAIL(1, "max_points must be >= 0");
+    pts_t bp, op;
+    int rc = pts_make(&bp, blats, blons, belevs, blafs, nB, type);
+    if(rc) return rc;
+    rc = pts_make(&op, plats, plons, pelevs, plafs, nS, type);
+    if(rc) { pts_free(&bp); return rc; }
+    memcpy(analysis, background, sizeof(float) * (size_t) nB * nEns);
+    int* validEns = malloc(sizeof(int) * (size_t) (nEns > 0 ? nEns : 1));
+    int E = (nS == 0 || nB == 0) ? 0 : valid_members(background, with_ens ? background_corr : NULL, nB, pbackground, with_ens ? pbackground_corr : NULL, nS, nEns, validEns);
+    if(E == 0) { free(validEns); pts_free(&bp); pts_free(&op); return 0; }
+    for(int e = 0; e < E; e++)
+        if(validEns[e] >= E) { free(validEns); pts_free(&bp); pts_free(&op); FAIL(2, "Mat::operator(): index out of bounds"); }
+    char* ok = malloc((size_t) nS);
+    for(int i = 0; i < nS; i++) ok[i] = is_valid(pobs[(size_t) i * nEns]) ? 1 : 0;   /* pobs[index][0], :463,:742 */
+    double* gZ = NULL;   /* :424-449, stored as float in the reference (vec2 gZ_R) */
+    if(with_ens) {
+        gZ = malloc(sizeof(double) * (size_t) nS * E);
+        for(int i = 0; i < nS; i++) {
+            normalised_perturbations(pbackground_corr + (size_t) i * nEns, validEns, E, gZ + (size_t) i * E);
+            for(int e = 0; e < E; e++) gZ[(size_t) i * E + e] = (float) gZ[(size_t) i * E + e];
+        }
+    }
+    cells_t cells;
+    float R0 = structure_loc_dist(s);
+    cells_build(&cells, &op, R0 > 0 ? 0.5 * R0 : 0);
+    int err = 0;
+    #pragma omp parallel
+    {
+        int* nb = NULL;
+        int nb_cap = 0, cand_cap = 0;
+        cand_t* cand = NULL;
+        double* XL = malloc(sizeof(double) * (size_t) E);
+        #pragma omp for schedule(dynamic, 16)
+        for(int y = 0; y < nB; y++) {
+            pt_t p1 = {bp.x[y], bp.y[y], bp.z[y], bp.elev[y], bp.laf[y]};
+            int lS = select_observations(&op, &cells, s, p1, ok, max_points, &nb, &nb_cap, &cand, &cand_cap);
+            if(lS == 0) continue;
+            if(with_ens) normalised_perturbations(background_corr + (size_t) y * nEns, validEns, E, XL);   /* lX_L, :495-510 */
+            double* A = malloc(sizeof(double) * (size_t) lS * lS);      /* lR_rr + lR_dd (ebe) / lCorr2D + lR_dd (ebesc), column-major */
+            double* Ainv = malloc(sizeof(double) * (size_t) lS * lS);
+            double* r = malloc(sizeof(double) * (size_t) lS);           /* lr_lr (ebe) / lCorr1D (ebesc) */
+            double* K = malloc(sizeof(double) * (size_t) lS);
+            for(int i = 0; i < lS; i++) {
+                int index = cand[i].index;
+                pt_t pi = {op.x[index], op.y[index], op.z[index], op.elev[index], op.laf[index]};
+                double xz = 1;
+                if(with_ens) {
+                    xz = 0;
+                    for(int e = 0; e < E; e++) xz += XL[e] * gZ[(size_t) index * E + e];
+                }
+                r[i] = (double) cand[i].rho * xz;
+                for(int j = 0; j < lS; j++) {
+                    int index_j = cand[j].index;
+                    pt_t pj = {op.x[index_j], op.y[index_j], op.z[index_j], op.elev[index_j], op.laf[index_j]};
+                    double zz = 1;
+                    if(with_ens) {
+                        zz = 0;
+                        for(int e = 0; e < E; e++) zz += gZ[(size_t) index * E + e] * gZ[(size_t) index_j * E + e];
+                    }
+                    A[i + (size_t) j * lS] = (double) structure_corr(s, pi, pj) * zz + (i == j ? (double) pratios[index] : 0.0);
+                }
+            }
+            if(!mat_inv(A, Ainv, lS)) { err = 2; free(A); free(Ainv); free(r); free(K); continue; }
+            for(int j = 0; j < lS; j++) {   /* lK = r * inv(A), :577,:820 */
+                double acc = 0;
+                for(int i = 0; i < lS; i++) acc += r[i] * Ainv[i + (size_t) j * lS];
+                K[j] = acc;
+            }
+            float std_ratios_lr = bratios[y];
+            for(int e = 0; e < E; e++) {
+                int ei = validEns[e];   /* == e, see above */
+                double acc = 0, mx = -INFINITY, mn = INFINITY;
+                for(int i = 0; i < lS; i++) {
+                    double innov = (float) (pobs[(size_t) cand[i].index * nEns + ei] - pbackground[(size_t) cand[i].index * nEns + ei]);
+                    acc += K[i] * innov;
+                    if(innov > mx) mx = innov;
+                    if(innov < mn) mn = innov;
+                }
+                double dx = std_ratios_lr * acc;
+                if(!allow_extrapolation) dx = clamp_increment(dx, mx, mn);
+                analysis[(size_t) y * nEns + ei] = background[(size_t) y * nEns + ei] + dx;
+            }
+            free(A); free(Ainv); free(r); free(K);
+        }
+        free(nb);
+        free(cand);
+        free(XL);
+    }
+    cells_free(&cells);
+    free(gZ); free(ok); free(validEns);
+    pts_free(&bp);
+    pts_free(&op);
+    if(err) FAIL(2, "inv(): matrix is singular");
+    return 0;
+}
+
+/* oi_ensi_multi.cpp:862-1311 (utem: the transform is computed from the standardised *_corr ensembles and applied to the
+ * ensemble mean / spread of background). pobs nS; background* nB x nEns; pbackground* nS x nEns. *num_skipped (may be NULL)
+ * counts the points left at their raw values because rcond(Pinv) <= 0 (:1106-1110). */
+int orc_ensi_multi_utem(const float* blats, const float* blons, const float* belevs, const float* blafs, int nB, const float* bratios,
+                        const float* background, const float* background_corr, int nEns, const float* plats, const float* plons,
+                        const float* pelevs, const float* plafs, int nS, int type, const float* pobs, const float* pratios,
+                        const float* pbackground, const float* pbackground_corr, const orc_structure* s, int max_points,
+                        int allow_extrapolation, float* analysis) {
+    if(max_points < 0) FAIL(1, "max_points must be >= 0");
+    pts_t bp, op;
+    int rc = pts_make(&bp, blats, blons, belevs, blafs, nB, type);
+    if(rc) return rc;
+    rc = pts_make(&op, plats, plons, pelevs, plafs, nS, type);
+    if(rc) { pts_free(&bp); return rc; }
+    memcpy(analysis, background, sizeof(float) * (size_t) nB * nEns);
+    int* validEns = malloc(sizeof(int) * (size_t) (nEns > 0 ? nEns : 1));
+    const int E = (nS == 0 || nB == 0) ? 0 : valid_members(background, background_corr, nB, pbackground, pbackground_corr, nS, nEns, validEns);
+    if(E == 0) { free(validEns); pts_free(&bp); pts_free(&op); return 0; }
+    const float default_min_std = 0.0013;
+    const float const_fact = 1 / sqrt((double) (E - 1));   /* :959, a float here (ebe keeps the double) */
+    float* gY = malloc(sizeof(float) * (size_t) nS * E);
+    float* gY_corr = malloc(sizeof(float) * (size_t) nS * E);
+    float* gYhat = malloc(sizeof(float) * (size_t) nS);
+    char* ok = malloc((size_t) nS);
+    float* tmp = malloc(sizeof(float) * (size_t) E);
+    for(int i = 0; i < nS; i++) {   /* :960-994 */
+        ok[i] = is_valid(pobs[i]) ? 1 : 0;
+        for(int e = 0; e < E; e++) tmp[e] = pbackground[(size_t) i * nEns + validEns[e]];
+        float mean;
+        orc_calc_statistic(tmp, E, MEAN, &mean);
+        for(int e = 0; e < E; e++) gY[(size_t) i * E + e] = is_valid(mean) ? tmp[e] - mean : 0;
+        gYhat[i] = mean;
+        for(int e = 0; e < E; e++) tmp[e] = pbackground_corr[(size_t) i * nEns + validEns[e]];
+        float mean_corr, std_corr;
+        orc_calc_statistic(tmp, E, MEAN, &mean_corr);
+        orc_calc_statistic(tmp, E, STD, &std_corr);
+        int use = is_valid(mean_corr) && is_valid(std_corr) && std_corr > default_min_std;
+        for(int e = 0; e < E; e++) gY_corr[(size_t) i * E + e] = use ? const_fact * (tmp[e] - mean_corr) / std_corr : 0;
+    }
+    free(tmp);
+    cells_t cells;
+    float R0 = structure_loc_dist(s);
+    cells_build(&cells, &op, R0 > 0 ? 0.5 * R0 : 0);
+    #pragma omp parallel
+    {
+        int* nb = NULL;
+        int nb_cap = 0, cand_cap = 0;
+        cand_t* cand = NULL;
+        double* Pinv = malloc(sizeof(double) * (size_t) E * E);
+        double* P = malloc(sizeof(double) * (size_t) E * E);
+        double* S = malloc(sizeof(double) * (size_t) E * E);
+        double* val = malloc(sizeof(double) * (size_t) E);
+        double* vec = malloc(sizeof(double) * (size_t) E * E);
+        double* W = malloc(sizeof(double) * (size_t) E * E);
+        double* w = malloc(sizeof(double) * (size_t) E);
+        double* X = malloc(sizeof(double) * (size_t) E);
+        double* X_corr = malloc(sizeof(double) * (size_t) E);
+        float* X1 = malloc(sizeof(float) * (size_t) E);
+        float* X_corr1 = malloc(sizeof(float) * (size_t) E);
+        #pragma omp for schedule(dynamic, 16)
+        for(int y = 0; y < nB; y++) {
+            pt_t p1 = {bp.x[y], bp.y[y], bp.z[y], bp.elev[y], bp.laf[y]};
+            int lS = select_observations(&op, &cells, s, p1, ok, max_points, &nb, &nb_cap, &cand, &cand_cap);
+            if(lS == 0) continue;
+            float std_ratios_lr = bratios[y];
+            double* lY = malloc(sizeof(double) * (size_t) lS * E);        /* column-major, like the Armadillo matrix */
+            double* lYc = malloc(sizeof(double) * (size_t) lS * E);
+            double* Cm = malloc(sizeof(double) * (size_t) E * lS);
+            double* dd = malloc(sizeof(double) * (size_t) lS);
+            for(int i = 0; i < lS; i++) {
+                int index = cand[i].index;
+                double rinv = (double) cand[i].rho / pratios[index];        /* :1094 */
+                for(int e = 0; e < E; e++) {
+                    lY[i + (size_t) e * lS] = gY[(size_t) index * E + e];
+                    lYc[i + (size_t) e * lS] = gY_corr[(size_t) index * E + e];
+                    Cm[e + (size_t) i * E] = lYc[i + (size_t) e * lS] * rinv;
+                }
+                dd[i] = (double) pobs[index] - (double) gYhat[index];
+            }
+            for(int a = 0; a < E; a++)
+                for(int b = 0; b < E; b++) {
+                    double acc = 0;
+                    for(int i = 0; i < lS; i++) acc += Cm[a + (size_t) i * E] * lYc[i + (size_t) b * lS];
+                    Pinv[a + (size_t) b * E] = acc + (a == b ? 1.0 : 0.0);   /* :1105 */
+                }
+            int inv_ok = mat_inv(Pinv, P, E);
+            float cond = 0;
+            if(inv_ok) { double nn = mat_norm1(Pinv, E) * mat_norm1(P, E); cond = (nn != nn || nn == 0) ? 0 : 1.0 / nn; }
+            if(inv_ok && cond > 0) {
+                for(int i = 0; i < E * E; i++) S[i] = (double) (E - 1) * P[i];
+                mat_eig_sym(S, val, vec, E);
+                for(int a = 0; a < E; a++)
+                    for(int b = 0; b < E; b++) {
+                        double acc = 0;
+                        for(int k = 0; k < E; k++) acc += vec[a + (size_t) k * E] * sqrt(val[k]) * vec[b + (size_t) k * E];
+                        W[a + (size_t) b * E] = acc;
+                    }
+                for(int a = 0; a < E; a++) {
+                    double acc = 0;
+                    for(int i = 0; i < lS; i++) {
+                        double pc = 0;
+                        for(int b = 0; b < E; b++) pc += P[a + (size_t) b * E] * Cm[b + (size_t) i * E];
+                        acc += pc * dd[i];
+                    }
+                    w[a] = acc;
+                }
+                /* :1160-1198; every member is valid here (the members were screened above) */
+                float total = 0, total_corr = 0;
+                for(int e = 0; e < E; e++) {
+                    float value = background[(size_t) y * nEns + validEns[e]], value_corr = background_corr[(size_t) y * nEns + validEns[e]];
+                    X[e] = X1[e] = value;
+                    X_corr[e] = X_corr1[e] = value_corr;
+                    total += value;
+                    total_corr += value_corr;
+                }
+                float ensMean = total / E, ensMean_corr = total_corr / E, ensStd, ensStd_corr;
+                orc_calc_statistic(X1, E, STD, &ensStd);
+                orc_calc_statistic(X_corr1, E, STD, &ensStd_corr);
+                for(int e = 0; e < E; e++) {
+                    X[e] -= ensMean;
+                    float value_corr = X_corr[e];
+                    X_corr[e] = ensStd_corr <= default_min_std ? 0 : const_fact * (value_corr - ensMean_corr) / ensStd_corr;
+                }
+                for(int a = 0; a < E; a++)
+                    for(int b = 0; b < E; b++) W[a + (size_t) b * E] = ensStd * W[a + (size_t) b * E] + std_ratios_lr * w[a];   /* :1201-1205 */
+                for(int e = 0; e < E; e++) {
+                    float tot = 0;
+                    for(int k = 0; k < E; k++) tot += X_corr[k] * W[k + (size_t) e * E];
+                    float currIncrement = tot;
+                    if(!allow_extrapolation) {
+                        double lYe = lY[e];   /* a LINEAR index into the lS x E matrix, :1266-1267 */
+                        double mx = -INFINITY, mn = INFINITY;
+                        for(int i = 0; i < lS; i++) {
+                            double v = (double) pobs[cand[i].index] - (lYe + (double) gYhat[cand[i].index]);
+                            if(v > mx) mx = v;
+                            if(v < mn) mn = v;
+                        }
+                        float maxInc = mx, minInc = mn;
+                        float memberIncrement = currIncrement - X[e];
+                        if(maxInc > 0 && memberIncrement > maxInc) currIncrement = maxInc + X[e];
+                        else if(maxInc < 0 && memberIncrement > 0) currIncrement = 0 + X[e];
+                        else if(minInc < 0 && memberIncrement < minInc) currIncrement = minInc + X[e];
+                        else if(minInc > 0 && memberIncrement < 0) currIncrement = 0 + X[e];
+                    }
+                    analysis[(size_t) y * nEns + validEns[e]] = ensMean + currIncrement;
+                }
+            }
+            free(lY); free(lYc); free(Cm); free(dd);
+        }
+        free(nb); free(cand);
+        free(Pinv); free(P); free(S); free(val); free(vec); free(W); free(w); free(X); free(X_corr); free(X1); free(X_corr1);
+    }
+    cells_free(&cells);
+    free(gY); free(gY_corr); free(gYhat); free(ok); free(validEns);
+    pts_free(&bp);
+    pts_free(&op);
+    return 0;
+}

@@ -503,3 +503,57 @@ int ref_doping_circle(const float* glats, const float* glons, const float* gelev
 }
 
 }  // extern "C"
+
+// ---- ensi_multi / staticcorr_points -------------------------------------------------------------------
+extern "C" {
+// gridpp::staticcorr_points, corr_points.cpp:26-131. output nY x nS
+int ref_staticcorr_points(const float* lats, const float* lons, const float* elevs, const float* lafs, int nY, const float* klats,
+                          const float* klons, const float* kelevs, const float* klafs, int nS, int type, const gpp_structure* sd,
+                          int max_points, float* output) {
+    REF_TRY
+    gridpp::Points p = make_points(lats, lons, elevs, lafs, nY, type);
+    gridpp::Points k = make_points(klats, klons, kelevs, klafs, nS, type);
+    gridpp::StructureFunctionPtr s = make_structure(sd);
+    gridpp::vec2 out = gridpp::staticcorr_points(p, k, *s, max_points);
+    from_vec2(out, output, nY, nS);
+    REF_CATCH
+}
+// gridpp::optimal_interpolation_ensi_multi_ebe / _ebesc (Points overloads), oi_ensi_multi.cpp:329-628 / :630-859
+int ref_ensi_multi_ebe(const float* blats, const float* blons, const float* belevs, const float* blafs, int nB, const float* bratios,
+                       const float* background, const float* background_corr, int nE, const float* plats, const float* plons,
+                       const float* pelevs, const float* plafs, int nS, int type, const float* pobs, const float* pratios,
+                       const float* pbackground, const float* pbackground_corr, const gpp_structure* sd, int max_points,
+                       int allow_extrapolation, int with_ens, float* analysis) {
+    REF_TRY
+    gridpp::Points bp = make_points(blats, blons, belevs, blafs, nB, type);
+    gridpp::Points op = make_points(plats, plons, pelevs, plafs, nS, type);
+    gridpp::StructureFunctionPtr s = make_structure(sd);
+    gridpp::vec2 bg = to_vec2(background, nB, nE), pbg = to_vec2(pbackground, nS, nE), obs = to_vec2(pobs, nS, nE);
+    gridpp::vec br = to_vec(bratios, nB), pr = to_vec(pratios, nS);
+    gridpp::vec2 out;
+    if(with_ens) {
+        gridpp::vec2 bgc = to_vec2(background_corr, nB, nE), pbgc = to_vec2(pbackground_corr, nS, nE);
+        out = gridpp::optimal_interpolation_ensi_multi_ebe(bp, br, bg, bgc, op, obs, pr, pbg, pbgc, *s, max_points, allow_extrapolation != 0);
+    }
+    else out = gridpp::optimal_interpolation_ensi_multi_ebesc(bp, br, bg, op, obs, pr, pbg, *s, max_points, allow_extrapolation != 0);
+    from_vec2(out, analysis, nB, nE);
+    REF_CATCH
+}
+// gridpp::optimal_interpolation_ensi_multi_utem (Points overload), oi_ensi_multi.cpp:862-1311
+int ref_ensi_multi_utem(const float* blats, const float* blons, const float* belevs, const float* blafs, int nB, const float* bratios,
+                        const float* background, const float* background_corr, int nE, const float* plats, const float* plons,
+                        const float* pelevs, const float* plafs, int nS, int type, const float* pobs, const float* pratios,
+                        const float* pbackground, const float* pbackground_corr, const gpp_structure* sd, int max_points,
+                        int allow_extrapolation, float* analysis) {
+    REF_TRY
+    gridpp::Points bp = make_points(blats, blons, belevs, blafs, nB, type);
+    gridpp::Points op = make_points(plats, plons, pelevs, plafs, nS, type);
+    gridpp::StructureFunctionPtr s = make_structure(sd);
+    gridpp::vec2 bg = to_vec2(background, nB, nE), pbg = to_vec2(pbackground, nS, nE);
+    gridpp::vec2 bgc = to_vec2(background_corr, nB, nE), pbgc = to_vec2(pbackground_corr, nS, nE);
+    gridpp::vec br = to_vec(bratios, nB), pr = to_vec(pratios, nS), obs = to_vec(pobs, nS);
+    gridpp::vec2 out = gridpp::optimal_interpolation_ensi_multi_utem(bp, br, bg, bgc, op, obs, pr, pbg, pbgc, *s, max_points, allow_extrapolation != 0);
+    from_vec2(out, analysis, nB, nE);
+    REF_CATCH
+}
+}

@@ -102,6 +102,8 @@ static int checks() {
     // no observations: EnSI returns the background untouched without touching the device (oi_ensi.cpp:49-51)
     vec3 ens = {{{1, 2}, {3, 4}, {5, 6}}, {{7, 8}, {9, 10}, {11, 12}}};
     EXPECT(optimal_interpolation_ensi(grid, ens, Points(vec(), vec(), vec(), vec(), Cartesian), vec(), vec(), vec2(), barnes, 5) == ens);
+    EXPECT(optimal_interpolation_ensi_multi_ebesc(grid, vec2(), ens, Points(vec(), vec(), vec(), vec(), Cartesian), vec2(), vec(), vec2(), barnes, 5) == ens);
+    EXPECT_THROW(staticcorr_points(grid.to_points(), grid.to_points(), barnes, -1), std::invalid_argument);   // corr_points.cpp:34-35
     set_omp_threads(4);
     EXPECT(get_omp_threads() == 4);
     initialize_omp();
@@ -163,6 +165,15 @@ static int run() {
         for(int e = 0; e < nE; e++) pensemble[s][e] = by_member[e][s];
     write("pensemble", pensemble);
     write("ensi", optimal_interpolation_ensi(grid, ensemble, points, obs, sigmas, pensemble, structure, max_points));
+    {   // the "multi" variants (oi_ensi_multi.cpp) and staticcorr_points (corr_points.cpp); the ensemble doubles as its own *_corr
+        vec2 pobs2((size_t) nS, vec((size_t) nE));
+        for(int s = 0; s < nS; s++)
+            for(int e = 0; e < nE; e++) pobs2[s][e] = obs[s] + 0.125f * e;
+        write("ebesc", optimal_interpolation_ensi_multi_ebesc(grid, bvariance, ensemble, points, pobs2, ratios, pensemble, structure, max_points, false));
+        write("ebe", optimal_interpolation_ensi_multi_ebe(grid, bvariance, ensemble, ensemble, points, pobs2, ratios, pensemble, pensemble, structure, max_points));
+        write("utem", optimal_interpolation_ensi_multi_utem(grid, bvariance, ensemble, ensemble, points, obs, ratios, pensemble, pensemble, structure, max_points, false));
+        write("staticcorr", staticcorr_points(Points(read_f32("qlats"), read_f32("qlons"), vec(), vec(), Cartesian), points, structure, 5));
+    }
 
     write("mean", neighbourhood(background, hw, Mean));
     write("min", neighbourhood(background, hw, Min));

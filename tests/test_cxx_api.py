@@ -89,6 +89,14 @@ def test_cxx_api_matches_mirror_and_oracle(driver, gpp, orc, tmp_path):
     assert_bit_exact(out("pensemble", (S, E)), pens, "nearest(grid, points, vec3)")
     ensi = gpp.optimal_interpolation_ensi(grid, ens, points, obs, sigmas, pens, s, mp)
     assert_bit_exact(out("ensi", (ny, nx, E)), ensi, "optimal_interpolation_ensi")
+    pobs2 = (obs[:, None] + f32(0.125) * np.arange(E, dtype=f32)[None, :]).astype(f32)
+    assert_bit_exact(out("ebesc", (ny, nx, E)), gpp.optimal_interpolation_ensi_multi_ebesc(grid, bvar, ens, points, pobs2, ratios, pens, s, mp, False),
+                     "optimal_interpolation_ensi_multi_ebesc")
+    assert_bit_exact(out("ebe", (ny, nx, E)), gpp.optimal_interpolation_ensi_multi_ebe(grid, bvar, ens, ens, points, pobs2, ratios, pens, pens, s, mp),
+                     "optimal_interpolation_ensi_multi_ebe")
+    assert_bit_exact(out("utem", (ny, nx, E)), gpp.optimal_interpolation_ensi_multi_utem(grid, bvar, ens, ens, points, obs, ratios, pens, pens, s, mp, False),
+                     "optimal_interpolation_ensi_multi_utem")
+    assert_bit_exact(out("staticcorr", (20, S)), gpp.staticcorr_points(gpp.Points(qlat, qlon, None, None, gpp.Cartesian), points, s, 5), "staticcorr_points")
     for name, stat in (("mean", gpp.Mean), ("min", gpp.Min), ("max", gpp.Max)):
         assert_bit_exact(out(name, (ny, nx)), gpp.neighbourhood(bg, hw, stat), "neighbourhood " + name)
     assert_bit_exact(out("ens_mean", (ny, nx)), gpp.neighbourhood(ens, hw, gpp.Mean), "neighbourhood(vec3)")

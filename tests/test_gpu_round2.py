@@ -372,3 +372,104 @@ def test_gridding_large_random_vs_oracle(gpp, orc):
     assert_bit_exact(gpp.count(points, grid, 2500.0), orc.count((py, px), (y, x), 2500.0, B.CARTESIAN), "count")
     assert_bit_exact(gpp.gridding_nearest(grid, points, v, 0, gpp.Max), orc.gridding((y, x), (py, px), v, 0, 0, B.MAX, B.CARTESIAN, nearest=True),
                      "gridding_nearest")
+
+
+# ------------------------------------------------------------------ ensi_multi / staticcorr_points --
+def _multi_sets(gpp, a, ctype):
+    t = gpp.Cartesian if ctype == B.CARTESIAN else gpp.Geodetic
+    return gpp.Points(a["by"], a["bx"], a["be"], a["bf"], t), gpp.Points(a["py"], a["px"], a["pe"], a["pf"], t)
+
+
+def _multi_call(gpp, kind, bp, op, a, bg, pbg, s, mp, extr):
+    if kind == "ebesc":
+        return gpp.optimal_interpolation_ensi_multi_ebesc(bp, a["bratios"], bg, op, a["pobs2"], a["pratios"], pbg, s, mp, bool(extr))
+    if kind == "ebe":
+        return gpp.optimal_interpolation_ensi_multi_ebe(bp, a["bratios"], bg, a["background_corr"], op, a["pobs2"], a["pratios"], pbg,
+                                                        a["pbackground_corr"], s, mp, bool(extr))
+    return gpp.optimal_interpolation_ensi_multi_utem(bp, a["bratios"], bg, a["background_corr"], op, a["pobs1"], a["pratios"], pbg,
+                                                     a["pbackground_corr"], s, mp, bool(extr))
+
+
+def test_ensi_multi_and_staticcorr_golden(gpp):
+    """optimal_interpolation_ensi_multi_{ebe,ebesc,utem} and staticcorr_points against the fixture written by the compiled
+    reference (tests/golden/make_golden_ensi_multi.py): Cartesian Barnes with elevation and land-area terms, Geodetic Cressman;
+    unlimited and max_points = 12; with and without the anti-extrapolation filter; two trailing invalid members.
+    staticcorr_points is pure float arithmetic: bit for bit. The analyses go through a k x k solve (elimination here, an explicit
+    inverse in the reference) or an eigen-decomposition: the 1e-5 bar of SURVEY.md 8(d). The clamp is a branch on the
+    increment, so a value within rounding of a bound may take the other branch: at most a handful of outliers are tolerated and
+    their size is bounded separately."""
+    from test_oracle import _ensi_multi_cases
+    from util import golden
+    g = golden("ensi_multi")
+    n_runs = 0
+    for tag, ctype, spec, a, runs in _ensi_multi_cases(g):
+        bp, op = _multi_sets(gpp, a, ctype)
+        s = (gpp.BarnesStructure if spec[0] == B.BARNES else gpp.CressmanStructure)(*spec[1:])
+        for mp in (0, 12):
+            assert_bit_exact(gpp.staticcorr_points(bp, op, s, mp), a["staticcorr_mp%d" % mp], "%s staticcorr_points mp=%d" % (tag, mp))
+        for key, kind, mp, extr, bg, pbg in runs:
+            what = "%s %s" % (tag, key)
+            if kind == "utem" and mp == 0 and (a["staticcorr_mp0"] != 0).sum(1).max() > 64:
+                with pytest.raises(RuntimeError, match="at most 64 observations"):   # the EnSI kernel holds at most 64 observations per point
+                    _multi_call(gpp, kind, bp, op, a, bg, pbg, s, mp, extr)
+                continue
+            got = _multi_call(gpp, kind, bp, op, a, bg, pbg, s, mp, extr)
+            want = a[key]
+            assert got.shape == want.shape and got.dtype == want.dtype
+            assert_close(got, want, 1.0, RTOL, what, allow_outliers=0 if extr else 4)
+            assert np.nanmax(np.abs(got - want)) < 1e-2, what
+            untouched = (want == bg) | np.isnan(bg)
+            assert np.array_equal(got[untouched], bg[untouched], equal_nan=True), what + ": members / points the reference leaves alone"
+            n_runs += 1
+    assert n_runs >= 24
+    # an invalid member in the middle: the reference's innovation matrix is indexed out of bounds (Armadillo throws)
+    tag, ctype, spec, a, runs = next(_ensi_multi_cases(g))
+    bp, op = _multi_sets(gpp, a, ctype)
+    bg = a["background"].copy()
+    bg[0, 2] = np.nan
+    with pytest.raises(RuntimeError):
+        gpp.optimal_interpolation_ensi_multi_ebesc(bp, a["bratios"], bg, op, a["pobs2"], a["pratios"], a["pbackground"], gpp.BarnesStructure(*spec[1:]), 12)
+    out = gpp.optimal_interpolation_ensi_multi_utem(bp, a["bratios"], bg, a["background_corr"], op, a["pobs1"], a["pratios"], a["pbackground"],
+                                                    a["pbackground_corr"], gpp.BarnesStructure(*spec[1:]), 12)
+    assert np.isnan(out[0, 2]) and np.array_equal(out[1:, 2], bg[1:, 2]) and not np.isnan(np.delete(out, 2, axis=1)).any()
+
+
+def test_ensi_multi_grid_overloads_vs_oracle(gpp, orc):
+    """The Grid overloads (oi_ensi_multi.cpp:34-327 flatten the grid) on a 60 x 70 grid against the oracle's Points form, and the
+    argument checks of the reference."""
+    rng = np.random.default_rng(5)
+    ny, nx, S, E, dx, mp = 60, 70, 120, 10, 1000.0, 15
+    y, x = np.meshgrid(np.arange(ny, dtype=f32) * dx, np.arange(nx, dtype=f32) * dx, indexing="ij")
+    py, px = rng.uniform(0, ny * dx, S).astype(f32), rng.uniform(0, nx * dx, S).astype(f32)
+    bg = (rng.standard_normal((ny, nx, E)) + 2 * np.sin(y / 9000.0)[:, :, None]).astype(f32)
+    bgc = (rng.standard_normal((ny, nx, E)) + np.cos(x / 7000.0)[:, :, None]).astype(f32)
+    pbg, pbgc = rng.standard_normal((S, E)).astype(f32), rng.standard_normal((S, E)).astype(f32)
+    pobs2 = (pbg + 0.8 + 0.3 * rng.standard_normal((S, E))).astype(f32)
+    pobs1 = pobs2[:, 0].copy()
+    pratios, bratios = rng.uniform(0.1, 0.5, S).astype(f32), rng.uniform(0.8, 1.2, (ny, nx)).astype(f32)
+    grid, points = gpp.Grid(y, x, type=gpp.Cartesian), gpp.Points(py, px, type=gpp.Cartesian)
+    s, so = gpp.BarnesStructure(7000), B.make_structure(B.BARNES, 7000.0)
+    bp, op = (y.ravel(), x.ravel(), None, None), (py, px, None, None)
+    for extr in (True, False):
+        got = gpp.optimal_interpolation_ensi_multi_ebesc(grid, bratios, bg, points, pobs2, pratios, pbg, s, mp, extr)
+        want = orc.ensi_multi("ebesc", bp, bratios, bg, None, op, pobs2, pratios, pbg, None, so, mp, B.CARTESIAN, extr)
+        assert_close(got.reshape(-1, E), want, 1.0, RTOL, "ebesc grid", allow_outliers=0 if extr else 4)
+        got = gpp.optimal_interpolation_ensi_multi_ebe(grid, bratios, bg, bgc, points, pobs2, pratios, pbg, pbgc, s, mp, extr)
+        want = orc.ensi_multi("ebe", bp, bratios, bg, bgc, op, pobs2, pratios, pbg, pbgc, so, mp, B.CARTESIAN, extr)
+        assert_close(got.reshape(-1, E), want, 1.0, RTOL, "ebe grid", allow_outliers=0 if extr else 4)
+        got = gpp.optimal_interpolation_ensi_multi_utem(grid, bratios, bg, bgc, points, pobs1, pratios, pbg, pbgc, s, mp, extr)
+        want = orc.ensi_multi("utem", bp, bratios, bg, bgc, op, pobs1, pratios, pbg, pbgc, so, mp, B.CARTESIAN, extr)
+        assert_close(got.reshape(-1, E), want, 1.0, RTOL, "utem grid", allow_outliers=0 if extr else 4)
+        assert got.shape == bg.shape and np.abs(got - bg).max() > 0.05
+    with pytest.raises(ValueError):
+        gpp.optimal_interpolation_ensi_multi_ebesc(grid, bratios, bg, points, pobs2, pratios, pbg, s, -1)
+    with pytest.raises(ValueError):
+        gpp.optimal_interpolation_ensi_multi_ebesc(grid, bratios[:-1], bg, points, pobs2, pratios, pbg, s, mp)
+    with pytest.raises(ValueError):
+        gpp.optimal_interpolation_ensi_multi_utem(grid, bratios, bg, bgc, points, pobs2, pratios, pbg, pbgc, s, mp)   # pobs must be (S,)
+    with pytest.raises(ValueError):
+        gpp.staticcorr_points(points, gpp.Points(py, px), s, 3)   # coordinate types differ
+    none = gpp.Points([], [], type=gpp.Cartesian)
+    assert np.array_equal(gpp.optimal_interpolation_ensi_multi_ebe(grid, bratios, bg, bgc, none, np.zeros((0, E), f32), [], np.zeros((0, E), f32),
+                                                                   np.zeros((0, E), f32), s, mp), bg)
+    assert gpp.staticcorr_points(points, none, s, 0).shape == (S, 0)

@@ -474,3 +474,42 @@ def test_golden_gridding(orc):
         n += 1
     assert n >= 100
     assert_bit_exact(orc.fill_missing(g["fill_missing__in"]), g["fill_missing__out"], "fill_missing")
+
+
+def _ensi_multi_cases(g):
+    """(tag, ctype, structure, arrays, [(key, kind, max_points, extrapolation, background, pbackground)]) of ensi_multi.npz"""
+    for tag, ctype in (("cart", B.CARTESIAN), ("geo", B.GEODETIC)):
+        spec = g[tag + "__structure"]
+        a = {k[len(tag) + 2:]: g[k] for k in g.files if k.startswith(tag + "__")}
+        runs = []
+        for mp in (0, 12):
+            for extr in (0, 1):
+                for kind in ("ebesc", "ebe", "utem"):
+                    runs.append(("%s_mp%d_x%d" % (kind, mp, extr), kind, mp, extr, a["background"], a["pbackground"]))
+        for kind in ("ebesc", "ebe", "utem"):
+            runs.append(("tail_" + kind, kind, 12, 0, a["tail_background"], a["tail_pbackground"]))
+        yield tag, ctype, (int(spec[0]), float(spec[1]), float(spec[2]), float(spec[3])), a, runs
+
+
+def test_golden_ensi_multi(orc):
+    """Round 2: optimal_interpolation_ensi_multi_{ebe,ebesc,utem} (oi_ensi_multi.cpp:329-1311) and staticcorr_points
+    (corr_points.cpp:26-131): the C restatement against the fixture generated from the compiled reference
+    (tests/golden/make_golden_ensi_multi.py). The restatement follows the reference's operation order, so: bit for bit."""
+    g = golden("ensi_multi")
+    for tag, ctype, spec, a, runs in _ensi_multi_cases(g):
+        s = B.make_structure(*spec)
+        bp, op = (a["by"], a["bx"], a["be"], a["bf"]), (a["py"], a["px"], a["pe"], a["pf"])
+        for mp in (0, 12):
+            assert_bit_exact(orc.staticcorr_points(bp, op, s, mp, ctype), a["staticcorr_mp%d" % mp], "%s staticcorr mp=%d" % (tag, mp))
+        for key, kind, mp, extr, bg, pbg in runs:
+            corr = kind != "ebesc"
+            got = orc.ensi_multi(kind, bp, a["bratios"], bg, a["background_corr"] if corr else None, op, a["pobs1"] if kind == "utem" else a["pobs2"],
+                                 a["pratios"], pbg, a["pbackground_corr"] if corr else None, s, mp, ctype, bool(extr))
+            assert_bit_exact(got, a[key], tag + " " + key)
+    # an invalid member that is not the last one: the reference indexes past its innovation matrix (oi_ensi_multi.cpp:557,:806)
+    tag, ctype, spec, a, runs = next(_ensi_multi_cases(g))
+    bg = a["background"].copy()
+    bg[0, 2] = np.nan
+    with pytest.raises(RuntimeError):
+        orc.ensi_multi("ebesc", (a["by"], a["bx"], a["be"], a["bf"]), a["bratios"], bg, None, (a["py"], a["px"], a["pe"], a["pf"]), a["pobs2"],
+                       a["pratios"], a["pbackground"], None, B.make_structure(*spec), 12, ctype, True)
