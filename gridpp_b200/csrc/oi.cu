@@ -53,6 +53,14 @@ struct OiWorkHeader {
     int warps_done;
 };
 constexpr size_t OI_WORK_HEADER_BYTES = 256;
+// Progress words of the units that can be shared between warps (the last OI_PROG_WORDS units of more than one tile): tiles
+// taken from the front by the owner (low half) and from the back by warps that ran out of units (high half). Zero between
+// launches.
+#ifndef OI_PROG_WORDS
+#define OI_PROG_WORDS 65536
+#endif
+constexpr int PROG_WORDS = OI_PROG_WORDS;
+constexpr size_t OI_WORK_LRU_OFFSET = OI_WORK_HEADER_BYTES + sizeof(unsigned) * (size_t) PROG_WORDS;
 
 struct OiParams {
     // background points; gz / gelev / glaf may be NULL: z = 0 (Cartesian), no elevations / land fractions (NaN)
@@ -496,7 +504,12 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 2) oi_fast_kernel(const __
     W.z = 0.0; W.dmax = 0.0; W.dmin = 0.0; W.avar = 0.0;
 
     OiWorkHeader* hdr = reinterpret_cast<OiWorkHeader*>(P.workspace);
-    LruBlock* cache = reinterpret_cast<LruBlock*>(P.workspace + OI_WORK_HEADER_BYTES) + warp_global;
+    unsigned* prog = reinterpret_cast<unsigned*>(P.workspace + OI_WORK_HEADER_BYTES);
+    LruBlock* cache = reinterpret_cast<LruBlock*>(P.workspace + OI_WORK_LRU_OFFSET) + warp_global;
+    // units [split_from, n_multi) hold more than one tile and have a progress word
+    const int n_multi = N_LEVELS > 1 ? P.plan.end[N_LEVELS - 2] : 0;
+    const int split_from = max(0, n_multi - PROG_WORDS);
+    int scan_from = split_from;   // units before this one are known to be exhausted (only moves forward)
     if(lane < LRU_ENTRIES) cache->stamp[lane] = 0;
     __syncwarp();
     const int tiles_x = P.tile_nx > 0 ? (P.tile_nx + 3) / 4 : 0;
@@ -507,7 +520,35 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 2) oi_fast_kernel(const __
     int unit = 0;
     if(lane == 0) unit = atomicAdd(&hdr->next_unit, 1);
     unit = __shfl_sync(FULL, unit, 0);
-    if(unit >= P.plan.n_units) break;
+    bool helper = false;
+    if(unit >= P.plan.n_units) {
+        // Out of units: help with the unit that has the most tiles left, taking them from its far end. A unit's cost varies
+        // several-fold with the local churn of the selection, and without this the launch ends when the slowest large
+        // unit does -- which is what a row block of a multi-GPU run, with only a few large units per warp, is timed by.
+        int my_left = 0, my_u = 0, lowest = n_multi;
+        #pragma unroll 4
+        for(int u0 = scan_from; u0 < n_multi; u0 += 32) {
+            const int u = u0 + lane;
+            if(u < n_multi) {
+                const unsigned w = __ldcg(&prog[u - split_from]);
+                int level = 0;
+                #pragma unroll
+                for(int l = 0; l < N_LEVELS - 1; l++) level += u >= P.plan.end[l];
+                const int left = (1 << (2 * (TOP_SHIFT - level))) - (int) (w & 0xffffu) - (int) (w >> 16);
+                if(left > 0) lowest = min(lowest, u);
+                if(left > my_left) { my_left = left; my_u = u; }
+            }
+        }
+        scan_from = max(scan_from, __reduce_min_sync(FULL, lowest) & ~31);   // everything before it has been taken for good
+        const int best_left = __reduce_max_sync(FULL, my_left);
+        if(best_left == 0) break;
+        // several warps usually arrive here together: spread them over the units that tie
+        const unsigned ties = __ballot_sync(FULL, my_left == best_left);
+        unsigned pick = ties;
+        for(int skip = warp_global % __popc(ties); skip > 0; skip--) pick &= pick - 1;
+        unit = __shfl_sync(FULL, my_u, __ffs(pick) - 1);
+        helper = true;
+    }
     // ---- the unit's level (size), and where it lies
     int level = 0;
     #pragma unroll
@@ -516,7 +557,17 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 2) oi_fast_kernel(const __
     const int sh = TOP_SHIFT - level;                     // the unit is (1 << sh) x (1 << sh) tiles, or 1 << 2 sh runs
     const int n_sub = 1 << (2 * sh);
     const int ucy = P.tile_nx > 0 ? local / P.plan.cols[level] : 0, ucx = local - ucy * P.plan.cols[level];
-    for(int j_run = 0; j_run < n_sub; j_run++) {
+    const bool shared_unit = unit >= split_from && unit < n_multi;
+    for(int j_seq = 0; j_seq < n_sub; j_seq++) {
+        int j_run = j_seq;
+        if(shared_unit) {
+            unsigned w = 0;
+            if(lane == 0) w = atomicAdd(&prog[unit - split_from], helper ? 0x10000u : 1u);
+            w = __shfl_sync(FULL, w, 0);
+            const int front = (int) (w & 0xffffu), back = (int) (w >> 16);
+            if(front + back >= n_sub) break;   // every tile of the unit has been taken
+            j_run = helper ? n_sub - 1 - back : front;
+        }
         // ---- the run's points (offsets into the range), and a bounding sphere
         int npts, my_it = 0;
         if(P.tile_nx > 0) {
@@ -535,7 +586,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 2) oi_fast_kernel(const __
         }
         else {
             const int run = P.plan.base[level] + (local << (2 * sh)) + j_run;
-            if(run >= n_runs) break;
+            if(run >= n_runs) continue;
             npts = min(RUN, P.count - run * RUN);
             my_it = run * RUN + lane;
         }
@@ -743,9 +794,16 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 2) oi_fast_kernel(const __
     }
     }
     // the last warp to run out of work leaves the workspace ready for the next launch (no memset between launches)
+    int last = 0;
     if(lane == 0) {
         __threadfence();
-        if(atomicAdd(&hdr->warps_done, 1) == (int) (gridDim.x * WARPS_PER_CTA) - 1) {
+        last = atomicAdd(&hdr->warps_done, 1) == (int) (gridDim.x * WARPS_PER_CTA) - 1;
+    }
+    last = __shfl_sync(FULL, last, 0);
+    if(last) {
+        for(int u = lane; u < n_multi - split_from; u += 32) prog[u] = 0u;
+        __syncwarp();
+        if(lane == 0) {
             hdr->next_unit = 0;
             hdr->warps_done = 0;
             __threadfence();
@@ -1323,7 +1381,13 @@ UnitPlan oi_plan_units(int tile_nx, int count, long long warps) {
     long long rem = tiles ? (count / tile_nx + 3) / 4 : ((long long) count + RUN - 1) / RUN;   // tile rows, or runs
     long long rows[4] = {0, 0, 0, 0};
     auto unit_rows = [&](int l) { const int sh = TOP_SHIFT - l; return (long long) (tiles ? (1 << sh) : (1 << (2 * sh))); };
-    for(int l = N_LEVELS - 1; l >= 1; l--) {
+    // The largest unit in use. Level 0 always: large units solve the fewest systems, and the spread of their costs (several-fold,
+    // with the local churn of the selection) is evened out by the warps that run out of units taking tiles from the far end of
+    // the units still in progress (oi_fast_kernel). Measured on row blocks of C3 (profiles/oi_slices.py): starting from
+    // 2 x 2-tile units instead costs 15 % more per point. GPP_OI_FIRST_LEVEL overrides it for experiments.
+    int first = 0;
+    if(const char* env = std::getenv("GPP_OI_FIRST_LEVEL")) first = std::max(0, std::min(N_LEVELS - 1, std::atoi(env)));
+    for(int l = N_LEVELS - 1; l > first; l--) {
         const int sh = TOP_SHIFT - l;
         const long long area = (warps / 2 + 1) << (2 * (sh + 1));   // tiles (runs) wanted at this level
         long long want = (area + width - 1) / width;
@@ -1333,9 +1397,7 @@ UnitPlan oi_plan_units(int tile_nx, int count, long long warps) {
         rows[l] = r;
         rem -= r;
     }
-    rows[0] = rem - rem % unit_rows(0);
-    rem -= rows[0];
-    for(int l = 1; l < N_LEVELS; l++) {   // what does not fill a unit goes to the finer levels (the finest takes single rows)
+    for(int l = first; l < N_LEVELS; l++) {   // the bulk at the first level; what does not fill a unit goes to the finer ones
         const long long r = rem - rem % unit_rows(l);
         rows[l] += r;
         rem -= r;
@@ -1355,7 +1417,7 @@ UnitPlan oi_plan_units(int tile_nx, int count, long long warps) {
     u.n_units = (int) end;
     return u;
 }
-size_t oi_workspace_bytes() { return OI_WORK_HEADER_BYTES + sizeof(LruBlock) * (size_t) sm_count() * 2 * WARPS_PER_CTA; }
+size_t oi_workspace_bytes() { return OI_WORK_LRU_OFFSET + sizeof(LruBlock) * (size_t) sm_count() * 2 * WARPS_PER_CTA; }
 
 int check_structure(const gpp_structure* s) {
     if(!s) return fail(GPP_ERR_INVALID_ARGUMENT, "structure must not be NULL");
@@ -1639,7 +1701,7 @@ int gpp_optimal_interpolation_device_ws(const gpp_points* cbp, int first, int co
         const unsigned grid = (unsigned) std::max<long long>(1, std::min<long long>(((long long) P.plan.n_units + WARPS_PER_CTA - 1) / WARPS_PER_CTA, (long long) sms * 2));
         // the launch workspace: the caller's, else one of the slots the observation state owns, else a stream-ordered
         // allocation (observation states built on the stack by other entry points have no slots)
-        const size_t need = OI_WORK_HEADER_BYTES + sizeof(LruBlock) * (size_t) grid * WARPS_PER_CTA;
+        const size_t need = OI_WORK_LRU_OFFSET + sizeof(LruBlock) * (size_t) grid * WARPS_PER_CTA;
         unsigned char* temp = nullptr;
         if(d_workspace) {
             if(workspace_bytes < need) return fail(GPP_ERR_INVALID_ARGUMENT, "workspace of %zu bytes given, %zu needed (gpp_oi_workspace_bytes)", workspace_bytes, need);
@@ -1649,7 +1711,7 @@ int gpp_optimal_interpolation_device_ws(const gpp_points* cbp, int first, int co
             P.workspace = obs->work.ptr + obs->work_slot_bytes * (obs->work_next.fetch_add(1, std::memory_order_relaxed) % OI_WORK_SLOTS);
         else {
             GPP_CUDA(cudaMallocAsync((void**) &temp, need, stream));
-            GPP_CUDA(cudaMemsetAsync(temp, 0, OI_WORK_HEADER_BYTES, stream));
+            GPP_CUDA(cudaMemsetAsync(temp, 0, OI_WORK_LRU_OFFSET, stream));
             P.workspace = temp;
         }
         if(mode == 1) oi_fast_kernel<1><<<grid, WARPS_PER_CTA * 32, smem, stream>>>(P);
