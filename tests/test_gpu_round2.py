@@ -473,3 +473,30 @@ def test_ensi_multi_grid_overloads_vs_oracle(gpp, orc):
     assert np.array_equal(gpp.optimal_interpolation_ensi_multi_ebe(grid, bratios, bg, bgc, none, np.zeros((0, E), f32), [], np.zeros((0, E), f32),
                                                                    np.zeros((0, E), f32), s, mp), bg)
     assert gpp.staticcorr_points(points, none, s, 0).shape == (S, 0)
+
+
+# ------------------------------------------------------------------ device-resident chaining --
+def test_device_resident_chain_equals_host_calls(gpp):
+    """the analysis stays in HBM and is post-processed there -- OI -> neighbourhood mean -> quantile_fast, all on
+    the current stream, no host round trip -- and equals, bit for bit, the same three calls made one by one through the host
+    API (numpy in, numpy out)."""
+    import torch
+    from gridpp_b200 import device as gd
+    rng = np.random.default_rng(11)
+    ny, nx, dx = 300, 320, 500.0
+    y, x, py, px, bg, pbg, obs, ratios = _c3_like(rng, ny, nx, dx, density=0.02)
+    grid, points, s = gpp.Grid(y, x, type=gpp.Cartesian), gpp.Points(py, px, type=gpp.Cartesian), gpp.BarnesStructure(8000)
+    thr = np.linspace(-8, 8, 17).astype(f32)
+    state = gd.ObservationState(points, obs, ratios, pbg, s)
+    d_bg = torch.from_numpy(bg.ravel()).cuda()
+    d_an = gd.optimal_interpolation(grid, d_bg, state, 25).reshape(ny, nx)
+    d_mean = gd.neighbourhood(d_an, 5, gpp.Mean)
+    d_q = gd.neighbourhood_quantile_fast(d_mean, 0.9, 7, thr)
+    torch.cuda.synchronize()
+    an = gpp.optimal_interpolation(grid, bg, points, obs, ratios, pbg, s, 25)
+    mean = gpp.neighbourhood(an, 5, gpp.Mean)
+    q = gpp.neighbourhood_quantile_fast(mean, 0.9, 7, thr)
+    assert_bit_exact(d_an.cpu().numpy(), an, "analysis")
+    assert_bit_exact(d_mean.cpu().numpy(), mean, "mean of the analysis")
+    assert_bit_exact(d_q.cpu().numpy(), q, "quantile of the mean")
+    assert np.isfinite(q).all() and np.ptp(q) > 0
