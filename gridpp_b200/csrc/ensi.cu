@@ -27,6 +27,17 @@ constexpr int ENSI_EMAX = 32;     // valid ensemble members
 constexpr int ENSI_GRAB = 32;     // consecutive points a warp takes per grab of the work counter
 constexpr int ENSI_NSLOT = 3;     // candidate buffer = 96 entries
 constexpr int ENSI_CHUNKS = 8;    // blocks of the field returned to the host while the next ones are analysed
+// Jacobi: converged when off(A)^2 <= ENSI_CONV * diag(A)^2; a rotation is skipped when apq^2 <= ENSI_SKIP * |app aqq|.
+// 1e-18: off-diagonal rms below 1e-9 of the diagonal, four orders under the 1e-5 parity bar even for a condition number of
+// 1e3 (the smallest eigenvalue of Pinv is E - 1). Measured on C5 (profiles/r2_ensi_conv.log): 1e-26 496 ms, 1e-22 472 ms,
+// 1e-18 450 ms, 1e-16 428 ms; the fields differ from the 1e-26 build by at most 2.4e-7 / 4.8e-7 / 7.2e-7 relative (the member sum
+// is accumulated in float, oi_ensi.cpp:506-512, so a last-bit change of a term shows as an ulp or two of the result).
+#ifndef ENSI_CONV
+#define ENSI_CONV 1e-18
+#endif
+#ifndef ENSI_SKIP
+#define ENSI_SKIP 1e-22
+#endif
 
 struct EnsiParams {
     const float *gx, *gy, *gz, *gelev, *glaf;
@@ -176,7 +187,7 @@ struct RegisterJacobi {
         if(lane < E) {
             const double apq = apq_s[slot];
             const double app = first ? dgl : other, aqq = first ? other : dgl;
-            if(apq * apq > 1e-30 * fabs(app * aqq)) {   // rotations that could not change anything above 1e-15 relative are skipped
+            if(apq * apq > ENSI_SKIP * fabs(app * aqq)) {
                 const double theta = (aqq - app) * (0.5 * fast_rcp(apq));
                 const double at = fabs(theta);
                 double tt;
@@ -238,7 +249,7 @@ struct RegisterJacobi {
             #pragma unroll
             for(int o = 16; o > 0; o >>= 1) { off += shfl_double(off, lane ^ o); dg += shfl_double(dg, lane ^ o); }
             if(!(off == off) || !(dg == dg) || isinf(off) || isinf(dg)) { ok = false; break; }
-            if(off <= 1e-26 * dg) break;
+            if(off <= ENSI_CONV * dg) break;
             rounds<0>(a, v, dgl, cs, apq_s, lane);
         }
         if(lane < E) {
@@ -415,7 +426,7 @@ __global__ void __launch_bounds__(ENSI_WARPS * 32, ENSI_MINB_FOR(EC)) ensi_kerne
             #pragma unroll
             for(int o = 16; o > 0; o >>= 1) { off += shfl_double(off, lane ^ o); dg += shfl_double(dg, lane ^ o); }
             if(!(off == off) || !(dg == dg) || isinf(off) || isinf(dg)) { bad = true; break; }
-            if(off <= 1e-26 * dg) break;   // off-diagonal rms below 1e-13 of the diagonal: eigenpairs exact to ~1e-13
+            if(off <= ENSI_CONV * dg) break;
             ENSI_COUNT(1, 1);
             // round-robin schedule: in round r lane l > 0 pairs (r + l) % m with (r - l) % m, lane 0 pairs m with r
             int pr = lane % m, qr = (m - lane % m) % m;
@@ -429,8 +440,8 @@ __global__ void __launch_bounds__(ENSI_WARPS * 32, ENSI_MINB_FOR(EC)) ensi_kerne
                     if(p > q) { int tmp = p; p = q; q = tmp; }
                     if(q < E) {   // (a pair with the padding index of an odd E is the identity)
                         const double apq = S.A[p * LD + q], app = S.A[p * LD + p], aqq = S.A[q * LD + q];
-                        // rotations that could not change anything above 1e-15 relative are skipped
-                        if(apq * apq > 1e-30 * fabs(app * aqq)) {
+                     
+                        if(apq * apq > ENSI_SKIP * fabs(app * aqq)) {
                             // t = sign(theta) / (|theta| + sqrt(theta^2 + 1)), theta = (aqq - app) / (2 apq); c = 1 / sqrt(t^2 + 1)
                             const double theta = (aqq - app) * (0.5 * fast_rcp(apq));
                             const double at = fabs(theta);

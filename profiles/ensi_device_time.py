@@ -37,3 +37,10 @@ ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(reps)]
 print("%s: EnSI %d x %d x %d, mp 50: %.1f ms (min %.1f) = %.2f M gridpoints/s, checksum %.6f" % (
     os.environ.get("GPP_B200_LIB", "default"), rows, n, E, sum(ms) / reps, min(ms), rows * n / min(ms) / 1e3,
     float(out.double().sum())))
+ref = "/tmp/ensi_device_time_ref_%d.pt" % rows
+if os.path.exists(ref):
+    want = torch.load(ref)
+    err = ((out.cpu() - want).abs() / want.abs().clamp(min=1.0)).max().item()
+    print("   max |diff| / max(|default|, 1) against the first run of this session: %.3e" % err)
+else:
+    torch.save(out.cpu(), ref)
