@@ -50,5 +50,56 @@ gpp.optimal_interpolation_ensi(grid, rng.normal(size=(ny, nx, E)).astype(f32), p
 idx = grid.get_nearest_neighbour(25000.0, 35000.0)
 points.get_neighbours(25000.0, 35000.0, 5000.0)
 gpp.nearest(grid, points, bg)
+# ---- round 2 kernels
+# OI with the analysis variance (cached inverse), a grid large enough for every unit size and for tile stealing
+ny2, nx2 = 96, 128
+y2, x2 = np.meshgrid(np.arange(ny2) * dx, np.arange(nx2) * dx, indexing="ij")
+bg2 = rng.normal(size=(ny2, nx2)).astype(f32)
+grid2 = gpp.Grid(y2, x2, type=gpp.Cartesian)
+gpp.optimal_interpolation_full(grid2, bg2, np.ones(bg2.shape), points, obs, ratios, pbg, np.ones(S), gpp.BarnesStructure(10000), 30)
+for _ in range(2):
+    gpp.optimal_interpolation(grid2, bg2, points, obs, ratios, pbg, gpp.BarnesStructure(10000), 30)
+# float mean kernel (hw 1, 2, 3, 5, 7 on rows that are a multiple of 4 and >= 256 wide), Std / Variance, the gather statistics
+f = rng.uniform(size=(90, 512)).astype(f32)
+for hw in (1, 2, 3, 5, 7):
+    gpp.neighbourhood(f, hw, gpp.Mean)
+    gpp.neighbourhood(f, hw, gpp.Sum)
+f[rng.uniform(size=f.shape) < 0.02] = np.nan
+for st in (gpp.Mean, gpp.Std, gpp.Variance, gpp.Median, gpp.RandomChoice):
+    gpp.neighbourhood(f, 3, st)
+gpp.neighbourhood_quantile(f, 0.3, 2)
+gpp.neighbourhood_quantile(rng.uniform(size=(20, 30, 4)).astype(f32), 0.7, 1)
+gpp.neighbourhood_brute_force(f[:30, :40], 2, gpp.Max)
+rows = rng.normal(size=(500, 13)).astype(f32)
+for st in (gpp.Mean, gpp.Min, gpp.Median, gpp.Max, gpp.Std, gpp.Variance, gpp.Sum, gpp.Count):
+    gpp.calc_statistic(rows, st)
+gpp.calc_quantile(rows, 0.9)
+gpp.interpolate(rng.uniform(size=100).astype(f32), [0.0, 0.5, 1.0], [1.0, 2.0, 4.0])
+# radius-query consumers
+vals = rng.normal(size=S).astype(f32)
+for st in (gpp.Mean, gpp.Median, gpp.Std, gpp.Count):
+    gpp.gridding(grid, points, vals, 3000.0, 1, st)
+gpp.gridding_nearest(grid, points, vals, 0, gpp.Max)
+gpp.count(points, grid, 3000.0)
+gpp.count(grid, points, 3000.0)
+gpp.distance(grid, points, 3)
+gpp.fill(grid, bg, points, np.full(S, 1500.0, f32), -1.0, False)
+fm = bg.copy()
+fm[rng.uniform(size=fm.shape) < 0.3] = np.nan
+gpp.fill_missing(fm)
+gpp.doping_circle(grid, bg, points, vals, np.full(S, 1500.0, f32))
+gpp.doping_square(grid, bg, points, vals, np.full(S, 2, np.int32))
+# ensi_multi (elimination kernel with and without the ensemble correlations), utem (EnSI kernel), staticcorr_points
+nB = ny * nx
+bgE, bgcE = rng.normal(size=(ny, nx, E)).astype(f32), rng.normal(size=(ny, nx, E)).astype(f32)
+pbE, pbcE = rng.normal(size=(S, E)).astype(f32), rng.normal(size=(S, E)).astype(f32)
+pobsE = (pbE + 0.5).astype(f32)
+br = np.ones((ny, nx), f32)
+for mp in (12, 100):
+    gpp.optimal_interpolation_ensi_multi_ebesc(grid, br, bgE, points, pobsE, ratios, pbE, gpp.BarnesStructure(6000), mp, False)
+    gpp.optimal_interpolation_ensi_multi_ebe(grid, br, bgE, bgcE, points, pobsE, ratios, pbE, pbcE, gpp.BarnesStructure(6000), mp)
+gpp.optimal_interpolation_ensi_multi_utem(grid, br, bgE, bgcE, points, obs, ratios, pbE, pbcE, gpp.BarnesStructure(6000), 40, False)
+gpp.staticcorr_points(gpp.Points(y.ravel()[:200], x.ravel()[:200], type=gpp.Cartesian), points, gpp.BarnesStructure(6000), 10)
+gpp.staticcorr_points(gpp.Points(y.ravel()[:200], x.ravel()[:200], type=gpp.Cartesian), points, gpp.CressmanStructure(6000), 0)
 gpp.synchronize()
 print("sanitize_all: done")
