@@ -370,6 +370,47 @@ def ensi_metric(gpp, gd, torch, fp64_peak=None, with_cpu=True):
     return out
 
 
+def ensi_multi_metric(gpp):
+    """SURVEY 8(f)#1 on config 5's geometry: optimal_interpolation_ensi_multi_ebesc (member-by-member increments, static
+    correlations, max_points 30) end to end through the host API, and the reference's serial loop (oi_ensi_multi.cpp:715) on a
+    row-strided sample of the same points, checked against the GPU result."""
+    w = ensi_inputs(0, ENSI_N)
+    n, E, mp = ENSI_N, ENSI_E, 30
+    grid, points = gpp.Grid(w["y"], w["x"], type=gpp.Cartesian), gpp.Points(w["py"], w["px"], type=gpp.Cartesian)
+    s = gpp.BarnesStructure(H_SCALE)
+    pobs = (w["obs"][:, None] + 0.1 * np.arange(E, dtype=np.float32)[None, :]).astype(np.float32)
+    pratios = np.full(ENSI_S, 0.25, np.float32)
+    bratios = np.ones((n, n), np.float32)
+    t = []
+    for _ in range(2):
+        t0 = time.perf_counter()
+        host = gpp.optimal_interpolation_ensi_multi_ebesc(grid, bratios, w["bg"], points, pobs, pratios, w["pbg"], s, mp, False)
+        t.append(time.perf_counter() - t0)
+    out = {"workload": "optimal_interpolation_ensi_multi_ebesc %dx%d grid, %d members, %d obs, BarnesStructure(%g), max_points %d, clamp on"
+                       % (n, n, E, ENSI_S, H_SCALE, mp),
+           "seconds_end_to_end": t[-1], "gridpoints/s": n * n / t[-1], "h2d_bytes": int(w["bg"].nbytes + bratios.nbytes), "d2h_bytes": int(w["bg"].nbytes)}
+    try:
+        B, lib, kind, threads = _cpu_lib()
+        structure = B.make_structure(B.BARNES, H_SCALE)
+
+        def run(m):
+            pick = np.arange(0, n * n, max(1, n * n // m))[:m]
+            t0 = time.perf_counter()
+            want = lib.ensi_multi("ebesc", (w["y"].ravel()[pick], w["x"].ravel()[pick], None, None), bratios.ravel()[pick], w["bg"].reshape(-1, E)[pick],
+                                  None, (w["py"], w["px"], None, None), pobs, pratios, w["pbg"], None, structure, mp, B.CARTESIAN, False)
+            return pick, want, time.perf_counter() - t0
+        pick, want, sec = run(4000)
+        m = int(min(200_000, max(4000, 4000 / sec * 15.0)))
+        pick, want, sec = run(m)
+        err = np.abs(host.reshape(-1, E)[pick] - want) / np.maximum(np.abs(want), 2.0)
+        out["cpu_baseline"] = {"value": m / sec, "unit": "gridpoints/s", "cores": 1, "kind": kind, "seconds": sec,
+                               "sample": "%d row-strided gridpoints of the same workload (Points overload; the reference's loop is serial)" % m,
+                               "gpu_vs_cpu_max_rel_err": float(err.max())}
+    except Exception as e:
+        out["cpu_baseline"] = {"error": repr(e)}
+    return out
+
+
 def ensi_sharded_metric(gpp, torch, dist, rank, world, barrier):
     """Config 5 row-sharded: every rank analyses its block of rows against the full observation set through the host API
     (grid points are independent, oi_ensi.cpp:207-554; no member is invalid here, so the mask of :187-201 needs no
@@ -636,6 +677,10 @@ def run_ours(args):
                     line["secondary"]["ensi"] = ensi_metric(gpp, gd, torch, fp64_peak)
                 except Exception as e:
                     line["secondary"]["ensi"] = {"error": repr(e)}
+                try:
+                    line["secondary"]["ensi_multi_ebesc"] = ensi_multi_metric(gpp)
+                except Exception as e:
+                    line["secondary"]["ensi_multi_ebesc"] = {"error": repr(e)}
         if halo is not None:
             line["secondary_multi_gpu"] = halo
         emit(line)

@@ -31,6 +31,8 @@ Cartesian = 1
 # gridpp::Statistic (gridpp.h:88-100)
 Mean, Min, Median, Max, Quantile, Std, Variance, Sum, Count, RandomChoice, Unknown = 0, 10, 20, 30, 40, 50, 60, 70, 80, 90, -1
 MV = float("nan")
+# gridpp::GradientType (gridpp.h:126-129)
+MinMax, LinearRegression = 0, 10
 _BARNES, _CRESSMAN, _SOAR, _TOAR, _POWERLAW, _LINEAR = range(6)
 
 
@@ -919,6 +921,59 @@ def neighbourhood(input, halfwidth, statistic):
         return _np.zeros((0, 0), _np.float32)
     out = _np.empty(field.shape, _np.float32)
     _check(_libc.gpp_neighbourhood_host(_fptr(field), field.shape[0], field.shape[1], int(halfwidth), int(statistic), _fptr(out)))
+    return out
+
+
+def neighbourhood_search(array, search_array, halfwidth, search_target_min, search_target_max, search_delta, apply_array=None):
+    """gridpp::neighbourhood_search, neighbourhood_search.cpp:7-113: the mean of `array` over the window cells whose
+    `search_array` value is inside [search_target_min, search_target_max]; failing that the value at the cell closest to that
+    range (at least search_delta away from the centre's own search value); failing that the input value."""
+    a = _farray(array, 2, "array")
+    sa = _farray(search_array, 2, "search_array")
+    if search_target_min > search_target_max:
+        raise ValueError("Search_target_min must be smaller than search_target_max")
+    if halfwidth < 0:
+        raise ValueError("halfwidth must be positive")
+    if sa.shape != a.shape:
+        raise ValueError("search_array must either be the same size as array")
+    ap = None
+    if apply_array is not None:
+        ap = _np.ascontiguousarray(apply_array, dtype=_np.int32)
+        if ap.ndim != 2:
+            raise ValueError("apply_array must have 2 dimensions")
+        if ap.shape[0] > 1 and ap.shape != a.shape:
+            raise ValueError("apply_array must either be empty or same size as array")
+        if ap.size == 0:
+            ap = None
+        elif ap.shape != a.shape:
+            raise ValueError("apply_array must either be empty or same size as array")
+    out = _np.empty(a.shape, _np.float32)
+    if a.size:
+        _check(_libc.gpp_neighbourhood_search_host(_fptr(a), _fptr(sa), a.shape[0], a.shape[1], int(halfwidth), float(search_target_min),
+                                                   float(search_target_max), float(search_delta),
+                                                   ap.ctypes.data_as(_C.POINTER(_C.c_int)) if ap is not None else None, _fptr(out)))
+    return out
+
+
+def calc_gradient(base, values, gradient_type, halfwidth, min_num=2, min_range=MV, default_gradient=0):
+    """gridpp::calc_gradient, calc_gradient.cpp:6-126: the gradient of `values` with respect to `base` in every neighbourhood, from
+    the cells with the lowest and highest base (MinMax) or by linear regression over the window (LinearRegression)."""
+    b = _farray(base, 2, "base")
+    v = _farray(values, 2, "values")
+    if halfwidth <= 0:
+        raise ValueError("Halwidth cannot be <= 0; must be positive integer")
+    if is_valid(min_range) and min_range < 0:
+        raise ValueError("min_range must be >= 0")
+    if min_num < 0:
+        raise ValueError("num_min must be >= 0")
+    if b.shape[0] == 0:
+        raise ValueError("base input has no size")
+    if b.shape != v.shape:
+        raise ValueError("base is not the same size as values")
+    out = _np.empty(b.shape, _np.float32)
+    if b.size:
+        _check(_libc.gpp_calc_gradient_host(_fptr(b), _fptr(v), b.shape[0], b.shape[1], int(gradient_type), int(halfwidth), int(min_num),
+                                            float(min_range), float(default_gradient), _fptr(out)))
     return out
 
 

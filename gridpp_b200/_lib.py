@@ -83,6 +83,8 @@ _proto("gpp_optimal_interpolation_ensi_multi_ebe_host", C.c_int, vp, fp, fp, fp,
 _proto("gpp_optimal_interpolation_ensi_multi_ebesc_host", C.c_int, vp, fp, fp, C.c_int, vp, fp, fp, fp, sp, C.c_int, C.c_int, fp)
 _proto("gpp_optimal_interpolation_ensi_multi_utem_host", C.c_int, vp, fp, fp, fp, C.c_int, vp, fp, fp, fp, fp, sp, C.c_int, C.c_int, fp, ip)
 _proto("gpp_staticcorr_points_host", C.c_int, vp, vp, sp, C.c_int, fp)
+_proto("gpp_neighbourhood_search_host", C.c_int, fp, fp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, ip, fp)
+_proto("gpp_calc_gradient_host", C.c_int, fp, fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, fp)
 _proto("gpp_neighbourhood_host", C.c_int, fp, C.c_int, C.c_int, C.c_int, C.c_int, fp)
 _proto("gpp_neighbourhood_device", C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp)
 _proto("gpp_neighbourhood_quantile_fast_host", C.c_int, fp, C.c_int, C.c_int, C.c_float, fp, C.c_int, fp, C.c_int, fp)
@@ -133,6 +135,7 @@ EXPORTS = [
     "gpp_doping_square_host", "gpp_doping_circle_host",
     "gpp_calc_statistic_host", "gpp_calc_statistic_device", "gpp_calc_quantile_host", "gpp_interpolate_host",
     "gpp_neighbourhood_brute_force_host", "gpp_neighbourhood_brute_force_device",
+    "gpp_neighbourhood_search_host", "gpp_calc_gradient_host",
     "gpp_get_neighbourhood_thresholds_host", "gpp_structure_field_create", "gpp_structure_field_destroy",
     "gpp_structure_field_lookup_host", "gpp_structure_field_localization_distance", "gpp_optimal_interpolation_spatial_host",
 ]

@@ -54,6 +54,98 @@ __global__ void interpolate_kernel(const float* __restrict__ x, long long n, con
     out[t] = y;
 }
 
+// gridpp::neighbourhood_search, neighbourhood_search.cpp:7-113: one thread per pixel walks its clipped window in the reference's
+// (row-major) order -- the float accumulation, the "first hit wins" nearest-target rule and the `counter > 0` short-cut all
+// depend on that order.
+__global__ void neighbourhood_search_kernel(const float* __restrict__ array, const float* __restrict__ search, const int* __restrict__ apply,
+                                            int ny, int nx, int hw, float tmin, float tmax, float delta, float* __restrict__ out) {
+    const long long t = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if(t >= (long long) ny * nx) return;
+    const int y = (int) (t / nx), x = (int) (t - (long long) y * nx);
+    const float here = array[t], s_here = search[t];
+    float result = here;
+    const bool skip = !is_valid(s_here) || (apply && apply[t] == 0);              // :40-50
+    if(!skip && (!apply || apply[t] == 1)) {                                     // :63
+        float nearest = NAN, nearest_value = 0.f, accum = 0.f;
+        int counter = 0;
+        for(int yy = max(0, y - hw); yy <= min(ny - 1, y + hw); yy++)
+            for(int xx = max(0, x - hw); xx <= min(nx - 1, x + hw); xx++) {
+                const float sv = search[(size_t) yy * nx + xx], av = array[(size_t) yy * nx + xx];
+                if(!is_valid(sv) || !is_valid(av)) continue;
+                if(sv >= tmin && sv <= tmax) {
+                    counter++;
+                    accum = __fadd_rn(accum, av);
+                }
+                else if(counter > 0) continue;
+                else if(fabsf(__fsub_rn(sv, s_here)) >= delta) {
+                    if(!is_valid(nearest)) { nearest = sv; nearest_value = av; }
+                    else {
+                        const float curr = fminf(fabsf(__fsub_rn(sv, tmin)), fabsf(__fsub_rn(sv, tmax)));
+                        const float best = fminf(fabsf(__fsub_rn(nearest, tmin)), fabsf(__fsub_rn(nearest, tmax)));
+                        if(curr < best) { nearest = sv; nearest_value = av; }
+                    }
+                }
+            }
+        if(counter > 0) result = __fdiv_rn(accum, (float) counter);
+        else if(is_valid(nearest)) result = nearest_value;
+    }
+    out[t] = result;
+}
+
+// gridpp::calc_gradient, MinMax branch (calc_gradient.cpp:27-75): the values at the window's lowest and highest base
+__global__ void gradient_minmax_kernel(const float* __restrict__ base, const float* __restrict__ values, int ny, int nx, int hw, int num_min,
+                                       float min_range, float default_gradient, float* __restrict__ out) {
+    const long long t = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if(t >= (long long) ny * nx) return;
+    const int y = (int) (t / nx), x = (int) (t - (long long) y * nx);
+    float cmax = NAN, cmin = NAN, vmax = 0.f, vmin = 0.f;
+    int count = 0;
+    for(int yy = max(0, y - hw); yy <= min(ny - 1, y + hw); yy++)
+        for(int xx = max(0, x - hw); xx <= min(nx - 1, x + hw); xx++) {
+            const float b = base[(size_t) yy * nx + xx], v = values[(size_t) yy * nx + xx];
+            if(!is_valid(b) || !is_valid(v)) continue;
+            if(!is_valid(cmax) || b > cmax) { cmax = b; vmax = v; }
+            if(!is_valid(cmin) || b < cmin) { cmin = b; vmin = v; }
+            count++;
+        }
+    float r = default_gradient;
+    if(count >= num_min && is_valid(cmax) && is_valid(cmin) && !(fabsf(__fsub_rn(cmax, cmin)) <= min_range))
+        r = __fdiv_rn(__fsub_rn(vmax, vmin), __fsub_rn(cmax, cmin));
+    out[t] = r;
+}
+
+// LinearRegression branch (calc_gradient.cpp:77-124): the moment fields where both inputs are valid ...
+__global__ void gradient_moments_kernel(const float* __restrict__ base, const float* __restrict__ values, long long n, float* __restrict__ base0,
+                                        float* __restrict__ values0, float* __restrict__ bb, float* __restrict__ bv, float* __restrict__ valid) {
+    const long long t = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if(t >= n) return;
+    const float b = base[t], v = values[t];
+    const bool ok = is_valid(b) && is_valid(v);
+    base0[t] = ok ? b : NAN;
+    values0[t] = ok ? v : NAN;
+    bb[t] = ok ? __fmul_rn(b, b) : NAN;      // pow(base, 2) in double, stored as float: one rounding of the exact square
+    bv[t] = ok ? __fmul_rn(b, v) : NAN;
+    valid[t] = ok ? 1.f : 0.f;
+}
+// ... and the regression slope from their neighbourhood means
+__global__ void gradient_regression_kernel(const float* __restrict__ mX, const float* __restrict__ mY, const float* __restrict__ mXX,
+                                           const float* __restrict__ mXY, const float* __restrict__ count, long long n, int num_min, float min_range,
+                                           float default_gradient, float* __restrict__ out) {
+    const long long t = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if(t >= n) return;
+    float r = default_gradient;
+    const float var = __fsub_rn(mXX[t], __fmul_rn(mX[t], mX[t]));
+    if(count[t] >= (float) num_min && is_valid(mXX[t]) && is_valid(mXY[t]) && is_valid(mX[t]) && var != 0.f) {
+        bool valid_range = true;
+        if(is_valid(min_range)) {
+            const float range = __fsqrt_rn(var);
+            valid_range = is_valid(range) && !(range < min_range);
+        }
+        if(valid_range) r = __fdiv_rn(__fsub_rn(mXY[t], __fmul_rn(mX[t], mY[t])), var);
+    }
+    out[t] = r;
+}
+
 int run_rows(const float* d_a, long long n_rows, int T, int statistic, float quantile, const float* d_q_rows, float* d_out, cudaStream_t stream,
              bool* bad_quantile) {
     return run_rows(LinearRows{d_a, T}, n_rows, statistic, quantile, d_q_rows, d_out, stream, bad_quantile);
@@ -134,6 +226,68 @@ int gpp_neighbourhood_brute_force_host(const float* input, int ny, int nx, int n
     GPP_TRY(d_in.upload(input, n * ne));
     GPP_TRY(d_out.alloc(n));
     GPP_TRY(gpp_neighbourhood_brute_force_device(d_in.ptr, ny, nx, ne, 0, ny, halfwidth, statistic, quantile, d_out.ptr, nullptr));
+    GPP_TRY(d_out.download(output, n));
+    GPP_CUDA(cudaStreamSynchronize(0));
+    return GPP_OK;
+}
+
+/* gridpp::neighbourhood_search, neighbourhood_search.cpp:7-113 */
+int gpp_neighbourhood_search_host(const float* array, const float* search_array, int ny, int nx, int halfwidth, float search_target_min,
+                                  float search_target_max, float search_delta, const int* apply_array, float* output) {
+    if(search_target_min > search_target_max)
+        return fail(GPP_ERR_INVALID_ARGUMENT, "Search_target_min must be smaller than search_target_max");   // :10-12
+    if(halfwidth < 0) return fail(GPP_ERR_INVALID_ARGUMENT, "halfwidth must be positive");                   // :13-15
+    if(ny < 0 || nx < 0) return fail(GPP_ERR_INVALID_ARGUMENT, "negative size");
+    GPP_TRY(ensure_device());
+    const size_t n = (size_t) ny * nx;
+    if(n == 0) return GPP_OK;
+    DeviceBuffer<float> d_a, d_s, d_out;
+    DeviceBuffer<int> d_apply;
+    GPP_TRY(d_a.upload(array, n));
+    GPP_TRY(d_s.upload(search_array, n));
+    if(apply_array) GPP_TRY(d_apply.upload(apply_array, n));
+    GPP_TRY(d_out.alloc(n));
+    GPP_LAUNCH(neighbourhood_search_kernel, (unsigned) ((n + 127) / 128), 128, 0, 0, d_a.ptr, d_s.ptr, apply_array ? d_apply.ptr : nullptr, ny, nx,
+               halfwidth, search_target_min, search_target_max, search_delta, d_out.ptr);
+    GPP_TRY(d_out.download(output, n));
+    GPP_CUDA(cudaStreamSynchronize(0));
+    return GPP_OK;
+}
+
+/* gridpp::calc_gradient, calc_gradient.cpp:6-126. gradient_type: GPP_GRADIENT_MINMAX (0) or GPP_GRADIENT_LINEAR_REGRESSION (10) */
+int gpp_calc_gradient_host(const float* base, const float* values, int ny, int nx, int gradient_type, int halfwidth, int num_min, float min_range,
+                           float default_gradient, float* output) {
+    if(halfwidth <= 0) return fail(GPP_ERR_INVALID_ARGUMENT, "Halwidth cannot be <= 0; must be positive integer");   // :9-10
+    if(is_valid(min_range) && min_range < 0) return fail(GPP_ERR_INVALID_ARGUMENT, "min_range must be >= 0");
+    if(num_min < 0) return fail(GPP_ERR_INVALID_ARGUMENT, "num_min must be >= 0");
+    if(ny <= 0 || nx < 0) return fail(GPP_ERR_INVALID_ARGUMENT, "base input has no size");
+    GPP_TRY(ensure_device());
+    const size_t n = (size_t) ny * nx;
+    if(n == 0) return GPP_OK;
+    const unsigned blocks = (unsigned) ((n + 127) / 128);
+    DeviceBuffer<float> d_b, d_v, d_out;
+    GPP_TRY(d_b.upload(base, n));
+    GPP_TRY(d_v.upload(values, n));
+    GPP_TRY(d_out.alloc(n));
+    if(gradient_type == GPP_GRADIENT_MINMAX) {
+        GPP_LAUNCH(gradient_minmax_kernel, blocks, 128, 0, 0, d_b.ptr, d_v.ptr, ny, nx, halfwidth, num_min, min_range, default_gradient, d_out.ptr);
+    }
+    else if(gradient_type == GPP_GRADIENT_LINEAR_REGRESSION) {
+        DeviceBuffer<float> in[5], mean[5];
+        for(int i = 0; i < 5; i++) {
+            GPP_TRY(in[i].alloc(n));
+            GPP_TRY(mean[i].alloc(n));
+        }
+        GPP_LAUNCH(gradient_moments_kernel, blocks, 128, 0, 0, d_b.ptr, d_v.ptr, (long long) n, in[0].ptr, in[1].ptr, in[2].ptr, in[3].ptr, in[4].ptr);
+        for(int i = 0; i < 5; i++)   // meanX, meanY, meanXX, meanXY (Mean) and the number of valid pairs (Sum), :98-103
+            GPP_TRY(gpp_neighbourhood_device(in[i].ptr, ny, nx, 0, ny, halfwidth, i < 4 ? GPP_MEAN : GPP_SUM, mean[i].ptr, nullptr));
+        GPP_LAUNCH(gradient_regression_kernel, blocks, 128, 0, 0, mean[0].ptr, mean[1].ptr, mean[2].ptr, mean[3].ptr, mean[4].ptr, (long long) n, num_min,
+                   min_range, default_gradient, d_out.ptr);
+    }
+    else {   // any other value: the reference returns the field of default gradients (calc_gradient.cpp:24,125)
+        std::vector<float> fill(n, default_gradient);
+        GPP_TRY(d_out.upload(fill.data(), n));
+    }
     GPP_TRY(d_out.download(output, n));
     GPP_CUDA(cudaStreamSynchronize(0));
     return GPP_OK;

@@ -35,6 +35,7 @@ static const float MV = NAN;   // missing value (reference gridpp.h:49)
 
 enum Statistic { Mean = 0, Min = 10, Median = 20, Max = 30, Quantile = 40, Std = 50, Variance = 60, Sum = 70, Count = 80, RandomChoice = 90, Unknown = -1 };
 enum CoordinateType { Geodetic = 0, Cartesian = 1 };
+enum GradientType { MinMax = 0, LinearRegression = 10 };   // reference gridpp.h:126-129
 
 class not_implemented_exception : public std::logic_error {
 public:
@@ -877,6 +878,48 @@ inline vec2 brute_force(const vec& flat, int ny, int nx, int ne, int halfwidth, 
     return unflatten(out, ny, nx);
 }
 }  // namespace b200
+// neighbourhood_search.cpp:7-113
+inline vec2 neighbourhood_search(const vec2& array, const vec2& search_array, int halfwidth, float search_target_min, float search_target_max,
+                                 float search_delta, const ivec2& apply_array = ivec2()) {
+    b200::require(search_target_min <= search_target_max, "Search_target_min must be smaller than search_target_max");
+    b200::require(halfwidth >= 0, "halfwidth must be positive");
+    int ny, nx, sy, sx;
+    b200::shape_of(array, ny, nx, "array");
+    b200::shape_of(search_array, sy, sx, "search_array");
+    b200::require(sy == ny && sx == nx, "search_array must either be the same size as array");
+    b200::require(apply_array.size() <= 1 || ((int) apply_array.size() == ny && (int) apply_array[0].size() == nx),
+                  "apply_array must either be empty or same size as array");
+    ivec apply;
+    if(!apply_array.empty()) {
+        b200::require((int) apply_array.size() == ny, "apply_array must either be empty or same size as array");
+        for(const ivec& row : apply_array) {
+            b200::require((int) row.size() == nx, "apply_array must either be empty or same size as array");
+            apply.insert(apply.end(), row.begin(), row.end());
+        }
+    }
+    vec out((size_t) ny * nx);
+    if(!out.empty())
+        b200::check(gpp_neighbourhood_search_host(b200::flatten(array).data(), b200::flatten(search_array).data(), ny, nx, halfwidth, search_target_min,
+                                                  search_target_max, search_delta, apply.empty() ? nullptr : apply.data(), out.data()));
+    return b200::unflatten(out, ny, nx);
+}
+// calc_gradient.cpp:6-126
+inline vec2 calc_gradient(const vec2& base, const vec2& values, GradientType gradient_type, int halfwidth, int min_num = 2, float min_range = MV,
+                          float default_gradient = 0) {
+    b200::require(halfwidth > 0, "Halwidth cannot be <= 0; must be positive integer");
+    b200::require(!(is_valid(min_range) && min_range < 0), "min_range must be >= 0");
+    b200::require(min_num >= 0, "num_min must be >= 0");
+    b200::require(!base.empty(), "base input has no size");
+    int ny, nx, vy, vx;
+    b200::shape_of(base, ny, nx, "base");
+    b200::shape_of(values, vy, vx, "values");
+    b200::require(vy == ny && vx == nx, "base is not the same size as values");
+    vec out((size_t) ny * nx);
+    if(!out.empty())
+        b200::check(gpp_calc_gradient_host(b200::flatten(base).data(), b200::flatten(values).data(), ny, nx, (int) gradient_type, halfwidth, min_num, min_range,
+                                           default_gradient, out.data()));
+    return b200::unflatten(out, ny, nx);
+}
 inline vec2 neighbourhood_brute_force(const vec2& input, int halfwidth, Statistic statistic) {
     int ny, nx;
     b200::shape_of(input, ny, nx, "input");

@@ -392,6 +392,17 @@ int gpp_optimal_interpolation_ensi_multi_utem_host(const gpp_points* bpoints, co
 int gpp_staticcorr_points_host(const gpp_points* points, const gpp_points* knots, const gpp_structure* structure, int max_points,
                                float* output);
 
+/* ---- the last two window filters of SURVEY.md 8(f)#4 */
+#define GPP_GRADIENT_MINMAX 0                /* gridpp::MinMax, gridpp.h:126-129 */
+#define GPP_GRADIENT_LINEAR_REGRESSION 10    /* gridpp::LinearRegression */
+/* gridpp::neighbourhood_search(array, search_array, halfwidth, min, max, delta, apply_array), src/api/neighbourhood_search.cpp:7-113.
+ * apply_array: ny x nx ints (1 = correct this point), or NULL for the reference's empty ivec2 (every point). */
+int gpp_neighbourhood_search_host(const float* array, const float* search_array, int ny, int nx, int halfwidth, float search_target_min,
+                                  float search_target_max, float search_delta, const int* apply_array, float* output);
+/* gridpp::calc_gradient(base, values, gradient_type, halfwidth, num_min, min_range, default_gradient), src/api/calc_gradient.cpp:6-126 */
+int gpp_calc_gradient_host(const float* base, const float* values, int ny, int nx, int gradient_type, int halfwidth, int num_min, float min_range,
+                           float default_gradient, float* output);
+
 #ifdef __cplusplus
 }
 #endif

@@ -283,6 +283,23 @@ class CpuLib:
             timing.append(sec.value)
         return out
 
+    def neighbourhood_search(self, array, search_array, halfwidth, tmin, tmax, delta, apply_array=None):
+        """gridpp::neighbourhood_search (neighbourhood_search.cpp:7-113)"""
+        a, s = _f(array), _f(search_array)
+        ny, nx = a.shape
+        ap = np.ascontiguousarray(apply_array, np.int32) if apply_array is not None else None
+        out = np.empty((ny, nx), np.float32)
+        self._check(self._fn("neighbourhood_search")(_p(a), _p(s), ny, nx, halfwidth, C.c_float(tmin), C.c_float(tmax), C.c_float(delta), _p(ap), _p(out)))
+        return out
+
+    def calc_gradient(self, base, values, gradient_type, halfwidth, num_min=2, min_range=float("nan"), default_gradient=0.0):
+        """gridpp::calc_gradient (calc_gradient.cpp:6-126); gradient_type 0 = MinMax, 10 = LinearRegression"""
+        b, v = _f(base), _f(values)
+        ny, nx = b.shape
+        out = np.empty((ny, nx), np.float32)
+        self._check(self._fn("calc_gradient")(_p(b), _p(v), ny, nx, gradient_type, halfwidth, num_min, C.c_float(min_range), C.c_float(default_gradient), _p(out)))
+        return out
+
     def neighbourhood_brute_force(self, field, halfwidth, statistic):
         f = _f(field)
         ny, nx = f.shape

@@ -1968,3 +1968,108 @@ int orc_ensi_multi_utem(const float* blats, const float* blons, const float* bel
     pts_free(&op);
     return 0;
 }
+
+/* ------------------------------------------------------------------ neighbourhood_search / calc_gradient ---- */
+/* neighbourhood_search.cpp:7-113. apply may be NULL (the reference's empty ivec2: every point is treated) */
+int orc_neighbourhood_search(const float* array, const float* search, int ny, int nx, int halfwidth, float tmin, float tmax, float delta,
+                             const int* apply, float* output) {
+    if(tmin > tmax) FAIL(1, "Search_target_min must be smaller than search_target_max");
+    if(halfwidth < 0) FAIL(1, "halfwidth must be positive");
+    for(int y = 0; y < ny; y++)
+        for(int x = 0; x < nx; x++) {
+            size_t o = (size_t) y * nx + x;
+            float nearest_target = NAN, accum_temp = 0;
+            int iy = 0, ix = 0, counter = 0;
+            if(!is_valid(search[o])) { output[o] = array[o]; continue; }                 /* :40-44 */
+            if(apply && apply[o] == 0) { output[o] = array[o]; continue; }               /* :46-50 (an int is always "valid") */
+            for(int yy = y - halfwidth < 0 ? 0 : y - halfwidth; yy <= (y + halfwidth > ny - 1 ? ny - 1 : y + halfwidth); yy++)
+                for(int xx = x - halfwidth < 0 ? 0 : x - halfwidth; xx <= (x + halfwidth > nx - 1 ? nx - 1 : x + halfwidth); xx++) {
+                    size_t i = (size_t) yy * nx + xx;
+                    if(!is_valid(search[i]) || !is_valid(array[i])) continue;
+                    if(!apply || apply[o] == 1) {
+                        if(search[i] >= tmin && search[i] <= tmax) { counter++; accum_temp = accum_temp + array[i]; }
+                        else if(counter > 0) continue;
+                        else if(fabsf(search[i] - search[o]) >= delta) {
+                            if(!is_valid(nearest_target)) { nearest_target = search[i]; iy = yy; ix = xx; }
+                            else {
+                                float curr = fminf(fabsf(search[i] - tmin), fabsf(search[i] - tmax));
+                                float best = fminf(fabsf(nearest_target - tmin), fabsf(nearest_target - tmax));
+                                if(curr < best) { nearest_target = search[i]; iy = yy; ix = xx; }
+                            }
+                        }
+                    }
+                }
+            if(counter > 0) output[o] = accum_temp / counter;
+            else if(is_valid(nearest_target)) output[o] = array[(size_t) iy * nx + ix];
+            else output[o] = array[o];
+        }
+    return 0;
+}
+
+/* calc_gradient.cpp:6-126. gradient_type 0 = MinMax, 10 = LinearRegression (gridpp.h:126-129) */
+int orc_calc_gradient(const float* base, const float* values, int ny, int nx, int gradient_type, int halfwidth, int num_min, float min_range,
+                      float default_gradient, float* output) {
+    if(halfwidth <= 0) FAIL(1, "Halwidth cannot be <= 0; must be positive integer");
+    if(is_valid(min_range) && min_range < 0) FAIL(1, "min_range must be >= 0");
+    if(num_min < 0) FAIL(1, "num_min must be >= 0");
+    if(ny == 0) FAIL(1, "base input has no size");
+    size_t n = (size_t) ny * nx;
+    for(size_t i = 0; i < n; i++) output[i] = default_gradient;
+    if(gradient_type == 0) {
+        for(int y = 0; y < ny; y++)
+            for(int x = 0; x < nx; x++) {
+                float current_max = NAN, current_min = NAN;
+                size_t imax = 0, imin = 0;
+                int count = 0;
+                for(int yy = y - halfwidth < 0 ? 0 : y - halfwidth; yy <= (y + halfwidth > ny - 1 ? ny - 1 : y + halfwidth); yy++)
+                    for(int xx = x - halfwidth < 0 ? 0 : x - halfwidth; xx <= (x + halfwidth > nx - 1 ? nx - 1 : x + halfwidth); xx++) {
+                        size_t i = (size_t) yy * nx + xx;
+                        float current_base = base[i];
+                        if(!is_valid(current_base) || !is_valid(values[i])) continue;
+                        if(!is_valid(current_max) || current_base > current_max) { current_max = current_base; imax = i; }
+                        if(!is_valid(current_min) || current_base < current_min) { current_min = current_base; imin = i; }
+                        count++;
+                    }
+                size_t o = (size_t) y * nx + x;
+                if(count < num_min) output[o] = default_gradient;
+                else if(!is_valid(current_max) || !is_valid(current_min)) output[o] = default_gradient;
+                else if(fabsf(current_max - current_min) <= min_range) output[o] = default_gradient;   /* abs(float): the float overload */
+                else {
+                    float diffBase = current_max - current_min;
+                    float diffValues = values[imax] - values[imin];
+                    output[o] = diffValues / diffBase;
+                }
+            }
+    }
+    else if(gradient_type == 10) {
+        float* f[5];
+        float* m[5];
+        for(int k = 0; k < 5; k++) { f[k] = malloc(sizeof(float) * n); m[k] = malloc(sizeof(float) * n); }
+        for(size_t i = 0; i < n; i++) {
+            int ok = is_valid(base[i]) && is_valid(values[i]);
+            f[0][i] = ok ? base[i] : NAN;
+            f[1][i] = ok ? values[i] : NAN;
+            f[2][i] = ok ? (float) pow(base[i], 2) : NAN;
+            f[3][i] = ok ? base[i] * values[i] : NAN;
+            f[4][i] = ok ? 1 : 0;
+        }
+        int rc = 0;
+        for(int k = 0; k < 5 && rc == 0; k++) rc = orc_neighbourhood(f[k], ny, nx, halfwidth, k < 4 ? MEAN : SUM, m[k], NULL);
+        for(size_t i = 0; i < n && rc == 0; i++) {
+            float meanX = m[0][i], meanY = m[1][i], meanXX = m[2][i], meanXY = m[3][i], count = m[4][i];
+            output[i] = default_gradient;
+            if(count >= num_min && is_valid(meanXX) && is_valid(meanXY) && is_valid(meanX) && meanXX - meanX * meanX != 0) {
+                int valid_range = 1;
+                if(is_valid(min_range)) {
+                    float range = sqrtf(meanXX - meanX * meanX);
+                    if(!is_valid(range)) valid_range = 0;
+                    else if(range < min_range) valid_range = 0;
+                }
+                if(valid_range) output[i] = (meanXY - meanX * meanY) / (meanXX - meanX * meanX);
+            }
+        }
+        for(int k = 0; k < 5; k++) { free(f[k]); free(m[k]); }
+        return rc;
+    }
+    return 0;
+}

@@ -557,3 +557,31 @@ int ref_ensi_multi_utem(const float* blats, const float* blons, const float* bel
     REF_CATCH
 }
 }
+
+// ---- neighbourhood_search / calc_gradient -------------------------------------------------------------
+extern "C" {
+// gridpp::neighbourhood_search, neighbourhood_search.cpp:7-113; apply == NULL -> the default empty ivec2
+int ref_neighbourhood_search(const float* array, const float* search, int ny, int nx, int halfwidth, float tmin, float tmax, float delta,
+                             const int* apply, float* output) {
+    REF_TRY
+    gridpp::vec2 a = to_vec2(array, ny, nx), s = to_vec2(search, ny, nx);
+    gridpp::ivec2 ap;
+    if(apply) {
+        ap.assign(ny, gridpp::ivec(nx));
+        for(int y = 0; y < ny; y++)
+            for(int x = 0; x < nx; x++) ap[y][x] = apply[(size_t) y * nx + x];
+    }
+    gridpp::vec2 out = gridpp::neighbourhood_search(a, s, halfwidth, tmin, tmax, delta, ap);
+    from_vec2(out, output, ny, nx);
+    REF_CATCH
+}
+// gridpp::calc_gradient, calc_gradient.cpp:6-126
+int ref_calc_gradient(const float* base, const float* values, int ny, int nx, int gradient_type, int halfwidth, int num_min, float min_range,
+                      float default_gradient, float* output) {
+    REF_TRY
+    gridpp::vec2 b = to_vec2(base, ny, nx), v = to_vec2(values, ny, nx);
+    gridpp::vec2 out = gridpp::calc_gradient(b, v, (gridpp::GradientType) gradient_type, halfwidth, num_min, min_range, default_gradient);
+    from_vec2(out, output, ny, nx);
+    REF_CATCH
+}
+}

@@ -104,6 +104,8 @@ static int checks() {
     EXPECT(optimal_interpolation_ensi(grid, ens, Points(vec(), vec(), vec(), vec(), Cartesian), vec(), vec(), vec2(), barnes, 5) == ens);
     EXPECT(optimal_interpolation_ensi_multi_ebesc(grid, vec2(), ens, Points(vec(), vec(), vec(), vec(), Cartesian), vec2(), vec(), vec2(), barnes, 5) == ens);
     EXPECT_THROW(staticcorr_points(grid.to_points(), grid.to_points(), barnes, -1), std::invalid_argument);   // corr_points.cpp:34-35
+    EXPECT_THROW(neighbourhood_search(field, field, 1, 2.f, 1.f, 0.f), std::invalid_argument);   // neighbourhood_search.cpp:10-12
+    EXPECT_THROW(calc_gradient(field, field, MinMax, 0), std::invalid_argument);                 // calc_gradient.cpp:9-10
     set_omp_threads(4);
     EXPECT(get_omp_threads() == 4);
     initialize_omp();
@@ -193,6 +195,9 @@ static int run() {
     write("doping_circle", doping_circle(grid, background, points, obs, vec((size_t) nS, radius / 3), 100.f));
     write("doping_square", doping_square(grid, background, points, obs, ivec((size_t) nS, 1)));
     // statistics family (util.cpp:19-215,377-431; neighbourhood.cpp:211-238,528-539)
+    write("search", neighbourhood_search(background, bvariance, 2, 1.5f, 2.f, 0.2f));
+    write("gradient_minmax", calc_gradient(bvariance, background, MinMax, 2, 3, 0.1f, -1.f));
+    write("gradient_regression", calc_gradient(bvariance, background, LinearRegression, 2));
     write("nbh_std", neighbourhood(background, hw, Std));
     write("nbh_median", neighbourhood(background, hw, Median));
     write("nbh_quantile", neighbourhood_quantile(background, quantile, hw));

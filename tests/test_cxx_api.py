@@ -89,6 +89,9 @@ def test_cxx_api_matches_mirror_and_oracle(driver, gpp, orc, tmp_path):
     assert_bit_exact(out("pensemble", (S, E)), pens, "nearest(grid, points, vec3)")
     ensi = gpp.optimal_interpolation_ensi(grid, ens, points, obs, sigmas, pens, s, mp)
     assert_bit_exact(out("ensi", (ny, nx, E)), ensi, "optimal_interpolation_ensi")
+    assert_bit_exact(out("search", (ny, nx)), gpp.neighbourhood_search(bg, bvar, 2, 1.5, 2.0, 0.2), "neighbourhood_search")
+    assert_bit_exact(out("gradient_minmax", (ny, nx)), gpp.calc_gradient(bvar, bg, gpp.MinMax, 2, 3, 0.1, -1.0), "calc_gradient MinMax")
+    assert_bit_exact(out("gradient_regression", (ny, nx)), gpp.calc_gradient(bvar, bg, gpp.LinearRegression, 2), "calc_gradient LinearRegression")
     pobs2 = (obs[:, None] + f32(0.125) * np.arange(E, dtype=f32)[None, :]).astype(f32)
     assert_bit_exact(out("ebesc", (ny, nx, E)), gpp.optimal_interpolation_ensi_multi_ebesc(grid, bvar, ens, points, pobs2, ratios, pens, s, mp, False),
                      "optimal_interpolation_ensi_multi_ebesc")

@@ -500,3 +500,44 @@ def test_device_resident_chain_equals_host_calls(gpp):
     assert_bit_exact(d_mean.cpu().numpy(), mean, "mean of the analysis")
     assert_bit_exact(d_q.cpu().numpy(), q, "quantile of the mean")
     assert np.isfinite(q).all() and np.ptp(q) > 0
+
+
+# ------------------------------------------------------------------ neighbourhood_search / calc_gradient --
+def test_window_filters_golden(gpp, orc):
+    """neighbourhood_search and calc_gradient against the fixture written by the compiled reference
+    (tests/golden/make_golden_window_filters.py). neighbourhood_search and the MinMax gradient walk the window in the reference's
+    order with the reference's float operations: bit for bit. The LinearRegression gradient is built on five neighbourhood means
+    (within 1e-6 of the reference's double summed-area tables) and divides a difference of moments by a variance, which amplifies
+    that by |mean|^2 / variance: compared at 1e-5 of the gradient's scale where the variance is not dominated by cancellation,
+    and on a larger random case against the oracle."""
+    from util import golden
+    g = golden("window_filters")
+    a, s, ap = g["search__array"], g["search__search"], g["search__apply"]
+    for i, (hw, lo, hi, delta) in enumerate(g["search__cases"]):
+        assert_bit_exact(gpp.neighbourhood_search(a, s, int(hw), lo, hi, delta), g["search__case%d" % i], "search %d" % i)
+        assert_bit_exact(gpp.neighbourhood_search(a, s, int(hw), lo, hi, delta, ap), g["search__case%d_apply" % i], "search %d + apply" % i)
+    base, values = g["gradient__base"], g["gradient__values"]
+    for i, (hw, num_min, min_range, default) in enumerate(g["gradient__cases"]):
+        hw, num_min = int(hw), int(num_min)
+        assert_bit_exact(gpp.calc_gradient(base, values, gpp.MinMax, hw, num_min, min_range, default), g["gradient__minmax_case%d" % i], "MinMax %d" % i)
+        got = gpp.calc_gradient(base, values, gpp.LinearRegression, hw, num_min, min_range, default)
+        want = g["gradient__regression_case%d" % i]
+        # the elevations are ~300 +- 200: variance / mean^2 ~ 0.4, no cancellation to speak of
+        decided_same = (got == default) == (want == default)
+        assert decided_same.mean() > 0.999, "regression %d: default-gradient decisions differ at %d points" % (i, (~decided_same).sum())
+        assert_close(got[decided_same], want[decided_same], 0.01, 1e-4, "regression %d" % i)
+    # a larger random case against the oracle
+    rng = np.random.default_rng(3)
+    b = rng.standard_normal((300, 280)).astype(f32)
+    v = (2.5 * b + 0.3 * rng.standard_normal(b.shape)).astype(f32)
+    b[rng.uniform(size=b.shape) < 0.02] = np.nan
+    assert_bit_exact(gpp.calc_gradient(b, v, gpp.MinMax, 3), orc.calc_gradient(b, v, 0, 3), "MinMax random")
+    assert_close(gpp.calc_gradient(b, v, gpp.LinearRegression, 3), orc.calc_gradient(b, v, 10, 3), 1.0, 1e-4, "regression random")
+    sa = rng.uniform(0, 1, b.shape).astype(f32)
+    assert_bit_exact(gpp.neighbourhood_search(v, sa, 2, 0.9, 1.0, 0.05), orc.neighbourhood_search(v, sa, 2, 0.9, 1.0, 0.05), "search random")
+    with pytest.raises(ValueError):
+        gpp.neighbourhood_search(v, sa, 2, 1.0, 0.9, 0.05)
+    with pytest.raises(ValueError):
+        gpp.neighbourhood_search(v, sa[:-1], 2, 0.9, 1.0, 0.05)
+    with pytest.raises(ValueError):
+        gpp.calc_gradient(b, v, gpp.MinMax, 0)

@@ -513,3 +513,23 @@ def test_golden_ensi_multi(orc):
     with pytest.raises(RuntimeError):
         orc.ensi_multi("ebesc", (a["by"], a["bx"], a["be"], a["bf"]), a["bratios"], bg, None, (a["py"], a["px"], a["pe"], a["pf"]), a["pobs2"],
                        a["pratios"], a["pbackground"], None, B.make_structure(*spec), 12, ctype, True)
+
+
+def test_golden_window_filters(orc):
+    """Round 2: neighbourhood_search (neighbourhood_search.cpp:7-113) and calc_gradient (calc_gradient.cpp:6-126) restated
+    in C against the fixture generated from the compiled reference (tests/golden/make_golden_window_filters.py): bit for bit."""
+    g = golden("window_filters")
+    for i, (hw, lo, hi, delta) in enumerate(g["search__cases"]):
+        hw = int(hw)
+        assert_bit_exact(orc.neighbourhood_search(g["search__array"], g["search__search"], hw, lo, hi, delta), g["search__case%d" % i], "search %d" % i)
+        assert_bit_exact(orc.neighbourhood_search(g["search__array"], g["search__search"], hw, lo, hi, delta, g["search__apply"]),
+                         g["search__case%d_apply" % i], "search %d with apply_array" % i)
+    for i, (hw, num_min, min_range, default) in enumerate(g["gradient__cases"]):
+        hw, num_min = int(hw), int(num_min)
+        for name, gt in (("minmax", 0), ("regression", 10)):
+            assert_bit_exact(orc.calc_gradient(g["gradient__base"], g["gradient__values"], gt, hw, num_min, min_range, default),
+                             g["gradient__%s_case%d" % (name, i)], "gradient %s %d" % (name, i))
+    with pytest.raises(ValueError):
+        orc.neighbourhood_search(g["search__array"], g["search__search"], 1, 2.0, 1.0, 0.0)
+    with pytest.raises(ValueError):
+        orc.calc_gradient(g["gradient__base"], g["gradient__values"], 0, 0)
