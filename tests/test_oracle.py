@@ -533,3 +533,76 @@ def test_golden_window_filters(orc):
         orc.neighbourhood_search(g["search__array"], g["search__search"], 1, 2.0, 1.0, 0.0)
     with pytest.raises(ValueError):
         orc.calc_gradient(g["gradient__base"], g["gradient__values"], 0, 0)
+
+
+def test_ensi_oracle_against_lapack(orc):
+    """The EnSI numerics of both checkers rest on hand-written dense routines (Gauss-Jordan `inv`, exact 1-norm `rcond`, cyclic
+    Jacobi `eig_sym`: oracle/shims/armadillo and oracle/gridpp_oracle.c). This restates oi_ensi.cpp:282-554 per grid point with
+    LAPACK underneath (numpy.linalg.inv -> dgetrf/dgetri, numpy.linalg.eigh -> dsyevd) on the golden case and compares with the
+    oracle: the selection and rho come from the oracle's own structure function, the dense algebra does not. 1e-6 relative."""
+    g = golden("ensi_c5_density")
+    s = oracle_structure(parse_spec(g["structure"]))
+    y, x, bg = g["y"].ravel(), g["x"].ravel(), g["background"].reshape(-1, g["background"].shape[-1])
+    py, px, pobs, psig, pbg = g["py"], g["px"], g["pobs"], g["psigmas"], g["pbackground"]
+    nB, E, S = bg.shape[0], bg.shape[1], py.size
+    R = orc.structure_localization_distance(s)
+    nanv = np.full(S, np.nan, f32)
+    obs_pts = np.stack([px, py, np.zeros(S, f32), nanv, nanv], axis=1)
+    # :163-178 (all members valid in the fixture); float accumulation in member order, as calc_statistic does
+    gYhat = np.array([np.float32(sum((np.float32(v) for v in row), np.float32(0))) / np.float32(E) for row in pbg], f32)
+    gY = (pbg - gYhat[:, None]).astype(f32)
+    for name in ("mp20", "mp20_clamp", "unlimited"):
+        mp, extr = (int(v) for v in g[name + "__args"])
+        want = g[name + "__analysis"].reshape(nB, E)
+        got = bg.copy()
+        for b in range(nB):
+            d = np.sqrt((px - x[b]) * (px - x[b]) + (py - y[b]) * (py - y[b]), dtype=f32)
+            near = np.nonzero(d <= R)[0]
+            if near.size == 0:
+                continue
+            p1 = np.tile(np.array([x[b], y[b], 0, np.nan, np.nan], f32), (near.size, 1))
+            rho = orc.structure_corr(s, p1, obs_pts[near], background=True)
+            keep = (rho > 0) & np.isfinite(pobs[near])                          # :232-236: only pobs validity is tested
+            idx, rho = near[keep], rho[keep]
+            if mp > 0 and idx.size > mp:                                       # :244-255: best first
+                order = np.lexsort((idx, -rho.astype(np.float64)))[:mp]
+                idx, rho = idx[order], rho[order]
+            if idx.size == 0:
+                continue
+            lY = gY[idx].astype(np.float64)                                    # lS x E
+            rinv = rho.astype(np.float64) / (psig[idx] * psig[idx]).astype(np.float64)
+            Cm = lY.T * rinv[None, :]
+            Pinv = Cm @ lY + float(f32(E - 1)) * np.eye(E)
+            if 1.0 / np.linalg.cond(Pinv, 1) <= 0:
+                continue
+            P = np.linalg.inv(Pinv)
+            val, vec = np.linalg.eigh((E - 1) * P)
+            W = (vec * np.sqrt(val)[None, :]) @ vec.T
+            w = P @ Cm @ (pobs[idx].astype(np.float64) - gYhat[idx].astype(np.float64))
+            W = W + w[:, None]
+            total = np.float32(0)
+            for v in bg[b]:
+                total = np.float32(total + v)
+            ens_mean = np.float32(total / np.float32(E))
+            X = bg[b].astype(np.float64) - float(ens_mean)
+            for e in range(E):
+                tot = np.float32(0)
+                for k in range(E):
+                    tot = np.float32(float(tot) + X[k] * W[k, e])
+                inc = tot
+                if not extr:
+                    lYe = lY.ravel(order="F")[e]                                   # the linear index lY[e] of :523-524
+                    dd = pobs[idx].astype(np.float64) - (lYe + gYhat[idx].astype(np.float64))
+                    max_inc, min_inc = np.float32(dd.max()), np.float32(dd.min())
+                    member = np.float32(float(inc) - X[e])
+                    if max_inc > 0 and member > max_inc:
+                        inc = np.float32(float(max_inc) + X[e])
+                    elif max_inc < 0 and member > 0:
+                        inc = np.float32(X[e])
+                    elif min_inc < 0 and member < min_inc:
+                        inc = np.float32(float(min_inc) + X[e])
+                    elif min_inc > 0 and member < 0:
+                        inc = np.float32(X[e])
+                got[b, e] = np.float32(ens_mean + inc)
+        assert np.abs(want - bg).max() > 0.05
+        assert_close(got, want, 1.0, 1e-6, "LAPACK restatement, " + name)
