@@ -1471,35 +1471,47 @@ int pipelined_download(const std::vector<size_t>& bounds, const std::function<in
     PinnedStage& g_stage = stage_of_current_device();
     std::lock_guard<std::mutex> guard(g_stage.lock);
     GPP_TRY(g_stage.reserve(largest));
-    cudaStream_t copy_stream;
-    GPP_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
-    std::vector<cudaEvent_t> produced(n_chunks), copied(n_chunks);
+    // streams and events are released on every path out of this function
+    struct Stream {
+        cudaStream_t s = nullptr;
+        ~Stream() { if(s) cudaStreamDestroy(s); }
+        int create() { GPP_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)); return GPP_OK; }
+    };
+    struct Event {
+        cudaEvent_t e = nullptr;
+        ~Event() { if(e) cudaEventDestroy(e); }
+        int create() { GPP_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); return GPP_OK; }
+    };
+    Stream copy, comp[2];
+    GPP_TRY(copy.create());
+    const cudaStream_t copy_stream = copy.s;
+    std::vector<Event> produced(n_chunks), copied(n_chunks);
     for(int c = 0; c < n_chunks; c++) {
-        cudaEventCreateWithFlags(&produced[c], cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&copied[c], cudaEventDisableTiming);
+        GPP_TRY(produced[c].create());
+        GPP_TRY(copied[c].create());
     }
     int rc = GPP_OK;
     cudaStream_t compute[2] = {0, 0};
     if(overlap_blocks) {
-        cudaEvent_t ready;
-        cudaEventCreateWithFlags(&ready, cudaEventDisableTiming);
-        cudaEventRecord(ready, 0);
+        Event ready;
+        GPP_TRY(ready.create());
+        GPP_CUDA(cudaEventRecord(ready.e, 0));
         for(int i = 0; i < 2; i++) {
-            GPP_CUDA(cudaStreamCreateWithFlags(&compute[i], cudaStreamNonBlocking));
-            cudaStreamWaitEvent(compute[i], ready, 0);
+            GPP_TRY(comp[i].create());
+            compute[i] = comp[i].s;
+            GPP_CUDA(cudaStreamWaitEvent(compute[i], ready.e, 0));
         }
-        cudaEventDestroy(ready);
     }
     for(int c = 0; c < n_chunks && rc == GPP_OK; c++) {
         rc = launch(c, compute[c & 1]);
-        cudaEventRecord(produced[c], compute[c & 1]);
+        if(rc == GPP_OK && cudaEventRecord(produced[c].e, compute[c & 1]) != cudaSuccess) rc = fail(GPP_ERR_CUDA, "cudaEventRecord failed");
     }
     // The caller's array is usually fresh (untouched pages): fault it in now, while the device is busy with block 0,
     // instead of during the copies at the end (first-touch runs at 2-4 GB/s).
     if(rc == GPP_OK)
         for(size_t i = bounds[0]; i < bounds[n_chunks]; i += 1024) reinterpret_cast<volatile float*>(host_out)[i] = 0.f;
     auto finish = [&](int c) {   // block c: wait for its copy, move it to the caller's array
-        if(cudaEventSynchronize(copied[c]) != cudaSuccess) return fail(GPP_ERR_CUDA, "CUDA error while downloading a result block");
+        if(cudaEventSynchronize(copied[c].e) != cudaSuccess) return fail(GPP_ERR_CUDA, "CUDA error while downloading a result block");
         // a few threads: one core copies ~8 GB/s, and the copy of the last block is not hidden behind any kernel
         const size_t n = bounds[c + 1] - bounds[c];
         const int pieces = n >= (1u << 20) ? 4 : 1;
@@ -1513,19 +1525,16 @@ int pipelined_download(const std::vector<size_t>& bounds, const std::function<in
     for(int c = 0; c < n_chunks && rc == GPP_OK; c++) {
         if(c >= 2) rc = finish(c - 2);               // frees slot c & 1
         if(rc != GPP_OK) break;
-        cudaStreamWaitEvent(copy_stream, produced[c], 0);
-        cudaMemcpyAsync(g_stage.slot[c & 1], d_out + bounds[c], sizeof(float) * (bounds[c + 1] - bounds[c]), cudaMemcpyDeviceToHost, copy_stream);
-        cudaEventRecord(copied[c], copy_stream);
+        if(cudaStreamWaitEvent(copy_stream, produced[c].e, 0) != cudaSuccess ||
+           cudaMemcpyAsync(g_stage.slot[c & 1], d_out + bounds[c], sizeof(float) * (bounds[c + 1] - bounds[c]), cudaMemcpyDeviceToHost, copy_stream) != cudaSuccess ||
+           cudaEventRecord(copied[c].e, copy_stream) != cudaSuccess)
+            rc = fail(GPP_ERR_CUDA, "CUDA error while queueing the download of a result block");
     }
     for(int c = std::max(0, n_chunks - 2); c < n_chunks && rc == GPP_OK; c++) rc = finish(c);
+    // nothing of this call may still be running when the streams go away
     cudaStreamSynchronize(copy_stream);
     if(overlap_blocks)
-        for(int i = 0; i < 2; i++) {
-            cudaStreamSynchronize(compute[i]);
-            cudaStreamDestroy(compute[i]);
-        }
-    for(int c = 0; c < n_chunks; c++) { cudaEventDestroy(produced[c]); cudaEventDestroy(copied[c]); }
-    cudaStreamDestroy(copy_stream);
+        for(int i = 0; i < 2; i++) cudaStreamSynchronize(compute[i]);
     if(rc == GPP_OK) {
         cudaError_t err = cudaGetLastError();
         if(err != cudaSuccess) rc = fail(GPP_ERR_CUDA, "CUDA error %s: %s", cudaGetErrorName(err), cudaGetErrorString(err));
@@ -1533,6 +1542,10 @@ int pipelined_download(const std::vector<size_t>& bounds, const std::function<in
     return rc;
 }
 }  // namespace gpp
+
+int oi_device_range(const gpp_points* cbp, int first, int count, const float* d_background, const float* d_bvariance, const gpp_oi_obs* obs,
+                    const gpp_structure* structure, int max_points, int allow_extrapolation, float* d_analysis, float* d_analysis_variance,
+                    void* d_workspace, size_t workspace_bytes, void* stream_, int kcap_given);
 
 namespace {
 // Row blocks of the grid go through upload, analysis and download as a pipeline: block c's rows of the background (and
@@ -1544,12 +1557,21 @@ int analyse_pipelined(const gpp_points* bpoints, int nB, int nx, int n_chunks, c
     const int n_rows = nB / nx;
     std::vector<size_t> bounds(n_chunks + 1);
     for(int c = 0; c <= n_chunks; c++) bounds[c] = (size_t) ((long long) n_rows * c / n_chunks) * nx;
+    // unlimited max_points: one bound on the observations per point for the whole field, so that every block takes the same kernel
+    int kcap = 0;
+    if(max_points == 0 && obs->n_valid > FAST_K) {
+        gpp_points* bp = const_cast<gpp_points*>(bpoints);
+        GPP_TRY(bp->ensure_on_device());
+        int hmax = 0;
+        GPP_TRY(count_max_candidates(bp, 0, nB, nullptr, obs->view(), structure->term[0].loc_dist, 0, &hmax));
+        kcap = std::max(1, std::min(obs->n_valid, hmax));
+    }
     return pipelined_download(bounds, [&](int c, cudaStream_t stream) {
         const size_t first = bounds[c], count = bounds[c + 1] - bounds[c];
         GPP_CUDA(cudaMemcpyAsync(d_bg + first, background + first, sizeof(float) * count, cudaMemcpyHostToDevice, stream));
         if(bvariance) GPP_CUDA(cudaMemcpyAsync(d_bvar + first, bvariance + first, sizeof(float) * count, cudaMemcpyHostToDevice, stream));
-        return gpp_optimal_interpolation_device(bpoints, (int) first, (int) count, d_bg, bvariance ? d_bvar : nullptr, obs, structure, max_points,
-                                                allow_extrapolation, d_out, d_var, stream);
+        return oi_device_range(bpoints, (int) first, (int) count, d_bg, bvariance ? d_bvar : nullptr, obs, structure, max_points,
+                               allow_extrapolation, d_out, d_var, nullptr, 0, stream, kcap);
     }, d_out, analysis, true);
 }
 }  // namespace
@@ -1642,6 +1664,18 @@ int gpp_optimal_interpolation_device_ws(const gpp_points* cbp, int first, int co
                                         const float* d_bvariance, const gpp_oi_obs* obs, const gpp_structure* structure,
                                         int max_points, int allow_extrapolation, float* d_analysis, float* d_analysis_variance,
                                         void* d_workspace, size_t workspace_bytes, void* stream_) {
+    return oi_device_range(cbp, first, count, d_background, d_bvariance, obs, structure, max_points, allow_extrapolation, d_analysis,
+                           d_analysis_variance, d_workspace, workspace_bytes, stream_, 0);
+}
+
+}  // extern "C"
+
+// kcap_given > 0: the bound on the observations per point has been established for the WHOLE field by the caller (the
+// pipelined host path analyses a field block by block: with max_points == 0 every block would otherwise count its own
+// largest neighbourhood and could take a different kernel than its neighbours).
+int oi_device_range(const gpp_points* cbp, int first, int count, const float* d_background, const float* d_bvariance, const gpp_oi_obs* obs,
+                    const gpp_structure* structure, int max_points, int allow_extrapolation, float* d_analysis, float* d_analysis_variance,
+                    void* d_workspace, size_t workspace_bytes, void* stream_, int kcap_given) {
     cudaStream_t stream = (cudaStream_t) stream_;
     if(max_points < 0) return fail(GPP_ERR_INVALID_ARGUMENT, "max_points must be >= 0");   // oi.cpp:152
     if(!cbp || !obs) return fail(GPP_ERR_INVALID_ARGUMENT, "points and observation state must not be NULL");
@@ -1680,7 +1714,8 @@ int gpp_optimal_interpolation_device_ws(const gpp_points* cbp, int first, int co
     P.loc_d = 0.0;
 
     int kcap = max_points > 0 ? std::min(max_points, obs->n_valid) : obs->n_valid;
-    if(max_points == 0 && kcap > FAST_K) {
+    if(kcap_given > 0) kcap = std::min(kcap, kcap_given);
+    else if(max_points == 0 && kcap > FAST_K) {
         // unlimited: bound k by the largest neighbourhood actually present
         int hmax = 0;
         GPP_TRY(count_max_candidates(bp, first, count, d_background, P.obs, P.R, stream, &hmax));
@@ -1748,6 +1783,8 @@ int gpp_optimal_interpolation_device_ws(const gpp_points* cbp, int first, int co
     }
     return launch_general(P, kcap, count, stream);
 }
+
+extern "C" {
 
 // ---- spatially varying structure functions (structure.cpp:168-184 and the sibling constructors) ------------
 int gpp_structure_field_create(const gpp_points* grid, const float* h, const float* v, const float* w, gpp_structure_field** out) {

@@ -185,6 +185,71 @@ __global__ void __launch_bounds__(128) knn_kernel(const float* __restrict__ qx, 
     for(int i = 0; i < k; i++) out[(size_t) q * k + i] = i < K ? bi[i] : -1;
 }
 
+// The same search for any k: the sorted (d2, index) list of a query lives in global memory (bd scratch, the output row itself
+// holds the indices) instead of registers. Used above KNN_MAX neighbours, where insertion cost no longer matters next to the
+// number of cells a query has to visit.
+__global__ void __launch_bounds__(128) knn_any_kernel(const float* __restrict__ qx, const float* __restrict__ qy, const float* __restrict__ qz,
+                                                      int nq, CellGeom g, const int* __restrict__ cell_start, const int* __restrict__ order,
+                                                      const float* __restrict__ sx, const float* __restrict__ sy, const float* __restrict__ sz,
+                                                      int k, int include_match, double* __restrict__ scratch, int* __restrict__ out) {
+    int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if(q >= nq) return;
+    float x = qx[q], y = qy[q], z = qz[q];
+    double* bd = scratch + (size_t) q * k;
+    int* bi = out + (size_t) q * k;
+    for(int i = 0; i < k; i++) { bd[i] = INFINITY; bi[i] = -1; }
+    int have = 0;
+    int cc[3] = {cell_coord(g, 0, x), cell_coord(g, 1, y), cell_coord(g, 2, z)};
+    int maxr = max(g.n[0], max(g.n[1], g.n[2]));
+    float max_edge = fmaxf(g.edge[0], fmaxf(g.edge[1], g.edge[2]));
+    for(int r = 0; r <= maxr; r++) {
+        int b0[3], b1[3];
+        #pragma unroll
+        for(int d = 0; d < 3; d++) { b0[d] = max(0, cc[d] - r); b1[d] = min(g.n[d] - 1, cc[d] + r); }
+        for(int cz = b0[2]; cz <= b1[2]; cz++)
+            for(int cy = b0[1]; cy <= b1[1]; cy++) {
+                bool row_on_shell = abs(cz - cc[2]) == r || abs(cy - cc[1]) == r;
+                int nx = row_on_shell ? (b1[0] - b0[0] + 1) : (r == 0 ? 1 : 2);
+                for(int ix = 0; ix < nx; ix++) {
+                    int cx = row_on_shell ? b0[0] + ix : (ix == 0 ? cc[0] - r : cc[0] + r);
+                    if(cx < 0 || cx > g.n[0] - 1) continue;
+                    int id = (cz * g.n[1] + cy) * g.n[0] + cx;
+                    for(int s = cell_start[id]; s < cell_start[id + 1]; s++) {
+                        float px = sx[s], py = sy[s], pz = sz[s];
+                        if(!include_match && px == x && py == y && pz == z) continue;
+                        double d2 = dist2_double(x, y, z, px, py, pz);
+                        int idx = order[s];
+                        if(have == k && !(d2 < bd[k - 1] || (d2 == bd[k - 1] && idx < bi[k - 1]))) continue;
+                        int j = have < k ? have : k - 1;     // shift the worse entries down, insert
+                        while(j > 0 && (d2 < bd[j - 1] || (d2 == bd[j - 1] && idx < bi[j - 1]))) {
+                            bd[j] = bd[j - 1];
+                            bi[j] = bi[j - 1];
+                            j--;
+                        }
+                        bd[j] = d2;
+                        bi[j] = idx;
+                        if(have < k) have++;
+                    }
+                }
+            }
+        bool all = true;
+        #pragma unroll
+        for(int d = 0; d < 3; d++) if(b0[d] > 0 || b1[d] < g.n[d] - 1) all = false;
+        if(all) break;
+        if(have == k) {
+            float bound = INFINITY;
+            float qc[3] = {x, y, z};
+            #pragma unroll
+            for(int d = 0; d < 3; d++) {
+                if(b0[d] > 0) bound = fminf(bound, qc[d] - (g.lo[d] + b0[d] * g.edge[d]));
+                if(b1[d] < g.n[d] - 1) bound = fminf(bound, (g.lo[d] + (b1[d] + 1) * g.edge[d]) - qc[d]);
+            }
+            bound -= 1e-3f * max_edge;
+            if(bound > 0.f && bd[k - 1] < (double) bound * (double) bound) break;
+        }
+    }
+}
+
 // Radius query, one thread per query. KDTree::get_neighbours kdtree.cpp:39-62 with within_radius :247-260:
 // STRICTLY inside the box [q-r, q+r]^3 (Boost within()), straight distance <= r, > 0 unless include_match.
 // Pass 1 (out_index == NULL) counts; pass 2 stores up to `capacity` indices and sorts them ascending.
@@ -344,9 +409,16 @@ int run_knn(gpp_points* p, const float* qlats, const float* qlons, int nq, int k
         if(k == 1)
             GPP_LAUNCH(knn_kernel<1>, blocks_for(nq, 128), 128, 0, 0, dqx.ptr, dqy.ptr, dqz.ptr, nq, ix.geom, ix.cell_start.ptr,
                        ix.order.ptr, ix.sx.ptr, ix.sy.ptr, ix.sz.ptr, k, include_match, d_out.ptr);
-        else
+        else if(k <= KNN_MAX)
             GPP_LAUNCH(knn_kernel<KNN_MAX>, blocks_for(nq, 128), 128, 0, 0, dqx.ptr, dqy.ptr, dqz.ptr, nq, ix.geom,
                        ix.cell_start.ptr, ix.order.ptr, ix.sx.ptr, ix.sy.ptr, ix.sz.ptr, k, include_match, d_out.ptr);
+        else {
+            DeviceBuffer<double> scratch;
+            GPP_TRY(scratch.alloc((size_t) nq * k));
+            GPP_LAUNCH(knn_any_kernel, blocks_for(nq, 128), 128, 0, 0, dqx.ptr, dqy.ptr, dqz.ptr, nq, ix.geom, ix.cell_start.ptr, ix.order.ptr,
+                       ix.sx.ptr, ix.sy.ptr, ix.sz.ptr, k, include_match, scratch.ptr, d_out.ptr);
+            GPP_CUDA(cudaStreamSynchronize(0));   // the scratch goes out of scope
+        }
     }
     GPP_CUDA(cudaStreamSynchronize(0));
     return GPP_OK;
@@ -445,7 +517,6 @@ int gpp_points_closest_host(const gpp_points* cp, const float* qlats, const floa
                             int* out_index) {
     if(!cp) return fail(GPP_ERR_INVALID_ARGUMENT, "points must not be NULL");
     if(num < 0) return fail(GPP_ERR_INVALID_ARGUMENT, "num must be >= 0");
-    if(num > KNN_MAX) return fail(GPP_ERR_NOT_IMPLEMENTED, "get_closest_neighbours supports at most %d neighbours on the device", KNN_MAX);
     gpp_points* p = const_cast<gpp_points*>(cp);
     GPP_TRY(ensure_device());
     if(num == 0 || nq == 0) return GPP_OK;

@@ -541,3 +541,24 @@ def test_window_filters_golden(gpp, orc):
         gpp.neighbourhood_search(v, sa[:-1], 2, 0.9, 1.0, 0.05)
     with pytest.raises(ValueError):
         gpp.calc_gradient(b, v, gpp.MinMax, 0)
+
+
+def test_closest_neighbours_any_number(gpp, orc):
+    """KDTree::get_closest_neighbours (kdtree.cpp:82-103) for more neighbours than the register kernel holds (16): the general
+    kernel keeps the sorted list in global memory. Bit-equal to the oracle incl. duplicates (ties -> lowest index), more
+    neighbours than points, include_match = False; and gridpp::distance with num > 16."""
+    rng = np.random.default_rng(21)
+    for t, ctype, span in ((gpp.Cartesian, B.CARTESIAN, 50000.0), (gpp.Geodetic, B.GEODETIC, 3.0)):
+        n = 3000
+        lats, lons = (rng.uniform(0, span, n)).astype(f32), (rng.uniform(0, span, n)).astype(f32)
+        lats[100:110], lons[100:110] = lats[99], lons[99]                       # duplicates
+        ql, qo = rng.uniform(-0.1 * span, 1.1 * span, 200).astype(f32), rng.uniform(-0.1 * span, 1.1 * span, 200).astype(f32)
+        ql[:50], qo[:50] = lats[:50], lons[:50]                                 # queries on top of points
+        p = gpp.Points(lats, lons, type=t)
+        for num, match in ((17, True), (40, True), (40, False), (333, True)):
+            assert_bit_exact(p._set.closest(ql, qo, num, match), orc.points_closest(lats, lons, ctype, ql, qo, num, match), "closest %d" % num)
+        small = gpp.Points(lats[:25], lons[:25], type=t)
+        got = small._set.closest(ql[:20], qo[:20], 60, True)
+        assert got.shape == (20, 60) and (got[:, :25] >= 0).all() and (got[:, 25:] == -1).all()
+        assert len(small.get_closest_neighbours(float(ql[0]), float(qo[0]), 60)) == 25
+        assert_bit_exact(gpp.distance(p, gpp.Points(ql, qo, type=t), 30), orc.distance((lats, lons), (ql, qo), 30, ctype), "distance num=30")
