@@ -87,10 +87,6 @@ size_t em_layout(EmParams& P, bool with_ens) {
     return o;
 }
 
-__device__ __forceinline__ double shfl_d(double v, int src) {
-    return __hiloint2double(__shfl_sync(0xffffffffu, __double2hiint(v), src), __shfl_sync(0xffffffffu, __double2loint(v), src));
-}
-
 // candidates not cut to max_points keep the order of the radius query (ascending original index); a cut leaves them best first
 __device__ __forceinline__ void order_by_index(unsigned long long* key, int* pos, int k, int lane) {
     unsigned long long kk[EM_NSLOT - 1];
@@ -112,61 +108,6 @@ __device__ __forceinline__ void order_by_index(unsigned long long* key, int* pos
     for(int t = 0; t < EM_NSLOT - 1; t++)
         if(lane + 32 * t < k) { key[rr[t]] = kk[t]; pos[rr[t]] = pp[t]; }
     __syncwarp();
-}
-
-// Solves M x = rhs for the k x k matrix in S.M (row-major, leading dimension ld, rhs in column k) by Gaussian elimination
-// with partial pivoting; x ends up in S.x. Returns false when a pivot is zero or not finite.
-__device__ __forceinline__ bool solve_in_place(double* M, double* x, int k, int ld, int lane) {
-    constexpr int NT = (EM_KMAX + 1 + 31) / 32;
-    for(int c = 0; c < k; c++) {
-        double best = -1.0;
-        int bi = c;
-        for(int i = c + lane; i < k; i += 32) {
-            const double a = fabs(M[i * ld + c]);
-            if(a > best) { best = a; bi = i; }
-        }
-        #pragma unroll
-        for(int off = 16; off > 0; off >>= 1) {
-            const double ob = shfl_d(best, lane ^ off);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
-            if(ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-        }
-        if(!(best > 0.0) || isinf(best)) return false;
-        if(bi != c)
-            for(int j = c + lane; j <= k; j += 32) {
-                const double a = M[c * ld + j], b = M[bi * ld + j];
-                M[c * ld + j] = b;
-                M[bi * ld + j] = a;
-            }
-        __syncwarp();
-        const double piv = M[c * ld + c];
-        for(int i = c + 1 + lane; i < k; i += 32) M[i * ld + c] = M[i * ld + c] / piv;   // the multipliers
-        double prow[NT];
-        #pragma unroll
-        for(int t = 0; t < NT; t++) {
-            const int j = c + 1 + lane + 32 * t;
-            prow[t] = j <= k ? M[c * ld + j] : 0.0;
-        }
-        __syncwarp();
-        const int nt = (k - c + 31) / 32;   // column chunks still alive (columns c+1 .. k)
-        #pragma unroll 2
-        for(int i = c + 1; i < k; i++) {
-            const double f = M[i * ld + c];
-            #pragma unroll
-            for(int t = 0; t < NT; t++) {
-                const int j = c + 1 + lane + 32 * t;
-                if(t < nt && j <= k) M[i * ld + j] = fma(-f, prow[t], M[i * ld + j]);
-            }
-        }
-        __syncwarp();
-    }
-    for(int c = k - 1; c >= 0; c--) {
-        const double xc = M[c * ld + k] / M[c * ld + c];
-        if(lane == 0) x[c] = xc;
-        for(int i = lane; i < c; i += 32) M[i * ld + k] = fma(-M[i * ld + c], xc, M[i * ld + k]);
-        __syncwarp();
-    }
-    return true;
 }
 
 template <int SMODE, bool WITH_ENS>
@@ -238,10 +179,14 @@ __global__ void __launch_bounds__(64) ensi_multi_kernel(const __grid_constant__ 
                 S.M[i * ld + k] = r;
             }
             __syncwarp();
-            if(!solve_in_place(S.M, S.x, k, ld, lane)) {
+            const bool solved = k + 1 <= 32 ? ge_solve<1>(S.M, k, ld, 1, lane) : k + 1 <= 64 ? ge_solve<2>(S.M, k, ld, 1, lane)
+                                            : ge_solve<(EM_KMAX + 1 + 31) / 32>(S.M, k, ld, 1, lane);
+            if(!solved) {
                 if(lane == 0) atomicExch(P.singular, 1);
                 continue;
             }
+            __syncwarp();
+            for(int i = lane; i < k; i += 32) S.x[i] = S.M[i * ld + k];   // K' = A'^-1 r'
             __syncwarp();
             // ---- dx = bratio * K lInnov per member, the anti-extrapolation filter, analysis = background + dx (:577-613)
             const double ratio = (double) P.bratios[g];

@@ -1022,7 +1022,7 @@ __device__ __forceinline__ GeneralScratch scratch_for(unsigned char* base, size_
     unsigned char* p = base + (size_t) warp * bytes_per_warp;
     GeneralScratch s;
     s.M = reinterpret_cast<double*>(p);
-    p += sizeof(double) * (size_t) kcap * (kcap + 2);
+    p += sizeof(double) * (size_t) kcap * (kcap + 3);
     int cap = kcap + 32;
     for(int b = 0; b < 2; b++) {
         s.rho[b] = reinterpret_cast<float*>(p); p += sizeof(float) * cap;
@@ -1032,7 +1032,7 @@ __device__ __forceinline__ GeneralScratch scratch_for(unsigned char* base, size_
     return s;
 }
 size_t scratch_bytes(int kcap) {
-    size_t b = sizeof(double) * (size_t) kcap * (kcap + 2) + 2 * 3 * sizeof(float) * (size_t) (kcap + 32);
+    size_t b = sizeof(double) * (size_t) kcap * (kcap + 3) + 2 * 3 * sizeof(float) * (size_t) (kcap + 32);
     return (b + 255) / 256 * 256;
 }
 
@@ -1053,15 +1053,18 @@ __device__ int general_prune(const GeneralScratch& s, int src, int n, int k) {
 
 // smem_matrix_bytes > 0: the k x (k + 2) matrix of each warp lives in dynamic shared memory (k <= 64) instead of its
 // global scratch slab; the elimination is a chain of dependent row operations, so the memory latency is what it costs.
+template <bool IN_SMEM>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32) oi_general_kernel(const __grid_constant__ OiParams P, unsigned char* scratch,
-                                                                       size_t bytes_per_warp, int kcap, int smem_matrix_bytes) {
+                                                                       size_t bytes_per_warp, int kcap) {
     extern __shared__ __align__(16) unsigned char general_smem[];
     const unsigned lane = lane_id();
     const int warps_per_cta = blockDim.x >> 5;
     const int warp_global = blockIdx.x * warps_per_cta + (threadIdx.x >> 5);
     const int warps_total = gridDim.x * warps_per_cta;
-    GeneralScratch S = scratch_for(scratch, bytes_per_warp, warp_global, kcap);
-    if(smem_matrix_bytes > 0) S.M = reinterpret_cast<double*>(general_smem + (size_t) (threadIdx.x >> 5) * smem_matrix_bytes);
+    // IN_SMEM (k <= 64): the warp's whole scratch -- matrix and candidate buffers -- is shared memory, and the compiler sees it
+    // (shared-space loads and 32-bit addresses instead of generic ones)
+    const GeneralScratch S = IN_SMEM ? scratch_for(general_smem, bytes_per_warp, (int) (threadIdx.x >> 5), kcap)
+                                     : scratch_for(scratch, bytes_per_warp, warp_global, kcap);
     const ObsView& obs = P.obs;
 
     for(int it = warp_global; it < P.count; it += warps_total) {
@@ -1130,7 +1133,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) oi_general_kernel(const __
             continue;
         }
         // ---- assemble [P+R | d | rho], k x (k+2), row-major; lP(i,j) = corr(p_i, p_j) (oi.cpp:305-313)
-        const int ld = k + 2;
+        const int ld = (k + 2) | 1;   // odd: rows a lane apart fall into different banks
         for(int e = (int) lane; e < k * k; e += 32) {
             int i = e / k, j = e % k;
             int pi = S.pos[cur][i], pj = S.pos[cur][j];
@@ -1161,8 +1164,14 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) oi_general_kernel(const __
             dmin = fmin(dmin, shfl_double(dmin, lane ^ off));
         }
         __syncwarp();
-        // ---- Gauss-Jordan with partial pivoting
+        // ---- [A^-1 d | A^-1 rho]: Gaussian elimination with partial pivoting and two right-hand sides (oi.cuh ge_solve) for up to
+        // 128 observations; beyond that (no register-resident pivot row) Gauss-Jordan, one row operation at a time
         bool singular = false;
+        if(k + 2 <= 32) singular = !ge_solve<1>(S.M, k, ld, 2, (int) lane);          // (the pivot row's register chunks: 32 columns each)
+        else if(k + 2 <= 64) singular = !ge_solve<2>(S.M, k, ld, 2, (int) lane);
+        else if(k + 2 <= 96) singular = !ge_solve<3>(S.M, k, ld, 2, (int) lane);
+        else if(k <= 128) singular = !ge_solve<(128 + 2 + 31) / 32>(S.M, k, ld, 2, (int) lane);
+        else
         for(int c = 0; c < k; c++) {
             double best = -1.0;
             int brow = c;
@@ -1584,12 +1593,11 @@ int launch_general(const OiParams& P, int kcap, int count, cudaStream_t stream) 
     // k <= 64: the matrix goes to shared memory, 2 warps per CTA (34 KB each at k = 64)
     const bool in_smem = kcap <= 64;
     const int warps_per_cta = in_smem ? 2 : WARPS_PER_CTA;
-    const int matrix_bytes = in_smem ? (int) ((sizeof(double) * (size_t) kcap * (kcap + 2) + 15) / 16 * 16) : 0;
-    const size_t smem = (size_t) matrix_bytes * warps_per_cta;
+    const size_t smem = in_smem ? per_warp * warps_per_cta : 0;
     int per_sm = 2;
     if(in_smem) {
-        GPP_CUDA(cudaFuncSetAttribute(oi_general_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        GPP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, oi_general_kernel, warps_per_cta * 32, smem));
+        GPP_CUDA(cudaFuncSetAttribute(oi_general_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        GPP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, oi_general_kernel<true>, warps_per_cta * 32, smem));
         per_sm = std::max(per_sm, 1);
     }
     long long warps = (long long) sms * per_sm * warps_per_cta;
@@ -1600,11 +1608,14 @@ int launch_general(const OiParams& P, int kcap, int count, cudaStream_t stream) 
     unsigned grid = (unsigned) std::min<long long>(warps / warps_per_cta, ((long long) count + warps_per_cta - 1) / warps_per_cta);
     grid = std::max(grid, 1u);
     unsigned char* scratch = nullptr;
-    GPP_CUDA(cudaMallocAsync((void**) &scratch, (size_t) grid * warps_per_cta * per_warp, stream));
-    oi_general_kernel<<<grid, warps_per_cta * 32, smem, stream>>>(P, scratch, per_warp, kcap, matrix_bytes);
+    if(in_smem) oi_general_kernel<true><<<grid, warps_per_cta * 32, smem, stream>>>(P, nullptr, per_warp, kcap);
+    else {
+        GPP_CUDA(cudaMallocAsync((void**) &scratch, (size_t) grid * warps_per_cta * per_warp, stream));
+        oi_general_kernel<false><<<grid, warps_per_cta * 32, 0, stream>>>(P, scratch, per_warp, kcap);
+    }
     g_launches.fetch_add(1, std::memory_order_relaxed);
     cudaError_t err = cudaGetLastError();
-    cudaFreeAsync(scratch, stream);
+    if(scratch) cudaFreeAsync(scratch, stream);
     if(err != cudaSuccess) return fail(GPP_ERR_CUDA, "CUDA error %s launching oi_general_kernel: %s", cudaGetErrorName(err), cudaGetErrorString(err));
     return GPP_OK;
 }
@@ -1952,7 +1963,9 @@ int gpp_optimal_interpolation_host(const gpp_points* bpoints, const float* backg
     const int nx = bpoints->shape_nx;
     const int n_rows = nx > 0 ? nB / nx : 0;
     static const int want_chunks = [] { const char* e = getenv("GPP_OI_CHUNKS"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 4; }();
-    const int n_chunks = (nx > 0 && nB % nx == 0 && nB >= (1 << 21)) ? std::min(want_chunks, n_rows) : 1;
+    // fields of at least this many points are pipelined by row blocks (GPP_OI_PIPELINE_MIN overrides it for experiments)
+    static const int pipeline_min = [] { const char* e = getenv("GPP_OI_PIPELINE_MIN"); const int v = e ? atoi(e) : 0; return v > 0 ? v : (1 << 21); }();
+    const int n_chunks = (nx > 0 && nB % nx == 0 && nB >= pipeline_min) ? std::min(want_chunks, n_rows) : 1;
     int rc = n_chunks > 1 ? d_bg.alloc(nB) : d_bg.upload(background, nB);
     if(rc == GPP_OK && bvariance) rc = n_chunks > 1 ? d_bvar.alloc(nB) : d_bvar.upload(bvariance, nB);
     if(rc == GPP_OK) rc = d_out.alloc(nB);

@@ -142,6 +142,75 @@ __device__ __forceinline__ void seq_mean_std(const float* v, int n, float* mean_
     *std_out = __fsqrt_rn(var);
 }
 
+
+__device__ __forceinline__ double shfl_f64(double v, int src) {
+    return __hiloint2double(__shfl_sync(0xffffffffu, __double2hiint(v), src), __shfl_sync(0xffffffffu, __double2loint(v), src));
+}
+
+// Solves M X = B in place for one warp: M is k x k, row-major with leading dimension ld, in shared or global memory; the nrhs
+// right-hand sides are columns k .. k + nrhs - 1 of the same rows and hold X on return. Gaussian elimination with partial
+// pivoting (the largest |entry| of the column, lowest row on ties): lanes own columns, the pivot row is held in registers, the
+// multipliers of a column are formed by all lanes at once and the rows below the pivot are then updated without any
+// synchronisation between them; back substitution per right-hand side. NT * 32 >= k + nrhs. Returns false when a pivot is
+// zero or not finite (the reference's inv() throws).
+template <int NT>
+__device__ __forceinline__ bool ge_solve(double* M, int k, int ld, int nrhs, int lane) {
+    const int last = k + nrhs - 1;                     // last column in use
+    for(int c = 0; c < k; c++) {
+        double best = -1.0;
+        int bi = c;
+        for(int i = c + lane; i < k; i += 32) {
+            const double a = fabs(M[(size_t) i * ld + c]);
+            if(a > best) { best = a; bi = i; }
+        }
+        #pragma unroll
+        for(int off = 16; off > 0; off >>= 1) {
+            const double ob = shfl_f64(best, lane ^ off);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+            if(ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        if(!(best > 0.0) || isinf(best)) return false;
+        if(bi != c)
+            for(int j = c + lane; j <= last; j += 32) {
+                const double a = M[(size_t) c * ld + j], b = M[(size_t) bi * ld + j];
+                M[(size_t) c * ld + j] = b;
+                M[(size_t) bi * ld + j] = a;
+            }
+        __syncwarp();
+        const double piv = M[(size_t) c * ld + c];
+        for(int i = c + 1 + lane; i < k; i += 32) M[(size_t) i * ld + c] = M[(size_t) i * ld + c] / piv;   // the multipliers
+        double prow[NT];
+        #pragma unroll
+        for(int t = 0; t < NT; t++) {
+            const int j = c + 1 + lane + 32 * t;
+            prow[t] = j <= last ? M[(size_t) c * ld + j] : 0.0;
+        }
+        __syncwarp();
+        const int nt = (last - c + 31) / 32;           // column chunks still alive (columns c + 1 .. last)
+        #pragma unroll 2
+        for(int i = c + 1; i < k; i++) {
+            const double f = M[(size_t) i * ld + c];
+            #pragma unroll
+            for(int t = 0; t < NT; t++) {
+                const int j = c + 1 + lane + 32 * t;
+                if(t < nt && j <= last) M[(size_t) i * ld + j] = fma(-f, prow[t], M[(size_t) i * ld + j]);
+            }
+        }
+        __syncwarp();
+    }
+    for(int c = k - 1; c >= 0; c--) {
+        const double d = M[(size_t) c * ld + c];
+        for(int r = 0; r < nrhs; r++) {
+            const double xc = M[(size_t) c * ld + k + r] / d;
+            __syncwarp();
+            if(lane == 0) M[(size_t) c * ld + k + r] = xc;
+            for(int i = lane; i < c; i += 32) M[(size_t) i * ld + k + r] = fma(-M[(size_t) i * ld + c], xc, M[(size_t) i * ld + k + r]);
+        }
+        __syncwarp();
+    }
+    return true;
+}
+
 }  // namespace gpp
 
 constexpr unsigned OI_WORK_SLOTS = 4;

@@ -562,3 +562,34 @@ def test_closest_neighbours_any_number(gpp, orc):
         assert got.shape == (20, 60) and (got[:, :25] >= 0).all() and (got[:, 25:] == -1).all()
         assert len(small.get_closest_neighbours(float(ql[0]), float(qo[0]), 60)) == 25
         assert_bit_exact(gpp.distance(p, gpp.Points(ql, qo, type=t), 30), orc.distance((lats, lons), (ql, qo), 30, ctype), "distance num=30")
+
+
+def test_ensi_multi_many_members_and_limits(gpp, orc):
+    """ebe / ebesc take any number of members (loops over members, 40 here) and up to 128 observations per point; utem shares the
+    EnSI kernel's limits (32 valid members, 64 observations) and says so instead of computing something else."""
+    rng = np.random.default_rng(9)
+    nB, S, E = 500, 300, 40
+    by, bx = rng.uniform(0, 30000, nB).astype(f32), rng.uniform(0, 30000, nB).astype(f32)
+    py, px = rng.uniform(0, 30000, S).astype(f32), rng.uniform(0, 30000, S).astype(f32)
+    bg, bgc = rng.standard_normal((nB, E)).astype(f32), rng.standard_normal((nB, E)).astype(f32)
+    pbg, pbgc = rng.standard_normal((S, E)).astype(f32), rng.standard_normal((S, E)).astype(f32)
+    pobs2 = (pbg + 0.5 + 0.2 * rng.standard_normal((S, E))).astype(f32)
+    pratios, bratios = rng.uniform(0.1, 0.4, S).astype(f32), np.ones(nB, f32)
+    bp, op = gpp.Points(by, bx, type=gpp.Cartesian), gpp.Points(py, px, type=gpp.Cartesian)
+    s, so = gpp.BarnesStructure(2500), B.make_structure(B.BARNES, 2500.0)
+    sets = ((by, bx, None, None), (py, px, None, None))
+    for mp in (20, 0):   # 0: unlimited, ~60 observations in reach of a point here, up to ~100
+        got = gpp.optimal_interpolation_ensi_multi_ebe(bp, bratios, bg, bgc, op, pobs2, pratios, pbg, pbgc, s, mp)
+        want = orc.ensi_multi("ebe", sets[0], bratios, bg, bgc, sets[1], pobs2, pratios, pbg, pbgc, so, mp, B.CARTESIAN, True)
+        assert_close(got, want, 1.0, RTOL, "ebe E=40 mp=%d" % mp)
+        got = gpp.optimal_interpolation_ensi_multi_ebesc(bp, bratios, bg, op, pobs2, pratios, pbg, s, mp, False)
+        want = orc.ensi_multi("ebesc", sets[0], bratios, bg, None, sets[1], pobs2, pratios, pbg, None, so, mp, B.CARTESIAN, False)
+        assert_close(got, want, 1.0, RTOL, "ebesc E=40 mp=%d" % mp, allow_outliers=4)
+    with pytest.raises(RuntimeError, match="at most 32 valid ensemble members"):
+        gpp.optimal_interpolation_ensi_multi_utem(bp, bratios, bg, bgc, op, pobs2[:, 0], pratios, pbg, pbgc, s, 20)
+    wide = gpp.BarnesStructure(9000)   # several hundred observations in reach
+    with pytest.raises(RuntimeError, match="at most 128 observations"):
+        gpp.optimal_interpolation_ensi_multi_ebesc(bp, bratios, bg, op, pobs2, pratios, pbg, wide, 0)
+    assert gpp.staticcorr_points(bp, op, wide, 0).shape == (nB, S)
+    with pytest.raises(RuntimeError, match="at most 128"):
+        gpp.staticcorr_points(bp, op, wide, 200)
