@@ -1382,3 +1382,117 @@ def nearest(igrid, ogrid, ivalues):
     _check(_libc.gpp_nearest_host(igrid._set._handle, _fptr(ogrid._set._lats), _fptr(ogrid._set._lons), nq, _fptr(flat), nf,
                                   _fptr(out)))
     return out.reshape((nf,) + oshape) if multi else out.reshape(oshape)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Host-side helpers of the reference's public surface that involve no device work.
+def init_vec2(Y, X, value=MV):
+    """gridpp::init_vec2, util.cpp (gridpp.h:1563)"""
+    return _np.full((int(Y), int(X)), value, _np.float32)
+
+
+def init_ivec2(Y, X, value):
+    return _np.full((int(Y), int(X)), value, _np.int32)
+
+
+def init_vec3(Y, X, E, value=MV):
+    return _np.full((int(Y), int(X), int(E)), value, _np.float32)
+
+
+def init_ivec3(Y, X, E, value):
+    return _np.full((int(Y), int(X), int(E)), value, _np.int32)
+
+
+def point_in_rectangle(A, B, C, D, m):
+    """gridpp::point_in_rectangle, util.cpp:562-581: float arithmetic on the corners' lat / lon, both orientations accepted."""
+    f = _np.float32
+
+    def side(p1, p2, q):
+        lon, lat = f(f(p2.lon) - f(p1.lon)), f(f(-1) * f(f(p2.lat) - f(p1.lat)))       # vect2d, :563-568
+        c = f(f(-1) * f(f(lat * f(p1.lon)) + f(lon * f(p1.lat))))
+        return f(f(f(lat * f(q.lon)) + f(lon * f(q.lat))) + c)
+    d1, d2, d3, d4 = side(A, B, m), side(A, D, m), side(B, C, m), side(C, D, m)
+    opt1 = 0 >= d1 and 0 >= d4 and 0 <= d2 and 0 >= d3
+    opt2 = 0 <= d1 and 0 <= d4 and 0 >= d2 and 0 <= d3
+    return bool(opt1 or opt2)
+
+
+# The marshalling self-tests of the reference's SWIG module (src/api/swig.cpp:6-104, tests/test_swig.py): they pin down what
+# goes in (lists, tuples, arrays of any dtype; a wrong number of dimensions is an error; zero-length inputs of any rank are
+# accepted) and what comes out (float32 / int32 arrays). Here they run through the same converters every entry point uses.
+_SWIG_DEFAULT = -1
+
+
+def _iarray(a, ndim, name):
+    arr = _farray(a, ndim, name)       # the reference converts through its float typemap first, then truncates (swig/vector.i)
+    return arr.astype(_np.int32)
+
+
+def test_array(v):
+    return _farray(v, 1, "v")
+
+
+def test_vec_input(input):
+    total = _np.float32(0)
+    for v in _farray(input, 1, "input"):
+        total = _np.float32(total + v)
+    return float(total)
+
+
+def test_ivec_input(input):
+    return int(_iarray(input, 1, "input").sum())
+
+
+def test_vec2_input(input):
+    total = _np.float32(0)
+    for v in _farray(input, 2, "input").ravel():
+        total = _np.float32(total + v)
+    return float(total)
+
+
+def test_vec3_input(input):
+    total = _np.float32(0)
+    for v in _farray(input, 3, "input").ravel():
+        total = _np.float32(total + v)
+    return float(total)
+
+
+def test_vec_output():
+    return _np.full(3, _SWIG_DEFAULT, _np.float32)
+
+
+def test_vec2_output():
+    return _np.full((3, 3), _SWIG_DEFAULT, _np.float32)
+
+
+def test_vec3_output():
+    return _np.full((3, 3, 3), _SWIG_DEFAULT, _np.float32)
+
+
+def test_ivec_output():
+    return _np.full(3, _SWIG_DEFAULT, _np.int32)
+
+
+def test_ivec2_output():
+    return _np.full((3, 3), _SWIG_DEFAULT, _np.int32)
+
+
+def test_ivec3_output():
+    return _np.full((3, 3, 3), _SWIG_DEFAULT, _np.int32)
+
+
+def test_vec_argout():
+    return 0.0, _np.full(10, _SWIG_DEFAULT, _np.float32)
+
+
+def test_vec2_argout():
+    return 0.0, _np.full((10, 10), _SWIG_DEFAULT, _np.float32)
+
+
+def test_not_implemented_exception():
+    raise NotImplementedOnDevice("Function not yet implemented")
+
+
+for _name in [n for n in list(globals()) if n.startswith("test_")]:
+    globals()[_name].__test__ = False      # these are API functions, not tests for pytest to collect
+del _name
