@@ -593,3 +593,40 @@ def test_ensi_multi_many_members_and_limits(gpp, orc):
     assert gpp.staticcorr_points(bp, op, wide, 0).shape == (nB, S)
     with pytest.raises(RuntimeError, match="at most 128"):
         gpp.staticcorr_points(bp, op, wide, 200)
+
+
+def test_ensi_multi_pipelined_path_subsample(gpp, orc):
+    """Fields of 2^18 points or more go through the host pipeline (member scan on host threads, blocks uploaded / analysed /
+    returned on alternating streams). Every point is independent, so a sample of a 520 x 520 analysis must equal the oracle's
+    Points form on just those points; an invalid trailing member must come back untouched."""
+    rng = np.random.default_rng(13)
+    n, dx, E, S, mp = 520, 400.0, 6, 2500, 12
+    y, x = np.meshgrid(np.arange(n, dtype=f32) * dx, np.arange(n, dtype=f32) * dx, indexing="ij")
+    py, px = rng.uniform(0, n * dx, S).astype(f32), rng.uniform(0, n * dx, S).astype(f32)
+    bg = (rng.standard_normal((n, n, E)) + 2 * np.sin(y / 30000.0)[:, :, None]).astype(f32)
+    bgc = rng.standard_normal((n, n, E)).astype(f32)
+    bg[17, 300, E - 1] = np.nan                                   # the last member is invalid somewhere: left alone everywhere
+    pbg, pbgc = rng.standard_normal((S, E)).astype(f32), rng.standard_normal((S, E)).astype(f32)
+    pobs2 = (pbg + 0.6 + 0.3 * rng.standard_normal((S, E))).astype(f32)
+    pratios, bratios = rng.uniform(0.1, 0.5, S).astype(f32), rng.uniform(0.8, 1.2, (n, n)).astype(f32)
+    grid, points = gpp.Grid(y, x, type=gpp.Cartesian), gpp.Points(py, px, type=gpp.Cartesian)
+    s, so = gpp.BarnesStructure(6000), B.make_structure(B.BARNES, 6000.0)
+    pick = rng.choice(n * n, 2500, replace=False)
+    pick[:4] = [0, n - 1, n * (n - 1), n * n - 1]
+    bp = (y.ravel()[pick], x.ravel()[pick], None, None)
+    flat = lambda a: a.reshape(n * n, -1)[pick]
+    for kind in ("ebesc", "ebe"):
+        if kind == "ebesc":
+            got = gpp.optimal_interpolation_ensi_multi_ebesc(grid, bratios, bg, points, pobs2, pratios, pbg, s, mp, False)
+        else:
+            got = gpp.optimal_interpolation_ensi_multi_ebe(grid, bratios, bg, bgc, points, pobs2, pratios, pbg, pbgc, s, mp, False)
+        # the oracle sees only the sample: give it the same member validity by keeping the invalid value in the sample
+        sample_bg = flat(bg).copy()
+        sample_bg[5, E - 1] = np.nan
+        want = orc.ensi_multi(kind, bp, bratios.ravel()[pick], sample_bg, flat(bgc) if kind == "ebe" else None, (py, px, None, None), pobs2, pratios, pbg,
+                              pbgc if kind == "ebe" else None, so, mp, B.CARTESIAN, False)
+        g = flat(got).copy()
+        g[5, E - 1] = np.nan
+        assert_close(g[:, :E - 1], want[:, :E - 1], 1.0, RTOL, kind + " pipelined", allow_outliers=4)
+        assert np.array_equal(got[..., E - 1], bg[..., E - 1], equal_nan=True), kind + ": the invalid member must be untouched"
+        assert np.abs(got[..., :E - 1] - bg[..., :E - 1]).max() > 0.1
