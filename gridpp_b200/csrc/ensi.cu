@@ -287,6 +287,11 @@ __global__ void __launch_bounds__(ENSI_WARPS * 32, ENSI_MINB_FOR(EC)) ensi_kerne
     constexpr int EU = EC > 0 ? EC : ENSI_EMAX;   // trip count of the unrolled member loops
     const int Eeven = E + (E & 1), m = Eeven - 1;   // round-robin schedule over an even number of indices
     const int H = Eeven / 2;                        // rotations per round
+    __shared__ unsigned char tri[ENSI_EMAX / 2 * (ENSI_EMAX / 2 + 1) / 2];   // pair index -> (t, u >= t) of two rotations of a round
+    for(int u = 0, mm = 0; u < ENSI_EMAX / 2; u++)
+        for(int t = 0; t <= u; t++, mm++)
+            if((int) threadIdx.x == (mm & 63)) tri[mm] = (unsigned char) (t | (u << 4));
+    __syncthreads();
 
     // Blocks of ENSI_GRAB consecutive points are handed out dynamically (the cost per point varies with k and the
     // sweep count). Inside a block every point starts its Jacobi iteration from the eigenvectors of the point before
@@ -461,11 +466,57 @@ __global__ void __launch_bounds__(ENSI_WARPS * 32, ENSI_MINB_FOR(EC)) ensi_kerne
                 const int nrot = __popc(rmask);
                 if(nrot == 0) continue;
                 ENSI_COUNT(2, nrot);
-                if(rot) {
+#ifndef ENSI_NO_BLOCKS
+                const bool BLOCKS = (E & 1) == 0;   // (an odd E pairs one index with a padding index that has no row)
+#else
+                constexpr bool BLOCKS = false;
+#endif
+#ifndef ENSI_BLOCK_FRAC
+#define ENSI_BLOCK_FRAC 2
+#endif
+                const bool by_blocks = BLOCKS && ENSI_BLOCK_FRAC * nrot > H;   // skipped rotations take part as identities (c = 1, s = 0)
+                if(by_blocks) {
+                    if(lane < H) { S.pp[lane] = p | (q << 8); S.cs[lane] = make_double2(c, s); }
+                }
+                else if(rot) {
                     const int slot = __popc(rmask & ((1u << lane) - 1u));
                     S.pp[slot] = p | (q << 8); S.cs[slot] = make_double2(c, s);
                 }
                 __syncwarp();
+#ifndef ENSI_NO_BLOCKS
+                if(by_blocks) {
+                    // A round in which most index pairs are rotated: A <- J' A J one 2 x 2 block at a time. Block (t, u) of the rotations'
+                    // index pairs gets the left transform of rotation t and the right transform of rotation u in registers -- the
+                    // same operations in the same order as the row pass followed by the column pass below -- and is written once,
+                    // together with its mirror image (A stays symmetric): 4 loads and 8 stores per block for the H (H + 1) / 2
+                    // blocks with t <= u, against two loads and two stores per element in each of the two passes.
+                    for(int mm = lane; mm < H * (H + 1) / 2; mm += 32) {
+                        const int tu = tri[mm], t = tu & 15, u = tu >> 4;
+                        const int pq = S.pp[t], PQ = S.pp[u];
+                        const int p0 = pq & 255, q0 = pq >> 8, p1 = PQ & 255, q1 = PQ >> 8;
+                        const double2 rt = S.cs[t], ru = S.cs[u];
+                        const double a00 = S.A[p0 * LD + p1], a01 = S.A[p0 * LD + q1], a10 = S.A[q0 * LD + p1], a11 = S.A[q0 * LD + q1];
+                        const double b00 = rt.x * a00 - rt.y * a10, b10 = rt.y * a00 + rt.x * a10;
+                        const double b01 = rt.x * a01 - rt.y * a11, b11 = rt.y * a01 + rt.x * a11;
+                        const double r00 = ru.x * b00 - ru.y * b01, r01 = ru.y * b00 + ru.x * b01;
+                        const double r10 = ru.x * b10 - ru.y * b11, r11 = ru.y * b10 + ru.x * b11;
+                        S.A[p0 * LD + p1] = r00; S.A[p0 * LD + q1] = r01; S.A[q0 * LD + p1] = r10; S.A[q0 * LD + q1] = r11;
+                        if(t != u) { S.A[p1 * LD + p0] = r00; S.A[q1 * LD + p0] = r01; S.A[p1 * LD + q0] = r10; S.A[q1 * LD + q0] = r11; }
+                    }
+                    if(lane < E) {   // V <- V J: columns p, q, row `lane`
+                        double* vrow = S.V + lane * LD;
+                        for(int t = 0; t < H; t++) {
+                            const int pq = S.pp[t], p = pq & 255, q = pq >> 8;
+                            const double2 rot2 = S.cs[t];
+                            const double vp = vrow[p], vq = vrow[q];
+                            vrow[p] = rot2.x * vp - rot2.y * vq;
+                            vrow[q] = rot2.y * vp + rot2.x * vq;
+                        }
+                    }
+                    __syncwarp();
+                    continue;
+                }
+#endif
                 if(lane < E)   // A <- J' A: rows p, q of A, column `lane`
                     for(int t = 0; t < nrot; t++) {
                         const int pq = S.pp[t];
