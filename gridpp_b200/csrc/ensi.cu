@@ -68,7 +68,7 @@ struct EnsiParams {
 // out once (byte offsets in EnsiParams::off); the kernel only adds them to its warp's base.
 struct EnsiSmem {
     unsigned long long* key;      // [32 * ENSI_NSLOT] candidate keys
-    double* Y;                    // lY, k x E (leading dimension ld)
+    float* Y;                     // lY, k x E (leading dimension ld), the float values the reference holds (gY is a vec2)
     double* A;                    // Pinv, then its diagonalisation, E x E (aliases Y)
     double* T;                    // Pinv V of the warm start, E x E (aliases Y, behind A)
     double* V;                    // eigenvectors in columns; kept from one point to the next (warm start)
@@ -89,7 +89,7 @@ struct EnsiSmem {
         const int Ee = E + (E & 1), h = Ee / 2 + 1;
         take(O_KEY, sizeof(unsigned long long) * 32 * ENSI_NSLOT);
         // A and T reuse lY's storage: lY is consumed (Pinv, C d, the clamp's lY[e]) before they are written
-        take(O_Y, sizeof(double) * std::max((size_t) kcap * ld, (size_t) 2 * Ee * ld));
+        take(O_Y, std::max(sizeof(float) * (size_t) kcap * ld, sizeof(double) * (size_t) 2 * Ee * ld));
         take(O_V, sizeof(double) * Ee * ld);
         take(O_RINV, sizeof(double) * kcap);
         take(O_DD, sizeof(double) * kcap);
@@ -105,9 +105,9 @@ struct EnsiSmem {
     __device__ __forceinline__ void bind(unsigned char* base, const int* off, int E, int ld) {
         const int Ee = E + (E & 1);
         key = reinterpret_cast<unsigned long long*>(base + off[O_KEY]);
-        Y = reinterpret_cast<double*>(base + off[O_Y]);
-        A = Y;
-        T = Y + Ee * ld;
+        Y = reinterpret_cast<float*>(base + off[O_Y]);
+        A = reinterpret_cast<double*>(base + off[O_Y]);
+        T = A + Ee * ld;
         V = reinterpret_cast<double*>(base + off[O_V]);
         rinv = reinterpret_cast<double*>(base + off[O_RINV]);
         dd = reinterpret_cast<double*>(base + off[O_DD]);
@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(ENSI_WARPS * 32, ENSI_MINB_FOR(EC)) ensi_kerne
         __syncwarp();
         for(int idx = lane; idx < k * E; idx += 32) {
             const int i = idx / E, e = idx - i * E;
-            S.Y[i * LD + e] = (double) P.gY[(size_t) S.spos[i] * E + e];
+            S.Y[i * LD + e] = P.gY[(size_t) S.spos[i] * E + e];
         }
         __syncwarp();
         // ---- Pinv = C * lY + diag * I, C = lY' Rinv (oi_ensi.cpp:379-385), row `lane`; b = C (obs - yhat) (:428-437)
@@ -355,14 +355,14 @@ __global__ void __launch_bounds__(ENSI_WARPS * 32, ENSI_MINB_FOR(EC)) ensi_kerne
             double b = 0.0;
             if(lane < E) {
                 for(int i = 0; i < k; i++) {
-                    const double c = S.Y[i * LD + lane] * S.rinv[i];
+                    const double c = (double) S.Y[i * LD + lane] * S.rinv[i];
                     b = fma(c, S.dd[i], b);
                     #pragma unroll
                     for(int f = 0; f < EU; f++)
-                        if(EC > 0 || f < E) acc[f] = fma(c, S.Y[i * LD + f], acc[f]);
+                        if(EC > 0 || f < E) acc[f] = fma(c, (double) S.Y[i * LD + f], acc[f]);
                 }
                 S.b[lane] = b;
-                lYe = UTEM ? (double) P.gY_raw[(size_t) S.spos[lane % k] * E + lane / k] : S.Y[(lane % k) * LD + (lane / k)];
+                lYe = UTEM ? (double) P.gY_raw[(size_t) S.spos[lane % k] * E + lane / k] : (double) S.Y[(lane % k) * LD + (lane / k)];
             }
             __syncwarp();   // lY is dead from here on: A and T take its place
             const double diag = UTEM ? 1.0 : (double) (float) (E - 1);   // oi_ensi.cpp:383 with delta = 1; oi_ensi_multi.cpp:1105
