@@ -820,25 +820,48 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 2) oi_fast_kernel(const __
 // fallback for non-symmetric structure functions and larger k, two orders of magnitude slower.)
 constexpr int CHOL_K = 128;            // largest k of the Cholesky path (instantiated for 64 and 128)
 constexpr int CHOL_WARPS = 2;
+// Per-warp working set, carved from dynamic shared memory for the ACTUAL bound kcap on the observations per point (a fixed
+// KMAX = 64 layout is 23.7 KB per warp = 9 warps per SM; max_points 50 needs 14 KB = 16 warps, 40 needs 10 KB).
 template <int KMAX>
 struct CholSmem {
-    static constexpr int CHOL_PAIRS = KMAX * (KMAX + 1) / 2;
-    double A[CHOL_PAIRS];                  // packed lower triangle, row-major: (i, m <= i) at i (i + 1) / 2 + m
-    double d[KMAX], r[KMAX];               // innovations -> y -> z = A^-1 d (kept for reuse); rho -> u
-    unsigned long long key[KMAX + 32];
-    int pos[KMAX + 32];
-    int c_pos[KMAX], c_orig[KMAX];         // the selection in canonical order (ascending original index)
-    int prev_orig[KMAX];                   // the set whose z is in d
-    float sx[KMAX], sy[KMAX], sz[KMAX], selev[KMAX], slaf[KMAX], sratio[KMAX];
+    static constexpr int NSLOT = KMAX / 32 + 1;
+    double* A;                             // packed lower triangle, row-major: (i, m <= i) at i (i + 1) / 2 + m
+    double *d, *r;                         // innovations -> y -> z = A^-1 d (kept for reuse); rho -> u
+    unsigned long long* key;               // [32 NSLOT]
+    int* pos;                              // [32 NSLOT]
+    int *c_pos, *c_orig;                   // the selection in canonical order (ascending original index)
+    int* prev_orig;                        // the set whose z is in d
+    float *sx, *sy, *sz, *selev, *slaf, *sratio;
+    __host__ __device__ static size_t bytes(int kcap) {
+        size_t b = sizeof(double) * ((size_t) kcap * (kcap + 1) / 2 + 2 * (size_t) kcap);
+        b += sizeof(unsigned long long) * 32 * NSLOT;
+        b += sizeof(int) * (32 * NSLOT + 3 * (size_t) kcap);
+        b += sizeof(float) * 6 * (size_t) kcap;
+        return (b + 15) / 16 * 16;
+    }
+    __device__ __forceinline__ void bind(unsigned char* base, int kcap) {
+        A = reinterpret_cast<double*>(base);
+        d = A + kcap * (kcap + 1) / 2;
+        r = d + kcap;
+        key = reinterpret_cast<unsigned long long*>(r + kcap);
+        pos = reinterpret_cast<int*>(key + 32 * NSLOT);
+        c_pos = pos + 32 * NSLOT;
+        c_orig = c_pos + kcap;
+        prev_orig = c_orig + kcap;
+        sx = reinterpret_cast<float*>(prev_orig + kcap);
+        sy = sx + kcap; sz = sy + kcap; selev = sz + kcap; slaf = selev + kcap; sratio = slaf + kcap;
+    }
 };
 
 template <int SMODE, int KMAX>
 __global__ void __launch_bounds__(CHOL_WARPS * 32) oi_chol_kernel(const __grid_constant__ OiParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     typedef CholSmem<KMAX> Smem;
-    constexpr int CHOL_PAIRS = Smem::CHOL_PAIRS, NSLOT = KMAX / 32 + 1;
-    Smem& S = reinterpret_cast<Smem*>(smem_raw)[threadIdx.x >> 5];
-    unsigned short* lut = reinterpret_cast<unsigned short*>(smem_raw + sizeof(Smem) * CHOL_WARPS);   // pair -> (i << 8) | m
+    constexpr int NSLOT = Smem::NSLOT;
+    const int kcap = P.k, CHOL_PAIRS = kcap * (kcap + 1) / 2;
+    Smem S;
+    S.bind(smem_raw + (size_t) (threadIdx.x >> 5) * Smem::bytes(kcap), kcap);
+    unsigned short* lut = reinterpret_cast<unsigned short*>(smem_raw + Smem::bytes(kcap) * CHOL_WARPS);   // pair -> (i << 8) | m
     const int lane = (int) lane_id();
     const bool need_var = P.analysis_variance != nullptr;
     for(int p = threadIdx.x; p < CHOL_PAIRS; p += blockDim.x) {
@@ -1774,8 +1797,7 @@ int oi_device_range(const gpp_points* cbp, int first, int count, const float* d_
         const bool small = kcap <= 64;
         void (*kernel)(OiParams) = small ? (mode == 1 ? oi_chol_kernel<1, 64> : oi_chol_kernel<0, 64>)
                                          : (mode == 1 ? oi_chol_kernel<1, 128> : oi_chol_kernel<0, 128>);
-        const size_t smem = small ? sizeof(CholSmem<64>) * CHOL_WARPS + sizeof(unsigned short) * CholSmem<64>::CHOL_PAIRS
-                                  : sizeof(CholSmem<128>) * CHOL_WARPS + sizeof(unsigned short) * CholSmem<128>::CHOL_PAIRS;
+        const size_t smem = (small ? CholSmem<64>::bytes(kcap) : CholSmem<128>::bytes(kcap)) * CHOL_WARPS + sizeof(unsigned short) * ((size_t) kcap * (kcap + 1) / 2);
         int per_sm = 1;
         GPP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
         GPP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, CHOL_WARPS * 32, smem));
