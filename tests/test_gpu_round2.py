@@ -630,3 +630,50 @@ def test_ensi_multi_pipelined_path_subsample(gpp, orc):
         assert_close(g[:, :E - 1], want[:, :E - 1], 1.0, RTOL, kind + " pipelined", allow_outliers=4)
         assert np.array_equal(got[..., E - 1], bg[..., E - 1], equal_nan=True), kind + ": the invalid member must be untouched"
         assert np.abs(got[..., :E - 1] - bg[..., :E - 1]).max() > 0.1
+
+
+def test_next_rows_edge_cases(gpp, orc):
+    """Degenerate shapes of the SURVEY 8(f) rows against the oracle: a single member (the standardisation divides by
+    sqrt(E - 1) = 0 and falls back to zeros), a single observation, max_points = 1, observations that are all invalid, a point
+    with no observation in reach, a 1 x 1 field for the window filters."""
+    rng = np.random.default_rng(31)
+    nB, S = 60, 25
+    by, bx = rng.uniform(0, 10000, nB).astype(f32), rng.uniform(0, 10000, nB).astype(f32)
+    by[0], bx[0] = 90000.0, 90000.0                                            # nothing in reach: stays at the background
+    py, px = rng.uniform(0, 10000, S).astype(f32), rng.uniform(0, 10000, S).astype(f32)
+    bp, op = gpp.Points(by, bx, type=gpp.Cartesian), gpp.Points(py, px, type=gpp.Cartesian)
+    s, so = gpp.BarnesStructure(3000), B.make_structure(B.BARNES, 3000.0)
+    sets = ((by, bx, None, None), (py, px, None, None))
+    pr, br = rng.uniform(0.1, 0.5, S).astype(f32), rng.uniform(0.8, 1.2, nB).astype(f32)
+    for E in (1, 2, 5):
+        bg, bgc = rng.standard_normal((nB, E)).astype(f32), rng.standard_normal((nB, E)).astype(f32)
+        pbg, pbgc = rng.standard_normal((S, E)).astype(f32), rng.standard_normal((S, E)).astype(f32)
+        pobs2 = (pbg + 0.5).astype(f32)
+        for mp in (1, 7, 0):
+            what = "E=%d mp=%d" % (E, mp)
+            got = gpp.optimal_interpolation_ensi_multi_ebesc(bp, br, bg, op, pobs2, pr, pbg, s, mp, False)
+            want = orc.ensi_multi("ebesc", sets[0], br, bg, None, sets[1], pobs2, pr, pbg, None, so, mp, B.CARTESIAN, False)
+            assert_close(got, want, 1.0, RTOL, "ebesc " + what, allow_outliers=2)
+            assert np.array_equal(got[0], bg[0])
+            got = gpp.optimal_interpolation_ensi_multi_ebe(bp, br, bg, bgc, op, pobs2, pr, pbg, pbgc, s, mp, True)
+            want = orc.ensi_multi("ebe", sets[0], br, bg, bgc, sets[1], pobs2, pr, pbg, pbgc, so, mp, B.CARTESIAN, True)
+            assert_close(got, want, 1.0, RTOL, "ebe " + what)
+            if E > 1:
+                got = gpp.optimal_interpolation_ensi_multi_utem(bp, br, bg, bgc, op, pobs2[:, 0], pr, pbg, pbgc, s, mp, True)
+                want = orc.ensi_multi("utem", sets[0], br, bg, bgc, sets[1], pobs2[:, 0], pr, pbg, pbgc, so, mp, B.CARTESIAN, True)
+                assert_close(got, want, 1.0, RTOL, "utem " + what)
+        none_valid = np.full((S, E), np.nan, f32)
+        assert np.array_equal(gpp.optimal_interpolation_ensi_multi_ebesc(bp, br, bg, op, none_valid, pr, pbg, s, 5), bg)
+        one = gpp.Points(py[:1], px[:1], type=gpp.Cartesian)
+        got = gpp.optimal_interpolation_ensi_multi_ebesc(bp, br, bg, one, pobs2[:1], pr[:1], pbg[:1], s, 5)
+        want = orc.ensi_multi("ebesc", sets[0], br, bg, None, (py[:1], px[:1], None, None), pobs2[:1], pr[:1], pbg[:1], None, so, 5, B.CARTESIAN, True)
+        assert_close(got, want, 1.0, RTOL, "one observation, E=%d" % E)
+    assert_bit_exact(gpp.staticcorr_points(bp, op, s, 1), orc.staticcorr_points(sets[0], sets[1], so, 1, B.CARTESIAN), "staticcorr mp=1")
+    assert_bit_exact(gpp.staticcorr_points(bp, gpp.Points(py[:1], px[:1], type=gpp.Cartesian), s, 0),
+                     orc.staticcorr_points(sets[0], (py[:1], px[:1], None, None), so, 0, B.CARTESIAN), "staticcorr one knot")
+    one_cell = np.array([[2.5]], f32)
+    assert_bit_exact(gpp.neighbourhood_search(one_cell, one_cell, 3, 0.0, 1.0, 0.1), orc.neighbourhood_search(one_cell, one_cell, 3, 0.0, 1.0, 0.1), "search 1x1")
+    for gt in (gpp.MinMax, gpp.LinearRegression):
+        assert_bit_exact(gpp.calc_gradient(one_cell, one_cell, gt, 2, 0, 0.0, -3.0), orc.calc_gradient(one_cell, one_cell, int(gt), 2, 0, 0.0, -3.0), "gradient 1x1")
+    f = rng.standard_normal((5, 300)).astype(f32)
+    assert_bit_exact(gpp.neighbourhood_search(f, f, 0, -0.5, 0.5, 0.0), orc.neighbourhood_search(f, f, 0, -0.5, 0.5, 0.0), "search hw=0")
