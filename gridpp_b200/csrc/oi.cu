@@ -853,6 +853,21 @@ struct CholSmem {
     }
 };
 
+// A warp's cache of solved systems for the Cholesky path (global memory, L2-resident): the set in canonical order, z = (P+R)^-1 d
+// and the innovation extremes -- the register path's LruBlock for up to KMAX observations.
+constexpr int CHOL_LRU = 8;
+template <int KMAX>
+struct CholLru {
+    double z[CHOL_LRU][KMAX];
+    int orig[CHOL_LRU][KMAX];
+    double dmax[CHOL_LRU], dmin[CHOL_LRU];
+    unsigned sig[CHOL_LRU], stamp[CHOL_LRU];   // stamp: last use (0 = empty)
+    int k[CHOL_LRU];
+};
+
+// Points are taken 32 at a time: on whole rows of a known grid as a tile of 4 rows x 8 columns walked in serpentine order (the
+// region over which one set is selected is ~30 points across, so a compact block cuts fewer of them than a strip of 32, and
+// the cache above then sees a set again on the next row), otherwise 32 consecutive points.
 template <int SMODE, int KMAX>
 __global__ void __launch_bounds__(CHOL_WARPS * 32) oi_chol_kernel(const __grid_constant__ OiParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -876,12 +891,30 @@ __global__ void __launch_bounds__(CHOL_WARPS * 32) oi_chol_kernel(const __grid_c
     // order z = (P + R)^-1 d depends on the set alone (see oi_fast_kernel); the increment is then rho . z
     int prev_k = -1;
     double prev_dmax = 0.0, prev_dmin = 0.0;
+    CholLru<KMAX>* cache = reinterpret_cast<CholLru<KMAX>*>(P.workspace) + (blockIdx.x * CHOL_WARPS + (threadIdx.x >> 5));
+    if(lane < CHOL_LRU) cache->stamp[lane] = 0;
+    __syncwarp();
+    unsigned now = 0;
+    const int tiles_x = P.tile_nx > 0 ? (P.tile_nx + 7) / 8 : 0;
+    const int n_rows = P.tile_nx > 0 ? P.count / P.tile_nx : 0;
+    const int n_blocks = P.tile_nx > 0 ? tiles_x * ((n_rows + 3) / 4) : (P.count + 31) / 32;
     for(;;) {
-        int it0 = 0;
-        if(lane == 0) it0 = atomicAdd(P.work_counter, 32);
-        it0 = __shfl_sync(0xffffffffu, it0, 0);
-        if(it0 >= P.count) break;
-        for(int it = it0; it < min(it0 + 32, P.count); it++) {
+        int blk = 0;
+        if(lane == 0) blk = atomicAdd(P.work_counter, 1);
+        blk = __shfl_sync(0xffffffffu, blk, 0);
+        if(blk >= n_blocks) break;
+        for(int j = 0; j < 32; j++) {
+            int it;
+            if(P.tile_nx > 0) {
+                const int ty = blk / tiles_x, tx = blk - ty * tiles_x, r = j >> 3, c = (r & 1) ? 7 - (j & 7) : (j & 7);
+                const int row = 4 * ty + r, col = 8 * tx + c;
+                if(row >= n_rows || col >= P.tile_nx) continue;
+                it = row * P.tile_nx + col;
+            }
+            else {
+                it = blk * 32 + j;
+                if(it >= P.count) break;
+            }
             const int g = P.first + it;
             const float bg = P.background[g];
             int k = 0;
@@ -919,6 +952,28 @@ __global__ void __launch_bounds__(CHOL_WARPS * 32) oi_chol_kernel(const __grid_c
                 same = __all_sync(0xffffffffu, eq);
             }
             double avar = 0.0;
+            unsigned sig = 0;
+            if(!same && !need_var) {
+                // ---- the warp's cache of solved systems: one word per entry first, the member list only when that matches
+                now++;
+                unsigned h = 0;
+                for(int i = lane; i < k; i += 32) h += (unsigned) (S.c_orig[i] + 1) * 0x9E3779B1u;
+                sig = __reduce_add_sync(0xffffffffu, h);
+                unsigned m = __ballot_sync(0xffffffffu, lane < CHOL_LRU && cache->stamp[lane] != 0 && cache->sig[lane] == sig && cache->k[lane] == k);
+                while(m && !same) {
+                    const int e = __ffs(m) - 1;
+                    m &= m - 1;
+                    bool eq = true;
+                    for(int i = lane; i < k; i += 32) eq = eq && cache->orig[e][i] == S.c_orig[i];
+                    if(__all_sync(0xffffffffu, eq)) {
+                        for(int i = lane; i < k; i += 32) { S.d[i] = cache->z[e][i]; S.prev_orig[i] = S.c_orig[i]; }
+                        prev_dmax = cache->dmax[e]; prev_dmin = cache->dmin[e]; prev_k = k;
+                        if(lane == 0) cache->stamp[e] = now;
+                        __syncwarp();
+                        same = true;
+                    }
+                }
+            }
             if(!same) {
                 // ---- stage the selection
                 double dmax = -INFINITY, dmin = INFINITY;
@@ -1012,6 +1067,16 @@ __global__ void __launch_bounds__(CHOL_WARPS * 32) oi_chol_kernel(const __grid_c
                     __syncwarp();
                     if(lane == 0) S.d[j] = zj;
                     for(int i = lane; i < j; i += 32) S.d[i] = fma(-rowj[i], zj, S.d[i]);
+                    __syncwarp();
+                }
+                {   // keep the solution: the least recently used entry goes (empty ones first)
+                    const unsigned age = lane < CHOL_LRU ? (cache->stamp[lane] << 3) | (unsigned) lane : 0xffffffffu;
+                    const int victim = (int) (__reduce_min_sync(0xffffffffu, age) & 7u);
+                    for(int i = lane; i < k; i += 32) { cache->z[victim][i] = S.d[i]; cache->orig[victim][i] = S.c_orig[i]; }
+                    if(lane == 0) {
+                        cache->dmax[victim] = prev_dmax; cache->dmin[victim] = prev_dmin; cache->k[victim] = k;
+                        cache->sig[victim] = sig; cache->stamp[victim] = now;
+                    }
                     __syncwarp();
                 }
             }
@@ -1803,14 +1868,20 @@ int oi_device_range(const gpp_points* cbp, int first, int count, const float* d_
         GPP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, CHOL_WARPS * 32, smem));
         const long long want = ((long long) count + 32 * CHOL_WARPS - 1) / (32 * CHOL_WARPS);
         const unsigned grid = (unsigned) std::max<long long>(1, std::min<long long>(want, (long long) sms * std::max(per_sm, 1)));
-        int* counter = nullptr;
-        GPP_CUDA(cudaMallocAsync((void**) &counter, 256, stream));
-        GPP_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), stream));
+        // whole rows of a known grid -> 4 x 8 tiles
+        P.tile_nx = (bp->shape_nx > 0 && first % bp->shape_nx == 0 && count % bp->shape_nx == 0) ? bp->shape_nx : 0;
+        // launch scratch: the work counter, then one cache of solved systems per warp (its stamps are reset by the kernel)
+        const size_t lru_bytes = (small ? sizeof(CholLru<64>) : sizeof(CholLru<128>)) * (size_t) grid * CHOL_WARPS;
+        unsigned char* scratch = nullptr;
+        GPP_CUDA(cudaMallocAsync((void**) &scratch, 256 + lru_bytes, stream));
+        GPP_CUDA(cudaMemsetAsync(scratch, 0, sizeof(int), stream));
+        int* counter = reinterpret_cast<int*>(scratch);
         P.work_counter = counter;
+        P.workspace = scratch + 256;
         kernel<<<grid, CHOL_WARPS * 32, smem, stream>>>(P);
         g_launches.fetch_add(1, std::memory_order_relaxed);
         cudaError_t err = cudaGetLastError();
-        cudaFreeAsync(counter, stream);
+        cudaFreeAsync(scratch, stream);
         if(err != cudaSuccess) return fail(GPP_ERR_CUDA, "CUDA error %s launching oi_chol_kernel: %s", cudaGetErrorName(err), cudaGetErrorString(err));
         return GPP_OK;
     }

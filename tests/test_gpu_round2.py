@@ -677,3 +677,35 @@ def test_next_rows_edge_cases(gpp, orc):
         assert_bit_exact(gpp.calc_gradient(one_cell, one_cell, gt, 2, 0, 0.0, -3.0), orc.calc_gradient(one_cell, one_cell, int(gt), 2, 0, 0.0, -3.0), "gradient 1x1")
     f = rng.standard_normal((5, 300)).astype(f32)
     assert_bit_exact(gpp.neighbourhood_search(f, f, 0, -0.5, 0.5, 0.0), orc.neighbourhood_search(f, f, 0, -0.5, 0.5, 0.0), "search hw=0")
+
+
+def test_oi_cholesky_path_traversals(gpp, orc):
+    """30 < max_points <= 128 (and unlimited) take the Cholesky kernel: 4 x 8 tiles on whole rows of a grid, 32 consecutive points
+    otherwise, a per-warp cache of solved systems. The increment of a point is the same dot product whichever way it is
+    reached: Grid traversal == Points traversal == arbitrary ranges, bit for bit; a sample against the oracle."""
+    import torch
+    from gridpp_b200 import device as gd
+    rng = np.random.default_rng(4)
+    ny, nx, dx = 203, 301, 250.0          # neither a multiple of 4 rows nor of 8 columns
+    y, x, py, px, bg, pbg, obs, ratios = _c3_like(rng, ny, nx, dx)
+    bg[rng.uniform(size=bg.shape) < 0.002] = np.nan
+    grid, pts = gpp.Grid(y, x, type=gpp.Cartesian), gpp.Points(y.ravel(), x.ravel(), type=gpp.Cartesian)
+    points, s = gpp.Points(py, px, type=gpp.Cartesian), gpp.BarnesStructure(10000)
+    state = gd.ObservationState(points, obs, ratios, pbg, s)
+    d_bg = torch.from_numpy(bg.ravel()).cuda()
+    for mp in (50, 0):
+        whole = gd.optimal_interpolation(grid, d_bg, state, mp)
+        again = gd.optimal_interpolation(grid, d_bg, state, mp)
+        flat = gd.optimal_interpolation(pts, d_bg, state, mp)
+        parts = torch.full_like(d_bg, float("nan"))
+        cuts = [0, 301 * 7, 301 * 7 + 13, 40000, ny * nx]
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            gd.optimal_interpolation(grid, d_bg, state, mp, out=parts, first=a, count=b - a)
+        torch.cuda.synchronize()
+        assert torch.equal(whole.isnan(), torch.from_numpy(np.isnan(bg.ravel())).cuda())
+        for other, what in ((again, "second launch"), (flat, "Points traversal"), (parts, "ranges")):
+            assert torch.equal(torch.nan_to_num(whole), torch.nan_to_num(other)), "max_points %d: %s" % (mp, what)
+        pick = rng.choice(ny * nx, 1500, replace=False)
+        want = orc.optimal_interpolation((y.ravel()[pick], x.ravel()[pick], None, None), bg.ravel()[pick], (py, px, None, None), obs, ratios, pbg,
+                                         B.make_structure(B.BARNES, 10000.0), mp, B.CARTESIAN)
+        assert_close(whole.cpu().numpy()[pick], want, 1.0, RTOL, "Cholesky path, max_points %d" % mp)
