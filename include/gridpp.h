@@ -878,6 +878,56 @@ inline vec2 brute_force(const vec& flat, int ny, int nx, int ne, int halfwidth, 
     return unflatten(out, ny, nx);
 }
 }  // namespace b200
+// Host-side helpers of the public surface (util.cpp): containers of a given shape, shape checks, point_in_rectangle
+inline vec2 init_vec2(int Y, int X, float value = MV) { return vec2((size_t) Y, vec((size_t) X, value)); }
+inline ivec2 init_ivec2(int Y, int X, int value) { return ivec2((size_t) Y, ivec((size_t) X, value)); }
+inline vec3 init_vec3(int Y, int X, int E, float value = MV) { return vec3((size_t) Y, init_vec2(X, E, value)); }
+typedef std::vector<ivec2> ivec3;
+inline ivec3 init_ivec3(int Y, int X, int E, int value) { return ivec3((size_t) Y, init_ivec2(X, E, value)); }
+inline bool compatible_size(const vec2& a, const vec2& b) {   // util.cpp: same number of rows, every row the same length
+    if(a.size() != b.size()) return false;
+    for(size_t i = 0; i < a.size(); i++)
+        if(a[i].size() != b[i].size()) return false;
+    return true;
+}
+inline bool compatible_size(const vec2& a, const vec3& b) {
+    if(a.size() != b.size()) return false;
+    for(size_t i = 0; i < a.size(); i++)
+        if(a[i].size() != b[i].size()) return false;
+    return true;
+}
+inline bool compatible_size(const vec3& a, const vec3& b) {
+    if(a.size() != b.size()) return false;
+    for(size_t i = 0; i < a.size(); i++) {
+        if(a[i].size() != b[i].size()) return false;
+        for(size_t j = 0; j < a[i].size(); j++)
+            if(a[i][j].size() != b[i][j].size()) return false;
+    }
+    return true;
+}
+inline bool compatible_size(const Grid& grid, const vec2& v) {
+    const ivec shape = grid.size();
+    return (int) v.size() == shape[0] && (v.empty() || (int) v[0].size() == shape[1]);
+}
+inline bool compatible_size(const Grid& grid, const vec3& v) {
+    const ivec shape = grid.size();
+    return (int) v.size() == shape[0] && (v.empty() || (int) v[0].size() == shape[1]);
+}
+inline bool compatible_size(const Points& points, const vec& v) { return (int) v.size() == points.size(); }
+inline bool compatible_size(const Points& points, const vec2& v) { return (int) v.size() == points.size(); }
+// util.cpp:562-581: float arithmetic on the corners' lat / lon, both orientations accepted
+inline bool point_in_rectangle(const Point& A, const Point& B, const Point& C, const Point& D, const Point& m) {
+    auto side = [](const Point& p1, const Point& p2, const Point& q) {
+        const float lon = p2.lon - p1.lon, lat = -1 * (p2.lat - p1.lat);
+        const float c = -1 * (lat * p1.lon + lon * p1.lat);
+        return (lat * q.lon + lon * q.lat) + c;
+    };
+    const float D1 = side(A, B, m), D2 = side(A, D, m), D3 = side(B, C, m), D4 = side(C, D, m);
+    const bool opt1 = 0 >= D1 && 0 >= D4 && 0 <= D2 && 0 >= D3;
+    const bool opt2 = 0 <= D1 && 0 <= D4 && 0 >= D2 && 0 <= D3;
+    return opt1 || opt2;
+}
+
 // neighbourhood_search.cpp:7-113
 inline vec2 neighbourhood_search(const vec2& array, const vec2& search_array, int halfwidth, float search_target_min, float search_target_max,
                                  float search_delta, const ivec2& apply_array = ivec2()) {

@@ -106,6 +106,9 @@ static int checks() {
     EXPECT_THROW(staticcorr_points(grid.to_points(), grid.to_points(), barnes, -1), std::invalid_argument);   // corr_points.cpp:34-35
     EXPECT_THROW(neighbourhood_search(field, field, 1, 2.f, 1.f, 0.f), std::invalid_argument);   // neighbourhood_search.cpp:10-12
     EXPECT_THROW(calc_gradient(field, field, MinMax, 0), std::invalid_argument);                 // calc_gradient.cpp:9-10
+    EXPECT(init_vec2(2, 3, 1.5f) == vec2(2, vec(3, 1.5f)) && init_ivec3(1, 2, 2, -1)[0][1][1] == -1 && compatible_size(field, field));
+    EXPECT(point_in_rectangle(Point(0, 0), Point(0, 1), Point(1, 1), Point(1, 0), Point(0.5f, 0.5f)));
+    EXPECT(!point_in_rectangle(Point(0, 0), Point(0, 1), Point(1, 1), Point(1, 0), Point(1.5f, 0.5f)));
     set_omp_threads(4);
     EXPECT(get_omp_threads() == 4);
     initialize_omp();
