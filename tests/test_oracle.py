@@ -606,3 +606,64 @@ def test_ensi_oracle_against_lapack(orc):
                 got[b, e] = np.float32(ens_mean + inc)
         assert np.abs(want - bg).max() > 0.05
         assert_close(got, want, 1.0, 1e-6, "LAPACK restatement, " + name)
+
+
+def test_ensi_multi_oracle_against_lapack(orc):
+    """ebesc / ebe (oi_ensi_multi.cpp:630-859, :329-627) per point on numpy.linalg (LAPACK `inv`), to take the hand-written
+    Gauss-Jordan of both checkers out of the loop: selection and correlations from the oracle's own structure function
+    (staticcorr_points on the observations with a valid value), the dense algebra from LAPACK. 1e-6 relative."""
+    g = golden("ensi_multi")
+    tag, ctype, spec, a, runs = next(_ensi_multi_cases(g))
+    s = B.make_structure(*spec)
+    E = a["background"].shape[1]
+    ok = np.isfinite(a["pobs2"][:, 0])
+    vi = np.nonzero(ok)[0]
+    bp = (a["by"], a["bx"], a["be"], a["bf"])
+    op = tuple(a[k][vi] for k in ("py", "px", "pe", "pf"))
+    nV = vi.size
+    # observation-observation correlations, all pairs at once: structure.corr(p_i, p_j) on (x, y, z, elev, laf) rows (Cartesian)
+    P = np.stack([op[1], op[0], np.zeros(nV, f32), op[2], op[3]], axis=1)
+    Call = orc.structure_corr(s, np.repeat(P, nV, axis=0), np.tile(P, (nV, 1))).reshape(nV, nV).astype(np.float64)
+    innov = (a["pobs2"][vi] - a["pbackground"][vi]).astype(f32).astype(np.float64)
+
+    def standardise(rows):
+        out = np.zeros(rows.shape, np.float64)
+        for i, row in enumerate(rows):
+            mean = np.float32(sum((np.float32(v) for v in row), np.float32(0)) / np.float32(E))
+            d = (row - row[0]).astype(f32)
+            m1 = np.float32(sum((np.float32(v) for v in d), np.float32(0)) / np.float32(E))
+            m2 = np.float32(sum((np.float32(v * v) for v in d), np.float32(0)) / np.float32(E))
+            sd = np.float32(np.sqrt(max(np.float32(m2 - m1 * m1), np.float32(0))))
+            if sd > np.float32(0.0013):
+                out[i] = 1 / np.sqrt(E - 1.0) * (row - mean).astype(np.float64) / float(sd)
+        return out
+    Z = standardise(a["pbackground_corr"][vi]).astype(f32).astype(np.float64)       # gZ_R is a float table in the reference
+    XL = standardise(a["background_corr"])
+    for mp, extr in ((12, 0), (0, 1)):
+        rho = orc.staticcorr_points(bp, op, s, mp, ctype).astype(np.float64)       # (L, nV): the selection and its correlations
+        for kind in ("ebesc", "ebe"):
+            got = a["background"].copy()
+            for y in range(rho.shape[0]):
+                sel = np.nonzero(rho[y] > 0)[0]
+                if sel.size == 0:
+                    continue
+                A = Call[np.ix_(sel, sel)].copy()
+                r = rho[y, sel].copy()
+                if kind == "ebe":
+                    A *= Z[sel] @ Z[sel].T
+                    r *= Z[sel] @ XL[y]
+                A[np.diag_indices(sel.size)] += a["pratios"][vi][sel].astype(np.float64)
+                K = r @ np.linalg.inv(A)
+                dx = float(a["bratios"][y]) * (K @ innov[sel])
+                if not extr:
+                    mx, mn = innov[sel].max(axis=0).astype(f32), innov[sel].min(axis=0).astype(f32)
+                    # the reference's if / else-if chain: the first condition that holds wins
+                    first = (mx > 0) & (dx.astype(f32) > mx)
+                    second = ~first & (mx < 0) & (dx.astype(f32) > 0)
+                    third = ~first & ~second & (mn < 0) & (dx.astype(f32) < mn)
+                    fourth = ~first & ~second & ~third & (mn > 0) & (dx.astype(f32) < 0)
+                    inc = np.where(first, mx, np.where(second | fourth, np.float32(0), np.where(third, mn, dx.astype(f32)))).astype(f32)
+                    dx = inc.astype(np.float64)
+                got[y] = (a["background"][y].astype(np.float64) + dx).astype(f32)
+            want = a["%s_mp%d_x%d" % (kind, mp, extr)]
+            assert_close(got, want, 1.0, 1e-6, "LAPACK restatement of %s mp=%d extrapolation=%d" % (kind, mp, extr), allow_outliers=2 if not extr else 0)
