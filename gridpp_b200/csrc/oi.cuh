@@ -151,7 +151,8 @@ __device__ __forceinline__ double shfl_f64(double v, int src) {
 // right-hand sides are columns k .. k + nrhs - 1 of the same rows and hold X on return. Gaussian elimination with partial
 // pivoting (the largest |entry| of the column, lowest row on ties): lanes own columns, the pivot row is held in registers, the
 // multipliers of a column are formed by all lanes at once and the rows below the pivot are then updated without any
-// synchronisation between them; back substitution per right-hand side. NT * 32 >= k + nrhs. Returns false when a pivot is
+// synchronisation between them; back substitution with the lanes on rows (few right-hand sides) or one column per lane (many).
+// NT * 32 >= k + nrhs. Returns false when a pivot is
 // zero or not finite (the reference's inv() throws).
 template <int NT>
 __device__ __forceinline__ bool ge_solve(double* M, int k, int ld, int nrhs, int lane) {
@@ -197,6 +198,21 @@ __device__ __forceinline__ bool ge_solve(double* M, int k, int ld, int nrhs, int
             }
         }
         __syncwarp();
+    }
+    if(nrhs >= 8) {
+        // many right-hand sides: a lane takes a whole column and substitutes it back on its own -- no synchronisation, the row
+        // of U is a broadcast read and the column entries of neighbouring lanes are neighbours in memory
+        for(int r0 = 0; r0 < nrhs; r0 += 32) {
+            const int r = r0 + lane;
+            if(r < nrhs)
+                for(int c = k - 1; c >= 0; c--) {
+                    double acc = M[(size_t) c * ld + k + r];
+                    for(int j = c + 1; j < k; j++) acc = fma(-M[(size_t) c * ld + j], M[(size_t) j * ld + k + r], acc);
+                    M[(size_t) c * ld + k + r] = acc / M[(size_t) c * ld + c];
+                }
+        }
+        __syncwarp();
+        return true;
     }
     for(int c = k - 1; c >= 0; c--) {
         const double d = M[(size_t) c * ld + c];
