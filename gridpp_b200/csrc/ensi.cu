@@ -275,15 +275,18 @@ struct RegisterJacobi {
 // UTEM: gridpp::optimal_interpolation_ensi_multi_utem (oi_ensi_multi.cpp:862-1311) -- the same transform computed from the
 // standardised *_corr ensembles (Pinv = C Y_corr + I, Rinv = rho / pratios) and applied to the standardised perturbations
 // of background_corr, scaled by the spread of background and by bratios.
-template <int SMODE, int EC, bool UTEM = false>
+// PAD: the number of valid members is P.E <= EC -- the member loops unroll to EC with guards, which keeps the per-lane arrays at
+// EC entries instead of ENSI_EMAX (the fully generic EC = 0 form needs 64 + 64 registers for them and spills: 2.8x slower at E = 20)
+template <int SMODE, int EC, bool UTEM = false, bool PAD = false>
 __global__ void __launch_bounds__(ENSI_WARPS * 32, ENSI_MINB_FOR(EC)) ensi_kernel(const __grid_constant__ EnsiParams P) {
+    constexpr bool EXACT = EC > 0 && !PAD;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     EnsiSmem S;
     S.bind(smem_raw + (size_t) (threadIdx.x >> 5) * P.smem_per_warp, P.off, P.E, P.ld);
-    const int LD = EC > 0 ? (EC | 1) : P.ld;
+    const int LD = EXACT ? (EC | 1) : P.ld;
     const int lane = (int) lane_id();
     const CandBuf cb = {S.key, S.pos};
-    const int E = EC > 0 ? EC : P.E;
+    const int E = EXACT ? EC : P.E;
     constexpr int EU = EC > 0 ? EC : ENSI_EMAX;   // trip count of the unrolled member loops
     const int Eeven = E + (E & 1), m = Eeven - 1;   // round-robin schedule over an even number of indices
     const int H = Eeven / 2;                        // rotations per round
@@ -359,7 +362,7 @@ __global__ void __launch_bounds__(ENSI_WARPS * 32, ENSI_MINB_FOR(EC)) ensi_kerne
                     b = fma(c, S.dd[i], b);
                     #pragma unroll
                     for(int f = 0; f < EU; f++)
-                        if(EC > 0 || f < E) acc[f] = fma(c, (double) S.Y[i * LD + f], acc[f]);
+                        if(EXACT || f < E) acc[f] = fma(c, (double) S.Y[i * LD + f], acc[f]);
                 }
                 S.b[lane] = b;
                 lYe = UTEM ? (double) P.gY_raw[(size_t) S.spos[lane % k] * E + lane / k] : (double) S.Y[(lane % k) * LD + (lane / k)];
@@ -377,7 +380,7 @@ __global__ void __launch_bounds__(ENSI_WARPS * 32, ENSI_MINB_FOR(EC)) ensi_kerne
             if(!warm) {
                 #pragma unroll
                 for(int f = 0; f < EU; f++)
-                    if((EC > 0 || f < E) && lane < E) {
+                    if((EXACT || f < E) && lane < E) {
                         S.A[lane * LD + f] = acc[f];
                         S.V[lane * LD + f] = f == lane ? 1.0 : 0.0;
                     }
@@ -389,19 +392,19 @@ __global__ void __launch_bounds__(ENSI_WARPS * 32, ENSI_MINB_FOR(EC)) ensi_kerne
                         double t = 0.0;
                         #pragma unroll
                         for(int f = 0; f < EU; f++)
-                            if(EC > 0 || f < E) t = fma(acc[f], S.V[f * LD + j], t);
+                            if(EXACT || f < E) t = fma(acc[f], S.V[f * LD + j], t);
                         S.T[lane * LD + j] = t;
                     }
                 __syncwarp();
                 if(lane < E) {
                     #pragma unroll
                     for(int f = 0; f < EU; f++)
-                        if(EC > 0 || f < E) acc[f] = S.V[f * LD + lane];   // column `lane` of V
+                        if(EXACT || f < E) acc[f] = S.V[f * LD + lane];   // column `lane` of V
                     for(int j = 0; j < E; j++) {   // A = V' T, row `lane`
                         double t = 0.0;
                         #pragma unroll
                         for(int f = 0; f < EU; f++)
-                            if(EC > 0 || f < E) t = fma(acc[f], S.T[f * LD + j], t);
+                            if(EXACT || f < E) t = fma(acc[f], S.T[f * LD + j], t);
                         S.A[lane * LD + j] = t;
                     }
                 }
@@ -411,7 +414,7 @@ __global__ void __launch_bounds__(ENSI_WARPS * 32, ENSI_MINB_FOR(EC)) ensi_kerne
         // ---- cyclic Jacobi, parallel (round-robin) ordering: E/2 disjoint rotations per round
         bool bad = false;
 #ifdef ENSI_REGISTER_JACOBI
-        constexpr bool REGJ = EC > 0 && EC <= 20 && EC % 2 == 0;
+        constexpr bool REGJ = EXACT && EC <= 20 && EC % 2 == 0;
 #else
         constexpr bool REGJ = false;
 #endif
@@ -601,12 +604,12 @@ __global__ void __launch_bounds__(ENSI_WARPS * 32, ENSI_MINB_FOR(EC)) ensi_kerne
             float tot = 0.f;
             double vs[EU];   // row `lane` of V scaled by sqrt((E-1) / lambda)
             #pragma unroll
-            for(int f = 0; f < EU; f++) vs[f] = (EC > 0 || f < E) ? S.V[lane * LD + f] * S.sc[f] : 0.0;
+            for(int f = 0; f < EU; f++) vs[f] = (EXACT || f < E) ? S.V[lane * LD + f] * S.sc[f] : 0.0;
             for(int kk = 0; kk < E; kk++) {
                 double wke = 0.0;
                 #pragma unroll
                 for(int f = 0; f < EU; f++)
-                    if(EC > 0 || f < E) wke = fma(S.V[kk * LD + f], vs[f], wke);
+                    if(EXACT || f < E) wke = fma(S.V[kk * LD + f], vs[f], wke);
                 if(UTEM) {   // W(e, e2) = ensStd * W(e, e2) + std_ratios_lr * w(e), applied to X_corr (oi_ensi_multi.cpp:1201-1254)
                     wke = __dadd_rn(__dmul_rn((double) ensStd, wke), __dmul_rn((double) bratio, S.w[kk]));
                     tot = (float) __dadd_rn((double) tot, __dmul_rn(S.t[kk], wke));
@@ -757,13 +760,21 @@ int ensi_launch(const gpp_ensi_obs& st, gpp_points* bp, int first, int count, co
     const size_t smem = (size_t) P.smem_per_warp * ENSI_WARPS;
     const int mode = structure_mode(*structure);
     void (*kernel)(EnsiParams) = nullptr;
-    if(utem) kernel = mode == 1 ? ensi_kernel<1, 0, true> : ensi_kernel<0, 0, true>;
-    else switch(E) {   // the common ensemble sizes get their own instantiation
-        case 10: kernel = mode == 1 ? ensi_kernel<1, 10> : ensi_kernel<0, 10>; break;
-        case 20: kernel = mode == 1 ? ensi_kernel<1, 20> : ensi_kernel<0, 20>; break;
-        case 30: kernel = mode == 1 ? ensi_kernel<1, 30> : ensi_kernel<0, 30>; break;
-        default: kernel = mode == 1 ? ensi_kernel<1, 0> : ensi_kernel<0, 0>; break;
+    // the common ensemble sizes have their own instantiation; the others take the next padded size (8 / 16 / 24, else 32)
+#define ENSI_PICK(EC, PAD) (utem ? (mode == 1 ? ensi_kernel<1, EC, true, PAD> : ensi_kernel<0, EC, true, PAD>) \
+                                 : (mode == 1 ? ensi_kernel<1, EC, false, PAD> : ensi_kernel<0, EC, false, PAD>))
+    switch(E) {
+        case 10: kernel = ENSI_PICK(10, false); break;
+        case 20: kernel = ENSI_PICK(20, false); break;
+        case 30: kernel = ENSI_PICK(30, false); break;
+        default:
+            if(E <= 8) kernel = ENSI_PICK(8, true);
+            else if(E <= 16) kernel = ENSI_PICK(16, true);
+            else if(E <= 24) kernel = ENSI_PICK(24, true);
+            else kernel = ENSI_PICK(0, false);
+            break;
     }
+#undef ENSI_PICK
     GPP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     const long long want = ((long long) count + ENSI_WARPS - 1) / ENSI_WARPS;
     int per_sm = 1;   // what actually fits (registers and shared memory): one wave of resident CTAs
@@ -950,6 +961,7 @@ extern "C" int gpp_optimal_interpolation_ensi_multi_utem_host(const gpp_points* 
         return fail(GPP_ERR_INVALID_ARGUMENT, "NULL argument");
     GPP_TRY(reject_unset_scales(structure));
     GPP_TRY(ensure_device());
+    Trace trace("optimal_interpolation_ensi_multi_utem_host");
     // ---- members valid in all four ensembles (:929-953)
     DeviceBuffer<float> d_bg, d_bgc, d_br, d_out;
     DeviceBuffer<int> d_skipped;
@@ -969,9 +981,12 @@ extern "C" int gpp_optimal_interpolation_ensi_multi_utem_host(const gpp_points* 
             return fail(GPP_ERR_NOT_IMPLEMENTED, "optimal_interpolation_ensi_multi_utem supports at most %d valid ensemble members on the device", ENSI_EMAX);
         st.valid_ens[st.E++] = e;
     }
-    std::memcpy(analysis, background, sizeof(float) * nBE);
+    if(trace.on) { cudaStreamSynchronize(0); trace.lap("H2D + valid-member scan"); }
     const int E = st.E;
-    if(E == 0) return GPP_OK;
+    if(E == 0) {
+        std::memcpy(analysis, background, sizeof(float) * nBE);
+        return GPP_OK;
+    }
     // ---- the observation side (:955-994): perturbations about the mean, standardised *_corr perturbations, obs - yhat
     std::vector<char> valid(nS);
     std::vector<double> innov(nS);
@@ -1000,7 +1015,10 @@ extern "C" int gpp_optimal_interpolation_ensi_multi_utem_host(const gpp_points* 
     }
     std::vector<int> order;
     GPP_TRY(build_obs_table(opoints, valid, innov, ratio, structure->term[0].loc_dist, &st.table, &order));
-    if(st.table.n_valid == 0) return GPP_OK;
+    if(st.table.n_valid == 0) {
+        std::memcpy(analysis, background, sizeof(float) * nBE);
+        return GPP_OK;
+    }
     std::vector<float> a(order.size() * (size_t) E), b(order.size() * (size_t) E);
     for(size_t slot = 0; slot < order.size(); slot++)
         for(int e = 0; e < E; e++) {
@@ -1019,8 +1037,10 @@ extern "C" int gpp_optimal_interpolation_ensi_multi_utem_host(const gpp_points* 
     GPP_TRY(bp->ensure_on_device());
     int kcap = 0;
     GPP_TRY(ensi_kcap(st, bp, 0, nB, structure, max_points, 0, &kcap));
+    trace.lap("observation tables");
     GPP_TRY(ensi_launch(st, bp, 0, nB, d_bg.ptr, d_out.ptr, structure, kcap, allow_extrapolation, d_skipped.ptr, st.counters.ptr, 0, d_bgc.ptr,
                         d_br.ptr));
+    if(trace.on) { cudaStreamSynchronize(0); trace.lap("kernel"); }
     GPP_TRY(d_out.download(analysis, nBE));
     if(num_skipped) GPP_CUDA(cudaMemcpyAsync(num_skipped, d_skipped.ptr, sizeof(int), cudaMemcpyDeviceToHost, 0));
     GPP_CUDA(cudaStreamSynchronize(0));

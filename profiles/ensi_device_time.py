@@ -12,7 +12,7 @@ from gridpp_b200 import device as gd
 
 rows = int(sys.argv[1]) if len(sys.argv) > 1 else 2500
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
-n, dx, E, S = 2500, 200.0, 20, 5000
+n, dx, E, S = 2500, 200.0, (int(sys.argv[3]) if len(sys.argv) > 3 else 20), 5000
 rng = np.random.default_rng(1000)
 y, x = np.meshgrid(np.arange(rows, dtype=np.float32) * dx, np.arange(n, dtype=np.float32) * dx, indexing="ij")
 py, px = (rng.random(S) * n * dx).astype(np.float32), (rng.random(S) * n * dx).astype(np.float32)
@@ -37,7 +37,7 @@ ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(reps)]
 print("%s: EnSI %d x %d x %d, mp 50: %.1f ms (min %.1f) = %.2f M gridpoints/s, checksum %.6f" % (
     os.environ.get("GPP_B200_LIB", "default"), rows, n, E, sum(ms) / reps, min(ms), rows * n / min(ms) / 1e3,
     float(out.double().sum())))
-ref = "/tmp/ensi_device_time_ref_%d.pt" % rows
+ref = "/tmp/ensi_device_time_ref_%d_%d.pt" % (rows, E)
 if os.path.exists(ref):
     want = torch.load(ref)
     err = ((out.cpu() - want).abs() / want.abs().clamp(min=1.0)).max().item()
