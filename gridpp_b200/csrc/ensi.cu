@@ -965,11 +965,34 @@ extern "C" int gpp_optimal_interpolation_ensi_multi_utem_host(const gpp_points* 
     // ---- members valid in all four ensembles (:929-953)
     DeviceBuffer<float> d_bg, d_bgc, d_br, d_out;
     DeviceBuffer<int> d_skipped;
-    GPP_TRY(d_bg.upload(background, nBE));
-    GPP_TRY(d_bgc.upload(background_corr, nBE));
+    // large fields: scanned by host threads so that the uploads can be pipelined with the analysis, block by block
+    const int n_chunks = nB >= (1 << 18) ? ENSI_CHUNKS : 1;
     std::vector<int> ok(nE, 1), ok2(nE, 1);
-    GPP_TRY(gpp_ensi_valid_members_device(d_bg.ptr, nB, nE, ok.data(), nullptr));
-    GPP_TRY(gpp_ensi_valid_members_device(d_bgc.ptr, nB, nE, ok2.data(), nullptr));
+    if(n_chunks > 1) {
+        GPP_TRY(d_bg.alloc(nBE));
+        GPP_TRY(d_bgc.alloc(nBE));
+        std::vector<unsigned char> bad((size_t) nE, 0), bad2((size_t) nE, 0);
+        const int scan_threads = std::max(1, std::min(8, omp_get_num_procs()));
+        #pragma omp parallel num_threads(scan_threads)
+        {
+            std::vector<unsigned char> mine((size_t) nE, 0), mine2((size_t) nE, 0);
+            #pragma omp for schedule(static) nowait
+            for(long long p = 0; p < (long long) nB; p++) {
+                const float* row = background + (size_t) p * nE;
+                const float* row2 = background_corr + (size_t) p * nE;
+                for(int e = 0; e < nE; e++) { mine[e] |= (unsigned char) !is_valid(row[e]); mine2[e] |= (unsigned char) !is_valid(row2[e]); }
+            }
+            #pragma omp critical
+            for(int e = 0; e < nE; e++) { bad[e] |= mine[e]; bad2[e] |= mine2[e]; }
+        }
+        for(int e = 0; e < nE; e++) { ok[e] = !bad[e]; ok2[e] = !bad2[e]; }
+    }
+    else {
+        GPP_TRY(d_bg.upload(background, nBE));
+        GPP_TRY(d_bgc.upload(background_corr, nBE));
+        GPP_TRY(gpp_ensi_valid_members_device(d_bg.ptr, nB, nE, ok.data(), nullptr));
+        GPP_TRY(gpp_ensi_valid_members_device(d_bgc.ptr, nB, nE, ok2.data(), nullptr));
+    }
     gpp_ensi_obs st;
     st.nE = nE;
     st.E = 0;
@@ -1027,21 +1050,37 @@ extern "C" int gpp_optimal_interpolation_ensi_multi_utem_host(const gpp_points* 
         }
     GPP_TRY(st.gY.upload(a.data(), a.size()));
     GPP_TRY(st.gY_raw.upload(b.data(), b.size()));
-    GPP_TRY(st.counters.alloc(2));
-    GPP_CUDA(cudaMemsetAsync(st.counters.ptr, 0, sizeof(int) * 2, 0));
+    GPP_TRY(st.counters.alloc(2 * ENSI_COUNTER_SLOTS));
+    GPP_CUDA(cudaMemsetAsync(st.counters.ptr, 0, sizeof(int) * 2 * ENSI_COUNTER_SLOTS, 0));
     GPP_TRY(d_skipped.alloc(1));
     GPP_CUDA(cudaMemsetAsync(d_skipped.ptr, 0, sizeof(int), 0));
     GPP_TRY(d_br.upload(bratios, (size_t) nB));
     GPP_TRY(d_out.alloc(nBE));
-    GPP_CUDA(cudaMemcpyAsync(d_out.ptr, d_bg.ptr, sizeof(float) * nBE, cudaMemcpyDeviceToDevice, 0));
+    if(n_chunks == 1) GPP_CUDA(cudaMemcpyAsync(d_out.ptr, d_bg.ptr, sizeof(float) * nBE, cudaMemcpyDeviceToDevice, 0));
     GPP_TRY(bp->ensure_on_device());
     int kcap = 0;
     GPP_TRY(ensi_kcap(st, bp, 0, nB, structure, max_points, 0, &kcap));
     trace.lap("observation tables");
-    GPP_TRY(ensi_launch(st, bp, 0, nB, d_bg.ptr, d_out.ptr, structure, kcap, allow_extrapolation, d_skipped.ptr, st.counters.ptr, 0, d_bgc.ptr,
-                        d_br.ptr));
-    if(trace.on) { cudaStreamSynchronize(0); trace.lap("kernel"); }
-    GPP_TRY(d_out.download(analysis, nBE));
+    std::vector<size_t> bounds(n_chunks + 1);
+    for(int c = 0; c <= n_chunks; c++) bounds[c] = (size_t) ((long long) nB * c / n_chunks) * nE;
+    static_assert(ENSI_CHUNKS <= (int) ENSI_COUNTER_SLOTS, "one counter pair per block in flight");
+    auto launch = [&](int c, cudaStream_t stream) {
+        const int first = (int) (bounds[c] / nE), count = (int) ((bounds[c + 1] - bounds[c]) / nE);
+        if(n_chunks > 1) {   // this block's slices of the two ensembles come in on the stream that analyses it
+            const size_t n = bounds[c + 1] - bounds[c];
+            GPP_CUDA(cudaMemcpyAsync(d_bg.ptr + bounds[c], background + bounds[c], sizeof(float) * n, cudaMemcpyHostToDevice, stream));
+            GPP_CUDA(cudaMemcpyAsync(d_bgc.ptr + bounds[c], background_corr + bounds[c], sizeof(float) * n, cudaMemcpyHostToDevice, stream));
+            GPP_CUDA(cudaMemcpyAsync(d_out.ptr + bounds[c], d_bg.ptr + bounds[c], sizeof(float) * n, cudaMemcpyDeviceToDevice, stream));
+        }
+        return ensi_launch(st, bp, first, count, d_bg.ptr, d_out.ptr, structure, kcap, allow_extrapolation, d_skipped.ptr, st.counters.ptr + 2 * c, stream,
+                           d_bgc.ptr, d_br.ptr);
+    };
+    if(n_chunks > 1) GPP_TRY(pipelined_download(bounds, launch, d_out.ptr, analysis, true));
+    else {
+        GPP_TRY(launch(0, 0));
+        if(trace.on) { cudaStreamSynchronize(0); trace.lap("kernel"); }
+        GPP_TRY(d_out.download(analysis, nBE));
+    }
     if(num_skipped) GPP_CUDA(cudaMemcpyAsync(num_skipped, d_skipped.ptr, sizeof(int), cudaMemcpyDeviceToHost, 0));
     GPP_CUDA(cudaStreamSynchronize(0));
     return GPP_OK;

@@ -615,16 +615,19 @@ def test_ensi_multi_pipelined_path_subsample(gpp, orc):
     pick[:4] = [0, n - 1, n * (n - 1), n * n - 1]
     bp = (y.ravel()[pick], x.ravel()[pick], None, None)
     flat = lambda a: a.reshape(n * n, -1)[pick]
-    for kind in ("ebesc", "ebe"):
+    for kind in ("ebesc", "ebe", "utem"):
         if kind == "ebesc":
             got = gpp.optimal_interpolation_ensi_multi_ebesc(grid, bratios, bg, points, pobs2, pratios, pbg, s, mp, False)
-        else:
+        elif kind == "ebe":
             got = gpp.optimal_interpolation_ensi_multi_ebe(grid, bratios, bg, bgc, points, pobs2, pratios, pbg, pbgc, s, mp, False)
+        else:
+            got = gpp.optimal_interpolation_ensi_multi_utem(grid, bratios, bg, bgc, points, pobs2[:, 0], pratios, pbg, pbgc, s, mp, False)
         # the oracle sees only the sample: give it the same member validity by keeping the invalid value in the sample
         sample_bg = flat(bg).copy()
         sample_bg[5, E - 1] = np.nan
-        want = orc.ensi_multi(kind, bp, bratios.ravel()[pick], sample_bg, flat(bgc) if kind == "ebe" else None, (py, px, None, None), pobs2, pratios, pbg,
-                              pbgc if kind == "ebe" else None, so, mp, B.CARTESIAN, False)
+        corr = kind != "ebesc"
+        want = orc.ensi_multi(kind, bp, bratios.ravel()[pick], sample_bg, flat(bgc) if corr else None, (py, px, None, None),
+                              pobs2[:, 0] if kind == "utem" else pobs2, pratios, pbg, pbgc if corr else None, so, mp, B.CARTESIAN, False)
         g = flat(got).copy()
         g[5, E - 1] = np.nan
         assert_close(g[:, :E - 1], want[:, :E - 1], 1.0, RTOL, kind + " pipelined", allow_outliers=4)
